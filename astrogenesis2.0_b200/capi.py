@@ -1,0 +1,114 @@
+"""ctypes binding of include/agb200.h (libagb200.so).  No fallback: if the library is missing or no
+B200 is present, every call raises."""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import build as _build
+
+_pd = C.POINTER(C.c_double)
+_pu8 = C.POINTER(C.c_uint8)
+
+AGB_MEM_HOST, AGB_MEM_DEVICE = 0, 1
+AGB_OPT_TARGET_COUNTERS = 1
+
+EXPORTS = [
+    "agb_create", "agb_destroy", "agb_set_particles", "agb_set_particles_aos", "agb_build_tree", "agb_visual_density",
+    "agb_gas_density", "agb_forces", "agb_forces_slice", "agb_get_results", "agb_get_results_aos", "agb_get_counters",
+    "agb_set_option", "agb_get_tree_particles", "agb_get_node_count", "agb_get_nodes", "agb_get_target_counters",
+    "agb_get_phase_ms", "agb_get_stream", "agb_get_launch_count", "agb_strerror", "agb_last_error", "agb_version",
+]
+
+
+class Particles(C.Structure):
+    _fields_ = [("n", C.c_int64)] + [(k, _pd) for k in ("x", "y", "z", "vx", "vy", "vz", "mass", "U", "next_time", "mu")] + \
+        [("type", _pu8)] + [(k, _pd) for k in ("rho", "P", "T", "h", "dUdt", "ax", "ay", "az")]
+
+
+class Results(C.Structure):
+    _fields_ = [(k, _pd) for k in ("ax", "ay", "az", "dUdt", "h", "rho", "P", "T", "visualDensity")]
+
+
+class AosLayout(C.Structure):
+    _fields_ = [(k, C.c_int64) for k in ("position", "velocity", "acc", "mass", "type", "U", "next_time", "mu", "rho", "P", "T", "h", "dUdt", "visualDensity")]
+
+
+COUNTER_FIELDS = ("n_particles", "n_in_tree", "n_outliers", "n_nodes", "n_active", "max_depth", "edge_dropped", "interactions",
+                  "node_interactions", "leaf_interactions", "sph_interactions", "node_visits", "mac_exact_fallbacks",
+                  "groups", "gas_groups", "gas_orphans")
+
+
+class Counters(C.Structure):
+    _fields_ = [(k, C.c_int64) for k in COUNTER_FIELDS]
+
+
+class AgbError(RuntimeError):
+    def __init__(self, status, msg):
+        super().__init__("agb200 status %d: %s" % (status, msg))
+        self.status = status
+
+
+_lib = None
+
+
+def library_path():
+    return _build.LIB
+
+
+def load(build_if_needed=True):
+    """Load libagb200.so (building it in-tree with nvcc when stale). Raises if that is impossible."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if build_if_needed and _build.needs_build():
+        _build.build_lib()
+    if not os.path.exists(_build.LIB):
+        raise RuntimeError("libagb200.so is not built; run __graft_entry__.build() (there is no CPU fallback)")
+    lib = C.CDLL(_build.LIB)
+    vp = C.c_void_p
+    lib.agb_create.argtypes = [C.POINTER(vp), C.c_int, C.c_int]
+    lib.agb_destroy.argtypes = [vp]
+    lib.agb_set_particles.argtypes = [vp, C.POINTER(Particles), C.c_int]
+    lib.agb_set_particles_aos.argtypes = [vp, C.POINTER(vp), C.c_int64, C.POINTER(AosLayout)]
+    lib.agb_build_tree.argtypes = [vp, _pd]
+    lib.agb_visual_density.argtypes = [vp, C.c_double]
+    lib.agb_gas_density.argtypes = [vp, C.c_double]
+    lib.agb_forces.argtypes = [vp, C.c_double, C.c_double, C.c_double]
+    lib.agb_forces_slice.argtypes = [vp, C.c_double, C.c_double, C.c_double, C.c_int, C.c_int]
+    lib.agb_get_results.argtypes = [vp, C.POINTER(Results), C.c_int]
+    lib.agb_get_results_aos.argtypes = [vp, C.POINTER(vp), C.c_int64, C.POINTER(AosLayout)]
+    lib.agb_get_counters.argtypes = [vp, C.POINTER(Counters)]
+    lib.agb_set_option.argtypes = [vp, C.c_int, C.c_int64]
+    lib.agb_get_tree_particles.argtypes = [vp, C.POINTER(C.c_int32), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+    lib.agb_get_node_count.argtypes = [vp, C.POINTER(C.c_int64)]
+    lib.agb_get_nodes.argtypes = [vp, C.POINTER(C.c_int32), C.POINTER(C.c_int64), C.POINTER(C.c_int32), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)] + [_pd] * 8
+    lib.agb_get_target_counters.argtypes = [vp] + [C.POINTER(C.c_int32)] * 4
+    lib.agb_get_phase_ms.argtypes = [vp, _pd]
+    lib.agb_get_stream.argtypes = [vp, C.POINTER(vp)]
+    lib.agb_get_launch_count.argtypes = [vp, C.POINTER(C.c_int64)]
+    lib.agb_strerror.restype = C.c_char_p
+    lib.agb_strerror.argtypes = [C.c_int]
+    lib.agb_last_error.restype = C.c_char_p
+    lib.agb_last_error.argtypes = [vp]
+    lib.agb_version.restype = C.c_char_p
+    _lib = lib
+    return lib
+
+
+def check(ctx, status):
+    if status != 0:
+        lib = load()
+        msg = lib.agb_strerror(status).decode()
+        if ctx:
+            extra = lib.agb_last_error(ctx).decode()
+            if extra:
+                msg += " (" + extra + ")"
+        raise AgbError(status, msg)
+
+
+def dptr(a, ctype=C.c_double):
+    """Pointer to a numpy array's data, or NULL."""
+    if a is None:
+        return C.cast(None, C.POINTER(ctype))
+    return a.ctypes.data_as(C.POINTER(ctype))

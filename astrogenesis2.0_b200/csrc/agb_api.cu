@@ -1,0 +1,508 @@
+// agb_api.cu — the C ABI (include/agb200.h) over the device kernels: context, memory pool,
+// particle hand-over, the four Tree calls and result read-back.  Host-side only.
+#include "agb_internal.cuh"
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+int agb_walk_blocks(int sm_count);
+int agb_walk_warps_per_block();
+
+struct agb_ctx {
+    int device = 0, sm_count = 148;
+    cudaStream_t st = nullptr;
+    cudaEvent_t ev[8] = {};
+    AgbDev d;
+    AgbScalars* s = nullptr;            // device
+    AgbScalars hs;                      // host mirror (tail only is valid)
+    std::vector<void*> owned_inputs;    // device copies of caller-order inputs
+    bool bound = false, have_particles = false, built = false, dens_done = false, forces_done = false;
+    bool target_counters = false, counters_valid = false, vis_timed = false, gas_timed = false;
+    double phase_ms[5] = {0, 0, 0, 0, 0};
+    int64_t launches = 0;
+    std::string err;
+    // pinned staging for host particles
+    double* stage = nullptr; size_t stage_bytes = 0;
+    agb_counters last = {};
+};
+
+namespace {
+
+constexpr int64_t SPILL_PER_WARP = 8192;
+
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) {                                                                   \
+            c->err = std::string(#call) + ": " + cudaGetErrorString(e_);                           \
+            return AGB_ERR_CUDA;                                                                   \
+        }                                                                                          \
+    } while (0)
+
+template <class T> cudaError_t dalloc(T*& p, size_t count) { return cudaMalloc((void**)&p, std::max<size_t>(count, 1) * sizeof(T)); }
+template <class T> void dfree(T*& p) { if (p) cudaFree((void*)p); p = nullptr; }
+
+void free_pool(agb_ctx* c)
+{
+    AgbDev& d = c->d;
+    for (void* p : c->owned_inputs) cudaFree(p);
+    c->owned_inputs.clear();
+    dfree(d.ax); dfree(d.ay); dfree(d.az); dfree(d.dUdt); dfree(d.h); dfree(d.rho); dfree(d.P); dfree(d.T); dfree(d.vis);
+    for (int i = 0; i < 2; i++) { dfree(d.khi[i]); dfree(d.klo[i]); dfree(d.perm[i]); }
+    dfree(d.src_pm); dfree(d.src_gv); dfree(d.src_flag);
+    dfree(d.s_h); dfree(d.s_rho); dfree(d.s_P); dfree(d.s_U); dfree(d.s_mu); dfree(d.s_next); dfree(d.s_T); dfree(d.s_type);
+    dfree(d.lcp); dfree(d.nodebase); dfree(d.nodecnt); dfree(d.leafparent); dfree(d.group); dfree(d.leafdepth);
+    dfree(d.child); dfree(d.nfirst); dfree(d.nlast); dfree(d.nparent); dfree(d.arrived); dfree(d.ndepth);
+    dfree(d.nmark); dfree(d.ndup); dfree(d.leafmark); dfree(d.mom_pm); dfree(d.mom_gv); dfree(d.grouplist);
+    dfree(d.dist); dfree(d.blockhist); dfree(d.scanblk);
+    dfree(d.c_visits); dfree(d.c_accn); dfree(d.c_accl); dfree(d.c_sph);
+    d.cap = 0;
+}
+
+int ensure_pool(agb_ctx* c, int64_t n)
+{
+    AgbDev& d = c->d;
+    if (n <= d.cap) return AGB_OK;
+    free_pool(c);
+    const size_t cap = (size_t)n;
+    d.x = d.y = d.z = d.vx = d.vy = d.vz = d.mass = d.U = d.next = d.mu = nullptr; d.type = nullptr;
+    CK(dalloc(d.ax, cap)); CK(dalloc(d.ay, cap)); CK(dalloc(d.az, cap)); CK(dalloc(d.dUdt, cap)); CK(dalloc(d.h, cap));
+    CK(dalloc(d.rho, cap)); CK(dalloc(d.P, cap)); CK(dalloc(d.T, cap)); CK(dalloc(d.vis, cap));
+    for (int i = 0; i < 2; i++) { CK(dalloc(d.khi[i], cap)); CK(dalloc(d.klo[i], cap)); CK(dalloc(d.perm[i], cap)); }
+    CK(dalloc(d.src_pm, 2 * cap)); CK(dalloc(d.src_gv, 2 * cap)); CK(dalloc(d.src_flag, 2 * cap));
+    CK(dalloc(d.s_h, cap)); CK(dalloc(d.s_rho, cap)); CK(dalloc(d.s_P, cap)); CK(dalloc(d.s_U, cap)); CK(dalloc(d.s_mu, cap));
+    CK(dalloc(d.s_next, cap)); CK(dalloc(d.s_T, cap)); CK(dalloc(d.s_type, cap));
+    CK(dalloc(d.lcp, cap)); CK(dalloc(d.nodebase, cap)); CK(dalloc(d.nodecnt, cap)); CK(dalloc(d.leafparent, cap)); CK(dalloc(d.group, cap)); CK(dalloc(d.leafdepth, cap));
+    CK(dalloc(d.child, 8 * cap)); CK(dalloc(d.nfirst, cap)); CK(dalloc(d.nlast, cap)); CK(dalloc(d.nparent, cap)); CK(dalloc(d.arrived, cap)); CK(dalloc(d.ndepth, cap));
+    CK(dalloc(d.nmark, cap)); CK(dalloc(d.ndup, cap)); CK(dalloc(d.leafmark, cap)); CK(dalloc(d.mom_pm, cap)); CK(dalloc(d.mom_gv, cap)); CK(dalloc(d.grouplist, cap));
+    CK(dalloc(d.dist, cap));
+    CK(dalloc(d.blockhist, 256 * ((cap + 2047) / 2048 + 1)));
+    CK(dalloc(d.scanblk, (cap + 2047) / 2048 + 1));
+    d.cap = (int64_t)cap;
+    return AGB_OK;
+}
+
+int ensure_counters(agb_ctx* c)
+{
+    AgbDev& d = c->d;
+    if (d.c_visits) return AGB_OK;
+    CK(dalloc(d.c_visits, (size_t)d.cap)); CK(dalloc(d.c_accn, (size_t)d.cap)); CK(dalloc(d.c_accl, (size_t)d.cap)); CK(dalloc(d.c_sph, (size_t)d.cap));
+    return AGB_OK;
+}
+
+int fetch_scalars(agb_ctx* c)
+{
+    const size_t off = offsetof(AgbScalars, mean);
+    CK(cudaMemcpyAsync((char*)&c->hs + off, (char*)c->s + off, sizeof(AgbScalars) - off, cudaMemcpyDeviceToHost, c->st));
+    CK(cudaStreamSynchronize(c->st));
+    return AGB_OK;
+}
+
+// copy (or zero / constant fill) one caller array into an owned device array
+int put_array(agb_ctx* c, double* dst, const double* src, int64_t n, int memspace)
+{
+    if (!src) { CK(cudaMemsetAsync(dst, 0, (size_t)n * sizeof(double), c->st)); return AGB_OK; }
+    CK(cudaMemcpyAsync(dst, src, (size_t)n * sizeof(double), memspace == AGB_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, c->st));
+    return AGB_OK;
+}
+
+int own_input(agb_ctx* c, const double*& slot, const double* src, int64_t n)
+{
+    if (!src) { slot = nullptr; return AGB_OK; }
+    double* p = nullptr;
+    CK(dalloc(p, (size_t)n));
+    c->owned_inputs.push_back(p);
+    CK(cudaMemcpyAsync(p, src, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, c->st));
+    slot = p;
+    return AGB_OK;
+}
+
+} // namespace
+
+extern "C" {
+
+const char* agb_version(void) { return "agb200 0.1 (sm_100a)"; }
+
+const char* agb_strerror(int st)
+{
+    switch (st) {
+    case AGB_OK: return "ok";
+    case AGB_ERR_NO_DEVICE: return "no usable CUDA device (sm_100 required; there is no CPU fallback)";
+    case AGB_ERR_CUDA: return "CUDA error";
+    case AGB_ERR_INVALID: return "invalid argument or call order";
+    case AGB_ERR_DEPTH: return "coincident particles: octree deeper than 42 levels";
+    case AGB_ERR_UNSUPPORTED: return "parameter range not covered by the parity path";
+    case AGB_ERR_NOMEM: return "out of memory / traversal stack overflow";
+    }
+    return "unknown status";
+}
+
+const char* agb_last_error(agb_ctx* c) { return c ? c->err.c_str() : ""; }
+
+int agb_create(agb_ctx** out, int device, int compat_cores)
+{
+    if (!out) return AGB_ERR_INVALID;
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) return AGB_ERR_NO_DEVICE;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return AGB_ERR_NO_DEVICE;
+    if (prop.major != 10) return AGB_ERR_NO_DEVICE;         // the kernels are built for sm_100a only
+    if (cudaSetDevice(device) != cudaSuccess) return AGB_ERR_NO_DEVICE;
+    agb_ctx* c = new agb_ctx();
+    c->device = device;
+    c->sm_count = prop.multiProcessorCount;
+    c->d.cores = compat_cores > 0 ? compat_cores : 1;
+    if (cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking) != cudaSuccess) { delete c; return AGB_ERR_NO_DEVICE; }
+    for (auto& e : c->ev) cudaEventCreate(&e);
+    if (cudaMalloc((void**)&c->s, sizeof(AgbScalars)) != cudaSuccess) { delete c; return AGB_ERR_NOMEM; }
+    cudaMemsetAsync(c->s, 0, sizeof(AgbScalars), c->st);
+    memset(&c->hs, 0, sizeof(c->hs));
+    c->d.spill_warps = agb_walk_blocks(c->sm_count) * agb_walk_warps_per_block();
+    c->d.spill_per_warp = SPILL_PER_WARP;
+    if (cudaMalloc((void**)&c->d.spill, (size_t)c->d.spill_warps * SPILL_PER_WARP * sizeof(int2)) != cudaSuccess) { cudaFree(c->s); delete c; return AGB_ERR_NOMEM; }
+    *out = c;
+    return AGB_OK;
+}
+
+int agb_destroy(agb_ctx* c)
+{
+    if (!c) return AGB_ERR_INVALID;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->st);
+    free_pool(c);
+    cudaFree(c->d.spill);
+    cudaFree(c->s);
+    if (c->stage) cudaFreeHost(c->stage);
+    for (auto& e : c->ev) cudaEventDestroy(e);
+    cudaStreamDestroy(c->st);
+    delete c;
+    return AGB_OK;
+}
+
+int agb_set_option(agb_ctx* c, int option, int64_t value)
+{
+    if (!c) return AGB_ERR_INVALID;
+    if (option == AGB_OPT_TARGET_COUNTERS) { c->target_counters = value != 0; return AGB_OK; }
+    return AGB_ERR_INVALID;
+}
+
+int agb_set_particles(agb_ctx* c, const agb_particles* p, int memspace)
+{
+    if (!c || !p || p->n < 0 || p->n >= (1ll << 30) || (p->n > 0 && (!p->x || !p->y || !p->z || !p->mass || !p->type))) return AGB_ERR_INVALID;
+    CK(cudaSetDevice(c->device));
+    const int64_t n = p->n;
+    int rc = ensure_pool(c, n);
+    if (rc) return rc;
+    AgbDev& d = c->d;
+    d.n = n;
+    for (void* q : c->owned_inputs) cudaFree(q);
+    c->owned_inputs.clear();
+    if (memspace == AGB_MEM_DEVICE) {
+        // zero-copy: the caller's device arrays are read in place (they must stay valid until the next set_particles)
+        d.x = p->x; d.y = p->y; d.z = p->z; d.vx = p->vx; d.vy = p->vy; d.vz = p->vz; d.mass = p->mass; d.U = p->U; d.next = p->next_time; d.mu = p->mu;
+        d.type = p->type;
+        c->bound = true;
+    } else {
+        if ((rc = own_input(c, d.x, p->x, n)) || (rc = own_input(c, d.y, p->y, n)) || (rc = own_input(c, d.z, p->z, n)) ||
+            (rc = own_input(c, d.vx, p->vx, n)) || (rc = own_input(c, d.vy, p->vy, n)) || (rc = own_input(c, d.vz, p->vz, n)) ||
+            (rc = own_input(c, d.mass, p->mass, n)) || (rc = own_input(c, d.U, p->U, n)) || (rc = own_input(c, d.next, p->next_time, n)) ||
+            (rc = own_input(c, d.mu, p->mu, n))) return rc;
+        uint8_t* t = nullptr;
+        CK(dalloc(t, (size_t)n));
+        c->owned_inputs.push_back(t);
+        CK(cudaMemcpyAsync(t, p->type, (size_t)n, cudaMemcpyHostToDevice, c->st));
+        d.type = t;
+        c->bound = false;
+    }
+    if ((rc = put_array(c, d.ax, p->ax, n, memspace)) || (rc = put_array(c, d.ay, p->ay, n, memspace)) || (rc = put_array(c, d.az, p->az, n, memspace)) ||
+        (rc = put_array(c, d.dUdt, p->dUdt, n, memspace)) || (rc = put_array(c, d.h, p->h, n, memspace)) || (rc = put_array(c, d.rho, p->rho, n, memspace)) ||
+        (rc = put_array(c, d.P, p->P, n, memspace)) || (rc = put_array(c, d.T, p->T, n, memspace))) return rc;
+    CK(cudaMemsetAsync(d.vis, 0, (size_t)std::max<int64_t>(n, 1) * sizeof(double), c->st));
+    if (memspace == AGB_MEM_HOST) CK(cudaStreamSynchronize(c->st));   // caller buffers may be reused after return
+    c->have_particles = true; c->built = false; c->dens_done = false; c->forces_done = false; c->counters_valid = false;
+    return AGB_OK;
+}
+
+static inline double* aos_d(void* base, int64_t off) { return reinterpret_cast<double*>(static_cast<char*>(base) + off); }
+
+int agb_set_particles_aos(agb_ctx* c, void* const* parts, int64_t n, const agb_aos_layout* L)
+{
+    if (!c || !parts || !L || n < 0 || L->position < 0 || L->mass < 0 || L->type < 0) return AGB_ERR_INVALID;
+    // gather the array-of-structs records (the reference's Particle, 264 B each) into 21 SoA columns
+    const size_t cols = 21, need = cols * (size_t)std::max<int64_t>(n, 1) * sizeof(double) + (size_t)n;
+    if (need > c->stage_bytes) {
+        if (c->stage) cudaFreeHost(c->stage);
+        c->stage = nullptr; c->stage_bytes = 0;
+        CK(cudaMallocHost((void**)&c->stage, need));
+        c->stage_bytes = need;
+    }
+    double* col[21];
+    for (size_t k = 0; k < cols; k++) col[k] = c->stage + k * (size_t)std::max<int64_t>(n, 1);
+    uint8_t* typ = reinterpret_cast<uint8_t*>(c->stage + cols * (size_t)std::max<int64_t>(n, 1));
+    auto vec = [&](int64_t off, int64_t i, int k0) {
+        if (off < 0) { col[k0][i] = col[k0 + 1][i] = col[k0 + 2][i] = 0.0; return; }
+        const double* v = aos_d(parts[i], off); col[k0][i] = v[0]; col[k0 + 1][i] = v[1]; col[k0 + 2][i] = v[2];
+    };
+    auto sca = [&](int64_t off, int64_t i, int k, double dflt) { col[k][i] = off < 0 ? dflt : *aos_d(parts[i], off); };
+    for (int64_t i = 0; i < n; i++) {
+        if (!parts[i]) return AGB_ERR_INVALID;
+        vec(L->position, i, 0); vec(L->velocity, i, 3); vec(L->acc, i, 6);
+        sca(L->mass, i, 9, 0); sca(L->U, i, 10, 0); sca(L->next_time, i, 11, 0); sca(L->mu, i, 12, 0.58);
+        sca(L->rho, i, 13, 0); sca(L->P, i, 14, 0); sca(L->T, i, 15, 0); sca(L->h, i, 16, 0); sca(L->dUdt, i, 17, 0);
+        typ[i] = *reinterpret_cast<const uint8_t*>(static_cast<const char*>(parts[i]) + L->type);
+    }
+    agb_particles p;
+    memset(&p, 0, sizeof(p));
+    p.n = n;
+    p.x = col[0]; p.y = col[1]; p.z = col[2]; p.vx = col[3]; p.vy = col[4]; p.vz = col[5]; p.ax = col[6]; p.ay = col[7]; p.az = col[8];
+    p.mass = col[9]; p.U = col[10]; p.next_time = col[11]; p.mu = col[12]; p.rho = col[13]; p.P = col[14]; p.T = col[15]; p.h = col[16]; p.dUdt = col[17];
+    p.type = typ;
+    return agb_set_particles(c, &p, AGB_MEM_HOST);
+}
+
+int agb_build_tree(agb_ctx* c, double* root_radius)
+{
+    if (!c || !c->have_particles) return AGB_ERR_INVALID;
+    CK(cudaSetDevice(c->device));
+    AgbDev& d = c->d;
+    c->built = false; c->dens_done = false; c->forces_done = false; c->counters_valid = false;
+    if (d.n == 0) { if (root_radius) *root_radius = 0.0; memset((char*)&c->hs + offsetof(AgbScalars, mean), 0, sizeof(AgbScalars) - offsetof(AgbScalars, mean)); c->built = true; return AGB_OK; }
+    CK(cudaEventRecord(c->ev[0], c->st));
+    c->launches += agb_launch_extent(d, c->s, c->st);
+    c->launches += agb_launch_keygen(d, c->s, c->st);
+    c->launches += agb_launch_sort(d, c->s, c->st);
+    c->launches += agb_launch_links(d, c->s, c->st);
+    CK(cudaEventRecord(c->ev[1], c->st));
+    CK(cudaGetLastError());
+    int rc = fetch_scalars(c);
+    if (rc) return rc;
+    float ms = 0; cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]); c->phase_ms[0] = ms;
+    c->hs.R = 0; memcpy(&c->hs.R, &c->hs.Rbits, 8);
+    if (root_radius) *root_radius = c->hs.R;
+    if (c->hs.dup_keys > 0) { c->err = "coincident particles (shared 42-level path)"; return AGB_ERR_DEPTH; }
+    c->built = true;
+    return AGB_OK;
+}
+
+int agb_visual_density(agb_ctx* c, double radius)
+{
+    if (!c || !c->built) return AGB_ERR_INVALID;
+    CK(cudaSetDevice(c->device));
+    if (c->d.n == 0) return AGB_OK;
+    CK(cudaEventRecord(c->ev[2], c->st));
+    c->launches += agb_launch_visual(c->d, c->s, radius, c->st);
+    CK(cudaEventRecord(c->ev[3], c->st));
+    c->vis_timed = true;
+    CK(cudaGetLastError());
+    return AGB_OK;
+}
+
+int agb_gas_density(agb_ctx* c, double mass_in_h)
+{
+    if (!c || !c->built) return AGB_ERR_INVALID;
+    CK(cudaSetDevice(c->device));
+    c->dens_done = true;
+    if (c->d.n == 0) return AGB_OK;
+    CK(cudaEventRecord(c->ev[4], c->st));
+    if (c->hs.any_gas) c->launches += agb_launch_gas_density(c->d, c->s, mass_in_h, c->st);
+    CK(cudaEventRecord(c->ev[5], c->st));
+    c->gas_timed = true;
+    CK(cudaGetLastError());
+    return AGB_OK;
+}
+
+int agb_forces_slice(agb_ctx* c, double global_time, double e0, double theta, int part, int nparts)
+{
+    if (!c || !c->built || nparts < 1 || part < 0 || part >= nparts) return AGB_ERR_INVALID;
+    // For e0 <= 2.1474836e13 the reference's `abs(e)` (int abs(int), Node.cpp:302,354) can switch to the spline
+    // softening length; that branch is not reproduced (dead for every SI configuration).
+    if (!(e0 > 2.147483648e13)) { c->err = "e0 <= 2^31 * 1e4: the reference's int-abs softening branch is not covered"; return AGB_ERR_UNSUPPORTED; }
+    CK(cudaSetDevice(c->device));
+    AgbDev& d = c->d;
+    if (d.n == 0) { c->forces_done = true; return AGB_OK; }
+    if (c->target_counters) { int rc = ensure_counters(c); if (rc) return rc; }
+    const int64_t t0 = d.n * part / nparts, t1 = d.n * (part + 1) / nparts;
+    CK(cudaEventRecord(c->ev[6], c->st));
+    // gas targets need h/rho/P: if the caller skipped gas_density they are orphans (h = 0) and get no SPH, like the reference
+    c->launches += agb_launch_walk(d, c->s, global_time, e0, theta, t0, t1, c->target_counters, c->hs.any_gas != 0, c->sm_count, c->st, c->ev[0], c->ev[1]);
+    CK(cudaEventRecord(c->ev[7], c->st));
+    CK(cudaGetLastError());
+    int rc = fetch_scalars(c);
+    if (rc) return rc;
+    float ms = 0;
+    if (t1 > t0 && cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]) == cudaSuccess) c->phase_ms[3] = ms;
+    if (cudaEventElapsedTime(&ms, c->ev[6], c->ev[7]) == cudaSuccess) c->phase_ms[4] = ms;
+    if (c->vis_timed && cudaEventElapsedTime(&ms, c->ev[2], c->ev[3]) == cudaSuccess) c->phase_ms[1] = ms;
+    if (c->gas_timed && cudaEventElapsedTime(&ms, c->ev[4], c->ev[5]) == cudaSuccess) c->phase_ms[2] = ms;
+    (void)cudaGetLastError();
+    if (c->hs.walk_overflow) { c->err = "traversal stack overflow"; return AGB_ERR_NOMEM; }
+    c->forces_done = true; c->counters_valid = c->target_counters;
+    return AGB_OK;
+}
+
+int agb_forces(agb_ctx* c, double global_time, double e0, double theta) { return agb_forces_slice(c, global_time, e0, theta, 0, 1); }
+
+int agb_get_counters(agb_ctx* c, agb_counters* o)
+{
+    if (!c || !o) return AGB_ERR_INVALID;
+    const AgbScalars& h = c->hs;
+    memset(o, 0, sizeof(*o));
+    o->n_particles = c->d.n; o->n_in_tree = h.n_in_tree; o->n_outliers = h.n_outliers; o->n_nodes = h.n_nodes; o->n_active = h.n_active;
+    o->max_depth = h.max_depth; o->edge_dropped = h.edge_dropped;
+    o->node_interactions = (int64_t)h.c_node; o->leaf_interactions = (int64_t)h.c_leaf; o->interactions = (int64_t)(h.c_node + h.c_leaf);
+    o->sph_interactions = (int64_t)h.c_sph; o->node_visits = (int64_t)h.c_visits; o->mac_exact_fallbacks = (int64_t)h.c_exact;
+    o->groups = (c->d.n + 31) / 32; o->gas_groups = h.n_gas_groups; o->gas_orphans = h.n_gas_orphans;
+    return AGB_OK;
+}
+
+int agb_get_results(agb_ctx* c, const agb_results* r, int memspace)
+{
+    if (!c || !r || !c->have_particles) return AGB_ERR_INVALID;
+    CK(cudaSetDevice(c->device));
+    const size_t b = (size_t)c->d.n * sizeof(double);
+    const cudaMemcpyKind k = memspace == AGB_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+    const AgbDev& d = c->d;
+    struct { double* dst; const double* src; } cp[] = {{r->ax, d.ax}, {r->ay, d.ay}, {r->az, d.az}, {r->dUdt, d.dUdt}, {r->h, d.h},
+                                                       {r->rho, d.rho}, {r->P, d.P}, {r->T, d.T}, {r->visualDensity, d.vis}};
+    for (auto& e : cp) if (e.dst && b) CK(cudaMemcpyAsync(e.dst, e.src, b, k, c->st));
+    CK(cudaStreamSynchronize(c->st));
+    return AGB_OK;
+}
+
+int agb_get_results_aos(agb_ctx* c, void* const* parts, int64_t n, const agb_aos_layout* L)
+{
+    if (!c || !parts || !L || n != c->d.n) return AGB_ERR_INVALID;
+    const size_t nn = (size_t)std::max<int64_t>(n, 1), need = 9 * nn * sizeof(double);
+    if (need > c->stage_bytes) {
+        if (c->stage) cudaFreeHost(c->stage);
+        c->stage = nullptr; c->stage_bytes = 0;
+        CK(cudaMallocHost((void**)&c->stage, need));
+        c->stage_bytes = need;
+    }
+    double* col[9];
+    for (int k = 0; k < 9; k++) col[k] = c->stage + (size_t)k * nn;
+    agb_results r = {col[0], col[1], col[2], col[3], col[4], col[5], col[6], col[7], col[8]};
+    int rc = agb_get_results(c, &r, AGB_MEM_HOST);
+    if (rc) return rc;
+    for (int64_t i = 0; i < n; i++) {
+        if (L->acc >= 0) { double* a = aos_d(parts[i], L->acc); a[0] = col[0][i]; a[1] = col[1][i]; a[2] = col[2][i]; }
+        if (L->dUdt >= 0) *aos_d(parts[i], L->dUdt) = col[3][i];
+        if (L->h >= 0) *aos_d(parts[i], L->h) = col[4][i];
+        if (L->rho >= 0) *aos_d(parts[i], L->rho) = col[5][i];
+        if (L->P >= 0) *aos_d(parts[i], L->P) = col[6][i];
+        if (L->T >= 0) *aos_d(parts[i], L->T) = col[7][i];
+        if (L->visualDensity >= 0) *aos_d(parts[i], L->visualDensity) = col[8][i];
+    }
+    return AGB_OK;
+}
+
+int agb_get_tree_particles(agb_ctx* c, int32_t* leafdepth, uint64_t* key_hi, uint64_t* key_lo)
+{
+    if (!c || !c->built || !leafdepth || !key_hi || !key_lo) return AGB_ERR_INVALID;
+    CK(cudaSetDevice(c->device));
+    const int64_t n = c->d.n;
+    if (n == 0) return AGB_OK;
+    int32_t* dl = nullptr; uint64_t *dh = nullptr, *dlo = nullptr;
+    CK(dalloc(dl, (size_t)n)); CK(dalloc(dh, (size_t)n)); CK(dalloc(dlo, (size_t)n));
+    c->launches += agb_launch_dump_tree(c->d, c->s, dl, dh, dlo, c->st);
+    CK(cudaMemcpyAsync(leafdepth, dl, (size_t)n * 4, cudaMemcpyDeviceToHost, c->st));
+    CK(cudaMemcpyAsync(key_hi, dh, (size_t)n * 8, cudaMemcpyDeviceToHost, c->st));
+    CK(cudaMemcpyAsync(key_lo, dlo, (size_t)n * 8, cudaMemcpyDeviceToHost, c->st));
+    CK(cudaStreamSynchronize(c->st));
+    cudaFree(dl); cudaFree(dh); cudaFree(dlo);
+    return AGB_OK;
+}
+
+int agb_get_node_count(agb_ctx* c, int64_t* n_internal)
+{
+    if (!c || !c->built || !n_internal) return AGB_ERR_INVALID;
+    *n_internal = c->hs.n_nodes;
+    return AGB_OK;
+}
+
+int agb_get_nodes(agb_ctx* c, int32_t* depth, int64_t* count, int32_t* duplicated, uint64_t* key_hi, uint64_t* key_lo,
+                  double* mass, double* comx, double* comy, double* comz, double* gas_mass, double* mvx, double* mvy, double* mvz)
+{
+    if (!c || !c->built) return AGB_ERR_INVALID;
+    CK(cudaSetDevice(c->device));
+    const int64_t m = c->hs.n_nodes, n = c->d.n;
+    if (m == 0) return AGB_OK;
+    const AgbDev& d = c->d;
+    std::vector<int8_t> dep((size_t)m); std::vector<int32_t> first((size_t)m), last((size_t)m); std::vector<uint8_t> dup((size_t)m);
+    std::vector<double4> pm((size_t)m), gv((size_t)m); std::vector<uint64_t> khi((size_t)n), klo((size_t)n);
+    CK(cudaMemcpyAsync(dep.data(), d.ndepth, (size_t)m, cudaMemcpyDeviceToHost, c->st));
+    CK(cudaMemcpyAsync(first.data(), d.nfirst, (size_t)m * 4, cudaMemcpyDeviceToHost, c->st));
+    CK(cudaMemcpyAsync(last.data(), d.nlast, (size_t)m * 4, cudaMemcpyDeviceToHost, c->st));
+    CK(cudaMemcpyAsync(dup.data(), d.ndup, (size_t)m, cudaMemcpyDeviceToHost, c->st));
+    CK(cudaMemcpyAsync(pm.data(), d.src_pm + n, (size_t)m * sizeof(double4), cudaMemcpyDeviceToHost, c->st));
+    CK(cudaMemcpyAsync(gv.data(), d.src_gv + n, (size_t)m * sizeof(double4), cudaMemcpyDeviceToHost, c->st));
+    CK(cudaMemcpyAsync(khi.data(), d.khi[d.cur], (size_t)n * 8, cudaMemcpyDeviceToHost, c->st));
+    CK(cudaMemcpyAsync(klo.data(), d.klo[d.cur], (size_t)n * 8, cudaMemcpyDeviceToHost, c->st));
+    CK(cudaStreamSynchronize(c->st));
+    for (int64_t k = 0; k < m; k++) {
+        const int dp = dep[(size_t)k];
+        uint64_t h = khi[(size_t)first[(size_t)k]], l = klo[(size_t)first[(size_t)k]];
+        if (dp <= 0) { h = 0; l = 0; }
+        else if (dp <= 21) { h &= ~0ull << (63 - 3 * dp); l = 0; }
+        else if (dp < AGB_MAX_LEVELS) { l &= ~0ull << (63 - 3 * (dp - 21)); }
+        if (depth) depth[k] = dp;
+        if (count) count[k] = (int64_t)last[(size_t)k] - first[(size_t)k] + 1;
+        if (duplicated) duplicated[k] = dup[(size_t)k];
+        if (key_hi) key_hi[k] = h;
+        if (key_lo) key_lo[k] = l;
+        if (mass) mass[k] = pm[(size_t)k].w;
+        if (comx) comx[k] = pm[(size_t)k].x;
+        if (comy) comy[k] = pm[(size_t)k].y;
+        if (comz) comz[k] = pm[(size_t)k].z;
+        if (gas_mass) gas_mass[k] = gv[(size_t)k].w;
+        if (mvx) mvx[k] = gv[(size_t)k].x;
+        if (mvy) mvy[k] = gv[(size_t)k].y;
+        if (mvz) mvz[k] = gv[(size_t)k].z;
+    }
+    return AGB_OK;
+}
+
+int agb_get_target_counters(agb_ctx* c, int32_t* visits, int32_t* acc_nodes, int32_t* acc_leaves, int32_t* sph)
+{
+    if (!c || !c->counters_valid || !visits || !acc_nodes || !acc_leaves || !sph) return AGB_ERR_INVALID;
+    CK(cudaSetDevice(c->device));
+    const int64_t n = c->d.n;
+    if (n == 0) return AGB_OK;
+    int32_t* tmp = nullptr;
+    CK(dalloc(tmp, 4 * (size_t)n));
+    c->launches += agb_launch_unpermute_counters(c->d, tmp, tmp + n, tmp + 2 * n, tmp + 3 * n, c->st);
+    CK(cudaMemcpyAsync(visits, tmp, (size_t)n * 4, cudaMemcpyDeviceToHost, c->st));
+    CK(cudaMemcpyAsync(acc_nodes, tmp + n, (size_t)n * 4, cudaMemcpyDeviceToHost, c->st));
+    CK(cudaMemcpyAsync(acc_leaves, tmp + 2 * n, (size_t)n * 4, cudaMemcpyDeviceToHost, c->st));
+    CK(cudaMemcpyAsync(sph, tmp + 3 * n, (size_t)n * 4, cudaMemcpyDeviceToHost, c->st));
+    CK(cudaStreamSynchronize(c->st));
+    cudaFree(tmp);
+    return AGB_OK;
+}
+
+int agb_get_phase_ms(agb_ctx* c, double ms[5])
+{
+    if (!c || !ms) return AGB_ERR_INVALID;
+    for (int i = 0; i < 5; i++) ms[i] = c->phase_ms[i];
+    return AGB_OK;
+}
+
+int agb_get_stream(agb_ctx* c, void** stream)
+{
+    if (!c || !stream) return AGB_ERR_INVALID;
+    *stream = (void*)c->st;
+    return AGB_OK;
+}
+
+int agb_get_launch_count(agb_ctx* c, int64_t* launches)
+{
+    if (!c || !launches) return AGB_ERR_INVALID;
+    *launches = c->launches;
+    return AGB_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,618 @@
+// agb_build.cu — octree construction for the B200 force path (sm_100a).
+//
+// Replaces Tree::buildTree / Tree::calcTreeWidth (Physics/Tree/Tree.cpp:24-55, :86-117) and the two
+// insertion routines of the reference (Physics/Tree/Node.cpp:405-534 bulk, :597-699 one-by-one,
+// :702-719 getOctant).  The reference builds a pointer octree top-down; here the SAME tree (same
+// cells, same leaves, every level of every single-child chain kept) is produced bottom-up:
+//
+//   k_dist_partial/k_extent_*  root half-width R = max |x| among |x| <= mean + 10 sigma
+//   k_keygen                   per particle, the octant path root->leaf by the reference's own FP64
+//                              descent (strict '>' against cell centres produced by c +- r/2), packed
+//                              3 bit/level into a 126-bit key; particles outside the root cube are
+//                              flagged and sort to the end (they stay force targets, Node.cpp:606-612)
+//   k_sort_*                   LSD radix sort, 8-bit digits, 16 passes over (key_hi, key_lo, index)
+//   k_gather                   permute particle data into tree order (unified source table)
+//   k_lcp + scan               shared-levels of neighbouring keys -> one internal node per (first
+//                              particle, depth) pair; ids by prefix sum (children get larger ids)
+//   k_links                    ranges, parents and the 8 child slots by galloping searches on keys
+//   k_upward                   monopole moments bottom-up, "last child to arrive computes the parent"
+//   k_root_fix / k_finalize    reference quirk: with bulk insertion the ROOT's mass/COM include the
+//                              particles outside the cube (Node.cpp:477-499); COM, mVel, duplication
+//                              flags (nodes where bulk hands over to one-by-one insertion hold every
+//                              particle twice in childParticles, Node.cpp:420-428,518,615)
+//
+// All kernels here are HBM-bandwidth bound; geometry is evaluated with explicit round-to-nearest
+// intrinsics (no FMA contraction) so cell boundaries are the reference's, bit for bit.
+#include "agb_internal.cuh"
+#include <algorithm>
+
+namespace {
+
+constexpr int TPB = 256;
+
+__device__ __forceinline__ double warp_sum(double v)
+{
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_max(double v)
+{
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_down_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// ------------------------------------------------------------------ root extent
+__global__ void __launch_bounds__(TPB) k_dist_partial(const double* __restrict__ x, const double* __restrict__ y, const double* __restrict__ z,
+                                                        int64_t n, double* __restrict__ dist, AgbScalars* s)
+{
+    __shared__ double sh[2][TPB / 32];
+    double a = 0.0, b = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * TPB + threadIdx.x; i < n; i += (int64_t)gridDim.x * TPB) {
+        double px = x[i], py = y[i], pz = z[i];
+        // vec3::length (Math/vec3.cpp:76-78): sqrt(x*x + y*y + z*z), separately rounded
+        double d = __dsqrt_rn(__dadd_rn(__dadd_rn(__dmul_rn(px, px), __dmul_rn(py, py)), __dmul_rn(pz, pz)));
+        dist[i] = d;
+        a += d;
+        b += __dmul_rn(d, d);
+    }
+    a = warp_sum(a); b = warp_sum(b);
+    int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    if (l == 0) { sh[0][w] = a; sh[1][w] = b; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double sa = 0.0, sb = 0.0;
+        for (int i = 0; i < TPB / 32; i++) { sa += sh[0][i]; sb += sh[1][i]; }
+        s->partial_sum[blockIdx.x] = sa; s->partial_sq[blockIdx.x] = sb;
+    }
+}
+
+__global__ void k_extent_finish(AgbScalars* s, int nblocks, int64_t n)
+{
+    double sa = 0.0, sb = 0.0;
+    for (int i = 0; i < nblocks; i++) { sa += s->partial_sum[i]; sb += s->partial_sq[i]; }
+    double nn = (double)n;
+    double mean = __ddiv_rn(sa, nn);
+    double var = __dadd_rn(__ddiv_rn(sb, nn), -__dmul_rn(mean, mean));
+    double sd = __dsqrt_rn(var);
+    s->mean = mean; s->stdev = sd;
+    s->limit = __dadd_rn(mean, __dmul_rn(10.0, sd));     // Tree.cpp:89,105
+    s->Rbits = 0ull;
+    s->any_gas = 0; s->n_outliers = 0; s->dup_keys = 0; s->edge_dropped = 0; s->max_depth = 0; s->n_nodes = 0;
+}
+
+__global__ void __launch_bounds__(TPB) k_extent_max(const double* __restrict__ dist, int64_t n, AgbScalars* s)
+{
+    __shared__ double sh[TPB / 32];
+    const double lim = s->limit;
+    double m = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * TPB + threadIdx.x; i < n; i += (int64_t)gridDim.x * TPB) {
+        double d = dist[i];
+        if (d <= lim && d > m) m = d;
+    }
+    m = warp_max(m);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int i = 1; i < TPB / 32; i++) m = fmax(m, sh[i]);
+        atomicMax(&s->Rbits, (unsigned long long)__double_as_longlong(m));   // d >= 0: bit order == value order
+    }
+}
+
+// ------------------------------------------------------------------ keys
+__global__ void __launch_bounds__(TPB) k_keygen(const double* __restrict__ x, const double* __restrict__ y, const double* __restrict__ z, int64_t n,
+                                                  uint64_t* __restrict__ khi, uint64_t* __restrict__ klo, uint32_t* __restrict__ perm, AgbScalars* s)
+{
+    int64_t i = (int64_t)blockIdx.x * TPB + threadIdx.x;
+    bool outl = false, edge = false;
+    if (i < n) {
+        const double R = __longlong_as_double((long long)s->Rbits);
+        const double px = x[i], py = y[i], pz = z[i];
+        uint64_t hi = 0, lo = 0;
+        // root cube is centred on the origin (Tree.cpp:31); inclusive bounds (Node.cpp:706-711)
+        outl = px < -R || px > R || py < -R || py > R || pz < -R || pz > R;
+        if (outl) {
+            hi = AGB_OUTLIER_BIT; lo = (uint64_t)i;      // keep caller order among the outliers
+        } else {
+            double cx = 0.0, cy = 0.0, cz = 0.0, r = R;
+#pragma unroll 1
+            for (int l = 0; l < AGB_MAX_LEVELS; l++) {
+                if (l > 0) {
+                    edge |= px < __dadd_rn(cx, -r) || px > __dadd_rn(cx, r) || py < __dadd_rn(cy, -r) || py > __dadd_rn(cy, r) ||
+                            pz < __dadd_rn(cz, -r) || pz > __dadd_rn(cz, r);
+                }
+                const bool ox = px > cx, oy = py > cy, oz = pz > cz;       // Node.cpp:713-716
+                const uint64_t oct = (uint64_t)ox | ((uint64_t)oy << 1) | ((uint64_t)oz << 2);
+                if (l < 21) hi |= oct << (60 - 3 * l); else lo |= oct << (60 - 3 * (l - 21));
+                const double hr = __dmul_rn(r, 0.5);                       // Node.cpp:436-440
+                cx = __dadd_rn(cx, ox ? hr : -hr);
+                cy = __dadd_rn(cy, oy ? hr : -hr);
+                cz = __dadd_rn(cz, oz ? hr : -hr);
+                r = hr;
+            }
+        }
+        khi[i] = hi; klo[i] = lo; perm[i] = (uint32_t)i;
+    }
+    unsigned mo = __ballot_sync(0xffffffffu, outl), me = __ballot_sync(0xffffffffu, edge);
+    if ((threadIdx.x & 31) == 0) {
+        if (mo) atomicAdd(&s->n_outliers, __popc(mo));
+        if (me) atomicAdd(&s->edge_dropped, __popc(me));
+    }
+}
+
+// ------------------------------------------------------------------ LSD radix sort (8-bit digits)
+constexpr int SORT_ITEMS = 8;
+constexpr int SORT_TILE = TPB * SORT_ITEMS;       // 2048 keys per block
+
+__device__ __forceinline__ uint32_t digit_of(uint64_t w, int shift) { return (uint32_t)(w >> shift) & 255u; }
+
+// per-block digit histogram, written bin-major: hist[bin * nblocks + block]
+__global__ void __launch_bounds__(TPB) k_sort_hist(const uint64_t* __restrict__ word, int64_t n, int shift, uint32_t* __restrict__ hist, int nblocks)
+{
+    __shared__ uint32_t h[256];
+    h[threadIdx.x] = 0;
+    __syncthreads();
+    const int64_t base = (int64_t)blockIdx.x * SORT_TILE;
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+#pragma unroll
+    for (int j = 0; j < SORT_ITEMS; j++) {
+        int64_t i = base + (int64_t)w * (32 * SORT_ITEMS) + j * 32 + l;
+        if (i < n) atomicAdd(&h[digit_of(word[i], shift)], 1u);
+    }
+    __syncthreads();
+    hist[(size_t)threadIdx.x * nblocks + blockIdx.x] = h[threadIdx.x];
+}
+
+// one block per bin: exclusive scan along the blocks of that bin, total per bin
+__global__ void __launch_bounds__(1024) k_sort_scan(uint32_t* __restrict__ hist, int nblocks, AgbScalars* s)
+{
+    __shared__ uint32_t wsum[32];
+    __shared__ uint32_t carry;
+    uint32_t* row = hist + (size_t)blockIdx.x * nblocks;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    const int l = threadIdx.x & 31, w = threadIdx.x >> 5;
+    for (int b0 = 0; b0 < nblocks; b0 += 1024) {
+        int i = b0 + threadIdx.x;
+        uint32_t v = i < nblocks ? row[i] : 0u, inc = v;
+        for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, inc, o); if (l >= o) inc += t; }
+        if (l == 31) wsum[w] = inc;
+        __syncthreads();
+        if (w == 0) {
+            uint32_t t = wsum[l], ti = t;
+            for (int o = 1; o < 32; o <<= 1) { uint32_t u = __shfl_up_sync(0xffffffffu, ti, o); if (l >= o) ti += u; }
+            wsum[l] = ti - t;
+        }
+        __syncthreads();
+        uint32_t excl = carry + wsum[w] + inc - v;
+        if (i < nblocks) row[i] = excl;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry = excl + v;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) s->bintotal[blockIdx.x] = (int32_t)carry;
+}
+
+// stable scatter: rank inside the block by warp match + per-warp digit counters
+__global__ void __launch_bounds__(TPB) k_sort_scatter(const uint64_t* __restrict__ ihi, const uint64_t* __restrict__ ilo, const uint32_t* __restrict__ iv,
+                                                        uint64_t* __restrict__ ohi, uint64_t* __restrict__ olo, uint32_t* __restrict__ ov,
+                                                        int64_t n, int pass, const uint32_t* __restrict__ hist, int nblocks, const AgbScalars* __restrict__ s)
+{
+    __shared__ uint32_t wcnt[TPB / 32][256];
+    __shared__ uint32_t gbase[256];
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    for (int k = threadIdx.x; k < (TPB / 32) * 256; k += TPB) (&wcnt[0][0])[k] = 0;
+    // exclusive scan of the 256 bin totals (every block repeats this tiny scan)
+    {
+        uint32_t v = (uint32_t)s->bintotal[threadIdx.x], inc = v;
+        for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, inc, o); if (l >= o) inc += t; }
+        __shared__ uint32_t ws[TPB / 32];
+        if (l == 31) ws[w] = inc;
+        __syncthreads();
+        uint32_t off = 0;
+        for (int k = 0; k < w; k++) off += ws[k];
+        gbase[threadIdx.x] = off + inc - v + hist[(size_t)threadIdx.x * nblocks + blockIdx.x];
+    }
+    __syncthreads();
+    const int shift = (pass & 7) * 8;
+    const bool use_hi = pass >= 8;
+    const int64_t base = (int64_t)blockIdx.x * SORT_TILE + (int64_t)w * (32 * SORT_ITEMS) + l;
+    uint64_t kh[SORT_ITEMS], kl[SORT_ITEMS]; uint32_t kv[SORT_ITEMS]; uint32_t rk[SORT_ITEMS]; uint32_t dg[SORT_ITEMS];
+#pragma unroll
+    for (int j = 0; j < SORT_ITEMS; j++) {
+        int64_t i = base + j * 32;
+        if (i < n) { kh[j] = ihi[i]; kl[j] = ilo[i]; kv[j] = iv[i]; }
+        else { kh[j] = ~0ull; kl[j] = ~0ull; kv[j] = 0; }
+    }
+    const unsigned lt = (1u << l) - 1u;
+#pragma unroll
+    for (int j = 0; j < SORT_ITEMS; j++) {
+        int64_t i = base + j * 32;
+        bool valid = i < n;
+        uint32_t d = digit_of(use_hi ? kh[j] : kl[j], shift);
+        dg[j] = d;
+        unsigned vm = __ballot_sync(0xffffffffu, valid);
+        unsigned peers = __match_any_sync(0xffffffffu, valid ? d : 256u + (uint32_t)l) & vm;
+        uint32_t prev = valid ? wcnt[w][d] : 0u;
+        __syncwarp();
+        if (valid && (peers & lt) == 0) wcnt[w][d] = prev + __popc(peers);
+        __syncwarp();
+        rk[j] = prev + __popc(peers & lt);
+    }
+    __syncthreads();
+    {   // per digit: exclusive offsets across the warps of this block
+        uint32_t off = 0;
+#pragma unroll
+        for (int k = 0; k < TPB / 32; k++) { uint32_t t = wcnt[k][threadIdx.x]; wcnt[k][threadIdx.x] = off; off += t; }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < SORT_ITEMS; j++) {
+        int64_t i = base + j * 32;
+        if (i < n) {
+            uint32_t pos = gbase[dg[j]] + wcnt[w][dg[j]] + rk[j];
+            ohi[pos] = kh[j]; olo[pos] = kl[j]; ov[pos] = kv[j];
+        }
+    }
+}
+
+// ------------------------------------------------------------------ gather into tree order
+__global__ void __launch_bounds__(TPB) k_gather(AgbDev d, const uint32_t* __restrict__ perm, AgbScalars* s)
+{
+    int64_t i = (int64_t)blockIdx.x * TPB + threadIdx.x;
+    if (i >= d.n) return;
+    uint32_t p = perm[i];
+    double m = d.mass[p];
+    uint8_t t = d.type[p];
+    bool gas = t == 2;
+    d.src_pm[i] = make_double4(d.x[p], d.y[p], d.z[p], m);
+    d.src_gv[i] = make_double4(d.vx ? d.vx[p] : 0.0, d.vy ? d.vy[p] : 0.0, d.vz ? d.vz[p] : 0.0, gas ? m : 0.0);
+    d.src_flag[i] = (gas && m > 0.0) ? 1 : 0;
+    if (gas) s->any_gas = 1;
+    d.s_type[i] = t;
+    d.s_U[i] = d.U ? d.U[p] : 0.0;
+    d.s_mu[i] = d.mu ? d.mu[p] : 0.58;
+    d.s_next[i] = d.next ? d.next[p] : 0.0;
+    d.s_rho[i] = d.rho[p]; d.s_P[i] = d.P[p]; d.s_T[i] = d.T[p];
+    d.s_h[i] = gas ? 0.0 : d.h[p];                   // Tree.cpp:123-133 zeroes h of every gas particle
+    d.group[i] = -1;
+    d.leafparent[i] = -1;
+    d.leafdepth[i] = -1;
+    d.leafmark[i] = 0;
+}
+
+// ------------------------------------------------------------------ shared levels of neighbours, node counts
+__global__ void __launch_bounds__(TPB) k_lcp(const uint64_t* __restrict__ khi, const uint64_t* __restrict__ klo, int64_t n,
+                                               int8_t* __restrict__ lcp, int32_t* __restrict__ cnt, AgbScalars* s)
+{
+    int64_t i = (int64_t)blockIdx.x * TPB + threadIdx.x;
+    if (i >= n) return;
+    const int64_t nt = n - s->n_outliers;
+    int Li = -1, Lm = -1;
+    if (i < nt) {
+        uint64_t h = khi[i], l = klo[i];
+        if (i + 1 < nt) {
+            Li = agb_common_levels(h, l, khi[i + 1], klo[i + 1]);
+            if (Li >= AGB_MAX_LEVELS) { atomicAdd(&s->dup_keys, 1); Li = AGB_MAX_LEVELS - 1; }
+        }
+        if (i > 0) { Lm = agb_common_levels(khi[i - 1], klo[i - 1], h, l); if (Lm >= AGB_MAX_LEVELS) Lm = AGB_MAX_LEVELS - 1; }
+        int md = max(Li, Lm) + 1;
+        if (md > s->max_depth) atomicMax(&s->max_depth, md);
+    }
+    lcp[i] = (int8_t)Li;
+    cnt[i] = Li > Lm ? Li - Lm : 0;
+    if (i == 0) s->n_in_tree = (int32_t)nt;
+}
+
+// ------------------------------------------------------------------ exclusive scan (int32)
+constexpr int SCAN_TILE = 2048;
+__device__ __forceinline__ int block_excl_scan(int v, int* total)
+{   // 256 threads
+    __shared__ int ws[TPB / 32];
+    __shared__ int tot;
+    const int l = threadIdx.x & 31, w = threadIdx.x >> 5;
+    int inc = v;
+    for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, inc, o); if (l >= o) inc += t; }
+    __syncthreads();
+    if (l == 31) ws[w] = inc;
+    __syncthreads();
+    int off = 0;
+    for (int k = 0; k < w; k++) off += ws[k];
+    if (threadIdx.x == TPB - 1) tot = off + inc;
+    __syncthreads();
+    *total = tot;
+    return off + inc - v;
+}
+
+__global__ void __launch_bounds__(TPB) k_scan_reduce(const int32_t* __restrict__ in, int64_t n, int32_t* __restrict__ blk)
+{
+    int64_t base = (int64_t)blockIdx.x * SCAN_TILE + threadIdx.x * 8;
+    int v = 0;
+#pragma unroll
+    for (int j = 0; j < 8; j++) if (base + j < n) v += in[base + j];
+    int tot;
+    block_excl_scan(v, &tot);
+    if (threadIdx.x == 0) blk[blockIdx.x] = tot;
+}
+
+__global__ void __launch_bounds__(TPB) k_scan_blocks(int32_t* __restrict__ blk, int nb, int32_t* total_out)
+{
+    __shared__ int carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int b0 = 0; b0 < nb; b0 += TPB) {
+        int i = b0 + threadIdx.x;
+        int v = i < nb ? blk[i] : 0, tot;
+        int e = block_excl_scan(v, &tot);
+        int c = carry;
+        if (i < nb) blk[i] = c + e;
+        __syncthreads();
+        if (threadIdx.x == 0) carry = c + tot;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *total_out = carry;
+}
+
+__global__ void __launch_bounds__(TPB) k_scan_apply(const int32_t* __restrict__ in, int64_t n, const int32_t* __restrict__ blk, int32_t* __restrict__ out)
+{
+    int64_t base = (int64_t)blockIdx.x * SCAN_TILE + threadIdx.x * 8;
+    int v[8], sum = 0;
+#pragma unroll
+    for (int j = 0; j < 8; j++) { v[j] = base + j < n ? in[base + j] : 0; sum += v[j]; }
+    int tot;
+    int e = block_excl_scan(sum, &tot) + blk[blockIdx.x];
+#pragma unroll
+    for (int j = 0; j < 8; j++) { if (base + j < n) out[base + j] = e; e += v[j]; }
+}
+
+// ------------------------------------------------------------------ links
+__global__ void __launch_bounds__(TPB) k_init_nodes(AgbDev d, const AgbScalars* __restrict__ s)
+{
+    int64_t k = (int64_t)blockIdx.x * TPB + threadIdx.x;
+    if (k >= s->n_nodes) return;
+    int4 e = make_int4(-1, -1, -1, -1);
+    reinterpret_cast<int4*>(d.child)[2 * k] = e;
+    reinterpret_cast<int4*>(d.child)[2 * k + 1] = e;
+    d.arrived[k] = 0;
+    d.nmark[k] = 0;
+}
+
+struct KeyView { const uint64_t* hi; const uint64_t* lo; };
+
+// smallest s <= i whose key shares >= d levels with key i
+__device__ __forceinline__ int64_t find_first(KeyView K, int64_t i, int d, uint64_t h, uint64_t l)
+{
+    if (d <= 0) return 0;
+    int64_t step = 1;
+    while (i - step >= 0 && agb_common_levels(K.hi[i - step], K.lo[i - step], h, l) >= d) step <<= 1;
+    int64_t lo = max((int64_t)-1, i - step), hi = i - (step >> 1);      // key[lo] fails (or lo == -1), key[hi] passes
+    while (hi - lo > 1) {
+        int64_t mid = (lo + hi) >> 1;
+        if (agb_common_levels(K.hi[mid], K.lo[mid], h, l) >= d) hi = mid; else lo = mid;
+    }
+    return hi;
+}
+// largest e >= i (e < nt) whose key shares >= d levels with key i
+__device__ __forceinline__ int64_t find_last(KeyView K, int64_t i, int d, uint64_t h, uint64_t l, int64_t nt)
+{
+    if (d <= 0) return nt - 1;
+    int64_t step = 1;
+    while (i + step < nt && agb_common_levels(K.hi[i + step], K.lo[i + step], h, l) >= d) step <<= 1;
+    int64_t hi = min(nt, i + step), lo = i + (step >> 1);                // key[lo] passes, key[hi] fails (or hi == nt)
+    while (hi - lo > 1) {
+        int64_t mid = (lo + hi) >> 1;
+        if (agb_common_levels(K.hi[mid], K.lo[mid], h, l) >= d) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+__device__ __forceinline__ int node_id_at(const AgbDev& d, int64_t s, int depth)
+{   // id of the node of depth `depth` whose first particle is s
+    int Lprev = s > 0 ? (int)d.lcp[s - 1] : -1;
+    return d.nodebase[s] + (depth - Lprev - 1);
+}
+
+__global__ void __launch_bounds__(TPB) k_links(AgbDev d, const uint64_t* __restrict__ khi, const uint64_t* __restrict__ klo, const AgbScalars* __restrict__ s)
+{
+    int64_t i = (int64_t)blockIdx.x * TPB + threadIdx.x;
+    const int64_t nt = s->n_in_tree;
+    if (i >= nt) return;
+    if (nt < 2) { d.leafdepth[i] = 0; return; }              // a single particle: the root itself is the leaf (Node.cpp:409-418)
+    KeyView K{khi, klo};
+    const uint64_t h = khi[i], l = klo[i];
+    const int Li = d.lcp[i], Lm = i > 0 ? (int)d.lcp[i - 1] : -1;
+    const int base = d.nodebase[i];
+    const int N = (int)d.n;
+    for (int dep = Lm + 1; dep <= Li; dep++) {
+        int k = base + (dep - Lm - 1);
+        d.ndepth[k] = (int8_t)dep;
+        d.nfirst[k] = (int32_t)i;
+        d.nlast[k] = (int32_t)find_last(K, i, dep, h, l, nt);
+        int par;
+        if (dep == Lm + 1) {
+            if (dep == 0) par = -1;
+            else { int64_t sfirst = find_first(K, i, dep - 1, h, l); par = node_id_at(d, sfirst, dep - 1); }
+        } else par = k - 1;
+        d.nparent[k] = par;
+        if (par >= 0) d.child[(size_t)par * 8 + agb_octant_at(h, l, dep - 1)] = N + k;
+    }
+    // the particle's own leaf hangs below the deepest internal node that contains it
+    const int dp = max(Li, Lm);
+    int par;
+    if (Li > Lm) par = base + (Li - Lm - 1);
+    else { int64_t sfirst = find_first(K, i, dp, h, l); par = node_id_at(d, sfirst, dp); }
+    d.child[(size_t)par * 8 + agb_octant_at(h, l, dp)] = (int32_t)i;
+    d.leafparent[i] = par;
+    d.leafdepth[i] = (int8_t)(dp + 1);
+}
+
+// ------------------------------------------------------------------ upward pass (monopole + gas moments)
+__device__ __forceinline__ int count_node_children(const int32_t* child, int k, int N)
+{
+    const int4 a = reinterpret_cast<const int4*>(child)[2 * (size_t)k], b = reinterpret_cast<const int4*>(child)[2 * (size_t)k + 1];
+    return (a.x >= N) + (a.y >= N) + (a.z >= N) + (a.w >= N) + (b.x >= N) + (b.y >= N) + (b.z >= N) + (b.w >= N);
+}
+
+__device__ __forceinline__ double4 ldcg4(const double4* p)
+{   // L2-coherent read of data another SM has just published
+    const double2 a = __ldcg(reinterpret_cast<const double2*>(p)), b = __ldcg(reinterpret_cast<const double2*>(p) + 1);
+    return make_double4(a.x, a.y, b.x, b.y);
+}
+
+__device__ __forceinline__ void node_moments(const AgbDev& d, int k, int N)
+{
+    double sx = 0, sy = 0, sz = 0, m = 0, gx = 0, gy = 0, gz = 0, g = 0;
+#pragma unroll
+    for (int o = 0; o < 8; o++) {                      // fixed octant order => run-to-run identical sums
+        int c = d.child[(size_t)k * 8 + o];
+        if (c < 0) continue;
+        if (c < N) {
+            double4 pm = d.src_pm[c], gv = d.src_gv[c];
+            m += pm.w; sx += pm.x * pm.w; sy += pm.y * pm.w; sz += pm.z * pm.w;
+            g += gv.w; gx += gv.x * gv.w; gy += gv.y * gv.w; gz += gv.z * gv.w;
+        } else {
+            double4 pm = ldcg4(&d.mom_pm[c - N]), gv = ldcg4(&d.mom_gv[c - N]);
+            m += pm.w; sx += pm.x; sy += pm.y; sz += pm.z;
+            g += gv.w; gx += gv.x; gy += gv.y; gz += gv.z;
+        }
+    }
+    d.mom_pm[k] = make_double4(sx, sy, sz, m);
+    d.mom_gv[k] = make_double4(gx, gy, gz, g);
+}
+
+__global__ void __launch_bounds__(TPB) k_upward(AgbDev d, const AgbScalars* __restrict__ s)
+{
+    int k = blockIdx.x * TPB + threadIdx.x;
+    if (k >= s->n_nodes) return;
+    const int N = (int)d.n;
+    if (count_node_children(d.child, k, N) != 0) return;      // only nodes whose children are all leaves start a climb
+    int cur = k;
+    while (true) {
+        node_moments(d, cur, N);
+        __threadfence();
+        int par = d.nparent[cur];
+        if (par < 0) break;
+        int need = count_node_children(d.child, par, N);
+        int old = atomicAdd(&d.arrived[par], 1);
+        if (old + 1 < need) break;                             // a sibling subtree is still being summed
+        __threadfence();
+        cur = par;
+    }
+}
+
+// Reference quirk: bulk insertion accumulates the ROOT's mass / COM / gasMass / mVel over ALL particles,
+// including those outside the cube that are never inserted (Node.cpp:477-499 precede the octant test).
+__global__ void k_root_fix(AgbDev d, const AgbScalars* __restrict__ s)
+{
+    if (s->n_nodes < 1) return;
+    if (d.n < (int64_t)d.cores * 100) return;                  // one-by-one insertion rejects them at the root (Node.cpp:606-612)
+    double4 pm = d.mom_pm[0], gv = d.mom_gv[0];
+    for (int64_t i = s->n_in_tree; i < d.n; i++) {
+        double4 a = d.src_pm[i], b = d.src_gv[i];
+        pm.w += a.w; pm.x += a.x * a.w; pm.y += a.y * a.w; pm.z += a.z * a.w;
+        gv.w += b.w; gv.x += b.x * b.w; gv.y += b.y * b.w; gv.z += b.z * b.w;
+    }
+    d.mom_pm[0] = pm; d.mom_gv[0] = gv;
+}
+
+__global__ void __launch_bounds__(TPB) k_finalize(AgbDev d, const AgbScalars* __restrict__ s)
+{
+    int k = blockIdx.x * TPB + threadIdx.x;
+    if (k >= s->n_nodes) return;
+    const int64_t N = d.n;
+    double4 pm = d.mom_pm[k], gv = d.mom_gv[k];
+    double4 com = make_double4(0, 0, 0, pm.w), mv = make_double4(0, 0, 0, gv.w);
+    if (pm.w > 0.0) { com.x = pm.x / pm.w; com.y = pm.y / pm.w; com.z = pm.z / pm.w; }
+    if (gv.w > 0.0) { mv.x = gv.x / gv.w; mv.y = gv.y / gv.w; mv.z = gv.z / gv.w; }
+    d.src_pm[N + k] = com;
+    d.src_gv[N + k] = mv;
+    d.src_flag[N + k] = gv.w > 0.0 ? 1 : 0;
+    // nodes where bulk insertion (>= cores*100 particles) hands over to one-by-one insertion
+    const int64_t thr = (int64_t)d.cores * 100;
+    int par = d.nparent[k];
+    uint8_t dup = 0;
+    if (par >= 0) {
+        int64_t cnt = (int64_t)d.nlast[k] - d.nfirst[k] + 1;
+        int64_t pcnt = par == 0 ? N : (int64_t)d.nlast[par] - d.nfirst[par] + 1;   // the root is handed all N particles
+        dup = cnt < thr && pcnt >= thr;
+    }
+    d.ndup[k] = dup;
+}
+
+// ------------------------------------------------------------------ introspection
+__global__ void __launch_bounds__(TPB) k_dump_tree(AgbDev d, const uint64_t* __restrict__ khi, const uint64_t* __restrict__ klo, const uint32_t* __restrict__ perm,
+                                                     const AgbScalars* __restrict__ s, int32_t* leafdepth, uint64_t* ohi, uint64_t* olo)
+{
+    int64_t i = (int64_t)blockIdx.x * TPB + threadIdx.x;
+    if (i >= d.n) return;
+    uint32_t p = perm[i];
+    if (i >= s->n_in_tree) { leafdepth[p] = -1; ohi[p] = 0; olo[p] = 0; return; }
+    int ld = d.leafdepth[i];
+    leafdepth[p] = ld;
+    uint64_t h = khi[i], l = klo[i];
+    // keep only the first `ld` levels of the path
+    if (ld <= 0) { h = 0; l = 0; }
+    else if (ld <= 21) { h &= ~0ull << (63 - 3 * ld); l = 0; }
+    else if (ld < AGB_MAX_LEVELS) { l &= ~0ull << (63 - 3 * (ld - 21)); }
+    ohi[p] = h & ~AGB_OUTLIER_BIT; olo[p] = l;
+}
+
+} // namespace
+
+// ====================================================================== launchers
+static inline int nblk(int64_t n, int per) { return (int)((n + per - 1) / per); }
+
+int agb_launch_extent(const AgbDev& d, AgbScalars* s, cudaStream_t st)
+{
+    int nb = (int)std::min<int64_t>(1024, std::max<int64_t>(1, nblk(d.n, TPB)));
+    k_dist_partial<<<nb, TPB, 0, st>>>(d.x, d.y, d.z, d.n, d.dist, s);
+    k_extent_finish<<<1, 1, 0, st>>>(s, nb, d.n);
+    k_extent_max<<<nb, TPB, 0, st>>>(d.dist, d.n, s);
+    return 3;
+}
+
+int agb_launch_keygen(AgbDev& d, AgbScalars* s, cudaStream_t st)
+{
+    k_keygen<<<nblk(d.n, TPB), TPB, 0, st>>>(d.x, d.y, d.z, d.n, d.khi[0], d.klo[0], d.perm[0], s);
+    d.cur = 0;
+    return 1;
+}
+
+int agb_launch_sort(AgbDev& d, AgbScalars* s, cudaStream_t st)
+{
+    const int nb = nblk(d.n, SORT_TILE);
+    int launches = 0;
+    for (int pass = 0; pass < 16; pass++) {
+        const int in = d.cur, out = d.cur ^ 1;
+        const uint64_t* word = pass >= 8 ? d.khi[in] : d.klo[in];
+        k_sort_hist<<<nb, TPB, 0, st>>>(word, d.n, (pass & 7) * 8, d.blockhist, nb);
+        k_sort_scan<<<256, 1024, 0, st>>>(d.blockhist, nb, s);
+        k_sort_scatter<<<nb, TPB, 0, st>>>(d.khi[in], d.klo[in], d.perm[in], d.khi[out], d.klo[out], d.perm[out], d.n, pass, d.blockhist, nb, s);
+        d.cur = out;
+        launches += 3;
+    }
+    return launches;
+}
+
+int agb_launch_links(AgbDev& d, AgbScalars* s, cudaStream_t st)
+{
+    const int nb = nblk(d.n, TPB);
+    const uint64_t *khi = d.khi[d.cur], *klo = d.klo[d.cur];
+    k_gather<<<nb, TPB, 0, st>>>(d, d.perm[d.cur], s);
+    k_lcp<<<nb, TPB, 0, st>>>(khi, klo, d.n, d.lcp, d.nodecnt, s);
+    const int sb = nblk(d.n, SCAN_TILE);
+    k_scan_reduce<<<sb, TPB, 0, st>>>(d.nodecnt, d.n, d.scanblk);
+    k_scan_blocks<<<1, TPB, 0, st>>>(d.scanblk, sb, &s->n_nodes);
+    k_scan_apply<<<sb, TPB, 0, st>>>(d.nodecnt, d.n, d.scanblk, d.nodebase);
+    k_init_nodes<<<nb, TPB, 0, st>>>(d, s);
+    k_links<<<nb, TPB, 0, st>>>(d, khi, klo, s);
+    k_upward<<<nb, TPB, 0, st>>>(d, s);
+    k_root_fix<<<1, 1, 0, st>>>(d, s);
+    k_finalize<<<nb, TPB, 0, st>>>(d, s);
+    return 10;
+}
+
+int agb_launch_dump_tree(AgbDev& d, AgbScalars* s, int32_t* leafdepth, uint64_t* khi, uint64_t* klo, cudaStream_t st)
+{
+    k_dump_tree<<<nblk(d.n, TPB), TPB, 0, st>>>(d, d.khi[d.cur], d.klo[d.cur], d.perm[d.cur], s, leafdepth, khi, klo);
+    return 1;
+}

@@ -1,0 +1,99 @@
+// agb_internal.cuh — device-side data model shared by the kernels of the B200 force path.
+//
+// HBM layout (all structure-of-arrays, 180 GB budget; ~330 B per particle incl. tree):
+//   caller order   : x y z vx vy vz mass U next mu type      (inputs, bound or copied)
+//                    ax ay az dUdt h rho P T vis              (carried state / results)
+//   tree order     : key_hi key_lo perm                       (Morton-like 126-bit octant paths)
+//                    src_pm[N+M]  double4 (x, y, z, mass)     unified "source" table: index < N is
+//                    src_gv[N+M]  double4 (vx, vy, vz, gasM)  the i-th sorted particle, N+k is the
+//                    src_flag[N+M]                            k-th internal octree node (COM, mVel)
+//                    s_h s_rho s_P s_U s_mu s_next s_type leafdepth leafparent group
+//   nodes          : child[M][8] (int32 source index, -1 = empty) depth first last parent
+//                    mom_pm mom_gv (un-normalised moments of the upward pass) mark dup arrived
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/agb200.h"
+
+#define AGB_MAX_LEVELS 42
+#define AGB_OUTLIER_BIT 0x8000000000000000ull
+
+struct AgbDev {
+    int64_t n = 0, cap = 0;
+    int cores = 1;
+    // caller-order inputs (owned copies unless `bound`)
+    const double *x = nullptr, *y = nullptr, *z = nullptr, *vx = nullptr, *vy = nullptr, *vz = nullptr;
+    const double *mass = nullptr, *U = nullptr, *next = nullptr, *mu = nullptr;
+    const uint8_t* type = nullptr;
+    // caller-order state / results (always owned)
+    double *ax = nullptr, *ay = nullptr, *az = nullptr, *dUdt = nullptr, *h = nullptr, *rho = nullptr, *P = nullptr, *T = nullptr, *vis = nullptr;
+    // keys + permutation, ping-pong for the radix sort
+    uint64_t *khi[2] = {nullptr, nullptr}, *klo[2] = {nullptr, nullptr};
+    uint32_t* perm[2] = {nullptr, nullptr};
+    int cur = 0;                       // which ping-pong half holds the sorted result
+    // tree-order particle data
+    double4 *src_pm = nullptr, *src_gv = nullptr;
+    uint8_t* src_flag = nullptr;
+    double *s_h = nullptr, *s_rho = nullptr, *s_P = nullptr, *s_U = nullptr, *s_mu = nullptr, *s_next = nullptr, *s_T = nullptr;
+    uint8_t* s_type = nullptr;
+    int8_t* lcp = nullptr;             // common levels of sorted keys i, i+1
+    int32_t *nodebase = nullptr, *nodecnt = nullptr;
+    int32_t *leafparent = nullptr, *group = nullptr;
+    int8_t* leafdepth = nullptr;
+    // nodes (capacity cap)
+    int32_t *child = nullptr, *nfirst = nullptr, *nlast = nullptr, *nparent = nullptr, *arrived = nullptr;
+    int8_t* ndepth = nullptr;
+    uint8_t *nmark = nullptr, *ndup = nullptr, *leafmark = nullptr;
+    double4 *mom_pm = nullptr, *mom_gv = nullptr;
+    int32_t* grouplist = nullptr;
+    // scratch
+    double* dist = nullptr;
+    uint32_t* blockhist = nullptr;     // radix sort: [256][nblocks]
+    int32_t* scanblk = nullptr;
+    // per-target counters (optional)
+    int32_t *c_visits = nullptr, *c_accn = nullptr, *c_accl = nullptr, *c_sph = nullptr;
+    // walk spill stack
+    int2* spill = nullptr; int64_t spill_per_warp = 0; int spill_warps = 0;
+};
+
+// Device-resident scalars of one step (read back in a single copy when the host needs them).
+struct AgbScalars {
+    double partial_sum[1024], partial_sq[1024];
+    double mean, stdev, limit, R;
+    unsigned long long Rbits;
+    int32_t n_in_tree, n_outliers, n_nodes, dup_keys, edge_dropped, max_depth;
+    int32_t n_groups, n_gas_groups, n_gas_orphans, n_active;
+    unsigned int walk_next_group;
+    unsigned long long c_interactions, c_node, c_leaf, c_sph, c_visits, c_exact, c_spill;
+    int32_t bintotal[256];
+    int32_t vis_level;
+    int32_t walk_overflow, any_gas;
+};
+
+// ---- host-callable launchers (each returns the number of kernels it launched) ----
+int agb_launch_extent(const AgbDev& d, AgbScalars* s, cudaStream_t st);
+int agb_launch_keygen(AgbDev& d, AgbScalars* s, cudaStream_t st);
+int agb_launch_sort(AgbDev& d, AgbScalars* s, cudaStream_t st);
+int agb_launch_links(AgbDev& d, AgbScalars* s, cudaStream_t st);
+int agb_launch_visual(AgbDev& d, AgbScalars* s, double radius, cudaStream_t st);
+int agb_launch_gas_density(AgbDev& d, AgbScalars* s, double massInH, cudaStream_t st);
+int agb_launch_walk(AgbDev& d, AgbScalars* s, double globalTime, double e0, double theta, int64_t t0, int64_t t1,
+                    bool counters, bool any_gas, int sm_count, cudaStream_t st, cudaEvent_t ev0, cudaEvent_t ev1);
+int agb_launch_dump_tree(AgbDev& d, AgbScalars* s, int32_t* leafdepth, uint64_t* khi, uint64_t* klo, cudaStream_t st);
+int agb_launch_unpermute_counters(AgbDev& d, int32_t* v, int32_t* an, int32_t* al, int32_t* sp, cudaStream_t st);
+
+// ---- small device helpers ----
+__device__ __forceinline__ int agb_octant_at(uint64_t hi, uint64_t lo, int level)
+{
+    return level < 21 ? (int)((hi >> (60 - 3 * level)) & 7) : (int)((lo >> (60 - 3 * (level - 21))) & 7);
+}
+
+// number of leading octree levels two keys share (0..42)
+__device__ __forceinline__ int agb_common_levels(uint64_t ahi, uint64_t alo, uint64_t bhi, uint64_t blo)
+{
+    uint64_t xh = ahi ^ bhi;
+    if (xh) return (__clzll((long long)xh) - 1) / 3;
+    uint64_t xl = alo ^ blo;
+    if (xl) return 21 + (__clzll((long long)xl) - 1) / 3;
+    return AGB_MAX_LEVELS;
+}

@@ -1,0 +1,406 @@
+// agb_walk.cu — warp-cooperative Barnes–Hut walk with in-walk SPH (sm_100a).
+//
+// Replaces Tree::calculateForces (Physics/Tree/Tree.cpp:57-83), Node::calculateGravityForce
+// (Physics/Tree/Node.cpp:247-399) and Node::calcSPHForce (Node.cpp:88-172, Math/kernel.cpp:18-39).
+//
+// Parity contract: every target must interact with exactly the (node | leaf) set the reference's
+// per-particle recursion accepts: MAC `radius / r < theta` with radius = cell half-width and r the
+// distance to the node's centre of mass, tested at every level (single-child chains included);
+// force law  a += G M d / (r (r^2 + e0^2))  (the reference's spline softening is dead code for
+// e0 > 2.15e13); SPH pressure + Monaghan–Gingold viscosity + dU/dt against every
+// accepted node/leaf that holds gas and lies within r < 2 h_i, with the target's own h, rho, P.
+//
+// B200 mapping: one warp owns 32 tree-adjacent targets.  The warp walks the UNION of their trees
+// with a shared-memory stack of (node, lane-mask) pairs.  Each lane pops a different node and
+// classifies it against the bounding box of the warp's targets:
+//     box entirely beyond radius/theta   -> accepted by every lane in the mask
+//     box entirely inside radius/theta   -> opened by every lane in the mask (children inherit mask)
+//     straddling                         -> per-lane exact test (__ballot_sync splits the mask)
+// so the per-target accepted set is exact while most of the tree is pruned at 1/32 of the cost.
+// Accepted sources go to a shared-memory interaction list; the list is drained in tiles of 32:
+// lanes gather the 32 sources (coalesced double4 loads) into a staging buffer, then every lane runs
+// all of them against its own target out of shared memory (broadcast reads).  Arithmetic is FP64 on
+// the CUDA-core FP64 pipe (no tensor cores: this is not a dense contraction).  Decisions that must
+// match the reference bit for bit (MAC, r < 2h) use a cheap guarded test and fall back to the
+// reference's exact separately-rounded expression when within 1e-13 of the threshold.
+#include "agb_internal.cuh"
+#include <algorithm>
+
+namespace {
+
+constexpr int WALK_WARPS = 8;
+constexpr int WALK_TPB = WALK_WARPS * 32;
+constexpr int LCAP = 512;                  // interaction-list entries per warp
+constexpr int LGROW = 288;                 // worst-case growth per pop round: 32 lanes x (8 leaves + 1 node)
+constexpr int SCAP = 512;                  // shared part of the traversal stack
+constexpr int GASBIT = 1 << 30;
+constexpr int IDXMASK = GASBIT - 1;
+constexpr double kG = 6.67430e-11;         // Math/Constants.h:7
+constexpr double kPI = 3.14159265358979323846;
+constexpr double kGAMMA = 5.0 / 3.0;
+
+struct WarpSmem {
+    int2 list[LCAP];
+    int2 stack[SCAP];
+    double4 stage[32];
+};
+
+struct WalkParams {
+    const double4 *src_pm, *src_gv;
+    const uint8_t* src_flag;
+    const int32_t* child;
+    const int8_t* ndepth;
+    const double *s_h, *s_rho, *s_P, *s_next;
+    const uint8_t* s_type;
+    const uint32_t* perm;
+    double *ax, *ay, *az, *dUdt;
+    int32_t *c_visits, *c_accn, *c_accl, *c_sph;
+    int2* spill; int64_t spill_per_warp;
+    AgbScalars* s;
+    int64_t N, t0, t1;
+    unsigned ngroups;
+    double theta, e0, globalTime;
+};
+
+enum { OUT_NONE = 0, OUT_ACCEPT = 1, OUT_OPEN = 2, OUT_MIXED = 3 };
+
+__device__ __forceinline__ double warp_min(double v) { for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o)); return v; }
+__device__ __forceinline__ double warp_max(double v) { for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o)); return v; }
+__device__ __forceinline__ int warp_incl_scan(int v, int lane)
+{
+    for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o) v += t; }
+    return v;
+}
+__device__ __forceinline__ unsigned long long warp_sum_u64(unsigned long long v)
+{
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+template <bool COUNT, bool SPH>
+__global__ void __launch_bounds__(WALK_TPB, 2) k_walk(const WalkParams P)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    WarpSmem& sm = reinterpret_cast<WarpSmem*>(smem_raw)[warp];
+    int2* const spill = P.spill + (size_t)(blockIdx.x * WALK_WARPS + warp) * P.spill_per_warp;
+    const unsigned lt = (1u << lane) - 1u;
+    const int N = (int)P.N;
+    const double R = __longlong_as_double((long long)P.s->Rbits);
+    const int n_nodes = P.s->n_nodes, n_in_tree = P.s->n_in_tree;
+    const double theta = P.theta, theta2 = theta * theta;
+    const bool fast_mac = theta > 0.0;
+    // the law is evaluated in units of R so that r^2 (r^2+e0^2)^2 cannot overflow for any unit system
+    const double invR2 = R > 0.0 ? 1.0 / (R * R) : 1.0;
+    const double e02s = P.e0 * P.e0 * invR2;
+    const double GR3 = kG * invR2 * sqrt(invR2);
+
+    unsigned long long tot_node = 0, tot_leaf = 0, tot_sph = 0, tot_visit = 0, tot_exact = 0, tot_spill = 0;
+
+    auto stack_put = [&](int idx, int2 v) {
+        if (idx < SCAP) sm.stack[idx] = v;
+        else if (idx - SCAP < P.spill_per_warp) spill[idx - SCAP] = v;
+        else P.s->walk_overflow = 1;                      // reported as AGB_ERR_NOMEM by agb_forces
+    };
+    auto stack_get = [&](int idx) -> int2 {
+        if (idx < SCAP) return sm.stack[idx];
+        if (idx - SCAP < P.spill_per_warp) return spill[idx - SCAP];
+        return make_int2(-1, 0);
+    };
+
+    for (;;) {
+        unsigned g = 0;
+        if (lane == 0) g = atomicAdd(&P.s->walk_next_group, 1u);
+        g = __shfl_sync(0xffffffffu, g, 0);
+        if (g >= P.ngroups) break;
+        const int64_t t = P.t0 + (int64_t)g * 32 + lane;
+        const bool inrange = t < P.t1;
+        const double4 tp = inrange ? P.src_pm[t] : make_double4(0, 0, 0, 0);
+        const bool active = inrange && (P.s_next[t] == P.globalTime);           // Tree.cpp:75
+        const bool valid = active && tp.w != 0.0;                               // Node.cpp:265
+        // per-target SPH constants (the reference overrides h_j, rho_j, P_j with the target's, Node.cpp:94,101,108)
+        bool tgas = false;
+        double h_t = 0, hh4 = 0, inv_pi_h4 = 0, A2 = 0, cs = 0, tvx = 0, tvy = 0, tvz = 0;
+        if (SPH && valid && P.s_type[t] == 2) {
+            tgas = true;
+            h_t = P.s_h[t];
+            const double rho = P.s_rho[t], Pr = P.s_P[t];
+            hh4 = 4.0 * h_t * h_t;
+            inv_pi_h4 = 1.0 / (kPI * h_t * h_t * h_t) / h_t;
+            A2 = Pr / (rho * rho) + Pr / (rho * rho);
+            cs = sqrt(kGAMMA * Pr / rho);
+            const double4 v = P.src_gv[t];
+            tvx = v.x; tvy = v.y; tvz = v.z;
+        }
+        double ax = 0, ay = 0, az = 0, dU = 0;
+        int c_vis = (active && (n_nodes > 0 || !valid)) ? 1 : 0, c_an = 0, c_al = 0, c_sp = 0;              // the root call itself
+        const unsigned vmask = __ballot_sync(0xffffffffu, valid);
+
+        if (vmask) {
+            const double inf = __longlong_as_double(0x7ff0000000000000ll);
+            const double lox = warp_min(valid ? tp.x : inf), loy = warp_min(valid ? tp.y : inf), loz = warp_min(valid ? tp.z : inf);
+            const double hix = warp_max(valid ? tp.x : -inf), hiy = warp_max(valid ? tp.y : -inf), hiz = warp_max(valid ? tp.z : -inf);
+            int sp = 0, lc = 0;
+            bool root_pending = true;
+            if (n_nodes > 0) { if (lane == 0) sm.stack[0] = make_int2(N, (int)vmask); sp = 1; }
+            else if (n_in_tree == 1) { if (lane == 0) sm.list[0] = make_int2(0, (int)vmask); lc = 1; }
+            __syncwarp();
+
+            while (true) {
+                // ------------------------------------------------ traversal: fill the interaction list
+                while (sp > 0 && lc <= LCAP - LGROW) {
+                    const int cnt = min(sp, 32);
+                    sp -= cnt;
+                    int2 e = make_int2(-1, 0);
+                    if (lane < cnt) e = stack_get(sp + lane);
+                    if (sp + cnt > SCAP) tot_spill += 1;
+                    int outcome = OUT_NONE;
+                    double rad2 = 0;
+                    if (lane < cnt && e.x >= 0) {
+                        const double4 pm = P.src_pm[e.x];
+                        if (pm.w != 0.0) {                                       // Node.cpp:250 / :390
+                            const double rad = scalbn(R, -(int)P.ndepth[e.x - N]);
+                            rad2 = rad * rad;
+                            const double ax_ = fmax(0.0, fmax(lox - pm.x, pm.x - hix)), ay_ = fmax(0.0, fmax(loy - pm.y, pm.y - hiy)), az_ = fmax(0.0, fmax(loz - pm.z, pm.z - hiz));
+                            const double bx_ = fmax(fabs(pm.x - lox), fabs(pm.x - hix)), by_ = fmax(fabs(pm.y - loy), fabs(pm.y - hiy)), bz_ = fmax(fabs(pm.z - loz), fabs(pm.z - hiz));
+                            const double dmin2 = ax_ * ax_ + ay_ * ay_ + az_ * az_, dmax2 = bx_ * bx_ + by_ * by_ + bz_ * bz_;
+                            outcome = OUT_MIXED;
+                            if (fast_mac) {
+                                if (dmin2 * theta2 > rad2 * (1.0 + 1e-12)) outcome = OUT_ACCEPT;
+                                else if (dmin2 > 0.0 && dmax2 * theta2 < rad2 * (1.0 - 1e-12)) outcome = OUT_OPEN;
+                            }
+                        }
+                    }
+                    if (COUNT) {
+                        const unsigned vm = (outcome != OUT_NONE && !(root_pending && e.x == N)) ? (unsigned)e.y : 0u;
+                        for (int j = 0; j < cnt; j++) c_vis += (__shfl_sync(0xffffffffu, vm, j) >> lane) & 1u;
+                    }
+                    root_pending = false;
+                    // accepted by the whole mask
+                    const unsigned am = __ballot_sync(0xffffffffu, outcome == OUT_ACCEPT);
+                    if (outcome == OUT_ACCEPT) sm.list[lc + __popc(am & lt)] = e;
+                    lc += __popc(am);
+                    // opened by the whole mask: children inherit the mask
+                    const unsigned om = __ballot_sync(0xffffffffu, outcome == OUT_OPEN);
+                    if (om) {
+                        int ch[8];
+                        int nl = 0, nn = 0;
+                        if (outcome == OUT_OPEN) {
+                            const int4 c0 = reinterpret_cast<const int4*>(P.child)[2 * (size_t)(e.x - N)], c1 = reinterpret_cast<const int4*>(P.child)[2 * (size_t)(e.x - N) + 1];
+                            ch[0] = c0.x; ch[1] = c0.y; ch[2] = c0.z; ch[3] = c0.w; ch[4] = c1.x; ch[5] = c1.y; ch[6] = c1.z; ch[7] = c1.w;
+#pragma unroll
+                            for (int c = 0; c < 8; c++) { nl += (ch[c] >= 0 && ch[c] < N); nn += (ch[c] >= N); }
+                        }
+                        const int il = warp_incl_scan(nl, lane), in_ = warp_incl_scan(nn, lane);
+                        const int tl = __shfl_sync(0xffffffffu, il, 31), tn = __shfl_sync(0xffffffffu, in_, 31);
+                        if (outcome == OUT_OPEN) {
+                            int pl = lc + il - nl, pn = sp + in_ - nn;
+#pragma unroll
+                            for (int c = 0; c < 8; c++) {
+                                if (ch[c] >= N) stack_put(pn++, make_int2(ch[c], e.y));
+                                else if (ch[c] >= 0) sm.list[pl++] = make_int2(ch[c], e.y);
+                            }
+                        }
+                        lc += tl; sp += tn;
+                    }
+                    // straddling nodes: exact per-lane test
+                    unsigned mm = __ballot_sync(0xffffffffu, outcome == OUT_MIXED);
+                    while (mm) {
+                        const int src = __ffs(mm) - 1;
+                        mm &= mm - 1;
+                        const int nidx = __shfl_sync(0xffffffffu, e.x, src);
+                        const unsigned nmask = (unsigned)__shfl_sync(0xffffffffu, e.y, src);
+                        const double nrad2 = __shfl_sync(0xffffffffu, rad2, src);
+                        const double4 q = P.src_pm[nidx];
+                        bool acc_l = false, open_l = false;
+                        if ((nmask >> lane) & 1u) {
+                            const double dx = q.x - tp.x, dy = q.y - tp.y, dz = q.z - tp.z;
+                            const double r2 = fma(dz, dz, fma(dy, dy, dx * dx));
+                            if (r2 != 0.0) {                                     // Node.cpp:274 (r == 0 -> return)
+                                const double lhs = r2 * theta2;
+                                if (fast_mac && lhs > nrad2 * (1.0 + 1e-13)) acc_l = true;
+                                else if (fast_mac && lhs < nrad2 * (1.0 - 1e-13)) open_l = true;
+                                else {                                           // the reference's own expression, Node.cpp:271,331-334
+                                    const double r2e = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+                                    const double rad = scalbn(R, -(int)P.ndepth[nidx - N]);
+                                    acc_l = __ddiv_rn(rad, __dsqrt_rn(r2e)) < theta;
+                                    open_l = !acc_l;
+                                    tot_exact++;
+                                }
+                            }
+                        }
+                        const unsigned a = __ballot_sync(0xffffffffu, acc_l), o = __ballot_sync(0xffffffffu, open_l);
+                        if (a) { if (lane == 0) sm.list[lc] = make_int2(nidx, (int)a); lc++; }
+                        if (o) {
+                            const int chl = lane < 8 ? P.child[(size_t)(nidx - N) * 8 + lane] : -1;
+                            const unsigned lm = __ballot_sync(0xffffffffu, chl >= 0 && chl < N), nm = __ballot_sync(0xffffffffu, chl >= N);
+                            if (chl >= N) stack_put(sp + __popc(nm & lt), make_int2(chl, (int)o));
+                            else if (chl >= 0) sm.list[lc + __popc(lm & lt)] = make_int2(chl, (int)o);
+                            lc += __popc(lm); sp += __popc(nm);
+                        }
+                    }
+                    __syncwarp();
+                }
+
+                // ------------------------------------------------ drain the interaction list
+                for (int base = 0; base < lc; base += 32) {
+                    const int cnt = min(32, lc - base);
+                    __syncwarp();
+                    if (lane < cnt) {
+                        int2 e = sm.list[base + lane];
+                        sm.stage[lane] = P.src_pm[e.x];
+                        if (SPH && P.src_flag[e.x]) sm.list[base + lane].x = e.x | GASBIT;
+                        const unsigned pc = __popc((unsigned)e.y);
+                        if (e.x < N) tot_leaf += pc; else tot_node += pc;
+                    }
+                    __syncwarp();
+#pragma unroll 4
+                    for (int j = 0; j < cnt; j++) {
+                        const int2 e = sm.list[base + j];
+                        const double4 q = sm.stage[j];
+                        const int src = e.x & IDXMASK;
+                        const bool bit = ((unsigned)e.y >> lane) & 1u;
+                        const double dx = q.x - tp.x, dy = q.y - tp.y, dz = q.z - tp.z;
+                        const double r2 = fma(dz, dz, fma(dy, dy, dx * dx));
+                        // skip: not mine, zero-mass leaf (Node.cpp:390), myself (Node.cpp:260), r == 0 (Node.cpp:274)
+                        const bool seen = bit && q.w != 0.0;
+                        const bool ok = seen && src != (int)t && r2 != 0.0;
+                        const double r2s = r2 * invR2, q2 = r2s + e02s;
+                        double w = rsqrt(r2s * q2 * q2);                         // 1 / (r (r^2 + e0^2)) in units of R
+                        const double f = ok ? GR3 * q.w * w : 0.0;
+                        ax = fma(f, dx, ax); ay = fma(f, dy, ay); az = fma(f, dz, az);
+                        if (COUNT) {
+                            if (src < N) { c_vis += seen; c_al += ok; } else c_an += ok;
+                        }
+                        if (SPH) {
+                            if (ok && tgas && (e.x & GASBIT)) {
+                                // gate r < 2 h_i (Node.cpp:316,368): guarded fast test, exact expression near the threshold
+                                bool pass;
+                                if (r2 < hh4 * (1.0 - 1e-13)) pass = true;
+                                else if (r2 > hh4 * (1.0 + 1e-13)) pass = false;
+                                else {
+                                    const double r2e = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+                                    pass = __dsqrt_rn(r2e) < __dmul_rn(h_t, 2.0);
+                                    tot_exact++;
+                                }
+                                if (pass) {
+                                    const double4 gv = P.src_gv[src];            // (mVel | particle velocity, gasMass)
+                                    const double r = sqrt(r2), qq = r / h_t;
+                                    double gs = 0.0;                             // kernel.cpp:28-34
+                                    if (qq < 1.0) gs = -3.0 * qq + 2.25 * qq * qq;
+                                    else if (qq < 2.0) { const double u = 2.0 - qq; gs = -0.75 * u * u; }
+                                    const double gfac = gs * inv_pi_h4 / r;
+                                    const double sx = -dx, sy = -dy, sz = -dz;   // d = x_i - COM (Node.cpp:116)
+                                    const double gx = sx * gfac, gy = sy * gfac, gz = sz * gfac;
+                                    const double vx = tvx - gv.x, vy = tvy - gv.y, vz = tvz - gv.z;
+                                    const double vd = vx * sx + vy * sy + vz * sz;
+                                    const double mu = h_t * vd / (r2 + 0.01 * (h_t * h_t));
+                                    const double MU = vd < 0.0 ? (-0.5 * cs * mu + mu * mu) : 0.0;     // Node.cpp:142-152
+                                    const double coef = -gv.w * (A2 + MU);                             // Node.cpp:127 + :154
+                                    const double fx = coef * gx, fy = coef * gy, fz = coef * gz;
+                                    dU += 0.5 * gv.w * (A2 + MU) * (vx * gx + vy * gy + vz * gz);      // Node.cpp:167
+                                    if (!(isnan(fx) || isnan(fy) || isnan(fz))) { ax += fx; ay += fy; az += fz; }   // Node.cpp:169
+                                    tot_sph++;
+                                    if (COUNT) c_sp++;
+                                }
+                            }
+                        }
+                    }
+                }
+                lc = 0;
+                if (sp == 0) break;
+            }
+        }
+
+        if (active) {
+            const uint32_t p = P.perm[t];
+            P.ax[p] = ax; P.ay[p] = ay; P.az[p] = az;                           // Tree.cpp:77 (acc = 0) + accumulated force
+            if (SPH && tgas && dU != 0.0) P.dUdt[p] += dU;
+            if (COUNT) { P.c_visits[t] = c_vis; P.c_accn[t] = c_an; P.c_accl[t] = c_al; P.c_sph[t] = c_sp; }
+            tot_visit += (unsigned long long)c_vis;
+        } else if (COUNT && inrange) {
+            P.c_visits[t] = 0; P.c_accn[t] = 0; P.c_accl[t] = 0; P.c_sph[t] = 0;
+        }
+    }
+
+    tot_node = warp_sum_u64(tot_node); tot_leaf = warp_sum_u64(tot_leaf); tot_sph = warp_sum_u64(tot_sph);
+    tot_visit = warp_sum_u64(tot_visit); tot_exact = warp_sum_u64(tot_exact); tot_spill = warp_sum_u64(tot_spill);
+    if (lane == 0) {
+        if (tot_node) atomicAdd(&P.s->c_node, tot_node);
+        if (tot_leaf) atomicAdd(&P.s->c_leaf, tot_leaf);
+        if (tot_sph) atomicAdd(&P.s->c_sph, tot_sph);
+        if (tot_visit) atomicAdd(&P.s->c_visits, tot_visit);
+        if (tot_exact) atomicAdd(&P.s->c_exact, tot_exact);
+        if (tot_spill) atomicAdd(&P.s->c_spill, tot_spill);
+    }
+}
+
+__global__ void k_walk_reset(AgbScalars* s)
+{
+    s->walk_next_group = 0; s->walk_overflow = 0;
+    s->c_interactions = 0; s->c_node = 0; s->c_leaf = 0; s->c_sph = 0; s->c_visits = 0; s->c_exact = 0; s->c_spill = 0;
+}
+
+__global__ void k_count_active(const double* __restrict__ s_next, int64_t t0, int64_t t1, double gt, AgbScalars* s)
+{
+    int64_t i = t0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned m = __ballot_sync(0xffffffffu, i < t1 && s_next[i] == gt);
+    if ((threadIdx.x & 31) == 0 && m) atomicAdd(&s->n_active, __popc(m));
+}
+
+__global__ void k_unpermute_i32(const uint32_t* __restrict__ perm, int64_t n, const int32_t* a, const int32_t* b, const int32_t* c, const int32_t* d_,
+                                int32_t* oa, int32_t* ob, int32_t* oc, int32_t* od)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t p = perm[i];
+    oa[p] = a[i]; ob[p] = b[i]; oc[p] = c[i]; od[p] = d_[i];
+}
+
+template <bool COUNT, bool SPH>
+void launch_walk(const WalkParams& P, int blocks, cudaStream_t st)
+{
+    static bool attr_set = false;
+    const int smem = (int)sizeof(WarpSmem) * WALK_WARPS;
+    if (!attr_set) { cudaFuncSetAttribute(k_walk<COUNT, SPH>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr_set = true; }
+    k_walk<COUNT, SPH><<<blocks, WALK_TPB, smem, st>>>(P);
+}
+
+} // namespace
+
+int agb_walk_blocks(int sm_count) { return sm_count * 2; }
+int agb_walk_warps_per_block() { return WALK_WARPS; }
+
+int agb_launch_walk(AgbDev& d, AgbScalars* s, double globalTime, double e0, double theta, int64_t t0, int64_t t1,
+                    bool counters, bool any_gas, int sm_count, cudaStream_t st, cudaEvent_t ev0, cudaEvent_t ev1)
+{
+    WalkParams P;
+    P.src_pm = d.src_pm; P.src_gv = d.src_gv; P.src_flag = d.src_flag; P.child = d.child; P.ndepth = d.ndepth;
+    P.s_h = d.s_h; P.s_rho = d.s_rho; P.s_P = d.s_P; P.s_next = d.s_next; P.s_type = d.s_type; P.perm = d.perm[d.cur];
+    P.ax = d.ax; P.ay = d.ay; P.az = d.az; P.dUdt = d.dUdt;
+    P.c_visits = d.c_visits; P.c_accn = d.c_accn; P.c_accl = d.c_accl; P.c_sph = d.c_sph;
+    P.spill = d.spill; P.spill_per_warp = d.spill_per_warp;
+    P.s = s; P.N = d.n; P.t0 = t0; P.t1 = t1;
+    P.ngroups = (unsigned)((t1 - t0 + 31) / 32);
+    P.theta = theta; P.e0 = e0; P.globalTime = globalTime;
+    int launches = 0;
+    k_walk_reset<<<1, 1, 0, st>>>(s); launches++;
+    if (t1 > t0) {
+        cudaMemsetAsync(&s->n_active, 0, sizeof(int32_t), st);
+        k_count_active<<<(int)((t1 - t0 + 255) / 256), 256, 0, st>>>(d.s_next, t0, t1, globalTime, s); launches++;
+        int blocks = (int)std::min<int64_t>((int64_t)agb_walk_blocks(sm_count), ((int64_t)P.ngroups + WALK_WARPS - 1) / WALK_WARPS);
+        if (blocks * WALK_WARPS > d.spill_warps) blocks = d.spill_warps / WALK_WARPS;
+        if (ev0) cudaEventRecord(ev0, st);
+        if (counters) { if (any_gas) launch_walk<true, true>(P, blocks, st); else launch_walk<true, false>(P, blocks, st); }
+        else { if (any_gas) launch_walk<false, true>(P, blocks, st); else launch_walk<false, false>(P, blocks, st); }
+        if (ev1) cudaEventRecord(ev1, st);
+        launches++;
+    }
+    return launches;
+}
+
+int agb_launch_unpermute_counters(AgbDev& d, int32_t* v, int32_t* an, int32_t* al, int32_t* sp, cudaStream_t st)
+{
+    k_unpermute_i32<<<(int)((d.n + 255) / 256), 256, 0, st>>>(d.perm[d.cur], d.n, d.c_visits, d.c_accn, d.c_accl, d.c_sph, v, an, al, sp);
+    return 1;
+}

@@ -1,7 +1,7 @@
 """Synthetic initial conditions for the benchmark / parity configurations of SURVEY.md §8(d).
 
 All SI units (the reference path works in SI: |x| ~ 1e20..1e25 m, m ~ 1e35 kg).  The generator is
-numpy PCG64 with a fixed seed; particle order is generator order (no shuffle) so the oracle and the
+numpy PCG64 with a fixed seed; particle order is generator order (no shuffle) so the CPU checker and the
 GPU path see identical arrays.  Particle fields follow the reference's record
 (Physics/Particle.h:18-57): type 1 = star, 2 = gas, 3 = dark matter; mu defaults to 0.58.
 """

@@ -1,0 +1,144 @@
+/* agb200.h — C ABI of the B200-native force path for AstroGenesis2.0.
+ *
+ * This library replaces, as a drop-in, the per-step force path that the reference keeps behind its
+ * C++ class `Tree` (simulation/src/Physics/Tree/Tree.h:13-27) and that its driver calls in exactly
+ * this order once at start-up and once per step (Physics/Simulation.cpp:121-139 and :276-285):
+ *
+ *     Tree* t = new Tree(sim);  t->buildTree();       // driver then reads t->root->radius
+ *     t->calcVisualDensity();   t->calcGasDensity();  t->calculateForces();   delete t;
+ *
+ * The reference has no plugin/FFI layer of its own; the entry points below are what a binding of
+ * that call surface needs (INTEGRATION.md shows the `Tree`-shaped C++ adaptor and the ctypes stub).
+ * Plain pointers and sizes only; no C++/torch types; nothing throws across this boundary.  Every
+ * function returns an agb_status; unlike the reference (which prints to std::cerr and continues,
+ * e.g. Tree.cpp:70-74) problems are reported as codes.  One host thread per context.
+ *
+ * There is no CPU fallback: every entry point needs a CUDA device of compute capability 10.x and
+ * fails with AGB_ERR_NO_DEVICE otherwise.
+ */
+#ifndef AGB200_H
+#define AGB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct agb_ctx agb_ctx;
+
+typedef enum {
+    AGB_OK = 0,
+    AGB_ERR_NO_DEVICE = 1,      /* no usable sm_100 device / CUDA runtime failure at create      */
+    AGB_ERR_CUDA = 2,           /* a CUDA call or kernel failed; agb_last_error() has the text   */
+    AGB_ERR_INVALID = 3,        /* bad argument or call order (e.g. forces before build_tree)    */
+    AGB_ERR_DEPTH = 4,          /* two in-tree particles share all 42 octree levels (coincident  */
+                                /* points: the reference recurses without bound, Node.cpp:618-666) */
+    AGB_ERR_UNSUPPORTED = 5,    /* parameter range the parity path does not cover (see forces)   */
+    AGB_ERR_NOMEM = 6
+} agb_status;
+
+typedef enum { AGB_MEM_HOST = 0, AGB_MEM_DEVICE = 1 } agb_memspace;
+
+/* Structure-of-arrays view of the reference's particle record (Physics/Particle.h:18-57).
+ * Required: x y z mass type.  Optional (NULL allowed): vx vy vz U (0), next_time (0), mu (0.58),
+ * and the carried state rho P T h dUdt ax ay az (0) which the reference keeps inside Particle
+ * between steps: orphan gas keeps rho/P/T (Node.cpp:749-793), dUdt is accumulated, never reset, by
+ * the path (Node.cpp:167; TimeIntegration.cpp:37-40 resets it), and inactive particles keep acc
+ * (Tree.cpp:75-80).  type: 1 = star, 2 = gas, 3 = dark matter. */
+typedef struct {
+    int64_t n;
+    const double *x, *y, *z;
+    const double *vx, *vy, *vz;
+    const double *mass;
+    const double *U;
+    const double *next_time;        /* Particle::nextIntegrationTime */
+    const double *mu;
+    const uint8_t *type;
+    const double *rho, *P, *T, *h, *dUdt;
+    const double *ax, *ay, *az;
+} agb_particles;
+
+/* Results in the caller's particle order (the fields the path writes into Particle). NULL = skip. */
+typedef struct {
+    double *ax, *ay, *az;           /* Particle::acc           */
+    double *dUdt;
+    double *h, *rho, *P, *T;
+    double *visualDensity;
+} agb_results;
+
+/* Field offsets (bytes) inside the caller's array-of-structs particle record, so the reference's
+ * own `std::vector<Particle*>` (Simulation.h:70; sizeof(Particle) = 264) can be handed over as is.
+ * Vectors are 3 consecutive doubles. A negative offset marks an absent optional field. */
+typedef struct {
+    int64_t position, velocity, acc, mass, type, U, next_time, mu, rho, P, T, h, dUdt, visualDensity;
+} agb_aos_layout;
+
+/* Whole-step counters of the last agb_forces() call. */
+typedef struct {
+    int64_t n_particles, n_in_tree, n_outliers, n_nodes, n_active;
+    int64_t max_depth;
+    int64_t edge_dropped;           /* particles that fail a cell-bounds test below the root (FP edge, Node.cpp:606-612); kept in tree, reported */
+    int64_t interactions;           /* accepted (target, node) + (target, leaf) gravity pairs       */
+    int64_t node_interactions, leaf_interactions, sph_interactions;
+    int64_t node_visits;            /* calls of Node::calculateGravityForce the reference would make */
+    int64_t mac_exact_fallbacks;    /* MAC / SPH-gate decisions taken on the exact FP64 slow path  */
+    int64_t groups, gas_groups, gas_orphans;
+} agb_counters;
+
+/* -------- lifetime: `new Tree(sim)` / `delete tree`, but persistent across steps (pooled memory) */
+/* compat_cores = the reference's omp_get_max_threads(), which decides where bulk insertion hands
+ * over to one-by-one insertion (Node.cpp:420) and hence which density groups see every particle
+ * twice; <= 0 selects 1. */
+int agb_create(agb_ctx** out, int device, int compat_cores);
+int agb_destroy(agb_ctx* ctx);
+
+/* -------- particle hand-over (replaces the path's direct reads of Simulation::particles) */
+int agb_set_particles(agb_ctx* ctx, const agb_particles* p, int memspace);
+int agb_set_particles_aos(agb_ctx* ctx, void* const* particles, int64_t n, const agb_aos_layout* layout);
+
+/* -------- the four calls of the reference's Tree (same order, same meaning) */
+int agb_build_tree(agb_ctx* ctx, double* root_radius);                  /* Tree::buildTree, Tree.cpp:24-55; *root_radius = root->radius */
+int agb_visual_density(agb_ctx* ctx, double visual_density_radius);     /* Tree::calcVisualDensity, Tree.cpp:152-176 */
+int agb_gas_density(agb_ctx* ctx, double mass_in_h);                    /* Tree::calcGasDensity, Tree.cpp:119-150 */
+int agb_forces(agb_ctx* ctx, double global_time, double e0, double theta);   /* Tree::calculateForces, Tree.cpp:57-83 */
+/* Multi-GPU variant: walk only the `part`-th of `nparts` contiguous slices of the tree-ordered
+ * targets (every GPU holds the same gathered particles and builds the same tree). */
+int agb_forces_slice(agb_ctx* ctx, double global_time, double e0, double theta, int part, int nparts);
+
+/* -------- results (replaces the path's direct writes into Particle) */
+int agb_get_results(agb_ctx* ctx, const agb_results* r, int memspace);
+int agb_get_results_aos(agb_ctx* ctx, void* const* particles, int64_t n, const agb_aos_layout* layout);
+int agb_get_counters(agb_ctx* ctx, agb_counters* c);
+
+/* -------- options */
+typedef enum {
+    AGB_OPT_TARGET_COUNTERS = 1     /* 1: also record per-target visit / accept / SPH counts (parity tests) */
+} agb_option;
+int agb_set_option(agb_ctx* ctx, int option, int64_t value);
+
+/* -------- introspection used by the parity tests (tree topology, node table, per-target counters) */
+/* caller order; leafdepth = -1 for particles outside the root cube; key = octant path root->leaf,
+ * 3 bits per level, level l < 21 at key_hi >> (60-3l), else key_lo >> (60-3(l-21)). */
+int agb_get_tree_particles(agb_ctx* ctx, int32_t* leafdepth, uint64_t* key_hi, uint64_t* key_lo);
+int agb_get_node_count(agb_ctx* ctx, int64_t* n_internal);
+int agb_get_nodes(agb_ctx* ctx, int32_t* depth, int64_t* count, int32_t* duplicated, uint64_t* key_hi, uint64_t* key_lo,
+                  double* mass, double* comx, double* comy, double* comz, double* gas_mass, double* mvx, double* mvy, double* mvz);
+int agb_get_target_counters(agb_ctx* ctx, int32_t* visits, int32_t* acc_nodes, int32_t* acc_leaves, int32_t* sph);
+
+/* Device time (ms, CUDA events on the context's stream) of the last call of each phase:
+ * [0] build_tree [1] visual_density [2] gas_density [3] forces (walk kernel only) [4] forces (whole call). */
+int agb_get_phase_ms(agb_ctx* ctx, double ms[5]);
+/* The CUDA stream (cudaStream_t) all work of this context is issued on. */
+int agb_get_stream(agb_ctx* ctx, void** stream);
+/* Number of kernels this context launched since creation. */
+int agb_get_launch_count(agb_ctx* ctx, int64_t* launches);
+
+const char* agb_strerror(int status);
+const char* agb_last_error(agb_ctx* ctx);
+const char* agb_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AGB200_H */
