@@ -17,7 +17,7 @@ EXPORTS = [
     "agb_create", "agb_destroy", "agb_set_particles", "agb_set_particles_aos", "agb_build_tree", "agb_visual_density",
     "agb_gas_density", "agb_forces", "agb_forces_slice", "agb_get_results", "agb_get_results_aos", "agb_get_counters",
     "agb_set_option", "agb_get_tree_particles", "agb_get_node_count", "agb_get_nodes", "agb_get_target_counters",
-    "agb_get_phase_ms", "agb_get_stream", "agb_get_launch_count", "agb_strerror", "agb_last_error", "agb_version",
+    "agb_get_phase_ms", "agb_get_stream", "agb_get_launch_count", "agb_microbench", "agb_strerror", "agb_last_error", "agb_version",
 ]
 
 
@@ -87,6 +87,7 @@ def load(build_if_needed=True):
     lib.agb_get_phase_ms.argtypes = [vp, _pd]
     lib.agb_get_stream.argtypes = [vp, C.POINTER(vp)]
     lib.agb_get_launch_count.argtypes = [vp, C.POINTER(C.c_int64)]
+    lib.agb_microbench.argtypes = [vp, C.c_int, _pd]
     lib.agb_strerror.restype = C.c_char_p
     lib.agb_strerror.argtypes = [C.c_int]
     lib.agb_last_error.restype = C.c_char_p

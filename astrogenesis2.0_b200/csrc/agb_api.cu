@@ -18,7 +18,8 @@ struct agb_ctx {
     AgbDev d;
     AgbScalars* s = nullptr;            // device
     AgbScalars hs;                      // host mirror (tail only is valid)
-    std::vector<void*> owned_inputs;    // device copies of caller-order inputs
+    double* in_d[10] = {};             // pooled device copies of caller-order inputs (x y z vx vy vz mass U next mu)
+    uint8_t* in_type = nullptr;
     bool bound = false, have_particles = false, built = false, dens_done = false, forces_done = false;
     bool target_counters = false, counters_valid = false, vis_timed = false, gas_timed = false;
     double phase_ms[5] = {0, 0, 0, 0, 0};
@@ -48,8 +49,8 @@ template <class T> void dfree(T*& p) { if (p) cudaFree((void*)p); p = nullptr; }
 void free_pool(agb_ctx* c)
 {
     AgbDev& d = c->d;
-    for (void* p : c->owned_inputs) cudaFree(p);
-    c->owned_inputs.clear();
+    for (auto& q : c->in_d) dfree(q);
+    dfree(c->in_type);
     dfree(d.ax); dfree(d.ay); dfree(d.az); dfree(d.dUdt); dfree(d.h); dfree(d.rho); dfree(d.P); dfree(d.T); dfree(d.vis);
     for (int i = 0; i < 2; i++) { dfree(d.khi[i]); dfree(d.klo[i]); dfree(d.perm[i]); }
     dfree(d.src_pm); dfree(d.src_gv); dfree(d.src_flag);
@@ -79,6 +80,8 @@ int ensure_pool(agb_ctx* c, int64_t n)
     CK(dalloc(d.child, 8 * cap)); CK(dalloc(d.nfirst, cap)); CK(dalloc(d.nlast, cap)); CK(dalloc(d.nparent, cap)); CK(dalloc(d.arrived, cap)); CK(dalloc(d.ndepth, cap));
     CK(dalloc(d.nmark, cap)); CK(dalloc(d.ndup, cap)); CK(dalloc(d.leafmark, cap)); CK(dalloc(d.mom_pm, cap)); CK(dalloc(d.mom_gv, cap)); CK(dalloc(d.grouplist, cap));
     CK(dalloc(d.dist, cap));
+    for (auto& q : c->in_d) CK(dalloc(q, cap));
+    CK(dalloc(c->in_type, cap));
     CK(dalloc(d.blockhist, 256 * ((cap + 2047) / 2048 + 1)));
     CK(dalloc(d.scanblk, (cap + 2047) / 2048 + 1));
     d.cap = (int64_t)cap;
@@ -109,14 +112,11 @@ int put_array(agb_ctx* c, double* dst, const double* src, int64_t n, int memspac
     return AGB_OK;
 }
 
-int own_input(agb_ctx* c, const double*& slot, const double* src, int64_t n)
+int own_input(agb_ctx* c, const double*& slot, int which, const double* src, int64_t n)
 {
     if (!src) { slot = nullptr; return AGB_OK; }
-    double* p = nullptr;
-    CK(dalloc(p, (size_t)n));
-    c->owned_inputs.push_back(p);
-    CK(cudaMemcpyAsync(p, src, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, c->st));
-    slot = p;
+    CK(cudaMemcpyAsync(c->in_d[which], src, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, c->st));
+    slot = c->in_d[which];
     return AGB_OK;
 }
 
@@ -199,23 +199,18 @@ int agb_set_particles(agb_ctx* c, const agb_particles* p, int memspace)
     if (rc) return rc;
     AgbDev& d = c->d;
     d.n = n;
-    for (void* q : c->owned_inputs) cudaFree(q);
-    c->owned_inputs.clear();
     if (memspace == AGB_MEM_DEVICE) {
         // zero-copy: the caller's device arrays are read in place (they must stay valid until the next set_particles)
         d.x = p->x; d.y = p->y; d.z = p->z; d.vx = p->vx; d.vy = p->vy; d.vz = p->vz; d.mass = p->mass; d.U = p->U; d.next = p->next_time; d.mu = p->mu;
         d.type = p->type;
         c->bound = true;
     } else {
-        if ((rc = own_input(c, d.x, p->x, n)) || (rc = own_input(c, d.y, p->y, n)) || (rc = own_input(c, d.z, p->z, n)) ||
-            (rc = own_input(c, d.vx, p->vx, n)) || (rc = own_input(c, d.vy, p->vy, n)) || (rc = own_input(c, d.vz, p->vz, n)) ||
-            (rc = own_input(c, d.mass, p->mass, n)) || (rc = own_input(c, d.U, p->U, n)) || (rc = own_input(c, d.next, p->next_time, n)) ||
-            (rc = own_input(c, d.mu, p->mu, n))) return rc;
-        uint8_t* t = nullptr;
-        CK(dalloc(t, (size_t)n));
-        c->owned_inputs.push_back(t);
-        CK(cudaMemcpyAsync(t, p->type, (size_t)n, cudaMemcpyHostToDevice, c->st));
-        d.type = t;
+        if ((rc = own_input(c, d.x, 0, p->x, n)) || (rc = own_input(c, d.y, 1, p->y, n)) || (rc = own_input(c, d.z, 2, p->z, n)) ||
+            (rc = own_input(c, d.vx, 3, p->vx, n)) || (rc = own_input(c, d.vy, 4, p->vy, n)) || (rc = own_input(c, d.vz, 5, p->vz, n)) ||
+            (rc = own_input(c, d.mass, 6, p->mass, n)) || (rc = own_input(c, d.U, 7, p->U, n)) || (rc = own_input(c, d.next, 8, p->next_time, n)) ||
+            (rc = own_input(c, d.mu, 9, p->mu, n))) return rc;
+        CK(cudaMemcpyAsync(c->in_type, p->type, (size_t)n, cudaMemcpyHostToDevice, c->st));
+        d.type = c->in_type;
         c->bound = false;
     }
     if ((rc = put_array(c, d.ax, p->ax, n, memspace)) || (rc = put_array(c, d.ay, p->ay, n, memspace)) || (rc = put_array(c, d.az, p->az, n, memspace)) ||
@@ -354,7 +349,7 @@ int agb_get_counters(agb_ctx* c, agb_counters* o)
     o->n_particles = c->d.n; o->n_in_tree = h.n_in_tree; o->n_outliers = h.n_outliers; o->n_nodes = h.n_nodes; o->n_active = h.n_active;
     o->max_depth = h.max_depth; o->edge_dropped = h.edge_dropped;
     o->node_interactions = (int64_t)h.c_node; o->leaf_interactions = (int64_t)h.c_leaf; o->interactions = (int64_t)(h.c_node + h.c_leaf);
-    o->sph_interactions = (int64_t)h.c_sph; o->node_visits = (int64_t)h.c_visits; o->mac_exact_fallbacks = (int64_t)h.c_exact;
+    o->sph_interactions = (int64_t)h.c_sph; o->node_visits = c->counters_valid ? (int64_t)h.c_visits : -1; o->mac_exact_fallbacks = (int64_t)h.c_exact;
     o->groups = (c->d.n + 31) / 32; o->gas_groups = h.n_gas_groups; o->gas_orphans = h.n_gas_orphans;
     return AGB_OK;
 }
@@ -495,6 +490,17 @@ int agb_get_stream(agb_ctx* c, void** stream)
 {
     if (!c || !stream) return AGB_ERR_INVALID;
     *stream = (void*)c->st;
+    return AGB_OK;
+}
+
+int agb_microbench(agb_ctx* c, int kind, double* result)
+{
+    if (!c || !result || kind < 0 || kind > 2) return AGB_ERR_INVALID;
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->st));
+    *result = 0;
+    agb_launch_microbench(kind, c->sm_count, c->st, result);
+    CK(cudaGetLastError());
     return AGB_OK;
 }
 

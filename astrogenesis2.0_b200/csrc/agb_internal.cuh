@@ -80,6 +80,7 @@ int agb_launch_gas_density(AgbDev& d, AgbScalars* s, double massInH, cudaStream_
 int agb_launch_walk(AgbDev& d, AgbScalars* s, double globalTime, double e0, double theta, int64_t t0, int64_t t1,
                     bool counters, bool any_gas, int sm_count, cudaStream_t st, cudaEvent_t ev0, cudaEvent_t ev1);
 int agb_launch_dump_tree(AgbDev& d, AgbScalars* s, int32_t* leafdepth, uint64_t* khi, uint64_t* klo, cudaStream_t st);
+int agb_launch_microbench(int kind, int sm_count, cudaStream_t st, double* result);
 int agb_launch_unpermute_counters(AgbDev& d, int32_t* v, int32_t* an, int32_t* al, int32_t* sp, cudaStream_t st);
 
 // ---- small device helpers ----

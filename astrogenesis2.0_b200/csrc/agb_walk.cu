@@ -248,9 +248,14 @@ __global__ void __launch_bounds__(WALK_TPB, 2) k_walk(const WalkParams P)
                     __syncwarp();
                     if (lane < cnt) {
                         int2 e = sm.list[base + lane];
-                        sm.stage[lane] = P.src_pm[e.x];
+                        const double4 q = P.src_pm[e.x];
+                        sm.stage[lane] = q;
                         if (SPH && P.src_flag[e.x]) sm.list[base + lane].x = e.x | GASBIT;
-                        const unsigned pc = __popc((unsigned)e.y);
+                        // accepted pairs of this entry: lanes in the mask, minus the target's own leaf, none for a massless leaf
+                        unsigned m = (unsigned)e.y;
+                        const int64_t self_lane = (int64_t)e.x - (P.t0 + (int64_t)g * 32);
+                        if (e.x < N && self_lane >= 0 && self_lane < 32) m &= ~(1u << self_lane);
+                        const unsigned pc = q.w != 0.0 ? __popc(m) : 0u;
                         if (e.x < N) tot_leaf += pc; else tot_node += pc;
                     }
                     __syncwarp();
@@ -368,6 +373,24 @@ void launch_walk(const WalkParams& P, int blocks, cudaStream_t st)
 
 } // namespace
 
+// ---------------------------------------------------------------- roofline denominators, measured on the box
+// kind 0: FP64 FMA chains, 1: FP32 FMA chains (results in TFLOP/s, FMA = 2 flop); kind 2: device copy (GB/s, read+write)
+template <class T>
+__global__ void __launch_bounds__(256) k_fma_peak(T* out, int iters, T a, T b)
+{
+    T x0 = (T)threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+    for (int i = 0; i < iters; i++) {
+        x0 = x0 * a + b; x1 = x1 * a + b; x2 = x2 * a + b; x3 = x3 * a + b;
+        x4 = x4 * a + b; x5 = x5 * a + b; x6 = x6 * a + b; x7 = x7 * a + b;
+    }
+    T r = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
+    if (r == (T)123456.789) out[0] = r;
+}
+__global__ void __launch_bounds__(256) k_copy_peak(const double2* __restrict__ in, double2* __restrict__ out, size_t n)
+{
+    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (size_t)gridDim.x * 256) out[i] = in[i];
+}
+
 int agb_walk_blocks(int sm_count) { return sm_count * 2; }
 int agb_walk_warps_per_block() { return WALK_WARPS; }
 
@@ -397,6 +420,43 @@ int agb_launch_walk(AgbDev& d, AgbScalars* s, double globalTime, double e0, doub
         launches++;
     }
     return launches;
+}
+
+int agb_launch_microbench(int kind, int sm_count, cudaStream_t st, double* result)
+{
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    float best = 1e30f;
+    double work = 0;
+    if (kind == 0 || kind == 1) {
+        void* out = nullptr; cudaMalloc(&out, 64);
+        const int blocks = sm_count * 8, iters = 1 << 14;
+        for (int rep = 0; rep < 5; rep++) {
+            cudaEventRecord(e0, st);
+            if (kind == 0) k_fma_peak<double><<<blocks, 256, 0, st>>>((double*)out, iters, 1.0000001, 1e-9);
+            else k_fma_peak<float><<<blocks, 256, 0, st>>>((float*)out, iters, 1.0000001f, 1e-9f);
+            cudaEventRecord(e1, st); cudaEventSynchronize(e1);
+            float ms; cudaEventElapsedTime(&ms, e0, e1); if (rep > 0) best = std::min(best, ms);
+        }
+        work = 2.0 * 8.0 * iters * 256.0 * blocks;                 // flop
+        *result = work / (best * 1e-3) / 1e12;
+        cudaFree(out);
+    } else {
+        const size_t n = (size_t)1 << 26;                            // 1 GiB in + 1 GiB out
+        double2 *a = nullptr, *b = nullptr;
+        if (cudaMalloc((void**)&a, n * 16) != cudaSuccess || cudaMalloc((void**)&b, n * 16) != cudaSuccess) { cudaFree(a); return 0; }
+        cudaMemsetAsync(a, 0, n * 16, st);
+        for (int rep = 0; rep < 5; rep++) {
+            cudaEventRecord(e0, st);
+            k_copy_peak<<<sm_count * 16, 256, 0, st>>>(a, b, n);
+            cudaEventRecord(e1, st); cudaEventSynchronize(e1);
+            float ms; cudaEventElapsedTime(&ms, e0, e1); if (rep > 0) best = std::min(best, ms);
+        }
+        *result = 2.0 * n * 16 / (best * 1e-3) / 1e9;
+        cudaFree(a); cudaFree(b);
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    return 5;
 }
 
 int agb_launch_unpermute_counters(AgbDev& d, int32_t* v, int32_t* an, int32_t* al, int32_t* sp, cudaStream_t st)

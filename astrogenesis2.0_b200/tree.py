@@ -154,6 +154,12 @@ class Context:
         capi.check(self.h, self.lib.agb_get_stream(self.h, C.byref(s)))
         return s.value or 0
 
+    def microbench(self, kind):
+        """0: FP64 FMA TFLOP/s, 1: FP32 FMA TFLOP/s, 2: HBM copy GB/s (measured, not part of the path)."""
+        v = C.c_double()
+        capi.check(self.h, self.lib.agb_microbench(self.h, int(kind), C.byref(v)))
+        return v.value
+
     def launch_count(self):
         v = C.c_int64()
         capi.check(self.h, self.lib.agb_get_launch_count(self.h, C.byref(v)))

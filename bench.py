@@ -1,0 +1,376 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the force hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload NAME] [--impl reference]
+
+A step = one pass of the path over one synthetic particle set: build_tree -> visual_density ->
+gas_density -> forces (the reference's Simulation::run step, Simulation.cpp:276-285), all particles
+active.  `value` = particle-updates/s with the particles already resident in HBM; `e2e` = the same
+through the reference-facing Tree API with pinned HOST arrays (H2D of the particles and D2H of the
+results inside the timed region).  N > 1 (torchrun): every rank owns 1/N of the particles, the
+positions are all-gathered over NCCL each step, every GPU builds the same tree and walks its own
+slice of the tree-ordered targets (strong scaling).
+
+--impl reference times the reference's own CPU implementation (oracle/_ref/ag_ref_omp, compiled in
+place from the unmodified sources; all host threads) on the same workload; falls back to the
+single-threaded C oracle port when that binary is absent.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "particle-updates/s"
+WORKLOADS = {
+    # name: (generator, n, e0, neighbours for massInH, description)
+    "plummer1m": ("plummer", 1_000_000, 1e18, 0, "C1 Plummer sphere 1M, gravity-only, theta=0.5"),
+    "disk4m": ("disk", 4_000_000, 1e18, 64, "C2 disk galaxy 4M (halo+disk+bulge, 25% of disk gas)"),
+    "gas16m": ("gasdisk", 16_000_000, 1e18, 64, "C3 gas-rich disk 16M (50% of disk gas)"),
+    "merger64m": ("merger", 64_000_000, 1e18, 64, "C4 merger 64M"),
+    "plummer100k": ("plummer", 100_000, 1e18, 0, "small Plummer (debug)"),
+    "disk400k": ("disk", 400_000, 1e18, 64, "small disk (debug)"),
+}
+THETA = 0.5
+
+
+def make_particles(pkg, name, n_override=None):
+    gen, n, e0, nb, desc = WORKLOADS[name]
+    n = n_override or n
+    ics = pkg.ics
+    if gen == "plummer":
+        p = ics.plummer(n, seed=1234)
+    elif gen == "disk":
+        p = ics.disk_galaxy(n, seed=1234, gas_disk_fraction=0.25)
+    elif gen == "gasdisk":
+        p = ics.disk_galaxy(n, seed=1234, gas_disk_fraction=0.5)
+    else:
+        p = ics.merger(n, seed=1234)
+    mh = ics.gas_mass_in_h(p, nb) if nb else 1e40
+    return p, e0, mh, desc
+
+
+# ------------------------------------------------------------------ clocks sampling
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index=0):
+        self.rows = []
+        self.proc = None
+        self.index = index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:  # noqa: BLE001
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------ reference / CPU baseline
+def cpu_reference_run(p, e0, mh, reps, tmpdir):
+    """Times the reference path on host cores. Returns (seconds per step list, kind, cores, phases)."""
+    from oracle import agio, oracle
+    n = len(p["x"])
+    if os.access(oracle.REF_OMP_BIN, os.X_OK):
+        path = os.path.join(tmpdir, "bench.agp")
+        agio.write_agp(path, p)
+        out = subprocess.run([oracle.REF_OMP_BIN, "time", path, repr(THETA), repr(e0), repr(mh), "0", str(reps)],
+                             stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, check=True).stdout
+        rows = [json.loads(l) for l in out.splitlines() if l.startswith("{")]
+        secs = [r["build"] + r["visual"] + r["gas_density"] + r["forces"] for r in rows]
+        return secs, "reference", os.cpu_count(), rows
+    secs, rows = [], []
+    for _ in range(reps):
+        ph = {}
+        oracle.run(p, THETA, e0, mh, 0.0, cores=1, nodes=False, counters=False, phases=ph)
+        secs.append(sum(ph.values())); rows.append(ph)
+    return secs, "port", 1, rows
+
+
+def sample_size_for_cpu(n_full, steps, budget_s=25.0):
+    # ~1e-5 s per particle-step on 8 cores for the reference; keep the whole leg near budget_s
+    cores = os.cpu_count() or 8
+    per = 1.0e-5 * 8.0 / max(1, min(cores, 32))
+    n = int(budget_s / max(1, steps) / per)
+    return max(20_000, min(n_full, n))
+
+
+def run_reference_arm(args, pkg):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    name = args.workload or "plummer1m"
+    n_full = WORKLOADS[name][1]
+    total = args.steps + args.warmup
+    n = sample_size_for_cpu(n_full, total, budget_s=150.0)
+    p, e0, mh, desc = make_particles(pkg, name, n)
+    with tempfile.TemporaryDirectory() as d:
+        secs, kind, cores, rows = cpu_reference_run(p, e0, mh, total, d)
+    timed = secs[args.warmup:]
+    t = float(np.mean(timed))
+    value = n / t
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "particles/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": name, "description": desc, "n_particles": n_full, "theta": THETA, "e0": e0},
+        "cpu_baseline": {"value": value, "unit": "particles/s", "cores": cores, "kind": kind,
+                         "sample": "%d of %d particles of %s, %d timed steps, phases build+visual+gas_density+forces" % (n, n_full, name, len(timed))},
+        "e2e": {"value": value, "unit": "particles/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "phases_s": rows[-1],
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------ GPU arm
+def run_gpu_arm(args, pkg):
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200: there is no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    name = args.workload or "plummer1m"
+    p, e0, mh, desc = make_particles(pkg, name)
+    n = len(p["x"])
+    any_gas = bool((p["type"] == 2).any())
+    ctx = pkg.Context(local, 8)
+    stream = torch.cuda.ExternalStream(ctx.stream(), device=dev)
+
+    f8 = ["x", "y", "z", "vx", "vy", "vz", "mass", "U", "next_time", "mu"] if any_gas else ["x", "y", "z", "mass"]
+    # rank-local shard of the particle arrays (what a distributed driver would own and integrate)
+    lo, hi = n * rank // world, n * (rank + 1) // world
+    shard = {k: torch.from_numpy(np.ascontiguousarray(p[k][lo:hi])).to(dev) for k in f8}
+    shard["type"] = torch.from_numpy(np.ascontiguousarray(p["type"][lo:hi])).to(dev)
+    full = {k: (torch.empty(n, dtype=v.dtype, device=dev) if world > 1 else v) for k, v in shard.items()}
+    counts = [n * (r + 1) // world - n * r // world for r in range(world)]
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)      # > 126 MB L2
+
+    def gather():
+        if world == 1:
+            return
+        for k in full:
+            outs = list(torch.split(full[k], counts))
+            dist.all_gather(outs, shard[k])
+
+    def step():
+        gather()
+        if world > 1:
+            stream.wait_stream(torch.cuda.current_stream())
+        ptrs = {k: full[k].data_ptr() for k in full}
+        ctx.set_particles_device(ptrs, n)
+        R = ctx.build_tree()
+        ctx.visual_density(R / 100000)
+        ctx.gas_density(mh)
+        ctx.forces(0.0, e0, THETA, rank, world)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        flush.fill_(1)
+        step()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = ctx.launch_count()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    walk_ms, build_ms, inter = [], [], 0
+    barrier()
+    t_wall0 = time.perf_counter()
+    for i in range(args.steps):
+        flush.fill_(i & 0xff)                      # L2 flush between timed iterations (outside the timed interval)
+        barrier()
+        ev[i][0].record(stream if world == 1 else torch.cuda.current_stream())
+        step()
+        ev[i][1].record(stream)
+        ev[i][1].synchronize()
+        ph = ctx.phase_ms()
+        walk_ms.append(ph["walk_kernel"]); build_ms.append(ph["build"])
+        inter = ctx.counters()["interactions"]
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    step_ms = [a.elapsed_time(b) for a, b in ev]
+    launches = ctx.launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    tot = torch.tensor([sum(step_ms), float(inter), sum(walk_ms)], dtype=torch.float64, device=dev)
+    if world > 1:
+        mx = tot.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        sm = tot.clone(); dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        total_ms, walk_total_ms, inter_all = float(mx[0]), float(mx[2]), float(sm[1])
+    else:
+        total_ms, walk_total_ms, inter_all = float(tot[0]), float(tot[2]), float(inter)
+    ms_per_step = total_ms / args.steps
+    value = n / (ms_per_step * 1e-3)
+
+    # ---- end-to-end through the Tree API with pinned host arrays (N GPUs: every rank uploads its shard, results of its slice come back)
+    e2e = None
+    if world == 1:
+        host = {}
+        for k in f8 + ["type"]:
+            t = torch.from_numpy(np.ascontiguousarray(p[k])).pin_memory()
+            host[k] = t.numpy()
+        sim = pkg.Simulation(host, THETA, e0, mh, 0.0)
+        tree = pkg.Tree(sim, ctx)
+        outn = ("ax", "ay", "az", "visualDensity") + (("dUdt", "h", "rho", "P", "T") if any_gas else ())
+        pinned_out = {k: torch.empty(n, dtype=torch.float64).pin_memory() for k in outn}
+
+        def e2e_step():
+            ctx.set_particles(host)
+            R = ctx.build_tree()
+            ctx.visual_density(R / 100000)
+            ctx.gas_density(mh)
+            ctx.forces(0.0, e0, THETA)
+            r = pkg.capi.Results()
+            for k in outn:
+                setattr(r, k, pkg.capi.C.cast(pkg.capi.C.c_void_p(pinned_out[k].data_ptr()), pkg.capi.C.POINTER(pkg.capi.C.c_double)))
+            pkg.capi.check(ctx.h, ctx.lib.agb_get_results(ctx.h, pkg.capi.C.byref(r), pkg.capi.AGB_MEM_HOST))
+        for _ in range(max(1, args.warmup)):
+            e2e_step()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            e2e_step()
+        torch.cuda.synchronize()
+        te = (time.perf_counter() - t0) / args.steps
+        h2d = sum(host[k].nbytes for k in host) + 0
+        d2h = sum(v.numel() * 8 for v in pinned_out.values())
+        e2e = {"value": n / te, "unit": "particles/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "ms_per_step": te * 1e3}
+    else:
+        # multi-GPU e2e: host shard -> device shard (H2D), gather, step, D2H of the 3 acc arrays
+        host = {k: torch.from_numpy(np.ascontiguousarray(p[k][lo:hi])).pin_memory() for k in f8 + ["type"]}
+        out_d = {k: torch.empty(n, dtype=torch.float64, device=dev) for k in ("ax", "ay", "az")}
+        out_h = {k: torch.empty(n, dtype=torch.float64).pin_memory() for k in out_d}
+
+        def e2e_step():
+            for k in host:
+                shard[k].copy_(host[k], non_blocking=True)
+            step()
+            ctx.results_device({k: v.data_ptr() for k, v in out_d.items()})
+            for k in out_d:
+                out_h[k].copy_(out_d[k], non_blocking=True)
+            torch.cuda.synchronize()
+        e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            e2e_step()
+        barrier()
+        te = torch.tensor([(time.perf_counter() - t0) / args.steps], dtype=torch.float64, device=dev)
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        te = float(te[0])
+        e2e = {"value": n / te, "unit": "particles/s", "h2d_bytes_per_step": int(sum(v.numel() * v.element_size() for v in host.values()) * world),
+               "d2h_bytes_per_step": int(3 * 8 * n * world), "ms_per_step": te * 1e3}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (k_walk): FP64 CUDA-core pipe, measured denominator
+    flop_per_interaction = 21.5                      # 10 flop per node visit x 1.15 + 10 flop per accepted pair
+    walk_ms_avg = walk_total_ms / args.steps
+    fp64_peak = ctx.microbench(0)
+    achieved = flop_per_interaction * (inter_all / world if world > 1 else inter_all) / (walk_ms_avg * 1e-3) / 1e12
+    roofline = {"bound": "fp64", "kernel": "k_walk", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved / fp64_peak if fp64_peak else None,
+                "traffic": None, "peak_source": "measured on this GPU: FP64 FMA chain microbenchmark (agb_microbench kind 0)",
+                "algorithmic_flop_per_interaction": flop_per_interaction, "interactions_per_step": inter_all,
+                "interactions_per_s": inter_all / (walk_ms_avg * 1e-3), "walk_ms": walk_ms_avg, "build_ms": float(np.mean(build_ms))}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        hbm_peak, hbm_src = float(peaks["hbm_gbs"]), "MEASURED_PEAKS.json"
+    except Exception:  # noqa: BLE001
+        hbm_peak, hbm_src = 6650.0, "fallback (B200_PROFILING.md)"
+    build_bytes = 1024.0 * n                         # ~1 KB per particle for key-gen + 16-pass sort + permute + links
+    roofline["hbm_build"] = {"bound": "hbm", "achieved": build_bytes / (float(np.mean(build_ms)) * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                             "frac": build_bytes / (float(np.mean(build_ms)) * 1e-3) / 1e9 / hbm_peak, "peak_source": hbm_src}
+
+    # ---- CPU baseline on this box's host cores (bounded sample of the same workload)
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        ns = sample_size_for_cpu(n, 2, budget_s=20.0)
+        ps, _, _, _ = make_particles(pkg, name, ns)
+        with tempfile.TemporaryDirectory() as d:
+            secs, kind, cores, rows = cpu_reference_run(ps, e0, mh, 2, d)
+        cpu = {"value": ns / secs[-1], "unit": "particles/s", "cores": cores, "kind": kind,
+               "sample": "%d of %d particles of %s, 2nd of 2 steps, phases build+visual+gas_density+forces = %.3f s" % (ns, n, name, secs[-1])}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": "particles/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": name, "description": desc, "n_particles": n, "theta": THETA, "e0": e0, "massInH": mh, "all_active": True,
+                   "l2": "256 MiB buffer written between timed steps (L2 flush); working set %.0f MB" % (n * 330 / 1e6),
+                   "parallelism": "replicated tree, tree-ordered target slices, 1 NCCL all-gather/step" if world > 1 else "single GPU"},
+        "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+        "interactions_per_s": inter_all / (walk_ms_avg * 1e-3), "wall_s_timed_region": t_wall,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="agb200", choices=["agb200", "reference"])
+    ap.add_argument("--workload", default=None, choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    import __graft_entry__ as ge
+    pkg = ge.load_package()
+    if args.impl == "reference":
+        run_reference_arm(args, pkg)
+    else:
+        run_gpu_arm(args, pkg)
+
+
+if __name__ == "__main__":
+    main()

@@ -134,6 +134,10 @@ int agb_get_stream(agb_ctx* ctx, void** stream);
 /* Number of kernels this context launched since creation. */
 int agb_get_launch_count(agb_ctx* ctx, int64_t* launches);
 
+/* Roofline denominators measured on this device with tiny kernels (not part of the force path):
+ * kind 0 = FP64 FMA throughput [TFLOP/s], 1 = FP32 FMA throughput [TFLOP/s], 2 = HBM copy bandwidth [GB/s]. */
+int agb_microbench(agb_ctx* ctx, int kind, double* result);
+
 const char* agb_strerror(int status);
 const char* agb_last_error(agb_ctx* ctx);
 const char* agb_version(void);

@@ -61,7 +61,11 @@ def compare(got, want, p, ctx=None, check_counters=True, check_nodes=True):
                     den = np.abs(b) if scale is None else scale
                     den = np.where(den > 0, den, 1.0)
                     return float(np.max(np.abs(a - b) / den)) if len(a) else 0.0
-                rep["node_mass_maxrel"] = nerr("mass", "mass")
+                # the reference sums a node's particles sequentially: its own rounding error grows like count * 2^-53
+                ntol = np.maximum(1.0, nd["count"][go].astype(float)) * 2.0 ** -52
+                rep["node_mass_maxrel"] = nerr("mass", "mass") / 1.0
+                rep["node_mass_over_tol"] = float(np.max(np.abs(nd["mass"][go] - wn["mass"][internal][wo]) / np.maximum(wn["mass"][internal][wo], 1e-300) / ntol))
+                rep["node_gas_over_tol"] = float(np.max(np.abs(nd["gasMass"][go] - wn["gasMass"][internal][wo]) / np.maximum(wn["gasMass"][internal][wo], 1e-300) / ntol))
                 rep["node_gas_maxrel"] = nerr("gasMass", "gasMass")
                 rep["node_com_maxrel_R"] = max(nerr("com" + c, "com" + c, R) for c in "xyz")
                 rep["node_mvel_maxrel_v"] = max(nerr("mv" + c, "mv" + c, vmax) for c in "xyz")
@@ -86,6 +90,12 @@ def assert_parity(rep):
     for k in ("node_count_equal", "interactions_total_equal"):
         if k in rep:
             assert rep[k], (k, rep)
-    for k in ("node_mass_maxrel", "node_gas_maxrel", "node_com_maxrel_R", "node_mvel_maxrel_v"):
+    for k in ("node_com_maxrel_R", "node_mvel_maxrel_v"):
         if k in rep:
             assert rep[k] <= NODE_RTOL * 10, (k, rep)
+    for k in ("node_mass_over_tol", "node_gas_over_tol"):          # <= count * 2^-52 relative (the reference's own sequential-sum error)
+        if k in rep:
+            assert rep[k] <= 1.0, (k, rep)
+    for k in ("node_mass_maxrel", "node_gas_maxrel"):
+        if k in rep:
+            assert rep[k] <= 1e-10, (k, rep)
