@@ -57,7 +57,7 @@ void free_pool(agb_ctx* c)
     dfree(d.s_h); dfree(d.s_rho); dfree(d.s_P); dfree(d.s_U); dfree(d.s_mu); dfree(d.s_next); dfree(d.s_T); dfree(d.s_type);
     dfree(d.lcp); dfree(d.nodebase); dfree(d.nodecnt); dfree(d.leafparent); dfree(d.group); dfree(d.leafdepth);
     dfree(d.child); dfree(d.nfirst); dfree(d.nlast); dfree(d.nparent); dfree(d.arrived); dfree(d.ndepth);
-    dfree(d.nmark); dfree(d.ndup); dfree(d.leafmark); dfree(d.mom_pm); dfree(d.mom_gv); dfree(d.grouplist);
+    dfree(d.nmark); dfree(d.ndup); dfree(d.leafmark); dfree(d.mom_pm); dfree(d.mom_gv); dfree(d.grouplist); dfree(d.gasrank);
     dfree(d.dist); dfree(d.blockhist); dfree(d.scanblk);
     dfree(d.c_visits); dfree(d.c_accn); dfree(d.c_accl); dfree(d.c_sph);
     d.cap = 0;
@@ -78,7 +78,7 @@ int ensure_pool(agb_ctx* c, int64_t n)
     CK(dalloc(d.s_next, cap)); CK(dalloc(d.s_T, cap)); CK(dalloc(d.s_type, cap));
     CK(dalloc(d.lcp, cap)); CK(dalloc(d.nodebase, cap)); CK(dalloc(d.nodecnt, cap)); CK(dalloc(d.leafparent, cap)); CK(dalloc(d.group, cap)); CK(dalloc(d.leafdepth, cap));
     CK(dalloc(d.child, 8 * cap)); CK(dalloc(d.nfirst, cap)); CK(dalloc(d.nlast, cap)); CK(dalloc(d.nparent, cap)); CK(dalloc(d.arrived, cap)); CK(dalloc(d.ndepth, cap));
-    CK(dalloc(d.nmark, cap)); CK(dalloc(d.ndup, cap)); CK(dalloc(d.leafmark, cap)); CK(dalloc(d.mom_pm, cap)); CK(dalloc(d.mom_gv, cap)); CK(dalloc(d.grouplist, cap));
+    CK(dalloc(d.nmark, cap)); CK(dalloc(d.ndup, cap)); CK(dalloc(d.leafmark, cap)); CK(dalloc(d.mom_pm, cap)); CK(dalloc(d.mom_gv, cap)); CK(dalloc(d.grouplist, cap)); CK(dalloc(d.gasrank, cap + 1));
     CK(dalloc(d.dist, cap));
     for (auto& q : c->in_d) CK(dalloc(q, cap));
     CK(dalloc(c->in_type, cap));
@@ -350,7 +350,7 @@ int agb_get_counters(agb_ctx* c, agb_counters* o)
     o->max_depth = h.max_depth; o->edge_dropped = h.edge_dropped;
     o->node_interactions = (int64_t)h.c_node; o->leaf_interactions = (int64_t)h.c_leaf; o->interactions = (int64_t)(h.c_node + h.c_leaf);
     o->sph_interactions = (int64_t)h.c_sph; o->node_visits = c->counters_valid ? (int64_t)h.c_visits : -1; o->mac_exact_fallbacks = (int64_t)h.c_exact;
-    o->groups = (c->d.n + 31) / 32; o->gas_groups = h.n_gas_groups; o->gas_orphans = h.n_gas_orphans;
+    o->groups = (c->d.n + 31) / 32; o->gas_groups = h.n_gas_groups; o->gas_orphans = h.n_gas_orphans; o->gas_ties_exact = h.tie_exact; o->gas_ties_unresolved = h.tie_unresolved;
     return AGB_OK;
 }
 

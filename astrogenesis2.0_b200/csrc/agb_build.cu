@@ -67,9 +67,11 @@ __global__ void __launch_bounds__(TPB) k_dist_partial(const double* __restrict__
 }
 
 __global__ void k_extent_finish(AgbScalars* s, int nblocks, int64_t n)
-{
+{   // one warp: fixed lane-strided partial sums + butterfly => deterministic
     double sa = 0.0, sb = 0.0;
-    for (int i = 0; i < nblocks; i++) { sa += s->partial_sum[i]; sb += s->partial_sq[i]; }
+    for (int i = threadIdx.x; i < nblocks; i += 32) { sa += s->partial_sum[i]; sb += s->partial_sq[i]; }
+    for (int o = 16; o > 0; o >>= 1) { sa += __shfl_xor_sync(0xffffffffu, sa, o); sb += __shfl_xor_sync(0xffffffffu, sb, o); }
+    if (threadIdx.x != 0) return;
     double nn = (double)n;
     double mean = __ddiv_rn(sa, nn);
     double var = __dadd_rn(__ddiv_rn(sb, nn), -__dmul_rn(mean, mean));
@@ -501,17 +503,31 @@ __global__ void __launch_bounds__(TPB) k_upward(AgbDev d, const AgbScalars* __re
 
 // Reference quirk: bulk insertion accumulates the ROOT's mass / COM / gasMass / mVel over ALL particles,
 // including those outside the cube that are never inserted (Node.cpp:477-499 precede the octant test).
-__global__ void k_root_fix(AgbDev d, const AgbScalars* __restrict__ s)
+__global__ void __launch_bounds__(TPB) k_root_fix(AgbDev d, const AgbScalars* __restrict__ s)
 {
     if (s->n_nodes < 1) return;
     if (d.n < (int64_t)d.cores * 100) return;                  // one-by-one insertion rejects them at the root (Node.cpp:606-612)
-    double4 pm = d.mom_pm[0], gv = d.mom_gv[0];
-    for (int64_t i = s->n_in_tree; i < d.n; i++) {
+    __shared__ double sh[8][TPB / 32];
+    double v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int64_t i = s->n_in_tree + threadIdx.x; i < d.n; i += TPB) {
         double4 a = d.src_pm[i], b = d.src_gv[i];
-        pm.w += a.w; pm.x += a.x * a.w; pm.y += a.y * a.w; pm.z += a.z * a.w;
-        gv.w += b.w; gv.x += b.x * b.w; gv.y += b.y * b.w; gv.z += b.z * b.w;
+        v[3] += a.w; v[0] += a.x * a.w; v[1] += a.y * a.w; v[2] += a.z * a.w;
+        v[7] += b.w; v[4] += b.x * b.w; v[5] += b.y * b.w; v[6] += b.z * b.w;
     }
-    d.mom_pm[0] = pm; d.mom_gv[0] = gv;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        double x = warp_sum(v[k]);
+        if ((threadIdx.x & 31) == 0) sh[k][threadIdx.x >> 5] = x;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t[8];
+        for (int k = 0; k < 8; k++) { t[k] = 0; for (int w = 0; w < TPB / 32; w++) t[k] += sh[k][w]; }
+        double4 pm = d.mom_pm[0], gv = d.mom_gv[0];
+        pm.x += t[0]; pm.y += t[1]; pm.z += t[2]; pm.w += t[3];
+        gv.x += t[4]; gv.y += t[5]; gv.z += t[6]; gv.w += t[7];
+        d.mom_pm[0] = pm; d.mom_gv[0] = gv;
+    }
 }
 
 __global__ void __launch_bounds__(TPB) k_finalize(AgbDev d, const AgbScalars* __restrict__ s)
@@ -565,7 +581,7 @@ int agb_launch_extent(const AgbDev& d, AgbScalars* s, cudaStream_t st)
 {
     int nb = (int)std::min<int64_t>(1024, std::max<int64_t>(1, nblk(d.n, TPB)));
     k_dist_partial<<<nb, TPB, 0, st>>>(d.x, d.y, d.z, d.n, d.dist, s);
-    k_extent_finish<<<1, 1, 0, st>>>(s, nb, d.n);
+    k_extent_finish<<<1, 32, 0, st>>>(s, nb, d.n);
     k_extent_max<<<nb, TPB, 0, st>>>(d.dist, d.n, s);
     return 3;
 }
@@ -606,9 +622,18 @@ int agb_launch_links(AgbDev& d, AgbScalars* s, cudaStream_t st)
     k_init_nodes<<<nb, TPB, 0, st>>>(d, s);
     k_links<<<nb, TPB, 0, st>>>(d, khi, klo, s);
     k_upward<<<nb, TPB, 0, st>>>(d, s);
-    k_root_fix<<<1, 1, 0, st>>>(d, s);
+    k_root_fix<<<1, TPB, 0, st>>>(d, s);
     k_finalize<<<nb, TPB, 0, st>>>(d, s);
     return 10;
+}
+
+int agb_launch_scan_i32(const int32_t* in, int32_t* out, int64_t n, int32_t* blk, int32_t* total_out, cudaStream_t st)
+{
+    const int sb = nblk(n, SCAN_TILE);
+    k_scan_reduce<<<sb, TPB, 0, st>>>(in, n, blk);
+    k_scan_blocks<<<1, TPB, 0, st>>>(blk, sb, total_out);
+    k_scan_apply<<<sb, TPB, 0, st>>>(in, n, blk, out);
+    return 3;
 }
 
 int agb_launch_dump_tree(AgbDev& d, AgbScalars* s, int32_t* leafdepth, uint64_t* khi, uint64_t* klo, cudaStream_t st)

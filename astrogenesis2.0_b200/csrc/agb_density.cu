@@ -63,22 +63,88 @@ __global__ void __launch_bounds__(TPB) k_visual(AgbDev d, const uint32_t* __rest
 // ------------------------------------------------------------------ gas density: mark first-stop nodes
 __device__ __forceinline__ double gas_of(const AgbDev& d, int ref) { return d.src_gv[ref].w; }
 
-__global__ void __launch_bounds__(TPB) k_gas_mark(AgbDev d, const AgbScalars* __restrict__ s, double M)
+// ---- exact gasMass of a node, as the reference accumulates it -------------------------------------
+// With equal-mass gas particles and massInH a multiple of that mass, |M - g_node| == |M - g_parent|
+// ties are common, and the reference breaks them by the rounding of ITS sums: `gasMass += p->mass` in
+// list order = caller order restricted to the node (Node.cpp:477-480 bulk, :678-681 one-by-one).  The
+// upward pass sums in octant order, which differs in the last bits, so near a tie the reference's
+// left fold is recomputed bit-exactly from the node's gas particles visited in caller order.
+constexpr int FOLD_CAP = 1024;
+
+__global__ void __launch_bounds__(TPB) k_gas_flags(AgbDev d, int32_t* __restrict__ flag)
+{
+    int64_t i = (int64_t)blockIdx.x * TPB + threadIdx.x;
+    if (i < d.n) flag[i] = d.s_type[i] == 2;
+}
+
+__global__ void __launch_bounds__(TPB) k_gas_compact(AgbDev d, const uint32_t* __restrict__ perm, uint32_t* __restrict__ g_orig, double* __restrict__ g_m)
+{
+    int64_t i = (int64_t)blockIdx.x * TPB + threadIdx.x;
+    if (i >= d.n || d.s_type[i] != 2) return;
+    const int r = d.gasrank[i];
+    g_orig[r] = perm[i];
+    g_m[r] = d.src_pm[i].w;
+}
+
+struct GasFold { const int32_t* gasrank; const uint32_t* g_orig; const double* g_m; };
+
+// left fold of the masses of the gas particles ranked [g0, g0+k) taken in increasing caller index
+__device__ double fold_in_caller_order(const GasFold& F, int g0, int k)
+{
+    double sum = 0.0;
+    long long prev = -1;
+    for (int it = 0; it < k; it++) {
+        long long best = 1ll << 40; int bi = 0;
+        for (int r = 0; r < k; r++) { const long long o = F.g_orig[g0 + r]; if (o > prev && o < best) { best = o; bi = r; } }
+        sum = __dadd_rn(sum, F.g_m[g0 + bi]);
+        prev = best;
+    }
+    return sum;
+}
+
+// exact gasMass of internal node k (returns false if the node holds too many gas particles to fold)
+__device__ bool exact_gas(const AgbDev& d, const GasFold& F, const AgbScalars* s, int k, double* out)
+{
+    int g0, g1;
+    if (k == 0 && d.n >= (int64_t)d.cores * 100) { g0 = 0; g1 = s->n_gas_total; }       // the root sums every particle it is handed (Node.cpp:477-480)
+    else { g0 = F.gasrank[d.nfirst[k]]; g1 = F.gasrank[d.nlast[k] + 1]; }
+    if (g1 - g0 > FOLD_CAP) return false;
+    *out = fold_in_caller_order(F, g0, g1 - g0);
+    return true;
+}
+
+__global__ void __launch_bounds__(TPB) k_gas_mark(AgbDev d, AgbScalars* s, double M, GasFold F)
 {
     int64_t i = (int64_t)blockIdx.x * TPB + threadIdx.x;
     if (i >= s->n_in_tree) return;
     if (d.s_type[i] != 2) return;
     const int N = (int)d.n;
+    const double tau = 1e-9;
     // cur = -1 encodes "the particle's own leaf"
     int cur = -1;
     double g = d.src_gv[i].w;                                  // leaf gasMass = particle mass (Node.cpp:416)
+    bool g_exact = true;
     while (true) {
         if (g == 0.0) return;                                  // Node.cpp:724
         int par = cur < 0 ? d.leafparent[i] : d.nparent[cur];
         if (par < 0) return;                                   // root: parent == nullptr (Node.cpp:727)
         double gp = gas_of(d, N + par);
+        bool gp_exact = false;
         double d0 = fabs(__dadd_rn(M, -g)), d1 = fabs(__dadd_rn(M, -gp));
-        if (g < M && d0 > d1) { cur = par; g = gp; continue; } // Node.cpp:737-746 (after the recursion the 2nd test is false)
+        if (fabs(g - M) <= tau * M || fabs(d0 - d1) <= tau * fmax(M, gp)) {
+            // a decision of Node.cpp:737-751 hangs on the last bits: use the reference's own sums
+            bool ok = true;
+            const int kc = cur < 0 ? 1 : F.gasrank[d.nlast[cur] + 1] - F.gasrank[d.nfirst[cur]];
+            const int kp = (par == 0 && d.n >= (int64_t)d.cores * 100) ? s->n_gas_total : F.gasrank[d.nlast[par] + 1] - F.gasrank[d.nfirst[par]];
+            if (kc == kp) { gp = g; gp_exact = g_exact; }      // same gas particles, same order: the reference's two sums are identical
+            else {
+                if (!g_exact) { ok = exact_gas(d, F, s, cur, &g); g_exact = ok; }
+                if (ok) { ok = exact_gas(d, F, s, par, &gp); gp_exact = ok; }
+                atomicAdd(ok ? &s->tie_exact : &s->tie_unresolved, 1);
+            }
+            d0 = fabs(__dadd_rn(M, -g)); d1 = fabs(__dadd_rn(M, -gp));
+        }
+        if (g < M && d0 > d1) { cur = par; g = gp; g_exact = gp_exact; continue; } // Node.cpp:737-746 (after the recursion the 2nd test is false)
         if (d0 < d1) {                                         // Node.cpp:749-751: compute here
             if (cur < 0) d.leafmark[i] = 1; else d.nmark[cur] = 1;
         }
@@ -165,7 +231,7 @@ __global__ void __launch_bounds__(TPB) k_gas_scatter(AgbDev d, const uint32_t* _
     d.h[p] = d.s_h[i]; d.rho[p] = d.s_rho[i]; d.P[p] = d.s_P[i]; d.T[p] = d.s_T[i];
 }
 
-__global__ void k_gas_reset(AgbScalars* s) { s->n_gas_groups = 0; s->n_gas_orphans = 0; }
+__global__ void k_gas_reset(AgbScalars* s) { s->n_gas_groups = 0; s->n_gas_orphans = 0; s->tie_exact = 0; s->tie_unresolved = 0; }
 
 } // namespace
 
@@ -181,10 +247,19 @@ int agb_launch_gas_density(AgbDev& d, AgbScalars* s, double massInH, cudaStream_
 {
     const int nb = nblk(d.n, TPB);
     k_gas_reset<<<1, 1, 0, st>>>(s);
-    k_gas_mark<<<nb, TPB, 0, st>>>(d, s, massInH);
+    // compact (caller index, mass) of the gas particles in tree order; scratch that is free after the build is reused:
+    // flags -> nodecnt, caller indices -> the idle half of the sort's ping-pong permutation, masses -> dist
+    uint32_t* g_orig = d.perm[d.cur ^ 1];
+    double* g_m = d.dist;
+    k_gas_flags<<<nb, TPB, 0, st>>>(d, d.nodecnt);
+    int launches = agb_launch_scan_i32(d.nodecnt, d.gasrank, d.n, d.scanblk, &s->n_gas_total, st);
+    cudaMemcpyAsync(d.gasrank + d.n, &s->n_gas_total, sizeof(int32_t), cudaMemcpyDeviceToDevice, st);
+    k_gas_compact<<<nb, TPB, 0, st>>>(d, d.perm[d.cur], g_orig, g_m);
+    GasFold F{d.gasrank, g_orig, g_m};
+    k_gas_mark<<<nb, TPB, 0, st>>>(d, s, massInH, F);
     k_gas_group<<<nb, TPB, 0, st>>>(d, s);
     k_gas_collect<<<nb, TPB, 0, st>>>(d, s);
     k_gas_sum<<<nblk(d.n, TPB / 32), TPB, 0, st>>>(d, s);     // upper bound on groups; surplus warps exit
     k_gas_scatter<<<nb, TPB, 0, st>>>(d, d.perm[d.cur]);
-    return 6;
+    return 8 + launches;
 }

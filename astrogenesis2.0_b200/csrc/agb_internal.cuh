@@ -46,6 +46,7 @@ struct AgbDev {
     uint8_t *nmark = nullptr, *ndup = nullptr, *leafmark = nullptr;
     double4 *mom_pm = nullptr, *mom_gv = nullptr;
     int32_t* grouplist = nullptr;
+    int32_t* gasrank = nullptr;        // exclusive count of gas particles before tree position i
     // scratch
     double* dist = nullptr;
     uint32_t* blockhist = nullptr;     // radix sort: [256][nblocks]
@@ -68,6 +69,7 @@ struct AgbScalars {
     int32_t bintotal[256];
     int32_t vis_level;
     int32_t walk_overflow, any_gas;
+    int32_t n_gas_total, tie_exact, tie_unresolved;
 };
 
 // ---- host-callable launchers (each returns the number of kernels it launched) ----
@@ -80,6 +82,7 @@ int agb_launch_gas_density(AgbDev& d, AgbScalars* s, double massInH, cudaStream_
 int agb_launch_walk(AgbDev& d, AgbScalars* s, double globalTime, double e0, double theta, int64_t t0, int64_t t1,
                     bool counters, bool any_gas, int sm_count, cudaStream_t st, cudaEvent_t ev0, cudaEvent_t ev1);
 int agb_launch_dump_tree(AgbDev& d, AgbScalars* s, int32_t* leafdepth, uint64_t* khi, uint64_t* klo, cudaStream_t st);
+int agb_launch_scan_i32(const int32_t* in, int32_t* out, int64_t n, int32_t* blk, int32_t* total_out, cudaStream_t st);
 int agb_launch_microbench(int kind, int sm_count, cudaStream_t st, double* result);
 int agb_launch_unpermute_counters(AgbDev& d, int32_t* v, int32_t* an, int32_t* al, int32_t* sp, cudaStream_t st);
 

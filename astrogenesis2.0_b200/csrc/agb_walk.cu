@@ -42,8 +42,19 @@ constexpr double kGAMMA = 5.0 / 3.0;
 struct WarpSmem {
     int2 list[LCAP];
     int2 stack[SCAP];
-    double4 stage[32];
+    double4 stage[32];                     // drain: the 32 sources of a tile; traversal: (COM, mass) of straddling nodes
+    int4 mch[64];                          // traversal: the 8 child slots of straddling nodes
 };
+
+// 1/sqrt(x) for positive normal x: MUFU.RSQ64H seed (~2^-22) + one cubically convergent step (~2^-60).
+// None of the special-case handling of the library rsqrt() is needed here (x = 0 is masked by the caller).
+__device__ __forceinline__ double rsqrt_pos(double x)
+{
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    const double e = fma(-x * y, y, 1.0);
+    return fma(y, e * fma(0.375, e, 0.5), y);
+}
 
 struct WalkParams {
     const double4 *src_pm, *src_gv;
@@ -155,9 +166,10 @@ __global__ void __launch_bounds__(WALK_TPB, 2) k_walk(const WalkParams P)
                     if (lane < cnt) e = stack_get(sp + lane);
                     if (sp + cnt > SCAP) tot_spill += 1;
                     int outcome = OUT_NONE;
-                    double rad2 = 0;
+                    double rad2 = 0, pmx = 0, pmy = 0, pmz = 0;
                     if (lane < cnt && e.x >= 0) {
                         const double4 pm = P.src_pm[e.x];
+                        pmx = pm.x; pmy = pm.y; pmz = pm.z;
                         if (pm.w != 0.0) {                                       // Node.cpp:250 / :390
                             const double rad = scalbn(R, -(int)P.ndepth[e.x - N]);
                             rad2 = rad * rad;
@@ -203,15 +215,24 @@ __global__ void __launch_bounds__(WALK_TPB, 2) k_walk(const WalkParams P)
                         }
                         lc += tl; sp += tn;
                     }
-                    // straddling nodes: exact per-lane test
+                    // straddling nodes: exact per-lane test.  Their (COM, mass) and child slots are parked in shared
+                    // memory by the owning lanes first, so the serial loop below never waits on global memory.
                     unsigned mm = __ballot_sync(0xffffffffu, outcome == OUT_MIXED);
+                    if (mm) {
+                        if (outcome == OUT_MIXED) {
+                            sm.stage[lane] = make_double4(pmx, pmy, pmz, rad2);
+                            sm.mch[2 * lane] = reinterpret_cast<const int4*>(P.child)[2 * (size_t)(e.x - N)];
+                            sm.mch[2 * lane + 1] = reinterpret_cast<const int4*>(P.child)[2 * (size_t)(e.x - N) + 1];
+                        }
+                        __syncwarp();
+                    }
                     while (mm) {
                         const int src = __ffs(mm) - 1;
                         mm &= mm - 1;
                         const int nidx = __shfl_sync(0xffffffffu, e.x, src);
                         const unsigned nmask = (unsigned)__shfl_sync(0xffffffffu, e.y, src);
-                        const double nrad2 = __shfl_sync(0xffffffffu, rad2, src);
-                        const double4 q = P.src_pm[nidx];
+                        const double4 q = sm.stage[src];
+                        const double nrad2 = q.w;
                         bool acc_l = false, open_l = false;
                         if ((nmask >> lane) & 1u) {
                             const double dx = q.x - tp.x, dy = q.y - tp.y, dz = q.z - tp.z;
@@ -232,7 +253,7 @@ __global__ void __launch_bounds__(WALK_TPB, 2) k_walk(const WalkParams P)
                         const unsigned a = __ballot_sync(0xffffffffu, acc_l), o = __ballot_sync(0xffffffffu, open_l);
                         if (a) { if (lane == 0) sm.list[lc] = make_int2(nidx, (int)a); lc++; }
                         if (o) {
-                            const int chl = lane < 8 ? P.child[(size_t)(nidx - N) * 8 + lane] : -1;
+                            const int chl = lane < 8 ? reinterpret_cast<const int*>(sm.mch)[src * 8 + lane] : -1;
                             const unsigned lm = __ballot_sync(0xffffffffu, chl >= 0 && chl < N), nm = __ballot_sync(0xffffffffu, chl >= N);
                             if (chl >= N) stack_put(sp + __popc(nm & lt), make_int2(chl, (int)o));
                             else if (chl >= 0) sm.list[lc + __popc(lm & lt)] = make_int2(chl, (int)o);
@@ -271,7 +292,7 @@ __global__ void __launch_bounds__(WALK_TPB, 2) k_walk(const WalkParams P)
                         const bool seen = bit && q.w != 0.0;
                         const bool ok = seen && src != (int)t && r2 != 0.0;
                         const double r2s = r2 * invR2, q2 = r2s + e02s;
-                        double w = rsqrt(r2s * q2 * q2);                         // 1 / (r (r^2 + e0^2)) in units of R
+                        const double w = rsqrt_pos(r2s * q2 * q2);                         // 1 / (r (r^2 + e0^2)) in units of R
                         const double f = ok ? GR3 * q.w * w : 0.0;
                         ax = fma(f, dx, ax); ay = fma(f, dy, ay); az = fma(f, dz, az);
                         if (COUNT) {

@@ -79,9 +79,14 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append(line.strip())
+            self.rows.append((time.perf_counter(), line.strip()))
 
-    def stop(self):
+    def wait_first(self, timeout=3.0):
+        t0 = time.perf_counter()
+        while not self.rows and time.perf_counter() - t0 < timeout:
+            time.sleep(0.02)
+
+    def stop(self, t_begin=None, t_end=None):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -91,7 +96,11 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        rows = [r for t, r in self.rows if t_begin is None or (t_begin <= t <= t_end + 0.15)]
+        window = "timed region"
+        if not rows:
+            rows, window = [r for _, r in self.rows], "whole run (timed region shorter than the 100 ms sampling period)"
+        for r in rows:
             f = [x.strip() for x in r.split(",")]
             if len(f) < 7:
                 continue
@@ -102,7 +111,7 @@ class ClockSampler:
             for nm, v in zip(names, f[3:7]):
                 if v.lower().startswith("active"):
                     reasons.add(nm)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm), "window": window}
 
 
 # ------------------------------------------------------------------ reference / CPU baseline
@@ -212,13 +221,14 @@ def run_gpu_arm(args, pkg):
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        sampler.wait_first()
     for _ in range(args.warmup):
         flush.fill_(1)
         step()
     barrier()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
     launches0 = ctx.launch_count()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     walk_ms, build_ms, inter = [], [], 0
@@ -238,7 +248,7 @@ def run_gpu_arm(args, pkg):
     t_wall = time.perf_counter() - t_wall0
     step_ms = [a.elapsed_time(b) for a, b in ev]
     launches = ctx.launch_count() - launches0
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(t_wall0, t_wall0 + t_wall) if rank == 0 else None
     tot = torch.tensor([sum(step_ms), float(inter), sum(walk_ms)], dtype=torch.float64, device=dev)
     if world > 1:
         mx = tot.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
@@ -358,7 +368,7 @@ def run_gpu_arm(args, pkg):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="agb200", choices=["agb200", "reference"])
     ap.add_argument("--workload", default=None, choices=sorted(WORKLOADS))

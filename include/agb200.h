@@ -84,6 +84,8 @@ typedef struct {
     int64_t node_visits;            /* calls of Node::calculateGravityForce the reference would make */
     int64_t mac_exact_fallbacks;    /* MAC / SPH-gate decisions taken on the exact FP64 slow path  */
     int64_t groups, gas_groups, gas_orphans;
+    int64_t gas_ties_exact;         /* density-group decisions re-taken with the reference's own left-fold gasMass sums */
+    int64_t gas_ties_unresolved;    /* ... that involved more than 1024 gas particles and kept the tree-order sums       */
 } agb_counters;
 
 /* -------- lifetime: `new Tree(sim)` / `delete tree`, but persistent across steps (pooled memory) */
