@@ -320,7 +320,10 @@ int agb_forces_slice(agb_ctx* c, double global_time, double e0, double theta, in
     AgbDev& d = c->d;
     if (d.n == 0) { c->forces_done = true; return AGB_OK; }
     if (c->target_counters) { int rc = ensure_counters(c); if (rc) return rc; }
-    const int64_t t0 = d.n * part / nparts, t1 = d.n * (part + 1) / nparts;
+    // slice boundaries fall on multiples of 32 so that every warp owns the same 32 targets whatever the number of
+    // parts: results are then bit-identical for 1, 2, 4, 8 GPUs (same groups => same summation order)
+    const int64_t ngrp = (d.n + 31) / 32;
+    const int64_t t0 = std::min(d.n, ngrp * part / nparts * 32), t1 = std::min(d.n, ngrp * (part + 1) / nparts * 32);
     CK(cudaEventRecord(c->ev[6], c->st));
     // gas targets need h/rho/P: if the caller skipped gas_density they are orphans (h = 0) and get no SPH, like the reference
     c->launches += agb_launch_walk(d, c->s, global_time, e0, theta, t0, t1, c->target_counters, c->hs.any_gas != 0, c->sm_count, c->st, c->ev[0], c->ev[1]);

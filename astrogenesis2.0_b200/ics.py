@@ -37,7 +37,7 @@ def plummer(n, seed=1234, a=10 * KPC, mtot=1e11 * MSUN, gas_fraction=0.0, u_gas=
     # isotropic velocities with the local 1-D dispersion sigma^2 = G M / (6 sqrt(r^2 + a^2))
     sig = np.sqrt(G * mtot / (6.0 * np.sqrt(r * r + a * a)))
     p["vx"], p["vy"], p["vz"] = (sig * rng.standard_normal(n) for _ in range(3))
-    p["mass"][:] = mtot / n
+    p["mass"][:] = mtot / max(n, 1)
     if gas_fraction > 0:
         gas = rng.uniform(0, 1, n) < gas_fraction
         p["type"][gas] = 2

@@ -78,11 +78,12 @@ def test_tiny_and_empty(pkg, oracle, ctxs):
     assert got["R"] == 0.0 and len(got["ax"]) == 0
 
 
-def test_inactive_and_massless_targets(pkg, oracle, ctxs):
+def test_inactive_targets(pkg, oracle, ctxs):
+    # (zero-mass particles are not covered: the reference turns the COM of every one-by-one-inserted node whose first
+    #  particle is massless into NaN, Node.cpp:698 0/0, and then opens those nodes for every target)
     ctx = ctxs(8)
     p = pkg.ics.plummer(20000, seed=8, gas_fraction=0.2)
     p["next_time"][::3] = 7.0                    # inactive: keep their previous acc (Tree.cpp:75)
-    p["mass"][5::1000] = 0.0                     # massless: no force (Node.cpp:265), not a source (Node.cpp:250,390)
     prev = np.full(20000, 3.25)
     p2 = dict(p); p2["ax"] = prev.copy(); p2["ay"] = prev.copy(); p2["az"] = prev.copy()
     mh = pkg.ics.gas_mass_in_h(p, 32)
