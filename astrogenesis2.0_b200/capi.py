@@ -36,7 +36,8 @@ class AosLayout(C.Structure):
 
 COUNTER_FIELDS = ("n_particles", "n_in_tree", "n_outliers", "n_nodes", "n_active", "max_depth", "edge_dropped", "interactions",
                   "node_interactions", "leaf_interactions", "sph_interactions", "node_visits", "mac_exact_fallbacks",
-                  "groups", "gas_groups", "gas_orphans", "gas_ties_exact", "gas_ties_unresolved")
+                  "groups", "gas_groups", "gas_orphans", "gas_ties_exact", "gas_ties_unresolved",
+                  "walk_rounds", "walk_popped", "walk_straddling", "walk_opened", "walk_tiles", "walk_stack_spills")
 
 
 class Counters(C.Structure):

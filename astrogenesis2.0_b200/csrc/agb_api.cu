@@ -354,6 +354,8 @@ int agb_get_counters(agb_ctx* c, agb_counters* o)
     o->node_interactions = (int64_t)h.c_node; o->leaf_interactions = (int64_t)h.c_leaf; o->interactions = (int64_t)(h.c_node + h.c_leaf);
     o->sph_interactions = (int64_t)h.c_sph; o->node_visits = c->counters_valid ? (int64_t)h.c_visits : -1; o->mac_exact_fallbacks = (int64_t)h.c_exact;
     o->groups = (c->d.n + 31) / 32; o->gas_groups = h.n_gas_groups; o->gas_orphans = h.n_gas_orphans; o->gas_ties_exact = h.tie_exact; o->gas_ties_unresolved = h.tie_unresolved;
+    o->walk_rounds = (int64_t)h.st_rounds; o->walk_popped = (int64_t)h.st_popped; o->walk_straddling = (int64_t)h.st_mixed; o->walk_opened = (int64_t)h.st_open;
+    o->walk_tiles = (int64_t)h.st_drain; o->walk_stack_spills = (int64_t)h.c_spill;
     return AGB_OK;
 }
 

@@ -67,9 +67,11 @@ __device__ __forceinline__ double gas_of(const AgbDev& d, int ref) { return d.sr
 // With equal-mass gas particles and massInH a multiple of that mass, |M - g_node| == |M - g_parent|
 // ties are common, and the reference breaks them by the rounding of ITS sums: `gasMass += p->mass` in
 // list order = caller order restricted to the node (Node.cpp:477-480 bulk, :678-681 one-by-one).  The
-// upward pass sums in octant order, which differs in the last bits, so near a tie the reference's
-// left fold is recomputed bit-exactly from the node's gas particles visited in caller order.
-constexpr int FOLD_CAP = 1024;
+// upward pass sums in octant order, which differs in the last bits.  So: (pass 0) climbs that meet a
+// near-tie flag every ancestor that can still matter (gas <= 2 M) and park the particle; (fold) one
+// block per flagged node recomputes the reference's left fold bit-exactly from the node's gas
+// particles taken in caller order; (pass 1) parked particles climb again with those exact sums.
+constexpr int FOLD_MAX = 8192;            // gas particles per node the fold kernel sorts in shared memory
 
 __global__ void __launch_bounds__(TPB) k_gas_flags(AgbDev d, int32_t* __restrict__ flag)
 {
@@ -86,38 +88,40 @@ __global__ void __launch_bounds__(TPB) k_gas_compact(AgbDev d, const uint32_t* _
     g_m[r] = d.src_pm[i].w;
 }
 
-struct GasFold { const int32_t* gasrank; const uint32_t* g_orig; const double* g_m; };
+struct GasFold {
+    const int32_t* gasrank; const uint32_t* g_orig; const double* g_m;
+    uint8_t* nflag;            // per node: 0 = tree-order sum only, 1 = exact sum requested, 2 = exact sum ready, 3 = too large to fold
+    double* nexact;            // per node: the reference's left-fold gasMass
+    int32_t* foldlist;         // flagged nodes
+    uint8_t* pending;          // per tree-order particle: parked in pass 0
+};
 
-// left fold of the masses of the gas particles ranked [g0, g0+k) taken in increasing caller index
-__device__ double fold_in_caller_order(const GasFold& F, int g0, int k)
+__device__ __forceinline__ void node_gas_range(const AgbDev& d, const GasFold& F, const AgbScalars* s, int k, int* g0, int* g1)
 {
-    double sum = 0.0;
-    long long prev = -1;
-    for (int it = 0; it < k; it++) {
-        long long best = 1ll << 40; int bi = 0;
-        for (int r = 0; r < k; r++) { const long long o = F.g_orig[g0 + r]; if (o > prev && o < best) { best = o; bi = r; } }
-        sum = __dadd_rn(sum, F.g_m[g0 + bi]);
-        prev = best;
+    if (k == 0 && d.n >= (int64_t)d.cores * 100) { *g0 = 0; *g1 = s->n_gas_total; }     // the root sums every particle it is handed (Node.cpp:477-480)
+    else { *g0 = F.gasrank[d.nfirst[k]]; *g1 = F.gasrank[d.nlast[k] + 1]; }
+}
+
+__device__ __forceinline__ void flag_node(const GasFold& F, AgbScalars* s, int k)
+{
+    // idempotent byte store + one list slot per node: the first writer (CAS on the aligned word holding the byte) appends
+    unsigned int* word = reinterpret_cast<unsigned int*>(F.nflag + (k & ~3));
+    const unsigned int sh = (k & 3) * 8;
+    unsigned int old = *word;
+    while (((old >> sh) & 0xffu) == 0u) {
+        const unsigned int prev = atomicCAS(word, old, old | (1u << sh));
+        if (prev == old) { F.foldlist[atomicAdd(&s->n_fold, 1)] = k; break; }
+        old = prev;
     }
-    return sum;
 }
 
-// exact gasMass of internal node k (returns false if the node holds too many gas particles to fold)
-__device__ bool exact_gas(const AgbDev& d, const GasFold& F, const AgbScalars* s, int k, double* out)
-{
-    int g0, g1;
-    if (k == 0 && d.n >= (int64_t)d.cores * 100) { g0 = 0; g1 = s->n_gas_total; }       // the root sums every particle it is handed (Node.cpp:477-480)
-    else { g0 = F.gasrank[d.nfirst[k]]; g1 = F.gasrank[d.nlast[k] + 1]; }
-    if (g1 - g0 > FOLD_CAP) return false;
-    *out = fold_in_caller_order(F, g0, g1 - g0);
-    return true;
-}
-
+template <int PASS>
 __global__ void __launch_bounds__(TPB) k_gas_mark(AgbDev d, AgbScalars* s, double M, GasFold F)
 {
     int64_t i = (int64_t)blockIdx.x * TPB + threadIdx.x;
     if (i >= s->n_in_tree) return;
     if (d.s_type[i] != 2) return;
+    if (PASS == 1 && !F.pending[i]) return;
     const int N = (int)d.n;
     const double tau = 1e-9;
     // cur = -1 encodes "the particle's own leaf"
@@ -130,25 +134,71 @@ __global__ void __launch_bounds__(TPB) k_gas_mark(AgbDev d, AgbScalars* s, doubl
         if (par < 0) return;                                   // root: parent == nullptr (Node.cpp:727)
         double gp = gas_of(d, N + par);
         bool gp_exact = false;
+        if (PASS == 1 && F.nflag[par] == 2) { gp = F.nexact[par]; gp_exact = true; }
         double d0 = fabs(__dadd_rn(M, -g)), d1 = fabs(__dadd_rn(M, -gp));
         if (fabs(g - M) <= tau * M || fabs(d0 - d1) <= tau * fmax(M, gp)) {
-            // a decision of Node.cpp:737-751 hangs on the last bits: use the reference's own sums
-            bool ok = true;
-            const int kc = cur < 0 ? 1 : F.gasrank[d.nlast[cur] + 1] - F.gasrank[d.nfirst[cur]];
-            const int kp = (par == 0 && d.n >= (int64_t)d.cores * 100) ? s->n_gas_total : F.gasrank[d.nlast[par] + 1] - F.gasrank[d.nfirst[par]];
-            if (kc == kp) { gp = g; gp_exact = g_exact; }      // same gas particles, same order: the reference's two sums are identical
-            else {
-                if (!g_exact) { ok = exact_gas(d, F, s, cur, &g); g_exact = ok; }
-                if (ok) { ok = exact_gas(d, F, s, par, &gp); gp_exact = ok; }
-                atomicAdd(ok ? &s->tie_exact : &s->tie_unresolved, 1);
+            // a decision of Node.cpp:737-751 hangs on the last bits of the two sums
+            int a0, a1, b0, b1;
+            if (cur < 0) { a0 = 0; a1 = 1; } else node_gas_range(d, F, s, cur, &a0, &a1);
+            node_gas_range(d, F, s, par, &b0, &b1);
+            if (a1 - a0 == b1 - b0) { gp = g; gp_exact = g_exact; d1 = d0; }   // same gas particles in the same order: the reference's sums are identical
+            else if (PASS == 0) {
+                // park: request exact sums for this node and for every ancestor that can still take part in a tie
+                if (cur >= 0) flag_node(F, s, cur);
+                for (int a = par; a >= 0; a = d.nparent[a]) { flag_node(F, s, a); if (gas_of(d, N + a) > 2.0 * M * (1.0 + 1e-6)) break; }
+                F.pending[i] = 1;
+                return;
+            } else {
+                atomicAdd((g_exact && gp_exact) ? &s->tie_exact : &s->tie_unresolved, 1);
             }
-            d0 = fabs(__dadd_rn(M, -g)); d1 = fabs(__dadd_rn(M, -gp));
         }
         if (g < M && d0 > d1) { cur = par; g = gp; g_exact = gp_exact; continue; } // Node.cpp:737-746 (after the recursion the 2nd test is false)
         if (d0 < d1) {                                         // Node.cpp:749-751: compute here
             if (cur < 0) d.leafmark[i] = 1; else d.nmark[cur] = 1;
         }
         return;
+    }
+}
+
+// one block per flagged node: gas particles -> shared memory, bitonic sort by caller index, serial left fold
+__global__ void __launch_bounds__(TPB) k_gas_fold(AgbDev d, AgbScalars* s, GasFold F)
+{
+    extern __shared__ __align__(16) unsigned char fold_smem[];
+    double* sm_m = reinterpret_cast<double*>(fold_smem);
+    uint32_t* sm_i = reinterpret_cast<uint32_t*>(sm_m + FOLD_MAX);
+    for (int q = blockIdx.x; q < s->n_fold; q += gridDim.x) {
+        const int k = F.foldlist[q];
+        int g0, g1;
+        node_gas_range(d, F, s, k, &g0, &g1);
+        const int cnt = g1 - g0;
+        if (cnt > FOLD_MAX) { if (threadIdx.x == 0) F.nflag[k] = 3; continue; }
+        int p2 = 1;
+        while (p2 < cnt) p2 <<= 1;
+        __syncthreads();
+        for (int j = threadIdx.x; j < p2; j += TPB) {
+            sm_i[j] = j < cnt ? F.g_orig[g0 + j] : 0xffffffffu;
+            sm_m[j] = j < cnt ? F.g_m[g0 + j] : 0.0;
+        }
+        __syncthreads();
+        for (int size = 2; size <= p2; size <<= 1)
+            for (int stride = size >> 1; stride > 0; stride >>= 1) {
+                for (int j = threadIdx.x; j < p2; j += TPB) {
+                    const int partner = j ^ stride;
+                    if (partner > j) {
+                        const bool up = (j & size) == 0;
+                        const uint32_t a = sm_i[j], b = sm_i[partner];
+                        if ((a > b) == up) { sm_i[j] = b; sm_i[partner] = a; const double t = sm_m[j]; sm_m[j] = sm_m[partner]; sm_m[partner] = t; }
+                    }
+                }
+                __syncthreads();
+            }
+        if (threadIdx.x == 0) {
+            double sum = 0.0;
+            for (int j = 0; j < cnt; j++) sum = __dadd_rn(sum, sm_m[j]);
+            F.nexact[k] = sum;
+            __threadfence();
+            F.nflag[k] = 2;
+        }
     }
 }
 
@@ -231,7 +281,7 @@ __global__ void __launch_bounds__(TPB) k_gas_scatter(AgbDev d, const uint32_t* _
     d.h[p] = d.s_h[i]; d.rho[p] = d.s_rho[i]; d.P[p] = d.s_P[i]; d.T[p] = d.s_T[i];
 }
 
-__global__ void k_gas_reset(AgbScalars* s) { s->n_gas_groups = 0; s->n_gas_orphans = 0; s->tie_exact = 0; s->tie_unresolved = 0; }
+__global__ void k_gas_reset(AgbScalars* s) { s->n_gas_groups = 0; s->n_gas_orphans = 0; s->tie_exact = 0; s->tie_unresolved = 0; s->n_fold = 0; }
 
 } // namespace
 
@@ -255,11 +305,21 @@ int agb_launch_gas_density(AgbDev& d, AgbScalars* s, double massInH, cudaStream_
     int launches = agb_launch_scan_i32(d.nodecnt, d.gasrank, d.n, d.scanblk, &s->n_gas_total, st);
     cudaMemcpyAsync(d.gasrank + d.n, &s->n_gas_total, sizeof(int32_t), cudaMemcpyDeviceToDevice, st);
     k_gas_compact<<<nb, TPB, 0, st>>>(d, d.perm[d.cur], g_orig, g_m);
-    GasFold F{d.gasrank, g_orig, g_m};
-    k_gas_mark<<<nb, TPB, 0, st>>>(d, s, massInH, F);
+    // nflag/pending/foldlist/nexact borrow scratch that is idle here: arrived (int32/node), lcp (int8/particle),
+    // nodebase (int32/particle), and the idle ping-pong half of key_lo (8 B/particle)
+    GasFold F{d.gasrank, g_orig, g_m, reinterpret_cast<uint8_t*>(d.arrived), reinterpret_cast<double*>(d.klo[d.cur ^ 1]), d.nodebase,
+              reinterpret_cast<uint8_t*>(d.lcp)};
+    cudaMemsetAsync(d.arrived, 0, (size_t)d.n * sizeof(int32_t), st);
+    cudaMemsetAsync(d.lcp, 0, (size_t)d.n, st);
+    k_gas_mark<0><<<nb, TPB, 0, st>>>(d, s, massInH, F);
+    static bool attr = false;
+    const int fold_smem = FOLD_MAX * 12;
+    if (!attr) { cudaFuncSetAttribute(k_gas_fold, cudaFuncAttributeMaxDynamicSharedMemorySize, fold_smem); attr = true; }
+    k_gas_fold<<<296, TPB, fold_smem, st>>>(d, s, F);
+    k_gas_mark<1><<<nb, TPB, 0, st>>>(d, s, massInH, F);
     k_gas_group<<<nb, TPB, 0, st>>>(d, s);
     k_gas_collect<<<nb, TPB, 0, st>>>(d, s);
     k_gas_sum<<<nblk(d.n, TPB / 32), TPB, 0, st>>>(d, s);     // upper bound on groups; surplus warps exit
     k_gas_scatter<<<nb, TPB, 0, st>>>(d, d.perm[d.cur]);
-    return 8 + launches;
+    return 10 + launches;
 }

@@ -69,7 +69,8 @@ struct AgbScalars {
     int32_t bintotal[256];
     int32_t vis_level;
     int32_t walk_overflow, any_gas;
-    int32_t n_gas_total, tie_exact, tie_unresolved;
+    int32_t n_gas_total, tie_exact, tie_unresolved, n_fold;
+    unsigned long long st_rounds, st_popped, st_mixed, st_open, st_drain;   // walk statistics (tuning)
 };
 
 // ---- host-callable launchers (each returns the number of kernels it launched) ----

@@ -44,6 +44,7 @@ struct WarpSmem {
     int2 stack[SCAP];
     double4 stage[32];                     // drain: the 32 sources of a tile; traversal: (COM, mass) of straddling nodes
     int4 mch[64];                          // traversal: the 8 child slots of straddling nodes
+    double4 tsph[32];                      // per gas target: 1/h, 1/(pi h^4), 2 P/rho^2, sound speed (kept out of registers)
 };
 
 // 1/sqrt(x) for positive normal x: MUFU.RSQ64H seed (~2^-22) + one cubically convergent step (~2^-60).
@@ -107,6 +108,7 @@ __global__ void __launch_bounds__(WALK_TPB, 2) k_walk(const WalkParams P)
     const double GR3 = kG * invR2 * sqrt(invR2);
 
     unsigned long long tot_node = 0, tot_leaf = 0, tot_sph = 0, tot_visit = 0, tot_exact = 0, tot_spill = 0;
+    unsigned long long st_rounds = 0, st_popped = 0, st_mixed = 0, st_open = 0, st_drain = 0;
 
     auto stack_put = [&](int idx, int2 v) {
         if (idx < SCAP) sm.stack[idx] = v;
@@ -131,17 +133,16 @@ __global__ void __launch_bounds__(WALK_TPB, 2) k_walk(const WalkParams P)
         const bool valid = active && tp.w != 0.0;                               // Node.cpp:265
         // per-target SPH constants (the reference overrides h_j, rho_j, P_j with the target's, Node.cpp:94,101,108)
         bool tgas = false;
-        double h_t = 0, hh4 = 0, inv_pi_h4 = 0, A2 = 0, cs = 0, tvx = 0, tvy = 0, tvz = 0;
+        double h_t = 0, hh4 = 0, hh4c = 0;
         if (SPH && valid && P.s_type[t] == 2) {
             tgas = true;
             h_t = P.s_h[t];
-            const double rho = P.s_rho[t], Pr = P.s_P[t];
             hh4 = 4.0 * h_t * h_t;
-            inv_pi_h4 = 1.0 / (kPI * h_t * h_t * h_t) / h_t;
-            A2 = Pr / (rho * rho) + Pr / (rho * rho);
-            cs = sqrt(kGAMMA * Pr / rho);
-            const double4 v = P.src_gv[t];
-            tvx = v.x; tvy = v.y; tvz = v.z;
+            hh4c = hh4 * (1.0 + 1e-13);
+            // the reference overrides h_j, rho_j, P_j with the target's own values (Node.cpp:94,101,108)
+            const double rho = P.s_rho[t], Pr = P.s_P[t];
+            const double inv_h = 1.0 / h_t, pr2 = Pr / (rho * rho);
+            sm.tsph[lane] = make_double4(inv_h, inv_h * inv_h * inv_h * inv_h / kPI, pr2 + pr2, sqrt(kGAMMA * Pr / rho));
         }
         double ax = 0, ay = 0, az = 0, dU = 0;
         int c_vis = (active && (n_nodes > 0 || !valid)) ? 1 : 0, c_an = 0, c_al = 0, c_sp = 0;              // the root call itself
@@ -218,6 +219,7 @@ __global__ void __launch_bounds__(WALK_TPB, 2) k_walk(const WalkParams P)
                     // straddling nodes: exact per-lane test.  Their (COM, mass) and child slots are parked in shared
                     // memory by the owning lanes first, so the serial loop below never waits on global memory.
                     unsigned mm = __ballot_sync(0xffffffffu, outcome == OUT_MIXED);
+                    if (lane == 0) { st_rounds++; st_popped += cnt; st_mixed += __popc(mm); st_open += __popc(om); }
                     if (mm) {
                         if (outcome == OUT_MIXED) {
                             sm.stage[lane] = make_double4(pmx, pmy, pmz, rad2);
@@ -264,14 +266,16 @@ __global__ void __launch_bounds__(WALK_TPB, 2) k_walk(const WalkParams P)
                 }
 
                 // ------------------------------------------------ drain the interaction list
+                if (lane == 0) st_drain += (lc + 31) / 32;
                 for (int base = 0; base < lc; base += 32) {
                     const int cnt = min(32, lc - base);
                     __syncwarp();
+                    bool src_gas = false;
                     if (lane < cnt) {
-                        int2 e = sm.list[base + lane];
+                        const int2 e = sm.list[base + lane];
                         const double4 q = P.src_pm[e.x];
                         sm.stage[lane] = q;
-                        if (SPH && P.src_flag[e.x]) sm.list[base + lane].x = e.x | GASBIT;
+                        if (SPH) src_gas = P.src_flag[e.x] != 0;
                         // accepted pairs of this entry: lanes in the mask, minus the target's own leaf, none for a massless leaf
                         unsigned m = (unsigned)e.y;
                         const int64_t self_lane = (int64_t)e.x - (P.t0 + (int64_t)g * 32);
@@ -279,46 +283,62 @@ __global__ void __launch_bounds__(WALK_TPB, 2) k_walk(const WalkParams P)
                         const unsigned pc = q.w != 0.0 ? __popc(m) : 0u;
                         if (e.x < N) tot_leaf += pc; else tot_node += pc;
                     }
+                    const unsigned gasmask = SPH ? __ballot_sync(0xffffffffu, src_gas) : 0u;   // tile entries that hold gas
                     __syncwarp();
+                    unsigned gate = 0;                                                   // per lane: entries within ~2h (SPH candidates)
 #pragma unroll 4
                     for (int j = 0; j < cnt; j++) {
                         const int2 e = sm.list[base + j];
                         const double4 q = sm.stage[j];
-                        const int src = e.x & IDXMASK;
                         const bool bit = ((unsigned)e.y >> lane) & 1u;
                         const double dx = q.x - tp.x, dy = q.y - tp.y, dz = q.z - tp.z;
                         const double r2 = fma(dz, dz, fma(dy, dy, dx * dx));
-                        // skip: not mine, zero-mass leaf (Node.cpp:390), myself (Node.cpp:260), r == 0 (Node.cpp:274)
-                        const bool seen = bit && q.w != 0.0;
-                        const bool ok = seen && src != (int)t && r2 != 0.0;
+                        // No select is needed for the reference's skip rules: a massless leaf (Node.cpp:390) has q.w = 0;
+                        // the target's own leaf (Node.cpp:260) and any coincident source (r == 0, Node.cpp:274) have
+                        // d = 0 exactly, so f * d = 0 as long as f stays finite, which the 1e-300 guard ensures.
                         const double r2s = r2 * invR2, q2 = r2s + e02s;
-                        const double w = rsqrt_pos(r2s * q2 * q2);                         // 1 / (r (r^2 + e0^2)) in units of R
-                        const double f = ok ? GR3 * q.w * w : 0.0;
+                        const double w = rsqrt_pos(fma(r2s * q2, q2, 1e-300));   // 1 / (r (r^2 + e0^2)) in units of R
+                        const double f = (bit ? GR3 * q.w : 0.0) * w;
                         ax = fma(f, dx, ax); ay = fma(f, dy, ay); az = fma(f, dz, az);
+                        if (SPH) gate |= (r2 < hh4c ? 1u : 0u) << j;                     // hh4c = 0 for non-gas targets: never set
                         if (COUNT) {
-                            if (src < N) { c_vis += seen; c_al += ok; } else c_an += ok;
+                            const bool seen = bit && q.w != 0.0;
+                            const bool ok = seen && r2 != 0.0;
+                            if (e.x < N) { c_vis += seen; c_al += ok; } else c_an += ok;
                         }
-                        if (SPH) {
-                            if (ok && tgas && (e.x & GASBIT)) {
-                                // gate r < 2 h_i (Node.cpp:316,368): guarded fast test, exact expression near the threshold
-                                bool pass;
-                                if (r2 < hh4 * (1.0 - 1e-13)) pass = true;
-                                else if (r2 > hh4 * (1.0 + 1e-13)) pass = false;
-                                else {
+                    }
+                    if (SPH) {
+                        // second pass over the few (target, source) pairs that can pass r < 2 h_i (Node.cpp:316-325, :368-377)
+                        gate &= gasmask;
+                        unsigned any = __reduce_or_sync(0xffffffffu, gate);
+                        while (any) {
+                            const int j = __ffs(any) - 1;
+                            any &= any - 1;
+                            const int2 e = sm.list[base + j];
+                            if (((gate >> j) & 1u) && (((unsigned)e.y >> lane) & 1u)) {
+                                const double4 q = sm.stage[j];
+                                const double dx = q.x - tp.x, dy = q.y - tp.y, dz = q.z - tp.z;
+                                const double r2 = fma(dz, dz, fma(dy, dy, dx * dx));
+                                bool pass = q.w != 0.0 && r2 != 0.0;
+                                if (pass && !(r2 < hh4 * (1.0 - 1e-13))) {
+                                    // within 1e-13 of the gate: the reference's own separately rounded expression
                                     const double r2e = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
                                     pass = __dsqrt_rn(r2e) < __dmul_rn(h_t, 2.0);
                                     tot_exact++;
                                 }
                                 if (pass) {
-                                    const double4 gv = P.src_gv[src];            // (mVel | particle velocity, gasMass)
-                                    const double r = sqrt(r2), qq = r / h_t;
+                                    const double4 gv = P.src_gv[e.x];            // (mVel | particle velocity, gasMass)
+                                    const double4 tv = P.src_gv[t];
+                                    const double4 k4 = sm.tsph[lane];
+                                    const double inv_h = k4.x, inv_pi_h4 = k4.y, A2 = k4.z, cs = k4.w;
+                                    const double rinv = rsqrt_pos(r2), r = r2 * rinv, qq = r * inv_h;
                                     double gs = 0.0;                             // kernel.cpp:28-34
                                     if (qq < 1.0) gs = -3.0 * qq + 2.25 * qq * qq;
                                     else if (qq < 2.0) { const double u = 2.0 - qq; gs = -0.75 * u * u; }
-                                    const double gfac = gs * inv_pi_h4 / r;
+                                    const double gfac = gs * inv_pi_h4 * rinv;
                                     const double sx = -dx, sy = -dy, sz = -dz;   // d = x_i - COM (Node.cpp:116)
                                     const double gx = sx * gfac, gy = sy * gfac, gz = sz * gfac;
-                                    const double vx = tvx - gv.x, vy = tvy - gv.y, vz = tvz - gv.z;
+                                    const double vx = tv.x - gv.x, vy = tv.y - gv.y, vz = tv.z - gv.z;
                                     const double vd = vx * sx + vy * sy + vz * sz;
                                     const double mu = h_t * vd / (r2 + 0.01 * (h_t * h_t));
                                     const double MU = vd < 0.0 ? (-0.5 * cs * mu + mu * mu) : 0.0;     // Node.cpp:142-152
@@ -358,12 +378,15 @@ __global__ void __launch_bounds__(WALK_TPB, 2) k_walk(const WalkParams P)
         if (tot_visit) atomicAdd(&P.s->c_visits, tot_visit);
         if (tot_exact) atomicAdd(&P.s->c_exact, tot_exact);
         if (tot_spill) atomicAdd(&P.s->c_spill, tot_spill);
+        atomicAdd(&P.s->st_rounds, st_rounds); atomicAdd(&P.s->st_popped, st_popped); atomicAdd(&P.s->st_mixed, st_mixed);
+        atomicAdd(&P.s->st_open, st_open); atomicAdd(&P.s->st_drain, st_drain);
     }
 }
 
 __global__ void k_walk_reset(AgbScalars* s)
 {
     s->walk_next_group = 0; s->walk_overflow = 0;
+    s->st_rounds = 0; s->st_popped = 0; s->st_mixed = 0; s->st_open = 0; s->st_drain = 0;
     s->c_interactions = 0; s->c_node = 0; s->c_leaf = 0; s->c_sph = 0; s->c_visits = 0; s->c_exact = 0; s->c_spill = 0;
 }
 

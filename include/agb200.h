@@ -86,6 +86,9 @@ typedef struct {
     int64_t groups, gas_groups, gas_orphans;
     int64_t gas_ties_exact;         /* density-group decisions re-taken with the reference's own left-fold gasMass sums */
     int64_t gas_ties_unresolved;    /* ... that involved more than 1024 gas particles and kept the tree-order sums       */
+    /* walk statistics: pop rounds, nodes popped, nodes straddling the opening radius of their warp, nodes opened by the
+     * whole mask, 32-source tiles drained, rounds that touched the global-memory part of the stack */
+    int64_t walk_rounds, walk_popped, walk_straddling, walk_opened, walk_tiles, walk_stack_spills;
 } agb_counters;
 
 /* -------- lifetime: `new Tree(sim)` / `delete tree`, but persistent across steps (pooled memory) */
