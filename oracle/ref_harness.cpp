@@ -191,12 +191,16 @@ int cmd_run(int argc, char** argv)
     for (int64_t i = 0; i < n; i++) {
         Particle* p = sim.particles[(size_t)i];
         Counters c;
+#ifndef AG_GPU_TREE   // with the GPU Tree there is no host-side Node tree to walk
         if (sim.globalTime == p->nextIntegrationTime) count_walk(t.root, p, sim.theta, c);
+#endif
         c0[(size_t)i] = c.visits; c1[(size_t)i] = c.acc_nodes; c2[(size_t)i] = c.acc_leaves; c3[(size_t)i] = c.sph;
     }
     wr(f, c0); wr(f, c1); wr(f, c2); wr(f, c3);
     NodeDump D;
+#ifndef AG_GPU_TREE
     if (want_nodes) dump_nodes(t.root, 0, 0, 0, D);
+#endif
     int64_t m = (int64_t)D.depth.size();
     fwrite(&m, 8, 1, f);
     wr(f, D.depth); wr(f, D.isLeaf); wr(f, D.nchild); wr(f, D.hi); wr(f, D.lo);
@@ -231,7 +235,7 @@ int cmd_time(int argc, char** argv)
     sim.numberOfParticles = (int)sim.particles.size();
     sim.theta = atof(argv[3]); sim.e0 = atof(argv[4]); sim.massInH = atof(argv[5]); sim.globalTime = atof(argv[6]);
     int reps = atoi(argv[7]);
-#ifdef _OPENMP
+#if defined(_OPENMP)
     ag_stub_cores = 0;
 #else
     if (getenv("AG_CORES")) ag_stub_cores = atoi(getenv("AG_CORES"));
