@@ -191,19 +191,17 @@ def run_gpu_arm(args, pkg):
 
     f8 = ["x", "y", "z", "vx", "vy", "vz", "mass", "U", "next_time", "mu"] if any_gas else ["x", "y", "z", "mass"]
     # rank-local shard of the particle arrays (what a distributed driver would own and integrate)
-    lo, hi = n * rank // world, n * (rank + 1) // world
+    lo, hi = pkg.shard.shard_bounds(n, rank, world)
     shard = {k: torch.from_numpy(np.ascontiguousarray(p[k][lo:hi])).to(dev) for k in f8}
     shard["type"] = torch.from_numpy(np.ascontiguousarray(p["type"][lo:hi])).to(dev)
     full = {k: (torch.empty(n, dtype=v.dtype, device=dev) if world > 1 else v) for k, v in shard.items()}
-    counts = [n * (r + 1) // world - n * r // world for r in range(world)]
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)      # > 126 MB L2
 
+    scratch = {}
+
     def gather():
-        if world == 1:
-            return
-        for k in full:
-            outs = list(torch.split(full[k], counts))
-            dist.all_gather(outs, shard[k])
+        if world > 1:
+            pkg.shard.gather_particles(shard, n, world, out=full, scratch=scratch)
 
     def step():
         gather()

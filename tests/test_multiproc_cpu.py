@@ -1,0 +1,57 @@
+"""World-size-2 gloo tests (CPU) of the N > 1 host logic: particle sharding, the per-step all-gather and
+the tree-order slice rule that agb_forces_slice applies."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _worker(rank, world, port, n, q):
+    sys.path.insert(0, ROOT)
+    import __graft_entry__ as ge
+    pkg = ge.load_package()
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        p = pkg.ics.plummer(n, seed=5, gas_fraction=0.3)
+        lo, hi = pkg.shard.shard_bounds(n, rank, world)
+        shard = {k: torch.from_numpy(np.ascontiguousarray(p[k][lo:hi])) for k in ("x", "y", "z", "mass", "vx", "type")}
+        full = pkg.shard.gather_particles(shard, n, world)
+        ok = all(np.array_equal(full[k].numpy(), p[k]) for k in shard)
+        q.put((rank, ok, pkg.shard.slice_bounds(n, rank, world)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n", [1000, 4099])
+def test_gather_and_slices_world2(n):
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_worker, args=(r, world, port, n, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(ok for _, ok, _ in res)
+    (a0, a1), (b0, b1) = res[0][2], res[1][2]
+    assert a0 == 0 and a1 == b0 and b1 == n and a1 % 32 == 0          # contiguous cover, boundaries on warp groups
+
+
+def test_slice_rule_covers_everything(pkg):
+    for n in (0, 1, 31, 32, 33, 1000, 1_000_000, 16_000_001):
+        for parts in (1, 2, 4, 8):
+            b = [pkg.shard.slice_bounds(n, r, parts) for r in range(parts)]
+            assert b[0][0] == 0 and b[-1][1] == n
+            assert all(b[i][1] == b[i + 1][0] for i in range(parts - 1))
+            assert all(x[0] % 32 == 0 for x in b)
+            assert sum(pkg.shard.shard_counts(n, parts)) == n
