@@ -82,7 +82,7 @@ int ensure_pool(agb_ctx* c, int64_t n)
     CK(dalloc(d.dist, cap));
     for (auto& q : c->in_d) CK(dalloc(q, cap));
     CK(dalloc(c->in_type, cap));
-    CK(dalloc(d.blockhist, 256 * ((cap + 2047) / 2048 + 1)));
+    CK(dalloc(d.blockhist, 256 * ((cap + 2047) / 2048 + 1)));   // sort tiles are >= 2048 keys
     CK(dalloc(d.scanblk, (cap + 2047) / 2048 + 1));
     d.cap = (int64_t)cap;
     return AGB_OK;
@@ -441,7 +441,7 @@ int agb_get_nodes(agb_ctx* c, int32_t* depth, int64_t* count, int32_t* duplicate
     CK(cudaMemcpyAsync(pm.data(), d.src_pm + n, (size_t)m * sizeof(double4), cudaMemcpyDeviceToHost, c->st));
     CK(cudaMemcpyAsync(gv.data(), d.src_gv + n, (size_t)m * sizeof(double4), cudaMemcpyDeviceToHost, c->st));
     CK(cudaMemcpyAsync(khi.data(), d.khi[d.cur], (size_t)n * 8, cudaMemcpyDeviceToHost, c->st));
-    CK(cudaMemcpyAsync(klo.data(), d.klo[d.cur], (size_t)n * 8, cudaMemcpyDeviceToHost, c->st));
+    CK(cudaMemcpyAsync(klo.data(), d.klo[1], (size_t)n * 8, cudaMemcpyDeviceToHost, c->st));
     CK(cudaStreamSynchronize(c->st));
     for (int64_t k = 0; k < m; k++) {
         const int dp = dep[(size_t)k];

@@ -79,7 +79,7 @@ __global__ void k_extent_finish(AgbScalars* s, int nblocks, int64_t n)
     s->mean = mean; s->stdev = sd;
     s->limit = __dadd_rn(mean, __dmul_rn(10.0, sd));     // Tree.cpp:89,105
     s->Rbits = 0ull;
-    s->any_gas = 0; s->n_outliers = 0; s->dup_keys = 0; s->edge_dropped = 0; s->max_depth = 0; s->n_nodes = 0;
+    s->n_long_runs = 0; s->any_gas = 0; s->n_outliers = 0; s->dup_keys = 0; s->edge_dropped = 0; s->max_depth = 0; s->n_nodes = 0;
 }
 
 __global__ void __launch_bounds__(TPB) k_extent_max(const double* __restrict__ dist, int64_t n, AgbScalars* s)
@@ -142,22 +142,25 @@ __global__ void __launch_bounds__(TPB) k_keygen(const double* __restrict__ x, co
 }
 
 // ------------------------------------------------------------------ LSD radix sort (8-bit digits)
-constexpr int SORT_ITEMS = 8;
-constexpr int SORT_TILE = TPB * SORT_ITEMS;       // 2048 keys per block
+// Only key_hi (outlier flag + the first 21 levels) is radix sorted, together with the caller index: 8 stable
+// passes over 12-byte items.  key_lo (levels 21..41) matters only between particles that share all 21 upper
+// levels; it is gathered afterwards and those (short, rare) runs are ordered by k_fix_runs / k_fix_long_runs.
+template <int ITEMS> struct SortCfg { static constexpr int TILE = TPB * ITEMS; };
 
 __device__ __forceinline__ uint32_t digit_of(uint64_t w, int shift) { return (uint32_t)(w >> shift) & 255u; }
 
 // per-block digit histogram, written bin-major: hist[bin * nblocks + block]
+template <int ITEMS>
 __global__ void __launch_bounds__(TPB) k_sort_hist(const uint64_t* __restrict__ word, int64_t n, int shift, uint32_t* __restrict__ hist, int nblocks)
 {
     __shared__ uint32_t h[256];
     h[threadIdx.x] = 0;
     __syncthreads();
-    const int64_t base = (int64_t)blockIdx.x * SORT_TILE;
+    const int64_t base = (int64_t)blockIdx.x * SortCfg<ITEMS>::TILE;
     const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
 #pragma unroll
-    for (int j = 0; j < SORT_ITEMS; j++) {
-        int64_t i = base + (int64_t)w * (32 * SORT_ITEMS) + j * 32 + l;
+    for (int j = 0; j < ITEMS; j++) {
+        int64_t i = base + (int64_t)w * (32 * ITEMS) + j * 32 + l;
         if (i < n) atomicAdd(&h[digit_of(word[i], shift)], 1u);
     }
     __syncthreads();
@@ -194,20 +197,26 @@ __global__ void __launch_bounds__(1024) k_sort_scan(uint32_t* __restrict__ hist,
     if (threadIdx.x == 0) s->bintotal[blockIdx.x] = (int32_t)carry;
 }
 
-// stable scatter: rank inside the block by warp match + per-warp digit counters
-__global__ void __launch_bounds__(TPB) k_sort_scatter(const uint64_t* __restrict__ ihi, const uint64_t* __restrict__ ilo, const uint32_t* __restrict__ iv,
-                                                        uint64_t* __restrict__ ohi, uint64_t* __restrict__ olo, uint32_t* __restrict__ ov,
-                                                        int64_t n, int pass, const uint32_t* __restrict__ hist, int nblocks, const AgbScalars* __restrict__ s)
+// stable scatter: rank inside the block by warp match + per-warp digit counters, reorder the tile in shared
+// memory so that every digit's items leave as one contiguous, coalesced run
+template <int ITEMS>
+__global__ void __launch_bounds__(TPB) k_sort_scatter(const uint64_t* __restrict__ ihi, const uint32_t* __restrict__ iv,
+                                                        uint64_t* __restrict__ ohi, uint32_t* __restrict__ ov,
+                                                        int64_t n, int shift, const uint32_t* __restrict__ hist, int nblocks, const AgbScalars* __restrict__ s)
 {
-    __shared__ uint32_t wcnt[TPB / 32][256];
-    __shared__ uint32_t gbase[256];
+    constexpr int TILE = SortCfg<ITEMS>::TILE;
+    extern __shared__ __align__(16) unsigned char sort_smem[];
+    uint64_t* t_hi = reinterpret_cast<uint64_t*>(sort_smem);                 // [TILE]
+    uint32_t* t_v = reinterpret_cast<uint32_t*>(t_hi + TILE);                // [TILE]
+    uint32_t (*wcnt)[256] = reinterpret_cast<uint32_t (*)[256]>(t_v + TILE); // [TPB/32][256]
+    uint32_t* gbase = &wcnt[TPB / 32][0];                                    // [256] global base of (digit, block)
+    uint32_t* lbase = gbase + 256;                                           // [256] tile-local base of digit
+    __shared__ uint32_t ws[TPB / 32];
     const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
     for (int k = threadIdx.x; k < (TPB / 32) * 256; k += TPB) (&wcnt[0][0])[k] = 0;
-    // exclusive scan of the 256 bin totals (every block repeats this tiny scan)
-    {
+    {   // exclusive scan of the 256 bin totals (every block repeats this tiny scan)
         uint32_t v = (uint32_t)s->bintotal[threadIdx.x], inc = v;
         for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, inc, o); if (l >= o) inc += t; }
-        __shared__ uint32_t ws[TPB / 32];
         if (l == 31) ws[w] = inc;
         __syncthreads();
         uint32_t off = 0;
@@ -215,45 +224,124 @@ __global__ void __launch_bounds__(TPB) k_sort_scatter(const uint64_t* __restrict
         gbase[threadIdx.x] = off + inc - v + hist[(size_t)threadIdx.x * nblocks + blockIdx.x];
     }
     __syncthreads();
-    const int shift = (pass & 7) * 8;
-    const bool use_hi = pass >= 8;
-    const int64_t base = (int64_t)blockIdx.x * SORT_TILE + (int64_t)w * (32 * SORT_ITEMS) + l;
-    uint64_t kh[SORT_ITEMS], kl[SORT_ITEMS]; uint32_t kv[SORT_ITEMS]; uint32_t rk[SORT_ITEMS]; uint32_t dg[SORT_ITEMS];
+    const int64_t tile0 = (int64_t)blockIdx.x * TILE;
+    const int64_t base = tile0 + (int64_t)w * (32 * ITEMS) + l;
+    uint64_t kh[ITEMS]; uint32_t kv[ITEMS]; uint32_t rk[ITEMS];
 #pragma unroll
-    for (int j = 0; j < SORT_ITEMS; j++) {
+    for (int j = 0; j < ITEMS; j++) {
         int64_t i = base + j * 32;
-        if (i < n) { kh[j] = ihi[i]; kl[j] = ilo[i]; kv[j] = iv[i]; }
-        else { kh[j] = ~0ull; kl[j] = ~0ull; kv[j] = 0; }
+        if (i < n) { kh[j] = ihi[i]; kv[j] = iv[i]; } else { kh[j] = ~0ull; kv[j] = 0; }
     }
     const unsigned lt = (1u << l) - 1u;
 #pragma unroll
-    for (int j = 0; j < SORT_ITEMS; j++) {
-        int64_t i = base + j * 32;
-        bool valid = i < n;
-        uint32_t d = digit_of(use_hi ? kh[j] : kl[j], shift);
-        dg[j] = d;
-        unsigned vm = __ballot_sync(0xffffffffu, valid);
-        unsigned peers = __match_any_sync(0xffffffffu, valid ? d : 256u + (uint32_t)l) & vm;
-        uint32_t prev = valid ? wcnt[w][d] : 0u;
+    for (int j = 0; j < ITEMS; j++) {
+        const bool valid = base + j * 32 < n;
+        const uint32_t d = digit_of(kh[j], shift);
+        const unsigned vm = __ballot_sync(0xffffffffu, valid);
+        const unsigned peers = __match_any_sync(0xffffffffu, valid ? d : 256u + (uint32_t)l) & vm;
+        const uint32_t prev = valid ? wcnt[w][d] : 0u;
         __syncwarp();
         if (valid && (peers & lt) == 0) wcnt[w][d] = prev + __popc(peers);
         __syncwarp();
         rk[j] = prev + __popc(peers & lt);
     }
     __syncthreads();
-    {   // per digit: exclusive offsets across the warps of this block
+    {   // per digit: exclusive offsets across the warps of this block, then across digits
         uint32_t off = 0;
 #pragma unroll
         for (int k = 0; k < TPB / 32; k++) { uint32_t t = wcnt[k][threadIdx.x]; wcnt[k][threadIdx.x] = off; off += t; }
+        uint32_t inc = off;
+        for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, inc, o); if (l >= o) inc += t; }
+        if (l == 31) ws[w] = inc;
+        __syncthreads();
+        uint32_t woff = 0;
+        for (int k = 0; k < w; k++) woff += ws[k];
+        lbase[threadIdx.x] = woff + inc - off;
     }
     __syncthreads();
 #pragma unroll
-    for (int j = 0; j < SORT_ITEMS; j++) {
-        int64_t i = base + j * 32;
-        if (i < n) {
-            uint32_t pos = gbase[dg[j]] + wcnt[w][dg[j]] + rk[j];
-            ohi[pos] = kh[j]; olo[pos] = kl[j]; ov[pos] = kv[j];
+    for (int j = 0; j < ITEMS; j++) {
+        if (base + j * 32 < n) {
+            const uint32_t d = digit_of(kh[j], shift);
+            const uint32_t pos = lbase[d] + wcnt[w][d] + rk[j];
+            t_hi[pos] = kh[j]; t_v[pos] = kv[j];
         }
+    }
+    __syncthreads();
+    const int cnt = (int)min((int64_t)TILE, n - tile0);
+    for (int k = threadIdx.x; k < cnt; k += TPB) {
+        const uint64_t h = t_hi[k];
+        const uint32_t d = digit_of(h, shift);
+        const uint32_t pos = gbase[d] + ((uint32_t)k - lbase[d]);
+        ohi[pos] = h; ov[pos] = t_v[k];
+    }
+}
+
+// key_lo into tree order
+__global__ void __launch_bounds__(TPB) k_gather_lo(const uint64_t* __restrict__ lo_in, const uint32_t* __restrict__ perm, int64_t n, uint64_t* __restrict__ lo_out)
+{
+    int64_t i = (int64_t)blockIdx.x * TPB + threadIdx.x;
+    if (i < n) lo_out[i] = lo_in[perm[i]];
+}
+
+// runs of in-tree particles with equal key_hi (they share >= 21 levels): order them by key_lo.
+// Short runs are insertion-sorted by the thread at the run start; long ones are queued for k_fix_long_runs.
+constexpr int FIX_SHORT = 16, FIX_LONG_MAX = 4096;
+__global__ void __launch_bounds__(TPB) k_fix_runs(const uint64_t* __restrict__ hi, uint64_t* __restrict__ lo, uint32_t* __restrict__ perm, int64_t n,
+                                                    AgbScalars* s, int32_t* __restrict__ longlist)
+{
+    int64_t i = (int64_t)blockIdx.x * TPB + threadIdx.x;
+    const int64_t nt = n - s->n_outliers;
+    if (i + 1 >= nt) return;
+    const uint64_t h = hi[i];
+    if (hi[i + 1] != h || (i > 0 && hi[i - 1] == h)) return;       // not the first element of a run of >= 2
+    int64_t e = i + 1;
+    while (e + 1 < nt && hi[e + 1] == h) e++;
+    const int len = (int)(e - i + 1);
+    if (len > FIX_SHORT) {
+        if (len > FIX_LONG_MAX) { atomicAdd(&s->dup_keys, 1); return; }
+        longlist[2 * atomicAdd(&s->n_long_runs, 1)] = (int32_t)i; 
+        return;
+    }
+    for (int a = 1; a < len; a++) {                                  // stable insertion sort
+        const uint64_t kl = lo[i + a]; const uint32_t kp = perm[i + a];
+        int b = a - 1;
+        while (b >= 0 && lo[i + b] > kl) { lo[i + b + 1] = lo[i + b]; perm[i + b + 1] = perm[i + b]; b--; }
+        lo[i + b + 1] = kl; perm[i + b + 1] = kp;
+    }
+}
+
+__global__ void __launch_bounds__(TPB) k_fix_long_runs(const uint64_t* __restrict__ hi, uint64_t* __restrict__ lo, uint32_t* __restrict__ perm, int64_t n,
+                                                         const AgbScalars* __restrict__ s, const int32_t* __restrict__ longlist)
+{
+    __shared__ uint64_t sl[FIX_LONG_MAX];
+    __shared__ uint32_t sp[FIX_LONG_MAX];
+    const int64_t nt = n - s->n_outliers;
+    for (int q = blockIdx.x; q < s->n_long_runs; q += gridDim.x) {
+        const int64_t i = longlist[2 * q];
+        const uint64_t h = hi[i];
+        int64_t e = i;
+        while (e + 1 < nt && hi[e + 1] == h) e++;
+        const int len = (int)(e - i + 1);
+        int p2 = 1;
+        while (p2 < len) p2 <<= 1;
+        __syncthreads();
+        for (int j = threadIdx.x; j < p2; j += TPB) { sl[j] = j < len ? lo[i + j] : ~0ull; sp[j] = j < len ? perm[i + j] : 0xffffffffu; }
+        __syncthreads();
+        for (int size = 2; size <= p2; size <<= 1)
+            for (int stride = size >> 1; stride > 0; stride >>= 1) {
+                for (int j = threadIdx.x; j < p2; j += TPB) {
+                    const int partner = j ^ stride;
+                    if (partner > j) {
+                        const bool up = (j & size) == 0;
+                        const uint64_t a = sl[j], b = sl[partner];
+                        // ties cannot occur between real items (42-level duplicates are an error reported by k_lcp)
+                        if ((a > b) == up && a != b) { sl[j] = b; sl[partner] = a; const uint32_t t = sp[j]; sp[j] = sp[partner]; sp[partner] = t; }
+                    }
+                }
+                __syncthreads();
+            }
+        for (int j = threadIdx.x; j < len; j += TPB) { lo[i + j] = sl[j]; perm[i + j] = sp[j]; }
     }
 }
 
@@ -593,26 +681,39 @@ int agb_launch_keygen(AgbDev& d, AgbScalars* s, cudaStream_t st)
     return 1;
 }
 
+template <int ITEMS>
+static int sort_passes(AgbDev& d, AgbScalars* s, cudaStream_t st)
+{
+    constexpr int TILE = SortCfg<ITEMS>::TILE;
+    const int nb = nblk(d.n, TILE);
+    const int smem = TILE * 12 + (TPB / 32) * 256 * 4 + 2 * 256 * 4;
+    static bool attr = false;
+    if (!attr) { cudaFuncSetAttribute(k_sort_scatter<ITEMS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr = true; }
+    for (int pass = 0; pass < 8; pass++) {
+        const int in = d.cur, out = d.cur ^ 1;
+        k_sort_hist<ITEMS><<<nb, TPB, 0, st>>>(d.khi[in], d.n, pass * 8, d.blockhist, nb);
+        k_sort_scan<<<256, 1024, 0, st>>>(d.blockhist, nb, s);
+        k_sort_scatter<ITEMS><<<nb, TPB, smem, st>>>(d.khi[in], d.perm[in], d.khi[out], d.perm[out], d.n, pass * 8, d.blockhist, nb, s);
+        d.cur = out;
+    }
+    return 24;
+}
+
 int agb_launch_sort(AgbDev& d, AgbScalars* s, cudaStream_t st)
 {
-    const int nb = nblk(d.n, SORT_TILE);
-    int launches = 0;
-    for (int pass = 0; pass < 16; pass++) {
-        const int in = d.cur, out = d.cur ^ 1;
-        const uint64_t* word = pass >= 8 ? d.khi[in] : d.klo[in];
-        k_sort_hist<<<nb, TPB, 0, st>>>(word, d.n, (pass & 7) * 8, d.blockhist, nb);
-        k_sort_scan<<<256, 1024, 0, st>>>(d.blockhist, nb, s);
-        k_sort_scatter<<<nb, TPB, 0, st>>>(d.khi[in], d.klo[in], d.perm[in], d.khi[out], d.klo[out], d.perm[out], d.n, pass, d.blockhist, nb, s);
-        d.cur = out;
-        launches += 3;
-    }
-    return launches;
+    // key_hi + caller index: 8 passes; the result lands in half 0 again.  key_lo: klo[0] caller order -> klo[1] tree order.
+    int launches = d.n >= (4 << 20) ? sort_passes<16>(d, s, st) : sort_passes<8>(d, s, st);
+    const int nb = nblk(d.n, TPB);
+    k_gather_lo<<<nb, TPB, 0, st>>>(d.klo[0], d.perm[d.cur], d.n, d.klo[1]);
+    k_fix_runs<<<nb, TPB, 0, st>>>(d.khi[d.cur], d.klo[1], d.perm[d.cur], d.n, s, d.nodecnt);
+    k_fix_long_runs<<<64, TPB, 0, st>>>(d.khi[d.cur], d.klo[1], d.perm[d.cur], d.n, s, d.nodecnt);
+    return launches + 3;
 }
 
 int agb_launch_links(AgbDev& d, AgbScalars* s, cudaStream_t st)
 {
     const int nb = nblk(d.n, TPB);
-    const uint64_t *khi = d.khi[d.cur], *klo = d.klo[d.cur];
+    const uint64_t *khi = d.khi[d.cur], *klo = d.klo[1];
     k_gather<<<nb, TPB, 0, st>>>(d, d.perm[d.cur], s);
     k_lcp<<<nb, TPB, 0, st>>>(khi, klo, d.n, d.lcp, d.nodecnt, s);
     const int sb = nblk(d.n, SCAN_TILE);
@@ -638,6 +739,6 @@ int agb_launch_scan_i32(const int32_t* in, int32_t* out, int64_t n, int32_t* blk
 
 int agb_launch_dump_tree(AgbDev& d, AgbScalars* s, int32_t* leafdepth, uint64_t* khi, uint64_t* klo, cudaStream_t st)
 {
-    k_dump_tree<<<nblk(d.n, TPB), TPB, 0, st>>>(d, d.khi[d.cur], d.klo[d.cur], d.perm[d.cur], s, leafdepth, khi, klo);
+    k_dump_tree<<<nblk(d.n, TPB), TPB, 0, st>>>(d, d.khi[d.cur], d.klo[1], d.perm[d.cur], s, leafdepth, khi, klo);
     return 1;
 }

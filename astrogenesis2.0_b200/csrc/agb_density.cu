@@ -306,8 +306,8 @@ int agb_launch_gas_density(AgbDev& d, AgbScalars* s, double massInH, cudaStream_
     cudaMemcpyAsync(d.gasrank + d.n, &s->n_gas_total, sizeof(int32_t), cudaMemcpyDeviceToDevice, st);
     k_gas_compact<<<nb, TPB, 0, st>>>(d, d.perm[d.cur], g_orig, g_m);
     // nflag/pending/foldlist/nexact borrow scratch that is idle here: arrived (int32/node), lcp (int8/particle),
-    // nodebase (int32/particle), and the idle ping-pong half of key_lo (8 B/particle)
-    GasFold F{d.gasrank, g_orig, g_m, reinterpret_cast<uint8_t*>(d.arrived), reinterpret_cast<double*>(d.klo[d.cur ^ 1]), d.nodebase,
+    // nodebase (int32/particle), and the caller-order copy of key_lo (8 B/particle)
+    GasFold F{d.gasrank, g_orig, g_m, reinterpret_cast<uint8_t*>(d.arrived), reinterpret_cast<double*>(d.klo[0]), d.nodebase,
               reinterpret_cast<uint8_t*>(d.lcp)};
     cudaMemsetAsync(d.arrived, 0, (size_t)d.n * sizeof(int32_t), st);
     cudaMemsetAsync(d.lcp, 0, (size_t)d.n, st);

@@ -69,7 +69,7 @@ struct AgbScalars {
     int32_t bintotal[256];
     int32_t vis_level;
     int32_t walk_overflow, any_gas;
-    int32_t n_gas_total, tie_exact, tie_unresolved, n_fold;
+    int32_t n_gas_total, tie_exact, tie_unresolved, n_fold, n_long_runs;
     unsigned long long st_rounds, st_popped, st_mixed, st_open, st_drain;   // walk statistics (tuning)
 };
 

@@ -49,7 +49,16 @@ CASES = {
     "plummer_30k_theta03": lambda ics: (ics.plummer(30000, seed=7), 0.3, 1e19, 32, 8),
     "serial_root_500": lambda ics: (ics.plummer(500, seed=11, gas_fraction=0.5), 0.5, 1e18, 8, 8),
     "ragged_33": lambda ics: (ics.plummer(33, seed=12, gas_fraction=0.5), 0.5, 1e18, 4, 8),
+    "deep_core_30k": lambda ics: (_deep_core(ics), 0.5, 1e16, 32, 8),
 }
+
+
+def _deep_core(ics):
+    """A dense core 1e-6 of the size of its host: leaves deeper than the 21 levels of key_hi (exercises key_lo ordering)."""
+    a = ics.plummer(27000, seed=21, gas_fraction=0.2)
+    b = ics.plummer(3000, seed=22, gas_fraction=0.2, a=10 * ics.KPC * 1e-6, mtot=1e9 * ics.MSUN)
+    return {k: np.concatenate([a[k], b[k]]) for k in a}
+
 
 
 @pytest.mark.parametrize("case", sorted(CASES))
