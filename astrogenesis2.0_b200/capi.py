@@ -12,6 +12,7 @@ _pu8 = C.POINTER(C.c_uint8)
 
 AGB_MEM_HOST, AGB_MEM_DEVICE = 0, 1
 AGB_OPT_TARGET_COUNTERS = 1
+AGB_OPT_PRECISION = 2
 
 EXPORTS = [
     "agb_create", "agb_destroy", "agb_set_particles", "agb_set_particles_aos", "agb_build_tree", "agb_visual_density",

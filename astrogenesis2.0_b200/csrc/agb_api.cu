@@ -21,6 +21,7 @@ struct agb_ctx {
     double* in_d[10] = {};             // pooled device copies of caller-order inputs (x y z vx vy vz mass U next mu)
     uint8_t* in_type = nullptr;
     bool bound = false, have_particles = false, built = false, dens_done = false, forces_done = false;
+    bool mixed = true;                  // AGB_OPT_PRECISION
     bool target_counters = false, counters_valid = false, vis_timed = false, gas_timed = false;
     double phase_ms[5] = {0, 0, 0, 0, 0};
     int64_t launches = 0;
@@ -187,6 +188,7 @@ int agb_set_option(agb_ctx* c, int option, int64_t value)
 {
     if (!c) return AGB_ERR_INVALID;
     if (option == AGB_OPT_TARGET_COUNTERS) { c->target_counters = value != 0; return AGB_OK; }
+    if (option == AGB_OPT_PRECISION) { if (value != 0 && value != 1) return AGB_ERR_INVALID; c->mixed = value == 1; return AGB_OK; }
     return AGB_ERR_INVALID;
 }
 
@@ -326,7 +328,7 @@ int agb_forces_slice(agb_ctx* c, double global_time, double e0, double theta, in
     const int64_t t0 = std::min(d.n, ngrp * part / nparts * 32), t1 = std::min(d.n, ngrp * (part + 1) / nparts * 32);
     CK(cudaEventRecord(c->ev[6], c->st));
     // gas targets need h/rho/P: if the caller skipped gas_density they are orphans (h = 0) and get no SPH, like the reference
-    c->launches += agb_launch_walk(d, c->s, global_time, e0, theta, t0, t1, c->target_counters, c->hs.any_gas != 0, c->sm_count, c->st, c->ev[0], c->ev[1]);
+    c->launches += agb_launch_walk(d, c->s, global_time, e0, theta, t0, t1, c->target_counters, c->hs.any_gas != 0, c->mixed, c->sm_count, c->st, c->ev[0], c->ev[1]);
     CK(cudaEventRecord(c->ev[7], c->st));
     CK(cudaGetLastError());
     int rc = fetch_scalars(c);

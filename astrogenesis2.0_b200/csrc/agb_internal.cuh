@@ -81,7 +81,7 @@ int agb_launch_links(AgbDev& d, AgbScalars* s, cudaStream_t st);
 int agb_launch_visual(AgbDev& d, AgbScalars* s, double radius, cudaStream_t st);
 int agb_launch_gas_density(AgbDev& d, AgbScalars* s, double massInH, cudaStream_t st);
 int agb_launch_walk(AgbDev& d, AgbScalars* s, double globalTime, double e0, double theta, int64_t t0, int64_t t1,
-                    bool counters, bool any_gas, int sm_count, cudaStream_t st, cudaEvent_t ev0, cudaEvent_t ev1);
+                    bool counters, bool any_gas, bool mixed, int sm_count, cudaStream_t st, cudaEvent_t ev0, cudaEvent_t ev1);
 int agb_launch_dump_tree(AgbDev& d, AgbScalars* s, int32_t* leafdepth, uint64_t* khi, uint64_t* klo, cudaStream_t st);
 int agb_launch_scan_i32(const int32_t* in, int32_t* out, int64_t n, int32_t* blk, int32_t* total_out, cudaStream_t st);
 int agb_launch_microbench(int kind, int sm_count, cudaStream_t st, double* result);

@@ -89,7 +89,7 @@ __device__ __forceinline__ unsigned long long warp_sum_u64(unsigned long long v)
     return v;
 }
 
-template <bool COUNT, bool SPH>
+template <bool COUNT, bool SPH, bool MIXED>
 __global__ void __launch_bounds__(WALK_TPB, 2) k_walk(const WalkParams P)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -106,6 +106,13 @@ __global__ void __launch_bounds__(WALK_TPB, 2) k_walk(const WalkParams P)
     const double invR2 = R > 0.0 ? 1.0 / (R * R) : 1.0;
     const double e02s = P.e0 * P.e0 * invR2;
     const double GR3 = kG * invR2 * sqrt(invR2);
+    // mixed precision (MIXED): displacements as float-float differences in units of R about the warp's box centre,
+    // the law in FP32 (MUFU.RSQ + MUFU.RCP), FP32 partial sums per 32-source tile, FP64 accumulation across tiles.
+    // Masses are scaled by the mean in-tree mass so every FP32 quantity stays well inside the normal range.
+    const double invR = sqrt(invR2);
+    const double m0 = n_nodes > 0 ? fmax(P.src_pm[N].w / (double)max(n_in_tree, 1), 1e-300) : (n_in_tree > 0 && P.src_pm[0].w > 0.0 ? P.src_pm[0].w : 1.0);
+    const double inv_m0 = 1.0 / m0, acc_scale = kG * m0 * invR2;
+    const float e02f = (float)e02s;
 
     unsigned long long tot_node = 0, tot_leaf = 0, tot_sph = 0, tot_visit = 0, tot_exact = 0, tot_spill = 0;
     unsigned long long st_rounds = 0, st_popped = 0, st_mixed = 0, st_open = 0, st_drain = 0;
@@ -152,6 +159,14 @@ __global__ void __launch_bounds__(WALK_TPB, 2) k_walk(const WalkParams P)
             const double inf = __longlong_as_double(0x7ff0000000000000ll);
             const double lox = warp_min(valid ? tp.x : inf), loy = warp_min(valid ? tp.y : inf), loz = warp_min(valid ? tp.z : inf);
             const double hix = warp_max(valid ? tp.x : -inf), hiy = warp_max(valid ? tp.y : -inf), hiz = warp_max(valid ? tp.z : -inf);
+            const double cgx = 0.5 * (lox + hix), cgy = 0.5 * (loy + hiy), cgz = 0.5 * (loz + hiz);
+            float thx = 0, thy = 0, thz = 0, tlx = 0, tly = 0, tlz = 0, hh4cf = 0;
+            if (MIXED) {
+                const double rx = (tp.x - cgx) * invR, ry = (tp.y - cgy) * invR, rz = (tp.z - cgz) * invR;
+                thx = (float)rx; thy = (float)ry; thz = (float)rz;
+                tlx = (float)(rx - (double)thx); tly = (float)(ry - (double)thy); tlz = (float)(rz - (double)thz);
+                hh4cf = (float)(hh4 * invR2 * (1.0 + 1e-5));               // generous: the SPH pass re-tests in FP64
+            }
             int sp = 0, lc = 0;
             bool root_pending = true;
             if (n_nodes > 0) { if (lane == 0) sm.stack[0] = make_int2(N, (int)vmask); sp = 1; }
@@ -274,7 +289,13 @@ __global__ void __launch_bounds__(WALK_TPB, 2) k_walk(const WalkParams P)
                     if (lane < cnt) {
                         const int2 e = sm.list[base + lane];
                         const double4 q = P.src_pm[e.x];
-                        sm.stage[lane] = q;
+                        if (MIXED) {
+                            const double rx = (q.x - cgx) * invR, ry = (q.y - cgy) * invR, rz = (q.z - cgz) * invR;
+                            const float hx = (float)rx, hy = (float)ry, hz = (float)rz;
+                            float4* sf = reinterpret_cast<float4*>(&sm.stage[lane]);
+                            sf[0] = make_float4(hx, hy, hz, (float)(q.w * inv_m0));
+                            sf[1] = make_float4((float)(rx - (double)hx), (float)(ry - (double)hy), (float)(rz - (double)hz), 0.f);
+                        } else sm.stage[lane] = q;
                         if (SPH) src_gas = P.src_flag[e.x] != 0;
                         // accepted pairs of this entry: lanes in the mask, minus the target's own leaf, none for a massless leaf
                         unsigned m = (unsigned)e.y;
@@ -286,6 +307,32 @@ __global__ void __launch_bounds__(WALK_TPB, 2) k_walk(const WalkParams P)
                     const unsigned gasmask = SPH ? __ballot_sync(0xffffffffu, src_gas) : 0u;   // tile entries that hold gas
                     __syncwarp();
                     unsigned gate = 0;                                                   // per lane: entries within ~2h (SPH candidates)
+                    if (MIXED) {
+                        float fax = 0.f, fay = 0.f, faz = 0.f;
+#pragma unroll 4
+                        for (int j = 0; j < cnt; j++) {
+                            const int2 e = sm.list[base + j];
+                            const float4 a = reinterpret_cast<const float4*>(&sm.stage[j])[0], b = reinterpret_cast<const float4*>(&sm.stage[j])[1];
+                            const bool bit = ((unsigned)e.y >> lane) & 1u;
+                            const float dx = (a.x - thx) + (b.x - tlx), dy = (a.y - thy) + (b.y - tly), dz = (a.z - thz) + (b.z - tlz);
+                            const float r2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+                            // same skip rules as the FP64 loop: d = 0 exactly for the own leaf / coincident sources, and the 1e-30
+                            // floor (in units of R^2; real separations are >= 2^-84) keeps the factor finite so f * d = 0
+                            const float r2c = r2 + 1e-30f;
+                            float rinv, iq;
+                            asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rinv) : "f"(r2c));
+                            asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(iq) : "f"(r2c + e02f));
+                            const float f = bit ? a.w * (rinv * iq) : 0.f;
+                            fax = fmaf(f, dx, fax); fay = fmaf(f, dy, fay); faz = fmaf(f, dz, faz);
+                            if (SPH) gate |= (r2 < hh4cf ? 1u : 0u) << j;
+                            if (COUNT) {
+                                const bool seen = bit && a.w != 0.f;
+                                const bool ok = seen && r2 != 0.f;
+                                if (e.x < N) { c_vis += seen; c_al += ok; } else c_an += ok;
+                            }
+                        }
+                        ax = fma(acc_scale, (double)fax, ax); ay = fma(acc_scale, (double)fay, ay); az = fma(acc_scale, (double)faz, az);
+                    } else {
 #pragma unroll 4
                     for (int j = 0; j < cnt; j++) {
                         const int2 e = sm.list[base + j];
@@ -307,6 +354,7 @@ __global__ void __launch_bounds__(WALK_TPB, 2) k_walk(const WalkParams P)
                             if (e.x < N) { c_vis += seen; c_al += ok; } else c_an += ok;
                         }
                     }
+                    }
                     if (SPH) {
                         // second pass over the few (target, source) pairs that can pass r < 2 h_i (Node.cpp:316-325, :368-377)
                         gate &= gasmask;
@@ -316,10 +364,10 @@ __global__ void __launch_bounds__(WALK_TPB, 2) k_walk(const WalkParams P)
                             any &= any - 1;
                             const int2 e = sm.list[base + j];
                             if (((gate >> j) & 1u) && (((unsigned)e.y >> lane) & 1u)) {
-                                const double4 q = sm.stage[j];
+                                const double4 q = MIXED ? P.src_pm[e.x] : sm.stage[j];
                                 const double dx = q.x - tp.x, dy = q.y - tp.y, dz = q.z - tp.z;
                                 const double r2 = fma(dz, dz, fma(dy, dy, dx * dx));
-                                bool pass = q.w != 0.0 && r2 != 0.0;
+                                bool pass = q.w != 0.0 && r2 != 0.0 && r2 < hh4c;
                                 if (pass && !(r2 < hh4 * (1.0 - 1e-13))) {
                                     // within 1e-13 of the gate: the reference's own separately rounded expression
                                     const double r2e = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
@@ -406,13 +454,18 @@ __global__ void k_unpermute_i32(const uint32_t* __restrict__ perm, int64_t n, co
     oa[p] = a[i]; ob[p] = b[i]; oc[p] = c[i]; od[p] = d_[i];
 }
 
-template <bool COUNT, bool SPH>
+template <bool COUNT, bool SPH, bool MIXED>
 void launch_walk(const WalkParams& P, int blocks, cudaStream_t st)
 {
     static bool attr_set = false;
     const int smem = (int)sizeof(WarpSmem) * WALK_WARPS;
-    if (!attr_set) { cudaFuncSetAttribute(k_walk<COUNT, SPH>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr_set = true; }
-    k_walk<COUNT, SPH><<<blocks, WALK_TPB, smem, st>>>(P);
+    if (!attr_set) { cudaFuncSetAttribute(k_walk<COUNT, SPH, MIXED>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr_set = true; }
+    k_walk<COUNT, SPH, MIXED><<<blocks, WALK_TPB, smem, st>>>(P);
+}
+template <bool COUNT, bool SPH>
+void launch_walk2(const WalkParams& P, int blocks, bool mixed, cudaStream_t st)
+{
+    if (mixed) launch_walk<COUNT, SPH, true>(P, blocks, st); else launch_walk<COUNT, SPH, false>(P, blocks, st);
 }
 
 } // namespace
@@ -439,7 +492,7 @@ int agb_walk_blocks(int sm_count) { return sm_count * 2; }
 int agb_walk_warps_per_block() { return WALK_WARPS; }
 
 int agb_launch_walk(AgbDev& d, AgbScalars* s, double globalTime, double e0, double theta, int64_t t0, int64_t t1,
-                    bool counters, bool any_gas, int sm_count, cudaStream_t st, cudaEvent_t ev0, cudaEvent_t ev1)
+                    bool counters, bool any_gas, bool mixed, int sm_count, cudaStream_t st, cudaEvent_t ev0, cudaEvent_t ev1)
 {
     WalkParams P;
     P.src_pm = d.src_pm; P.src_gv = d.src_gv; P.src_flag = d.src_flag; P.child = d.child; P.ndepth = d.ndepth;
@@ -458,8 +511,8 @@ int agb_launch_walk(AgbDev& d, AgbScalars* s, double globalTime, double e0, doub
         int blocks = (int)std::min<int64_t>((int64_t)agb_walk_blocks(sm_count), ((int64_t)P.ngroups + WALK_WARPS - 1) / WALK_WARPS);
         if (blocks * WALK_WARPS > d.spill_warps) blocks = d.spill_warps / WALK_WARPS;
         if (ev0) cudaEventRecord(ev0, st);
-        if (counters) { if (any_gas) launch_walk<true, true>(P, blocks, st); else launch_walk<true, false>(P, blocks, st); }
-        else { if (any_gas) launch_walk<false, true>(P, blocks, st); else launch_walk<false, false>(P, blocks, st); }
+        if (counters) { if (any_gas) launch_walk2<true, true>(P, blocks, mixed, st); else launch_walk2<true, false>(P, blocks, mixed, st); }
+        else { if (any_gas) launch_walk2<false, true>(P, blocks, mixed, st); else launch_walk2<false, false>(P, blocks, mixed, st); }
         if (ev1) cudaEventRecord(ev1, st);
         launches++;
     }

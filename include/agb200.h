@@ -118,7 +118,10 @@ int agb_get_counters(agb_ctx* ctx, agb_counters* c);
 
 /* -------- options */
 typedef enum {
-    AGB_OPT_TARGET_COUNTERS = 1     /* 1: also record per-target visit / accept / SPH counts (parity tests) */
+    AGB_OPT_TARGET_COUNTERS = 1,    /* 1: also record per-target visit / accept / SPH counts (parity tests) */
+    AGB_OPT_PRECISION = 2           /* arithmetic of the pair forces: 0 = FP64 throughout (agrees with the reference to ~1e-14),
+                                       1 = mixed (default): float-float displacements, FP32 law, FP64 accumulation; ~1e-7.
+                                       The accepted (target, source) sets, densities and SPH terms are identical in both. */
 } agb_option;
 int agb_set_option(agb_ctx* ctx, int option, int64_t value);
 

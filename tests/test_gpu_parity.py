@@ -15,12 +15,13 @@ pytestmark = pytest.mark.gpu
 def ctxs(pkg):
     made = {}
 
-    def get(cores):
-        if cores not in made:
+    def get(cores, mixed=True):
+        if (cores, mixed) not in made:
             c = pkg.Context(0, cores)
             c.set_option(pkg.capi.AGB_OPT_TARGET_COUNTERS, 1)
-            made[cores] = c
-        return made[cores]
+            c.set_option(pkg.capi.AGB_OPT_PRECISION, 1 if mixed else 0)
+            made[(cores, mixed)] = c
+        return made[(cores, mixed)]
     yield get
     for c in made.values():
         c.close()
@@ -31,10 +32,14 @@ def run_gpu(pkg, ctx, p, theta, e0, mh, gt=0.0):
     return got
 
 
+PRECISIONS = [pytest.param(True, id="mixed"), pytest.param(False, id="fp64")]
+
+
+@pytest.mark.parametrize("mixed", PRECISIONS)
 @pytest.mark.parametrize("name", GOLDEN_CASES)
-def test_golden_reference_vectors(pkg, ctxs, name):
+def test_golden_reference_vectors(pkg, ctxs, name, mixed):
     p, want, par = load_golden(name)
-    ctx = ctxs(int(par["cores"]))
+    ctx = ctxs(int(par["cores"]), mixed)
     got = run_gpu(pkg, ctx, p, par["theta"], par["e0"], par["massInH"], par["globalTime"])
     rep = compare(got, want, p, ctx)
     print(name, rep)
@@ -61,27 +66,31 @@ def _deep_core(ics):
 
 
 
+@pytest.mark.parametrize("mixed", PRECISIONS)
 @pytest.mark.parametrize("case", sorted(CASES))
-def test_against_oracle(pkg, oracle, ctxs, case):
+def test_against_oracle(pkg, oracle, ctxs, case, mixed):
     p, theta, e0, nb, cores = CASES[case](pkg.ics)
     mh = pkg.ics.gas_mass_in_h(p, nb)
-    ctx = ctxs(cores)
+    ctx = ctxs(cores, mixed)
     got = run_gpu(pkg, ctx, p, theta, e0, mh)
     want = oracle.run(p, theta, e0, mh, 0.0, cores)
     rep = compare(got, want, p, ctx)
-    print(case, rep)
+    print(case, "mixed" if mixed else "fp64", rep)
     assert_parity(rep)
+    if not mixed:
+        assert rep["acc_median"] < 1e-12 and rep["acc_p99"] < 1e-10, rep        # the FP64 path only differs by summation order
 
 
-def test_tiny_and_empty(pkg, oracle, ctxs):
-    ctx = ctxs(8)
+@pytest.mark.parametrize("mixed", PRECISIONS)
+def test_tiny_and_empty(pkg, oracle, ctxs, mixed):
+    ctx = ctxs(8, mixed)
     for n in (1, 2, 3):
         p = pkg.ics.plummer(n, seed=20 + n, gas_fraction=1.0)
         got = run_gpu(pkg, ctx, p, 0.5, 1e18, 1e40)
         want = oracle.run(p, 0.5, 1e18, 1e40, 0.0, 8)
         assert got["R"] == want["R"]
         for k in ("ax", "ay", "az"):
-            assert np.allclose(got[k], want[k], rtol=1e-12, atol=0), (n, k, got[k], want[k])
+            assert np.allclose(got[k], want[k], rtol=1e-6 if mixed else 1e-12, atol=0), (n, k, got[k], want[k])
     p = pkg.ics.plummer(0)
     got = run_gpu(pkg, ctx, p, 0.5, 1e18, 1e40)
     assert got["R"] == 0.0 and len(got["ax"]) == 0
