@@ -43,7 +43,6 @@ struct WarpSmem {
     int2 list[LCAP];
     int2 stack[SCAP];
     double4 stage[32];                     // drain: the 32 sources of a tile; traversal: (COM, mass) of straddling nodes
-    int4 mch[64];                          // traversal: the 8 child slots of straddling nodes
     double4 tsph[32];                      // per gas target: 1/h, 1/(pi h^4), 2 P/rho^2, sound speed (kept out of registers)
 };
 
@@ -204,80 +203,78 @@ __global__ void __launch_bounds__(WALK_TPB, 2) k_walk(const WalkParams P)
                         for (int j = 0; j < cnt; j++) c_vis += (__shfl_sync(0xffffffffu, vm, j) >> lane) & 1u;
                     }
                     root_pending = false;
-                    // accepted by the whole mask
-                    const unsigned am = __ballot_sync(0xffffffffu, outcome == OUT_ACCEPT);
-                    if (outcome == OUT_ACCEPT) sm.list[lc + __popc(am & lt)] = e;
+                    // lanes of the entry's mask that accept the node / open it
+                    unsigned amask = outcome == OUT_ACCEPT ? (unsigned)e.y : 0u, omask = outcome == OUT_OPEN ? (unsigned)e.y : 0u;
+                    // child slots of every node that may be opened are requested now, before the serial part below
+                    int4 c0 = make_int4(-1, -1, -1, -1), c1 = c0;
+                    if (outcome >= OUT_OPEN) {
+                        c0 = reinterpret_cast<const int4*>(P.child)[2 * (size_t)(e.x - N)];
+                        c1 = reinterpret_cast<const int4*>(P.child)[2 * (size_t)(e.x - N) + 1];
+                    }
+                    // straddling nodes: per-lane test, one node at a time; (COM, radius^2) parked in shared memory by the owners
+                    unsigned mm = __ballot_sync(0xffffffffu, outcome == OUT_MIXED);
+                    if (lane == 0) { st_rounds++; st_popped += cnt; st_mixed += __popc(mm); }
+                    if (mm) {
+                        if (outcome == OUT_MIXED) sm.stage[lane] = make_double4(pmx, pmy, pmz, rad2);
+                        __syncwarp();
+                        const unsigned my = (unsigned)e.y;
+                        do {
+                            const int src = __ffs(mm) - 1;
+                            mm &= mm - 1;
+                            const unsigned nmask = __shfl_sync(0xffffffffu, my, src);
+                            const double4 q = sm.stage[src];
+                            bool acc_l = false, open_l = false;
+                            if ((nmask >> lane) & 1u) {
+                                const double dx = q.x - tp.x, dy = q.y - tp.y, dz = q.z - tp.z;
+                                const double r2 = fma(dz, dz, fma(dy, dy, dx * dx));
+                                if (r2 != 0.0) {                                 // Node.cpp:274 (r == 0 -> return)
+                                    const double lhs = r2 * theta2;
+                                    if (fast_mac && lhs > q.w * (1.0 + 1e-13)) acc_l = true;
+                                    else if (fast_mac && lhs < q.w * (1.0 - 1e-13)) open_l = true;
+                                    else {                                       // the reference's own expression, Node.cpp:271,331-334
+                                        const double r2e = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+                                        acc_l = __ddiv_rn(__dsqrt_rn(q.w), __dsqrt_rn(r2e)) < theta;   // sqrt(radius^2) is exact: radius = R 2^-k
+                                        open_l = !acc_l;
+                                        tot_exact++;
+                                    }
+                                }
+                            }
+                            const unsigned a = __ballot_sync(0xffffffffu, acc_l), o = __ballot_sync(0xffffffffu, open_l);
+                            if (lane == src) { amask = a; omask = o; }
+                        } while (mm);
+                    }
+                    // one list entry per node with acceptors
+                    const unsigned am = __ballot_sync(0xffffffffu, amask != 0u);
+                    if (amask != 0u) sm.list[lc + __popc(am & lt)] = make_int2(e.x, (int)amask);
                     lc += __popc(am);
-                    // opened by the whole mask: children inherit the mask
-                    const unsigned om = __ballot_sync(0xffffffffu, outcome == OUT_OPEN);
+                    // children of every node with openers inherit the openers' mask: leaves -> list, nodes -> stack
+                    const unsigned om = __ballot_sync(0xffffffffu, omask != 0u);
                     if (om) {
-                        int ch[8];
+                        const int ch[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
                         int nl = 0, nn = 0;
-                        if (outcome == OUT_OPEN) {
-                            const int4 c0 = reinterpret_cast<const int4*>(P.child)[2 * (size_t)(e.x - N)], c1 = reinterpret_cast<const int4*>(P.child)[2 * (size_t)(e.x - N) + 1];
-                            ch[0] = c0.x; ch[1] = c0.y; ch[2] = c0.z; ch[3] = c0.w; ch[4] = c1.x; ch[5] = c1.y; ch[6] = c1.z; ch[7] = c1.w;
+                        if (omask != 0u) {
 #pragma unroll
                             for (int c = 0; c < 8; c++) { nl += (ch[c] >= 0 && ch[c] < N); nn += (ch[c] >= N); }
                         }
                         const int il = warp_incl_scan(nl, lane), in_ = warp_incl_scan(nn, lane);
                         const int tl = __shfl_sync(0xffffffffu, il, 31), tn = __shfl_sync(0xffffffffu, in_, 31);
-                        if (outcome == OUT_OPEN) {
+                        if (omask != 0u) {
                             int pl = lc + il - nl, pn = sp + in_ - nn;
 #pragma unroll
                             for (int c = 0; c < 8; c++) {
-                                if (ch[c] >= N) stack_put(pn++, make_int2(ch[c], e.y));
-                                else if (ch[c] >= 0) sm.list[pl++] = make_int2(ch[c], e.y);
+                                if (ch[c] >= N) stack_put(pn++, make_int2(ch[c], (int)omask));
+                                else if (ch[c] >= 0) sm.list[pl++] = make_int2(ch[c], (int)omask);
                             }
                         }
                         lc += tl; sp += tn;
-                    }
-                    // straddling nodes: exact per-lane test.  Their (COM, mass) and child slots are parked in shared
-                    // memory by the owning lanes first, so the serial loop below never waits on global memory.
-                    unsigned mm = __ballot_sync(0xffffffffu, outcome == OUT_MIXED);
-                    if (lane == 0) { st_rounds++; st_popped += cnt; st_mixed += __popc(mm); st_open += __popc(om); }
-                    if (mm) {
-                        if (outcome == OUT_MIXED) {
-                            sm.stage[lane] = make_double4(pmx, pmy, pmz, rad2);
-                            sm.mch[2 * lane] = reinterpret_cast<const int4*>(P.child)[2 * (size_t)(e.x - N)];
-                            sm.mch[2 * lane + 1] = reinterpret_cast<const int4*>(P.child)[2 * (size_t)(e.x - N) + 1];
-                        }
-                        __syncwarp();
-                    }
-                    while (mm) {
-                        const int src = __ffs(mm) - 1;
-                        mm &= mm - 1;
-                        const int nidx = __shfl_sync(0xffffffffu, e.x, src);
-                        const unsigned nmask = (unsigned)__shfl_sync(0xffffffffu, e.y, src);
-                        const double4 q = sm.stage[src];
-                        const double nrad2 = q.w;
-                        bool acc_l = false, open_l = false;
-                        if ((nmask >> lane) & 1u) {
-                            const double dx = q.x - tp.x, dy = q.y - tp.y, dz = q.z - tp.z;
-                            const double r2 = fma(dz, dz, fma(dy, dy, dx * dx));
-                            if (r2 != 0.0) {                                     // Node.cpp:274 (r == 0 -> return)
-                                const double lhs = r2 * theta2;
-                                if (fast_mac && lhs > nrad2 * (1.0 + 1e-13)) acc_l = true;
-                                else if (fast_mac && lhs < nrad2 * (1.0 - 1e-13)) open_l = true;
-                                else {                                           // the reference's own expression, Node.cpp:271,331-334
-                                    const double r2e = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
-                                    const double rad = scalbn(R, -(int)P.ndepth[nidx - N]);
-                                    acc_l = __ddiv_rn(rad, __dsqrt_rn(r2e)) < theta;
-                                    open_l = !acc_l;
-                                    tot_exact++;
-                                }
-                            }
-                        }
-                        const unsigned a = __ballot_sync(0xffffffffu, acc_l), o = __ballot_sync(0xffffffffu, open_l);
-                        if (a) { if (lane == 0) sm.list[lc] = make_int2(nidx, (int)a); lc++; }
-                        if (o) {
-                            const int chl = lane < 8 ? reinterpret_cast<const int*>(sm.mch)[src * 8 + lane] : -1;
-                            const unsigned lm = __ballot_sync(0xffffffffu, chl >= 0 && chl < N), nm = __ballot_sync(0xffffffffu, chl >= N);
-                            if (chl >= N) stack_put(sp + __popc(nm & lt), make_int2(chl, (int)o));
-                            else if (chl >= 0) sm.list[lc + __popc(lm & lt)] = make_int2(chl, (int)o);
-                            lc += __popc(lm); sp += __popc(nm);
-                        }
+                        if (lane == 0) st_open += __popc(om);
                     }
                     __syncwarp();
+                    // warm L1 with the node records the next round will pop
+                    if (lane < sp && lane < 32) {
+                        const int2 nx = stack_get(sp - 1 - lane);
+                        if (nx.x >= 0) asm volatile("prefetch.global.L1 [%0];" ::"l"(P.src_pm + nx.x));
+                    }
                 }
 
                 // ------------------------------------------------ drain the interaction list
@@ -305,6 +302,7 @@ __global__ void __launch_bounds__(WALK_TPB, 2) k_walk(const WalkParams P)
                         if (e.x < N) tot_leaf += pc; else tot_node += pc;
                     }
                     const unsigned gasmask = SPH ? __ballot_sync(0xffffffffu, src_gas) : 0u;   // tile entries that hold gas
+                    if (base + 32 + lane < lc) asm volatile("prefetch.global.L1 [%0];" ::"l"(P.src_pm + sm.list[base + 32 + lane].x));
                     __syncwarp();
                     unsigned gate = 0;                                                   // per lane: entries within ~2h (SPH candidates)
                     if (MIXED) {
