@@ -10,6 +10,7 @@
 
 int agb_walk_blocks(int sm_count);
 int agb_walk_warps_per_block();
+void agb_far_capacity(int* lcap, int* fcap, int* targets);
 
 struct agb_ctx {
     int device = 0, sm_count = 148;
@@ -60,6 +61,7 @@ void free_pool(agb_ctx* c)
     dfree(d.child); dfree(d.nfirst); dfree(d.nlast); dfree(d.nparent); dfree(d.arrived); dfree(d.ndepth);
     dfree(d.nmark); dfree(d.ndup); dfree(d.leafmark); dfree(d.mom_pm); dfree(d.mom_gv); dfree(d.grouplist); dfree(d.gasrank);
     dfree(d.dist); dfree(d.blockhist); dfree(d.scanblk);
+    dfree(d.far_list); dfree(d.far_front); dfree(d.far_cnt);
     dfree(d.c_visits); dfree(d.c_accn); dfree(d.c_accl); dfree(d.c_sph);
     d.cap = 0;
 }
@@ -81,6 +83,11 @@ int ensure_pool(agb_ctx* c, int64_t n)
     CK(dalloc(d.child, 8 * cap)); CK(dalloc(d.nfirst, cap)); CK(dalloc(d.nlast, cap)); CK(dalloc(d.nparent, cap)); CK(dalloc(d.arrived, cap)); CK(dalloc(d.ndepth, cap));
     CK(dalloc(d.nmark, cap)); CK(dalloc(d.ndup, cap)); CK(dalloc(d.leafmark, cap)); CK(dalloc(d.mom_pm, cap)); CK(dalloc(d.mom_gv, cap)); CK(dalloc(d.grouplist, cap)); CK(dalloc(d.gasrank, cap + 1));
     CK(dalloc(d.dist, cap));
+    {
+        int lcap, fcap, tg; agb_far_capacity(&lcap, &fcap, &tg);
+        const size_t nsg = cap / (size_t)tg + 2;
+        CK(dalloc(d.far_list, nsg * lcap)); CK(dalloc(d.far_front, nsg * fcap)); CK(dalloc(d.far_cnt, nsg * 3));
+    }
     for (auto& q : c->in_d) CK(dalloc(q, cap));
     CK(dalloc(c->in_type, cap));
     CK(dalloc(d.blockhist, 256 * ((cap + 2047) / 2048 + 1)));   // sort tiles are >= 2048 keys
@@ -322,10 +329,11 @@ int agb_forces_slice(agb_ctx* c, double global_time, double e0, double theta, in
     AgbDev& d = c->d;
     if (d.n == 0) { c->forces_done = true; return AGB_OK; }
     if (c->target_counters) { int rc = ensure_counters(c); if (rc) return rc; }
-    // slice boundaries fall on multiples of 32 so that every warp owns the same 32 targets whatever the number of
+    // slice boundaries fall on multiples of 256 (the far-field super-groups) so that every warp owns the same 32 targets and
+    // every super-group the same 256 whatever the number of
     // parts: results are then bit-identical for 1, 2, 4, 8 GPUs (same groups => same summation order)
-    const int64_t ngrp = (d.n + 31) / 32;
-    const int64_t t0 = std::min(d.n, ngrp * part / nparts * 32), t1 = std::min(d.n, ngrp * (part + 1) / nparts * 32);
+    const int64_t ngrp = (d.n + 255) / 256;
+    const int64_t t0 = std::min(d.n, ngrp * part / nparts * 256), t1 = std::min(d.n, ngrp * (part + 1) / nparts * 256);
     CK(cudaEventRecord(c->ev[6], c->st));
     // gas targets need h/rho/P: if the caller skipped gas_density they are orphans (h = 0) and get no SPH, like the reference
     c->launches += agb_launch_walk(d, c->s, global_time, e0, theta, t0, t1, c->target_counters, c->hs.any_gas != 0, c->mixed, c->sm_count, c->st, c->ev[0], c->ev[1]);

@@ -55,6 +55,8 @@ struct AgbDev {
     int32_t *c_visits = nullptr, *c_accn = nullptr, *c_accl = nullptr, *c_sph = nullptr;
     // walk spill stack
     int2* spill = nullptr; int64_t spill_per_warp = 0; int spill_warps = 0;
+    // far-field prepass output, per super-group of 256 targets
+    int32_t *far_list = nullptr, *far_front = nullptr, *far_cnt = nullptr;
 };
 
 // Device-resident scalars of one step (read back in a single copy when the host needs them).

@@ -32,7 +32,11 @@ constexpr int WALK_WARPS = 8;
 constexpr int WALK_TPB = WALK_WARPS * 32;
 constexpr int LCAP = 512;                  // interaction-list entries per warp
 constexpr int LGROW = 288;                 // worst-case growth per pop round: 32 lanes x (8 leaves + 1 node)
-constexpr int SCAP = 512;                  // shared part of the traversal stack
+#ifndef AGB_WALK_CTAS_PER_SM
+#define AGB_WALK_CTAS_PER_SM 2
+#endif
+constexpr int WALK_CTAS = AGB_WALK_CTAS_PER_SM;
+constexpr int SCAP = WALK_CTAS >= 3 ? 384 : 512;   // shared part of the traversal stack (the rest spills to global memory)
 constexpr int GASBIT = 1 << 30;
 constexpr int IDXMASK = GASBIT - 1;
 constexpr double kG = 6.67430e-11;         // Math/Constants.h:7
@@ -67,6 +71,7 @@ struct WalkParams {
     double *ax, *ay, *az, *dUdt;
     int32_t *c_visits, *c_accn, *c_accl, *c_sph;
     int2* spill; int64_t spill_per_warp;
+    int32_t *far_list, *far_front, *far_cnt;   // per super-group (256 targets): shared accept list, hand-over frontier, {n_list, n_front, n_visits}
     AgbScalars* s;
     int64_t N, t0, t1;
     unsigned ngroups;
@@ -88,8 +93,119 @@ __device__ __forceinline__ unsigned long long warp_sum_u64(unsigned long long v)
     return v;
 }
 
+
+constexpr int SG_GROUPS = 8;               // warps (32-target groups) per super-group
+constexpr int FAR_LCAP = 4096, FAR_FCAP = 2048, FAR_SCAP = 1024;
+
+struct Box { double lox, loy, loz, hix, hiy, hiz; };
+
+// Opening test of a node against a box of targets: ACCEPT / OPEN only when every point of the box takes the same
+// decision as the reference's `radius / r < theta` (Node.cpp:331-334) with a 1e-12 margin; r == 0 is impossible
+// for OPEN because the COM must lie outside the box.
+__device__ __forceinline__ int classify_box(const double4& pm, double rad2, const Box& b, double theta2, bool fast_mac)
+{
+    const double ax_ = fmax(0.0, fmax(b.lox - pm.x, pm.x - b.hix)), ay_ = fmax(0.0, fmax(b.loy - pm.y, pm.y - b.hiy)), az_ = fmax(0.0, fmax(b.loz - pm.z, pm.z - b.hiz));
+    const double bx_ = fmax(fabs(pm.x - b.lox), fabs(pm.x - b.hix)), by_ = fmax(fabs(pm.y - b.loy), fabs(pm.y - b.hiy)), bz_ = fmax(fabs(pm.z - b.loz), fabs(pm.z - b.hiz));
+    const double dmin2 = ax_ * ax_ + ay_ * ay_ + az_ * az_, dmax2 = bx_ * bx_ + by_ * by_ + bz_ * bz_;
+    if (fast_mac) {
+        if (dmin2 * theta2 > rad2 * (1.0 + 1e-12)) return OUT_ACCEPT;
+        if (dmin2 > 0.0 && dmax2 * theta2 < rad2 * (1.0 - 1e-12)) return OUT_OPEN;
+    }
+    return OUT_MIXED;
+}
+
+// Far-field prepass: one warp per super-group of 256 tree-adjacent targets walks the tree once against the box of
+// all of them.  Nodes every target accepts go to a list shared by the 8 warps that own those targets, nodes every
+// target opens are descended here, and nodes that straddle the opening radius of the big box are handed over to the
+// per-warp walks (k_walk) as their starting frontier.  The upper tree is thus traversed once per 256 targets
+// instead of once per 32, and the shared entries are evaluated with full lane masks.
+__global__ void __launch_bounds__(128) k_far(const WalkParams P, int nsg, int64_t sg_first)
+{
+    __shared__ int stack_s[4][FAR_SCAP];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int* const stk = stack_s[warp];
+    const unsigned lt = (1u << lane) - 1u;
+    const int N = (int)P.N;
+    const double R = __longlong_as_double((long long)P.s->Rbits);
+    const int n_nodes = P.s->n_nodes, n_in_tree = P.s->n_in_tree;
+    const double theta2 = P.theta * P.theta;
+    const bool fast_mac = P.theta > 0.0;
+    const double inf = __longlong_as_double(0x7ff0000000000000ll);
+    for (int sgi = blockIdx.x * 4 + warp; sgi < nsg; sgi += gridDim.x * 4) {
+        const int64_t tb = (sg_first + sgi) * (32 * SG_GROUPS);
+        int32_t* const fl = P.far_list + (size_t)sgi * FAR_LCAP;
+        int32_t* const ff = P.far_front + (size_t)sgi * FAR_FCAP;
+        Box b{inf, inf, inf, -inf, -inf, -inf};
+        for (int j = 0; j < SG_GROUPS; j++) {
+            const int64_t t = tb + j * 32 + lane;
+            if (t >= P.t0 && t < P.t1) {
+                const double4 tp = P.src_pm[t];
+                if (P.s_next[t] == P.globalTime && tp.w != 0.0) {
+                    b.lox = fmin(b.lox, tp.x); b.loy = fmin(b.loy, tp.y); b.loz = fmin(b.loz, tp.z);
+                    b.hix = fmax(b.hix, tp.x); b.hiy = fmax(b.hiy, tp.y); b.hiz = fmax(b.hiz, tp.z);
+                }
+            }
+        }
+        b.lox = warp_min(b.lox); b.loy = warp_min(b.loy); b.loz = warp_min(b.loz);
+        b.hix = warp_max(b.hix); b.hiy = warp_max(b.hiy); b.hiz = warp_max(b.hiz);
+        int nl = 0, nf = 0, nvis = 0, sp = 0;
+        if (b.lox <= b.hix) {
+            if (n_nodes > 0) { if (lane == 0) stk[0] = N; sp = 1; }
+            else if (n_in_tree == 1) { if (lane == 0) fl[0] = 0; nl = 1; }
+            __syncwarp();
+            while (sp > 0) {
+                const int cnt = min(sp, 32);
+                sp -= cnt;
+                const int node = lane < cnt ? stk[sp + lane] : -1;
+                int outcome = OUT_NONE;
+                if (node >= 0) {
+                    const double4 pm = P.src_pm[node];
+                    if (pm.w != 0.0) {
+                        const double rad = scalbn(R, -(int)P.ndepth[node - N]);
+                        outcome = classify_box(pm, rad * rad, b, theta2, fast_mac);
+                        // out of room in the shared list or the stack: leave the node (and all below it) to the per-warp walks
+                        if (outcome != OUT_MIXED && (nl > FAR_LCAP - 32 * 9 || sp > FAR_SCAP - 32 * 9)) outcome = OUT_MIXED;
+                    }
+                }
+                __syncwarp();
+                nvis += __popc(__ballot_sync(0xffffffffu, (outcome == OUT_ACCEPT || outcome == OUT_OPEN) && node != N));
+                const unsigned fm = __ballot_sync(0xffffffffu, outcome == OUT_MIXED);
+                if (outcome == OUT_MIXED) { const int pos = nf + __popc(fm & lt); if (pos < FAR_FCAP) ff[pos] = node; else P.s->walk_overflow = 1; }
+                nf = min(nf + __popc(fm), FAR_FCAP);
+                const unsigned am = __ballot_sync(0xffffffffu, outcome == OUT_ACCEPT);
+                if (outcome == OUT_ACCEPT) fl[nl + __popc(am & lt)] = node;
+                nl += __popc(am);
+                const unsigned om = __ballot_sync(0xffffffffu, outcome == OUT_OPEN);
+                if (om) {
+                    int ch[8] = {-1, -1, -1, -1, -1, -1, -1, -1};
+                    int cl = 0, cn = 0;
+                    if (outcome == OUT_OPEN) {
+                        const int4 c0 = reinterpret_cast<const int4*>(P.child)[2 * (size_t)(node - N)], c1 = reinterpret_cast<const int4*>(P.child)[2 * (size_t)(node - N) + 1];
+                        ch[0] = c0.x; ch[1] = c0.y; ch[2] = c0.z; ch[3] = c0.w; ch[4] = c1.x; ch[5] = c1.y; ch[6] = c1.z; ch[7] = c1.w;
+#pragma unroll
+                        for (int c = 0; c < 8; c++) { cl += (ch[c] >= 0 && ch[c] < N); cn += (ch[c] >= N); }
+                    }
+                    const int il = warp_incl_scan(cl, lane), in_ = warp_incl_scan(cn, lane);
+                    const int tl = __shfl_sync(0xffffffffu, il, 31), tn = __shfl_sync(0xffffffffu, in_, 31);
+                    if (outcome == OUT_OPEN) {
+                        int pl = nl + il - cl, pn = sp + in_ - cn;
+#pragma unroll
+                        for (int c = 0; c < 8; c++) {
+                            if (ch[c] >= N) stk[pn++] = ch[c];
+                            else if (ch[c] >= 0) fl[pl++] = ch[c];
+                        }
+                    }
+                    nl += tl; sp += tn;
+                }
+                __syncwarp();
+            }
+        }
+        if (lane == 0) { P.far_cnt[3 * sgi] = nl; P.far_cnt[3 * sgi + 1] = nf; P.far_cnt[3 * sgi + 2] = nvis; }
+    }
+}
+
 template <bool COUNT, bool SPH, bool MIXED>
-__global__ void __launch_bounds__(WALK_TPB, 2) k_walk(const WalkParams P)
+__global__ void __launch_bounds__(WALK_TPB, WALK_CTAS) k_walk(const WalkParams P, int64_t sg_first)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -166,13 +282,25 @@ __global__ void __launch_bounds__(WALK_TPB, 2) k_walk(const WalkParams P)
                 tlx = (float)(rx - (double)thx); tly = (float)(ry - (double)thy); tlz = (float)(rz - (double)thz);
                 hh4cf = (float)(hh4 * invR2 * (1.0 + 1e-5));               // generous: the SPH pass re-tests in FP64
             }
-            int sp = 0, lc = 0;
-            bool root_pending = true;
-            if (n_nodes > 0) { if (lane == 0) sm.stack[0] = make_int2(N, (int)vmask); sp = 1; }
-            else if (n_in_tree == 1) { if (lane == 0) sm.list[0] = make_int2(0, (int)vmask); lc = 1; }
+            const Box wb{lox, loy, loz, hix, hiy, hiz};
+            // start from what the far-field prepass left for this super-group: a shared accept list and a frontier
+            const int64_t sgi = (P.t0 / 32 + (int64_t)g) / SG_GROUPS - sg_first;
+            const int32_t* const fl = P.far_list + (size_t)sgi * FAR_LCAP;
+            const int32_t* const ff = P.far_front + (size_t)sgi * FAR_FCAP;
+            const int n_fl = P.far_cnt[3 * sgi], n_ff = P.far_cnt[3 * sgi + 1];
+            if (COUNT && valid) c_vis += P.far_cnt[3 * sgi + 2];
+            int sp = n_ff, lc = 0, cpos = 0;
+            for (int i = lane; i < n_ff; i += 32) stack_put(i, make_int2(ff[i], (int)vmask));
             __syncwarp();
 
             while (true) {
+                if (cpos < n_fl) {
+                    // ------------------------------------------------ import a chunk of the shared far-field list (full mask)
+                    const int nimp = min(n_fl - cpos, LCAP);
+                    for (int i = lane; i < nimp; i += 32) sm.list[i] = make_int2(fl[cpos + i], (int)vmask);
+                    lc = nimp; cpos += nimp;
+                    __syncwarp();
+                } else
                 // ------------------------------------------------ traversal: fill the interaction list
                 while (sp > 0 && lc <= LCAP - LGROW) {
                     const int cnt = min(sp, 32);
@@ -188,21 +316,13 @@ __global__ void __launch_bounds__(WALK_TPB, 2) k_walk(const WalkParams P)
                         if (pm.w != 0.0) {                                       // Node.cpp:250 / :390
                             const double rad = scalbn(R, -(int)P.ndepth[e.x - N]);
                             rad2 = rad * rad;
-                            const double ax_ = fmax(0.0, fmax(lox - pm.x, pm.x - hix)), ay_ = fmax(0.0, fmax(loy - pm.y, pm.y - hiy)), az_ = fmax(0.0, fmax(loz - pm.z, pm.z - hiz));
-                            const double bx_ = fmax(fabs(pm.x - lox), fabs(pm.x - hix)), by_ = fmax(fabs(pm.y - loy), fabs(pm.y - hiy)), bz_ = fmax(fabs(pm.z - loz), fabs(pm.z - hiz));
-                            const double dmin2 = ax_ * ax_ + ay_ * ay_ + az_ * az_, dmax2 = bx_ * bx_ + by_ * by_ + bz_ * bz_;
-                            outcome = OUT_MIXED;
-                            if (fast_mac) {
-                                if (dmin2 * theta2 > rad2 * (1.0 + 1e-12)) outcome = OUT_ACCEPT;
-                                else if (dmin2 > 0.0 && dmax2 * theta2 < rad2 * (1.0 - 1e-12)) outcome = OUT_OPEN;
-                            }
+                            outcome = classify_box(pm, rad2, wb, theta2, fast_mac);
                         }
                     }
                     if (COUNT) {
-                        const unsigned vm = (outcome != OUT_NONE && !(root_pending && e.x == N)) ? (unsigned)e.y : 0u;
+                        const unsigned vm = (outcome != OUT_NONE && e.x != N) ? (unsigned)e.y : 0u;
                         for (int j = 0; j < cnt; j++) c_vis += (__shfl_sync(0xffffffffu, vm, j) >> lane) & 1u;
                     }
-                    root_pending = false;
                     // lanes of the entry's mask that accept the node / open it
                     unsigned amask = outcome == OUT_ACCEPT ? (unsigned)e.y : 0u, omask = outcome == OUT_OPEN ? (unsigned)e.y : 0u;
                     // child slots of every node that may be opened are requested now, before the serial part below
@@ -400,7 +520,7 @@ __global__ void __launch_bounds__(WALK_TPB, 2) k_walk(const WalkParams P)
                     }
                 }
                 lc = 0;
-                if (sp == 0) break;
+                if (sp == 0 && cpos >= n_fl) break;
             }
         }
 
@@ -458,7 +578,7 @@ void launch_walk(const WalkParams& P, int blocks, cudaStream_t st)
     static bool attr_set = false;
     const int smem = (int)sizeof(WarpSmem) * WALK_WARPS;
     if (!attr_set) { cudaFuncSetAttribute(k_walk<COUNT, SPH, MIXED>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr_set = true; }
-    k_walk<COUNT, SPH, MIXED><<<blocks, WALK_TPB, smem, st>>>(P);
+    k_walk<COUNT, SPH, MIXED><<<blocks, WALK_TPB, smem, st>>>(P, P.t0 / (32 * SG_GROUPS));
 }
 template <bool COUNT, bool SPH>
 void launch_walk2(const WalkParams& P, int blocks, bool mixed, cudaStream_t st)
@@ -486,8 +606,9 @@ __global__ void __launch_bounds__(256) k_copy_peak(const double2* __restrict__ i
     for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (size_t)gridDim.x * 256) out[i] = in[i];
 }
 
-int agb_walk_blocks(int sm_count) { return sm_count * 2; }
+int agb_walk_blocks(int sm_count) { return sm_count * WALK_CTAS; }
 int agb_walk_warps_per_block() { return WALK_WARPS; }
+void agb_far_capacity(int* lcap, int* fcap, int* targets) { *lcap = FAR_LCAP; *fcap = FAR_FCAP; *targets = 32 * SG_GROUPS; }
 
 int agb_launch_walk(AgbDev& d, AgbScalars* s, double globalTime, double e0, double theta, int64_t t0, int64_t t1,
                     bool counters, bool any_gas, bool mixed, int sm_count, cudaStream_t st, cudaEvent_t ev0, cudaEvent_t ev1)
@@ -498,6 +619,7 @@ int agb_launch_walk(AgbDev& d, AgbScalars* s, double globalTime, double e0, doub
     P.ax = d.ax; P.ay = d.ay; P.az = d.az; P.dUdt = d.dUdt;
     P.c_visits = d.c_visits; P.c_accn = d.c_accn; P.c_accl = d.c_accl; P.c_sph = d.c_sph;
     P.spill = d.spill; P.spill_per_warp = d.spill_per_warp;
+    P.far_list = d.far_list; P.far_front = d.far_front; P.far_cnt = d.far_cnt;
     P.s = s; P.N = d.n; P.t0 = t0; P.t1 = t1;
     P.ngroups = (unsigned)((t1 - t0 + 31) / 32);
     P.theta = theta; P.e0 = e0; P.globalTime = globalTime;
@@ -509,6 +631,11 @@ int agb_launch_walk(AgbDev& d, AgbScalars* s, double globalTime, double e0, doub
         int blocks = (int)std::min<int64_t>((int64_t)agb_walk_blocks(sm_count), ((int64_t)P.ngroups + WALK_WARPS - 1) / WALK_WARPS);
         if (blocks * WALK_WARPS > d.spill_warps) blocks = d.spill_warps / WALK_WARPS;
         if (ev0) cudaEventRecord(ev0, st);
+        {   // far-field prepass, one warp per super-group of 256 targets
+            const int64_t sg_first = t0 / (32 * SG_GROUPS);
+            const int nsg = (int)((t1 + 32 * SG_GROUPS - 1) / (32 * SG_GROUPS) - sg_first);
+            k_far<<<std::min((nsg + 3) / 4, sm_count * 8), 128, 0, st>>>(P, nsg, sg_first); launches++;
+        }
         if (counters) { if (any_gas) launch_walk2<true, true>(P, blocks, mixed, st); else launch_walk2<true, false>(P, blocks, mixed, st); }
         else { if (any_gas) launch_walk2<false, true>(P, blocks, mixed, st); else launch_walk2<false, false>(P, blocks, mixed, st); }
         if (ev1) cudaEventRecord(ev1, st);

@@ -6,7 +6,7 @@ Pure torch.distributed, so the same code runs on NCCL (GPUs) and on gloo (CPU te
 import torch
 import torch.distributed as dist
 
-GROUP = 32          # targets per warp; slices are multiples of it so results are bit-identical for any world size
+GROUP = 256         # targets per far-field super-group (8 warps); slices are multiples of it => bit-identical results for any world size
 
 
 def shard_bounds(n, rank, world):

@@ -44,7 +44,7 @@ def test_gather_and_slices_world2(n):
         assert p.exitcode == 0
     assert all(ok for _, ok, _ in res)
     (a0, a1), (b0, b1) = res[0][2], res[1][2]
-    assert a0 == 0 and a1 == b0 and b1 == n and a1 % 32 == 0          # contiguous cover, boundaries on warp groups
+    assert a0 == 0 and a1 == b0 and b1 == n and a1 % 256 == 0          # contiguous cover, boundaries on warp groups
 
 
 def test_slice_rule_covers_everything(pkg):
@@ -53,5 +53,5 @@ def test_slice_rule_covers_everything(pkg):
             b = [pkg.shard.slice_bounds(n, r, parts) for r in range(parts)]
             assert b[0][0] == 0 and b[-1][1] == n
             assert all(b[i][1] == b[i + 1][0] for i in range(parts - 1))
-            assert all(x[0] % 32 == 0 for x in b)
+            assert all(x[0] % 256 == 0 for x in b)
             assert sum(pkg.shard.shard_counts(n, parts)) == n
