@@ -275,11 +275,15 @@ __global__ void __launch_bounds__(WALK_TPB, WALK_CTAS) k_walk(const WalkParams P
             const double lox = warp_min(valid ? tp.x : inf), loy = warp_min(valid ? tp.y : inf), loz = warp_min(valid ? tp.z : inf);
             const double hix = warp_max(valid ? tp.x : -inf), hiy = warp_max(valid ? tp.y : -inf), hiz = warp_max(valid ? tp.z : -inf);
             const double cgx = 0.5 * (lox + hix), cgy = 0.5 * (loy + hiy), cgz = 0.5 * (loz + hiz);
-            float thx = 0, thy = 0, thz = 0, tlx = 0, tly = 0, tlz = 0, hh4cf = 0;
+            float2 nth_x = make_float2(0.f, 0.f), nth_y = nth_x, nth_z = nth_x, ntl_x = nth_x, ntl_y = nth_x, ntl_z = nth_x;
+            float hh4cf = 0;
             if (MIXED) {
+                // minus the target's own float-float position, duplicated into both halves of a packed register
                 const double rx = (tp.x - cgx) * invR, ry = (tp.y - cgy) * invR, rz = (tp.z - cgz) * invR;
-                thx = (float)rx; thy = (float)ry; thz = (float)rz;
-                tlx = (float)(rx - (double)thx); tly = (float)(ry - (double)thy); tlz = (float)(rz - (double)thz);
+                const float thx = (float)rx, thy = (float)ry, thz = (float)rz;
+                const float tlx = (float)(rx - (double)thx), tly = (float)(ry - (double)thy), tlz = (float)(rz - (double)thz);
+                nth_x = make_float2(-thx, -thx); nth_y = make_float2(-thy, -thy); nth_z = make_float2(-thz, -thz);
+                ntl_x = make_float2(-tlx, -tlx); ntl_y = make_float2(-tly, -tly); ntl_z = make_float2(-tlz, -tlz);
                 hh4cf = (float)(hh4 * invR2 * (1.0 + 1e-5));               // generous: the SPH pass re-tests in FP64
             }
             const Box wb{lox, loy, loz, hix, hiy, hiz};
@@ -407,11 +411,13 @@ __global__ void __launch_bounds__(WALK_TPB, WALK_CTAS) k_walk(const WalkParams P
                         const int2 e = sm.list[base + lane];
                         const double4 q = P.src_pm[e.x];
                         if (MIXED) {
+                            // two sources share one 64-byte record, components interleaved (x0 x1 y0 y1 | z0 z1 m0 m1 | lo parts),
+                            // so the evaluation loop can use Blackwell's packed FP32x2 instructions across the pair
                             const double rx = (q.x - cgx) * invR, ry = (q.y - cgy) * invR, rz = (q.z - cgz) * invR;
                             const float hx = (float)rx, hy = (float)ry, hz = (float)rz;
-                            float4* sf = reinterpret_cast<float4*>(&sm.stage[lane]);
-                            sf[0] = make_float4(hx, hy, hz, (float)(q.w * inv_m0));
-                            sf[1] = make_float4((float)(rx - (double)hx), (float)(ry - (double)hy), (float)(rz - (double)hz), 0.f);
+                            float* sf = reinterpret_cast<float*>(&sm.stage[lane & ~1]) + (lane & 1);
+                            sf[0] = hx; sf[2] = hy; sf[4] = hz; sf[6] = (float)(q.w * inv_m0);
+                            sf[8] = (float)(rx - (double)hx); sf[10] = (float)(ry - (double)hy); sf[12] = (float)(rz - (double)hz);
                         } else sm.stage[lane] = q;
                         if (SPH) src_gas = P.src_flag[e.x] != 0;
                         // accepted pairs of this entry: lanes in the mask, minus the target's own leaf, none for a massless leaf
@@ -421,35 +427,49 @@ __global__ void __launch_bounds__(WALK_TPB, WALK_CTAS) k_walk(const WalkParams P
                         const unsigned pc = q.w != 0.0 ? __popc(m) : 0u;
                         if (e.x < N) tot_leaf += pc; else tot_node += pc;
                     }
+                    if (MIXED && lane == cnt && (cnt & 1)) {
+                        // odd tile: the unused half of the last pair must hold finite numbers (0 * inf would poison the sums)
+                        float* sf = reinterpret_cast<float*>(&sm.stage[lane & ~1]) + (lane & 1);
+                        sf[0] = 1.f; sf[2] = 1.f; sf[4] = 1.f; sf[6] = 0.f; sf[8] = 0.f; sf[10] = 0.f; sf[12] = 0.f;
+                    }
                     const unsigned gasmask = SPH ? __ballot_sync(0xffffffffu, src_gas) : 0u;   // tile entries that hold gas
                     if (base + 32 + lane < lc) asm volatile("prefetch.global.L1 [%0];" ::"l"(P.src_pm + sm.list[base + 32 + lane].x));
                     __syncwarp();
                     unsigned gate = 0;                                                   // per lane: entries within ~2h (SPH candidates)
                     if (MIXED) {
-                        float fax = 0.f, fay = 0.f, faz = 0.f;
-#pragma unroll 4
-                        for (int j = 0; j < cnt; j++) {
-                            const int2 e = sm.list[base + j];
-                            const float4 a = reinterpret_cast<const float4*>(&sm.stage[j])[0], b = reinterpret_cast<const float4*>(&sm.stage[j])[1];
-                            const bool bit = ((unsigned)e.y >> lane) & 1u;
-                            const float dx = (a.x - thx) + (b.x - tlx), dy = (a.y - thy) + (b.y - tly), dz = (a.z - thz) + (b.z - tlz);
-                            const float r2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+                        float2 fax = make_float2(0.f, 0.f), fay = fax, faz = fax;
+                        const float2 tiny2 = make_float2(1e-30f, 1e-30f), e022 = make_float2(e02f, e02f);
+#pragma unroll 2
+                        for (int j = 0; j < cnt; j += 2) {
+                            const int4 ee = *reinterpret_cast<const int4*>(&sm.list[base + j]);      // entries j, j+1: (src, mask) x 2
+                            const float4* rec = reinterpret_cast<const float4*>(&sm.stage[j]);
+                            const float4 r0 = rec[0], r1 = rec[1], r2_ = rec[2], r3 = rec[3];
+                            const bool bit0 = ((unsigned)ee.y >> lane) & 1u, bit1 = (j + 1 < cnt) && (((unsigned)ee.w >> lane) & 1u);
+                            // float-float displacement for both sources at once (FADD2)
+                            const float2 dx = __fadd2_rn(__fadd2_rn(make_float2(r0.x, r0.y), nth_x), __fadd2_rn(make_float2(r2_.x, r2_.y), ntl_x));
+                            const float2 dy = __fadd2_rn(__fadd2_rn(make_float2(r0.z, r0.w), nth_y), __fadd2_rn(make_float2(r2_.z, r2_.w), ntl_y));
+                            const float2 dz = __fadd2_rn(__fadd2_rn(make_float2(r1.x, r1.y), nth_z), __fadd2_rn(make_float2(r3.x, r3.y), ntl_z));
+                            const float2 r2 = __ffma2_rn(dz, dz, __ffma2_rn(dy, dy, __fmul2_rn(dx, dx)));
                             // same skip rules as the FP64 loop: d = 0 exactly for the own leaf / coincident sources, and the 1e-30
                             // floor (in units of R^2; real separations are >= 2^-84) keeps the factor finite so f * d = 0
-                            const float r2c = r2 + 1e-30f;
-                            float rinv, iq;
-                            asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rinv) : "f"(r2c));
-                            asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(iq) : "f"(r2c + e02f));
-                            const float f = bit ? a.w * (rinv * iq) : 0.f;
-                            fax = fmaf(f, dx, fax); fay = fmaf(f, dy, fay); faz = fmaf(f, dz, faz);
-                            if (SPH) gate |= (r2 < hh4cf ? 1u : 0u) << j;
+                            const float2 r2c = __fadd2_rn(r2, tiny2), q2 = __fadd2_rn(r2c, e022);
+                            float2 rinv, iq;
+                            asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rinv.x) : "f"(r2c.x));
+                            asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rinv.y) : "f"(r2c.y));
+                            asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(iq.x) : "f"(q2.x));
+                            asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(iq.y) : "f"(q2.y));
+                            float2 f = __fmul2_rn(make_float2(r1.z, r1.w), __fmul2_rn(rinv, iq));
+                            f.x = bit0 ? f.x : 0.f; f.y = bit1 ? f.y : 0.f;
+                            fax = __ffma2_rn(f, dx, fax); fay = __ffma2_rn(f, dy, fay); faz = __ffma2_rn(f, dz, faz);
+                            if (SPH) gate |= ((r2.x < hh4cf ? 1u : 0u) << j) | ((r2.y < hh4cf && j + 1 < cnt ? 2u : 0u) << j);
                             if (COUNT) {
-                                const bool seen = bit && a.w != 0.f;
-                                const bool ok = seen && r2 != 0.f;
-                                if (e.x < N) { c_vis += seen; c_al += ok; } else c_an += ok;
+                                const bool seen0 = bit0 && r1.z != 0.f, ok0 = seen0 && r2.x != 0.f;
+                                const bool seen1 = bit1 && r1.w != 0.f, ok1 = seen1 && r2.y != 0.f;
+                                if (ee.x < N) { c_vis += seen0; c_al += ok0; } else c_an += ok0;
+                                if (ee.z < N) { c_vis += seen1; c_al += ok1; } else c_an += ok1;
                             }
                         }
-                        ax = fma(acc_scale, (double)fax, ax); ay = fma(acc_scale, (double)fay, ay); az = fma(acc_scale, (double)faz, az);
+                        ax = fma(acc_scale, (double)(fax.x + fax.y), ax); ay = fma(acc_scale, (double)(fay.x + fay.y), ay); az = fma(acc_scale, (double)(faz.x + faz.y), az);
                     } else {
 #pragma unroll 4
                     for (int j = 0; j < cnt; j++) {
