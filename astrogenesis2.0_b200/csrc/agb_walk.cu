@@ -158,7 +158,10 @@ __global__ void __launch_bounds__(128) k_far(const WalkParams P, int nsg, int64_
                 sp -= cnt;
                 const int node = lane < cnt ? stk[sp + lane] : -1;
                 int outcome = OUT_NONE;
+                int4 c0 = make_int4(-1, -1, -1, -1), c1 = c0;
                 if (node >= 0) {
+                    c0 = __ldg(reinterpret_cast<const int4*>(P.child) + 2 * (size_t)(node - N));
+                    c1 = __ldg(reinterpret_cast<const int4*>(P.child) + 2 * (size_t)(node - N) + 1);
                     const double4 pm = P.src_pm[node];
                     if (pm.w != 0.0) {
                         const double rad = scalbn(R, -(int)P.ndepth[node - N]);
@@ -180,7 +183,6 @@ __global__ void __launch_bounds__(128) k_far(const WalkParams P, int nsg, int64_
                     int ch[8] = {-1, -1, -1, -1, -1, -1, -1, -1};
                     int cl = 0, cn = 0;
                     if (outcome == OUT_OPEN) {
-                        const int4 c0 = reinterpret_cast<const int4*>(P.child)[2 * (size_t)(node - N)], c1 = reinterpret_cast<const int4*>(P.child)[2 * (size_t)(node - N) + 1];
                         ch[0] = c0.x; ch[1] = c0.y; ch[2] = c0.z; ch[3] = c0.w; ch[4] = c1.x; ch[5] = c1.y; ch[6] = c1.z; ch[7] = c1.w;
 #pragma unroll
                         for (int c = 0; c < 8; c++) { cl += (ch[c] >= 0 && ch[c] < N); cn += (ch[c] >= N); }
@@ -314,7 +316,12 @@ __global__ void __launch_bounds__(WALK_TPB, WALK_CTAS) k_walk(const WalkParams P
                     if (sp + cnt > SCAP) tot_spill += 1;
                     int outcome = OUT_NONE;
                     double rad2 = 0, pmx = 0, pmy = 0, pmz = 0;
+                    // the child slots are requested together with the node record (two independent L2 round trips instead
+                    // of two dependent ones); they are simply not used when the node turns out to be accepted
+                    int4 c0 = make_int4(-1, -1, -1, -1), c1 = c0;
                     if (lane < cnt && e.x >= 0) {
+                        c0 = __ldg(reinterpret_cast<const int4*>(P.child) + 2 * (size_t)(e.x - N));
+                        c1 = __ldg(reinterpret_cast<const int4*>(P.child) + 2 * (size_t)(e.x - N) + 1);
                         const double4 pm = P.src_pm[e.x];
                         pmx = pm.x; pmy = pm.y; pmz = pm.z;
                         if (pm.w != 0.0) {                                       // Node.cpp:250 / :390
@@ -329,12 +336,6 @@ __global__ void __launch_bounds__(WALK_TPB, WALK_CTAS) k_walk(const WalkParams P
                     }
                     // lanes of the entry's mask that accept the node / open it
                     unsigned amask = outcome == OUT_ACCEPT ? (unsigned)e.y : 0u, omask = outcome == OUT_OPEN ? (unsigned)e.y : 0u;
-                    // child slots of every node that may be opened are requested now, before the serial part below
-                    int4 c0 = make_int4(-1, -1, -1, -1), c1 = c0;
-                    if (outcome >= OUT_OPEN) {
-                        c0 = reinterpret_cast<const int4*>(P.child)[2 * (size_t)(e.x - N)];
-                        c1 = reinterpret_cast<const int4*>(P.child)[2 * (size_t)(e.x - N) + 1];
-                    }
                     // straddling nodes: per-lane test, one node at a time; (COM, radius^2) parked in shared memory by the owners
                     unsigned mm = __ballot_sync(0xffffffffu, outcome == OUT_MIXED);
                     if (lane == 0) { st_rounds++; st_popped += cnt; st_mixed += __popc(mm); }
@@ -342,29 +343,44 @@ __global__ void __launch_bounds__(WALK_TPB, WALK_CTAS) k_walk(const WalkParams P
                         if (outcome == OUT_MIXED) sm.stage[lane] = make_double4(pmx, pmy, pmz, rad2);
                         __syncwarp();
                         const unsigned my = (unsigned)e.y;
+                        // two nodes per iteration: their dependency chains interleave
                         do {
-                            const int src = __ffs(mm) - 1;
+                            const int src0 = __ffs(mm) - 1;
                             mm &= mm - 1;
-                            const unsigned nmask = __shfl_sync(0xffffffffu, my, src);
-                            const double4 q = sm.stage[src];
-                            bool acc_l = false, open_l = false;
-                            if ((nmask >> lane) & 1u) {
-                                const double dx = q.x - tp.x, dy = q.y - tp.y, dz = q.z - tp.z;
-                                const double r2 = fma(dz, dz, fma(dy, dy, dx * dx));
-                                if (r2 != 0.0) {                                 // Node.cpp:274 (r == 0 -> return)
-                                    const double lhs = r2 * theta2;
-                                    if (fast_mac && lhs > q.w * (1.0 + 1e-13)) acc_l = true;
-                                    else if (fast_mac && lhs < q.w * (1.0 - 1e-13)) open_l = true;
-                                    else {                                       // the reference's own expression, Node.cpp:271,331-334
-                                        const double r2e = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
-                                        acc_l = __ddiv_rn(__dsqrt_rn(q.w), __dsqrt_rn(r2e)) < theta;   // sqrt(radius^2) is exact: radius = R 2^-k
-                                        open_l = !acc_l;
-                                        tot_exact++;
-                                    }
+                            const int src1 = mm ? __ffs(mm) - 1 : src0;
+                            const bool two = mm != 0u;
+                            mm &= mm - 1;
+                            const unsigned nmask0 = __shfl_sync(0xffffffffu, my, src0), nmask1 = __shfl_sync(0xffffffffu, my, src1);
+                            const double4 q0 = sm.stage[src0], q1 = sm.stage[src1];
+                            bool acc0 = false, open0 = false, acc1 = false, open1 = false;
+                            const double dx0 = q0.x - tp.x, dy0 = q0.y - tp.y, dz0 = q0.z - tp.z;
+                            const double dx1 = q1.x - tp.x, dy1 = q1.y - tp.y, dz1 = q1.z - tp.z;
+                            const double r20 = fma(dz0, dz0, fma(dy0, dy0, dx0 * dx0)), r21 = fma(dz1, dz1, fma(dy1, dy1, dx1 * dx1));
+                            const double lhs0 = r20 * theta2, lhs1 = r21 * theta2;
+                            if (((nmask0 >> lane) & 1u) && r20 != 0.0) {             // Node.cpp:274 (r == 0 -> return)
+                                if (fast_mac && lhs0 > q0.w * (1.0 + 1e-13)) acc0 = true;
+                                else if (fast_mac && lhs0 < q0.w * (1.0 - 1e-13)) open0 = true;
+                                else {                                               // the reference's own expression, Node.cpp:271,331-334
+                                    const double r2e = __dadd_rn(__dadd_rn(__dmul_rn(dx0, dx0), __dmul_rn(dy0, dy0)), __dmul_rn(dz0, dz0));
+                                    acc0 = __ddiv_rn(__dsqrt_rn(q0.w), __dsqrt_rn(r2e)) < theta;   // sqrt(radius^2) is exact: radius = R 2^-k
+                                    open0 = !acc0;
+                                    tot_exact++;
                                 }
                             }
-                            const unsigned a = __ballot_sync(0xffffffffu, acc_l), o = __ballot_sync(0xffffffffu, open_l);
-                            if (lane == src) { amask = a; omask = o; }
+                            if (two && ((nmask1 >> lane) & 1u) && r21 != 0.0) {
+                                if (fast_mac && lhs1 > q1.w * (1.0 + 1e-13)) acc1 = true;
+                                else if (fast_mac && lhs1 < q1.w * (1.0 - 1e-13)) open1 = true;
+                                else {
+                                    const double r2e = __dadd_rn(__dadd_rn(__dmul_rn(dx1, dx1), __dmul_rn(dy1, dy1)), __dmul_rn(dz1, dz1));
+                                    acc1 = __ddiv_rn(__dsqrt_rn(q1.w), __dsqrt_rn(r2e)) < theta;
+                                    open1 = !acc1;
+                                    tot_exact++;
+                                }
+                            }
+                            const unsigned a0 = __ballot_sync(0xffffffffu, acc0), o0 = __ballot_sync(0xffffffffu, open0);
+                            const unsigned a1 = __ballot_sync(0xffffffffu, acc1), o1 = __ballot_sync(0xffffffffu, open1);
+                            if (lane == src0) { amask = a0; omask = o0; }
+                            if (two && lane == src1) { amask = a1; omask = o1; }
                         } while (mm);
                     }
                     // one list entry per node with acceptors
