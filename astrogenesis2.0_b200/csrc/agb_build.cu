@@ -101,44 +101,64 @@ __global__ void __launch_bounds__(TPB) k_extent_max(const double* __restrict__ d
 }
 
 // ------------------------------------------------------------------ keys
+// The reference's descent (Node.cpp:433-443 child centres, :702-719 getOctant): from level `l0` for `nl` levels,
+// returns the packed octants and carries the cell on.  Level l < 21 sits at bit 60-3l of key_hi, 21 <= l < 42 at
+// bit 60-3(l-21) of key_lo.
+struct Cell { double cx, cy, cz, r; };
+
+__device__ __forceinline__ uint64_t descend21(double px, double py, double pz, Cell& c, bool check_bounds_first, bool& edge)
+{
+    uint64_t key = 0;
+#pragma unroll 1
+    for (int l = 0; l < 21; l++) {
+        if (l > 0 || check_bounds_first) {
+            edge |= px < __dadd_rn(c.cx, -c.r) || px > __dadd_rn(c.cx, c.r) || py < __dadd_rn(c.cy, -c.r) || py > __dadd_rn(c.cy, c.r) ||
+                    pz < __dadd_rn(c.cz, -c.r) || pz > __dadd_rn(c.cz, c.r);
+        }
+        const bool ox = px > c.cx, oy = py > c.cy, oz = pz > c.cz;       // Node.cpp:713-716, strict '>'
+        key |= ((uint64_t)ox | ((uint64_t)oy << 1) | ((uint64_t)oz << 2)) << (60 - 3 * l);
+        const double hr = __dmul_rn(c.r, 0.5);                             // Node.cpp:436-440
+        c.cx = __dadd_rn(c.cx, ox ? hr : -hr);
+        c.cy = __dadd_rn(c.cy, oy ? hr : -hr);
+        c.cz = __dadd_rn(c.cz, oz ? hr : -hr);
+        c.r = hr;
+    }
+    return key;
+}
+
+// key_hi (outlier flag + levels 0..20) for every particle; key_lo is produced on demand by key_lo_of()
 __global__ void __launch_bounds__(TPB) k_keygen(const double* __restrict__ x, const double* __restrict__ y, const double* __restrict__ z, int64_t n,
-                                                  uint64_t* __restrict__ khi, uint64_t* __restrict__ klo, uint32_t* __restrict__ perm, AgbScalars* s)
+                                                  uint64_t* __restrict__ khi, uint32_t* __restrict__ perm, AgbScalars* s)
 {
     int64_t i = (int64_t)blockIdx.x * TPB + threadIdx.x;
     bool outl = false, edge = false;
     if (i < n) {
         const double R = __longlong_as_double((long long)s->Rbits);
         const double px = x[i], py = y[i], pz = z[i];
-        uint64_t hi = 0, lo = 0;
+        uint64_t hi;
         // root cube is centred on the origin (Tree.cpp:31); inclusive bounds (Node.cpp:706-711)
         outl = px < -R || px > R || py < -R || py > R || pz < -R || pz > R;
-        if (outl) {
-            hi = AGB_OUTLIER_BIT; lo = (uint64_t)i;      // keep caller order among the outliers
-        } else {
-            double cx = 0.0, cy = 0.0, cz = 0.0, r = R;
-#pragma unroll 1
-            for (int l = 0; l < AGB_MAX_LEVELS; l++) {
-                if (l > 0) {
-                    edge |= px < __dadd_rn(cx, -r) || px > __dadd_rn(cx, r) || py < __dadd_rn(cy, -r) || py > __dadd_rn(cy, r) ||
-                            pz < __dadd_rn(cz, -r) || pz > __dadd_rn(cz, r);
-                }
-                const bool ox = px > cx, oy = py > cy, oz = pz > cz;       // Node.cpp:713-716
-                const uint64_t oct = (uint64_t)ox | ((uint64_t)oy << 1) | ((uint64_t)oz << 2);
-                if (l < 21) hi |= oct << (60 - 3 * l); else lo |= oct << (60 - 3 * (l - 21));
-                const double hr = __dmul_rn(r, 0.5);                       // Node.cpp:436-440
-                cx = __dadd_rn(cx, ox ? hr : -hr);
-                cy = __dadd_rn(cy, oy ? hr : -hr);
-                cz = __dadd_rn(cz, oz ? hr : -hr);
-                r = hr;
-            }
-        }
-        khi[i] = hi; klo[i] = lo; perm[i] = (uint32_t)i;
+        if (outl) hi = AGB_OUTLIER_BIT;           // the stable sort keeps caller order among the outliers
+        else { Cell c{0.0, 0.0, 0.0, R}; hi = descend21(px, py, pz, c, false, edge); }
+        khi[i] = hi; perm[i] = (uint32_t)i;
     }
     unsigned mo = __ballot_sync(0xffffffffu, outl), me = __ballot_sync(0xffffffffu, edge);
     if ((threadIdx.x & 31) == 0) {
         if (mo) atomicAdd(&s->n_outliers, __popc(mo));
         if (me) atomicAdd(&s->edge_dropped, __popc(me));
     }
+}
+
+// levels 21..41 of one particle (only needed where two particles share all of key_hi)
+__device__ uint64_t key_lo_of(double px, double py, double pz, double R, AgbScalars* s)
+{
+    bool edge = false;
+    Cell c{0.0, 0.0, 0.0, R};
+    descend21(px, py, pz, c, false, edge);
+    bool edge2 = false;
+    const uint64_t lo = descend21(px, py, pz, c, true, edge2);
+    if (edge2 && !edge) atomicAdd(&s->edge_dropped, 1);
+    return lo;
 }
 
 // ------------------------------------------------------------------ LSD radix sort (8-bit digits)
@@ -277,17 +297,11 @@ __global__ void __launch_bounds__(TPB) k_sort_scatter(const uint64_t* __restrict
     }
 }
 
-// key_lo into tree order
-__global__ void __launch_bounds__(TPB) k_gather_lo(const uint64_t* __restrict__ lo_in, const uint32_t* __restrict__ perm, int64_t n, uint64_t* __restrict__ lo_out)
-{
-    int64_t i = (int64_t)blockIdx.x * TPB + threadIdx.x;
-    if (i < n) lo_out[i] = lo_in[perm[i]];
-}
-
 // runs of in-tree particles with equal key_hi (they share >= 21 levels): order them by key_lo.
 // Short runs are insertion-sorted by the thread at the run start; long ones are queued for k_fix_long_runs.
 constexpr int FIX_SHORT = 16, FIX_LONG_MAX = 4096;
 __global__ void __launch_bounds__(TPB) k_fix_runs(const uint64_t* __restrict__ hi, uint64_t* __restrict__ lo, uint32_t* __restrict__ perm, int64_t n,
+                                                    const double* __restrict__ x, const double* __restrict__ y, const double* __restrict__ z,
                                                     AgbScalars* s, int32_t* __restrict__ longlist)
 {
     int64_t i = (int64_t)blockIdx.x * TPB + threadIdx.x;
@@ -300,9 +314,11 @@ __global__ void __launch_bounds__(TPB) k_fix_runs(const uint64_t* __restrict__ h
     const int len = (int)(e - i + 1);
     if (len > FIX_SHORT) {
         if (len > FIX_LONG_MAX) { atomicAdd(&s->dup_keys, 1); return; }
-        longlist[2 * atomicAdd(&s->n_long_runs, 1)] = (int32_t)i; 
+        longlist[atomicAdd(&s->n_long_runs, 1)] = (int32_t)i;
         return;
     }
+    const double R = __longlong_as_double((long long)s->Rbits);
+    for (int a = 0; a < len; a++) { const uint32_t p = perm[i + a]; lo[i + a] = key_lo_of(x[p], y[p], z[p], R, s); }
     for (int a = 1; a < len; a++) {                                  // stable insertion sort
         const uint64_t kl = lo[i + a]; const uint32_t kp = perm[i + a];
         int b = a - 1;
@@ -312,13 +328,15 @@ __global__ void __launch_bounds__(TPB) k_fix_runs(const uint64_t* __restrict__ h
 }
 
 __global__ void __launch_bounds__(TPB) k_fix_long_runs(const uint64_t* __restrict__ hi, uint64_t* __restrict__ lo, uint32_t* __restrict__ perm, int64_t n,
-                                                         const AgbScalars* __restrict__ s, const int32_t* __restrict__ longlist)
+                                                         const double* __restrict__ x, const double* __restrict__ y, const double* __restrict__ z,
+                                                         AgbScalars* s, const int32_t* __restrict__ longlist)
 {
     __shared__ uint64_t sl[FIX_LONG_MAX];
     __shared__ uint32_t sp[FIX_LONG_MAX];
     const int64_t nt = n - s->n_outliers;
+    const double R = __longlong_as_double((long long)s->Rbits);
     for (int q = blockIdx.x; q < s->n_long_runs; q += gridDim.x) {
-        const int64_t i = longlist[2 * q];
+        const int64_t i = longlist[q];
         const uint64_t h = hi[i];
         int64_t e = i;
         while (e + 1 < nt && hi[e + 1] == h) e++;
@@ -326,7 +344,10 @@ __global__ void __launch_bounds__(TPB) k_fix_long_runs(const uint64_t* __restric
         int p2 = 1;
         while (p2 < len) p2 <<= 1;
         __syncthreads();
-        for (int j = threadIdx.x; j < p2; j += TPB) { sl[j] = j < len ? lo[i + j] : ~0ull; sp[j] = j < len ? perm[i + j] : 0xffffffffu; }
+        for (int j = threadIdx.x; j < p2; j += TPB) {
+            if (j < len) { const uint32_t p = perm[i + j]; sp[j] = p; sl[j] = key_lo_of(x[p], y[p], z[p], R, s); }
+            else { sl[j] = ~0ull; sp[j] = 0xffffffffu; }
+        }
         __syncthreads();
         for (int size = 2; size <= p2; size <<= 1)
             for (int stride = size >> 1; stride > 0; stride >>= 1) {
@@ -355,15 +376,21 @@ __global__ void __launch_bounds__(TPB) k_gather(AgbDev d, const uint32_t* __rest
     uint8_t t = d.type[p];
     bool gas = t == 2;
     d.src_pm[i] = make_double4(d.x[p], d.y[p], d.z[p], m);
-    d.src_gv[i] = make_double4(d.vx ? d.vx[p] : 0.0, d.vy ? d.vy[p] : 0.0, d.vz ? d.vz[p] : 0.0, gas ? m : 0.0);
-    d.src_flag[i] = (gas && m > 0.0) ? 1 : 0;
-    if (gas) s->any_gas = 1;
     d.s_type[i] = t;
-    d.s_U[i] = d.U ? d.U[p] : 0.0;
-    d.s_mu[i] = d.mu ? d.mu[p] : 0.58;
     d.s_next[i] = d.next ? d.next[p] : 0.0;
-    d.s_rho[i] = d.rho[p]; d.s_P[i] = d.P[p]; d.s_T[i] = d.T[p];
-    d.s_h[i] = gas ? 0.0 : d.h[p];                   // Tree.cpp:123-133 zeroes h of every gas particle
+    if (gas) {
+        // velocity, U, mu and the carried h/rho/P/T are only ever read for gas (Node.cpp:88-172, :722-796)
+        d.src_gv[i] = make_double4(d.vx ? d.vx[p] : 0.0, d.vy ? d.vy[p] : 0.0, d.vz ? d.vz[p] : 0.0, m);
+        d.src_flag[i] = m > 0.0 ? 1 : 0;
+        s->any_gas = 1;
+        d.s_U[i] = d.U ? d.U[p] : 0.0;
+        d.s_mu[i] = d.mu ? d.mu[p] : 0.58;
+        d.s_rho[i] = d.rho[p]; d.s_P[i] = d.P[p]; d.s_T[i] = d.T[p];
+        d.s_h[i] = 0.0;                               // Tree.cpp:123-133 zeroes h of every gas particle
+    } else {
+        d.src_gv[i] = make_double4(0.0, 0.0, 0.0, 0.0);
+        d.src_flag[i] = 0;
+    }
     d.group[i] = -1;
     d.leafparent[i] = -1;
     d.leafdepth[i] = -1;
@@ -548,9 +575,20 @@ __device__ __forceinline__ double4 ldcg4(const double4* p)
     return make_double4(a.x, a.y, b.x, b.y);
 }
 
-__device__ __forceinline__ void node_moments(const AgbDev& d, int k, int N)
+__device__ __forceinline__ void node_moments(const AgbDev& d, int k, int N, bool any_gas)
 {
     double sx = 0, sy = 0, sz = 0, m = 0, gx = 0, gy = 0, gz = 0, g = 0;
+    if (!any_gas) {
+#pragma unroll
+        for (int o = 0; o < 8; o++) {
+            int c = d.child[(size_t)k * 8 + o];
+            if (c < 0) continue;
+            if (c < N) { double4 pm = d.src_pm[c]; m += pm.w; sx += pm.x * pm.w; sy += pm.y * pm.w; sz += pm.z * pm.w; }
+            else { double4 pm = ldcg4(&d.mom_pm[c - N]); m += pm.w; sx += pm.x; sy += pm.y; sz += pm.z; }
+        }
+        d.mom_pm[k] = make_double4(sx, sy, sz, m);
+        return;
+    }
 #pragma unroll
     for (int o = 0; o < 8; o++) {                      // fixed octant order => run-to-run identical sums
         int c = d.child[(size_t)k * 8 + o];
@@ -576,8 +614,9 @@ __global__ void __launch_bounds__(TPB) k_upward(AgbDev d, const AgbScalars* __re
     const int N = (int)d.n;
     if (count_node_children(d.child, k, N) != 0) return;      // only nodes whose children are all leaves start a climb
     int cur = k;
+    const bool any_gas = s->any_gas != 0;
     while (true) {
-        node_moments(d, cur, N);
+        node_moments(d, cur, N, any_gas);
         __threadfence();
         int par = d.nparent[cur];
         if (par < 0) break;
@@ -611,7 +650,7 @@ __global__ void __launch_bounds__(TPB) k_root_fix(AgbDev d, const AgbScalars* __
     if (threadIdx.x == 0) {
         double t[8];
         for (int k = 0; k < 8; k++) { t[k] = 0; for (int w = 0; w < TPB / 32; w++) t[k] += sh[k][w]; }
-        double4 pm = d.mom_pm[0], gv = d.mom_gv[0];
+        double4 pm = d.mom_pm[0], gv = s->any_gas ? d.mom_gv[0] : make_double4(0, 0, 0, 0);
         pm.x += t[0]; pm.y += t[1]; pm.z += t[2]; pm.w += t[3];
         gv.x += t[4]; gv.y += t[5]; gv.z += t[6]; gv.w += t[7];
         d.mom_pm[0] = pm; d.mom_gv[0] = gv;
@@ -623,7 +662,7 @@ __global__ void __launch_bounds__(TPB) k_finalize(AgbDev d, const AgbScalars* __
     int k = blockIdx.x * TPB + threadIdx.x;
     if (k >= s->n_nodes) return;
     const int64_t N = d.n;
-    double4 pm = d.mom_pm[k], gv = d.mom_gv[k];
+    double4 pm = d.mom_pm[k], gv = s->any_gas ? d.mom_gv[k] : make_double4(0, 0, 0, 0);
     double4 com = make_double4(0, 0, 0, pm.w), mv = make_double4(0, 0, 0, gv.w);
     if (pm.w > 0.0) { com.x = pm.x / pm.w; com.y = pm.y / pm.w; com.z = pm.z / pm.w; }
     if (gv.w > 0.0) { mv.x = gv.x / gv.w; mv.y = gv.y / gv.w; mv.z = gv.z / gv.w; }
@@ -676,7 +715,7 @@ int agb_launch_extent(const AgbDev& d, AgbScalars* s, cudaStream_t st)
 
 int agb_launch_keygen(AgbDev& d, AgbScalars* s, cudaStream_t st)
 {
-    k_keygen<<<nblk(d.n, TPB), TPB, 0, st>>>(d.x, d.y, d.z, d.n, d.khi[0], d.klo[0], d.perm[0], s);
+    k_keygen<<<nblk(d.n, TPB), TPB, 0, st>>>(d.x, d.y, d.z, d.n, d.khi[0], d.perm[0], s);
     d.cur = 0;
     return 1;
 }
@@ -701,13 +740,14 @@ static int sort_passes(AgbDev& d, AgbScalars* s, cudaStream_t st)
 
 int agb_launch_sort(AgbDev& d, AgbScalars* s, cudaStream_t st)
 {
-    // key_hi + caller index: 8 passes; the result lands in half 0 again.  key_lo: klo[0] caller order -> klo[1] tree order.
+    // key_hi + caller index: 8 passes; the result lands in half 0 again.  key_lo (tree order, klo[1]) is zero except
+    // inside runs of equal key_hi, where it is computed on demand and decides the order.
     int launches = d.n >= (4 << 20) ? sort_passes<16>(d, s, st) : sort_passes<8>(d, s, st);
     const int nb = nblk(d.n, TPB);
-    k_gather_lo<<<nb, TPB, 0, st>>>(d.klo[0], d.perm[d.cur], d.n, d.klo[1]);
-    k_fix_runs<<<nb, TPB, 0, st>>>(d.khi[d.cur], d.klo[1], d.perm[d.cur], d.n, s, d.nodecnt);
-    k_fix_long_runs<<<64, TPB, 0, st>>>(d.khi[d.cur], d.klo[1], d.perm[d.cur], d.n, s, d.nodecnt);
-    return launches + 3;
+    cudaMemsetAsync(d.klo[1], 0, (size_t)d.n * sizeof(uint64_t), st);
+    k_fix_runs<<<nb, TPB, 0, st>>>(d.khi[d.cur], d.klo[1], d.perm[d.cur], d.n, d.x, d.y, d.z, s, d.nodecnt);
+    k_fix_long_runs<<<64, TPB, 0, st>>>(d.khi[d.cur], d.klo[1], d.perm[d.cur], d.n, d.x, d.y, d.z, s, d.nodecnt);
+    return launches + 2;
 }
 
 int agb_launch_links(AgbDev& d, AgbScalars* s, cudaStream_t st)
