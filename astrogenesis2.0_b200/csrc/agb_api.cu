@@ -14,7 +14,9 @@ void agb_far_capacity(int* lcap, int* fcap, int* targets);
 
 struct agb_ctx {
     int device = 0, sm_count = 148;
-    cudaStream_t st = nullptr;
+    cudaStream_t st = nullptr, st_copy = nullptr;   // compute stream; upload stream for everything but x, y, z
+    cudaEvent_t ev_in = nullptr;                      // uploads on st_copy complete
+    bool in_pending = false;
     cudaEvent_t ev[8] = {};
     AgbDev d;
     AgbScalars* s = nullptr;            // device
@@ -115,15 +117,17 @@ int fetch_scalars(agb_ctx* c)
 // copy (or zero / constant fill) one caller array into an owned device array
 int put_array(agb_ctx* c, double* dst, const double* src, int64_t n, int memspace)
 {
-    if (!src) { CK(cudaMemsetAsync(dst, 0, (size_t)n * sizeof(double), c->st)); return AGB_OK; }
-    CK(cudaMemcpyAsync(dst, src, (size_t)n * sizeof(double), memspace == AGB_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, c->st));
+    if (!src) { CK(cudaMemsetAsync(dst, 0, (size_t)n * sizeof(double), c->st_copy)); return AGB_OK; }
+    CK(cudaMemcpyAsync(dst, src, (size_t)n * sizeof(double), memspace == AGB_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, c->st_copy));
     return AGB_OK;
 }
 
+// positions go on the compute stream (the build starts with them); everything else is uploaded on a second stream
+// that the build only joins before it permutes the particle data (k_gather), so it overlaps extent + keys + sort
 int own_input(agb_ctx* c, const double*& slot, int which, const double* src, int64_t n)
 {
     if (!src) { slot = nullptr; return AGB_OK; }
-    CK(cudaMemcpyAsync(c->in_d[which], src, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, c->st));
+    CK(cudaMemcpyAsync(c->in_d[which], src, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, which < 3 ? c->st : c->st_copy));
     slot = c->in_d[which];
     return AGB_OK;
 }
@@ -165,6 +169,8 @@ int agb_create(agb_ctx** out, int device, int compat_cores)
     c->sm_count = prop.multiProcessorCount;
     c->d.cores = compat_cores > 0 ? compat_cores : 1;
     if (cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking) != cudaSuccess) { delete c; return AGB_ERR_NO_DEVICE; }
+    if (cudaStreamCreateWithFlags(&c->st_copy, cudaStreamNonBlocking) != cudaSuccess) { delete c; return AGB_ERR_NO_DEVICE; }
+    cudaEventCreateWithFlags(&c->ev_in, cudaEventDisableTiming);
     for (auto& e : c->ev) cudaEventCreate(&e);
     if (cudaMalloc((void**)&c->s, sizeof(AgbScalars)) != cudaSuccess) { delete c; return AGB_ERR_NOMEM; }
     cudaMemsetAsync(c->s, 0, sizeof(AgbScalars), c->st);
@@ -180,8 +186,9 @@ int agb_destroy(agb_ctx* c)
 {
     if (!c) return AGB_ERR_INVALID;
     cudaSetDevice(c->device);
-    cudaStreamSynchronize(c->st);
+    cudaStreamSynchronize(c->st); cudaStreamSynchronize(c->st_copy);
     free_pool(c);
+    cudaEventDestroy(c->ev_in); cudaStreamDestroy(c->st_copy);
     cudaFree(c->d.spill);
     cudaFree(c->s);
     if (c->stage) cudaFreeHost(c->stage);
@@ -218,15 +225,18 @@ int agb_set_particles(agb_ctx* c, const agb_particles* p, int memspace)
             (rc = own_input(c, d.vx, 3, p->vx, n)) || (rc = own_input(c, d.vy, 4, p->vy, n)) || (rc = own_input(c, d.vz, 5, p->vz, n)) ||
             (rc = own_input(c, d.mass, 6, p->mass, n)) || (rc = own_input(c, d.U, 7, p->U, n)) || (rc = own_input(c, d.next, 8, p->next_time, n)) ||
             (rc = own_input(c, d.mu, 9, p->mu, n))) return rc;
-        CK(cudaMemcpyAsync(c->in_type, p->type, (size_t)n, cudaMemcpyHostToDevice, c->st));
+        CK(cudaMemcpyAsync(c->in_type, p->type, (size_t)n, cudaMemcpyHostToDevice, c->st_copy));
         d.type = c->in_type;
         c->bound = false;
     }
     if ((rc = put_array(c, d.ax, p->ax, n, memspace)) || (rc = put_array(c, d.ay, p->ay, n, memspace)) || (rc = put_array(c, d.az, p->az, n, memspace)) ||
         (rc = put_array(c, d.dUdt, p->dUdt, n, memspace)) || (rc = put_array(c, d.h, p->h, n, memspace)) || (rc = put_array(c, d.rho, p->rho, n, memspace)) ||
         (rc = put_array(c, d.P, p->P, n, memspace)) || (rc = put_array(c, d.T, p->T, n, memspace))) return rc;
-    CK(cudaMemsetAsync(d.vis, 0, (size_t)std::max<int64_t>(n, 1) * sizeof(double), c->st));
-    if (memspace == AGB_MEM_HOST) CK(cudaStreamSynchronize(c->st));   // caller buffers may be reused after return
+    CK(cudaMemsetAsync(d.vis, 0, (size_t)std::max<int64_t>(n, 1) * sizeof(double), c->st_copy));
+    CK(cudaEventRecord(c->ev_in, c->st_copy));
+    c->in_pending = true;
+    // Host arrays are read asynchronously (pinned memory makes that a true overlap): like the reference, which reads
+    // Simulation::particles during buildTree, they must stay untouched until agb_build_tree has returned.
     c->have_particles = true; c->built = false; c->dens_done = false; c->forces_done = false; c->counters_valid = false;
     return AGB_OK;
 }
@@ -279,6 +289,7 @@ int agb_build_tree(agb_ctx* c, double* root_radius)
     c->launches += agb_launch_extent(d, c->s, c->st);
     c->launches += agb_launch_keygen(d, c->s, c->st);
     c->launches += agb_launch_sort(d, c->s, c->st);
+    if (c->in_pending) { CK(cudaStreamWaitEvent(c->st, c->ev_in, 0)); c->in_pending = false; }
     c->launches += agb_launch_links(d, c->s, c->st);
     CK(cudaEventRecord(c->ev[1], c->st));
     CK(cudaGetLastError());
@@ -375,6 +386,7 @@ int agb_get_results(agb_ctx* c, const agb_results* r, int memspace)
     CK(cudaSetDevice(c->device));
     const size_t b = (size_t)c->d.n * sizeof(double);
     const cudaMemcpyKind k = memspace == AGB_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+    if (c->in_pending) { CK(cudaStreamWaitEvent(c->st, c->ev_in, 0)); c->in_pending = false; }
     const AgbDev& d = c->d;
     struct { double* dst; const double* src; } cp[] = {{r->ax, d.ax}, {r->ay, d.ay}, {r->az, d.az}, {r->dUdt, d.dUdt}, {r->h, d.h},
                                                        {r->rho, d.rho}, {r->P, d.P}, {r->T, d.T}, {r->visualDensity, d.vis}};

@@ -71,6 +71,7 @@ class Context:
         keep["type"] = t
         st.type = capi.dptr(t, C.c_uint8)
         capi.check(self.h, self.lib.agb_set_particles(self.h, C.byref(st), capi.AGB_MEM_HOST))
+        self._keep = keep          # uploads are asynchronous: the arrays must outlive agb_build_tree
         self.n = n
 
     def set_particles_device(self, ptrs, n):

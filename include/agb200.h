@@ -98,7 +98,9 @@ typedef struct {
 int agb_create(agb_ctx** out, int device, int compat_cores);
 int agb_destroy(agb_ctx* ctx);
 
-/* -------- particle hand-over (replaces the path's direct reads of Simulation::particles) */
+/* -------- particle hand-over (replaces the path's direct reads of Simulation::particles)
+ * Host arrays are uploaded asynchronously and must stay untouched until agb_build_tree() has returned (the reference
+ * likewise reads its particles during buildTree); device arrays are read in place until the next hand-over. */
 int agb_set_particles(agb_ctx* ctx, const agb_particles* p, int memspace);
 int agb_set_particles_aos(agb_ctx* ctx, void* const* particles, int64_t n, const agb_aos_layout* layout);
 
