@@ -36,7 +36,7 @@ constexpr int LGROW = 288;                 // worst-case growth per pop round: 3
 #define AGB_WALK_CTAS_PER_SM 2
 #endif
 constexpr int WALK_CTAS = AGB_WALK_CTAS_PER_SM;
-constexpr int SCAP = WALK_CTAS >= 3 ? 384 : 512;   // shared part of the traversal stack (the rest spills to global memory)
+constexpr int SCAP = 384;   // shared part of the traversal stack (the rest spills to global memory)
 constexpr int GASBIT = 1 << 30;
 constexpr int IDXMASK = GASBIT - 1;
 constexpr double kG = 6.67430e-11;         // Math/Constants.h:7
@@ -47,7 +47,9 @@ struct WarpSmem {
     int2 list[LCAP];
     int2 stack[SCAP];
     double4 stage[32];                     // drain: the 32 sources of a tile; traversal: (COM, mass) of straddling nodes
-    double4 tsph[32];                      // per gas target: 1/h, 1/(pi h^4), 2 P/rho^2, sound speed (kept out of registers)
+    double4 tsph[96];                      // per gas target: (1/h, 1/(pi h^4), 2 P/rho^2, sound speed), (vx, vy, vz, h), 8 floats: -(float-float position), (2h/R)^2
+    double4 res[32];                       // SPH pair results (fx, fy, fz, dU) on their way to the owning lane
+    double4 gst[32];                       // drain: (velocity | mVel, gasMass) of the tile's gas-bearing sources
 };
 
 // 1/sqrt(x) for positive normal x: MUFU.RSQ64H seed (~2^-22) + one cubically convergent step (~2^-60).
@@ -230,6 +232,7 @@ __global__ void __launch_bounds__(WALK_TPB, WALK_CTAS) k_walk(const WalkParams P
     const double m0 = n_nodes > 0 ? fmax(P.src_pm[N].w / (double)max(n_in_tree, 1), 1e-300) : (n_in_tree > 0 && P.src_pm[0].w > 0.0 ? P.src_pm[0].w : 1.0);
     const double inv_m0 = 1.0 / m0, acc_scale = kG * m0 * invR2;
     const float e02f = (float)e02s;
+    const double invR4 = invR2 * invR2;
 
     unsigned long long tot_node = 0, tot_leaf = 0, tot_sph = 0, tot_visit = 0, tot_exact = 0, tot_spill = 0;
     unsigned long long st_rounds = 0, st_popped = 0, st_mixed = 0, st_open = 0, st_drain = 0;
@@ -266,7 +269,9 @@ __global__ void __launch_bounds__(WALK_TPB, WALK_CTAS) k_walk(const WalkParams P
             // the reference overrides h_j, rho_j, P_j with the target's own values (Node.cpp:94,101,108)
             const double rho = P.s_rho[t], Pr = P.s_P[t];
             const double inv_h = 1.0 / h_t, pr2 = Pr / (rho * rho);
-            sm.tsph[lane] = make_double4(inv_h, inv_h * inv_h * inv_h * inv_h / kPI, pr2 + pr2, sqrt(kGAMMA * Pr / rho));
+            sm.tsph[3 * lane] = make_double4(inv_h, inv_h * inv_h * inv_h * inv_h / kPI, pr2 + pr2, sqrt(kGAMMA * Pr / rho));
+            const double4 tv = P.src_gv[t];
+            sm.tsph[3 * lane + 1] = make_double4(tv.x, tv.y, tv.z, h_t);
         }
         double ax = 0, ay = 0, az = 0, dU = 0;
         int c_vis = (active && (n_nodes > 0 || !valid)) ? 1 : 0, c_an = 0, c_al = 0, c_sp = 0;              // the root call itself
@@ -278,7 +283,7 @@ __global__ void __launch_bounds__(WALK_TPB, WALK_CTAS) k_walk(const WalkParams P
             const double hix = warp_max(valid ? tp.x : -inf), hiy = warp_max(valid ? tp.y : -inf), hiz = warp_max(valid ? tp.z : -inf);
             const double cgx = 0.5 * (lox + hix), cgy = 0.5 * (loy + hiy), cgz = 0.5 * (loz + hiz);
             float2 nth_x = make_float2(0.f, 0.f), nth_y = nth_x, nth_z = nth_x, ntl_x = nth_x, ntl_y = nth_x, ntl_z = nth_x;
-            float hh4cf = 0;
+            float hh4cf = 0, hh4sf = 0;
             if (MIXED) {
                 // minus the target's own float-float position, duplicated into both halves of a packed register
                 const double rx = (tp.x - cgx) * invR, ry = (tp.y - cgy) * invR, rz = (tp.z - cgz) * invR;
@@ -286,7 +291,12 @@ __global__ void __launch_bounds__(WALK_TPB, WALK_CTAS) k_walk(const WalkParams P
                 const float tlx = (float)(rx - (double)thx), tly = (float)(ry - (double)thy), tlz = (float)(rz - (double)thz);
                 nth_x = make_float2(-thx, -thx); nth_y = make_float2(-thy, -thy); nth_z = make_float2(-thz, -thz);
                 ntl_x = make_float2(-tlx, -tlx); ntl_y = make_float2(-tly, -tly); ntl_z = make_float2(-tlz, -tlz);
-                hh4cf = (float)(hh4 * invR2 * (1.0 + 1e-5));               // generous: the SPH pass re-tests in FP64
+                hh4sf = (float)(hh4 * invR2);
+                hh4cf = hh4sf * (1.0f + 1e-5f);                            // generous: the SPH pass decides
+                if (SPH && tgas) {
+                    float* tf = reinterpret_cast<float*>(&sm.tsph[3 * lane + 2]);
+                    tf[0] = nth_x.x; tf[1] = nth_y.x; tf[2] = nth_z.x; tf[3] = ntl_x.x; tf[4] = ntl_y.x; tf[5] = ntl_z.x; tf[6] = hh4sf; tf[7] = 0.f;
+                }
             }
             const Box wb{lox, loy, loz, hix, hiy, hiz};
             // start from what the far-field prepass left for this super-group: a shared accept list and a frontier
@@ -435,7 +445,7 @@ __global__ void __launch_bounds__(WALK_TPB, WALK_CTAS) k_walk(const WalkParams P
                             sf[0] = hx; sf[2] = hy; sf[4] = hz; sf[6] = (float)(q.w * inv_m0);
                             sf[8] = (float)(rx - (double)hx); sf[10] = (float)(ry - (double)hy); sf[12] = (float)(rz - (double)hz);
                         } else sm.stage[lane] = q;
-                        if (SPH) src_gas = P.src_flag[e.x] != 0;
+                        if (SPH) { src_gas = P.src_flag[e.x] != 0; if (src_gas) sm.gst[lane] = P.src_gv[e.x]; }
                         // accepted pairs of this entry: lanes in the mask, minus the target's own leaf, none for a massless leaf
                         unsigned m = (unsigned)e.y;
                         const int64_t self_lane = (int64_t)e.x - (P.t0 + (int64_t)g * 32);
@@ -477,7 +487,7 @@ __global__ void __launch_bounds__(WALK_TPB, WALK_CTAS) k_walk(const WalkParams P
                             float2 f = __fmul2_rn(make_float2(r1.z, r1.w), __fmul2_rn(rinv, iq));
                             f.x = bit0 ? f.x : 0.f; f.y = bit1 ? f.y : 0.f;
                             fax = __ffma2_rn(f, dx, fax); fay = __ffma2_rn(f, dy, fay); faz = __ffma2_rn(f, dz, faz);
-                            if (SPH) gate |= ((r2.x < hh4cf ? 1u : 0u) << j) | ((r2.y < hh4cf && j + 1 < cnt ? 2u : 0u) << j);
+                            if (SPH) gate |= ((bit0 && r2.x < hh4cf ? 1u : 0u) << j) | ((bit1 && r2.y < hh4cf ? 2u : 0u) << j);
                             if (COUNT) {
                                 const bool seen0 = bit0 && r1.z != 0.f, ok0 = seen0 && r2.x != 0.f;
                                 const bool seen1 = bit1 && r1.w != 0.f, ok1 = seen1 && r2.y != 0.f;
@@ -511,14 +521,90 @@ __global__ void __launch_bounds__(WALK_TPB, WALK_CTAS) k_walk(const WalkParams P
                     }
                     if (SPH) {
                         // second pass over the few (target, source) pairs that can pass r < 2 h_i (Node.cpp:316-325, :368-377)
-                        gate &= gasmask;
-                        unsigned any = __reduce_or_sync(0xffffffffu, gate);
-                        while (any) {
-                            const int j = __ffs(any) - 1;
-                            any &= any - 1;
+                        unsigned mine = gate & gasmask;
+                        if (MIXED) {
+                            // Pair-parallel: the warp's candidate (target, source) pairs of this tile are enumerated in (target, source)
+                            // order and handed out one per lane, 32 at a time; results travel through shared memory back to the owning
+                            // lane, which adds its own pairs in source order (deterministic, identical to a per-target loop).
+                            const int npair = __popc(mine);
+                            const int incl = warp_incl_scan(npair, lane);
+                            const int total = __shfl_sync(0xffffffffu, incl, 31);
+                            for (int c0 = 0; c0 < total; c0 += 32) {
+                                const int p = c0 + lane;
+                                int owner = 0;                                   // first lane whose inclusive count exceeds p
+#pragma unroll
+                                for (int step = 16; step > 0; step >>= 1) {
+                                    const int probe = __shfl_sync(0xffffffffu, incl, owner + step - 1);
+                                    if (probe <= p) owner += step;
+                                }
+                                owner = min(owner, 31);
+                                const int o_incl = __shfl_sync(0xffffffffu, incl, owner), o_cnt = __shfl_sync(0xffffffffu, npair, owner);
+                                const unsigned o_mine = __shfl_sync(0xffffffffu, mine, owner);
+                                double fx = 0, fy = 0, fz = 0, du = 0;
+                                if (p < total) {
+                                    const int j = __fns(o_mine, 0, p - (o_incl - o_cnt) + 1);
+                                    const int2 e = sm.list[base + j];
+                                    const double4 gv = sm.gst[j];                // (mVel | particle velocity, gasMass)
+                                    const double4 k4 = sm.tsph[3 * owner], tv = sm.tsph[3 * owner + 1];
+                                    const float* tf = reinterpret_cast<const float*>(&sm.tsph[3 * owner + 2]);
+                                    const float* rec = reinterpret_cast<const float*>(&sm.stage[j & ~1]) + (j & 1);
+                                    // displacement from the tile's float-float record (units of R), like the gravity loop; d = x_i - COM (Node.cpp:116)
+                                    const float sx = -((rec[0] + tf[0]) + (rec[8] + tf[3])), sy = -((rec[2] + tf[1]) + (rec[10] + tf[4])),
+                                                sz = -((rec[4] + tf[2]) + (rec[12] + tf[5]));
+                                    const float r2s = fmaf(sz, sz, fmaf(sy, sy, sx * sx)), hh4o = tf[6];
+                                    const bool live = rec[6] != 0.f && r2s != 0.f;
+                                    bool pass = live && r2s < hh4o;
+                                    if (live && fabsf(r2s - hh4o) <= 4e-6f * hh4o) {
+                                        // too close to the gate for FP32: the reference's own separately rounded FP64 expression
+                                        const double4 q = P.src_pm[e.x], ot = P.src_pm[P.t0 + (int64_t)g * 32 + owner];
+                                        const double dx = q.x - ot.x, dy = q.y - ot.y, dz = q.z - ot.z;
+                                        const double r2e = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+                                        pass = __dsqrt_rn(r2e) < __dmul_rn(tv.w, 2.0);
+                                        tot_exact++;
+                                    }
+                                    if (pass) {
+                                        const float hs = (float)(tv.w * invR), inv_hs = 1.0f / hs, ipi4 = inv_hs * inv_hs * inv_hs * inv_hs * 0.318309886f;
+                                        float rinv;
+                                        asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rinv) : "f"(r2s));
+                                        const float r = r2s * rinv, qq = r * inv_hs;
+                                        float gs = 0.f;                          // kernel.cpp:28-34
+                                        if (qq < 1.f) gs = -3.f * qq + 2.25f * qq * qq;
+                                        else if (qq < 2.f) { const float u = 2.f - qq; gs = -0.75f * u * u; }
+                                        const float gfac = gs * ipi4 * rinv;
+                                        const float gx = sx * gfac, gy = sy * gfac, gz = sz * gfac;   // grad W * R^4
+                                        const float vx = (float)(tv.x - gv.x), vy = (float)(tv.y - gv.y), vz = (float)(tv.z - gv.z);
+                                        const float vds = vx * sx + vy * sy + vz * sz;                // v_ij . d / R
+                                        const float mu = hs * vds / (r2s + 0.01f * hs * hs);
+                                        const float MUf = vds < 0.f ? (-0.5f * (float)k4.w * mu + mu * mu) : 0.f;   // Node.cpp:142-152
+                                        const double amu = k4.z + (double)MUf, coef = -gv.w * amu * invR4;          // Node.cpp:127 + :154
+                                        fx = coef * (double)gx; fy = coef * (double)gy; fz = coef * (double)gz;
+                                        du = 0.5 * gv.w * amu * invR4 * (double)(vx * gx + vy * gy + vz * gz);      // Node.cpp:167
+                                        if (isnan(fx) || isnan(fy) || isnan(fz)) { fx = 0; fy = 0; fz = 0; }         // Node.cpp:169
+                                        tot_sph++;
+                                    }
+                                    sm.res[lane] = make_double4(fx, fy, fz, pass ? du : __longlong_as_double(0x7ff8000000000001ll));
+                                }
+                                __syncwarp();
+                                // my pairs inside this chunk are the contiguous lanes [a, b)
+                                const int a = max(incl - npair, c0) - c0, b = min(incl, c0 + 32) - c0;
+                                for (int i = a; i < b; i++) {
+                                    const double4 r = sm.res[i];
+                                    if (__double_as_longlong(r.w) != 0x7ff8000000000001ll) { ax += r.x; ay += r.y; az += r.z; dU += r.w; if (COUNT) c_sp++; }
+                                }
+                                __syncwarp();
+                            }
+                        } else
+                        // FP64 mode: every gas lane runs through ITS OWN candidates (a per-lane loop: lanes only diverge in trip count)
+                        while (mine) {
+                            const int j = __ffs(mine) - 1;
+                            mine &= mine - 1;
                             const int2 e = sm.list[base + j];
-                            if (((gate >> j) & 1u) && (((unsigned)e.y >> lane) & 1u)) {
-                                const double4 q = MIXED ? P.src_pm[e.x] : sm.stage[j];
+                            if (!(((unsigned)e.y >> lane) & 1u)) continue;
+                            const double4 gv = sm.gst[j];                    // (mVel | particle velocity, gasMass)
+                            const double4 k4 = sm.tsph[3 * lane], tv = sm.tsph[3 * lane + 1];
+                            const double A2 = k4.z;
+                            {
+                                const double4 q = sm.stage[j];
                                 const double dx = q.x - tp.x, dy = q.y - tp.y, dz = q.z - tp.z;
                                 const double r2 = fma(dz, dz, fma(dy, dy, dx * dx));
                                 bool pass = q.w != 0.0 && r2 != 0.0 && r2 < hh4c;
@@ -529,10 +615,7 @@ __global__ void __launch_bounds__(WALK_TPB, WALK_CTAS) k_walk(const WalkParams P
                                     tot_exact++;
                                 }
                                 if (pass) {
-                                    const double4 gv = P.src_gv[e.x];            // (mVel | particle velocity, gasMass)
-                                    const double4 tv = P.src_gv[t];
-                                    const double4 k4 = sm.tsph[lane];
-                                    const double inv_h = k4.x, inv_pi_h4 = k4.y, A2 = k4.z, cs = k4.w;
+                                    const double inv_h = k4.x, inv_pi_h4 = k4.y, cs = k4.w;
                                     const double rinv = rsqrt_pos(r2), r = r2 * rinv, qq = r * inv_h;
                                     double gs = 0.0;                             // kernel.cpp:28-34
                                     if (qq < 1.0) gs = -3.0 * qq + 2.25 * qq * qq;
