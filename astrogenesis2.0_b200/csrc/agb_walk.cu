@@ -276,6 +276,7 @@ __global__ void __launch_bounds__(WALK_TPB, WALK_CTAS) k_walk(const WalkParams P
         double ax = 0, ay = 0, az = 0, dU = 0;
         int c_vis = (active && (n_nodes > 0 || !valid)) ? 1 : 0, c_an = 0, c_al = 0, c_sp = 0;              // the root call itself
         const unsigned vmask = __ballot_sync(0xffffffffu, valid);
+        const bool wgas = SPH && __any_sync(0xffffffffu, tgas && h_t > 0.0);   // any target of this warp that can feel SPH at all
 
         if (vmask) {
             const double inf = __longlong_as_double(0x7ff0000000000000ll);
@@ -445,7 +446,7 @@ __global__ void __launch_bounds__(WALK_TPB, WALK_CTAS) k_walk(const WalkParams P
                             sf[0] = hx; sf[2] = hy; sf[4] = hz; sf[6] = (float)(q.w * inv_m0);
                             sf[8] = (float)(rx - (double)hx); sf[10] = (float)(ry - (double)hy); sf[12] = (float)(rz - (double)hz);
                         } else sm.stage[lane] = q;
-                        if (SPH) { src_gas = P.src_flag[e.x] != 0; if (src_gas) sm.gst[lane] = P.src_gv[e.x]; }
+                        if (SPH && wgas) { const double4 gvv = P.src_gv[e.x]; src_gas = gvv.w > 0.0; sm.gst[lane] = gvv; }   // independent of the load above
                         // accepted pairs of this entry: lanes in the mask, minus the target's own leaf, none for a massless leaf
                         unsigned m = (unsigned)e.y;
                         const int64_t self_lane = (int64_t)e.x - (P.t0 + (int64_t)g * 32);
@@ -458,7 +459,7 @@ __global__ void __launch_bounds__(WALK_TPB, WALK_CTAS) k_walk(const WalkParams P
                         float* sf = reinterpret_cast<float*>(&sm.stage[lane & ~1]) + (lane & 1);
                         sf[0] = 1.f; sf[2] = 1.f; sf[4] = 1.f; sf[6] = 0.f; sf[8] = 0.f; sf[10] = 0.f; sf[12] = 0.f;
                     }
-                    const unsigned gasmask = SPH ? __ballot_sync(0xffffffffu, src_gas) : 0u;   // tile entries that hold gas
+                    const unsigned gasmask = (SPH && wgas) ? __ballot_sync(0xffffffffu, src_gas) : 0u;   // tile entries that hold gas
                     if (base + 32 + lane < lc) asm volatile("prefetch.global.L1 [%0];" ::"l"(P.src_pm + sm.list[base + 32 + lane].x));
                     __syncwarp();
                     unsigned gate = 0;                                                   // per lane: entries within ~2h (SPH candidates)
@@ -487,7 +488,7 @@ __global__ void __launch_bounds__(WALK_TPB, WALK_CTAS) k_walk(const WalkParams P
                             float2 f = __fmul2_rn(make_float2(r1.z, r1.w), __fmul2_rn(rinv, iq));
                             f.x = bit0 ? f.x : 0.f; f.y = bit1 ? f.y : 0.f;
                             fax = __ffma2_rn(f, dx, fax); fay = __ffma2_rn(f, dy, fay); faz = __ffma2_rn(f, dz, faz);
-                            if (SPH) gate |= ((bit0 && r2.x < hh4cf ? 1u : 0u) << j) | ((bit1 && r2.y < hh4cf ? 2u : 0u) << j);
+                            if (SPH && wgas) gate |= ((bit0 && r2.x < hh4cf ? 1u : 0u) << j) | ((bit1 && r2.y < hh4cf ? 2u : 0u) << j);
                             if (COUNT) {
                                 const bool seen0 = bit0 && r1.z != 0.f, ok0 = seen0 && r2.x != 0.f;
                                 const bool seen1 = bit1 && r1.w != 0.f, ok1 = seen1 && r2.y != 0.f;
@@ -511,7 +512,7 @@ __global__ void __launch_bounds__(WALK_TPB, WALK_CTAS) k_walk(const WalkParams P
                         const double w = rsqrt_pos(fma(r2s * q2, q2, 1e-300));   // 1 / (r (r^2 + e0^2)) in units of R
                         const double f = (bit ? GR3 * q.w : 0.0) * w;
                         ax = fma(f, dx, ax); ay = fma(f, dy, ay); az = fma(f, dz, az);
-                        if (SPH) gate |= (r2 < hh4c ? 1u : 0u) << j;                     // hh4c = 0 for non-gas targets: never set
+                        if (SPH && wgas) gate |= (r2 < hh4c ? 1u : 0u) << j;            // hh4c = 0 for non-gas targets: never set
                         if (COUNT) {
                             const bool seen = bit && q.w != 0.0;
                             const bool ok = seen && r2 != 0.0;
@@ -519,7 +520,7 @@ __global__ void __launch_bounds__(WALK_TPB, WALK_CTAS) k_walk(const WalkParams P
                         }
                     }
                     }
-                    if (SPH) {
+                    if (SPH && wgas && __any_sync(0xffffffffu, (gate & gasmask) != 0u)) {
                         // second pass over the few (target, source) pairs that can pass r < 2 h_i (Node.cpp:316-325, :368-377)
                         unsigned mine = gate & gasmask;
                         if (MIXED) {
