@@ -1,0 +1,351 @@
+// driver/agb_sim.cpp — small C++ driver around the B200 force path (host side of SURVEY.md §8(f)-1).
+//
+// It reproduces the call order and the integrator of the reference's driver so that a user of
+// AstroGenesis2.0 can run the same Config.ini on the GPU path:
+//   * Config.ini: flat `key = value`, '#' comments, unknown key => hard error, same keys as
+//     DataManager::loadConfig (simulation/src/File/DataManager.cpp:1360-1415);
+//   * initial conditions: the reference's `.age` snapshots (DataManager.cpp:216-258 writer, :534-574 reader:
+//     40-byte header + 94 bytes per particle) or this repo's `.agp` test format;
+//   * Simulation::init force evaluation (Physics/Simulation.cpp:101-139) and the KDK main loop of
+//     Simulation::run (:166-345) with Kick / Drift / Ueuler (Physics/TimeIntegration.cpp:10-41), the Hubble
+//     rescale (:330-332) and power-of-two individual time steps (:196-207, :222-232);
+//   * per-phase timings in the reference's processLog.csv format (File/Log.cpp:175-221: `name;seconds`, decimal comma);
+//   * `.age` snapshots every endTime/fixedTimeSteps like DataManager::saveData (first numParticlesOutput particles).
+// Cooling / star formation are no-ops in the reference (calls commented out, Simulation.cpp:312-320) and here.
+// The force path itself is only reached through the C ABI (include/agb200.h); there is no CPU fallback.
+//
+//   agb_sim --config Config.ini [--input-root DIR] [--output-root DIR] [--steps K] [--device D] [--cores C]
+//           [--precision fp64|mixed] [--dump final.agp] [--overwrite]
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <limits>
+#include <map>
+#include <sstream>
+#include <string>
+#include <sys/stat.h>
+#include <vector>
+
+#include "agb200.h"
+
+namespace {
+
+constexpr double GAMMA = 5.0 / 3.0, K_B = 1.38064852e-23, PRTN = 1.6726219e-27;   // Math/Constants.h:15-18
+constexpr double KMS = 1.0e3, MPC = 3.08567758149137e22;                          // Math/Units.h
+
+struct Config {
+    double numberOfParticles = 0, eta = 2, maxTimeStep = 1e13, minTimeStep = 1e13, globalTime = 0, endTime = 1e16, fixedTimeSteps = 1000;
+    double e0 = 1e19, massInH = 1e40, H0 = 70, theta = 0.5, numParticlesOutput = 0;
+    bool starFormation = false, cooling = false;
+    std::string inputPath, inputDataFormat = "age", outputFolderName = "run", outputDataFormat = "age";
+};
+
+std::string trim(const std::string& s)
+{
+    size_t a = s.find_first_not_of(" \t\r\n"), b = s.find_last_not_of(" \t\r\n");
+    return a == std::string::npos ? "" : s.substr(a, b - a + 1);
+}
+
+bool load_config(const std::string& path, Config& c)
+{
+    std::ifstream f(path);
+    if (!f) { fprintf(stderr, "cannot open config %s\n", path.c_str()); return false; }
+    std::string line;
+    while (std::getline(f, line)) {
+        std::string t = trim(line);
+        if (t.empty() || t[0] == '#') continue;
+        size_t eq = t.find('=');
+        if (eq == std::string::npos) continue;                       // e.g. the [Simulation] section header
+        std::string key = trim(t.substr(0, eq)), val = trim(t.substr(eq + 1));
+        auto num = [&](double& d) { d = std::stod(val); };
+        auto flag = [&](bool& b) { if (val == "true" || val == "True") b = true; else if (val == "false" || val == "False") b = false; };
+        try {
+            if (key == "numberOfParticles") num(c.numberOfParticles);
+            else if (key == "eta") num(c.eta);
+            else if (key == "maxTimeStep") num(c.maxTimeStep);
+            else if (key == "minTimeStep") num(c.minTimeStep);
+            else if (key == "globalTime") num(c.globalTime);
+            else if (key == "endTime") num(c.endTime);
+            else if (key == "fixedTimeSteps") num(c.fixedTimeSteps);
+            else if (key == "e0") num(c.e0);
+            else if (key == "massInH") num(c.massInH);
+            else if (key == "starformation") flag(c.starFormation);
+            else if (key == "cooling") flag(c.cooling);
+            else if (key == "H0") num(c.H0);
+            else if (key == "theta") num(c.theta);
+            else if (key == "inputPath") c.inputPath = val;
+            else if (key == "inputDataFormat") c.inputDataFormat = val;
+            else if (key == "outputFolderName") c.outputFolderName = val;
+            else if (key == "outputDataFormat") c.outputDataFormat = val;
+            else if (key == "numParticlesOutput") num(c.numParticlesOutput);
+            else { fprintf(stderr, "unknown key: %s\n", key.c_str()); return false; }
+        } catch (const std::exception&) { fprintf(stderr, "invalid value for %s: %s\n", key.c_str(), val.c_str()); return false; }
+    }
+    if (c.numParticlesOutput > c.numberOfParticles) { fprintf(stderr, "Number of particles to output is greater than the total number of particles.\n"); return false; }
+    return true;
+}
+
+struct Particles {
+    int64_t n = 0;
+    std::vector<double> x, y, z, vx, vy, vz, mass, U, next, mu, rho, P, T, h, dUdt, ax, ay, az, vis, timeStep;
+    std::vector<uint8_t> type, galaxyPart;
+    std::vector<uint32_t> id;
+    void resize(int64_t m)
+    {
+        n = m;
+        for (auto* v : {&x, &y, &z, &vx, &vy, &vz, &mass, &U, &next, &rho, &P, &T, &h, &dUdt, &ax, &ay, &az, &vis, &timeStep}) v->assign((size_t)m, 0.0);
+        mu.assign((size_t)m, 0.58);
+        type.assign((size_t)m, 1); galaxyPart.assign((size_t)m, 1); id.assign((size_t)m, 0);
+    }
+};
+
+#pragma pack(push, 1)
+struct AgeRecord { double pos[3], vel[3], mass, T, P, visualDensity, U; uint8_t type, galaxyPart; uint32_t id; };
+#pragma pack(pop)
+struct AgeHeader { int32_t numParticles[3]; int32_t pad; double deltaTime, endTime, currentTime; };
+static_assert(sizeof(AgeRecord) == 94 && sizeof(AgeHeader) == 40, ".age layout");
+
+bool load_age(const std::string& path, Particles& p)
+{
+    FILE* f = fopen(path.c_str(), "rb");
+    if (!f) { perror(path.c_str()); return false; }
+    AgeHeader h;
+    if (fread(&h, sizeof(h), 1, f) != 1) { fclose(f); return false; }
+    const int64_t n = (int64_t)h.numParticles[0] + h.numParticles[1] + h.numParticles[2];
+    p.resize(n);
+    std::vector<AgeRecord> buf((size_t)n);
+    if (n && fread(buf.data(), sizeof(AgeRecord), (size_t)n, f) != (size_t)n) { fclose(f); fprintf(stderr, "short .age file\n"); return false; }
+    fclose(f);
+    for (int64_t i = 0; i < n; i++) {
+        const AgeRecord& r = buf[(size_t)i];
+        p.x[i] = r.pos[0]; p.y[i] = r.pos[1]; p.z[i] = r.pos[2]; p.vx[i] = r.vel[0]; p.vy[i] = r.vel[1]; p.vz[i] = r.vel[2];
+        p.mass[i] = r.mass; p.T[i] = r.T; p.P[i] = r.P; p.vis[i] = r.visualDensity; p.U[i] = r.U; p.type[i] = r.type; p.galaxyPart[i] = r.galaxyPart; p.id[i] = r.id;
+    }
+    return true;
+}
+
+bool save_age(const std::string& path, const Particles& p, int64_t count, double deltaTime, double endTime, double currentTime)
+{
+    FILE* f = fopen(path.c_str(), "wb");
+    if (!f) { perror(path.c_str()); return false; }
+    AgeHeader h{};
+    for (int64_t i = 0; i < count; i++) if (p.type[i] >= 1 && p.type[i] <= 3) h.numParticles[p.type[i] - 1]++;
+    h.deltaTime = deltaTime; h.endTime = endTime; h.currentTime = currentTime;
+    fwrite(&h, sizeof(h), 1, f);
+    std::vector<AgeRecord> buf((size_t)count);
+    for (int64_t i = 0; i < count; i++) {
+        AgeRecord& r = buf[(size_t)i];
+        r.pos[0] = p.x[i]; r.pos[1] = p.y[i]; r.pos[2] = p.z[i]; r.vel[0] = p.vx[i]; r.vel[1] = p.vy[i]; r.vel[2] = p.vz[i];
+        r.mass = p.mass[i]; r.T = p.T[i]; r.P = p.P[i]; r.visualDensity = p.vis[i]; r.U = p.U[i]; r.type = p.type[i]; r.galaxyPart = p.galaxyPart[i]; r.id = p.id[i];
+    }
+    fwrite(buf.data(), sizeof(AgeRecord), (size_t)count, f);
+    fclose(f);
+    return true;
+}
+
+// this repo's test format (oracle/agio.py): "AGPART01", int64 N, 13 double columns, uint8 type
+const char* AGP_COLS[13] = {"x", "y", "z", "vx", "vy", "vz", "mass", "U", "next_time", "rho", "P", "T", "mu"};
+std::vector<double>* agp_col(Particles& p, int k)
+{
+    std::vector<double>* c[13] = {&p.x, &p.y, &p.z, &p.vx, &p.vy, &p.vz, &p.mass, &p.U, &p.next, &p.rho, &p.P, &p.T, &p.mu};
+    return c[k];
+}
+bool load_agp(const std::string& path, Particles& p)
+{
+    FILE* f = fopen(path.c_str(), "rb");
+    if (!f) { perror(path.c_str()); return false; }
+    char magic[8]; int64_t n = 0;
+    if (fread(magic, 1, 8, f) != 8 || memcmp(magic, "AGPART01", 8) || fread(&n, 8, 1, f) != 1) { fclose(f); return false; }
+    p.resize(n);
+    for (int k = 0; k < 13; k++) if (n && fread(agp_col(p, k)->data(), 8, (size_t)n, f) != (size_t)n) { fclose(f); return false; }
+    if (n && fread(p.type.data(), 1, (size_t)n, f) != (size_t)n) { fclose(f); return false; }
+    fclose(f);
+    for (int64_t i = 0; i < n; i++) p.id[i] = (uint32_t)i;
+    return true;
+}
+bool save_agp(const std::string& path, Particles& p)
+{
+    FILE* f = fopen(path.c_str(), "wb");
+    if (!f) { perror(path.c_str()); return false; }
+    fwrite("AGPART01", 1, 8, f); fwrite(&p.n, 8, 1, f);
+    for (int k = 0; k < 13; k++) fwrite(agp_col(p, k)->data(), 8, (size_t)p.n, f);
+    fwrite(p.type.data(), 1, (size_t)p.n, f);
+    fclose(f);
+    // companion file with the fields .agp does not carry
+    FILE* g = fopen((path + ".acc").c_str(), "wb");
+    if (!g) return false;
+    for (auto* v : {&p.ax, &p.ay, &p.az, &p.dUdt, &p.h, &p.vis, &p.next, &p.timeStep}) fwrite(v->data(), 8, (size_t)p.n, g);
+    fclose(g);
+    return true;
+}
+
+struct PhaseLog {                                            // File/Log.cpp:175-221
+    std::string path; std::string current; std::chrono::steady_clock::time_point t0;
+    void start(const std::string& name) { end(); current = name; t0 = std::chrono::steady_clock::now(); }
+    void end()
+    {
+        if (current.empty() || path.empty()) { current.clear(); return; }
+        double s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        std::ostringstream os; os << s;
+        std::string num = os.str();
+        std::replace(num.begin(), num.end(), '.', ',');
+        std::ofstream f(path, std::ios::app);
+        f << current << ";" << num << "\n";
+        current.clear();
+    }
+};
+
+void check(agb_ctx* c, int rc, const char* what)
+{
+    if (rc != AGB_OK) { fprintf(stderr, "agb200: %s failed: %s (%s)\n", what, agb_strerror(rc), agb_last_error(c)); exit(3); }
+}
+
+struct Driver {
+    Config cfg; Particles p; agb_ctx* ctx = nullptr; PhaseLog log;
+    double globalTime = 0, visualDensityRadius = 0;
+
+    void force_path(bool first)
+    {
+        agb_particles in{};
+        in.n = p.n; in.x = p.x.data(); in.y = p.y.data(); in.z = p.z.data(); in.vx = p.vx.data(); in.vy = p.vy.data(); in.vz = p.vz.data();
+        in.mass = p.mass.data(); in.U = p.U.data(); in.next_time = p.next.data(); in.mu = p.mu.data(); in.type = p.type.data();
+        in.rho = p.rho.data(); in.P = p.P.data(); in.T = p.T.data(); in.h = p.h.data(); in.dUdt = p.dUdt.data();
+        in.ax = p.ax.data(); in.ay = p.ay.data(); in.az = p.az.data();
+        log.start("build tree");
+        check(ctx, agb_set_particles(ctx, &in, AGB_MEM_HOST), "set_particles");
+        double R = 0;
+        check(ctx, agb_build_tree(ctx, &R), "build_tree");
+        if (first) visualDensityRadius = R / 100000;                    // Simulation.cpp:126
+        log.start("Visual Density");
+        check(ctx, agb_visual_density(ctx, visualDensityRadius), "visual_density");
+        log.start("SPH density and update");
+        check(ctx, agb_gas_density(ctx, cfg.massInH), "gas_density");
+        log.start("Force Calculation");
+        check(ctx, agb_forces(ctx, globalTime, cfg.e0, cfg.theta), "forces");
+        agb_results out{p.ax.data(), p.ay.data(), p.az.data(), p.dUdt.data(), p.h.data(), p.rho.data(), p.P.data(), p.T.data(), p.vis.data()};
+        check(ctx, agb_get_results(ctx, &out, AGB_MEM_HOST), "get_results");
+        log.end();
+    }
+
+    void assign_timestep(int64_t i)
+    {                                                                   // Simulation.cpp:196-207 / :222-232
+        double a = std::sqrt(p.ax[i] * p.ax[i] + p.ay[i] * p.ay[i] + p.az[i] * p.az[i]);
+        if (a > 0) {
+            double ts = cfg.eta * std::sqrt(cfg.e0 / a);
+            ts = std::clamp(ts, cfg.minTimeStep, cfg.maxTimeStep);
+            p.timeStep[i] = std::max(std::pow(2, std::floor(std::log2(ts))), cfg.minTimeStep);
+        } else p.timeStep[i] = cfg.minTimeStep;
+        p.next[i] = globalTime + p.timeStep[i];
+    }
+    void kick(int64_t i, double dt)
+    {                                                                   // TimeIntegration.cpp:10-19
+        if (std::isnan(p.ax[i]) || std::isnan(p.ay[i]) || std::isnan(p.az[i])) return;
+        p.vx[i] = p.vx[i] + p.ax[i] * dt / 2; p.vy[i] = p.vy[i] + p.ay[i] * dt / 2; p.vz[i] = p.vz[i] + p.az[i] * dt / 2;
+    }
+
+    int run(int64_t max_steps, const std::string& outdir)
+    {
+        const int64_t n = p.n;
+        const double fixedStep = cfg.endTime / cfg.fixedTimeSteps;
+        for (int64_t i = 0; i < n; i++) if (p.type[i] == 2) p.T[i] = (GAMMA - 1.0) * p.U[i] * PRTN * p.mu[i] / K_B;   // Simulation.cpp:108-112
+        globalTime = 0.0;
+        for (int64_t i = 0; i < n; i++) p.next[i] = 0.0;              // Particle::nextIntegrationTime defaults to 0 (Particle.h:29)
+        force_path(true);                                                // Simulation.cpp:120-139
+        if (!outdir.empty()) save_age(outdir + "/0.age", p, (int64_t)cfg.numParticlesOutput, fixedStep, cfg.endTime, 0.0);
+        double nextSaveTime = fixedStep;
+        for (int64_t i = 0; i < n; i++) p.next[i] = 0.0;
+#pragma omp parallel for
+        for (int64_t i = 0; i < n; i++) assign_timestep(i);
+        const double H0SI = (cfg.H0 * KMS) / MPC;
+        int64_t step = 0;
+        while (globalTime < cfg.endTime && (max_steps < 0 || step < max_steps)) {
+#pragma omp parallel for
+            for (int64_t i = 0; i < n; i++) if (globalTime >= p.next[i]) assign_timestep(i);
+            double mn = std::numeric_limits<double>::max();
+#pragma omp parallel for reduction(min : mn)
+            for (int64_t i = 0; i < n; i++) if (p.next[i] < mn) mn = p.next[i];
+            globalTime = mn;
+            log.start("first kick");
+#pragma omp parallel for
+            for (int64_t i = 0; i < n; i++)
+                if (globalTime == p.next[i]) {
+                    const double dt = p.timeStep[i];
+                    kick(i, dt);
+                    p.x[i] = p.x[i] + p.vx[i] * dt; p.y[i] = p.y[i] + p.vy[i] * dt; p.z[i] = p.z[i] + p.vz[i] * dt;   // Drift
+                }
+            force_path(false);                                           // Simulation.cpp:275-285
+            log.start("second kick");
+#pragma omp parallel for
+            for (int64_t i = 0; i < n; i++)
+                if (globalTime == p.next[i]) {
+                    const double dt = p.timeStep[i];
+                    if (p.type[i] == 2) {                                // Ueuler, TimeIntegration.cpp:28-41
+                        if (!std::isnan(p.dUdt[i])) p.U[i] += p.dUdt[i] * dt;
+                        p.dUdt[i] = 0;
+                    }
+                    const double scale = std::exp(H0SI * dt);            // Simulation.cpp:330-332
+                    p.x[i] *= scale; p.y[i] *= scale; p.z[i] *= scale;
+                    kick(i, dt);
+                    p.next[i] += dt;
+                }
+            log.end();
+            step++;
+            if (!outdir.empty() && globalTime >= nextSaveTime) {
+                log.start("Save data");
+                save_age(outdir + "/" + std::to_string((int)(nextSaveTime / fixedStep)) + ".age", p, (int64_t)cfg.numParticlesOutput, fixedStep, cfg.endTime, globalTime);
+                log.end();
+                nextSaveTime += fixedStep;
+            }
+        }
+        printf("steps %lld globalTime %.17g\n", (long long)step, globalTime);
+        return 0;
+    }
+};
+
+} // namespace
+
+int main(int argc, char** argv)
+{
+    std::map<std::string, std::string> opt;
+    bool overwrite = false;
+    for (int i = 1; i < argc; i++) {
+        std::string a = argv[i];
+        if (a == "--overwrite") { overwrite = true; continue; }
+        if (a.rfind("--", 0) == 0 && i + 1 < argc) { opt[a.substr(2)] = argv[++i]; continue; }
+        fprintf(stderr, "usage: agb_sim --config Config.ini [--input-root DIR] [--output-root DIR] [--steps K] [--device D] [--cores C] [--precision fp64|mixed] [--dump final.agp] [--overwrite]\n");
+        return 2;
+    }
+    Driver d;
+    if (!load_config(opt.count("config") ? opt["config"] : "../Config.ini", d.cfg)) return 2;
+    const std::string inroot = opt.count("input-root") ? opt["input-root"] : "../../input_data/";
+    const std::string inpath = inroot + (inroot.empty() || inroot.back() == '/' ? "" : "/") + d.cfg.inputPath;
+    bool ok = d.cfg.inputDataFormat == "age" ? load_age(inpath, d.p) : d.cfg.inputDataFormat == "agp" ? load_agp(inpath, d.p) : false;
+    if (!ok) { fprintf(stderr, "cannot read initial conditions %s (format %s; supported: age, agp)\n", inpath.c_str(), d.cfg.inputDataFormat.c_str()); return 2; }
+    if ((int64_t)d.cfg.numberOfParticles != d.p.n) {                     // Simulation.cpp:92-98
+        fprintf(stderr, "Error: Number of particles in the ConfigFile (%lld) does not match the data file (%lld).\n", (long long)d.cfg.numberOfParticles, (long long)d.p.n);
+        return 2;
+    }
+    std::string outdir;
+    if (opt.count("output-root")) {
+        outdir = opt["output-root"] + "/" + d.cfg.outputFolderName;
+        struct stat st;
+        if (stat(outdir.c_str(), &st) == 0 && !overwrite) { fprintf(stderr, "output folder %s exists (use --overwrite)\n", outdir.c_str()); return 2; }
+        std::string cmd = "mkdir -p '" + outdir + "/logs'";
+        if (system(cmd.c_str()) != 0) return 2;
+        d.log.path = outdir + "/logs/processLog.csv";
+        std::ofstream(d.log.path, std::ios::trunc);
+    }
+    const int cores = opt.count("cores") ? atoi(opt["cores"].c_str()) : 8;
+    int rc = agb_create(&d.ctx, opt.count("device") ? atoi(opt["device"].c_str()) : 0, cores);
+    if (rc != AGB_OK) { fprintf(stderr, "agb200: %s\n", agb_strerror(rc)); return 3; }
+    if (opt.count("precision")) agb_set_option(d.ctx, AGB_OPT_PRECISION, opt["precision"] == "fp64" ? 0 : 1);
+    rc = d.run(opt.count("steps") ? atoll(opt["steps"].c_str()) : -1, outdir);
+    if (opt.count("dump")) save_agp(opt["dump"], d.p);
+    agb_destroy(d.ctx);
+    return rc;
+}

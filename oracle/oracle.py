@@ -74,11 +74,7 @@ def run(p, theta, e0, massInH, globalTime=0.0, cores=8, visual_radius=None, node
     typ = np.ascontiguousarray(p["type"], dtype=np.uint8)
     o = {k: f8(k).copy() for k in ("rho", "P", "T")}
     for k in ("ax", "ay", "az", "dUdt", "h", "vis"):
-        o[k] = np.zeros(n)
-    if "dUdt" in p:
-        o["dUdt"] = f8("dUdt").copy()
-    if "h" in p:
-        o["h"] = f8("h").copy()
+        o[k] = f8(k).copy() if k in p else np.zeros(n)       # carried state: acc of inactive particles, accumulated dUdt, h
     o["leafdepth"] = np.zeros(n, dtype=np.int32)
     o["key_hi"] = np.zeros(n, dtype=np.uint64)
     o["key_lo"] = np.zeros(n, dtype=np.uint64)
@@ -127,6 +123,23 @@ def run(p, theta, e0, massInH, globalTime=0.0, cores=8, visual_radius=None, node
 
 def have_ref():
     return os.access(REF_BIN, os.X_OK)
+
+
+def run_ref_steps(p, theta, e0, massInH, cores, eta, min_ts, max_ts, H0, nsteps):
+    """initial forces + nsteps iterations of the reference's main loop on oracle/_ref/ag_ref (its own integrator + Tree)."""
+    from . import agio
+    with tempfile.TemporaryDirectory() as d:
+        agio.write_agp(os.path.join(d, "in.agp"), p)
+        out = os.path.join(d, "out.agp")
+        subprocess.check_call([REF_BIN, "steps", os.path.join(d, "in.agp"), out] + [repr(float(v)) for v in (theta, e0, massInH)] + [str(int(cores))] +
+                              [repr(float(v)) for v in (eta, min_ts, max_ts, H0)] + [str(int(nsteps))], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        q = agio.read_agp(out)
+        n = len(q["x"])
+        raw = np.fromfile(out + ".acc", dtype="<f8")
+        for i, k in enumerate(("ax", "ay", "az", "dUdt", "h", "vis", "next_time2", "timeStep")):
+            q[k] = raw[i * n:(i + 1) * n].copy()
+        q["globalTime"] = float(raw[8 * n])
+    return q
 
 
 def run_ref(p, theta, e0, massInH, globalTime=0.0, cores=8, nodes=True):

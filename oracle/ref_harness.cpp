@@ -13,6 +13,10 @@
 //   ag_ref run     <in.agp> <out.ago> <theta> <e0> <massInH> <globalTime> <cores> [nodes=1]
 //   ag_ref convert <format> <path-below-input_data> <out.agp>      (uses DataManager::loadICs)
 //   ag_ref time    <in.agp> <theta> <e0> <massInH> <globalTime> <reps>   (phase timings, JSON)
+//   ag_ref steps   <in.agp> <out.agp> <theta> <e0> <massInH> <cores> <eta> <minTimeStep> <maxTimeStep> <H0> <nsteps>
+//                  initial force evaluation + nsteps iterations of the reference's main loop (Simulation.cpp:166-345) with the
+//                  reference's own TimeIntegration and Tree; writes the final particle state (the loop itself is restated here
+//                  because Simulation::run is welded to Config.ini, the console and snapshot output)
 //
 // File formats (little endian), shared with oracle/agio.py:
 //   .agp  "AGPART01", int64 N, double[N] x y z vx vy vz mass U next_time rho P T mu, uint8[N] type
@@ -35,6 +39,11 @@
 #include "Tree.h"
 #include "Node.h"
 #include "DataManager.h"
+#include "TimeIntegration.h"
+#include "Units.h"
+#include <algorithm>
+#include <cmath>
+#include <limits>
 
 extern "C" { int ag_stub_cores = 1; }
 
@@ -261,6 +270,75 @@ int cmd_time(int argc, char** argv)
     return 0;
 }
 
+
+// Restatement of the control flow of Simulation::init (force part) + Simulation::run for `nsteps` loop iterations,
+// calling the reference's own Tree and TimeIntegration.  Output .agp carries acc in (rho,P,T unchanged) plus a second
+// file <out>.acc with ax ay az dUdt h visualDensity next_time timeStep globalTime.
+int cmd_steps(int argc, char** argv)
+{
+    if (argc < 13) { fprintf(stderr, "usage: steps in out theta e0 massInH cores eta minTS maxTS H0 nsteps\n"); return 2; }
+    Simulation sim;
+    if (!load_agp(argv[2], sim.particles)) return 2;
+    const int n = sim.numberOfParticles = (int)sim.particles.size();
+    sim.theta = atof(argv[4]); sim.e0 = atof(argv[5]); sim.massInH = atof(argv[6]);
+    ag_stub_cores = atoi(argv[7]);
+    sim.eta = atof(argv[8]); sim.minTimeStep = atof(argv[9]); sim.maxTimeStep = atof(argv[10]); sim.H0 = atof(argv[11]);
+    const int nsteps = atoi(argv[12]);
+    TimeIntegration ti;
+    std::vector<Particle*>& ps = sim.particles;
+    sim.globalTime = 0.0;
+    for (int i = 0; i < n; i++)                                       // Simulation.cpp:101-113
+        if (ps[i]->type == 2) ps[i]->T = (Constants::GAMMA - 1.0) * ps[i]->U * Constants::prtn * ps[i]->mu / (Constants::k_b);
+    {   // Simulation.cpp:120-139
+        Tree t(&sim); t.buildTree(); sim.visualDensityRadius = t.root->radius / 100000;
+        t.calcVisualDensity(); t.calcGasDensity(); t.calculateForces();
+    }
+    auto assign = [&](Particle* p) {                                  // Simulation.cpp:196-207 / :222-232
+        double accelMag = p->acc.length();
+        if (accelMag > 0) {
+            double timeStep = sim.eta * std::sqrt(sim.e0 / accelMag);
+            p->timeStep = std::clamp(timeStep, sim.minTimeStep, sim.maxTimeStep);
+            p->timeStep = std::max(std::pow(2, std::floor(std::log2(p->timeStep))), sim.minTimeStep);
+            p->nextIntegrationTime = sim.globalTime + p->timeStep;
+        } else { p->timeStep = sim.minTimeStep; p->nextIntegrationTime = sim.globalTime + p->timeStep; }
+    };
+    for (int i = 0; i < n; i++) ps[i]->nextIntegrationTime = 0.0;
+    for (int i = 0; i < n; i++) assign(ps[i]);
+    for (int step = 0; step < nsteps; step++) {
+        for (int i = 0; i < n; i++) if (sim.globalTime >= ps[i]->nextIntegrationTime) assign(ps[i]);
+        double mn = std::numeric_limits<double>::max();
+        for (int i = 0; i < n; i++) if (ps[i]->nextIntegrationTime < mn) mn = ps[i]->nextIntegrationTime;
+        sim.globalTime = mn;
+        for (int i = 0; i < n; i++) if (sim.globalTime == ps[i]->nextIntegrationTime) { ti.Kick(ps[i], ps[i]->timeStep); ti.Drift(ps[i], ps[i]->timeStep); }
+        Tree* t = new Tree(&sim);
+        t->buildTree(); t->calcVisualDensity(); t->calcGasDensity(); t->calculateForces();
+        for (int i = 0; i < n; i++) {
+            Particle* p = ps[i];
+            if (sim.globalTime == p->nextIntegrationTime) {
+                if (p->type == 2) ti.Ueuler(p, p->timeStep);
+                double H0SI = (sim.H0 * Units::KMS) / Units::MPC;
+                double scale_factor = exp(H0SI * p->timeStep);
+                p->position *= scale_factor;
+                ti.Kick(p, p->timeStep);
+                p->nextIntegrationTime += p->timeStep;
+            }
+        }
+        delete t;
+    }
+    if (!save_agp(argv[3], ps)) return 2;
+    std::string extra = std::string(argv[3]) + ".acc";
+    FILE* f = fopen(extra.c_str(), "wb");
+    if (!f) return 2;
+    std::vector<double> v((size_t)n);
+    auto col = [&](auto get) { for (int i = 0; i < n; i++) v[(size_t)i] = get(ps[(size_t)i]); wr(f, v); };
+    col([](Particle* p) { return p->acc.x; }); col([](Particle* p) { return p->acc.y; }); col([](Particle* p) { return p->acc.z; });
+    col([](Particle* p) { return p->dUdt; }); col([](Particle* p) { return p->h; }); col([](Particle* p) { return p->visualDensity; });
+    col([](Particle* p) { return p->nextIntegrationTime; }); col([](Particle* p) { return p->timeStep; });
+    fwrite(&sim.globalTime, 8, 1, f);
+    fclose(f);
+    return 0;
+}
+
 } // namespace
 
 int main(int argc, char** argv)
@@ -270,6 +348,7 @@ int main(int argc, char** argv)
     if (cmd == "run") return cmd_run(argc, argv);
     if (cmd == "convert") return cmd_convert(argc, argv);
     if (cmd == "time") return cmd_time(argc, argv);
+    if (cmd == "steps") return cmd_steps(argc, argv);
     fprintf(stderr, "unknown command %s\n", argv[1]);
     return 2;
 }

@@ -1,0 +1,105 @@
+"""The C++ driver (driver/agb_sim.cpp): Config.ini handling on CPU, and on the GPU a multi-step KDK run compared with
+the numpy restatement of the reference's loop (oracle/integrator.py, itself bit-identical to the reference) driven by
+the CPU oracle's forces."""
+import os
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BIN = os.path.join(ROOT, "driver", "agb_sim")
+
+CONFIG = """[Simulation]
+    #comment line
+    numberOfParticles = {n}
+    eta = {eta}
+    maxTimeStep = {max_ts}
+    minTimeStep = {min_ts}
+    globalTime = 0.0
+    endTime = 1e16
+    fixedTimeSteps = 1000
+    e0 = {e0}
+    massInH = {mh}
+    starformation = false
+    cooling = false
+    H0 = 70
+    theta = 0.5
+    inputPath = ic.agp
+    inputDataFormat = agp
+    outputFolderName = run
+    outputDataFormat = age
+    numParticlesOutput = {n}
+"""
+
+
+def ensure_bin():
+    if not os.access(BIN, os.X_OK):
+        sys.path.insert(0, ROOT)
+        import __graft_entry__ as ge
+        ge.build()
+    return BIN
+
+
+def test_config_errors_cpu():
+    b = ensure_bin()
+    with tempfile.TemporaryDirectory() as d:
+        cfg = os.path.join(d, "Config.ini")
+        open(cfg, "w").write("numberOfParticles = 10\nbogusKey = 1\n")
+        r = subprocess.run([b, "--config", cfg], capture_output=True, text=True)
+        assert r.returncode == 2 and "unknown key" in r.stderr                       # DataManager.cpp:1403-1406
+        open(cfg, "w").write("numberOfParticles = 10\nnumParticlesOutput = 20\n")
+        r = subprocess.run([b, "--config", cfg], capture_output=True, text=True)
+        assert r.returncode == 2 and "greater than" in r.stderr                      # DataManager.cpp:1417-1421
+
+
+def test_integrator_restatement_matches_reference(oracle, pkg):
+    """CPU: oracle/integrator.py + C oracle forces == the reference's own loop, bit for bit, with several time-step bins."""
+    if not oracle.have_ref():
+        pytest.skip("oracle/_ref not built here")
+    from oracle import integrator
+    p = pkg.ics.plummer(1500, seed=42, gas_fraction=0.3)
+    mh = pkg.ics.gas_mass_in_h(p, 16)
+    a = integrator.run_steps(p, integrator.oracle_forces(0.5, 1e18, mh, 2), e0=1e18, eta=0.02, min_ts=1e10, max_ts=1e13, H0=70.0, nsteps=5)
+    b = oracle.run_ref_steps(p, 0.5, 1e18, mh, 2, 0.02, 1e10, 1e13, 70.0, 5)
+    assert len(np.unique(a["timeStep"])) > 2 and a["globalTime"] == b["globalTime"]
+    for k in ("x", "y", "z", "vx", "vy", "vz", "U", "rho", "P", "T", "ax", "ay", "az", "dUdt", "h", "vis", "timeStep"):
+        assert np.array_equal(a[k], b[k]), k
+    assert np.array_equal(a["next_time"], b["next_time2"])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("precision", ["fp64", "mixed"])
+def test_driver_multi_step_gpu(oracle, pkg, precision):
+    b = ensure_bin()
+    from oracle import agio, integrator
+    p = pkg.ics.plummer(3000, seed=42, gas_fraction=0.3)
+    mh = pkg.ics.gas_mass_in_h(p, 16)
+    par = dict(n=3000, eta=0.02, max_ts=1e13, min_ts=1e10, e0=1e18, mh=repr(mh))
+    nsteps = 6
+    want = integrator.run_steps(p, integrator.oracle_forces(0.5, 1e18, mh, 8), e0=1e18, eta=0.02, min_ts=1e10, max_ts=1e13, H0=70.0, nsteps=nsteps)
+    with tempfile.TemporaryDirectory() as d:
+        agio.write_agp(os.path.join(d, "ic.agp"), p)
+        open(os.path.join(d, "Config.ini"), "w").write(CONFIG.format(**par))
+        out = os.path.join(d, "final.agp")
+        r = subprocess.run([b, "--config", os.path.join(d, "Config.ini"), "--input-root", d, "--output-root", d, "--steps", str(nsteps), "--cores", "8",
+                            "--precision", precision, "--dump", out], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        got = agio.read_agp(out)
+        raw = np.fromfile(out + ".acc", dtype="<f8").reshape(8, -1)
+        log = open(os.path.join(d, "run", "logs", "processLog.csv")).read()
+        snap0 = os.path.getsize(os.path.join(d, "run", "0.age"))
+    assert snap0 == 40 + 94 * 3000                                                    # DataManager.cpp:216-258
+    assert "build tree;" in log and "Force Calculation;" in log and "second kick;" in log and "," in log.split(";")[1]
+    assert ("globalTime %.17g" % want["globalTime"]) in r.stdout
+    tol = 1e-11 if precision == "fp64" else 2e-6
+    assert np.array_equal(raw[7], want["timeStep"]) or precision == "mixed"          # identical time-step bins
+    for k in ("x", "y", "z"):
+        assert np.allclose(got[k], want[k], rtol=1e-9 if precision == "mixed" else 1e-13, atol=0), k
+    dv = np.sqrt(sum((got[k] - want[k]) ** 2 for k in ("vx", "vy", "vz"))) / np.sqrt(sum((want[k] - p[k]) ** 2 for k in ("vx", "vy", "vz")))
+    assert np.median(dv) <= tol and np.percentile(dv, 99) <= 100 * tol, (np.median(dv), np.percentile(dv, 99))
+    gas = p["type"] == 2
+    assert np.array_equal(raw[4][gas], want["h"][gas])                                # density groups identical after 6 steps
+    assert np.allclose(got["U"][gas], want["U"][gas], rtol=1e-6 if precision == "mixed" else 1e-12, atol=0)
