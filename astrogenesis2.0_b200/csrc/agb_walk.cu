@@ -678,9 +678,15 @@ __global__ void k_walk_reset(AgbScalars* s)
 
 __global__ void k_count_active(const double* __restrict__ s_next, int64_t t0, int64_t t1, double gt, AgbScalars* s)
 {
-    int64_t i = t0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    unsigned m = __ballot_sync(0xffffffffu, i < t1 && s_next[i] == gt);
-    if ((threadIdx.x & 31) == 0 && m) atomicAdd(&s->n_active, __popc(m));
+    __shared__ int cnt;
+    if (threadIdx.x == 0) cnt = 0;
+    __syncthreads();
+    int local = 0;
+    for (int64_t i = t0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < t1; i += (int64_t)gridDim.x * blockDim.x) local += s_next[i] == gt;
+    local = __reduce_add_sync(0xffffffffu, local);
+    if ((threadIdx.x & 31) == 0 && local) atomicAdd(&cnt, local);
+    __syncthreads();
+    if (threadIdx.x == 0 && cnt) atomicAdd(&s->n_active, cnt);
 }
 
 __global__ void k_unpermute_i32(const uint32_t* __restrict__ perm, int64_t n, const int32_t* a, const int32_t* b, const int32_t* c, const int32_t* d_,
@@ -747,7 +753,7 @@ int agb_launch_walk(AgbDev& d, AgbScalars* s, double globalTime, double e0, doub
     k_walk_reset<<<1, 1, 0, st>>>(s); launches++;
     if (t1 > t0) {
         cudaMemsetAsync(&s->n_active, 0, sizeof(int32_t), st);
-        k_count_active<<<(int)((t1 - t0 + 255) / 256), 256, 0, st>>>(d.s_next, t0, t1, globalTime, s); launches++;
+        k_count_active<<<(int)std::min<int64_t>((t1 - t0 + 255) / 256, 4 * sm_count), 256, 0, st>>>(d.s_next, t0, t1, globalTime, s); launches++;
         int blocks = (int)std::min<int64_t>((int64_t)agb_walk_blocks(sm_count), ((int64_t)P.ngroups + WALK_WARPS - 1) / WALK_WARPS);
         if (blocks * WALK_WARPS > d.spill_warps) blocks = d.spill_warps / WALK_WARPS;
         if (ev0) cudaEventRecord(ev0, st);
