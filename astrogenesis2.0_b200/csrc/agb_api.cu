@@ -62,7 +62,7 @@ void free_pool(agb_ctx* c)
     dfree(d.lcp); dfree(d.nodebase); dfree(d.nodecnt); dfree(d.leafparent); dfree(d.group); dfree(d.leafdepth);
     dfree(d.child); dfree(d.nfirst); dfree(d.nlast); dfree(d.nparent); dfree(d.arrived); dfree(d.ndepth);
     dfree(d.nmark); dfree(d.ndup); dfree(d.leafmark); dfree(d.mom_pm); dfree(d.mom_gv); dfree(d.grouplist); dfree(d.gasrank);
-    dfree(d.dist); dfree(d.blockhist); dfree(d.scanblk);
+    dfree(d.rec); dfree(d.blockhist); dfree(d.scanblk);
     dfree(d.far_list); dfree(d.far_front); dfree(d.far_cnt);
     dfree(d.c_visits); dfree(d.c_accn); dfree(d.c_accl); dfree(d.c_sph);
     d.cap = 0;
@@ -84,7 +84,7 @@ int ensure_pool(agb_ctx* c, int64_t n)
     CK(dalloc(d.lcp, cap)); CK(dalloc(d.nodebase, cap)); CK(dalloc(d.nodecnt, cap)); CK(dalloc(d.leafparent, cap)); CK(dalloc(d.group, cap)); CK(dalloc(d.leafdepth, cap));
     CK(dalloc(d.child, 8 * cap)); CK(dalloc(d.nfirst, cap)); CK(dalloc(d.nlast, cap)); CK(dalloc(d.nparent, cap)); CK(dalloc(d.arrived, cap)); CK(dalloc(d.ndepth, cap));
     CK(dalloc(d.nmark, cap)); CK(dalloc(d.ndup, cap)); CK(dalloc(d.leafmark, cap)); CK(dalloc(d.mom_pm, cap)); CK(dalloc(d.mom_gv, cap)); CK(dalloc(d.grouplist, cap)); CK(dalloc(d.gasrank, cap + 1));
-    CK(dalloc(d.dist, cap));
+    CK(dalloc(d.rec, cap));
     {
         int lcap, fcap, tg; agb_far_capacity(&lcap, &fcap, &tg);
         const size_t nsg = cap / (size_t)tg + 2;
@@ -221,11 +221,11 @@ int agb_set_particles(agb_ctx* c, const agb_particles* p, int memspace)
         d.type = p->type;
         c->bound = true;
     } else {
+        CK(cudaMemcpyAsync(c->in_type, p->type, (size_t)n, cudaMemcpyHostToDevice, c->st));   // needed by the key pass
         if ((rc = own_input(c, d.x, 0, p->x, n)) || (rc = own_input(c, d.y, 1, p->y, n)) || (rc = own_input(c, d.z, 2, p->z, n)) ||
             (rc = own_input(c, d.vx, 3, p->vx, n)) || (rc = own_input(c, d.vy, 4, p->vy, n)) || (rc = own_input(c, d.vz, 5, p->vz, n)) ||
             (rc = own_input(c, d.mass, 6, p->mass, n)) || (rc = own_input(c, d.U, 7, p->U, n)) || (rc = own_input(c, d.next, 8, p->next_time, n)) ||
             (rc = own_input(c, d.mu, 9, p->mu, n))) return rc;
-        CK(cudaMemcpyAsync(c->in_type, p->type, (size_t)n, cudaMemcpyHostToDevice, c->st_copy));
         d.type = c->in_type;
         c->bound = false;
     }

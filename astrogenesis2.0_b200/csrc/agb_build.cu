@@ -43,7 +43,7 @@ __device__ __forceinline__ double warp_max(double v)
 
 // ------------------------------------------------------------------ root extent
 __global__ void __launch_bounds__(TPB) k_dist_partial(const double* __restrict__ x, const double* __restrict__ y, const double* __restrict__ z,
-                                                        int64_t n, double* __restrict__ dist, AgbScalars* s)
+                                                        int64_t n, double4* __restrict__ rec, AgbScalars* s)
 {
     __shared__ double sh[2][TPB / 32];
     double a = 0.0, b = 0.0;
@@ -51,7 +51,7 @@ __global__ void __launch_bounds__(TPB) k_dist_partial(const double* __restrict__
         double px = x[i], py = y[i], pz = z[i];
         // vec3::length (Math/vec3.cpp:76-78): sqrt(x*x + y*y + z*z), separately rounded
         double d = __dsqrt_rn(__dadd_rn(__dadd_rn(__dmul_rn(px, px), __dmul_rn(py, py)), __dmul_rn(pz, pz)));
-        dist[i] = d;
+        rec[i] = make_double4(px, py, pz, d);          // packed once, coalesced: later random accesses touch one 32-byte sector
         a += d;
         b += __dmul_rn(d, d);
     }
@@ -82,13 +82,13 @@ __global__ void k_extent_finish(AgbScalars* s, int nblocks, int64_t n)
     s->n_long_runs = 0; s->any_gas = 0; s->n_outliers = 0; s->dup_keys = 0; s->edge_dropped = 0; s->max_depth = 0; s->n_nodes = 0;
 }
 
-__global__ void __launch_bounds__(TPB) k_extent_max(const double* __restrict__ dist, int64_t n, AgbScalars* s)
+__global__ void __launch_bounds__(TPB) k_extent_max(const double4* __restrict__ rec, int64_t n, AgbScalars* s)
 {
     __shared__ double sh[TPB / 32];
     const double lim = s->limit;
     double m = 0.0;
     for (int64_t i = (int64_t)blockIdx.x * TPB + threadIdx.x; i < n; i += (int64_t)gridDim.x * TPB) {
-        double d = dist[i];
+        double d = rec[i].w;
         if (d <= lim && d > m) m = d;
     }
     m = warp_max(m);
@@ -127,20 +127,21 @@ __device__ __forceinline__ uint64_t descend21(double px, double py, double pz, C
 }
 
 // key_hi (outlier flag + levels 0..20) for every particle; key_lo is produced on demand by key_lo_of()
-__global__ void __launch_bounds__(TPB) k_keygen(const double* __restrict__ x, const double* __restrict__ y, const double* __restrict__ z, int64_t n,
+__global__ void __launch_bounds__(TPB) k_keygen(const double4* __restrict__ rec, const uint8_t* __restrict__ type, int64_t n,
                                                   uint64_t* __restrict__ khi, uint32_t* __restrict__ perm, AgbScalars* s)
 {
     int64_t i = (int64_t)blockIdx.x * TPB + threadIdx.x;
     bool outl = false, edge = false;
     if (i < n) {
         const double R = __longlong_as_double((long long)s->Rbits);
-        const double px = x[i], py = y[i], pz = z[i];
+        const double4 r4 = rec[i];
+        const double px = r4.x, py = r4.y, pz = r4.z;
         uint64_t hi;
         // root cube is centred on the origin (Tree.cpp:31); inclusive bounds (Node.cpp:706-711)
         outl = px < -R || px > R || py < -R || py > R || pz < -R || pz > R;
         if (outl) hi = AGB_OUTLIER_BIT;           // the stable sort keeps caller order among the outliers
         else { Cell c{0.0, 0.0, 0.0, R}; hi = descend21(px, py, pz, c, false, edge); }
-        khi[i] = hi; perm[i] = (uint32_t)i;
+        khi[i] = hi; perm[i] = (uint32_t)i | (type[i] == 2 ? AGB_GAS_BIT : 0u);   // the sort payload also carries "is gas"
     }
     unsigned mo = __ballot_sync(0xffffffffu, outl), me = __ballot_sync(0xffffffffu, edge);
     if ((threadIdx.x & 31) == 0) {
@@ -301,8 +302,7 @@ __global__ void __launch_bounds__(TPB) k_sort_scatter(const uint64_t* __restrict
 // Short runs are insertion-sorted by the thread at the run start; long ones are queued for k_fix_long_runs.
 constexpr int FIX_SHORT = 16, FIX_LONG_MAX = 4096;
 __global__ void __launch_bounds__(TPB) k_fix_runs(const uint64_t* __restrict__ hi, uint64_t* __restrict__ lo, uint32_t* __restrict__ perm, int64_t n,
-                                                    const double* __restrict__ x, const double* __restrict__ y, const double* __restrict__ z,
-                                                    AgbScalars* s, int32_t* __restrict__ longlist)
+                                                    const double4* __restrict__ rec, AgbScalars* s, int32_t* __restrict__ longlist)
 {
     int64_t i = (int64_t)blockIdx.x * TPB + threadIdx.x;
     const int64_t nt = n - s->n_outliers;
@@ -318,7 +318,7 @@ __global__ void __launch_bounds__(TPB) k_fix_runs(const uint64_t* __restrict__ h
         return;
     }
     const double R = __longlong_as_double((long long)s->Rbits);
-    for (int a = 0; a < len; a++) { const uint32_t p = perm[i + a]; lo[i + a] = key_lo_of(x[p], y[p], z[p], R, s); }
+    for (int a = 0; a < len; a++) { const double4 r4 = rec[perm[i + a] & AGB_IDX_MASK]; lo[i + a] = key_lo_of(r4.x, r4.y, r4.z, R, s); }
     for (int a = 1; a < len; a++) {                                  // stable insertion sort
         const uint64_t kl = lo[i + a]; const uint32_t kp = perm[i + a];
         int b = a - 1;
@@ -328,8 +328,7 @@ __global__ void __launch_bounds__(TPB) k_fix_runs(const uint64_t* __restrict__ h
 }
 
 __global__ void __launch_bounds__(TPB) k_fix_long_runs(const uint64_t* __restrict__ hi, uint64_t* __restrict__ lo, uint32_t* __restrict__ perm, int64_t n,
-                                                         const double* __restrict__ x, const double* __restrict__ y, const double* __restrict__ z,
-                                                         AgbScalars* s, const int32_t* __restrict__ longlist)
+                                                         const double4* __restrict__ rec, AgbScalars* s, const int32_t* __restrict__ longlist)
 {
     __shared__ uint64_t sl[FIX_LONG_MAX];
     __shared__ uint32_t sp[FIX_LONG_MAX];
@@ -345,7 +344,7 @@ __global__ void __launch_bounds__(TPB) k_fix_long_runs(const uint64_t* __restric
         while (p2 < len) p2 <<= 1;
         __syncthreads();
         for (int j = threadIdx.x; j < p2; j += TPB) {
-            if (j < len) { const uint32_t p = perm[i + j]; sp[j] = p; sl[j] = key_lo_of(x[p], y[p], z[p], R, s); }
+            if (j < len) { const uint32_t p = perm[i + j]; const double4 r4 = rec[p & AGB_IDX_MASK]; sp[j] = p; sl[j] = key_lo_of(r4.x, r4.y, r4.z, R, s); }
             else { sl[j] = ~0ull; sp[j] = 0xffffffffu; }
         }
         __syncthreads();
@@ -367,16 +366,17 @@ __global__ void __launch_bounds__(TPB) k_fix_long_runs(const uint64_t* __restric
 }
 
 // ------------------------------------------------------------------ gather into tree order
-__global__ void __launch_bounds__(TPB) k_gather(AgbDev d, const uint32_t* __restrict__ perm, AgbScalars* s)
+__global__ void __launch_bounds__(TPB) k_gather(AgbDev d, uint32_t* __restrict__ perm, AgbScalars* s)
 {
     int64_t i = (int64_t)blockIdx.x * TPB + threadIdx.x;
     if (i >= d.n) return;
-    uint32_t p = perm[i];
-    double m = d.mass[p];
-    uint8_t t = d.type[p];
-    bool gas = t == 2;
-    d.src_pm[i] = make_double4(d.x[p], d.y[p], d.z[p], m);
-    d.s_type[i] = t;
+    const uint32_t val = perm[i], p = val & AGB_IDX_MASK;
+    const bool gas = (val & AGB_GAS_BIT) != 0u;
+    perm[i] = p;                                      // from here on the permutation is a plain caller index
+    const double m = d.mass[p];
+    const double4 r4 = d.rec[p];
+    d.src_pm[i] = make_double4(r4.x, r4.y, r4.z, m);
+    d.s_type[i] = gas ? 2 : 1;                        // only "gas or not" matters on the path (Node.cpp:319,371,478,679,763)
     d.s_next[i] = d.next ? d.next[p] : 0.0;
     if (gas) {
         // velocity, U, mu and the carried h/rho/P/T are only ever read for gas (Node.cpp:88-172, :722-796)
@@ -707,15 +707,15 @@ static inline int nblk(int64_t n, int per) { return (int)((n + per - 1) / per); 
 int agb_launch_extent(const AgbDev& d, AgbScalars* s, cudaStream_t st)
 {
     int nb = (int)std::min<int64_t>(1024, std::max<int64_t>(1, nblk(d.n, TPB)));
-    k_dist_partial<<<nb, TPB, 0, st>>>(d.x, d.y, d.z, d.n, d.dist, s);
+    k_dist_partial<<<nb, TPB, 0, st>>>(d.x, d.y, d.z, d.n, d.rec, s);
     k_extent_finish<<<1, 32, 0, st>>>(s, nb, d.n);
-    k_extent_max<<<nb, TPB, 0, st>>>(d.dist, d.n, s);
+    k_extent_max<<<nb, TPB, 0, st>>>(d.rec, d.n, s);
     return 3;
 }
 
 int agb_launch_keygen(AgbDev& d, AgbScalars* s, cudaStream_t st)
 {
-    k_keygen<<<nblk(d.n, TPB), TPB, 0, st>>>(d.x, d.y, d.z, d.n, d.khi[0], d.perm[0], s);
+    k_keygen<<<nblk(d.n, TPB), TPB, 0, st>>>(d.rec, d.type, d.n, d.khi[0], d.perm[0], s);
     d.cur = 0;
     return 1;
 }
@@ -745,8 +745,8 @@ int agb_launch_sort(AgbDev& d, AgbScalars* s, cudaStream_t st)
     int launches = d.n >= (4 << 20) ? sort_passes<16>(d, s, st) : sort_passes<8>(d, s, st);
     const int nb = nblk(d.n, TPB);
     cudaMemsetAsync(d.klo[1], 0, (size_t)d.n * sizeof(uint64_t), st);
-    k_fix_runs<<<nb, TPB, 0, st>>>(d.khi[d.cur], d.klo[1], d.perm[d.cur], d.n, d.x, d.y, d.z, s, d.nodecnt);
-    k_fix_long_runs<<<64, TPB, 0, st>>>(d.khi[d.cur], d.klo[1], d.perm[d.cur], d.n, d.x, d.y, d.z, s, d.nodecnt);
+    k_fix_runs<<<nb, TPB, 0, st>>>(d.khi[d.cur], d.klo[1], d.perm[d.cur], d.n, d.rec, s, d.nodecnt);
+    k_fix_long_runs<<<64, TPB, 0, st>>>(d.khi[d.cur], d.klo[1], d.perm[d.cur], d.n, d.rec, s, d.nodecnt);
     return launches + 2;
 }
 

@@ -298,9 +298,9 @@ int agb_launch_gas_density(AgbDev& d, AgbScalars* s, double massInH, cudaStream_
     const int nb = nblk(d.n, TPB);
     k_gas_reset<<<1, 1, 0, st>>>(s);
     // compact (caller index, mass) of the gas particles in tree order; scratch that is free after the build is reused:
-    // flags -> nodecnt, caller indices -> the idle half of the sort's ping-pong permutation, masses -> dist
+    // flags -> nodecnt, caller indices -> the idle half of the sort's ping-pong permutation, masses -> rec
     uint32_t* g_orig = d.perm[d.cur ^ 1];
-    double* g_m = d.dist;
+    double* g_m = reinterpret_cast<double*>(d.rec);
     k_gas_flags<<<nb, TPB, 0, st>>>(d, d.nodecnt);
     int launches = agb_launch_scan_i32(d.nodecnt, d.gasrank, d.n, d.scanblk, &s->n_gas_total, st);
     cudaMemcpyAsync(d.gasrank + d.n, &s->n_gas_total, sizeof(int32_t), cudaMemcpyDeviceToDevice, st);

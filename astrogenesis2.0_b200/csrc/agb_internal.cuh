@@ -17,6 +17,8 @@
 
 #define AGB_MAX_LEVELS 42
 #define AGB_OUTLIER_BIT 0x8000000000000000ull
+#define AGB_GAS_BIT 0x80000000u          /* sort payload: caller index (< 2^30) | "type == 2" */
+#define AGB_IDX_MASK 0x7fffffffu
 
 struct AgbDev {
     int64_t n = 0, cap = 0;
@@ -48,7 +50,7 @@ struct AgbDev {
     int32_t* grouplist = nullptr;
     int32_t* gasrank = nullptr;        // exclusive count of gas particles before tree position i
     // scratch
-    double* dist = nullptr;
+    double4* rec = nullptr;            // caller order: (x, y, z, |x|) packed by the extent pass
     uint32_t* blockhist = nullptr;     // radix sort: [256][nblocks]
     int32_t* scanblk = nullptr;
     // per-target counters (optional)
