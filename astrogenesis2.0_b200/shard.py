@@ -49,3 +49,47 @@ def gather_particles(shard, n, world, out=None, scratch=None):
             full[k][off: off + c].copy_(buf[r * mx: r * mx + c])
             off += c
     return full
+
+
+class PackedGather:
+    """One NCCL all-gather per step for all float64 particle arrays (plus one for the uint8 types): every rank keeps its
+    shard as rows of a packed [fields, max_count] buffer; the gathered [world, fields, max_count] block is transposed on
+    the device into full-length per-field arrays.  5 collectives per step become 2 (latency bound at 1M particles)."""
+
+    def __init__(self, shard, n, world):
+        self.n, self.world = n, world
+        self.counts = shard_counts(n, world)
+        self.mx = max(self.counts)
+        self.fields = [k for k, v in shard.items() if v.dtype == torch.float64]
+        self.bytes_fields = [k for k, v in shard.items() if v.dtype == torch.uint8]
+        dev = next(iter(shard.values())).device
+        self.local = torch.zeros(len(self.fields), self.mx, dtype=torch.float64, device=dev)
+        self.local_b = torch.zeros(max(1, len(self.bytes_fields)), self.mx, dtype=torch.uint8, device=dev)
+        self.recv = torch.empty(world, len(self.fields), self.mx, dtype=torch.float64, device=dev)
+        self.recv_b = torch.empty(world, max(1, len(self.bytes_fields)), self.mx, dtype=torch.uint8, device=dev)
+        self.full = torch.empty(len(self.fields), world * self.mx, dtype=torch.float64, device=dev)
+        self.full_b = torch.empty(max(1, len(self.bytes_fields)), world * self.mx, dtype=torch.uint8, device=dev)
+        self.even = all(c == self.mx for c in self.counts)
+        self.out = {k: (self.full[i, :n] if self.even else torch.empty(n, dtype=torch.float64, device=dev)) for i, k in enumerate(self.fields)}
+        self.out.update({k: (self.full_b[i, :n] if self.even else torch.empty(n, dtype=torch.uint8, device=dev)) for i, k in enumerate(self.bytes_fields)})
+
+    def gather(self, shard):
+        c = next(iter(shard.values())).numel()
+        for i, k in enumerate(self.fields):
+            self.local[i, :c].copy_(shard[k])
+        for i, k in enumerate(self.bytes_fields):
+            self.local_b[i, :c].copy_(shard[k])
+        dist.all_gather_into_tensor(self.recv.view(-1), self.local.view(-1))
+        self.full.view(len(self.fields), self.world, self.mx).copy_(self.recv.permute(1, 0, 2))
+        if self.bytes_fields:
+            dist.all_gather_into_tensor(self.recv_b.view(-1), self.local_b.view(-1))
+            self.full_b.view(len(self.bytes_fields), self.world, self.mx).copy_(self.recv_b.permute(1, 0, 2))
+        if not self.even:
+            for i, k in enumerate(self.fields + self.bytes_fields):
+                src = self.full if i < len(self.fields) else self.full_b
+                row = i if i < len(self.fields) else i - len(self.fields)
+                off = 0
+                for r, cnt in enumerate(self.counts):
+                    self.out[k][off: off + cnt].copy_(src[row, r * self.mx: r * self.mx + cnt])
+                    off += cnt
+        return self.out

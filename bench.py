@@ -197,11 +197,13 @@ def run_gpu_arm(args, pkg):
     full = {k: (torch.empty(n, dtype=v.dtype, device=dev) if world > 1 else v) for k, v in shard.items()}
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)      # > 126 MB L2
 
-    scratch = {}
+    packed = pkg.shard.PackedGather(shard, n, world) if world > 1 else None
+    if world > 1:
+        full = packed.out
 
     def gather():
         if world > 1:
-            pkg.shard.gather_particles(shard, n, world, out=full, scratch=scratch)
+            packed.gather(shard)
 
     def step():
         gather()

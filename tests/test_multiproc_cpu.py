@@ -24,6 +24,9 @@ def _worker(rank, world, port, n, q):
         shard = {k: torch.from_numpy(np.ascontiguousarray(p[k][lo:hi])) for k in ("x", "y", "z", "mass", "vx", "type")}
         full = pkg.shard.gather_particles(shard, n, world)
         ok = all(np.array_equal(full[k].numpy(), p[k]) for k in shard)
+        pg = pkg.shard.PackedGather(shard, n, world)
+        out = pg.gather(shard)
+        ok = ok and all(np.array_equal(out[k].numpy(), p[k]) for k in shard)
         q.put((rank, ok, pkg.shard.slice_bounds(n, rank, world)))
     finally:
         dist.destroy_process_group()
