@@ -16,6 +16,7 @@
 //
 // All kernels are HBM-bound streaming / pointer-chasing passes over O(N) data.
 #include "agb_internal.cuh"
+#include <algorithm>
 
 namespace {
 
@@ -79,17 +80,19 @@ __global__ void __launch_bounds__(TPB) k_gas_flags(AgbDev d, int32_t* __restrict
     if (i < d.n) flag[i] = d.s_type[i] == 2;
 }
 
-__global__ void __launch_bounds__(TPB) k_gas_compact(AgbDev d, const uint32_t* __restrict__ perm, uint32_t* __restrict__ g_orig, double* __restrict__ g_m)
+__global__ void __launch_bounds__(TPB) k_gas_compact(AgbDev d, const uint32_t* __restrict__ perm, uint32_t* __restrict__ g_orig, double4* __restrict__ g_pm,
+                                                       int32_t* __restrict__ g_tree)
 {
     int64_t i = (int64_t)blockIdx.x * TPB + threadIdx.x;
     if (i >= d.n || d.s_type[i] != 2) return;
     const int r = d.gasrank[i];
     g_orig[r] = perm[i];
-    g_m[r] = d.src_pm[i].w;
+    g_pm[r] = d.src_pm[i];
+    g_tree[r] = (int32_t)i;
 }
 
 struct GasFold {
-    const int32_t* gasrank; const uint32_t* g_orig; const double* g_m;
+    const int32_t* gasrank; const uint32_t* g_orig; const double4* g_pm; const int32_t* g_tree;
     uint8_t* nflag;            // per node: 0 = tree-order sum only, 1 = exact sum requested, 2 = exact sum ready, 3 = too large to fold
     double* nexact;            // per node: the reference's left-fold gasMass
     int32_t* foldlist;         // flagged nodes
@@ -177,7 +180,7 @@ __global__ void __launch_bounds__(TPB) k_gas_fold(AgbDev d, AgbScalars* s, GasFo
         __syncthreads();
         for (int j = threadIdx.x; j < p2; j += TPB) {
             sm_i[j] = j < cnt ? F.g_orig[g0 + j] : 0xffffffffu;
-            sm_m[j] = j < cnt ? F.g_m[g0 + j] : 0.0;
+            sm_m[j] = j < cnt ? F.g_pm[g0 + j].w : 0.0;
         }
         __syncthreads();
         for (int size = 2; size <= p2; size <<= 1)
@@ -246,38 +249,40 @@ __device__ __forceinline__ double spline_w(double r, double h)
 }
 
 // one warp per surviving group: fixed-shape (lane-strided, then butterfly) sum => deterministic
-__global__ void __launch_bounds__(TPB) k_gas_sum(AgbDev d, const AgbScalars* __restrict__ s)
+__global__ void __launch_bounds__(TPB) k_gas_sum(AgbDev d, const AgbScalars* __restrict__ s, GasFold F)
 {
-    const int g = (blockIdx.x * TPB + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (g >= s->n_gas_groups) return;
-    const int k = d.grouplist[g];
+    const int lane = threadIdx.x & 31;
     const double R = __longlong_as_double((long long)s->Rbits);
+    for (int g = (blockIdx.x * TPB + threadIdx.x) >> 5; g < s->n_gas_groups; g += (gridDim.x * TPB) >> 5) {
+    const int k = d.grouplist[g];
     const double h = __dmul_rn(radius_at(R, d.ndepth[k]), 2.0);          // Node.cpp:765
     const double4 com = d.src_pm[d.n + k];
-    const int first = d.nfirst[k], last = d.nlast[k];
+    // the node's gas particles are a contiguous range of the compact gas list (tree order)
+    const int g0 = F.gasrank[d.nfirst[k]], g1 = F.gasrank[d.nlast[k] + 1];
     double acc = 0.0;
-    for (int j = first + lane; j <= last; j += 32) {
-        if (d.s_type[j] != 2) continue;
-        double4 pm = d.src_pm[j];
-        double dx = pm.x - com.x, dy = pm.y - com.y, dz = pm.z - com.z;
+    for (int r = g0 + lane; r < g1; r += 32) {
+        const double4 pm = F.g_pm[r];
+        const double dx = pm.x - com.x, dy = pm.y - com.y, dz = pm.z - com.z;
         acc += pm.w * spline_w(sqrt(dx * dx + dy * dy + dz * dz), h);
     }
     for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
     if (d.ndup[k]) acc += acc;                                            // every particle listed twice (Node.cpp:518 + :615)
-    for (int j = first + lane; j <= last; j += 32) {
-        if (d.s_type[j] != 2) continue;
+    for (int r = g0 + lane; r < g1; r += 32) {
+        const int j = F.g_tree[r];
         d.s_h[j] = h; d.s_rho[j] = acc;
         d.s_P[j] = (kGAMMA - 1.0) * d.s_U[j] * acc;                       // Node.cpp:789
         d.s_T[j] = (kGAMMA - 1.0) * d.s_U[j] * kPRTN * d.s_mu[j] / kKB;   // Node.cpp:791
     }
+    }
 }
 
-// back to caller order
-__global__ void __launch_bounds__(TPB) k_gas_scatter(AgbDev d, const uint32_t* __restrict__ perm)
+// back to caller order (gas only, through the compact list)
+__global__ void __launch_bounds__(TPB) k_gas_scatter(AgbDev d, const AgbScalars* __restrict__ s, GasFold F)
 {
-    int64_t i = (int64_t)blockIdx.x * TPB + threadIdx.x;
-    if (i >= d.n || d.s_type[i] != 2) return;
-    const uint32_t p = perm[i];
+    const int r = blockIdx.x * TPB + threadIdx.x;
+    if (r >= s->n_gas_total) return;
+    const int i = F.g_tree[r];
+    const uint32_t p = F.g_orig[r];
     d.h[p] = d.s_h[i]; d.rho[p] = d.s_rho[i]; d.P[p] = d.s_P[i]; d.T[p] = d.s_T[i];
 }
 
@@ -300,14 +305,15 @@ int agb_launch_gas_density(AgbDev& d, AgbScalars* s, double massInH, cudaStream_
     // compact (caller index, mass) of the gas particles in tree order; scratch that is free after the build is reused:
     // flags -> nodecnt, caller indices -> the idle half of the sort's ping-pong permutation, masses -> rec
     uint32_t* g_orig = d.perm[d.cur ^ 1];
-    double* g_m = reinterpret_cast<double*>(d.rec);
+    double4* g_pm = d.rec;                                  // (x, y, z, m) of the gas particles, compact, tree order
+    int32_t* g_tree = d.nodecnt + 0;                        // their tree positions (the flags in nodecnt are dead after the scan)
     k_gas_flags<<<nb, TPB, 0, st>>>(d, d.nodecnt);
     int launches = agb_launch_scan_i32(d.nodecnt, d.gasrank, d.n, d.scanblk, &s->n_gas_total, st);
     cudaMemcpyAsync(d.gasrank + d.n, &s->n_gas_total, sizeof(int32_t), cudaMemcpyDeviceToDevice, st);
-    k_gas_compact<<<nb, TPB, 0, st>>>(d, d.perm[d.cur], g_orig, g_m);
+    k_gas_compact<<<nb, TPB, 0, st>>>(d, d.perm[d.cur], g_orig, g_pm, g_tree);
     // nflag/pending/foldlist/nexact borrow scratch that is idle here: arrived (int32/node), lcp (int8/particle),
     // nodebase (int32/particle), and the caller-order copy of key_lo (8 B/particle)
-    GasFold F{d.gasrank, g_orig, g_m, reinterpret_cast<uint8_t*>(d.arrived), reinterpret_cast<double*>(d.klo[0]), d.nodebase,
+    GasFold F{d.gasrank, g_orig, g_pm, g_tree, reinterpret_cast<uint8_t*>(d.arrived), reinterpret_cast<double*>(d.klo[0]), d.nodebase,
               reinterpret_cast<uint8_t*>(d.lcp)};
     cudaMemsetAsync(d.arrived, 0, (size_t)d.n * sizeof(int32_t), st);
     cudaMemsetAsync(d.lcp, 0, (size_t)d.n, st);
@@ -319,7 +325,7 @@ int agb_launch_gas_density(AgbDev& d, AgbScalars* s, double massInH, cudaStream_
     k_gas_mark<1><<<nb, TPB, 0, st>>>(d, s, massInH, F);
     k_gas_group<<<nb, TPB, 0, st>>>(d, s);
     k_gas_collect<<<nb, TPB, 0, st>>>(d, s);
-    k_gas_sum<<<nblk(d.n, TPB / 32), TPB, 0, st>>>(d, s);     // upper bound on groups; surplus warps exit
-    k_gas_scatter<<<nb, TPB, 0, st>>>(d, d.perm[d.cur]);
+    k_gas_sum<<<std::min(nblk(d.n, TPB / 32), 148 * 16), TPB, 0, st>>>(d, s, F);   // one warp per group, grid-stride
+    k_gas_scatter<<<nb, TPB, 0, st>>>(d, s, F);
     return 10 + launches;
 }
