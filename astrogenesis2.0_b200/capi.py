@@ -18,7 +18,8 @@ EXPORTS = [
     "agb_create", "agb_destroy", "agb_set_particles", "agb_set_particles_aos", "agb_build_tree", "agb_visual_density",
     "agb_gas_density", "agb_forces", "agb_forces_slice", "agb_get_results", "agb_get_results_aos", "agb_get_counters",
     "agb_set_option", "agb_get_tree_particles", "agb_get_node_count", "agb_get_nodes", "agb_get_target_counters",
-    "agb_get_phase_ms", "agb_get_stream", "agb_get_launch_count", "agb_microbench", "agb_strerror", "agb_last_error", "agb_version",
+    "agb_get_phase_ms", "agb_get_stream", "agb_get_launch_count", "agb_microbench",
+    "agb_integrator_init", "agb_integrator_assign_all", "agb_step_begin", "agb_step_end", "agb_get_state", "agb_strerror", "agb_last_error", "agb_version",
 ]
 
 
@@ -90,6 +91,11 @@ def load(build_if_needed=True):
     lib.agb_get_stream.argtypes = [vp, C.POINTER(vp)]
     lib.agb_get_launch_count.argtypes = [vp, C.POINTER(C.c_int64)]
     lib.agb_microbench.argtypes = [vp, C.c_int, _pd]
+    lib.agb_integrator_init.argtypes = [vp] + [C.c_double] * 5
+    lib.agb_integrator_assign_all.argtypes = [vp]
+    lib.agb_step_begin.argtypes = [vp, _pd]
+    lib.agb_step_end.argtypes = [vp]
+    lib.agb_get_state.argtypes = [vp] + [_pd] * 9
     lib.agb_strerror.restype = C.c_char_p
     lib.agb_strerror.argtypes = [C.c_int]
     lib.agb_last_error.restype = C.c_char_p

@@ -31,6 +31,8 @@ struct agb_ctx {
     std::string err;
     // pinned staging for host particles
     double* stage = nullptr; size_t stage_bytes = 0;
+    // device-resident integrator
+    AgbInt I = {}; bool int_ready = false; double* timestep = nullptr; unsigned long long* d_min = nullptr; double int_time = 0.0;
     agb_counters last = {};
 };
 
@@ -54,7 +56,7 @@ void free_pool(agb_ctx* c)
 {
     AgbDev& d = c->d;
     for (auto& q : c->in_d) dfree(q);
-    dfree(c->in_type);
+    dfree(c->in_type); dfree(c->timestep);
     dfree(d.ax); dfree(d.ay); dfree(d.az); dfree(d.dUdt); dfree(d.h); dfree(d.rho); dfree(d.P); dfree(d.T); dfree(d.vis);
     for (int i = 0; i < 2; i++) { dfree(d.khi[i]); dfree(d.klo[i]); dfree(d.perm[i]); }
     dfree(d.src_pm); dfree(d.src_gv); dfree(d.src_flag);
@@ -91,6 +93,7 @@ int ensure_pool(agb_ctx* c, int64_t n)
         CK(dalloc(d.far_list, nsg * lcap)); CK(dalloc(d.far_front, nsg * fcap)); CK(dalloc(d.far_cnt, nsg * 3));
     }
     for (auto& q : c->in_d) CK(dalloc(q, cap));
+    CK(dalloc(c->timestep, cap));
     CK(dalloc(c->in_type, cap));
     CK(dalloc(d.blockhist, 256 * ((cap + 2047) / 2048 + 1)));   // sort tiles are >= 2048 keys
     CK(dalloc(d.scanblk, (cap + 2047) / 2048 + 1));
@@ -238,6 +241,7 @@ int agb_set_particles(agb_ctx* c, const agb_particles* p, int memspace)
     // Host arrays are read asynchronously (pinned memory makes that a true overlap): like the reference, which reads
     // Simulation::particles during buildTree, they must stay untouched until agb_build_tree has returned.
     c->have_particles = true; c->built = false; c->dens_done = false; c->forces_done = false; c->counters_valid = false;
+    c->int_ready = false;
     return AGB_OK;
 }
 
@@ -517,6 +521,82 @@ int agb_get_stream(agb_ctx* c, void** stream)
 {
     if (!c || !stream) return AGB_ERR_INVALID;
     *stream = (void*)c->st;
+    return AGB_OK;
+}
+
+// ---------------------------------------------------------------- device-resident driver loop
+int agb_integrator_init(agb_ctx* c, double eta, double min_time_step, double max_time_step, double H0, double e0)
+{
+    if (!c || !c->have_particles || c->bound) return AGB_ERR_INVALID;          // needs the owned (host-uploaded) particle copies
+    if (!(min_time_step > 0.0) || !(max_time_step >= min_time_step)) return AGB_ERR_INVALID;
+    CK(cudaSetDevice(c->device));
+    AgbDev& d = c->d;
+    if (!d.vx || !d.vy || !d.vz || !d.U || !d.next) { c->err = "integrator needs vx, vy, vz, U and next_time arrays"; return AGB_ERR_INVALID; }
+    if (c->in_pending) { CK(cudaStreamWaitEvent(c->st, c->ev_in, 0)); c->in_pending = false; }
+    AgbInt& I = c->I;
+    I.x = c->in_d[0]; I.y = c->in_d[1]; I.z = c->in_d[2]; I.vx = c->in_d[3]; I.vy = c->in_d[4]; I.vz = c->in_d[5]; I.U = c->in_d[7]; I.next = c->in_d[8];
+    I.mu = d.mu; I.timestep = c->timestep;
+    I.eta = eta; I.e0 = e0; I.min_ts = min_time_step; I.max_ts = max_time_step;
+    const double H0SI = (H0 * 1.0e3) / 3.08567758149137e22;                    // Math/Units.h, Simulation.cpp:329
+    int kmin, kmax;
+    frexp(min_time_step, &kmin); frexp(max_time_step, &kmax);
+    I.k0 = kmin - 2;
+    if (kmax - I.k0 >= AGB_INT_BINS) { c->err = "time-step range spans more than 2^126"; return AGB_ERR_UNSUPPORTED; }
+    for (int j = 0; j < AGB_INT_BINS; j++) I.scale_tab[j] = exp(H0SI * ldexp(1.0, I.k0 + j));
+    I.scale_min = exp(H0SI * min_time_step);
+    if (!c->d_min) CK(cudaMalloc((void**)&c->d_min, sizeof(unsigned long long)));
+    c->launches += agb_launch_int_init(d, I, c->st);
+    c->int_time = 0.0; c->int_ready = true;
+    CK(cudaGetLastError());
+    return AGB_OK;
+}
+
+int agb_integrator_assign_all(agb_ctx* c)
+{
+    if (!c || !c->int_ready) return AGB_ERR_INVALID;
+    CK(cudaSetDevice(c->device));
+    c->launches += agb_launch_int_assign(c->d, c->I, c->int_time, true, c->st);     // Simulation.cpp:189-208
+    CK(cudaGetLastError());
+    return AGB_OK;
+}
+
+int agb_step_begin(agb_ctx* c, double* global_time)
+{
+    if (!c || !c->int_ready || !global_time) return AGB_ERR_INVALID;
+    CK(cudaSetDevice(c->device));
+    AgbDev& d = c->d;
+    c->launches += agb_launch_int_assign(d, c->I, c->int_time, false, c->st);         // Simulation.cpp:213-234
+    c->launches += agb_launch_int_min(d, c->I, c->d_min, c->st);                      // :237-254
+    unsigned long long bits = 0;
+    CK(cudaMemcpyAsync(&bits, c->d_min, sizeof(bits), cudaMemcpyDeviceToHost, c->st));
+    CK(cudaStreamSynchronize(c->st));
+    double gt; memcpy(&gt, &bits, 8);
+    c->int_time = gt; *global_time = gt;
+    c->launches += agb_launch_int_first(d, c->I, gt, c->st);                          // :258-272
+    c->built = false; c->dens_done = false; c->forces_done = false; c->counters_valid = false;
+    c->have_particles = true;
+    CK(cudaGetLastError());
+    return AGB_OK;
+}
+
+int agb_step_end(agb_ctx* c)
+{
+    if (!c || !c->int_ready || !c->forces_done) return AGB_ERR_INVALID;
+    CK(cudaSetDevice(c->device));
+    c->launches += agb_launch_int_second(c->d, c->I, c->int_time, c->st);             // :296-341
+    CK(cudaGetLastError());
+    return AGB_OK;
+}
+
+int agb_get_state(agb_ctx* c, double* x, double* y, double* z, double* vx, double* vy, double* vz, double* U, double* next_time, double* time_step)
+{
+    if (!c || !c->have_particles || c->bound) return AGB_ERR_INVALID;
+    CK(cudaSetDevice(c->device));
+    const size_t b = (size_t)c->d.n * sizeof(double);
+    struct { double* dst; const double* src; } cp[] = {{x, c->in_d[0]}, {y, c->in_d[1]}, {z, c->in_d[2]}, {vx, c->in_d[3]}, {vy, c->in_d[4]}, {vz, c->in_d[5]},
+                                                       {U, c->in_d[7]}, {next_time, c->in_d[8]}, {time_step, c->timestep}};
+    for (auto& e : cp) if (e.dst && b) CK(cudaMemcpyAsync(e.dst, e.src, b, cudaMemcpyDeviceToHost, c->st));
+    CK(cudaStreamSynchronize(c->st));
     return AGB_OK;
 }
 

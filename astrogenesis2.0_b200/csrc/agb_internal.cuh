@@ -77,6 +77,20 @@ struct AgbScalars {
     unsigned long long st_rounds, st_popped, st_mixed, st_open, st_drain;   // walk statistics (tuning)
 };
 
+// Device-resident integrator state (agb_integrate.cu): mutable views of the owned particle copies + per-particle step
+#define AGB_INT_BINS 128
+struct AgbInt {
+    double *x, *y, *z, *vx, *vy, *vz, *U, *next; const double* mu;
+    double* timestep;
+    double eta, e0, min_ts, max_ts;
+    double scale_min; int k0; double scale_tab[AGB_INT_BINS];   // exp(H0 dt) per power-of-two bin 2^(k0 + j), from the host's libm
+};
+int agb_launch_int_init(AgbDev& d, const AgbInt& I, cudaStream_t st);
+int agb_launch_int_assign(AgbDev& d, const AgbInt& I, double gt, bool all, cudaStream_t st);
+int agb_launch_int_min(AgbDev& d, const AgbInt& I, unsigned long long* out, cudaStream_t st);
+int agb_launch_int_first(AgbDev& d, const AgbInt& I, double gt, cudaStream_t st);
+int agb_launch_int_second(AgbDev& d, const AgbInt& I, double gt, cudaStream_t st);
+
 // ---- host-callable launchers (each returns the number of kernels it launched) ----
 int agb_launch_extent(const AgbDev& d, AgbScalars* s, cudaStream_t st);
 int agb_launch_keygen(AgbDev& d, AgbScalars* s, cudaStream_t st);

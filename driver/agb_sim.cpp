@@ -15,7 +15,9 @@
 // The force path itself is only reached through the C ABI (include/agb200.h); there is no CPU fallback.
 //
 //   agb_sim --config Config.ini [--input-root DIR] [--output-root DIR] [--steps K] [--device D] [--cores C]
-//           [--precision fp64|mixed] [--dump final.agp] [--overwrite]
+//           [--precision fp64|mixed] [--dump final.agp] [--overwrite] [--device-resident]
+// --device-resident keeps positions, velocities and results in HBM between steps (agb_integrator_* / agb_step_*):
+// only the scalar time crosses PCIe per step; state is copied back for snapshots and at the end.
 #include <algorithm>
 #include <chrono>
 #include <cmath>
@@ -208,6 +210,7 @@ void check(agb_ctx* c, int rc, const char* what)
 struct Driver {
     Config cfg; Particles p; agb_ctx* ctx = nullptr; PhaseLog log;
     double globalTime = 0, visualDensityRadius = 0;
+    bool device_resident = false;
 
     void force_path(bool first)
     {
@@ -230,6 +233,68 @@ struct Driver {
         agb_results out{p.ax.data(), p.ay.data(), p.az.data(), p.dUdt.data(), p.h.data(), p.rho.data(), p.P.data(), p.T.data(), p.vis.data()};
         check(ctx, agb_get_results(ctx, &out, AGB_MEM_HOST), "get_results");
         log.end();
+    }
+
+    void upload()
+    {
+        agb_particles in{};
+        in.n = p.n; in.x = p.x.data(); in.y = p.y.data(); in.z = p.z.data(); in.vx = p.vx.data(); in.vy = p.vy.data(); in.vz = p.vz.data();
+        in.mass = p.mass.data(); in.U = p.U.data(); in.next_time = p.next.data(); in.mu = p.mu.data(); in.type = p.type.data();
+        in.rho = p.rho.data(); in.P = p.P.data(); in.T = p.T.data(); in.h = p.h.data(); in.dUdt = p.dUdt.data();
+        in.ax = p.ax.data(); in.ay = p.ay.data(); in.az = p.az.data();
+        check(ctx, agb_set_particles(ctx, &in, AGB_MEM_HOST), "set_particles");
+    }
+    void device_force_path(bool first)
+    {
+        log.start("build tree");
+        double R = 0;
+        check(ctx, agb_build_tree(ctx, &R), "build_tree");
+        if (first) visualDensityRadius = R / 100000;
+        log.start("Visual Density");
+        check(ctx, agb_visual_density(ctx, visualDensityRadius), "visual_density");
+        log.start("SPH density and update");
+        check(ctx, agb_gas_density(ctx, cfg.massInH), "gas_density");
+        log.start("Force Calculation");
+        check(ctx, agb_forces(ctx, globalTime, cfg.e0, cfg.theta), "forces");
+        log.end();
+    }
+    void download()
+    {
+        agb_results out{p.ax.data(), p.ay.data(), p.az.data(), p.dUdt.data(), p.h.data(), p.rho.data(), p.P.data(), p.T.data(), p.vis.data()};
+        check(ctx, agb_get_results(ctx, &out, AGB_MEM_HOST), "get_results");
+        check(ctx, agb_get_state(ctx, p.x.data(), p.y.data(), p.z.data(), p.vx.data(), p.vy.data(), p.vz.data(), p.U.data(), p.next.data(), p.timeStep.data()), "get_state");
+    }
+    int run_device(int64_t max_steps, const std::string& outdir)
+    {
+        const double fixedStep = cfg.endTime / cfg.fixedTimeSteps;
+        globalTime = 0.0;
+        for (int64_t i = 0; i < p.n; i++) p.next[i] = 0.0;
+        upload();
+        check(ctx, agb_integrator_init(ctx, cfg.eta, cfg.minTimeStep, cfg.maxTimeStep, cfg.H0, cfg.e0), "integrator_init");
+        device_force_path(true);
+        if (!outdir.empty()) { download(); save_age(outdir + "/0.age", p, (int64_t)cfg.numParticlesOutput, fixedStep, cfg.endTime, 0.0); }
+        check(ctx, agb_integrator_assign_all(ctx), "assign_all");
+        double nextSaveTime = fixedStep;
+        int64_t step = 0;
+        while (globalTime < cfg.endTime && (max_steps < 0 || step < max_steps)) {
+            log.start("first kick");
+            check(ctx, agb_step_begin(ctx, &globalTime), "step_begin");
+            device_force_path(false);
+            log.start("second kick");
+            check(ctx, agb_step_end(ctx), "step_end");
+            log.end();
+            step++;
+            if (!outdir.empty() && globalTime >= nextSaveTime) {
+                log.start("Save data");
+                download();
+                save_age(outdir + "/" + std::to_string((int)(nextSaveTime / fixedStep)) + ".age", p, (int64_t)cfg.numParticlesOutput, fixedStep, cfg.endTime, globalTime);
+                log.end();
+                nextSaveTime += fixedStep;
+            }
+        }
+        download();
+        printf("steps %lld globalTime %.17g\n", (long long)step, globalTime);
+        return 0;
     }
 
     void assign_timestep(int64_t i)
@@ -312,10 +377,11 @@ struct Driver {
 int main(int argc, char** argv)
 {
     std::map<std::string, std::string> opt;
-    bool overwrite = false;
+    bool overwrite = false, device_resident = false;
     for (int i = 1; i < argc; i++) {
         std::string a = argv[i];
         if (a == "--overwrite") { overwrite = true; continue; }
+        if (a == "--device-resident") { device_resident = true; continue; }
         if (a.rfind("--", 0) == 0 && i + 1 < argc) { opt[a.substr(2)] = argv[++i]; continue; }
         fprintf(stderr, "usage: agb_sim --config Config.ini [--input-root DIR] [--output-root DIR] [--steps K] [--device D] [--cores C] [--precision fp64|mixed] [--dump final.agp] [--overwrite]\n");
         return 2;
@@ -344,7 +410,8 @@ int main(int argc, char** argv)
     int rc = agb_create(&d.ctx, opt.count("device") ? atoi(opt["device"].c_str()) : 0, cores);
     if (rc != AGB_OK) { fprintf(stderr, "agb200: %s\n", agb_strerror(rc)); return 3; }
     if (opt.count("precision")) agb_set_option(d.ctx, AGB_OPT_PRECISION, opt["precision"] == "fp64" ? 0 : 1);
-    rc = d.run(opt.count("steps") ? atoll(opt["steps"].c_str()) : -1, outdir);
+    const int64_t max_steps = opt.count("steps") ? atoll(opt["steps"].c_str()) : -1;
+    rc = device_resident ? d.run_device(max_steps, outdir) : d.run(max_steps, outdir);
     if (opt.count("dump")) save_agp(opt["dump"], d.p);
     agb_destroy(d.ctx);
     return rc;

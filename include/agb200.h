@@ -113,6 +113,22 @@ int agb_forces(agb_ctx* ctx, double global_time, double e0, double theta);   /* 
  * targets (every GPU holds the same gathered particles and builds the same tree). */
 int agb_forces_slice(agb_ctx* ctx, double global_time, double e0, double theta, int part, int nparts);
 
+/* -------- device-resident driver loop (optional).  With particles handed over from HOST memory the
+ * context owns device copies; these calls advance them in place exactly like the reference's loop, so nothing but the
+ * scalar time crosses PCIe per step:
+ *   agb_integrator_init(..)                       gas T from U (Simulation.cpp:108-112), nextIntegrationTime = 0
+ *   build_tree / visual_density / gas_density / forces(global_time = 0)       initial forces (Simulation.cpp:120-139)
+ *   agb_integrator_assign_all()                   power-of-two time steps from |acc| (Simulation.cpp:189-208)
+ *   per step: agb_step_begin(&t)  ->  build_tree, visual_density, gas_density, forces(t)  ->  agb_step_end()
+ * step_begin = re-binning of due particles, t = min nextIntegrationTime, first Kick + Drift of the active particles
+ * (Simulation.cpp:213-272, TimeIntegration.cpp:10-26); step_end = Ueuler, Hubble rescale, second Kick, next += dt
+ * (Simulation.cpp:296-341).  agb_get_state copies positions, velocities, U, next time and time step back (NULL = skip). */
+int agb_integrator_init(agb_ctx* ctx, double eta, double min_time_step, double max_time_step, double H0, double e0);
+int agb_integrator_assign_all(agb_ctx* ctx);
+int agb_step_begin(agb_ctx* ctx, double* global_time);
+int agb_step_end(agb_ctx* ctx);
+int agb_get_state(agb_ctx* ctx, double* x, double* y, double* z, double* vx, double* vy, double* vz, double* U, double* next_time, double* time_step);
+
 /* -------- results (replaces the path's direct writes into Particle) */
 int agb_get_results(agb_ctx* ctx, const agb_results* r, int memspace);
 int agb_get_results_aos(agb_ctx* ctx, void* const* particles, int64_t n, const agb_aos_layout* layout);

@@ -71,8 +71,9 @@ def test_integrator_restatement_matches_reference(oracle, pkg):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("resident", [False, True], ids=["host-loop", "device-resident"])
 @pytest.mark.parametrize("precision", ["fp64", "mixed"])
-def test_driver_multi_step_gpu(oracle, pkg, precision):
+def test_driver_multi_step_gpu(oracle, pkg, precision, resident):
     b = ensure_bin()
     from oracle import agio, integrator
     p = pkg.ics.plummer(3000, seed=42, gas_fraction=0.3)
@@ -85,7 +86,7 @@ def test_driver_multi_step_gpu(oracle, pkg, precision):
         open(os.path.join(d, "Config.ini"), "w").write(CONFIG.format(**par))
         out = os.path.join(d, "final.agp")
         r = subprocess.run([b, "--config", os.path.join(d, "Config.ini"), "--input-root", d, "--output-root", d, "--steps", str(nsteps), "--cores", "8",
-                            "--precision", precision, "--dump", out], capture_output=True, text=True)
+                            "--precision", precision, "--dump", out] + (["--device-resident"] if resident else []), capture_output=True, text=True)
         assert r.returncode == 0, r.stderr
         got = agio.read_agp(out)
         raw = np.fromfile(out + ".acc", dtype="<f8").reshape(8, -1)
