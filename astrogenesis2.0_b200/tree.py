@@ -155,6 +155,27 @@ class Context:
         capi.check(self.h, self.lib.agb_get_stream(self.h, C.byref(s)))
         return s.value or 0
 
+    # ---- device-resident driver loop
+    def integrator_init(self, eta, min_ts, max_ts, H0, e0):
+        capi.check(self.h, self.lib.agb_integrator_init(self.h, float(eta), float(min_ts), float(max_ts), float(H0), float(e0)))
+
+    def integrator_assign_all(self):
+        capi.check(self.h, self.lib.agb_integrator_assign_all(self.h))
+
+    def step_begin(self):
+        t = C.c_double()
+        capi.check(self.h, self.lib.agb_step_begin(self.h, C.byref(t)))
+        return t.value
+
+    def step_end(self):
+        capi.check(self.h, self.lib.agb_step_end(self.h))
+
+    def state(self):
+        names = ("x", "y", "z", "vx", "vy", "vz", "U", "next_time", "timeStep")
+        out = {k: np.empty(self.n) for k in names}
+        capi.check(self.h, self.lib.agb_get_state(self.h, *[capi.dptr(out[k]) for k in names]))
+        return out
+
     def microbench(self, kind):
         """0: FP64 FMA TFLOP/s, 1: FP32 FMA TFLOP/s, 2: HBM copy GB/s (measured, not part of the path)."""
         v = C.c_double()
