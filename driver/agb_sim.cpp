@@ -5,7 +5,8 @@
 //   * Config.ini: flat `key = value`, '#' comments, unknown key => hard error, same keys as
 //     DataManager::loadConfig (simulation/src/File/DataManager.cpp:1360-1415);
 //   * initial conditions: the reference's `.age` snapshots (DataManager.cpp:216-258 writer, :534-574 reader:
-//     40-byte header + 94 bytes per particle) or this repo's `.agp` test format;
+//     40-byte header + 94 bytes per particle), Gadget-2 SnapFormat-1 files as DataManager.cpp:811-1331 reads them
+//     (the reference's shipped examples), or this repo's `.agp` test format;
 //   * Simulation::init force evaluation (Physics/Simulation.cpp:101-139) and the KDK main loop of
 //     Simulation::run (:166-345) with Kick / Drift / Ueuler (Physics/TimeIntegration.cpp:10-41), the Hubble
 //     rescale (:330-332) and power-of-two individual time steps (:196-207, :222-232);
@@ -15,7 +16,7 @@
 // The force path itself is only reached through the C ABI (include/agb200.h); there is no CPU fallback.
 //
 //   agb_sim --config Config.ini [--input-root DIR] [--output-root DIR] [--steps K] [--device D] [--cores C]
-//           [--precision fp64|mixed] [--dump final.agp] [--overwrite] [--device-resident]
+//           [--precision fp64|mixed] [--dump final.agp] [--overwrite] [--device-resident] [--convert-only out.agp]
 // --device-resident keeps positions, velocities and results in HBM between steps (agb_integrator_* / agb_step_*):
 // only the scalar time crosses PCIe per step; state is copied back for snapshots and at the end.
 #include <algorithm>
@@ -147,6 +148,62 @@ bool save_age(const std::string& path, const Particles& p, int64_t count, double
     }
     fwrite(buf.data(), sizeof(AgeRecord), (size_t)count, f);
     fclose(f);
+    return true;
+}
+
+// Gadget-2 SnapFormat 1 as the reference reads it (DataManager.cpp:811-1331): 4-byte record markers around a 256-byte
+// header, POS, VEL, ID, [MASS if a populated type has massarr == 0], [U if there is gas]; floats; kpc, km/s, 1e10 Msun,
+// (km/s)^2.  Type map: 0 -> gas (2), 1 -> dark matter (3, halo), 2/4/5 -> star (1), 3 -> star (1, bulge).  Like the
+// reference, an existing MASS block is indexed by the running particle number.
+struct GadgetHeader {
+    uint32_t npart[6]; double massarr[6]; double time, redshift; int32_t flag_sfr, flag_feedback; uint32_t npartTotal[6];
+    int32_t flag_cooling, num_files; double BoxSize, Omega0, OmegaLambda, HubbleParam; int32_t flag_stellarage, flag_metals;
+    uint32_t npartTotalHighWord[6]; int32_t flag_entropy_instead_u; char fill[60];
+};
+static_assert(sizeof(GadgetHeader) == 256, "gadget header");
+
+template <class T> bool read_block(FILE* f, std::vector<T>& v, size_t want_items)
+{
+    uint32_t a = 0, b = 0;
+    if (fread(&a, 4, 1, f) != 1) return false;
+    v.assign(std::max(want_items, (size_t)a / sizeof(T)), T());
+    if (a && fread(v.data(), 1, a, f) != a) return false;
+    if (fread(&b, 4, 1, f) != 1 || a != b) return false;
+    return true;
+}
+
+bool load_gadget(const std::string& path, Particles& p)
+{
+    constexpr double KPC = 3.08567758149137e19, MSUN = 1.98847e30;
+    FILE* f = fopen(path.c_str(), "rb");
+    if (!f) { perror(path.c_str()); return false; }
+    uint32_t a = 0, b = 0;
+    GadgetHeader h;
+    if (fread(&a, 4, 1, f) != 1 || fread(&h, sizeof(h), 1, f) != 1 || fread(&b, 4, 1, f) != 1 || a != sizeof(h)) { fclose(f); return false; }
+    size_t total = 0;
+    for (int i = 0; i < 6; i++) total += h.npart[i];
+    std::vector<float> pos, vel, mass, u; std::vector<uint32_t> ids;
+    bool ok = read_block(f, pos, total * 3) && read_block(f, vel, total * 3) && read_block(f, ids, total);
+    bool individual = false;
+    for (int i = 0; i < 6 && !individual; i++) if (h.massarr[i] < 1e-10f && h.npart[i] != 0) individual = true;
+    if (ok && individual) ok = read_block(f, mass, total);
+    if (ok && h.npart[0] > 0) ok = read_block(f, u, h.npart[0]);
+    fclose(f);
+    if (!ok) { fprintf(stderr, "malformed gadget file %s\n", path.c_str()); return false; }
+    p.resize((int64_t)total);
+    size_t cur = 0, gas = 0;
+    for (int type = 0; type < 6; type++)
+        for (uint32_t k = 0; k < h.npart[type]; k++, cur++) {
+            p.id[cur] = ids[cur];
+            if (type == 1) { p.type[cur] = 3; p.galaxyPart[cur] = 3; }
+            else if (type == 3) { p.type[cur] = 1; p.galaxyPart[cur] = 2; }
+            else if (type == 0) { p.type[cur] = 2; p.galaxyPart[cur] = 1; }
+            else { p.type[cur] = 1; p.galaxyPart[cur] = 1; }
+            p.mass[cur] = individual ? mass[cur] * MSUN * 1e10 : h.massarr[type] * MSUN * 1e10;
+            p.x[cur] = (double)pos[3 * cur] * KPC; p.y[cur] = (double)pos[3 * cur + 1] * KPC; p.z[cur] = (double)pos[3 * cur + 2] * KPC;
+            p.vx[cur] = (double)vel[3 * cur] * KMS; p.vy[cur] = (double)vel[3 * cur + 1] * KMS; p.vz[cur] = (double)vel[3 * cur + 2] * KMS;
+            if (type == 0) p.U[cur] = u[gas++] * 1e6;
+        }
     return true;
 }
 
@@ -390,8 +447,10 @@ int main(int argc, char** argv)
     if (!load_config(opt.count("config") ? opt["config"] : "../Config.ini", d.cfg)) return 2;
     const std::string inroot = opt.count("input-root") ? opt["input-root"] : "../../input_data/";
     const std::string inpath = inroot + (inroot.empty() || inroot.back() == '/' ? "" : "/") + d.cfg.inputPath;
-    bool ok = d.cfg.inputDataFormat == "age" ? load_age(inpath, d.p) : d.cfg.inputDataFormat == "agp" ? load_agp(inpath, d.p) : false;
-    if (!ok) { fprintf(stderr, "cannot read initial conditions %s (format %s; supported: age, agp)\n", inpath.c_str(), d.cfg.inputDataFormat.c_str()); return 2; }
+    bool ok = d.cfg.inputDataFormat == "age" ? load_age(inpath, d.p) : d.cfg.inputDataFormat == "agp" ? load_agp(inpath, d.p) :
+              d.cfg.inputDataFormat == "gadget" ? load_gadget(inpath, d.p) : false;
+    if (!ok) { fprintf(stderr, "cannot read initial conditions %s (format %s; supported: age, agp, gadget)\n", inpath.c_str(), d.cfg.inputDataFormat.c_str()); return 2; }
+    if (opt.count("convert-only")) return save_agp(opt["convert-only"], d.p) ? 0 : 2;      // no GPU involved
     if ((int64_t)d.cfg.numberOfParticles != d.p.n) {                     // Simulation.cpp:92-98
         fprintf(stderr, "Error: Number of particles in the ConfigFile (%lld) does not match the data file (%lld).\n", (long long)d.cfg.numberOfParticles, (long long)d.p.n);
         return 2;

@@ -108,3 +108,25 @@ def test_driver_multi_step_gpu(oracle, pkg, precision, resident):
     gas = p["type"] == 2
     assert np.array_equal(raw[4][gas], want["h"][gas])                                # density groups identical after 6 steps
     assert np.allclose(got["U"][gas], want["U"][gas], rtol=1e-6 if precision == "mixed" else 1e-12, atol=0)
+
+
+@pytest.mark.parametrize("name,rel", [("gassphere", "Example/gassphere_littleendian.dat"), ("galic22k", "Example/galiC_M1_22k.dat")])
+def test_gadget_reader_matches_reference_loader(name, rel):
+    """CPU: the driver's Gadget reader against the arrays the reference's own DataManager::loadICs produced (golden in_*)."""
+    src = os.path.join("/root/reference/input_data", rel)
+    if not os.path.exists(src):
+        pytest.skip("reference example ICs are only present in the build container")
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from conftest import load_golden
+    from oracle import agio
+    b = ensure_bin()
+    p, _, _ = load_golden(name)
+    with tempfile.TemporaryDirectory() as d:
+        cfg = os.path.join(d, "Config.ini")
+        open(cfg, "w").write("numberOfParticles = %d\ninputPath = %s\ninputDataFormat = gadget\n" % (len(p["x"]), rel))
+        out = os.path.join(d, "ic.agp")
+        r = subprocess.run([b, "--config", cfg, "--input-root", "/root/reference/input_data", "--convert-only", out], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        got = agio.read_agp(out)
+    for k in ("x", "y", "z", "vx", "vy", "vz", "mass", "U", "type"):
+        assert np.array_equal(got[k], p[k]), k
