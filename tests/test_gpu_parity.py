@@ -186,6 +186,69 @@ def test_direct_sum_bound_gpu(pkg, ctxs):
     assert np.mean(err) < 5e-2, np.mean(err)
 
 
+def _lattice(pkg, k):
+    """k^3 lattice centred on the origin (odd k: particles ON the root's split planes, one AT the root centre), equal masses:
+    node centres of mass coincide with particles (r == 0 rule, Node.cpp:274) and octant ties hit the strict '>' (Node.cpp:713-716)."""
+    g = (np.arange(k) - (k - 1) / 2.0) * 1.0e20
+    X, Y, Z = np.meshgrid(g, g, g, indexing="ij")
+    n = k ** 3
+    p = pkg.ics.plummer(n, seed=1)
+    p["x"], p["y"], p["z"] = X.ravel().copy(), Y.ravel().copy(), Z.ravel().copy()
+    p["vx"][:] = 0; p["vy"][:] = 0; p["vz"][:] = 0
+    return p
+
+
+@pytest.mark.parametrize("mixed", PRECISIONS)
+@pytest.mark.parametrize("k,cores", [(9, 1), (9, 8), (16, 1)])
+def test_lattice_split_planes_and_coincident_com(pkg, oracle, ctxs, k, cores, mixed):
+    p = _lattice(pkg, k)
+    ctx = ctxs(cores, mixed)
+    got = run_gpu(pkg, ctx, p, 0.5, 1e18, 1e40)
+    want = oracle.run(p, 0.5, 1e18, 1e40, 0.0, cores)
+    rep = compare(got, want, p, ctx)
+    print("lattice", k, cores, rep)
+    for key in ("leafdepth_mismatch", "key_mismatch", "node_topology_mismatch", "node_nchild_mismatch"):
+        assert rep[key] == 0, (key, rep)
+    # On an exact lattice many opening tests are exact ties (r == 2 radius) that the reference breaks by the last bits of ITS
+    # centre-of-mass sums (caller-order left folds); the tree-order sums here differ in those bits, so a few targets open a
+    # node the reference accepts or vice versa (DESIGN.md, known divergences).  Everything else must agree.
+    tc = ctx.target_counters()
+    same = (tc["visits"] == want["visits"]) & (tc["acc_nodes"] == want["acc_nodes"]) & (tc["acc_leaves"] == want["acc_leaves"])
+    assert same.mean() > 0.95, same.mean()
+    a = np.sqrt(want["ax"] ** 2 + want["ay"] ** 2 + want["az"] ** 2)
+    err = np.sqrt((got["ax"] - want["ax"]) ** 2 + (got["ay"] - want["ay"]) ** 2 + (got["az"] - want["az"]) ** 2)
+    scale = np.median(a[a > 0])                           # a lattice is full of cancellations: use the typical acceleration
+    assert np.max(err[same]) <= (1e-6 if mixed else 1e-12) * scale
+    assert np.max(err[~same]) <= 5e-2 * scale if (~same).any() else True     # a flipped tie costs at most the tree's own error
+
+
+def test_coincident_particles_are_an_error(pkg, ctxs):
+    """Two particles at the same position: the reference recurses until the stack overflows (Node.cpp:618-666); here AGB_ERR_DEPTH."""
+    ctx = ctxs(8)
+    p = pkg.ics.plummer(1000, seed=17)
+    p["x"][10], p["y"][10], p["z"][10] = p["x"][500], p["y"][500], p["z"][500]
+    ctx.set_particles(p)
+    with pytest.raises(pkg.capi.AgbError) as ei:
+        ctx.build_tree()
+    assert ei.value.status == 4
+    with pytest.raises(pkg.capi.AgbError):
+        ctx.forces(0.0, 1e18, 0.5)                                    # no usable tree
+
+
+@pytest.mark.parametrize("theta", [0.0, 1.5])
+def test_extreme_opening_angles(pkg, oracle, ctxs, theta):
+    """theta = 0: nothing is ever accepted, the walk degenerates to a direct sum over leaves; theta = 1.5: beyond the reference's
+    recommended maximum, even the root is accepted by distant targets."""
+    ctx = ctxs(8, False)
+    p = pkg.ics.plummer(3000, seed=18, gas_fraction=0.2)
+    mh = pkg.ics.gas_mass_in_h(p, 16)
+    got = run_gpu(pkg, ctx, p, theta, 1e18, mh)
+    want = oracle.run(p, theta, 1e18, mh, 0.0, 8)
+    rep = compare(got, want, p, ctx)
+    print("theta", theta, rep)
+    assert_parity(rep)
+
+
 def test_unsupported_small_softening(pkg, ctxs):
     ctx = ctxs(8)
     p = pkg.ics.plummer(100, seed=16)
