@@ -324,6 +324,7 @@ __global__ void __launch_bounds__(WALK_TPB, WALK_CTAS) k_walk(const WalkParams P
                     sp -= cnt;
                     int2 e = make_int2(-1, 0);
                     if (lane < cnt) e = stack_get(sp + lane);
+                    __syncwarp();                                            // the slots just read are overwritten by this round's pushes
                     if (sp + cnt > SCAP) tot_spill += 1;
                     int outcome = OUT_NONE;
                     double rad2 = 0, pmx = 0, pmy = 0, pmz = 0;
@@ -640,6 +641,7 @@ __global__ void __launch_bounds__(WALK_TPB, WALK_CTAS) k_walk(const WalkParams P
                     }
                 }
                 lc = 0;
+                __syncwarp();                                                // the list is rewritten by the next import / round
                 if (sp == 0 && cpos >= n_fl) break;
             }
         }
