@@ -65,7 +65,7 @@ void free_pool(agb_ctx* c)
     dfree(d.child); dfree(d.nfirst); dfree(d.nlast); dfree(d.nparent); dfree(d.arrived); dfree(d.ndepth);
     dfree(d.nmark); dfree(d.ndup); dfree(d.leafmark); dfree(d.mom_pm); dfree(d.mom_gv); dfree(d.grouplist); dfree(d.gasrank);
     dfree(d.rec); dfree(d.blockhist); dfree(d.scanblk);
-    dfree(d.far_list); dfree(d.far_front); dfree(d.far_cnt);
+    dfree(d.far_list); dfree(d.far_front); dfree(d.far_cnt); dfree(d.act_list);
     dfree(d.c_visits); dfree(d.c_accn); dfree(d.c_accl); dfree(d.c_sph);
     d.cap = 0;
 }
@@ -91,6 +91,7 @@ int ensure_pool(agb_ctx* c, int64_t n)
         int lcap, fcap, tg; agb_far_capacity(&lcap, &fcap, &tg);
         const size_t nsg = cap / (size_t)tg + 2;
         CK(dalloc(d.far_list, nsg * lcap)); CK(dalloc(d.far_front, nsg * fcap)); CK(dalloc(d.far_cnt, nsg * 3));
+        CK(dalloc(d.act_list, cap));
     }
     for (auto& q : c->in_d) CK(dalloc(q, cap));
     CK(dalloc(c->timestep, cap));
@@ -344,20 +345,18 @@ int agb_forces_slice(agb_ctx* c, double global_time, double e0, double theta, in
     AgbDev& d = c->d;
     if (d.n == 0) { c->forces_done = true; return AGB_OK; }
     if (c->target_counters) { int rc = ensure_counters(c); if (rc) return rc; }
-    // slice boundaries fall on multiples of 256 (the far-field super-groups) so that every warp owns the same 32 targets and
-    // every super-group the same 256 whatever the number of
-    // parts: results are then bit-identical for 1, 2, 4, 8 GPUs (same groups => same summation order)
-    const int64_t ngrp = (d.n + 255) / 256;
-    const int64_t t0 = std::min(d.n, ngrp * part / nparts * 256), t1 = std::min(d.n, ngrp * (part + 1) / nparts * 256);
+    // The targets are the ACTIVE particles in tree order; slice boundaries fall on multiples of 256 of them (the far-field
+    // super-groups), so every warp owns the same 32 targets whatever the number of parts: results are bit-identical for
+    // 1, 2, 4, 8 GPUs (same groups => same summation order).  The slicing itself happens on the device (agb_walk.cu).
     CK(cudaEventRecord(c->ev[6], c->st));
     // gas targets need h/rho/P: if the caller skipped gas_density they are orphans (h = 0) and get no SPH, like the reference
-    c->launches += agb_launch_walk(d, c->s, global_time, e0, theta, t0, t1, c->target_counters, c->hs.any_gas != 0, c->mixed, c->sm_count, c->st, c->ev[0], c->ev[1]);
+    c->launches += agb_launch_walk(d, c->s, global_time, e0, theta, part, nparts, c->target_counters, c->hs.any_gas != 0, c->mixed, c->sm_count, c->st, c->ev[0], c->ev[1]);
     CK(cudaEventRecord(c->ev[7], c->st));
     CK(cudaGetLastError());
     int rc = fetch_scalars(c);
     if (rc) return rc;
     float ms = 0;
-    if (t1 > t0 && cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]) == cudaSuccess) c->phase_ms[3] = ms;
+    if (cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]) == cudaSuccess) c->phase_ms[3] = ms;
     if (cudaEventElapsedTime(&ms, c->ev[6], c->ev[7]) == cudaSuccess) c->phase_ms[4] = ms;
     if (c->vis_timed && cudaEventElapsedTime(&ms, c->ev[2], c->ev[3]) == cudaSuccess) c->phase_ms[1] = ms;
     if (c->gas_timed && cudaEventElapsedTime(&ms, c->ev[4], c->ev[5]) == cudaSuccess) c->phase_ms[2] = ms;

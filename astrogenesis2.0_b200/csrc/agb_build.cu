@@ -440,8 +440,9 @@ __device__ __forceinline__ int block_excl_scan(int v, int* total)
     return off + inc - v;
 }
 
-__global__ void __launch_bounds__(TPB) k_scan_reduce(const int32_t* __restrict__ in, int64_t n, int32_t* __restrict__ blk)
+__global__ void __launch_bounds__(TPB) k_scan_reduce(const int32_t* __restrict__ in, int64_t n, int32_t* __restrict__ blk, const int32_t* skip_if_n)
 {
+    if (skip_if_n && *skip_if_n == n) return;
     int64_t base = (int64_t)blockIdx.x * SCAN_TILE + threadIdx.x * 8;
     int v = 0;
 #pragma unroll
@@ -451,8 +452,9 @@ __global__ void __launch_bounds__(TPB) k_scan_reduce(const int32_t* __restrict__
     if (threadIdx.x == 0) blk[blockIdx.x] = tot;
 }
 
-__global__ void __launch_bounds__(TPB) k_scan_blocks(int32_t* __restrict__ blk, int nb, int32_t* total_out)
+__global__ void __launch_bounds__(TPB) k_scan_blocks(int32_t* __restrict__ blk, int nb, int32_t* total_out, const int32_t* skip_if_n, int64_t n)
 {
+    if (skip_if_n && *skip_if_n == n) return;
     __shared__ int carry;
     if (threadIdx.x == 0) carry = 0;
     __syncthreads();
@@ -469,8 +471,9 @@ __global__ void __launch_bounds__(TPB) k_scan_blocks(int32_t* __restrict__ blk, 
     if (threadIdx.x == 0) *total_out = carry;
 }
 
-__global__ void __launch_bounds__(TPB) k_scan_apply(const int32_t* __restrict__ in, int64_t n, const int32_t* __restrict__ blk, int32_t* __restrict__ out)
+__global__ void __launch_bounds__(TPB) k_scan_apply(const int32_t* __restrict__ in, int64_t n, const int32_t* __restrict__ blk, int32_t* __restrict__ out, const int32_t* skip_if_n)
 {
+    if (skip_if_n && *skip_if_n == n) return;
     int64_t base = (int64_t)blockIdx.x * SCAN_TILE + threadIdx.x * 8;
     int v[8], sum = 0;
 #pragma unroll
@@ -757,9 +760,9 @@ int agb_launch_links(AgbDev& d, AgbScalars* s, cudaStream_t st)
     k_gather<<<nb, TPB, 0, st>>>(d, d.perm[d.cur], s);
     k_lcp<<<nb, TPB, 0, st>>>(khi, klo, d.n, d.lcp, d.nodecnt, s);
     const int sb = nblk(d.n, SCAN_TILE);
-    k_scan_reduce<<<sb, TPB, 0, st>>>(d.nodecnt, d.n, d.scanblk);
-    k_scan_blocks<<<1, TPB, 0, st>>>(d.scanblk, sb, &s->n_nodes);
-    k_scan_apply<<<sb, TPB, 0, st>>>(d.nodecnt, d.n, d.scanblk, d.nodebase);
+    k_scan_reduce<<<sb, TPB, 0, st>>>(d.nodecnt, d.n, d.scanblk, nullptr);
+    k_scan_blocks<<<1, TPB, 0, st>>>(d.scanblk, sb, &s->n_nodes, nullptr, d.n);
+    k_scan_apply<<<sb, TPB, 0, st>>>(d.nodecnt, d.n, d.scanblk, d.nodebase, nullptr);
     k_init_nodes<<<nb, TPB, 0, st>>>(d, s);
     k_links<<<nb, TPB, 0, st>>>(d, khi, klo, s);
     k_upward<<<nb, TPB, 0, st>>>(d, s);
@@ -768,12 +771,13 @@ int agb_launch_links(AgbDev& d, AgbScalars* s, cudaStream_t st)
     return 10;
 }
 
-int agb_launch_scan_i32(const int32_t* in, int32_t* out, int64_t n, int32_t* blk, int32_t* total_out, cudaStream_t st)
+// skip_if_n (device, optional): the three kernels return at once when *skip_if_n == n (nothing to compact)
+int agb_launch_scan_i32(const int32_t* in, int32_t* out, int64_t n, int32_t* blk, int32_t* total_out, cudaStream_t st, const int32_t* skip_if_n)
 {
     const int sb = nblk(n, SCAN_TILE);
-    k_scan_reduce<<<sb, TPB, 0, st>>>(in, n, blk);
-    k_scan_blocks<<<1, TPB, 0, st>>>(blk, sb, total_out);
-    k_scan_apply<<<sb, TPB, 0, st>>>(in, n, blk, out);
+    k_scan_reduce<<<sb, TPB, 0, st>>>(in, n, blk, skip_if_n);
+    k_scan_blocks<<<1, TPB, 0, st>>>(blk, sb, total_out, skip_if_n, n);
+    k_scan_apply<<<sb, TPB, 0, st>>>(in, n, blk, out, skip_if_n);
     return 3;
 }
 

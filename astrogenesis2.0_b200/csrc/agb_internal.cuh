@@ -59,6 +59,7 @@ struct AgbDev {
     int2* spill = nullptr; int64_t spill_per_warp = 0; int spill_warps = 0;
     // far-field prepass output, per super-group of 256 targets
     int32_t *far_list = nullptr, *far_front = nullptr, *far_cnt = nullptr;
+    int32_t* act_list = nullptr;       // tree positions of the active targets of the current forces call
 };
 
 // Device-resident scalars of one step (read back in a single copy when the host needs them).
@@ -73,7 +74,7 @@ struct AgbScalars {
     int32_t bintotal[256];
     int32_t vis_level;
     int32_t walk_overflow, any_gas;
-    int32_t n_gas_total, tie_exact, tie_unresolved, n_fold, n_long_runs;
+    int32_t n_gas_total, tie_exact, tie_unresolved, n_fold, n_long_runs, n_scan_tmp;
     unsigned long long st_rounds, st_popped, st_mixed, st_open, st_drain;   // walk statistics (tuning)
 };
 
@@ -98,10 +99,10 @@ int agb_launch_sort(AgbDev& d, AgbScalars* s, cudaStream_t st);
 int agb_launch_links(AgbDev& d, AgbScalars* s, cudaStream_t st);
 int agb_launch_visual(AgbDev& d, AgbScalars* s, double radius, cudaStream_t st);
 int agb_launch_gas_density(AgbDev& d, AgbScalars* s, double massInH, cudaStream_t st);
-int agb_launch_walk(AgbDev& d, AgbScalars* s, double globalTime, double e0, double theta, int64_t t0, int64_t t1,
+int agb_launch_walk(AgbDev& d, AgbScalars* s, double globalTime, double e0, double theta, int part, int nparts,
                     bool counters, bool any_gas, bool mixed, int sm_count, cudaStream_t st, cudaEvent_t ev0, cudaEvent_t ev1);
 int agb_launch_dump_tree(AgbDev& d, AgbScalars* s, int32_t* leafdepth, uint64_t* khi, uint64_t* klo, cudaStream_t st);
-int agb_launch_scan_i32(const int32_t* in, int32_t* out, int64_t n, int32_t* blk, int32_t* total_out, cudaStream_t st);
+int agb_launch_scan_i32(const int32_t* in, int32_t* out, int64_t n, int32_t* blk, int32_t* total_out, cudaStream_t st, const int32_t* skip_if_n = nullptr);
 int agb_launch_microbench(int kind, int sm_count, cudaStream_t st, double* result);
 int agb_launch_unpermute_counters(AgbDev& d, int32_t* v, int32_t* an, int32_t* al, int32_t* sp, cudaStream_t st);
 

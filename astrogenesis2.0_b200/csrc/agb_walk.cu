@@ -75,8 +75,9 @@ struct WalkParams {
     int2* spill; int64_t spill_per_warp;
     int32_t *far_list, *far_front, *far_cnt;   // per super-group (256 targets): shared accept list, hand-over frontier, {n_list, n_front, n_visits}
     AgbScalars* s;
-    int64_t N, t0, t1;
-    unsigned ngroups;
+    int64_t N;
+    const int32_t* act_list;                 // tree positions of the active targets (unused when every particle is active)
+    int part, nparts;                        // this call walks the part-th of nparts slices of the active targets
     double theta, e0, globalTime;
 };
 
@@ -101,6 +102,19 @@ constexpr int FAR_LCAP = 4096, FAR_FCAP = 2048, FAR_SCAP = 1024;
 
 struct Box { double lox, loy, loz, hix, hiy, hiz; };
 
+// The targets of a call: the active particles (Tree.cpp:75) in tree order, compacted, cut into `nparts` slices whose
+// boundaries are multiples of 256 (one far-field super-group) so that groups are the same for any number of GPUs.
+struct Slice { int64_t a0, a1; bool ident; };
+__device__ __forceinline__ Slice target_slice(const WalkParams& P)
+{
+    const int64_t na = P.s->n_active, nsg = (na + 32 * SG_GROUPS - 1) / (32 * SG_GROUPS);
+    Slice sl;
+    sl.a0 = min(na, nsg * P.part / P.nparts * (32 * SG_GROUPS));
+    sl.a1 = min(na, nsg * (P.part + 1) / P.nparts * (32 * SG_GROUPS));
+    sl.ident = na == P.N;
+    return sl;
+}
+
 // Opening test of a node against a box of targets: ACCEPT / OPEN only when every point of the box takes the same
 // decision as the reference's `radius / r < theta` (Node.cpp:331-334) with a 1e-12 margin; r == 0 is impossible
 // for OPEN because the COM must lie outside the box.
@@ -121,7 +135,7 @@ __device__ __forceinline__ int classify_box(const double4& pm, double rad2, cons
 // target opens are descended here, and nodes that straddle the opening radius of the big box are handed over to the
 // per-warp walks (k_walk) as their starting frontier.  The upper tree is thus traversed once per 256 targets
 // instead of once per 32, and the shared entries are evaluated with full lane masks.
-__global__ void __launch_bounds__(128) k_far(const WalkParams P, int nsg, int64_t sg_first)
+__global__ void __launch_bounds__(128) k_far(const WalkParams P)
 {
     __shared__ int stack_s[4][FAR_SCAP];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -133,16 +147,18 @@ __global__ void __launch_bounds__(128) k_far(const WalkParams P, int nsg, int64_
     const double theta2 = P.theta * P.theta;
     const bool fast_mac = P.theta > 0.0;
     const double inf = __longlong_as_double(0x7ff0000000000000ll);
+    const Slice sl = target_slice(P);
+    const int nsg = (int)((sl.a1 - sl.a0 + 32 * SG_GROUPS - 1) / (32 * SG_GROUPS));
     for (int sgi = blockIdx.x * 4 + warp; sgi < nsg; sgi += gridDim.x * 4) {
-        const int64_t tb = (sg_first + sgi) * (32 * SG_GROUPS);
+        const int64_t tb = sl.a0 + (int64_t)sgi * (32 * SG_GROUPS);
         int32_t* const fl = P.far_list + (size_t)sgi * FAR_LCAP;
         int32_t* const ff = P.far_front + (size_t)sgi * FAR_FCAP;
         Box b{inf, inf, inf, -inf, -inf, -inf};
         for (int j = 0; j < SG_GROUPS; j++) {
-            const int64_t t = tb + j * 32 + lane;
-            if (t >= P.t0 && t < P.t1) {
-                const double4 tp = P.src_pm[t];
-                if (P.s_next[t] == P.globalTime && tp.w != 0.0) {
+            const int64_t idx = tb + j * 32 + lane;
+            if (idx < sl.a1) {
+                const double4 tp = P.src_pm[sl.ident ? idx : (int64_t)P.act_list[idx]];
+                if (tp.w != 0.0) {
                     b.lox = fmin(b.lox, tp.x); b.loy = fmin(b.loy, tp.y); b.loz = fmin(b.loz, tp.z);
                     b.hix = fmax(b.hix, tp.x); b.hiy = fmax(b.hiy, tp.y); b.hiz = fmax(b.hiz, tp.z);
                 }
@@ -209,7 +225,7 @@ __global__ void __launch_bounds__(128) k_far(const WalkParams P, int nsg, int64_
 }
 
 template <bool COUNT, bool SPH, bool MIXED>
-__global__ void __launch_bounds__(WALK_TPB, WALK_CTAS) k_walk(const WalkParams P, int64_t sg_first)
+__global__ void __launch_bounds__(WALK_TPB, WALK_CTAS) k_walk(const WalkParams P)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -221,6 +237,8 @@ __global__ void __launch_bounds__(WALK_TPB, WALK_CTAS) k_walk(const WalkParams P
     const int n_nodes = P.s->n_nodes, n_in_tree = P.s->n_in_tree;
     const double theta = P.theta, theta2 = theta * theta;
     const bool fast_mac = theta > 0.0;
+    const Slice sl = target_slice(P);
+    const unsigned ngroups = (unsigned)((sl.a1 - sl.a0 + 31) / 32);
     // the law is evaluated in units of R so that r^2 (r^2+e0^2)^2 cannot overflow for any unit system
     const double invR2 = R > 0.0 ? 1.0 / (R * R) : 1.0;
     const double e02s = P.e0 * P.e0 * invR2;
@@ -252,11 +270,12 @@ __global__ void __launch_bounds__(WALK_TPB, WALK_CTAS) k_walk(const WalkParams P
         unsigned g = 0;
         if (lane == 0) g = atomicAdd(&P.s->walk_next_group, 1u);
         g = __shfl_sync(0xffffffffu, g, 0);
-        if (g >= P.ngroups) break;
-        const int64_t t = P.t0 + (int64_t)g * 32 + lane;
-        const bool inrange = t < P.t1;
+        if (g >= ngroups) break;
+        const int64_t idx = sl.a0 + (int64_t)g * 32 + lane;
+        const bool inrange = idx < sl.a1;
+        const int64_t t = !inrange ? -1 : sl.ident ? idx : (int64_t)P.act_list[idx];
         const double4 tp = inrange ? P.src_pm[t] : make_double4(0, 0, 0, 0);
-        const bool active = inrange && (P.s_next[t] == P.globalTime);           // Tree.cpp:75
+        const bool active = inrange;                                            // the list only holds active targets (Tree.cpp:75)
         const bool valid = active && tp.w != 0.0;                               // Node.cpp:265
         // per-target SPH constants (the reference overrides h_j, rho_j, P_j with the target's, Node.cpp:94,101,108)
         bool tgas = false;
@@ -276,6 +295,7 @@ __global__ void __launch_bounds__(WALK_TPB, WALK_CTAS) k_walk(const WalkParams P
         double ax = 0, ay = 0, az = 0, dU = 0;
         int c_vis = (active && (n_nodes > 0 || !valid)) ? 1 : 0, c_an = 0, c_al = 0, c_sp = 0;              // the root call itself
         const unsigned vmask = __ballot_sync(0xffffffffu, valid);
+        const int tmin = __shfl_sync(0xffffffffu, (int)t, 0), tmax = __reduce_max_sync(0xffffffffu, (int)t);   // targets are sorted by tree position
         const bool wgas = SPH && __any_sync(0xffffffffu, tgas && h_t > 0.0);   // any target of this warp that can feel SPH at all
 
         if (vmask) {
@@ -296,12 +316,12 @@ __global__ void __launch_bounds__(WALK_TPB, WALK_CTAS) k_walk(const WalkParams P
                 hh4cf = hh4sf * (1.0f + 1e-5f);                            // generous: the SPH pass decides
                 if (SPH && tgas) {
                     float* tf = reinterpret_cast<float*>(&sm.tsph[3 * lane + 2]);
-                    tf[0] = nth_x.x; tf[1] = nth_y.x; tf[2] = nth_z.x; tf[3] = ntl_x.x; tf[4] = ntl_y.x; tf[5] = ntl_z.x; tf[6] = hh4sf; tf[7] = 0.f;
+                    tf[0] = nth_x.x; tf[1] = nth_y.x; tf[2] = nth_z.x; tf[3] = ntl_x.x; tf[4] = ntl_y.x; tf[5] = ntl_z.x; tf[6] = hh4sf; tf[7] = __int_as_float((int)t);
                 }
             }
             const Box wb{lox, loy, loz, hix, hiy, hiz};
             // start from what the far-field prepass left for this super-group: a shared accept list and a frontier
-            const int64_t sgi = (P.t0 / 32 + (int64_t)g) / SG_GROUPS - sg_first;
+            const int64_t sgi = (int64_t)g / SG_GROUPS;
             const int32_t* const fl = P.far_list + (size_t)sgi * FAR_LCAP;
             const int32_t* const ff = P.far_front + (size_t)sgi * FAR_FCAP;
             const int n_fl = P.far_cnt[3 * sgi], n_ff = P.far_cnt[3 * sgi + 1];
@@ -435,6 +455,7 @@ __global__ void __launch_bounds__(WALK_TPB, WALK_CTAS) k_walk(const WalkParams P
                     const int cnt = min(32, lc - base);
                     __syncwarp();
                     bool src_gas = false;
+                    unsigned pc_mask = 0u; int ex_part = -1;
                     if (lane < cnt) {
                         const int2 e = sm.list[base + lane];
                         const double4 q = P.src_pm[e.x];
@@ -449,11 +470,14 @@ __global__ void __launch_bounds__(WALK_TPB, WALK_CTAS) k_walk(const WalkParams P
                         } else sm.stage[lane] = q;
                         if (SPH && wgas) { const double4 gvv = P.src_gv[e.x]; src_gas = gvv.w > 0.0; sm.gst[lane] = gvv; }   // independent of the load above
                         // accepted pairs of this entry: lanes in the mask, minus the target's own leaf, none for a massless leaf
-                        unsigned m = (unsigned)e.y;
-                        const int64_t self_lane = (int64_t)e.x - (P.t0 + (int64_t)g * 32);
-                        if (e.x < N && self_lane >= 0 && self_lane < 32) m &= ~(1u << self_lane);
-                        const unsigned pc = q.w != 0.0 ? __popc(m) : 0u;
-                        if (e.x < N) tot_leaf += pc; else tot_node += pc;
+                        pc_mask = q.w != 0.0 ? (unsigned)e.y : 0u;
+                        ex_part = e.x < N ? e.x : -1;
+                    }
+                    {   // a leaf that is one of this warp's own targets does not count as an interaction with itself
+                        const bool maybe = ex_part >= tmin && ex_part <= tmax;
+                        if (__any_sync(0xffffffffu, maybe))
+                            for (int l2 = 0; l2 < 32; l2++) { const int tl = __shfl_sync(0xffffffffu, (int)t, l2); if (ex_part >= 0 && ex_part == tl) pc_mask &= ~(1u << l2); }
+                        if (ex_part >= 0) tot_leaf += __popc(pc_mask); else tot_node += __popc(pc_mask);
                     }
                     if (MIXED && lane == cnt && (cnt & 1)) {
                         // odd tile: the unused half of the last pair must hold finite numbers (0 * inf would poison the sums)
@@ -558,7 +582,7 @@ __global__ void __launch_bounds__(WALK_TPB, WALK_CTAS) k_walk(const WalkParams P
                                     bool pass = live && r2s < hh4o;
                                     if (live && fabsf(r2s - hh4o) <= 4e-6f * hh4o) {
                                         // too close to the gate for FP32: the reference's own separately rounded FP64 expression
-                                        const double4 q = P.src_pm[e.x], ot = P.src_pm[P.t0 + (int64_t)g * 32 + owner];
+                                        const double4 q = P.src_pm[e.x], ot = P.src_pm[__float_as_int(tf[7])];
                                         const double dx = q.x - ot.x, dy = q.y - ot.y, dz = q.z - ot.z;
                                         const double r2e = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
                                         pass = __dsqrt_rn(r2e) < __dmul_rn(tv.w, 2.0);
@@ -652,8 +676,6 @@ __global__ void __launch_bounds__(WALK_TPB, WALK_CTAS) k_walk(const WalkParams P
             if (SPH && tgas && dU != 0.0) P.dUdt[p] += dU;
             if (COUNT) { P.c_visits[t] = c_vis; P.c_accn[t] = c_an; P.c_accl[t] = c_al; P.c_sph[t] = c_sp; }
             tot_visit += (unsigned long long)c_vis;
-        } else if (COUNT && inrange) {
-            P.c_visits[t] = 0; P.c_accn[t] = 0; P.c_accl[t] = 0; P.c_sph[t] = 0;
         }
     }
 
@@ -678,17 +700,32 @@ __global__ void k_walk_reset(AgbScalars* s)
     s->c_interactions = 0; s->c_node = 0; s->c_leaf = 0; s->c_sph = 0; s->c_visits = 0; s->c_exact = 0; s->c_spill = 0;
 }
 
-__global__ void k_count_active(const double* __restrict__ s_next, int64_t t0, int64_t t1, double gt, AgbScalars* s)
+// ---- active targets (Tree.cpp:75: globalTime == nextIntegrationTime), compacted in tree order
+__global__ void k_count_active(const double* __restrict__ s_next, int64_t n, double gt, AgbScalars* s)
 {
     __shared__ int cnt;
     if (threadIdx.x == 0) cnt = 0;
     __syncthreads();
     int local = 0;
-    for (int64_t i = t0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < t1; i += (int64_t)gridDim.x * blockDim.x) local += s_next[i] == gt;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) local += s_next[i] == gt;
     local = __reduce_add_sync(0xffffffffu, local);
     if ((threadIdx.x & 31) == 0 && local) atomicAdd(&cnt, local);
     __syncthreads();
     if (threadIdx.x == 0 && cnt) atomicAdd(&s->n_active, cnt);
+}
+// the three kernels below return at once when every particle is active (the list is then the identity and never read)
+__global__ void k_active_flags(const double* __restrict__ s_next, int64_t n, double gt, const AgbScalars* __restrict__ s, int32_t* __restrict__ flag)
+{
+    if (s->n_active == n) return;
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) flag[i] = s_next[i] == gt;
+}
+__global__ void k_active_compact(const double* __restrict__ s_next, int64_t n, double gt, const AgbScalars* __restrict__ s, const int32_t* __restrict__ rank,
+                                 int32_t* __restrict__ list)
+{
+    if (s->n_active == n) return;
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && s_next[i] == gt) list[rank[i]] = (int32_t)i;
 }
 
 __global__ void k_unpermute_i32(const uint32_t* __restrict__ perm, int64_t n, const int32_t* a, const int32_t* b, const int32_t* c, const int32_t* d_,
@@ -706,7 +743,7 @@ void launch_walk(const WalkParams& P, int blocks, cudaStream_t st)
     static bool attr_set = false;
     const int smem = (int)sizeof(WarpSmem) * WALK_WARPS;
     if (!attr_set) { cudaFuncSetAttribute(k_walk<COUNT, SPH, MIXED>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr_set = true; }
-    k_walk<COUNT, SPH, MIXED><<<blocks, WALK_TPB, smem, st>>>(P, P.t0 / (32 * SG_GROUPS));
+    k_walk<COUNT, SPH, MIXED><<<blocks, WALK_TPB, smem, st>>>(P);
 }
 template <bool COUNT, bool SPH>
 void launch_walk2(const WalkParams& P, int blocks, bool mixed, cudaStream_t st)
@@ -738,7 +775,7 @@ int agb_walk_blocks(int sm_count) { return sm_count * WALK_CTAS; }
 int agb_walk_warps_per_block() { return WALK_WARPS; }
 void agb_far_capacity(int* lcap, int* fcap, int* targets) { *lcap = FAR_LCAP; *fcap = FAR_FCAP; *targets = 32 * SG_GROUPS; }
 
-int agb_launch_walk(AgbDev& d, AgbScalars* s, double globalTime, double e0, double theta, int64_t t0, int64_t t1,
+int agb_launch_walk(AgbDev& d, AgbScalars* s, double globalTime, double e0, double theta, int part, int nparts,
                     bool counters, bool any_gas, bool mixed, int sm_count, cudaStream_t st, cudaEvent_t ev0, cudaEvent_t ev1)
 {
     WalkParams P;
@@ -748,22 +785,28 @@ int agb_launch_walk(AgbDev& d, AgbScalars* s, double globalTime, double e0, doub
     P.c_visits = d.c_visits; P.c_accn = d.c_accn; P.c_accl = d.c_accl; P.c_sph = d.c_sph;
     P.spill = d.spill; P.spill_per_warp = d.spill_per_warp;
     P.far_list = d.far_list; P.far_front = d.far_front; P.far_cnt = d.far_cnt;
-    P.s = s; P.N = d.n; P.t0 = t0; P.t1 = t1;
-    P.ngroups = (unsigned)((t1 - t0 + 31) / 32);
+    P.s = s; P.N = d.n; P.act_list = d.act_list; P.part = part; P.nparts = nparts;
     P.theta = theta; P.e0 = e0; P.globalTime = globalTime;
     int launches = 0;
+    const int nb = (int)((d.n + 255) / 256);
     k_walk_reset<<<1, 1, 0, st>>>(s); launches++;
-    if (t1 > t0) {
+    if (d.n > 0) {
         cudaMemsetAsync(&s->n_active, 0, sizeof(int32_t), st);
-        k_count_active<<<(int)std::min<int64_t>((t1 - t0 + 255) / 256, 4 * sm_count), 256, 0, st>>>(d.s_next, t0, t1, globalTime, s); launches++;
-        int blocks = (int)std::min<int64_t>((int64_t)agb_walk_blocks(sm_count), ((int64_t)P.ngroups + WALK_WARPS - 1) / WALK_WARPS);
+        k_count_active<<<std::min(nb, 4 * sm_count), 256, 0, st>>>(d.s_next, d.n, globalTime, s); launches++;
+        // compact list of the active targets (scratch: flags -> nodecnt, ranks -> nodebase; both are idle after the densities)
+        k_active_flags<<<nb, 256, 0, st>>>(d.s_next, d.n, globalTime, s, d.nodecnt); launches++;
+        launches += agb_launch_scan_i32(d.nodecnt, d.nodebase, d.n, d.scanblk, &s->n_scan_tmp, st, &s->n_active);
+        k_active_compact<<<nb, 256, 0, st>>>(d.s_next, d.n, globalTime, s, d.nodebase, d.act_list); launches++;
+        if (counters) {
+            cudaMemsetAsync(d.c_visits, 0, (size_t)d.n * 4, st); cudaMemsetAsync(d.c_accn, 0, (size_t)d.n * 4, st);
+            cudaMemsetAsync(d.c_accl, 0, (size_t)d.n * 4, st); cudaMemsetAsync(d.c_sph, 0, (size_t)d.n * 4, st);
+        }
+        const int64_t max_groups = (d.n / nparts + 32 * SG_GROUPS + 31) / 32;
+        int blocks = (int)std::min<int64_t>((int64_t)agb_walk_blocks(sm_count), (max_groups + WALK_WARPS - 1) / WALK_WARPS);
         if (blocks * WALK_WARPS > d.spill_warps) blocks = d.spill_warps / WALK_WARPS;
         if (ev0) cudaEventRecord(ev0, st);
-        {   // far-field prepass, one warp per super-group of 256 targets
-            const int64_t sg_first = t0 / (32 * SG_GROUPS);
-            const int nsg = (int)((t1 + 32 * SG_GROUPS - 1) / (32 * SG_GROUPS) - sg_first);
-            k_far<<<std::min((nsg + 3) / 4, sm_count * 8), 128, 0, st>>>(P, nsg, sg_first); launches++;
-        }
+        // far-field prepass, one warp per super-group of 256 targets
+        k_far<<<(int)std::min<int64_t>((max_groups / SG_GROUPS + 4) / 4, (int64_t)sm_count * 8), 128, 0, st>>>(P); launches++;
         if (counters) { if (any_gas) launch_walk2<true, true>(P, blocks, mixed, st); else launch_walk2<true, false>(P, blocks, mixed, st); }
         else { if (any_gas) launch_walk2<false, true>(P, blocks, mixed, st); else launch_walk2<false, false>(P, blocks, mixed, st); }
         if (ev1) cudaEventRecord(ev1, st);

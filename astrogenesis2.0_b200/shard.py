@@ -19,7 +19,8 @@ def shard_counts(n, world):
 
 
 def slice_bounds(n, part, nparts):
-    """Tree-order target slice walked by `part` — the rule agb_forces_slice applies (agb_api.cu)."""
+    """Slice of the (active, tree-ordered) targets walked by `part` — the rule agb_forces_slice applies on the device
+    (target_slice in agb_walk.cu); n = number of active targets."""
     ngrp = (n + GROUP - 1) // GROUP
     return min(n, ngrp * part // nparts * GROUP), min(n, ngrp * (part + 1) // nparts * GROUP)
 
