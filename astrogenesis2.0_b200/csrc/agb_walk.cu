@@ -475,7 +475,8 @@ __global__ void __launch_bounds__(WALK_TPB, WALK_CTAS) k_walk(const WalkParams P
                     }
                     {   // a leaf that is one of this warp's own targets does not count as an interaction with itself
                         const bool maybe = ex_part >= tmin && ex_part <= tmax;
-                        if (__any_sync(0xffffffffu, maybe))
+                        if (sl.ident) { if (maybe) pc_mask &= ~(1u << (ex_part - tmin)); }        // every particle active: lane = offset in the group
+                        else if (__any_sync(0xffffffffu, maybe))
                             for (int l2 = 0; l2 < 32; l2++) { const int tl = __shfl_sync(0xffffffffu, (int)t, l2); if (ex_part >= 0 && ex_part == tl) pc_mask &= ~(1u << l2); }
                         if (ex_part >= 0) tot_leaf += __popc(pc_mask); else tot_node += __popc(pc_mask);
                     }
