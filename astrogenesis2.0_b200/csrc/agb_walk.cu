@@ -28,8 +28,6 @@
 
 namespace {
 
-constexpr int WALK_WARPS = 8;
-constexpr int WALK_TPB = WALK_WARPS * 32;
 constexpr int LCAP = 512;                  // interaction-list entries per warp
 constexpr int LGROW = 288;                 // worst-case growth per pop round: 32 lanes x (8 leaves + 1 node)
 #ifndef AGB_WALK_CTAS_PER_SM
@@ -43,14 +41,20 @@ constexpr double kG = 6.67430e-11;         // Math/Constants.h:7
 constexpr double kPI = 3.14159265358979323846;
 constexpr double kGAMMA = 5.0 / 3.0;
 
-struct WarpSmem {
-    int2 list[LCAP];
-    int2 stack[SCAP];
-    double4 stage[32];                     // drain: the 32 sources of a tile; traversal: (COM, mass) of straddling nodes
+// Per-warp shared memory.  The SPH operands exist only in the SPH variants: the gravity-only kernels need 8 KB per warp
+// instead of 13 KB, which leaves ~100 KB of the SM for L1 (10 warps per CTA were tried: register spills cost more).
+template <bool SPH> struct SphSmem {
     double4 tsph[96];                      // per gas target: (1/h, 1/(pi h^4), 2 P/rho^2, sound speed), (vx, vy, vz, h), 8 floats: -(float-float position), (2h/R)^2
     double4 res[32];                       // SPH pair results (fx, fy, fz, dU) on their way to the owning lane
     double4 gst[32];                       // drain: (velocity | mVel, gasMass) of the tile's gas-bearing sources
 };
+template <> struct SphSmem<false> { double4 tsph[1], res[1], gst[1]; };
+template <bool SPH> struct WarpSmem : SphSmem<SPH> {
+    int2 list[LCAP];
+    int2 stack[SCAP];
+    double4 stage[32];                     // drain: the 32 sources of a tile; traversal: (COM, mass) of straddling nodes
+};
+template <bool SPH> struct WalkCfg { static constexpr int WARPS = 8, TPB = WARPS * 32; };
 
 // 1/sqrt(x) for positive normal x: MUFU.RSQ64H seed (~2^-22) + one cubically convergent step (~2^-60).
 // None of the special-case handling of the library rsqrt() is needed here (x = 0 is masked by the caller).
@@ -225,12 +229,12 @@ __global__ void __launch_bounds__(128) k_far(const WalkParams P)
 }
 
 template <bool COUNT, bool SPH, bool MIXED>
-__global__ void __launch_bounds__(WALK_TPB, WALK_CTAS) k_walk(const WalkParams P)
+__global__ void __launch_bounds__(WalkCfg<SPH>::TPB, WALK_CTAS) k_walk(const WalkParams P)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    WarpSmem& sm = reinterpret_cast<WarpSmem*>(smem_raw)[warp];
-    int2* const spill = P.spill + (size_t)(blockIdx.x * WALK_WARPS + warp) * P.spill_per_warp;
+    WarpSmem<SPH>& sm = reinterpret_cast<WarpSmem<SPH>*>(smem_raw)[warp];
+    int2* const spill = P.spill + (size_t)(blockIdx.x * WalkCfg<SPH>::WARPS + warp) * P.spill_per_warp;
     const unsigned lt = (1u << lane) - 1u;
     const int N = (int)P.N;
     const double R = __longlong_as_double((long long)P.s->Rbits);
@@ -739,17 +743,20 @@ __global__ void k_unpermute_i32(const uint32_t* __restrict__ perm, int64_t n, co
 }
 
 template <bool COUNT, bool SPH, bool MIXED>
-void launch_walk(const WalkParams& P, int blocks, cudaStream_t st)
+void launch_walk(const WalkParams& P, int64_t max_groups, int sm_count, int spill_warps, cudaStream_t st)
 {
     static bool attr_set = false;
-    const int smem = (int)sizeof(WarpSmem) * WALK_WARPS;
+    constexpr int WARPS = WalkCfg<SPH>::WARPS;
+    const int smem = (int)sizeof(WarpSmem<SPH>) * WARPS;
     if (!attr_set) { cudaFuncSetAttribute(k_walk<COUNT, SPH, MIXED>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr_set = true; }
-    k_walk<COUNT, SPH, MIXED><<<blocks, WALK_TPB, smem, st>>>(P);
+    int blocks = (int)std::min<int64_t>((int64_t)sm_count * WALK_CTAS, (max_groups + WARPS - 1) / WARPS);
+    if (blocks * WARPS > spill_warps) blocks = spill_warps / WARPS;
+    k_walk<COUNT, SPH, MIXED><<<blocks, WalkCfg<SPH>::TPB, smem, st>>>(P);
 }
 template <bool COUNT, bool SPH>
-void launch_walk2(const WalkParams& P, int blocks, bool mixed, cudaStream_t st)
+void launch_walk2(const WalkParams& P, int64_t max_groups, int sm_count, int spill_warps, bool mixed, cudaStream_t st)
 {
-    if (mixed) launch_walk<COUNT, SPH, true>(P, blocks, st); else launch_walk<COUNT, SPH, false>(P, blocks, st);
+    if (mixed) launch_walk<COUNT, SPH, true>(P, max_groups, sm_count, spill_warps, st); else launch_walk<COUNT, SPH, false>(P, max_groups, sm_count, spill_warps, st);
 }
 
 } // namespace
@@ -773,7 +780,7 @@ __global__ void __launch_bounds__(256) k_copy_peak(const double2* __restrict__ i
 }
 
 int agb_walk_blocks(int sm_count) { return sm_count * WALK_CTAS; }
-int agb_walk_warps_per_block() { return WALK_WARPS; }
+int agb_walk_warps_per_block() { return 8; }
 void agb_far_capacity(int* lcap, int* fcap, int* targets) { *lcap = FAR_LCAP; *fcap = FAR_FCAP; *targets = 32 * SG_GROUPS; }
 
 int agb_launch_walk(AgbDev& d, AgbScalars* s, double globalTime, double e0, double theta, int part, int nparts,
@@ -803,13 +810,11 @@ int agb_launch_walk(AgbDev& d, AgbScalars* s, double globalTime, double e0, doub
             cudaMemsetAsync(d.c_accl, 0, (size_t)d.n * 4, st); cudaMemsetAsync(d.c_sph, 0, (size_t)d.n * 4, st);
         }
         const int64_t max_groups = (d.n / nparts + 32 * SG_GROUPS + 31) / 32;
-        int blocks = (int)std::min<int64_t>((int64_t)agb_walk_blocks(sm_count), (max_groups + WALK_WARPS - 1) / WALK_WARPS);
-        if (blocks * WALK_WARPS > d.spill_warps) blocks = d.spill_warps / WALK_WARPS;
         if (ev0) cudaEventRecord(ev0, st);
         // far-field prepass, one warp per super-group of 256 targets
         k_far<<<(int)std::min<int64_t>((max_groups / SG_GROUPS + 4) / 4, (int64_t)sm_count * 8), 128, 0, st>>>(P); launches++;
-        if (counters) { if (any_gas) launch_walk2<true, true>(P, blocks, mixed, st); else launch_walk2<true, false>(P, blocks, mixed, st); }
-        else { if (any_gas) launch_walk2<false, true>(P, blocks, mixed, st); else launch_walk2<false, false>(P, blocks, mixed, st); }
+        if (counters) { if (any_gas) launch_walk2<true, true>(P, max_groups, sm_count, d.spill_warps, mixed, st); else launch_walk2<true, false>(P, max_groups, sm_count, d.spill_warps, mixed, st); }
+        else { if (any_gas) launch_walk2<false, true>(P, max_groups, sm_count, d.spill_warps, mixed, st); else launch_walk2<false, false>(P, max_groups, sm_count, d.spill_warps, mixed, st); }
         if (ev1) cudaEventRecord(ev1, st);
         launches++;
     }
