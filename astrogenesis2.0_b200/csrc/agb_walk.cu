@@ -176,6 +176,12 @@ __global__ void __launch_bounds__(128) k_far(const WalkParams P)
             else if (n_in_tree == 1) { if (lane == 0) fl[0] = 0; nl = 1; }
             __syncwarp();
             while (sp > 0) {
+                if (nl > FAR_LCAP - 32 * 9 || nf > FAR_FCAP - FAR_SCAP - 64) {
+                    // out of room (tiny opening angles): stop here and hand every pending node to the per-warp walks
+                    for (int i = lane; i < sp; i += 32) ff[nf + i] = stk[i];
+                    nf += sp; sp = 0;
+                    break;
+                }
                 const int cnt = min(sp, 32);
                 sp -= cnt;
                 const int node = lane < cnt ? stk[sp + lane] : -1;
@@ -188,8 +194,8 @@ __global__ void __launch_bounds__(128) k_far(const WalkParams P)
                     if (pm.w != 0.0) {
                         const double rad = scalbn(R, -(int)P.ndepth[node - N]);
                         outcome = classify_box(pm, rad * rad, b, theta2, fast_mac);
-                        // out of room in the shared list or the stack: leave the node (and all below it) to the per-warp walks
-                        if (outcome != OUT_MIXED && (nl > FAR_LCAP - 32 * 9 || sp > FAR_SCAP - 32 * 9)) outcome = OUT_MIXED;
+                        // out of room on the stack: leave the node (and all below it) to the per-warp walks
+                        if (outcome == OUT_OPEN && sp > FAR_SCAP - 32 * 9) outcome = OUT_MIXED;
                     }
                 }
                 __syncwarp();

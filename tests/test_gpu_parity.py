@@ -222,6 +222,18 @@ def test_lattice_split_planes_and_coincident_com(pkg, oracle, ctxs, k, cores, mi
     assert np.max(err[~same]) <= 5e-2 * scale if (~same).any() else True     # a flipped tie costs at most the tree's own error
 
 
+def test_small_opening_angle_far_list_overflow(pkg, oracle, ctxs):
+    """theta = 0.12 makes the shared far-field list of a super-group overflow its 4096 slots: the prepass must hand the rest
+    over to the per-warp walks without changing any result."""
+    ctx = ctxs(8, False)
+    p = pkg.ics.plummer(60000, seed=19)
+    got = run_gpu(pkg, ctx, p, 0.12, 1e18, 1e40)
+    want = oracle.run(p, 0.12, 1e18, 1e40, 0.0, 8, nodes=False)
+    rep = compare(got, want, p, ctx, check_nodes=False)
+    print("theta 0.12", rep, ctx.counters()["interactions"] / 60000)
+    assert_parity(rep)
+
+
 def test_coincident_particles_are_an_error(pkg, ctxs):
     """Two particles at the same position: the reference recurses until the stack overflows (Node.cpp:618-666); here AGB_ERR_DEPTH."""
     ctx = ctxs(8)
