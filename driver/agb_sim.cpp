@@ -207,6 +207,60 @@ bool load_gadget(const std::string& path, Particles& p)
     return true;
 }
 
+// "makeGal" = Gadget SnapFormat 2 as the reference reads it (DataManager.cpp:580-810): every block is preceded by a
+// 16-byte label record (size, 4-char label, next-block size, size); fixed block order POS VEL ID MASS U RHO HSML, of which
+// RHO and HSML are skipped; MASS holds entries only for types whose header mass is 0, U only for gas.  Like the reference,
+// the reader always consumes a MASS block header, so on files WITHOUT a MASS block (its own Example/galaxy_gas.dat) the U
+// values come out shifted by six floats -- reproduced on purpose: the arrays must equal the reference loader's.  The reference
+// shuffles the particles afterwards with a random_device seed (DataManager.cpp:780-783); file order is kept here.
+bool load_makegal(const std::string& path, Particles& p)
+{
+    constexpr double KPC = 3.08567758149137e19, MSUN = 1.98847e30;
+    FILE* f = fopen(path.c_str(), "rb");
+    if (!f) { perror(path.c_str()); return false; }
+    struct Header { int32_t npart[6]; double mass[6]; double time, redshift; int32_t flag_sfr, flag_feedback, npartTotal[6], flag_cooling, num_files;
+                    double BoxSize, Omega0, OmegaLambda, HubbleParam; char fill[256 - 6 * 4 - 6 * 8 - 2 * 8 - 2 * 4 - 6 * 4 - 2 * 4 - 4 * 8]; } h;
+    static_assert(sizeof(Header) == 256, "makeGal header");
+    char lab[16]; int32_t sz = 0;
+    bool ok = fread(lab, 1, 16, f) == 16 && fread(&sz, 4, 1, f) == 1 && fread(&h, sizeof(h), 1, f) == 1 && fread(&sz, 4, 1, f) == 1;
+    size_t total = 0;
+    for (int i = 0; i < 6; i++) total += (size_t)h.npart[i];
+    p.resize((int64_t)total);
+    std::vector<float> pos(3 * total), vel(3 * total), mass(total), u(total, 0.f);
+    std::vector<uint32_t> ids(total);
+    for (int bnr = 0; ok && bnr < 7; bnr++) {
+        ok = fread(lab, 1, 16, f) == 16 && fread(&sz, 4, 1, f) == 1;
+        if (!ok) break;
+        if (bnr == 0) ok = fread(pos.data(), 4, 3 * total, f) == 3 * total;
+        else if (bnr == 1) ok = fread(vel.data(), 4, 3 * total, f) == 3 * total;
+        else if (bnr == 2) ok = fread(ids.data(), 4, total, f) == total;
+        else if (bnr == 3) {
+            size_t idx = 0;
+            for (int t = 0; t < 6 && ok; t++)
+                for (int i = 0; i < h.npart[t] && ok; i++, idx++) {
+                    if (h.mass[t] == 0 && h.npart[t] > 0) ok = fread(&mass[idx], 4, 1, f) == 1;
+                    else mass[idx] = (float)h.mass[t];
+                }
+        } else if (bnr == 4) ok = h.npart[0] == 0 || fread(u.data(), 4, (size_t)h.npart[0], f) == (size_t)h.npart[0];
+        else break;                                  // RHO, HSML: skipped by the reference, nothing after them is read
+        ok = ok && fread(&sz, 4, 1, f) == 1;
+    }
+    fclose(f);
+    if (!ok) { fprintf(stderr, "malformed makeGal file %s\n", path.c_str()); return false; }
+    size_t idx = 0;
+    for (int t = 0; t < 6; t++)
+        for (int i = 0; i < h.npart[t]; i++, idx++) {
+            p.x[idx] = (double)pos[3 * idx] * KPC; p.y[idx] = (double)pos[3 * idx + 1] * KPC; p.z[idx] = (double)pos[3 * idx + 2] * KPC;
+            p.vx[idx] = (double)vel[3 * idx] * KMS; p.vy[idx] = (double)vel[3 * idx + 1] * KMS; p.vz[idx] = (double)vel[3 * idx + 2] * KMS;
+            p.id[idx] = ids[idx];
+            p.mass[idx] = mass[idx] * MSUN * 1e10;
+            p.U[idx] = (t == 0 ? u[idx] : 0.0f) * 1e6;
+            p.type[idx] = t == 0 ? 2 : t == 1 ? 3 : 1;
+            p.galaxyPart[idx] = t == 1 ? 3 : (t == 3 || t == 5) ? 2 : 1;
+        }
+    return true;
+}
+
 // this repo's test format (oracle/agio.py): "AGPART01", int64 N, 13 double columns, uint8 type
 const char* AGP_COLS[13] = {"x", "y", "z", "vx", "vy", "vz", "mass", "U", "next_time", "rho", "P", "T", "mu"};
 std::vector<double>* agp_col(Particles& p, int k)
@@ -448,8 +502,8 @@ int main(int argc, char** argv)
     const std::string inroot = opt.count("input-root") ? opt["input-root"] : "../../input_data/";
     const std::string inpath = inroot + (inroot.empty() || inroot.back() == '/' ? "" : "/") + d.cfg.inputPath;
     bool ok = d.cfg.inputDataFormat == "age" ? load_age(inpath, d.p) : d.cfg.inputDataFormat == "agp" ? load_agp(inpath, d.p) :
-              d.cfg.inputDataFormat == "gadget" ? load_gadget(inpath, d.p) : false;
-    if (!ok) { fprintf(stderr, "cannot read initial conditions %s (format %s; supported: age, agp, gadget)\n", inpath.c_str(), d.cfg.inputDataFormat.c_str()); return 2; }
+              d.cfg.inputDataFormat == "gadget" ? load_gadget(inpath, d.p) : d.cfg.inputDataFormat == "makeGal" ? load_makegal(inpath, d.p) : false;
+    if (!ok) { fprintf(stderr, "cannot read initial conditions %s (format %s; supported: age, agp, gadget, makeGal)\n", inpath.c_str(), d.cfg.inputDataFormat.c_str()); return 2; }
     if (opt.count("convert-only")) return save_agp(opt["convert-only"], d.p) ? 0 : 2;      // no GPU involved
     if ((int64_t)d.cfg.numberOfParticles != d.p.n) {                     // Simulation.cpp:92-98
         fprintf(stderr, "Error: Number of particles in the ConfigFile (%lld) does not match the data file (%lld).\n", (long long)d.cfg.numberOfParticles, (long long)d.p.n);
