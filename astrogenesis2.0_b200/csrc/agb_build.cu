@@ -546,7 +546,6 @@ __global__ void __launch_bounds__(TPB) k_links(AgbDev d, const uint64_t* __restr
         int k = base + (dep - Lm - 1);
         d.ndepth[k] = (int8_t)dep;
         d.nfirst[k] = (int32_t)i;
-        d.nlast[k] = (int32_t)find_last(K, i, dep, h, l, nt);
         int par;
         if (dep == Lm + 1) {
             if (dep == 0) par = -1;
@@ -581,15 +580,18 @@ __device__ __forceinline__ double4 ldcg4(const double4* p)
 __device__ __forceinline__ void node_moments(const AgbDev& d, int k, int N, bool any_gas)
 {
     double sx = 0, sy = 0, sz = 0, m = 0, gx = 0, gy = 0, gz = 0, g = 0;
+    // the node's particle range ends where its last child's range ends (children are in key order)
+    int last = -1;
     if (!any_gas) {
 #pragma unroll
         for (int o = 0; o < 8; o++) {
             int c = d.child[(size_t)k * 8 + o];
             if (c < 0) continue;
-            if (c < N) { double4 pm = d.src_pm[c]; m += pm.w; sx += pm.x * pm.w; sy += pm.y * pm.w; sz += pm.z * pm.w; }
-            else { double4 pm = ldcg4(&d.mom_pm[c - N]); m += pm.w; sx += pm.x; sy += pm.y; sz += pm.z; }
+            if (c < N) { double4 pm = d.src_pm[c]; m += pm.w; sx += pm.x * pm.w; sy += pm.y * pm.w; sz += pm.z * pm.w; last = max(last, c); }
+            else { double4 pm = ldcg4(&d.mom_pm[c - N]); m += pm.w; sx += pm.x; sy += pm.y; sz += pm.z; last = max(last, __ldcg(&d.nlast[c - N])); }
         }
         d.mom_pm[k] = make_double4(sx, sy, sz, m);
+        d.nlast[k] = last;
         return;
     }
 #pragma unroll
@@ -600,14 +602,17 @@ __device__ __forceinline__ void node_moments(const AgbDev& d, int k, int N, bool
             double4 pm = d.src_pm[c], gv = d.src_gv[c];
             m += pm.w; sx += pm.x * pm.w; sy += pm.y * pm.w; sz += pm.z * pm.w;
             g += gv.w; gx += gv.x * gv.w; gy += gv.y * gv.w; gz += gv.z * gv.w;
+            last = max(last, c);
         } else {
             double4 pm = ldcg4(&d.mom_pm[c - N]), gv = ldcg4(&d.mom_gv[c - N]);
             m += pm.w; sx += pm.x; sy += pm.y; sz += pm.z;
             g += gv.w; gx += gv.x; gy += gv.y; gz += gv.z;
+            last = max(last, __ldcg(&d.nlast[c - N]));
         }
     }
     d.mom_pm[k] = make_double4(sx, sy, sz, m);
     d.mom_gv[k] = make_double4(gx, gy, gz, g);
+    d.nlast[k] = last;
 }
 
 __global__ void __launch_bounds__(TPB) k_upward(AgbDev d, const AgbScalars* __restrict__ s)
