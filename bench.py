@@ -391,8 +391,8 @@ def run_gpu_arm(args, pkg):
 
     line = {
         "metric": METRIC, "value": value, "unit": "particles/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
-        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": name, "description": desc, "n_particles": n, "theta": THETA, "e0": e0, "massInH": mh, "all_active": True,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64 decisions and accumulation, f32 pair forces (mixed mode)", "data": "synthetic",
+        "config": {"workload": name, "description": desc, "n_particles": n, "theta": THETA, "e0": e0, "massInH": mh, "all_active": True, "precision": "mixed",
                    "l2": "256 MiB buffer written between timed steps (L2 flush); working set %.0f MB" % (n * 330 / 1e6),
                    "parallelism": "replicated tree, tree-ordered target slices, 1 NCCL all-gather/step" if world > 1 else "single GPU"},
         "e2e": e2e, "resident_sim_step": resident, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
