@@ -734,8 +734,7 @@ static int sort_passes(AgbDev& d, AgbScalars* s, cudaStream_t st)
     constexpr int TILE = SortCfg<ITEMS>::TILE;
     const int nb = nblk(d.n, TILE);
     const int smem = TILE * 12 + (TPB / 32) * 256 * 4 + 2 * 256 * 4;
-    static bool attr = false;
-    if (!attr) { cudaFuncSetAttribute(k_sort_scatter<ITEMS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr = true; }
+    cudaFuncSetAttribute(k_sort_scatter<ITEMS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);   // per device; cheap, so not cached
     for (int pass = 0; pass < 8; pass++) {
         const int in = d.cur, out = d.cur ^ 1;
         k_sort_hist<ITEMS><<<nb, TPB, 0, st>>>(d.khi[in], d.n, pass * 8, d.blockhist, nb);

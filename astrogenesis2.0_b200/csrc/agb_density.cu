@@ -318,9 +318,8 @@ int agb_launch_gas_density(AgbDev& d, AgbScalars* s, double massInH, cudaStream_
     cudaMemsetAsync(d.arrived, 0, (size_t)d.n * sizeof(int32_t), st);
     cudaMemsetAsync(d.lcp, 0, (size_t)d.n, st);
     k_gas_mark<0><<<nb, TPB, 0, st>>>(d, s, massInH, F);
-    static bool attr = false;
     const int fold_smem = FOLD_MAX * 12;
-    if (!attr) { cudaFuncSetAttribute(k_gas_fold, cudaFuncAttributeMaxDynamicSharedMemorySize, fold_smem); attr = true; }
+    cudaFuncSetAttribute(k_gas_fold, cudaFuncAttributeMaxDynamicSharedMemorySize, fold_smem);
     k_gas_fold<<<296, TPB, fold_smem, st>>>(d, s, F);
     k_gas_mark<1><<<nb, TPB, 0, st>>>(d, s, massInH, F);
     k_gas_group<<<nb, TPB, 0, st>>>(d, s);

@@ -751,10 +751,9 @@ __global__ void k_unpermute_i32(const uint32_t* __restrict__ perm, int64_t n, co
 template <bool COUNT, bool SPH, bool MIXED>
 void launch_walk(const WalkParams& P, int64_t max_groups, int sm_count, int spill_warps, cudaStream_t st)
 {
-    static bool attr_set = false;
     constexpr int WARPS = WalkCfg<SPH>::WARPS;
     const int smem = (int)sizeof(WarpSmem<SPH>) * WARPS;
-    if (!attr_set) { cudaFuncSetAttribute(k_walk<COUNT, SPH, MIXED>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr_set = true; }
+    cudaFuncSetAttribute(k_walk<COUNT, SPH, MIXED>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);   // per device; cheap, so not cached
     int blocks = (int)std::min<int64_t>((int64_t)sm_count * WALK_CTAS, (max_groups + WARPS - 1) / WARPS);
     if (blocks * WARPS > spill_warps) blocks = spill_warps / WARPS;
     k_walk<COUNT, SPH, MIXED><<<blocks, WalkCfg<SPH>::TPB, smem, st>>>(P);
