@@ -11,12 +11,13 @@
 //     Simulation::run (:166-345) with Kick / Drift / Ueuler (Physics/TimeIntegration.cpp:10-41), the Hubble
 //     rescale (:330-332) and power-of-two individual time steps (:196-207, :222-232);
 //   * per-phase timings in the reference's processLog.csv format (File/Log.cpp:175-221: `name;seconds`, decimal comma);
-//   * `.age` snapshots every endTime/fixedTimeSteps like DataManager::saveData (first numParticlesOutput particles).
+//   * snapshots in `outputDataFormat` (age, ag, agc, gadget) every endTime/fixedTimeSteps like DataManager::saveData
+//     (first numParticlesOutput particles; DataManager.cpp:86-424), and `.ag`/`.agc` as input formats too (:446-533).
 // Cooling / star formation are no-ops in the reference (calls commented out, Simulation.cpp:312-320) and here.
 // The force path itself is only reached through the C ABI (include/agb200.h); there is no CPU fallback.
 //
 //   agb_sim --config Config.ini [--input-root DIR] [--output-root DIR] [--steps K] [--device D] [--cores C]
-//           [--precision fp64|mixed] [--dump final.agp] [--overwrite] [--device-resident] [--convert-only out.agp]
+//           [--precision fp64|mixed] [--dump final.agp] [--overwrite] [--device-resident] [--convert-only out.agp] [--snapshot-only DIR [--snapshot-index N] [--snapshot-time T]]
 // --device-resident keeps positions, velocities and results in HBM between steps (agb_integrator_* / agb_step_*):
 // only the scalar time crosses PCIe per step; state is copied back for snapshots and at the end.
 #include <algorithm>
@@ -151,6 +152,77 @@ bool save_age(const std::string& path, const Particles& p, int64_t count, double
     return true;
 }
 
+// `.ag` (62 B/particle: pos, mass, T, visualDensity, sfr, type, galaxyPart, id) and `.agc` (26 B/particle: float pos,
+// visualDensity, sfr, T, type, galaxyPart) — the reference's two render formats (DataManager.cpp:120-215 writers,
+// :446-533 readers).  Neither carries velocities or U; `sfr` is never set by the reference (SFR.cpp is dead code), so
+// it is written as 0 and ignored on input.
+#pragma pack(push, 1)
+struct AgRecord { double pos[3], mass, T, visualDensity, sfr; uint8_t type, galaxyPart; uint32_t id; };
+struct AgcRecord { float pos[3], visualDensity, sfr, T; uint8_t type, galaxyPart; };
+#pragma pack(pop)
+static_assert(sizeof(AgRecord) == 62 && sizeof(AgcRecord) == 26, ".ag/.agc layout");
+
+template <class Rec, class Fill> bool load_records(const std::string& path, Particles& p, Fill fill)
+{
+    FILE* f = fopen(path.c_str(), "rb");
+    if (!f) { perror(path.c_str()); return false; }
+    AgeHeader h;
+    if (fread(&h, sizeof(h), 1, f) != 1) { fclose(f); return false; }
+    const int64_t n = (int64_t)h.numParticles[0] + h.numParticles[1] + h.numParticles[2];
+    p.resize(n);
+    std::vector<Rec> buf((size_t)n);
+    if (n && fread(buf.data(), sizeof(Rec), (size_t)n, f) != (size_t)n) { fclose(f); fprintf(stderr, "short snapshot file %s\n", path.c_str()); return false; }
+    fclose(f);
+    for (int64_t i = 0; i < n; i++) fill(buf[(size_t)i], i);
+    return true;
+}
+
+bool load_ag(const std::string& path, Particles& p)
+{
+    return load_records<AgRecord>(path, p, [&](const AgRecord& r, int64_t i) {
+        p.x[i] = r.pos[0]; p.y[i] = r.pos[1]; p.z[i] = r.pos[2]; p.mass[i] = r.mass; p.T[i] = r.T; p.vis[i] = r.visualDensity;
+        p.type[i] = r.type; p.galaxyPart[i] = r.galaxyPart; p.id[i] = r.id;
+    });
+}
+
+bool load_agc(const std::string& path, Particles& p)
+{
+    return load_records<AgcRecord>(path, p, [&](const AgcRecord& r, int64_t i) {     // mass stays 0, as in the reference (:504-528)
+        p.x[i] = r.pos[0]; p.y[i] = r.pos[1]; p.z[i] = r.pos[2]; p.T[i] = r.T; p.vis[i] = r.visualDensity; p.type[i] = r.type; p.galaxyPart[i] = r.galaxyPart;
+    });
+}
+
+template <class Rec, class Fill> bool save_records(const std::string& path, const Particles& p, int64_t count, double deltaTime, double endTime, double currentTime, Fill fill)
+{
+    FILE* f = fopen(path.c_str(), "wb");
+    if (!f) { perror(path.c_str()); return false; }
+    AgeHeader h{};
+    for (int64_t i = 0; i < count; i++) if (p.type[i] >= 1 && p.type[i] <= 3) h.numParticles[p.type[i] - 1]++;
+    h.deltaTime = deltaTime; h.endTime = endTime; h.currentTime = currentTime;
+    fwrite(&h, sizeof(h), 1, f);
+    std::vector<Rec> buf((size_t)count);
+    for (int64_t i = 0; i < count; i++) fill(buf[(size_t)i], i);
+    fwrite(buf.data(), sizeof(Rec), (size_t)count, f);
+    fclose(f);
+    return true;
+}
+
+bool save_ag(const std::string& path, const Particles& p, int64_t count, double deltaTime, double endTime, double currentTime)
+{
+    return save_records<AgRecord>(path, p, count, deltaTime, endTime, currentTime, [&](AgRecord& r, int64_t i) {
+        r.pos[0] = p.x[i]; r.pos[1] = p.y[i]; r.pos[2] = p.z[i]; r.mass = p.mass[i]; r.T = p.T[i]; r.visualDensity = p.vis[i]; r.sfr = 0.0;
+        r.type = p.type[i]; r.galaxyPart = p.galaxyPart[i]; r.id = p.id[i];
+    });
+}
+
+bool save_agc(const std::string& path, const Particles& p, int64_t count, double deltaTime, double endTime, double currentTime)
+{
+    return save_records<AgcRecord>(path, p, count, deltaTime, endTime, currentTime, [&](AgcRecord& r, int64_t i) {
+        r.pos[0] = (float)p.x[i]; r.pos[1] = (float)p.y[i]; r.pos[2] = (float)p.z[i]; r.visualDensity = (float)p.vis[i]; r.sfr = 0.f; r.T = (float)p.T[i];
+        r.type = p.type[i]; r.galaxyPart = p.galaxyPart[i];
+    });
+}
+
 // Gadget-2 SnapFormat 1 as the reference reads it (DataManager.cpp:811-1331): 4-byte record markers around a 256-byte
 // header, POS, VEL, ID, [MASS if a populated type has massarr == 0], [U if there is gas]; floats; kpc, km/s, 1e10 Msun,
 // (km/s)^2.  Type map: 0 -> gas (2), 1 -> dark matter (3, halo), 2/4/5 -> star (1), 3 -> star (1, bulge).  Like the
@@ -205,6 +277,68 @@ bool load_gadget(const std::string& path, Particles& p)
             if (type == 0) p.U[cur] = u[gas++] * 1e6;
         }
     return true;
+}
+
+// Gadget-2 SnapFormat 1 exactly as the reference writes it (DataManager.cpp:263-417), quirks included so that files
+// are byte-identical: disk stars (type 1, galaxyPart 1) are counted as Gadget type 2 but stored in the leading block
+// together with the gas (so they also get a U entry), bulge stars (type 1, part 2) come second and are counted as type
+// 3, halo particles (type 3, part 3) come third and are counted as type 1, anything else is only counted (as type 0);
+// the VEL block holds position / (km/s) because the reference's block helper always reads `position` (:333-340, :363).
+bool save_gadget(const std::string& path, const Particles& p, int64_t count, double currentTime)
+{
+    constexpr double KPC = 3.08567758149137e19, MSUN = 1.98847e30;
+    FILE* f = fopen(path.c_str(), "wb");
+    if (!f) { perror(path.c_str()); return false; }
+    GadgetHeader h;
+    memset(&h, 0, sizeof(h));
+    std::vector<int64_t> lead, second, third;
+    for (int64_t i = 0; i < count; i++) {
+        int gt = 0;
+        if (p.galaxyPart[i] == 1 && p.type[i] == 1) { gt = 2; lead.push_back(i); }
+        if (p.galaxyPart[i] == 3 && p.type[i] == 3) { gt = 1; third.push_back(i); }
+        if (p.galaxyPart[i] == 2 && p.type[i] == 1) { gt = 3; second.push_back(i); }
+        if (p.type[i] == 2) { gt = 0; lead.push_back(i); }
+        h.npart[gt]++; h.npartTotal[gt]++;
+    }
+    h.time = currentTime; h.num_files = 1; h.HubbleParam = 1.0;
+    std::vector<int64_t> order(lead);
+    order.insert(order.end(), second.begin(), second.end());
+    order.insert(order.end(), third.begin(), third.end());
+    auto block = [&](const void* data, size_t bytes) { uint32_t b = (uint32_t)bytes; fwrite(&b, 4, 1, f); fwrite(data, 1, bytes, f); fwrite(&b, 4, 1, f); };
+    block(&h, sizeof(h));
+    std::vector<float> v(order.size() * 3);
+    for (double unit : {(double)(float)KPC, (double)(float)KMS}) {          // the reference's helper takes the unit as a float (:333)
+        for (size_t k = 0; k < order.size(); k++) {
+            const int64_t i = order[k];
+            v[3 * k] = (float)(p.x[i] / unit); v[3 * k + 1] = (float)(p.y[i] / unit); v[3 * k + 2] = (float)(p.z[i] / unit);
+        }
+        block(v.data(), v.size() * sizeof(float));
+    }
+    std::vector<uint32_t> ids(order.size());
+    for (size_t k = 0; k < order.size(); k++) ids[k] = p.id[order[k]];
+    block(ids.data(), ids.size() * sizeof(uint32_t));
+    std::vector<float> m(order.size());
+    for (size_t k = 0; k < order.size(); k++) m[k] = (float)(p.mass[order[k]] / (MSUN * 1e10));
+    block(m.data(), m.size() * sizeof(float));
+    if (!lead.empty()) {
+        std::vector<float> u(lead.size());
+        for (size_t k = 0; k < lead.size(); k++) u[k] = (float)(p.U[lead[k]] / 1e6);
+        block(u.data(), u.size() * sizeof(float));
+    }
+    fclose(f);
+    return true;
+}
+
+// DataManager::saveData's format switch (DataManager.cpp:100-110): <outdir>/<timeStep><ending>.
+bool save_snapshot(const std::string& outdir, const std::string& fmt, int timeStep, const Particles& p, int64_t count, double deltaTime, double endTime, double currentTime)
+{
+    const std::string stem = outdir + "/" + std::to_string(timeStep);
+    if (fmt == "age") return save_age(stem + ".age", p, count, deltaTime, endTime, currentTime);
+    if (fmt == "ag") return save_ag(stem + ".ag", p, count, deltaTime, endTime, currentTime);
+    if (fmt == "agc") return save_agc(stem + ".agc", p, count, deltaTime, endTime, currentTime);
+    if (fmt == "gadget") return save_gadget(stem + ".gadget", p, count, currentTime);
+    fprintf(stderr, "Unknown output data format: %s\n", fmt.c_str());       // hdf5 is an empty stub in the reference (:259-262)
+    return false;
 }
 
 // "makeGal" = Gadget SnapFormat 2 as the reference reads it (DataManager.cpp:580-810): every block is preceded by a
@@ -383,7 +517,7 @@ struct Driver {
         upload();
         check(ctx, agb_integrator_init(ctx, cfg.eta, cfg.minTimeStep, cfg.maxTimeStep, cfg.H0, cfg.e0), "integrator_init");
         device_force_path(true);
-        if (!outdir.empty()) { download(); save_age(outdir + "/0.age", p, (int64_t)cfg.numParticlesOutput, fixedStep, cfg.endTime, 0.0); }
+        if (!outdir.empty()) { download(); save_snapshot(outdir, cfg.outputDataFormat, 0, p, (int64_t)cfg.numParticlesOutput, fixedStep, cfg.endTime, 0.0); }
         check(ctx, agb_integrator_assign_all(ctx), "assign_all");
         double nextSaveTime = fixedStep;
         int64_t step = 0;
@@ -398,7 +532,7 @@ struct Driver {
             if (!outdir.empty() && globalTime >= nextSaveTime) {
                 log.start("Save data");
                 download();
-                save_age(outdir + "/" + std::to_string((int)(nextSaveTime / fixedStep)) + ".age", p, (int64_t)cfg.numParticlesOutput, fixedStep, cfg.endTime, globalTime);
+                save_snapshot(outdir, cfg.outputDataFormat, (int)(nextSaveTime / fixedStep), p, (int64_t)cfg.numParticlesOutput, fixedStep, cfg.endTime, globalTime);
                 log.end();
                 nextSaveTime += fixedStep;
             }
@@ -432,7 +566,7 @@ struct Driver {
         globalTime = 0.0;
         for (int64_t i = 0; i < n; i++) p.next[i] = 0.0;              // Particle::nextIntegrationTime defaults to 0 (Particle.h:29)
         force_path(true);                                                // Simulation.cpp:120-139
-        if (!outdir.empty()) save_age(outdir + "/0.age", p, (int64_t)cfg.numParticlesOutput, fixedStep, cfg.endTime, 0.0);
+        if (!outdir.empty()) save_snapshot(outdir, cfg.outputDataFormat, 0, p, (int64_t)cfg.numParticlesOutput, fixedStep, cfg.endTime, 0.0);
         double nextSaveTime = fixedStep;
         for (int64_t i = 0; i < n; i++) p.next[i] = 0.0;
 #pragma omp parallel for
@@ -473,7 +607,7 @@ struct Driver {
             step++;
             if (!outdir.empty() && globalTime >= nextSaveTime) {
                 log.start("Save data");
-                save_age(outdir + "/" + std::to_string((int)(nextSaveTime / fixedStep)) + ".age", p, (int64_t)cfg.numParticlesOutput, fixedStep, cfg.endTime, globalTime);
+                save_snapshot(outdir, cfg.outputDataFormat, (int)(nextSaveTime / fixedStep), p, (int64_t)cfg.numParticlesOutput, fixedStep, cfg.endTime, globalTime);
                 log.end();
                 nextSaveTime += fixedStep;
             }
@@ -502,9 +636,16 @@ int main(int argc, char** argv)
     const std::string inroot = opt.count("input-root") ? opt["input-root"] : "../../input_data/";
     const std::string inpath = inroot + (inroot.empty() || inroot.back() == '/' ? "" : "/") + d.cfg.inputPath;
     bool ok = d.cfg.inputDataFormat == "age" ? load_age(inpath, d.p) : d.cfg.inputDataFormat == "agp" ? load_agp(inpath, d.p) :
-              d.cfg.inputDataFormat == "gadget" ? load_gadget(inpath, d.p) : d.cfg.inputDataFormat == "makeGal" ? load_makegal(inpath, d.p) : false;
-    if (!ok) { fprintf(stderr, "cannot read initial conditions %s (format %s; supported: age, agp, gadget, makeGal)\n", inpath.c_str(), d.cfg.inputDataFormat.c_str()); return 2; }
+              d.cfg.inputDataFormat == "gadget" ? load_gadget(inpath, d.p) : d.cfg.inputDataFormat == "makeGal" ? load_makegal(inpath, d.p) :
+              d.cfg.inputDataFormat == "ag" ? load_ag(inpath, d.p) : d.cfg.inputDataFormat == "agc" ? load_agc(inpath, d.p) : false;
+    if (!ok) { fprintf(stderr, "cannot read initial conditions %s (format %s; supported: age, ag, agc, agp, gadget, makeGal)\n", inpath.c_str(), d.cfg.inputDataFormat.c_str()); return 2; }
     if (opt.count("convert-only")) return save_agp(opt["convert-only"], d.p) ? 0 : 2;      // no GPU involved
+    if (opt.count("snapshot-only")) {                                                      // DIR/<n>.<outputDataFormat> of the loaded set, no GPU involved
+        const int64_t count = std::min<int64_t>(d.cfg.numParticlesOutput > 0 ? (int64_t)d.cfg.numParticlesOutput : d.p.n, d.p.n);
+        const int ts = opt.count("snapshot-index") ? atoi(opt["snapshot-index"].c_str()) : 0;
+        return save_snapshot(opt["snapshot-only"], d.cfg.outputDataFormat, ts, d.p, count, d.cfg.endTime / d.cfg.fixedTimeSteps, d.cfg.endTime,
+                             opt.count("snapshot-time") ? atof(opt["snapshot-time"].c_str()) : 0.0) ? 0 : 2;
+    }
     if ((int64_t)d.cfg.numberOfParticles != d.p.n) {                     // Simulation.cpp:92-98
         fprintf(stderr, "Error: Number of particles in the ConfigFile (%lld) does not match the data file (%lld).\n", (long long)d.cfg.numberOfParticles, (long long)d.p.n);
         return 2;

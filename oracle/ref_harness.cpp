@@ -235,6 +235,23 @@ int cmd_convert(int argc, char** argv)
     return save_agp(argv[4], sim.particles) ? 0 : 2;
 }
 
+// DataManager::saveData on a set loaded by DataManager::loadICs: <outdir>/<timeStep>.<fmt> (DataManager.cpp:86-424).
+int cmd_save(int argc, char** argv)
+{
+    if (argc < 10) { fprintf(stderr, "usage: save in_format relpath out_format outdir/ timeStep deltaTime endTime currentTime [count]\n"); return 2; }
+    const char* root = getenv("AG_REFERENCE_ROOT");
+    std::string cwd = std::string(root ? root : "/root/reference") + "/simulation/src";
+    if (chdir(cwd.c_str()) != 0) { perror(cwd.c_str()); return 2; }
+    Simulation sim;
+    DataManager dm(argv[5]);
+    dm.inputPath = argv[3]; dm.inputFormat = argv[2]; dm.outputFormat = argv[4];
+    dm.loadICs(sim.particles, &sim);
+    if (sim.particles.empty()) return 2;
+    const int count = argc > 10 ? atoi(argv[10]) : (int)sim.particles.size();
+    dm.saveData(sim.particles, atoi(argv[6]), 0, count, atof(argv[7]), atof(argv[8]), atof(argv[9]));
+    return 0;
+}
+
 // Phase timings of the reference path (same phases as its processLog.csv, Simulation.cpp:120-139).
 int cmd_time(int argc, char** argv)
 {
@@ -347,6 +364,7 @@ int main(int argc, char** argv)
     std::string cmd = argv[1];
     if (cmd == "run") return cmd_run(argc, argv);
     if (cmd == "convert") return cmd_convert(argc, argv);
+    if (cmd == "save") return cmd_save(argc, argv);
     if (cmd == "time") return cmd_time(argc, argv);
     if (cmd == "steps") return cmd_steps(argc, argv);
     fprintf(stderr, "unknown command %s\n", argv[1]);
