@@ -398,6 +398,43 @@ int agb_get_results(agb_ctx* c, const agb_results* r, int memspace)
     return AGB_OK;
 }
 
+int agb_get_slice_count(agb_ctx* c, int part, int nparts, int64_t* count)
+{
+    if (!c || !count || !c->forces_done || nparts < 1 || part < 0 || part >= nparts) return AGB_ERR_INVALID;
+    int64_t a0 = 0, a1 = 0;
+    if (c->d.n > 0) agb_slice_bounds(c->hs.n_active, part, nparts, &a0, &a1);
+    *count = a1 - a0;
+    return AGB_OK;
+}
+
+int agb_get_slice_results(agb_ctx* c, int part, int nparts, uint32_t* index, double* ax, double* ay, double* az, double* dUdt, int memspace)
+{
+    int64_t cnt = 0;
+    if (agb_get_slice_count(c, part, nparts, &cnt) != AGB_OK) return AGB_ERR_INVALID;
+    if (cnt == 0) return AGB_OK;
+    CK(cudaSetDevice(c->device));
+    AgbDev& d = c->d;
+    int64_t a0 = 0, a1 = 0;
+    agb_slice_bounds(c->hs.n_active, part, nparts, &a0, &a1);
+    const bool ident = c->hs.n_active == d.n;
+    if (memspace == AGB_MEM_DEVICE) {
+        c->launches += agb_launch_slice_results(d, a0, a1, ident, index, ax, ay, az, dUdt, c->st);
+        CK(cudaStreamSynchronize(c->st));
+        return AGB_OK;
+    }
+    // host destination: compact on the device first (scratch that is idle between the walk and the next build), then D2H
+    double* col = reinterpret_cast<double*>(d.rec);                    // 4 columns of cnt <= cap doubles
+    uint32_t* idx = reinterpret_cast<uint32_t*>(d.nodecnt);
+    c->launches += agb_launch_slice_results(d, a0, a1, ident, index ? idx : nullptr, ax ? col : nullptr, ay ? col + cnt : nullptr, az ? col + 2 * cnt : nullptr,
+                                            dUdt ? col + 3 * cnt : nullptr, c->st);
+    if (index) CK(cudaMemcpyAsync(index, idx, (size_t)cnt * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->st));
+    double* dst[4] = {ax, ay, az, dUdt};
+    for (int k = 0; k < 4; k++) if (dst[k]) CK(cudaMemcpyAsync(dst[k], col + (size_t)k * cnt, (size_t)cnt * sizeof(double), cudaMemcpyDeviceToHost, c->st));
+    CK(cudaStreamSynchronize(c->st));
+    CK(cudaGetLastError());
+    return AGB_OK;
+}
+
 int agb_get_results_aos(agb_ctx* c, void* const* parts, int64_t n, const agb_aos_layout* L)
 {
     if (!c || !parts || !L || n != c->d.n) return AGB_ERR_INVALID;

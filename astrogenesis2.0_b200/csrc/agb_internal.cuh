@@ -99,6 +99,9 @@ int agb_launch_sort(AgbDev& d, AgbScalars* s, cudaStream_t st);
 int agb_launch_links(AgbDev& d, AgbScalars* s, cudaStream_t st);
 int agb_launch_visual(AgbDev& d, AgbScalars* s, double radius, cudaStream_t st);
 int agb_launch_gas_density(AgbDev& d, AgbScalars* s, double massInH, cudaStream_t st);
+// compact (index, acc, dUdt) of the active targets [a0, a1) in tree order (agb_get_slice_results)
+void agb_slice_bounds(int64_t n_active, int part, int nparts, int64_t* a0, int64_t* a1);
+int agb_launch_slice_results(const AgbDev& d, int64_t a0, int64_t a1, bool ident, uint32_t* index, double* ax, double* ay, double* az, double* dUdt, cudaStream_t st);
 int agb_launch_walk(AgbDev& d, AgbScalars* s, double globalTime, double e0, double theta, int part, int nparts,
                     bool counters, bool any_gas, bool mixed, int sm_count, cudaStream_t st, cudaEvent_t ev0, cudaEvent_t ev1);
 int agb_launch_dump_tree(AgbDev& d, AgbScalars* s, int32_t* leafdepth, uint64_t* khi, uint64_t* klo, cudaStream_t st);

@@ -748,6 +748,22 @@ __global__ void k_unpermute_i32(const uint32_t* __restrict__ perm, int64_t n, co
     oa[p] = a[i]; ob[p] = b[i]; oc[p] = c[i]; od[p] = d_[i];
 }
 
+__global__ void k_slice_results(const uint32_t* __restrict__ perm, const int32_t* __restrict__ act_list, int64_t a0, int64_t a1, bool ident,
+                                const double* __restrict__ sax, const double* __restrict__ say, const double* __restrict__ saz, const double* __restrict__ sdu,
+                                uint32_t* __restrict__ index, double* __restrict__ ax, double* __restrict__ ay, double* __restrict__ az, double* __restrict__ dUdt)
+{
+    const int64_t i = a0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a1) return;
+    const int64_t t = ident ? i : (int64_t)act_list[i];
+    const uint32_t p = perm[t];
+    const int64_t k = i - a0;
+    if (index) index[k] = p;
+    if (ax) ax[k] = sax[p];
+    if (ay) ay[k] = say[p];
+    if (az) az[k] = saz[p];
+    if (dUdt) dUdt[k] = sdu[p];
+}
+
 template <bool COUNT, bool SPH, bool MIXED>
 void launch_walk(const WalkParams& P, int64_t max_groups, int sm_count, int spill_warps, cudaStream_t st)
 {
@@ -824,6 +840,21 @@ int agb_launch_walk(AgbDev& d, AgbScalars* s, double globalTime, double e0, doub
         launches++;
     }
     return launches;
+}
+
+// host mirror of target_slice()
+void agb_slice_bounds(int64_t n_active, int part, int nparts, int64_t* a0, int64_t* a1)
+{
+    const int64_t g = 32 * SG_GROUPS, nsg = (n_active + g - 1) / g;
+    *a0 = std::min(n_active, nsg * part / nparts * g);
+    *a1 = std::min(n_active, nsg * (part + 1) / nparts * g);
+}
+
+int agb_launch_slice_results(const AgbDev& d, int64_t a0, int64_t a1, bool ident, uint32_t* index, double* ax, double* ay, double* az, double* dUdt, cudaStream_t st)
+{
+    if (a1 <= a0) return 0;
+    k_slice_results<<<(int)((a1 - a0 + 255) / 256), 256, 0, st>>>(d.perm[d.cur], d.act_list, a0, a1, ident, d.ax, d.ay, d.az, d.dUdt, index, ax, ay, az, dUdt);
+    return 1;
 }
 
 int agb_launch_microbench(int kind, int sm_count, cudaStream_t st, double* result)

@@ -108,6 +108,22 @@ class Context:
         capi.check(self.h, self.lib.agb_get_results(self.h, C.byref(r), capi.AGB_MEM_HOST))
         return out
 
+    def slice_count(self, part, nparts):
+        c = C.c_int64()
+        capi.check(self.h, self.lib.agb_get_slice_count(self.h, int(part), int(nparts), C.byref(c)))
+        return c.value
+
+    def slice_results(self, part, nparts, names=("ax", "ay", "az", "dUdt"), out=None):
+        """Compact results of one target slice (agb_get_slice_results): dict with `index` (caller-order positions of the
+        slice's targets, tree order) and the requested columns.  `out` may hold preallocated (pinned) numpy arrays."""
+        cnt = self.slice_count(part, nparts)
+        res = {"index": (out["index"][:cnt] if out else np.empty(cnt, np.uint32))}
+        for k in names:
+            res[k] = out[k][:cnt] if out else np.empty(cnt)
+        cols = [capi.dptr(res.get(k)) for k in ("ax", "ay", "az", "dUdt")]
+        capi.check(self.h, self.lib.agb_get_slice_results(self.h, int(part), int(nparts), capi.dptr(res["index"], C.c_uint32), *cols, capi.AGB_MEM_HOST))
+        return res
+
     def results_device(self, ptrs):
         r = capi.Results()
         for k in _OUT:

@@ -293,30 +293,36 @@ def run_gpu_arm(args, pkg):
         d2h = sum(v.numel() * 8 for v in pinned_out.values())
         e2e = {"value": n / te, "unit": "particles/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "ms_per_step": te * 1e3}
     else:
-        # multi-GPU e2e: host shard -> device shard (H2D), gather, step, D2H of the 3 acc arrays
+        # multi-GPU e2e: host shard -> device shard (H2D), gather, step, then every rank brings back the compact results of
+        # ITS slice of the targets (caller-order index + acc [+ dUdt]; agb_get_slice_results) into pinned host memory
         host = {k: torch.from_numpy(np.ascontiguousarray(p[k][lo:hi])).pin_memory() for k in f8 + ["type"]}
-        out_d = {k: torch.empty(n, dtype=torch.float64, device=dev) for k in ("ax", "ay", "az")}
-        out_h = {k: torch.empty(n, dtype=torch.float64).pin_memory() for k in out_d}
+        cols = ("ax", "ay", "az") + (("dUdt",) if any_gas else ())
+        cap = n // world + 1024
+        out_t = {k: torch.empty(cap, dtype=torch.float64).pin_memory() for k in cols}
+        out_t["index"] = torch.empty(cap, dtype=torch.int32).pin_memory()
+        out_np = {k: v.numpy() for k, v in out_t.items()}
+        out_np["index"] = out_np["index"].view(np.uint32)
 
         def e2e_step():
             for k in host:
                 shard[k].copy_(host[k], non_blocking=True)
             step()
-            ctx.results_device({k: v.data_ptr() for k, v in out_d.items()})
-            for k in out_d:
-                out_h[k].copy_(out_d[k], non_blocking=True)
-            torch.cuda.synchronize()
-        e2e_step()
+            return ctx.slice_results(rank, world, names=cols, out=out_np)
+        r = e2e_step()
+        mine = len(r["index"]) * (4 + 8 * len(cols))
         barrier()
         t0 = time.perf_counter()
         for _ in range(args.steps):
             e2e_step()
         barrier()
-        te = torch.tensor([(time.perf_counter() - t0) / args.steps], dtype=torch.float64, device=dev)
+        te = torch.tensor([(time.perf_counter() - t0) / args.steps, 0.0], dtype=torch.float64, device=dev)
+        by = torch.tensor([0.0, float(mine)], dtype=torch.float64, device=dev)
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        dist.all_reduce(by, op=dist.ReduceOp.SUM)
         te = float(te[0])
         e2e = {"value": n / te, "unit": "particles/s", "h2d_bytes_per_step": int(sum(v.numel() * v.element_size() for v in host.values()) * world),
-               "d2h_bytes_per_step": int(3 * 8 * n * world), "ms_per_step": te * 1e3}
+               "d2h_bytes_per_step": int(by[1]), "ms_per_step": te * 1e3,
+               "what": "per rank: H2D of its particle shard, NCCL all-gather, build, densities, walk of its target slice, D2H of that slice's (index, acc[, dUdt])"}
 
     # ---- device-resident simulation steps (integrator kernels + force path, nothing but the time crosses PCIe)
     resident = None

@@ -112,6 +112,13 @@ int agb_forces(agb_ctx* ctx, double global_time, double e0, double theta);   /* 
 /* Multi-GPU variant: walk only the `part`-th of `nparts` contiguous slices of the tree-ordered
  * targets (every GPU holds the same gathered particles and builds the same tree). */
 int agb_forces_slice(agb_ctx* ctx, double global_time, double e0, double theta, int part, int nparts);
+/* The targets of slice (part, nparts) after agb_forces[_slice]: their number, and their results in compact form —
+ * index[k] = position of the k-th target (tree order) in the caller's particle arrays, ax/ay/az/dUdt[k] its results.
+ * What each GPU of a target-sharded run sends back instead of N-sized arrays: the slices of all parts are disjoint and
+ * together hold every active particle exactly once (Tree.cpp:65-80 writes acc / dUdt of active particles only).
+ * Output arrays need room for *count entries (query with index = NULL first, or size them for N); NULL = not wanted. */
+int agb_get_slice_count(agb_ctx* ctx, int part, int nparts, int64_t* count);
+int agb_get_slice_results(agb_ctx* ctx, int part, int nparts, uint32_t* index, double* ax, double* ay, double* az, double* dUdt, int memspace);
 
 /* -------- device-resident driver loop (optional).  With particles handed over from HOST memory the
  * context owns device copies; these calls advance them in place exactly like the reference's loop, so nothing but the

@@ -166,6 +166,41 @@ def test_slices_equal_whole(pkg, ctxs):
         assert np.array_equal(out[k], whole[k]), k
 
 
+@pytest.mark.parametrize("active_frac", [1.0, 0.3])
+def test_slice_results_cover_the_active_targets_once(pkg, ctxs, active_frac):
+    """agb_get_slice_results: the compact (index, acc, dUdt) of the 3 slices are disjoint, cover exactly the active
+    particles, equal the N-sized result arrays, and follow shard.slice_bounds (the host mirror of the device slicing)."""
+    ctx = ctxs(8)
+    p = pkg.ics.disk_galaxy(40000, seed=21)
+    n = len(p["x"])
+    rng = np.random.default_rng(5)
+    p["next_time"] = np.where(rng.random(n) < active_frac, 0.0, 1e13)
+    mh = pkg.ics.gas_mass_in_h(p, 64)
+    ctx.set_particles(p)
+    R = ctx.build_tree(); ctx.visual_density(R / 1e5); ctx.gas_density(mh)
+    seen = np.zeros(n, np.int32)
+    got = {k: np.full(n, np.nan) for k in ("ax", "ay", "az", "dUdt")}
+    n_active = int((p["next_time"] == 0.0).sum())
+    for part in range(3):
+        ctx.forces(0.0, 1e18, 0.5, part, 3)
+        r = ctx.slice_results(part, 3)
+        lo, hi = pkg.shard.slice_bounds(n_active, part, 3)
+        assert len(r["index"]) == hi - lo == ctx.slice_count(part, 3)
+        np.add.at(seen, r["index"], 1)
+        for k in got:
+            got[k][r["index"]] = r[k]
+    active = p["next_time"] == 0.0
+    assert np.array_equal(seen, active.astype(np.int32))
+    full = ctx.results()
+    for k in got:
+        assert np.array_equal(got[k][active], full[k][active]), k
+    # tree order: the slice's targets are sorted by their octant-path keys
+    ld, khi, klo = ctx.tree_particles()
+    idx = ctx.slice_results(1, 3, names=())["index"]
+    idx = idx[ld[idx] >= 0]
+    assert np.all(khi[idx][1:] >= khi[idx][:-1])
+
+
 def test_direct_sum_bound_gpu(pkg, ctxs):
     ctx = ctxs(8)
     p = pkg.ics.plummer(30000, seed=15)
