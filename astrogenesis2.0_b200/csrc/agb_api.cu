@@ -34,6 +34,9 @@ struct agb_ctx {
     // device-resident integrator
     AgbInt I = {}; bool int_ready = false; double* timestep = nullptr; unsigned long long* d_min = nullptr; double int_time = 0.0;
     agb_counters last = {};
+    // agb_bind_results: destinations registered in advance, streamed out as soon as their phase is done
+    agb_results bres = {}; bool bres_on = false; int bres_space = AGB_MEM_HOST; bool bres_sent[9] = {};
+    cudaEvent_t ev_out = nullptr;
 };
 
 namespace {
@@ -136,6 +139,31 @@ int own_input(agb_ctx* c, const double*& slot, int which, const double* src, int
     return AGB_OK;
 }
 
+// results table order: ax ay az dUdt h rho P T visualDensity
+struct ResCol { double* dst; const double* src; };
+void result_table(const agb_results& r, const AgbDev& d, ResCol cp[9])
+{
+    ResCol t[9] = {{r.ax, d.ax}, {r.ay, d.ay}, {r.az, d.az}, {r.dUdt, d.dUdt}, {r.h, d.h}, {r.rho, d.rho}, {r.P, d.P}, {r.T, d.T}, {r.visualDensity, d.vis}};
+    for (int i = 0; i < 9; i++) cp[i] = t[i];
+}
+
+// send the bound destinations of columns [first, last] on the copy stream once the compute stream has produced them
+int stream_out(agb_ctx* c, int first, int last)
+{
+    if (!c->bres_on || c->d.n == 0) return AGB_OK;
+    ResCol cp[9];
+    result_table(c->bres, c->d, cp);
+    bool any = false;
+    for (int i = first; i <= last; i++) any = any || cp[i].dst;
+    if (!any) return AGB_OK;
+    CK(cudaEventRecord(c->ev_out, c->st));
+    CK(cudaStreamWaitEvent(c->st_copy, c->ev_out, 0));
+    const cudaMemcpyKind k = c->bres_space == AGB_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+    for (int i = first; i <= last; i++)
+        if (cp[i].dst) { CK(cudaMemcpyAsync(cp[i].dst, cp[i].src, (size_t)c->d.n * sizeof(double), k, c->st_copy)); c->bres_sent[i] = true; }
+    return AGB_OK;
+}
+
 } // namespace
 
 extern "C" {
@@ -175,6 +203,7 @@ int agb_create(agb_ctx** out, int device, int compat_cores)
     if (cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking) != cudaSuccess) { delete c; return AGB_ERR_NO_DEVICE; }
     if (cudaStreamCreateWithFlags(&c->st_copy, cudaStreamNonBlocking) != cudaSuccess) { delete c; return AGB_ERR_NO_DEVICE; }
     cudaEventCreateWithFlags(&c->ev_in, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&c->ev_out, cudaEventDisableTiming);
     for (auto& e : c->ev) cudaEventCreate(&e);
     if (cudaMalloc((void**)&c->s, sizeof(AgbScalars)) != cudaSuccess) { delete c; return AGB_ERR_NOMEM; }
     cudaMemsetAsync(c->s, 0, sizeof(AgbScalars), c->st);
@@ -192,7 +221,7 @@ int agb_destroy(agb_ctx* c)
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->st); cudaStreamSynchronize(c->st_copy);
     free_pool(c);
-    cudaEventDestroy(c->ev_in); cudaStreamDestroy(c->st_copy);
+    cudaEventDestroy(c->ev_in); cudaEventDestroy(c->ev_out); cudaStreamDestroy(c->st_copy);
     cudaFree(c->d.spill);
     cudaFree(c->s);
     if (c->stage) cudaFreeHost(c->stage);
@@ -243,6 +272,7 @@ int agb_set_particles(agb_ctx* c, const agb_particles* p, int memspace)
     // Simulation::particles during buildTree, they must stay untouched until agb_build_tree has returned.
     c->have_particles = true; c->built = false; c->dens_done = false; c->forces_done = false; c->counters_valid = false;
     c->int_ready = false;
+    for (bool& f : c->bres_sent) f = false;
     return AGB_OK;
 }
 
@@ -318,7 +348,7 @@ int agb_visual_density(agb_ctx* c, double radius)
     CK(cudaEventRecord(c->ev[3], c->st));
     c->vis_timed = true;
     CK(cudaGetLastError());
-    return AGB_OK;
+    return stream_out(c, 8, 8);
 }
 
 int agb_gas_density(agb_ctx* c, double mass_in_h)
@@ -332,7 +362,7 @@ int agb_gas_density(agb_ctx* c, double mass_in_h)
     CK(cudaEventRecord(c->ev[5], c->st));
     c->gas_timed = true;
     CK(cudaGetLastError());
-    return AGB_OK;
+    return stream_out(c, 4, 7);
 }
 
 int agb_forces_slice(agb_ctx* c, double global_time, double e0, double theta, int part, int nparts)
@@ -390,11 +420,28 @@ int agb_get_results(agb_ctx* c, const agb_results* r, int memspace)
     const size_t b = (size_t)c->d.n * sizeof(double);
     const cudaMemcpyKind k = memspace == AGB_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
     if (c->in_pending) { CK(cudaStreamWaitEvent(c->st, c->ev_in, 0)); c->in_pending = false; }
-    const AgbDev& d = c->d;
-    struct { double* dst; const double* src; } cp[] = {{r->ax, d.ax}, {r->ay, d.ay}, {r->az, d.az}, {r->dUdt, d.dUdt}, {r->h, d.h},
-                                                       {r->rho, d.rho}, {r->P, d.P}, {r->T, d.T}, {r->visualDensity, d.vis}};
-    for (auto& e : cp) if (e.dst && b) CK(cudaMemcpyAsync(e.dst, e.src, b, k, c->st));
+    ResCol cp[9], bp[9];
+    result_table(*r, c->d, cp);
+    result_table(c->bres, c->d, bp);
+    bool streamed = false;
+    for (int i = 0; i < 9; i++) {
+        // a column already on its way to this very destination (agb_bind_results) is not sent twice
+        if (c->bres_on && c->bres_sent[i] && cp[i].dst == bp[i].dst && memspace == c->bres_space) { streamed = streamed || cp[i].dst; continue; }
+        if (cp[i].dst && b) CK(cudaMemcpyAsync(cp[i].dst, cp[i].src, b, k, c->st));
+    }
     CK(cudaStreamSynchronize(c->st));
+    if (streamed) CK(cudaStreamSynchronize(c->st_copy));
+    return AGB_OK;
+}
+
+int agb_bind_results(agb_ctx* c, const agb_results* r, int memspace)
+{
+    if (!c) return AGB_ERR_INVALID;
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->st_copy));                 // nothing may still be flowing to the old destinations
+    c->bres_on = r != nullptr;
+    if (r) { c->bres = *r; c->bres_space = memspace; }
+    for (bool& f : c->bres_sent) f = false;
     return AGB_OK;
 }
 

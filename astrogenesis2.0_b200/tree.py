@@ -124,6 +124,24 @@ class Context:
         capi.check(self.h, self.lib.agb_get_slice_results(self.h, int(part), int(nparts), capi.dptr(res["index"], C.c_uint32), *cols, capi.AGB_MEM_HOST))
         return res
 
+    def bind_results(self, out):
+        """Register host arrays (dict name -> float64 numpy array of length n, ideally pinned) as the destination of the
+        results: density outputs are sent while the walk runs (agb_bind_results).  `results_into(out)` completes them."""
+        if out is None:
+            capi.check(self.h, self.lib.agb_bind_results(self.h, None, capi.AGB_MEM_HOST))
+            return
+        r = capi.Results()
+        for k in _OUT:
+            setattr(r, k, capi.dptr(out.get(k)))
+        capi.check(self.h, self.lib.agb_bind_results(self.h, C.byref(r), capi.AGB_MEM_HOST))
+
+    def results_into(self, out):
+        r = capi.Results()
+        for k in _OUT:
+            setattr(r, k, capi.dptr(out.get(k)))
+        capi.check(self.h, self.lib.agb_get_results(self.h, C.byref(r), capi.AGB_MEM_HOST))
+        return out
+
     def results_device(self, ptrs):
         r = capi.Results()
         for k in _OUT:

@@ -271,16 +271,16 @@ def run_gpu_arm(args, pkg):
         outn = ("ax", "ay", "az", "visualDensity") + (("dUdt", "h", "rho", "P", "T") if any_gas else ())
         pinned_out = {k: torch.empty(n, dtype=torch.float64).pin_memory() for k in outn}
 
+        out_np = {k: v.numpy() for k, v in pinned_out.items()}
+        ctx.bind_results(out_np)          # density outputs leave while the walk runs; acc / dUdt follow in results_into
+
         def e2e_step():
             ctx.set_particles(host)
             R = ctx.build_tree()
             ctx.visual_density(R / 100000)
             ctx.gas_density(mh)
             ctx.forces(0.0, e0, THETA)
-            r = pkg.capi.Results()
-            for k in outn:
-                setattr(r, k, pkg.capi.C.cast(pkg.capi.C.c_void_p(pinned_out[k].data_ptr()), pkg.capi.C.POINTER(pkg.capi.C.c_double)))
-            pkg.capi.check(ctx.h, ctx.lib.agb_get_results(ctx.h, pkg.capi.C.byref(r), pkg.capi.AGB_MEM_HOST))
+            ctx.results_into(out_np)
         for _ in range(max(1, args.warmup)):
             e2e_step()
         torch.cuda.synchronize()
@@ -292,6 +292,7 @@ def run_gpu_arm(args, pkg):
         h2d = sum(host[k].nbytes for k in host) + 0
         d2h = sum(v.numel() * 8 for v in pinned_out.values())
         e2e = {"value": n / te, "unit": "particles/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "ms_per_step": te * 1e3}
+        ctx.bind_results(None)
     else:
         # multi-GPU e2e: host shard -> device shard (H2D), gather, step, then every rank brings back the compact results of
         # ITS slice of the targets (caller-order index + acc [+ dUdt]; agb_get_slice_results) into pinned host memory

@@ -138,6 +138,11 @@ int agb_get_state(agb_ctx* ctx, double* x, double* y, double* z, double* vx, dou
 
 /* -------- results (replaces the path's direct writes into Particle) */
 int agb_get_results(agb_ctx* ctx, const agb_results* r, int memspace);
+/* Optional: register the destinations of agb_get_results in advance.  Each bound array is then sent on a second stream
+ * as soon as its phase has finished — visualDensity after agb_visual_density, h / rho / P / T after agb_gas_density — so
+ * those transfers overlap the tree walk; agb_get_results with the same pointers sends the rest (acc, dUdt) and waits for
+ * all of it.  The arrays must stay valid (and untouched) until agb_get_results returns; r = NULL unbinds. */
+int agb_bind_results(agb_ctx* ctx, const agb_results* r, int memspace);
 int agb_get_results_aos(agb_ctx* ctx, void* const* particles, int64_t n, const agb_aos_layout* layout);
 int agb_get_counters(agb_ctx* ctx, agb_counters* c);
 

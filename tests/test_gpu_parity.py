@@ -201,6 +201,34 @@ def test_slice_results_cover_the_active_targets_once(pkg, ctxs, active_frac):
     assert np.all(khi[idx][1:] >= khi[idx][:-1])
 
 
+def test_bound_results_equal_fetched_results(pkg, ctxs):
+    """agb_bind_results: outputs streamed out early (densities during the walk) are the same arrays agb_get_results returns."""
+    ctx = ctxs(8)
+    p = pkg.ics.disk_galaxy(60000, seed=23)
+    mh = pkg.ics.gas_mass_in_h(p, 64)
+    want = run_gpu(pkg, ctx, p, 0.5, 1e18, mh)
+    want["visualDensity"] = want["vis"]
+    n = len(p["x"])
+    names = ("ax", "ay", "az", "dUdt", "h", "rho", "P", "T", "visualDensity")
+    out = {k: np.full(n, np.nan) for k in names}
+    ctx.bind_results(out)
+    try:
+        for _ in range(2):                                 # twice: the second step reuses the binding
+            for v in out.values():
+                v.fill(np.nan)
+            ctx.set_particles(p)
+            R = ctx.build_tree(); ctx.visual_density(R / 1e5); ctx.gas_density(mh); ctx.forces(0.0, 1e18, 0.5)
+            ctx.results_into(out)
+            for k in names:
+                assert np.array_equal(out[k], want[k]), k
+        # other destinations are still served in full
+        other = ctx.results()
+        for k in names:
+            assert np.array_equal(other[k], want[k]), k
+    finally:
+        ctx.bind_results(None)
+
+
 def test_direct_sum_bound_gpu(pkg, ctxs):
     ctx = ctxs(8)
     p = pkg.ics.plummer(30000, seed=15)
