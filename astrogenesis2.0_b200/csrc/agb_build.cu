@@ -565,27 +565,34 @@ __global__ void __launch_bounds__(TPB) k_links(AgbDev d, const uint64_t* __restr
 }
 
 // ------------------------------------------------------------------ upward pass (monopole + gas moments)
-__device__ __forceinline__ int count_node_children(const int32_t* child, int k, int N)
-{
-    const int4 a = reinterpret_cast<const int4*>(child)[2 * (size_t)k], b = reinterpret_cast<const int4*>(child)[2 * (size_t)k + 1];
-    return (a.x >= N) + (a.y >= N) + (a.z >= N) + (a.w >= N) + (b.x >= N) + (b.y >= N) + (b.z >= N) + (b.w >= N);
-}
-
 __device__ __forceinline__ double4 ldcg4(const double4* p)
 {   // L2-coherent read of data another SM has just published
     const double2 a = __ldcg(reinterpret_cast<const double2*>(p)), b = __ldcg(reinterpret_cast<const double2*>(p) + 1);
     return make_double4(a.x, a.y, b.x, b.y);
 }
 
-__device__ __forceinline__ void node_moments(const AgbDev& d, int k, int N, bool any_gas)
+struct ChildLinks { int4 a, b; };
+__device__ __forceinline__ ChildLinks load_links(const int32_t* child, int k)
+{
+    ChildLinks L;
+    L.a = reinterpret_cast<const int4*>(child)[2 * (size_t)k]; L.b = reinterpret_cast<const int4*>(child)[2 * (size_t)k + 1];
+    return L;
+}
+__device__ __forceinline__ int count_node_children(const ChildLinks& L, int N)
+{
+    return (L.a.x >= N) + (L.a.y >= N) + (L.a.z >= N) + (L.a.w >= N) + (L.b.x >= N) + (L.b.y >= N) + (L.b.z >= N) + (L.b.w >= N);
+}
+
+__device__ __forceinline__ void node_moments(const AgbDev& d, int k, int N, bool any_gas, const ChildLinks& L)
 {
     double sx = 0, sy = 0, sz = 0, m = 0, gx = 0, gy = 0, gz = 0, g = 0;
     // the node's particle range ends where its last child's range ends (children are in key order)
     int last = -1;
+    const int ch[8] = {L.a.x, L.a.y, L.a.z, L.a.w, L.b.x, L.b.y, L.b.z, L.b.w};
     if (!any_gas) {
 #pragma unroll
         for (int o = 0; o < 8; o++) {
-            int c = d.child[(size_t)k * 8 + o];
+            const int c = ch[o];
             if (c < 0) continue;
             if (c < N) { double4 pm = d.src_pm[c]; m += pm.w; sx += pm.x * pm.w; sy += pm.y * pm.w; sz += pm.z * pm.w; last = max(last, c); }
             else { double4 pm = ldcg4(&d.mom_pm[c - N]); m += pm.w; sx += pm.x; sy += pm.y; sz += pm.z; last = max(last, __ldcg(&d.nlast[c - N])); }
@@ -596,7 +603,7 @@ __device__ __forceinline__ void node_moments(const AgbDev& d, int k, int N, bool
     }
 #pragma unroll
     for (int o = 0; o < 8; o++) {                      // fixed octant order => run-to-run identical sums
-        int c = d.child[(size_t)k * 8 + o];
+        const int c = ch[o];
         if (c < 0) continue;
         if (c < N) {
             double4 pm = d.src_pm[c], gv = d.src_gv[c];
@@ -615,24 +622,28 @@ __device__ __forceinline__ void node_moments(const AgbDev& d, int k, int N, bool
     d.nlast[k] = last;
 }
 
+// Last-arriver climb.  The dependent chain per level is kept to: child moments -> store + fence -> atomic; the parent's
+// links (needed for the arrival count now and for its moments next) and the grandparent id are fetched ahead of it.
 __global__ void __launch_bounds__(TPB) k_upward(AgbDev d, const AgbScalars* __restrict__ s)
 {
     int k = blockIdx.x * TPB + threadIdx.x;
     if (k >= s->n_nodes) return;
     const int N = (int)d.n;
-    if (count_node_children(d.child, k, N) != 0) return;      // only nodes whose children are all leaves start a climb
-    int cur = k;
+    ChildLinks L = load_links(d.child, k);
+    if (count_node_children(L, N) != 0) return;               // only nodes whose children are all leaves start a climb
+    int cur = k, par = d.nparent[cur];
     const bool any_gas = s->any_gas != 0;
     while (true) {
-        node_moments(d, cur, N, any_gas);
-        __threadfence();
-        int par = d.nparent[cur];
+        ChildLinks Lp = L; int ppar = -1;
+        if (par >= 0) { Lp = load_links(d.child, par); ppar = d.nparent[par]; }
+        node_moments(d, cur, N, any_gas, L);
         if (par < 0) break;
-        int need = count_node_children(d.child, par, N);
-        int old = atomicAdd(&d.arrived[par], 1);
+        __threadfence();
+        const int need = count_node_children(Lp, N);
+        const int old = atomicAdd(&d.arrived[par], 1);
         if (old + 1 < need) break;                             // a sibling subtree is still being summed
         __threadfence();
-        cur = par;
+        cur = par; par = ppar; L = Lp;
     }
 }
 
