@@ -366,3 +366,29 @@ def test_full_size_properties(pkg, ctxs, n):
         b = np.array([got["ax"][i], got["ay"][i], got["az"][i]])
         err.append(np.linalg.norm(a - b) / np.linalg.norm(a))
     assert np.mean(err) < 5e-2, np.mean(err)
+
+
+def test_full_size_gas_disk_mixed_vs_fp64(pkg, ctxs):
+    """BASELINE config C2 (disk galaxy 4M with SPH gas) at full size: the default mixed-precision walk against the FP64
+    walk (the mode pinned to the reference at oracle sizes).  Decisions are taken in FP64 in both, so everything
+    discrete is identical; acc and dU/dt agree within the north_star tolerance (median 1e-6, p99 1e-4)."""
+    p = pkg.ics.disk_galaxy(4_000_000, seed=1234, gas_disk_fraction=0.25)
+    mh = pkg.ics.gas_mass_in_h(p, 64)
+    a = run_gpu(pkg, ctxs(8, True), p, 0.5, 1e18, mh)
+    ca, ta = ctxs(8, True).counters(), ctxs(8, True).target_counters()
+    b = run_gpu(pkg, ctxs(8, False), p, 0.5, 1e18, mh)
+    cb, tb = ctxs(8, False).counters(), ctxs(8, False).target_counters()
+    for k in ("n_in_tree", "n_outliers", "n_nodes", "max_depth", "interactions", "sph_interactions", "gas_groups", "gas_orphans", "node_visits"):
+        assert ca[k] == cb[k], k
+    for k in ta:
+        assert np.array_equal(ta[k], tb[k]), k
+    for k in ("h", "rho", "P", "T", "vis"):
+        assert np.array_equal(a[k], b[k]), k
+    assert a["R"] == b["R"] and ca["sph_interactions"] > 0
+    na = np.sqrt(a["ax"] ** 2 + a["ay"] ** 2 + a["az"] ** 2)
+    err = np.sqrt((a["ax"] - b["ax"]) ** 2 + (a["ay"] - b["ay"]) ** 2 + (a["az"] - b["az"]) ** 2) / np.sqrt(b["ax"] ** 2 + b["ay"] ** 2 + b["az"] ** 2)
+    assert np.all(np.isfinite(na)) and np.median(err) <= 1e-6 and np.percentile(err, 99) <= 1e-4, (np.median(err), np.percentile(err, 99), err.max())
+    gas = (p["type"] == 2) & (b["dUdt"] != 0)
+    du = np.abs(a["dUdt"][gas] - b["dUdt"][gas]) / np.abs(b["dUdt"][gas])
+    assert np.median(du) <= 1e-6 and np.percentile(du, 99) <= 1e-4, (np.median(du), np.percentile(du, 99))
+    print("C2 4M mixed vs fp64: acc median %.2e p99 %.2e max %.2e; dUdt median %.2e p99 %.2e" % (np.median(err), np.percentile(err, 99), err.max(), np.median(du), np.percentile(du, 99)))
