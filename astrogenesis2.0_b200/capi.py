@@ -39,7 +39,9 @@ class AosLayout(C.Structure):
 COUNTER_FIELDS = ("n_particles", "n_in_tree", "n_outliers", "n_nodes", "n_active", "max_depth", "edge_dropped", "interactions",
                   "node_interactions", "leaf_interactions", "sph_interactions", "node_visits", "mac_exact_fallbacks",
                   "groups", "gas_groups", "gas_orphans", "gas_ties_exact", "gas_ties_unresolved",
-                  "walk_rounds", "walk_popped", "walk_straddling", "walk_opened", "walk_tiles", "walk_stack_spills")
+                  "walk_rounds", "walk_popped", "walk_straddling", "walk_opened", "walk_tiles", "walk_stack_spills",
+                  "walk_ent_wide", "walk_ent_half", "walk_ent_quarter", "walk_bits_wide", "walk_bits_half", "walk_bits_quarter", "walk_ent_far",
+                  "walk_ent_class0", "walk_ent_class1", "walk_ent_class2")
 
 
 class Counters(C.Structure):
@@ -64,11 +66,12 @@ def load(build_if_needed=True):
     global _lib
     if _lib is not None:
         return _lib
-    if build_if_needed and _build.needs_build():
+    path = os.environ.get("AGB200_LIB") or _build.LIB          # A/B runs of two builds of the same ABI (development only)
+    if path == _build.LIB and build_if_needed and _build.needs_build():
         _build.build_lib()
-    if not os.path.exists(_build.LIB):
+    if not os.path.exists(path):
         raise RuntimeError("libagb200.so is not built; run __graft_entry__.build() (there is no CPU fallback)")
-    lib = C.CDLL(_build.LIB)
+    lib = C.CDLL(path)
     vp = C.c_void_p
     lib.agb_create.argtypes = [C.POINTER(vp), C.c_int, C.c_int]
     lib.agb_destroy.argtypes = [vp]

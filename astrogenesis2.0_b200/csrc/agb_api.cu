@@ -410,6 +410,10 @@ int agb_get_counters(agb_ctx* c, agb_counters* o)
     o->groups = (c->d.n + 31) / 32; o->gas_groups = h.n_gas_groups; o->gas_orphans = h.n_gas_orphans; o->gas_ties_exact = h.tie_exact; o->gas_ties_unresolved = h.tie_unresolved;
     o->walk_rounds = (int64_t)h.st_rounds; o->walk_popped = (int64_t)h.st_popped; o->walk_straddling = (int64_t)h.st_mixed; o->walk_opened = (int64_t)h.st_open;
     o->walk_tiles = (int64_t)h.st_drain; o->walk_stack_spills = (int64_t)h.c_spill;
+    o->walk_ent_wide = (int64_t)h.st_cls[0]; o->walk_ent_half = (int64_t)h.st_cls[1]; o->walk_ent_quarter = (int64_t)h.st_cls[2];
+    o->walk_bits_wide = (int64_t)h.st_cls[3]; o->walk_bits_half = (int64_t)h.st_cls[4]; o->walk_bits_quarter = (int64_t)h.st_cls[5];
+    o->walk_ent_far = (int64_t)h.st_cls[6];
+    o->walk_ent_class0 = (int64_t)h.st_cls[7]; o->walk_ent_class1 = (int64_t)h.st_cls[8]; o->walk_ent_class2 = (int64_t)h.st_cls[9];
     return AGB_OK;
 }
 

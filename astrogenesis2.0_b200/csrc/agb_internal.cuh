@@ -76,6 +76,7 @@ struct AgbScalars {
     int32_t walk_overflow, any_gas;
     int32_t n_gas_total, tie_exact, tie_unresolved, n_fold, n_long_runs, n_scan_tmp;
     unsigned long long st_rounds, st_popped, st_mixed, st_open, st_drain;   // walk statistics (tuning)
+    unsigned long long st_cls[10];     // counter mode: list entries / acceptor bits by lane span (any, one half, one quarter), far-list entries, entries per evaluation class
 };
 
 // Device-resident integrator state (agb_integrate.cu): mutable views of the owned particle copies + per-particle step

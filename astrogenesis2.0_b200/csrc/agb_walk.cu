@@ -25,6 +25,8 @@
 // reference's exact separately-rounded expression when within 1e-13 of the threshold.
 #include "agb_internal.cuh"
 #include <algorithm>
+#include <cstdlib>
+#include <type_traits>
 
 namespace {
 
@@ -83,6 +85,7 @@ struct WalkParams {
     const int32_t* act_list;                 // tree positions of the active targets (unused when every particle is active)
     int part, nparts;                        // this call walks the part-th of nparts slices of the active targets
     double theta, e0, globalTime;
+    float far_k2;                            // squared "far" distance in half-diagonals of the warp's box (mixed mode, class split)
 };
 
 enum { OUT_NONE = 0, OUT_ACCEPT = 1, OUT_OPEN = 2, OUT_MIXED = 3 };
@@ -238,6 +241,10 @@ template <bool COUNT, bool SPH, bool MIXED>
 __global__ void __launch_bounds__(WalkCfg<SPH>::TPB, WALK_CTAS) k_walk(const WalkParams P)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    // The three evaluation classes of the mixed-precision drain are used by the gravity-only kernels.  In the SPH kernels the
+    // extra loops push the code executed per group beyond the 32 KB instruction cache (measured: 25 % of the stall samples
+    // turn into "no instruction"), so those keep the single float-float loop.
+    constexpr bool CLASSES = MIXED && !SPH;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     WarpSmem<SPH>& sm = reinterpret_cast<WarpSmem<SPH>*>(smem_raw)[warp];
     int2* const spill = P.spill + (size_t)(blockIdx.x * WalkCfg<SPH>::WARPS + warp) * P.spill_per_warp;
@@ -247,10 +254,14 @@ __global__ void __launch_bounds__(WalkCfg<SPH>::TPB, WALK_CTAS) k_walk(const Wal
     const int n_nodes = P.s->n_nodes, n_in_tree = P.s->n_in_tree;
     const double theta = P.theta, theta2 = theta * theta;
     const bool fast_mac = theta > 0.0;
+    const double inv_theta2 = fast_mac ? 1.0 / theta2 : 0.0;
     const Slice sl = target_slice(P);
     const unsigned ngroups = (unsigned)((sl.a1 - sl.a0 + 31) / 32);
     // the law is evaluated in units of R so that r^2 (r^2+e0^2)^2 cannot overflow for any unit system
-    const double invR2 = R > 0.0 ? 1.0 / (R * R) : 1.0;
+    // ... in units of L = R / 2^16 in fact (a power of two: bit-identical FP64 results): the FP32 law below evaluates
+    // rsqrt(r^2 (r^2 + e0^2)^2) with ONE MUFU, and with this unit the argument stays inside the FP32 range for
+    // separations down to ~1e-12 R and softening lengths from ~1e-10 R to ~50 R.
+    const double invR2 = R > 0.0 ? 4294967296.0 / (R * R) : 1.0;
     const double e02s = P.e0 * P.e0 * invR2;
     const double GR3 = kG * invR2 * sqrt(invR2);
     // mixed precision (MIXED): displacements as float-float differences in units of R about the warp's box centre,
@@ -264,6 +275,7 @@ __global__ void __launch_bounds__(WalkCfg<SPH>::TPB, WALK_CTAS) k_walk(const Wal
 
     unsigned long long tot_node = 0, tot_leaf = 0, tot_sph = 0, tot_visit = 0, tot_exact = 0, tot_spill = 0;
     unsigned long long st_rounds = 0, st_popped = 0, st_mixed = 0, st_open = 0, st_drain = 0;
+    unsigned long long st_cls[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};   // COUNT only: list entries / set bits by lane span (any, one half, one quarter), far-list entries
 
     auto stack_put = [&](int idx, int2 v) {
         if (idx < SCAP) sm.stack[idx] = v;
@@ -314,15 +326,22 @@ __global__ void __launch_bounds__(WalkCfg<SPH>::TPB, WALK_CTAS) k_walk(const Wal
             const double hix = warp_max(valid ? tp.x : -inf), hiy = warp_max(valid ? tp.y : -inf), hiz = warp_max(valid ? tp.z : -inf);
             const double cgx = 0.5 * (lox + hix), cgy = 0.5 * (loy + hiy), cgz = 0.5 * (loz + hiz);
             float2 nth_x = make_float2(0.f, 0.f), nth_y = nth_x, nth_z = nth_x, ntl_x = nth_x, ntl_y = nth_x, ntl_z = nth_x;
-            float hh4cf = 0, hh4sf = 0;
+            float hh4cf = 0, hh4sf = 0, far2 = 0;
+            // the target's position about the centre of the warp's box in units of L, as a float-float pair
+            const double rx = (tp.x - cgx) * invR, ry = (tp.y - cgy) * invR, rz = (tp.z - cgz) * invR;
+            const float thx = (float)rx, thy = (float)ry, thz = (float)rz;
+            const float ntx = -thx, nty = -thy, ntz = -thz;
+            // half extents of the warp's box (rounded up); FP32 opening tests need |d| > half-diagonal / 16
+            const float bhx = (float)(0.5 * (hix - lox) * invR) * (1.0f + 1e-6f), bhy = (float)(0.5 * (hiy - loy) * invR) * (1.0f + 1e-6f),
+                        bhz = (float)(0.5 * (hiz - loz) * invR) * (1.0f + 1e-6f);
+            const float hd2 = bhx * bhx + bhy * bhy + bhz * bhz, guard2 = hd2 * (1.0f / 256.0f);
             if (MIXED) {
                 // minus the target's own float-float position, duplicated into both halves of a packed register
-                const double rx = (tp.x - cgx) * invR, ry = (tp.y - cgy) * invR, rz = (tp.z - cgz) * invR;
-                const float thx = (float)rx, thy = (float)ry, thz = (float)rz;
                 const float tlx = (float)(rx - (double)thx), tly = (float)(ry - (double)thy), tlz = (float)(rz - (double)thz);
                 nth_x = make_float2(-thx, -thx); nth_y = make_float2(-thy, -thy); nth_z = make_float2(-thz, -thz);
                 ntl_x = make_float2(-tlx, -tlx); ntl_y = make_float2(-tly, -tly); ntl_z = make_float2(-tlz, -tlz);
                 hh4sf = (float)(hh4 * invR2);
+                far2 = P.far_k2 * hd2;                                      // the squared "far" distance: 2 half-diagonals of the box
                 hh4cf = hh4sf * (1.0f + 1e-5f);                            // generous: the SPH pass decides
                 if (SPH && tgas) {
                     float* tf = reinterpret_cast<float*>(&sm.tsph[3 * lane + 2]);
@@ -336,6 +355,7 @@ __global__ void __launch_bounds__(WalkCfg<SPH>::TPB, WALK_CTAS) k_walk(const Wal
             const int32_t* const ff = P.far_front + (size_t)sgi * FAR_FCAP;
             const int n_fl = P.far_cnt[3 * sgi], n_ff = P.far_cnt[3 * sgi + 1];
             if (COUNT && valid) c_vis += P.far_cnt[3 * sgi + 2];
+            if (COUNT) st_cls[6] += n_fl;
             int sp = n_ff, lc = 0, cpos = 0;
             for (int i = lane; i < n_ff; i += 32) stack_put(i, make_int2(ff[i], (int)vmask));
             __syncwarp();
@@ -382,9 +402,35 @@ __global__ void __launch_bounds__(WalkCfg<SPH>::TPB, WALK_CTAS) k_walk(const Wal
                     unsigned mm = __ballot_sync(0xffffffffu, outcome == OUT_MIXED);
                     if (lane == 0) { st_rounds++; st_popped += cnt; st_mixed += __popc(mm); }
                     if (mm) {
-                        if (outcome == OUT_MIXED) sm.stage[lane] = make_double4(pmx, pmy, pmz, rad2);
+                        // Per-lane tests in FP32 first: the node's position about the box centre (units of L) and two thresholds on r^2
+                        // that bracket radius^2 / theta^2 by +-4e-5.  With |d| > half-diagonal / 16 (the guard) the FP32 r^2 is within
+                        // 7e-6 of the true one, so an FP32 verdict outside the bracket is the FP64 verdict; everything else (inside
+                        // the bracket, too close to the node, theta <= 0) is re-decided in FP64 exactly as before.
+                        if (outcome == OUT_MIXED) {
+                            const double thr = rad2 * invR2 * inv_theta2;
+                            float4* st = reinterpret_cast<float4*>(&sm.stage[lane]);
+                            st[0] = make_float4((float)((pmx - cgx) * invR), (float)((pmy - cgy) * invR), (float)((pmz - cgz) * invR), fmaxf((float)(thr * (1.0 + 4e-5)), guard2));
+                            st[1] = make_float4((float)(thr * (1.0 - 4e-5)), __int_as_float(e.x), 0.f, 0.f);
+                        }
                         __syncwarp();
                         const unsigned my = (unsigned)e.y;
+                        auto exact_mac = [&](const int node, bool& acc, bool& open) {
+                            const double4 q = P.src_pm[node];
+                            const double rad = scalbn(R, -(int)P.ndepth[node - N]), qw = rad * rad;
+                            const double dx = q.x - tp.x, dy = q.y - tp.y, dz = q.z - tp.z;
+                            const double r2 = fma(dz, dz, fma(dy, dy, dx * dx)), lhs = r2 * theta2;
+                            acc = false; open = false;
+                            if (r2 != 0.0) {                                         // Node.cpp:274 (r == 0 -> return)
+                                if (fast_mac && lhs > qw * (1.0 + 1e-13)) acc = true;
+                                else if (fast_mac && lhs < qw * (1.0 - 1e-13)) open = true;
+                                else {                                               // the reference's own expression, Node.cpp:271,331-334
+                                    const double r2e = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+                                    acc = __ddiv_rn(__dsqrt_rn(qw), __dsqrt_rn(r2e)) < theta;      // sqrt(radius^2) is exact: radius = R 2^-k
+                                    open = !acc;
+                                    tot_exact++;
+                                }
+                            }
+                        };
                         // two nodes per iteration: their dependency chains interleave
                         do {
                             const int src0 = __ffs(mm) - 1;
@@ -393,31 +439,18 @@ __global__ void __launch_bounds__(WalkCfg<SPH>::TPB, WALK_CTAS) k_walk(const Wal
                             const bool two = mm != 0u;
                             mm &= mm - 1;
                             const unsigned nmask0 = __shfl_sync(0xffffffffu, my, src0), nmask1 = __shfl_sync(0xffffffffu, my, src1);
-                            const double4 q0 = sm.stage[src0], q1 = sm.stage[src1];
-                            bool acc0 = false, open0 = false, acc1 = false, open1 = false;
-                            const double dx0 = q0.x - tp.x, dy0 = q0.y - tp.y, dz0 = q0.z - tp.z;
-                            const double dx1 = q1.x - tp.x, dy1 = q1.y - tp.y, dz1 = q1.z - tp.z;
-                            const double r20 = fma(dz0, dz0, fma(dy0, dy0, dx0 * dx0)), r21 = fma(dz1, dz1, fma(dy1, dy1, dx1 * dx1));
-                            const double lhs0 = r20 * theta2, lhs1 = r21 * theta2;
-                            if (((nmask0 >> lane) & 1u) && r20 != 0.0) {             // Node.cpp:274 (r == 0 -> return)
-                                if (fast_mac && lhs0 > q0.w * (1.0 + 1e-13)) acc0 = true;
-                                else if (fast_mac && lhs0 < q0.w * (1.0 - 1e-13)) open0 = true;
-                                else {                                               // the reference's own expression, Node.cpp:271,331-334
-                                    const double r2e = __dadd_rn(__dadd_rn(__dmul_rn(dx0, dx0), __dmul_rn(dy0, dy0)), __dmul_rn(dz0, dz0));
-                                    acc0 = __ddiv_rn(__dsqrt_rn(q0.w), __dsqrt_rn(r2e)) < theta;   // sqrt(radius^2) is exact: radius = R 2^-k
-                                    open0 = !acc0;
-                                    tot_exact++;
-                                }
-                            }
-                            if (two && ((nmask1 >> lane) & 1u) && r21 != 0.0) {
-                                if (fast_mac && lhs1 > q1.w * (1.0 + 1e-13)) acc1 = true;
-                                else if (fast_mac && lhs1 < q1.w * (1.0 - 1e-13)) open1 = true;
-                                else {
-                                    const double r2e = __dadd_rn(__dadd_rn(__dmul_rn(dx1, dx1), __dmul_rn(dy1, dy1)), __dmul_rn(dz1, dz1));
-                                    acc1 = __ddiv_rn(__dsqrt_rn(q1.w), __dsqrt_rn(r2e)) < theta;
-                                    open1 = !acc1;
-                                    tot_exact++;
-                                }
+                            const float4* s0 = reinterpret_cast<const float4*>(&sm.stage[src0]);
+                            const float4* s1 = reinterpret_cast<const float4*>(&sm.stage[src1]);
+                            const float4 a0_ = s0[0], b0_ = s0[1], a1_ = s1[0], b1_ = s1[1];
+                            const float dx0 = a0_.x + ntx, dy0 = a0_.y + nty, dz0 = a0_.z + ntz, dx1 = a1_.x + ntx, dy1 = a1_.y + nty, dz1 = a1_.z + ntz;
+                            const float r20 = fmaf(dz0, dz0, fmaf(dy0, dy0, dx0 * dx0)), r21 = fmaf(dz1, dz1, fmaf(dy1, dy1, dx1 * dx1));
+                            const bool in0 = (nmask0 >> lane) & 1u, in1 = two && ((nmask1 >> lane) & 1u);
+                            bool acc0 = in0 && fast_mac && r20 > a0_.w, open0 = in0 && fast_mac && r20 < b0_.x && r20 > guard2;
+                            bool acc1 = in1 && fast_mac && r21 > a1_.w, open1 = in1 && fast_mac && r21 < b1_.x && r21 > guard2;
+                            const bool ex0 = in0 && !acc0 && !open0, ex1 = in1 && !acc1 && !open1;
+                            if (ex0 || ex1) {
+                                if (ex0) exact_mac(__float_as_int(b0_.y), acc0, open0);
+                                if (ex1) exact_mac(__float_as_int(b1_.y), acc1, open1);
                             }
                             const unsigned a0 = __ballot_sync(0xffffffffu, acc0), o0 = __ballot_sync(0xffffffffu, open0);
                             const unsigned a1 = __ballot_sync(0xffffffffu, acc1), o1 = __ballot_sync(0xffffffffu, open1);
@@ -466,22 +499,52 @@ __global__ void __launch_bounds__(WalkCfg<SPH>::TPB, WALK_CTAS) k_walk(const Wal
                     __syncwarp();
                     bool src_gas = false;
                     unsigned pc_mask = 0u; int ex_part = -1;
+                    // Mixed mode sorts the tile's entries into three classes, evaluated by three loops of decreasing speed:
+                    //   0  far + accepted by every target: single-float displacements, no mask
+                    //   1  far: single-float displacements
+                    //   2  near: float-float displacements (close pairs cancel)
+                    // "far" = at least 2 half-diagonals of the warp's box away from the box: dropping the low parts then costs
+                    // <= 2^-24 (|s| + |t|) / |d| <= 1.2e-7 relative per pair.
+                    int pos = lane, cls = 3;
+                    int2 e = make_int2(0, 0);
+                    if (lane < cnt) e = sm.list[base + lane];
+                    if (CLASSES) __syncwarp();                                      // the tile's list entries are rewritten in class order below
+                    double4 q = make_double4(0, 0, 0, 0), gvv = q;
+                    float hx = 0, hy = 0, hz = 0, lx = 0, ly = 0, lz = 0;
                     if (lane < cnt) {
-                        const int2 e = sm.list[base + lane];
-                        const double4 q = P.src_pm[e.x];
+                        q = P.src_pm[e.x];
+                        if (SPH && wgas) { gvv = P.src_gv[e.x]; src_gas = gvv.w > 0.0; }   // independent of the load above
                         if (MIXED) {
-                            // two sources share one 64-byte record, components interleaved (x0 x1 y0 y1 | z0 z1 m0 m1 | lo parts),
-                            // so the evaluation loop can use Blackwell's packed FP32x2 instructions across the pair
                             const double rx = (q.x - cgx) * invR, ry = (q.y - cgy) * invR, rz = (q.z - cgz) * invR;
-                            const float hx = (float)rx, hy = (float)ry, hz = (float)rz;
-                            float* sf = reinterpret_cast<float*>(&sm.stage[lane & ~1]) + (lane & 1);
-                            sf[0] = hx; sf[2] = hy; sf[4] = hz; sf[6] = (float)(q.w * inv_m0);
-                            sf[8] = (float)(rx - (double)hx); sf[10] = (float)(ry - (double)hy); sf[12] = (float)(rz - (double)hz);
-                        } else sm.stage[lane] = q;
-                        if (SPH && wgas) { const double4 gvv = P.src_gv[e.x]; src_gas = gvv.w > 0.0; sm.gst[lane] = gvv; }   // independent of the load above
+                            hx = (float)rx; hy = (float)ry; hz = (float)rz;
+                            lx = (float)(rx - (double)hx); ly = (float)(ry - (double)hy); lz = (float)(rz - (double)hz);
+                            if (CLASSES) {
+                                const float fx_ = fmaxf(0.f, fabsf(hx) - bhx), fy_ = fmaxf(0.f, fabsf(hy) - bhy), fz_ = fmaxf(0.f, fabsf(hz) - bhz);
+                                const bool far = fmaf(fz_, fz_, fmaf(fy_, fy_, fx_ * fx_)) >= far2;
+                                cls = !far ? 2 : (unsigned)e.y == vmask ? 0 : 1;
+                            } else cls = 2;
+                        }
                         // accepted pairs of this entry: lanes in the mask, minus the target's own leaf, none for a massless leaf
                         pc_mask = q.w != 0.0 ? (unsigned)e.y : 0u;
                         ex_part = e.x < N ? e.x : -1;
+                    }
+                    int b0 = 0, b1 = 0;                                             // class loops: [0, b0) [b0, b1) [b1, cnt)
+                    if (CLASSES) {
+                        const unsigned m0_ = __ballot_sync(0xffffffffu, cls == 0), m1_ = __ballot_sync(0xffffffffu, cls == 1), m2_ = __ballot_sync(0xffffffffu, cls == 2);
+                        const int n0 = __popc(m0_), n1 = __popc(m1_);
+                        pos = cls == 0 ? __popc(m0_ & lt) : cls == 1 ? n0 + __popc(m1_ & lt) : n0 + n1 + __popc(m2_ & lt);
+                        b0 = n0 & ~1; b1 = (n0 + n1) & ~1;                          // a pair that straddles two classes runs in the slower one
+                        if (lane < cnt) sm.list[base + pos] = e;
+                    }
+                    if (lane < cnt) {
+                        if (MIXED) {
+                            // two sources share one 64-byte record, components interleaved (x0 x1 y0 y1 | z0 z1 m0 m1 | lo parts),
+                            // so the evaluation loop can use Blackwell's packed FP32x2 instructions across the pair
+                            float* sf = reinterpret_cast<float*>(&sm.stage[pos & ~1]) + (pos & 1);
+                            sf[0] = hx; sf[2] = hy; sf[4] = hz; sf[6] = (float)(q.w * inv_m0);
+                            sf[8] = lx; sf[10] = ly; sf[12] = lz;
+                        } else sm.stage[lane] = q;
+                        if (SPH && wgas) sm.gst[pos] = gvv;
                     }
                     {   // a leaf that is one of this warp's own targets does not count as an interaction with itself
                         const bool maybe = ex_part >= tmin && ex_part <= tmax;
@@ -490,48 +553,79 @@ __global__ void __launch_bounds__(WalkCfg<SPH>::TPB, WALK_CTAS) k_walk(const Wal
                             for (int l2 = 0; l2 < 32; l2++) { const int tl = __shfl_sync(0xffffffffu, (int)t, l2); if (ex_part >= 0 && ex_part == tl) pc_mask &= ~(1u << l2); }
                         if (ex_part >= 0) tot_leaf += __popc(pc_mask); else tot_node += __popc(pc_mask);
                     }
+                    if (COUNT) {
+                        // tuning statistics: how many list entries have their acceptors inside one half / one quarter of the warp
+                        const unsigned m = pc_mask;
+                        int span = -1;
+                        if (m) {
+                            const bool qt = !(m & ~0xffu) || !(m & ~0xff00u) || !(m & ~0xff0000u) || !(m & ~0xff000000u);
+                            const bool hf = !(m & 0xffff0000u) || !(m & 0xffffu);
+                            span = qt ? 2 : hf ? 1 : 0;
+                        }
+#pragma unroll
+                        for (int c = 0; c < 3; c++) {
+                            st_cls[c] += __popc(__ballot_sync(0xffffffffu, span == c));
+                            st_cls[3 + c] += __reduce_add_sync(0xffffffffu, span == c ? __popc(m) : 0);
+                            st_cls[7 + c] += __popc(__ballot_sync(0xffffffffu, cls == c));      // evaluation classes (mixed mode)
+                        }
+                    }
                     if (MIXED && lane == cnt && (cnt & 1)) {
                         // odd tile: the unused half of the last pair must hold finite numbers (0 * inf would poison the sums)
                         float* sf = reinterpret_cast<float*>(&sm.stage[lane & ~1]) + (lane & 1);
                         sf[0] = 1.f; sf[2] = 1.f; sf[4] = 1.f; sf[6] = 0.f; sf[8] = 0.f; sf[10] = 0.f; sf[12] = 0.f;
                     }
-                    const unsigned gasmask = (SPH && wgas) ? __ballot_sync(0xffffffffu, src_gas) : 0u;   // tile entries that hold gas
+                    const unsigned gasmask = (SPH && wgas) ? __reduce_or_sync(0xffffffffu, src_gas ? 1u << pos : 0u) : 0u;   // tile positions that hold gas
                     if (base + 32 + lane < lc) asm volatile("prefetch.global.L1 [%0];" ::"l"(P.src_pm + sm.list[base + 32 + lane].x));
                     __syncwarp();
                     unsigned gate = 0;                                                   // per lane: entries within ~2h (SPH candidates)
                     if (MIXED) {
                         float2 fax = make_float2(0.f, 0.f), fay = fax, faz = fax;
-                        const float2 tiny2 = make_float2(1e-30f, 1e-30f), e022 = make_float2(e02f, e02f);
+                        // the law m d / (r (r^2 + e0^2)) with one MUFU per source: rsqrt(r^2 (r^2 + e0^2)^2).  Skip rules as in the
+                        // FP64 loop: d = 0 exactly for the own leaf / coincident sources, and the 1e-37 floor keeps the factor
+                        // finite so that f * d = 0; a massless source has m = 0.
+                        const float2 tiny2 = make_float2(1e-37f, 1e-37f), e022 = make_float2(e02f, e02f);
+                        auto pair_loop = [&](auto lo_, auto masked_, const int j0, const int j1) {
+                            constexpr bool LO = decltype(lo_)::value, MASKED = decltype(masked_)::value;
 #pragma unroll 2
-                        for (int j = 0; j < cnt; j += 2) {
-                            const int4 ee = *reinterpret_cast<const int4*>(&sm.list[base + j]);      // entries j, j+1: (src, mask) x 2
-                            const float4* rec = reinterpret_cast<const float4*>(&sm.stage[j]);
-                            const float4 r0 = rec[0], r1 = rec[1], r2_ = rec[2], r3 = rec[3];
-                            const bool bit0 = ((unsigned)ee.y >> lane) & 1u, bit1 = (j + 1 < cnt) && (((unsigned)ee.w >> lane) & 1u);
-                            // float-float displacement for both sources at once (FADD2)
-                            const float2 dx = __fadd2_rn(__fadd2_rn(make_float2(r0.x, r0.y), nth_x), __fadd2_rn(make_float2(r2_.x, r2_.y), ntl_x));
-                            const float2 dy = __fadd2_rn(__fadd2_rn(make_float2(r0.z, r0.w), nth_y), __fadd2_rn(make_float2(r2_.z, r2_.w), ntl_y));
-                            const float2 dz = __fadd2_rn(__fadd2_rn(make_float2(r1.x, r1.y), nth_z), __fadd2_rn(make_float2(r3.x, r3.y), ntl_z));
-                            const float2 r2 = __ffma2_rn(dz, dz, __ffma2_rn(dy, dy, __fmul2_rn(dx, dx)));
-                            // same skip rules as the FP64 loop: d = 0 exactly for the own leaf / coincident sources, and the 1e-30
-                            // floor (in units of R^2; real separations are >= 2^-84) keeps the factor finite so f * d = 0
-                            const float2 r2c = __fadd2_rn(r2, tiny2), q2 = __fadd2_rn(r2c, e022);
-                            float2 rinv, iq;
-                            asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rinv.x) : "f"(r2c.x));
-                            asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rinv.y) : "f"(r2c.y));
-                            asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(iq.x) : "f"(q2.x));
-                            asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(iq.y) : "f"(q2.y));
-                            float2 f = __fmul2_rn(make_float2(r1.z, r1.w), __fmul2_rn(rinv, iq));
-                            f.x = bit0 ? f.x : 0.f; f.y = bit1 ? f.y : 0.f;
-                            fax = __ffma2_rn(f, dx, fax); fay = __ffma2_rn(f, dy, fay); faz = __ffma2_rn(f, dz, faz);
-                            if (SPH && wgas) gate |= ((bit0 && r2.x < hh4cf ? 1u : 0u) << j) | ((bit1 && r2.y < hh4cf ? 2u : 0u) << j);
-                            if (COUNT) {
-                                const bool seen0 = bit0 && r1.z != 0.f, ok0 = seen0 && r2.x != 0.f;
-                                const bool seen1 = bit1 && r1.w != 0.f, ok1 = seen1 && r2.y != 0.f;
-                                if (ee.x < N) { c_vis += seen0; c_al += ok0; } else c_an += ok0;
-                                if (ee.z < N) { c_vis += seen1; c_al += ok1; } else c_an += ok1;
+                            for (int j = j0; j < j1; j += 2) {
+                                const float4* rec = reinterpret_cast<const float4*>(&sm.stage[j]);
+                                const float4 r0 = rec[0], r1 = rec[1];
+                                float2 dx = __fadd2_rn(make_float2(r0.x, r0.y), nth_x), dy = __fadd2_rn(make_float2(r0.z, r0.w), nth_y), dz = __fadd2_rn(make_float2(r1.x, r1.y), nth_z);
+                                if (LO) {                                          // float-float displacement for both sources at once (FADD2)
+                                    const float4 r2_ = rec[2]; const float2 r3 = *reinterpret_cast<const float2*>(rec + 3);
+                                    dx = __fadd2_rn(dx, __fadd2_rn(make_float2(r2_.x, r2_.y), ntl_x));
+                                    dy = __fadd2_rn(dy, __fadd2_rn(make_float2(r2_.z, r2_.w), ntl_y));
+                                    dz = __fadd2_rn(dz, __fadd2_rn(r3, ntl_z));
+                                }
+                                const float2 r2 = __ffma2_rn(dz, dz, __ffma2_rn(dy, dy, __fmul2_rn(dx, dx)));
+                                const float2 q2 = __fadd2_rn(r2, e022);
+                                const float2 xx = __ffma2_rn(__fmul2_rn(r2, q2), q2, tiny2);
+                                float2 w;
+                                asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(w.x) : "f"(xx.x));
+                                asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(w.y) : "f"(xx.y));
+                                float2 f = __fmul2_rn(make_float2(r1.z, r1.w), w);
+                                bool bit0 = true, bit1 = true;
+                                int4 ee = make_int4(0, 0, 0, 0);
+                                if (MASKED || COUNT) {                             // counter mode: same arithmetic, plus the bookkeeping
+                                    ee = *reinterpret_cast<const int4*>(&sm.list[base + j]);      // entries j, j+1: (src, mask) x 2
+                                    bit0 = ((unsigned)ee.y >> lane) & 1u; bit1 = (j + 1 < cnt) && (((unsigned)ee.w >> lane) & 1u);
+                                }
+                                if (MASKED) { f.x = bit0 ? f.x : 0.f; f.y = bit1 ? f.y : 0.f; }
+                                fax = __ffma2_rn(f, dx, fax); fay = __ffma2_rn(f, dy, fay); faz = __ffma2_rn(f, dz, faz);
+                                if (SPH && wgas) gate |= ((bit0 && r2.x < hh4cf ? 1u : 0u) << j) | ((bit1 && r2.y < hh4cf ? 2u : 0u) << j);
+                                if (COUNT) {
+                                    const bool seen0 = bit0 && r1.z != 0.f, ok0 = seen0 && r2.x != 0.f;
+                                    const bool seen1 = bit1 && r1.w != 0.f, ok1 = seen1 && r2.y != 0.f;
+                                    if (ee.x < N) { c_vis += seen0; c_al += ok0; } else c_an += ok0;
+                                    if (ee.z < N) { c_vis += seen1; c_al += ok1; } else c_an += ok1;
+                                }
                             }
+                        };
+                        if (CLASSES) {
+                            pair_loop(std::false_type{}, std::false_type{}, 0, b0);
+                            pair_loop(std::false_type{}, std::true_type{}, b0, b1);
                         }
+                        pair_loop(std::true_type{}, std::true_type{}, b1, cnt);
                         ax = fma(acc_scale, (double)(fax.x + fax.y), ax); ay = fma(acc_scale, (double)(fay.x + fay.y), ay); az = fma(acc_scale, (double)(faz.x + faz.y), az);
                     } else {
 #pragma unroll 4
@@ -682,6 +776,7 @@ __global__ void __launch_bounds__(WalkCfg<SPH>::TPB, WALK_CTAS) k_walk(const Wal
         }
 
         if (active) {
+            if (!valid) { ax = 0; ay = 0; az = 0; }                            // Node.cpp:265; such lanes are not masked out in the class-0 loop
             const uint32_t p = P.perm[t];
             P.ax[p] = ax; P.ay[p] = ay; P.az[p] = az;                           // Tree.cpp:77 (acc = 0) + accumulated force
             if (SPH && tgas && dU != 0.0) P.dUdt[p] += dU;
@@ -701,6 +796,7 @@ __global__ void __launch_bounds__(WalkCfg<SPH>::TPB, WALK_CTAS) k_walk(const Wal
         if (tot_spill) atomicAdd(&P.s->c_spill, tot_spill);
         atomicAdd(&P.s->st_rounds, st_rounds); atomicAdd(&P.s->st_popped, st_popped); atomicAdd(&P.s->st_mixed, st_mixed);
         atomicAdd(&P.s->st_open, st_open); atomicAdd(&P.s->st_drain, st_drain);
+        if (COUNT) for (int c = 0; c < 10; c++) atomicAdd(&P.s->st_cls[c], st_cls[c]);
     }
 }
 
@@ -708,6 +804,7 @@ __global__ void k_walk_reset(AgbScalars* s)
 {
     s->walk_next_group = 0; s->walk_overflow = 0;
     s->st_rounds = 0; s->st_popped = 0; s->st_mixed = 0; s->st_open = 0; s->st_drain = 0;
+    for (int c = 0; c < 10; c++) s->st_cls[c] = 0;
     s->c_interactions = 0; s->c_node = 0; s->c_leaf = 0; s->c_sph = 0; s->c_visits = 0; s->c_exact = 0; s->c_spill = 0;
 }
 
@@ -816,6 +913,9 @@ int agb_launch_walk(AgbDev& d, AgbScalars* s, double globalTime, double e0, doub
     P.far_list = d.far_list; P.far_front = d.far_front; P.far_cnt = d.far_cnt;
     P.s = s; P.N = d.n; P.act_list = d.act_list; P.part = part; P.nparts = nparts;
     P.theta = theta; P.e0 = e0; P.globalTime = globalTime;
+    // tuning knob (not part of the ABI): AGB200_WALK_FAR_K2=1e30 sends every pair through the float-float loop
+    static const float far_k2 = getenv("AGB200_WALK_FAR_K2") ? (float)atof(getenv("AGB200_WALK_FAR_K2")) : 4.0f;
+    P.far_k2 = far_k2;
     int launches = 0;
     const int nb = (int)((d.n + 255) / 256);
     k_walk_reset<<<1, 1, 0, st>>>(s); launches++;

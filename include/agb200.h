@@ -89,6 +89,11 @@ typedef struct {
     /* walk statistics: pop rounds, nodes popped, nodes straddling the opening radius of their warp, nodes opened by the
      * whole mask, 32-source tiles drained, rounds that touched the global-memory part of the stack */
     int64_t walk_rounds, walk_popped, walk_straddling, walk_opened, walk_tiles, walk_stack_spills;
+    /* counter mode only: interaction-list entries whose acceptors span the warp / sit in one half / in one quarter of its
+     * lanes, the acceptor bits of each class, and the entries imported from the far-field prepass (per group) */
+    int64_t walk_ent_wide, walk_ent_half, walk_ent_quarter, walk_bits_wide, walk_bits_half, walk_bits_quarter, walk_ent_far;
+    /* ... and the entries evaluated by each of the three pair loops of the mixed-precision walk (far + every target, far, near) */
+    int64_t walk_ent_class0, walk_ent_class1, walk_ent_class2;
 } agb_counters;
 
 /* -------- lifetime: `new Tree(sim)` / `delete tree`, but persistent across steps (pooled memory) */

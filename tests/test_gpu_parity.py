@@ -149,6 +149,30 @@ def test_run_to_run_bitwise_reproducible(pkg, ctxs):
         assert np.array_equal(a[k], b[k]), k
 
 
+@pytest.mark.parametrize("mixed", PRECISIONS)
+def test_counter_mode_is_the_production_arithmetic(pkg, ctxs, mixed):
+    """The parity tests above run with per-target counters switched on (a different kernel instantiation).  The production
+    instantiation (counters off: what bench.py times) must produce the same bits in the default mixed mode, so that every
+    tolerance asserted against the oracle holds for it too."""
+    p = pkg.ics.disk_galaxy(100000, seed=5)
+    mh = pkg.ics.gas_mass_in_h(p, 64)
+    a = run_gpu(pkg, ctxs(8, mixed), p, 0.5, 1e18, mh)
+    plain = pkg.Context(0, 8)
+    plain.set_option(pkg.capi.AGB_OPT_PRECISION, 1 if mixed else 0)
+    try:
+        b = run_gpu(pkg, plain, p, 0.5, 1e18, mh)
+        assert plain.counters()["interactions"] == ctxs(8, mixed).counters()["interactions"]
+    finally:
+        plain.close()
+    for k in ("h", "rho", "P", "T", "vis"):
+        assert np.array_equal(a[k], b[k]), k
+    for k in ("ax", "ay", "az", "dUdt"):
+        if mixed:
+            assert np.array_equal(a[k], b[k]), k
+        else:   # the FP64 loop is plain C++: the two instantiations may contract different multiply-adds into FMAs
+            assert np.allclose(a[k], b[k], rtol=1e-11, atol=0), k
+
+
 def test_slices_equal_whole(pkg, ctxs):
     """Multi-GPU sharding: walking the tree-ordered targets in 1 or 4 slices gives bit-identical results."""
     ctx = ctxs(8)
