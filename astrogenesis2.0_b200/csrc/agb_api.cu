@@ -70,6 +70,7 @@ void free_pool(agb_ctx* c)
     dfree(d.rec); dfree(d.blockhist); dfree(d.scanblk);
     dfree(d.far_list); dfree(d.far_front); dfree(d.far_cnt); dfree(d.act_list);
     dfree(d.c_visits); dfree(d.c_accn); dfree(d.c_accl); dfree(d.c_sph);
+    dfree(d.rec_ent); dfree(d.rec_next); dfree(d.rec_head); d.rec_cap = 0;
     d.cap = 0;
 }
 
@@ -110,6 +111,21 @@ int ensure_counters(agb_ctx* c)
     AgbDev& d = c->d;
     if (d.c_visits) return AGB_OK;
     CK(dalloc(d.c_visits, (size_t)d.cap)); CK(dalloc(d.c_accn, (size_t)d.cap)); CK(dalloc(d.c_accl, (size_t)d.cap)); CK(dalloc(d.c_sph, (size_t)d.cap));
+    return AGB_OK;
+}
+
+// Tile records of the mixed-precision SPH pass (260 B each): at most one per 32-source tile of a group with gas targets.
+// The pool starts small; when a walk runs out of records k_sph does nothing, agb_forces grows the pool to what that walk
+// asked for and walks again (once per run in practice: the pool is kept across steps).
+int ensure_sph_records(agb_ctx* c, int64_t want)
+{
+    AgbDev& d = c->d;
+    want = std::min<int64_t>(std::max<int64_t>(want, std::max<int64_t>(65536, d.cap / 8)), 0x7fffff00);
+    if (!d.rec_head) CK(dalloc(d.rec_head, (size_t)d.cap / 32 + 16));
+    if (d.rec_ent && d.rec_cap >= want) return AGB_OK;
+    dfree(d.rec_ent); dfree(d.rec_next); d.rec_cap = 0;
+    CK(dalloc(d.rec_ent, (size_t)want * 32)); CK(dalloc(d.rec_next, (size_t)want));
+    d.rec_cap = want;
     return AGB_OK;
 }
 
@@ -375,23 +391,31 @@ int agb_forces_slice(agb_ctx* c, double global_time, double e0, double theta, in
     AgbDev& d = c->d;
     if (d.n == 0) { c->forces_done = true; return AGB_OK; }
     if (c->target_counters) { int rc = ensure_counters(c); if (rc) return rc; }
+    if (c->hs.any_gas && c->mixed) { int rc = ensure_sph_records(c, 0); if (rc) return rc; }
     // The targets are the ACTIVE particles in tree order; slice boundaries fall on multiples of 256 of them (the far-field
     // super-groups), so every warp owns the same 32 targets whatever the number of parts: results are bit-identical for
     // 1, 2, 4, 8 GPUs (same groups => same summation order).  The slicing itself happens on the device (agb_walk.cu).
     CK(cudaEventRecord(c->ev[6], c->st));
     // gas targets need h/rho/P: if the caller skipped gas_density they are orphans (h = 0) and get no SPH, like the reference
-    c->launches += agb_launch_walk(d, c->s, global_time, e0, theta, part, nparts, c->target_counters, c->hs.any_gas != 0, c->mixed, c->sm_count, c->st, c->ev[0], c->ev[1]);
-    CK(cudaEventRecord(c->ev[7], c->st));
-    CK(cudaGetLastError());
-    int rc = fetch_scalars(c);
-    if (rc) return rc;
+    const bool any_gas = c->hs.any_gas != 0;
+    for (int attempt = 0;; attempt++) {
+        c->launches += agb_launch_walk(d, c->s, global_time, e0, theta, part, nparts, c->target_counters, any_gas, c->mixed, c->sm_count, c->st, c->ev[0], c->ev[1]);
+        CK(cudaEventRecord(c->ev[7], c->st));
+        CK(cudaGetLastError());
+        int rc = fetch_scalars(c);
+        if (rc) return rc;
+        if (c->hs.walk_overflow != 2 || attempt >= 2) break;
+        // out of SPH tile records: nothing but acc was written (k_sph skipped itself); grow the pool and walk again
+        rc = ensure_sph_records(c, (int64_t)(c->hs.cand_cursor + c->hs.cand_cursor / 4) + 1024);
+        if (rc) return rc;
+    }
     float ms = 0;
     if (cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]) == cudaSuccess) c->phase_ms[3] = ms;
     if (cudaEventElapsedTime(&ms, c->ev[6], c->ev[7]) == cudaSuccess) c->phase_ms[4] = ms;
     if (c->vis_timed && cudaEventElapsedTime(&ms, c->ev[2], c->ev[3]) == cudaSuccess) c->phase_ms[1] = ms;
     if (c->gas_timed && cudaEventElapsedTime(&ms, c->ev[4], c->ev[5]) == cudaSuccess) c->phase_ms[2] = ms;
     (void)cudaGetLastError();
-    if (c->hs.walk_overflow) { c->err = "traversal stack overflow"; return AGB_ERR_NOMEM; }
+    if (c->hs.walk_overflow) { c->err = c->hs.walk_overflow == 2 ? "SPH tile-record pool overflow" : "traversal stack overflow"; return AGB_ERR_NOMEM; }
     c->forces_done = true; c->counters_valid = c->target_counters;
     return AGB_OK;
 }

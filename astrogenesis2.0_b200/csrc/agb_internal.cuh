@@ -60,6 +60,8 @@ struct AgbDev {
     // far-field prepass output, per super-group of 256 targets
     int32_t *far_list = nullptr, *far_front = nullptr, *far_cnt = nullptr;
     int32_t* act_list = nullptr;       // tree positions of the active targets of the current forces call
+    // mixed-precision SPH: records (32 x (source, accepting gas targets) + link) written by the walk for k_sph, last record per group
+    int2* rec_ent = nullptr; int32_t *rec_next = nullptr, *rec_head = nullptr; int64_t rec_cap = 0;
 };
 
 // Device-resident scalars of one step (read back in a single copy when the host needs them).
@@ -70,6 +72,7 @@ struct AgbScalars {
     int32_t n_in_tree, n_outliers, n_nodes, dup_keys, edge_dropped, max_depth;
     int32_t n_groups, n_gas_groups, n_gas_orphans, n_active;
     unsigned int walk_next_group;
+    unsigned long long cand_cursor;    // bump allocator of the SPH tile records
     unsigned long long c_interactions, c_node, c_leaf, c_sph, c_visits, c_exact, c_spill;
     int32_t bintotal[256];
     int32_t vis_level;

@@ -43,18 +43,28 @@ constexpr double kG = 6.67430e-11;         // Math/Constants.h:7
 constexpr double kPI = 3.14159265358979323846;
 constexpr double kGAMMA = 5.0 / 3.0;
 
-// Per-warp shared memory.  The SPH operands exist only in the SPH variants: the gravity-only kernels need 8 KB per warp
-// instead of 13 KB, which leaves ~100 KB of the SM for L1 (10 warps per CTA were tried: register spills cost more).
-template <bool SPH> struct SphSmem {
-    double4 tsph[96];                      // per gas target: (1/h, 1/(pi h^4), 2 P/rho^2, sound speed), (vx, vy, vz, h), 8 floats: -(float-float position), (2h/R)^2
-    double4 res[32];                       // SPH pair results (fx, fy, fz, dU) on their way to the owning lane
+// Per-warp shared memory.  In-walk SPH operands exist only in the FP64 SPH kernels; the mixed-precision SPH kernels only
+// record, per tile, which (target, source) pairs lie within ~2h for k_sph; the gravity-only kernels need 8 KB per warp.
+constexpr int REC_BATCH = 8;               // tile records a warp takes from the pool at a time
+template <bool INWALK> struct SphSmem { double4 tsph[1], gst[1]; };
+template <> struct SphSmem<true> {
+    double4 tsph[96];                      // per gas target: (1/h, 1/(pi h^4), 2 P/rho^2, sound speed), (vx, vy, vz, h)
     double4 gst[32];                       // drain: (velocity | mVel, gasMass) of the tile's gas-bearing sources
 };
-template <> struct SphSmem<false> { double4 tsph[1], res[1], gst[1]; };
-template <bool SPH> struct WarpSmem : SphSmem<SPH> {
+template <bool SPH, bool MIXED> struct WarpSmem : SphSmem<SPH && !MIXED> {
+    int2 rsrc[SPH && MIXED ? 64 : 2];      // SPLIT: (source, gas targets that accepted it) waiting for the next k_sph record
     int2 list[LCAP];
     int2 stack[SCAP];
-    double4 stage[32];                     // drain: the 32 sources of a tile; traversal: (COM, mass) of straddling nodes
+    double4 stage[32];                     // drain: the 32 sources of a tile; traversal: FP32 records of straddling nodes
+};
+// k_sph: per gas target (1/h, 1/(pi h^4), 2 P/rho^2, sound speed), (vx, vy, vz, h), 8 floats: -(float-float position), (2h/L)^2, tree position
+struct SphWarp {
+    double4 tsph[96];
+    double4 res[32];                       // pair results (fx, fy, fz, dU) on their way to the owning lane
+    double4 gst[32];                       // (velocity | mVel, gasMass) of the tile's sources
+    double4 stage[32];                     // float-float records of the tile's sources, two per 64-byte record
+    int list[32];                          // the record's sources
+    unsigned lmask[32];                    // ... and the gas targets that accepted each (0 for sources without gas)
 };
 template <bool SPH> struct WalkCfg { static constexpr int WARPS = 8, TPB = WARPS * 32; };
 
@@ -85,6 +95,9 @@ struct WalkParams {
     const int32_t* act_list;                 // tree positions of the active targets (unused when every particle is active)
     int part, nparts;                        // this call walks the part-th of nparts slices of the active targets
     double theta, e0, globalTime;
+    // mixed SPH: records written by k_walk for k_sph: 32 x (source, mask of the gas targets that accepted it) and a link to the
+    // group's previous record; rec_head[g] = last record of group g (-1: none)
+    int2* rec_ent; int32_t *rec_next, *rec_head; int64_t rec_cap;
     float far_k2;                            // squared "far" distance in half-diagonals of the warp's box (mixed mode, class split)
 };
 
@@ -92,6 +105,7 @@ enum { OUT_NONE = 0, OUT_ACCEPT = 1, OUT_OPEN = 2, OUT_MIXED = 3 };
 
 __device__ __forceinline__ double warp_min(double v) { for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o)); return v; }
 __device__ __forceinline__ double warp_max(double v) { for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o)); return v; }
+__device__ __forceinline__ float warp_max_f(float v) { return __int_as_float(__reduce_max_sync(0xffffffffu, __float_as_int(v))); }   // v >= 0
 __device__ __forceinline__ int warp_incl_scan(int v, int lane)
 {
     for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o) v += t; }
@@ -241,12 +255,11 @@ template <bool COUNT, bool SPH, bool MIXED>
 __global__ void __launch_bounds__(WalkCfg<SPH>::TPB, WALK_CTAS) k_walk(const WalkParams P)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    // The three evaluation classes of the mixed-precision drain are used by the gravity-only kernels.  In the SPH kernels the
-    // extra loops push the code executed per group beyond the 32 KB instruction cache (measured: 25 % of the stall samples
-    // turn into "no instruction"), so those keep the single float-float loop.
-    constexpr bool CLASSES = MIXED && !SPH;
+    constexpr bool CLASSES = MIXED, FULLCLASS = CLASSES;
+    constexpr bool INWALK = SPH && !MIXED;      // FP64 mode evaluates SPH pairs inside the walk
+    constexpr bool SPLIT = SPH && MIXED;        // mixed mode records the pairs within ~2h; k_sph evaluates them afterwards
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    WarpSmem<SPH>& sm = reinterpret_cast<WarpSmem<SPH>*>(smem_raw)[warp];
+    WarpSmem<SPH, MIXED>& sm = reinterpret_cast<WarpSmem<SPH, MIXED>*>(smem_raw)[warp];
     int2* const spill = P.spill + (size_t)(blockIdx.x * WalkCfg<SPH>::WARPS + warp) * P.spill_per_warp;
     const unsigned lt = (1u << lane) - 1u;
     const int N = (int)P.N;
@@ -307,19 +320,46 @@ __global__ void __launch_bounds__(WalkCfg<SPH>::TPB, WALK_CTAS) k_walk(const Wal
             h_t = P.s_h[t];
             hh4 = 4.0 * h_t * h_t;
             hh4c = hh4 * (1.0 + 1e-13);
-            // the reference overrides h_j, rho_j, P_j with the target's own values (Node.cpp:94,101,108)
-            const double rho = P.s_rho[t], Pr = P.s_P[t];
-            const double inv_h = 1.0 / h_t, pr2 = Pr / (rho * rho);
-            sm.tsph[3 * lane] = make_double4(inv_h, inv_h * inv_h * inv_h * inv_h / kPI, pr2 + pr2, sqrt(kGAMMA * Pr / rho));
-            const double4 tv = P.src_gv[t];
-            sm.tsph[3 * lane + 1] = make_double4(tv.x, tv.y, tv.z, h_t);
+            if (INWALK) {
+                // the reference overrides h_j, rho_j, P_j with the target's own values (Node.cpp:94,101,108)
+                const double rho = P.s_rho[t], Pr = P.s_P[t];
+                const double inv_h = 1.0 / h_t, pr2 = Pr / (rho * rho);
+                sm.tsph[3 * lane] = make_double4(inv_h, inv_h * inv_h * inv_h * inv_h / kPI, pr2 + pr2, sqrt(kGAMMA * Pr / rho));
+                const double4 tv = P.src_gv[t];
+                sm.tsph[3 * lane + 1] = make_double4(tv.x, tv.y, tv.z, h_t);
+            }
         }
         double ax = 0, ay = 0, az = 0, dU = 0;
         int c_vis = (active && (n_nodes > 0 || !valid)) ? 1 : 0, c_an = 0, c_al = 0, c_sp = 0;              // the root call itself
         const unsigned vmask = __ballot_sync(0xffffffffu, valid);
         const int tmin = __shfl_sync(0xffffffffu, (int)t, 0), tmax = __reduce_max_sync(0xffffffffu, (int)t);   // targets are sorted by tree position
-        const bool wgas = SPH && __any_sync(0xffffffffu, tgas && h_t > 0.0);   // any target of this warp that can feel SPH at all
-
+        const unsigned gasl = SPH ? __ballot_sync(0xffffffffu, tgas && h_t > 0.0) : 0u;   // targets of this warp that can feel SPH at all
+        const bool wgas = gasl != 0u;
+        int rec_last = -1, rec_free = 0, rec_idx = 0;                            // SPLIT: this group's last record, records left of the batch taken from the pool
+        int rfill = 0;                                                           // SPLIT: entries waiting in sm.rsrc (< 64)
+        auto rec_flush = [&](const bool full) {
+            // writes the first 32 waiting entries (full) or all of them (< 32, end of the group) as one record
+            if (rfill == 0) return;
+            if (rec_free == 0) {
+                if (lane == 0) rec_idx = (int)min(atomicAdd(&P.s->cand_cursor, (unsigned long long)REC_BATCH), 0x7ffffff0ull);
+                rec_idx = __shfl_sync(0xffffffffu, rec_idx, 0);
+                rec_free = REC_BATCH;
+            }
+            __syncwarp();
+            const int n = full ? 32 : rfill;
+            const int2 mine_ = lane < n ? sm.rsrc[lane] : make_int2(-1, 0);
+            const int2 next_ = (full && 32 + lane < rfill) ? sm.rsrc[32 + lane] : make_int2(-1, 0);
+            if ((int64_t)rec_idx < P.rec_cap) {
+                P.rec_ent[(size_t)rec_idx * 32 + lane] = mine_;
+                if (lane == 0) P.rec_next[rec_idx] = rec_last;
+                rec_last = rec_idx;
+            } else if (lane == 0) P.s->walk_overflow = 2;
+            rec_idx++; rec_free--;
+            __syncwarp();
+            rfill -= n;
+            if (lane < rfill) sm.rsrc[lane] = next_;
+            __syncwarp();
+        };
         if (vmask) {
             const double inf = __longlong_as_double(0x7ff0000000000000ll);
             const double lox = warp_min(valid ? tp.x : inf), loy = warp_min(valid ? tp.y : inf), loz = warp_min(valid ? tp.z : inf);
@@ -342,11 +382,14 @@ __global__ void __launch_bounds__(WalkCfg<SPH>::TPB, WALK_CTAS) k_walk(const Wal
                 ntl_x = make_float2(-tlx, -tlx); ntl_y = make_float2(-tly, -tly); ntl_z = make_float2(-tlz, -tlz);
                 hh4sf = (float)(hh4 * invR2);
                 far2 = P.far_k2 * hd2;                                      // the squared "far" distance: 2 half-diagonals of the box
-                hh4cf = hh4sf * (1.0f + 1e-5f);                            // generous: the SPH pass decides
-                if (SPH && tgas) {
-                    float* tf = reinterpret_cast<float*>(&sm.tsph[3 * lane + 2]);
-                    tf[0] = nth_x.x; tf[1] = nth_y.x; tf[2] = nth_z.x; tf[3] = ntl_x.x; tf[4] = ntl_y.x; tf[5] = ntl_z.x; tf[6] = hh4sf; tf[7] = __int_as_float((int)t);
-                }
+                hh4cf = hh4sf * (1.0f + 1e-5f);
+            }
+            // SPLIT: a source can only matter to SPH if it lies within 2 h_max of the warp's box (h = 2 radius of a cell, so 2h / L
+            // is exact in FP32); the margins cover the FP32 rounding of the source position and of the box
+            float cand2 = 0.f;
+            if (SPLIT && wgas) {
+                const float hm = sqrtf(warp_max_f((gasl >> lane) & 1u ? hh4sf : 0.f)) * (1.0f + 1e-4f) + 1e-5f * sqrtf(hd2);
+                cand2 = hm * hm;
             }
             const Box wb{lox, loy, loz, hix, hiy, hiz};
             // start from what the far-field prepass left for this super-group: a shared accept list and a frontier
@@ -510,19 +553,17 @@ __global__ void __launch_bounds__(WalkCfg<SPH>::TPB, WALK_CTAS) k_walk(const Wal
                     if (lane < cnt) e = sm.list[base + lane];
                     if (CLASSES) __syncwarp();                                      // the tile's list entries are rewritten in class order below
                     double4 q = make_double4(0, 0, 0, 0), gvv = q;
-                    float hx = 0, hy = 0, hz = 0, lx = 0, ly = 0, lz = 0;
+                    float hx = 0, hy = 0, hz = 0, lx = 0, ly = 0, lz = 0, dmin2 = 0;
                     if (lane < cnt) {
                         q = P.src_pm[e.x];
-                        if (SPH && wgas) { gvv = P.src_gv[e.x]; src_gas = gvv.w > 0.0; }   // independent of the load above
+                        if (INWALK && wgas) { gvv = P.src_gv[e.x]; src_gas = gvv.w > 0.0; }   // independent of the load above
                         if (MIXED) {
                             const double rx = (q.x - cgx) * invR, ry = (q.y - cgy) * invR, rz = (q.z - cgz) * invR;
                             hx = (float)rx; hy = (float)ry; hz = (float)rz;
                             lx = (float)(rx - (double)hx); ly = (float)(ry - (double)hy); lz = (float)(rz - (double)hz);
-                            if (CLASSES) {
-                                const float fx_ = fmaxf(0.f, fabsf(hx) - bhx), fy_ = fmaxf(0.f, fabsf(hy) - bhy), fz_ = fmaxf(0.f, fabsf(hz) - bhz);
-                                const bool far = fmaf(fz_, fz_, fmaf(fy_, fy_, fx_ * fx_)) >= far2;
-                                cls = !far ? 2 : (unsigned)e.y == vmask ? 0 : 1;
-                            } else cls = 2;
+                            const float fx_ = fmaxf(0.f, fabsf(hx) - bhx), fy_ = fmaxf(0.f, fabsf(hy) - bhy), fz_ = fmaxf(0.f, fabsf(hz) - bhz);
+                            dmin2 = fmaf(fz_, fz_, fmaf(fy_, fy_, fx_ * fx_));
+                            cls = dmin2 < far2 ? 2 : (FULLCLASS && (unsigned)e.y == vmask) ? 0 : 1;
                         }
                         // accepted pairs of this entry: lanes in the mask, minus the target's own leaf, none for a massless leaf
                         pc_mask = q.w != 0.0 ? (unsigned)e.y : 0u;
@@ -544,7 +585,7 @@ __global__ void __launch_bounds__(WalkCfg<SPH>::TPB, WALK_CTAS) k_walk(const Wal
                             sf[0] = hx; sf[2] = hy; sf[4] = hz; sf[6] = (float)(q.w * inv_m0);
                             sf[8] = lx; sf[10] = ly; sf[12] = lz;
                         } else sm.stage[lane] = q;
-                        if (SPH && wgas) sm.gst[pos] = gvv;
+                        if (INWALK && wgas) sm.gst[pos] = gvv;
                     }
                     {   // a leaf that is one of this warp's own targets does not count as an interaction with itself
                         const bool maybe = ex_part >= tmin && ex_part <= tmax;
@@ -552,6 +593,17 @@ __global__ void __launch_bounds__(WalkCfg<SPH>::TPB, WALK_CTAS) k_walk(const Wal
                         else if (__any_sync(0xffffffffu, maybe))
                             for (int l2 = 0; l2 < 32; l2++) { const int tl = __shfl_sync(0xffffffffu, (int)t, l2); if (ex_part >= 0 && ex_part == tl) pc_mask &= ~(1u << l2); }
                         if (ex_part >= 0) tot_leaf += __popc(pc_mask); else tot_node += __popc(pc_mask);
+                    }
+                    if (SPLIT && wgas) {
+                        // sources within 2 h_max of the warp's box that a gas target accepted: (source, those targets) for k_sph
+                        const unsigned gm = pc_mask & gasl;
+                        const bool cand = gm != 0u && dmin2 < cand2;
+                        const unsigned cm = __ballot_sync(0xffffffffu, cand);
+                        if (cm) {
+                            if (cand) sm.rsrc[rfill + __popc(cm & lt)] = make_int2(e.x, (int)gm);
+                            rfill += __popc(cm);
+                            if (rfill >= 32) rec_flush(true);
+                        }
                     }
                     if (COUNT) {
                         // tuning statistics: how many list entries have their acceptors inside one half / one quarter of the warp
@@ -574,7 +626,7 @@ __global__ void __launch_bounds__(WalkCfg<SPH>::TPB, WALK_CTAS) k_walk(const Wal
                         float* sf = reinterpret_cast<float*>(&sm.stage[lane & ~1]) + (lane & 1);
                         sf[0] = 1.f; sf[2] = 1.f; sf[4] = 1.f; sf[6] = 0.f; sf[8] = 0.f; sf[10] = 0.f; sf[12] = 0.f;
                     }
-                    const unsigned gasmask = (SPH && wgas) ? __reduce_or_sync(0xffffffffu, src_gas ? 1u << pos : 0u) : 0u;   // tile positions that hold gas
+                    const unsigned gasmask = (INWALK && wgas) ? __reduce_or_sync(0xffffffffu, src_gas ? 1u << pos : 0u) : 0u;   // tile positions that hold gas
                     if (base + 32 + lane < lc) asm volatile("prefetch.global.L1 [%0];" ::"l"(P.src_pm + sm.list[base + 32 + lane].x));
                     __syncwarp();
                     unsigned gate = 0;                                                   // per lane: entries within ~2h (SPH candidates)
@@ -612,7 +664,6 @@ __global__ void __launch_bounds__(WalkCfg<SPH>::TPB, WALK_CTAS) k_walk(const Wal
                                 }
                                 if (MASKED) { f.x = bit0 ? f.x : 0.f; f.y = bit1 ? f.y : 0.f; }
                                 fax = __ffma2_rn(f, dx, fax); fay = __ffma2_rn(f, dy, fay); faz = __ffma2_rn(f, dz, faz);
-                                if (SPH && wgas) gate |= ((bit0 && r2.x < hh4cf ? 1u : 0u) << j) | ((bit1 && r2.y < hh4cf ? 2u : 0u) << j);
                                 if (COUNT) {
                                     const bool seen0 = bit0 && r1.z != 0.f, ok0 = seen0 && r2.x != 0.f;
                                     const bool seen1 = bit1 && r1.w != 0.f, ok1 = seen1 && r2.y != 0.f;
@@ -621,10 +672,8 @@ __global__ void __launch_bounds__(WalkCfg<SPH>::TPB, WALK_CTAS) k_walk(const Wal
                                 }
                             }
                         };
-                        if (CLASSES) {
-                            pair_loop(std::false_type{}, std::false_type{}, 0, b0);
-                            pair_loop(std::false_type{}, std::true_type{}, b0, b1);
-                        }
+                        if (FULLCLASS) pair_loop(std::false_type{}, std::false_type{}, 0, b0);
+                        if (CLASSES) pair_loop(std::false_type{}, std::true_type{}, b0, b1);
                         pair_loop(std::true_type{}, std::true_type{}, b1, cnt);
                         ax = fma(acc_scale, (double)(fax.x + fax.y), ax); ay = fma(acc_scale, (double)(fay.x + fay.y), ay); az = fma(acc_scale, (double)(faz.x + faz.y), az);
                     } else {
@@ -642,7 +691,7 @@ __global__ void __launch_bounds__(WalkCfg<SPH>::TPB, WALK_CTAS) k_walk(const Wal
                         const double w = rsqrt_pos(fma(r2s * q2, q2, 1e-300));   // 1 / (r (r^2 + e0^2)) in units of R
                         const double f = (bit ? GR3 * q.w : 0.0) * w;
                         ax = fma(f, dx, ax); ay = fma(f, dy, ay); az = fma(f, dz, az);
-                        if (SPH && wgas) gate |= (r2 < hh4c ? 1u : 0u) << j;            // hh4c = 0 for non-gas targets: never set
+                        if (INWALK && wgas) gate |= (r2 < hh4c ? 1u : 0u) << j;            // hh4c = 0 for non-gas targets: never set
                         if (COUNT) {
                             const bool seen = bit && q.w != 0.0;
                             const bool ok = seen && r2 != 0.0;
@@ -650,81 +699,10 @@ __global__ void __launch_bounds__(WalkCfg<SPH>::TPB, WALK_CTAS) k_walk(const Wal
                         }
                     }
                     }
-                    if (SPH && wgas && __any_sync(0xffffffffu, (gate & gasmask) != 0u)) {
+                    if (INWALK && wgas && __any_sync(0xffffffffu, (gate & gasmask) != 0u)) {
                         // second pass over the few (target, source) pairs that can pass r < 2 h_i (Node.cpp:316-325, :368-377)
                         unsigned mine = gate & gasmask;
-                        if (MIXED) {
-                            // Pair-parallel: the warp's candidate (target, source) pairs of this tile are enumerated in (target, source)
-                            // order and handed out one per lane, 32 at a time; results travel through shared memory back to the owning
-                            // lane, which adds its own pairs in source order (deterministic, identical to a per-target loop).
-                            const int npair = __popc(mine);
-                            const int incl = warp_incl_scan(npair, lane);
-                            const int total = __shfl_sync(0xffffffffu, incl, 31);
-                            for (int c0 = 0; c0 < total; c0 += 32) {
-                                const int p = c0 + lane;
-                                int owner = 0;                                   // first lane whose inclusive count exceeds p
-#pragma unroll
-                                for (int step = 16; step > 0; step >>= 1) {
-                                    const int probe = __shfl_sync(0xffffffffu, incl, owner + step - 1);
-                                    if (probe <= p) owner += step;
-                                }
-                                owner = min(owner, 31);
-                                const int o_incl = __shfl_sync(0xffffffffu, incl, owner), o_cnt = __shfl_sync(0xffffffffu, npair, owner);
-                                const unsigned o_mine = __shfl_sync(0xffffffffu, mine, owner);
-                                double fx = 0, fy = 0, fz = 0, du = 0;
-                                if (p < total) {
-                                    const int j = __fns(o_mine, 0, p - (o_incl - o_cnt) + 1);
-                                    const int2 e = sm.list[base + j];
-                                    const double4 gv = sm.gst[j];                // (mVel | particle velocity, gasMass)
-                                    const double4 k4 = sm.tsph[3 * owner], tv = sm.tsph[3 * owner + 1];
-                                    const float* tf = reinterpret_cast<const float*>(&sm.tsph[3 * owner + 2]);
-                                    const float* rec = reinterpret_cast<const float*>(&sm.stage[j & ~1]) + (j & 1);
-                                    // displacement from the tile's float-float record (units of R), like the gravity loop; d = x_i - COM (Node.cpp:116)
-                                    const float sx = -((rec[0] + tf[0]) + (rec[8] + tf[3])), sy = -((rec[2] + tf[1]) + (rec[10] + tf[4])),
-                                                sz = -((rec[4] + tf[2]) + (rec[12] + tf[5]));
-                                    const float r2s = fmaf(sz, sz, fmaf(sy, sy, sx * sx)), hh4o = tf[6];
-                                    const bool live = rec[6] != 0.f && r2s != 0.f;
-                                    bool pass = live && r2s < hh4o;
-                                    if (live && fabsf(r2s - hh4o) <= 4e-6f * hh4o) {
-                                        // too close to the gate for FP32: the reference's own separately rounded FP64 expression
-                                        const double4 q = P.src_pm[e.x], ot = P.src_pm[__float_as_int(tf[7])];
-                                        const double dx = q.x - ot.x, dy = q.y - ot.y, dz = q.z - ot.z;
-                                        const double r2e = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
-                                        pass = __dsqrt_rn(r2e) < __dmul_rn(tv.w, 2.0);
-                                        tot_exact++;
-                                    }
-                                    if (pass) {
-                                        const float hs = (float)(tv.w * invR), inv_hs = 1.0f / hs, ipi4 = inv_hs * inv_hs * inv_hs * inv_hs * 0.318309886f;
-                                        float rinv;
-                                        asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rinv) : "f"(r2s));
-                                        const float r = r2s * rinv, qq = r * inv_hs;
-                                        float gs = 0.f;                          // kernel.cpp:28-34
-                                        if (qq < 1.f) gs = -3.f * qq + 2.25f * qq * qq;
-                                        else if (qq < 2.f) { const float u = 2.f - qq; gs = -0.75f * u * u; }
-                                        const float gfac = gs * ipi4 * rinv;
-                                        const float gx = sx * gfac, gy = sy * gfac, gz = sz * gfac;   // grad W * R^4
-                                        const float vx = (float)(tv.x - gv.x), vy = (float)(tv.y - gv.y), vz = (float)(tv.z - gv.z);
-                                        const float vds = vx * sx + vy * sy + vz * sz;                // v_ij . d / R
-                                        const float mu = hs * vds / (r2s + 0.01f * hs * hs);
-                                        const float MUf = vds < 0.f ? (-0.5f * (float)k4.w * mu + mu * mu) : 0.f;   // Node.cpp:142-152
-                                        const double amu = k4.z + (double)MUf, coef = -gv.w * amu * invR4;          // Node.cpp:127 + :154
-                                        fx = coef * (double)gx; fy = coef * (double)gy; fz = coef * (double)gz;
-                                        du = 0.5 * gv.w * amu * invR4 * (double)(vx * gx + vy * gy + vz * gz);      // Node.cpp:167
-                                        if (isnan(fx) || isnan(fy) || isnan(fz)) { fx = 0; fy = 0; fz = 0; }         // Node.cpp:169
-                                        tot_sph++;
-                                    }
-                                    sm.res[lane] = make_double4(fx, fy, fz, pass ? du : __longlong_as_double(0x7ff8000000000001ll));
-                                }
-                                __syncwarp();
-                                // my pairs inside this chunk are the contiguous lanes [a, b)
-                                const int a = max(incl - npair, c0) - c0, b = min(incl, c0 + 32) - c0;
-                                for (int i = a; i < b; i++) {
-                                    const double4 r = sm.res[i];
-                                    if (__double_as_longlong(r.w) != 0x7ff8000000000001ll) { ax += r.x; ay += r.y; az += r.z; dU += r.w; if (COUNT) c_sp++; }
-                                }
-                                __syncwarp();
-                            }
-                        } else
+                        if (!MIXED)
                         // FP64 mode: every gas lane runs through ITS OWN candidates (a per-lane loop: lanes only diverge in trip count)
                         while (mine) {
                             const int j = __ffs(mine) - 1;
@@ -774,12 +752,12 @@ __global__ void __launch_bounds__(WalkCfg<SPH>::TPB, WALK_CTAS) k_walk(const Wal
                 if (sp == 0 && cpos >= n_fl) break;
             }
         }
-
+        if (SPLIT) { rec_flush(false); if (lane == 0) P.rec_head[g] = rec_last; }
         if (active) {
             if (!valid) { ax = 0; ay = 0; az = 0; }                            // Node.cpp:265; such lanes are not masked out in the class-0 loop
             const uint32_t p = P.perm[t];
             P.ax[p] = ax; P.ay[p] = ay; P.az[p] = az;                           // Tree.cpp:77 (acc = 0) + accumulated force
-            if (SPH && tgas && dU != 0.0) P.dUdt[p] += dU;
+            if (INWALK && tgas && dU != 0.0) P.dUdt[p] += dU;
             if (COUNT) { P.c_visits[t] = c_vis; P.c_accn[t] = c_an; P.c_accl[t] = c_al; P.c_sph[t] = c_sp; }
             tot_visit += (unsigned long long)c_vis;
         }
@@ -800,9 +778,196 @@ __global__ void __launch_bounds__(WalkCfg<SPH>::TPB, WALK_CTAS) k_walk(const Wal
     }
 }
 
+// ---- SPH pairs of the mixed-precision mode (Node::calcSPHForce, Node.cpp:88-172; the gate of Node.cpp:316-325, :368-377).
+// k_walk<SPH, MIXED> records, per group of 32 targets, the accepted gas-bearing sources that lie within 2 h_max of the
+// group's box together with the gas targets that accepted them.  Here one warp per group takes those entries in tiles of
+// 32, enumerates the (target, source) pairs in (target, source) order and hands them out one per lane: the exact gate
+// r < 2 h_i (FP32, FP64 when within 4e-6 of the threshold), the kernel gradient / viscosity algebra in FP32, the final
+// products in FP64; results travel through shared memory back to the owning lane, which adds its own pairs in source
+// order (deterministic: bit-identical from run to run and for any number of GPUs).
+template <bool COUNT>
+__global__ void __launch_bounds__(256, 3) k_sph(const WalkParams P)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    SphWarp& sm = reinterpret_cast<SphWarp*>(smem_raw)[warp];
+    const double R = __longlong_as_double((long long)P.s->Rbits);
+    const double invR2 = R > 0.0 ? 4294967296.0 / (R * R) : 1.0, invR = sqrt(invR2), invR4 = invR2 * invR2;   // same unit L = R / 2^16 as k_walk
+    const Slice sl = target_slice(P);
+    const unsigned ngroups = (unsigned)((sl.a1 - sl.a0 + 31) / 32);
+    unsigned long long tot_sph = 0, tot_exact = 0;
+    if (P.s->walk_overflow) return;                                             // incomplete records: agb_forces grows the pool and walks again
+    for (unsigned g = blockIdx.x * 8 + warp; g < ngroups; g += gridDim.x * 8) {
+        const int head = P.rec_head[g];
+        if (head < 0) continue;
+        const int64_t idx = sl.a0 + (int64_t)g * 32 + lane;
+        const bool inrange = idx < sl.a1;
+        const int64_t t = !inrange ? -1 : sl.ident ? idx : (int64_t)P.act_list[idx];
+        const double4 tp = inrange ? P.src_pm[t] : make_double4(0, 0, 0, 0);
+        const bool valid = inrange && tp.w != 0.0;                              // Node.cpp:265
+        bool tgas = false;
+        double h_t = 0;
+        __syncwarp();
+        if (valid && P.s_type[t] == 2) {
+            h_t = P.s_h[t];
+            tgas = h_t > 0.0;
+            if (tgas) {
+                // the reference overrides h_j, rho_j, P_j with the target's own values (Node.cpp:94,101,108)
+                const double rho = P.s_rho[t], Pr = P.s_P[t];
+                const double inv_h = 1.0 / h_t, pr2 = Pr / (rho * rho);
+                sm.tsph[3 * lane] = make_double4(inv_h, inv_h * inv_h * inv_h * inv_h / kPI, pr2 + pr2, sqrt(kGAMMA * Pr / rho));
+                const double4 tv = P.src_gv[t];
+                sm.tsph[3 * lane + 1] = make_double4(tv.x, tv.y, tv.z, h_t);
+            }
+        }
+        const double inf = __longlong_as_double(0x7ff0000000000000ll);
+        const double lox = warp_min(valid ? tp.x : inf), loy = warp_min(valid ? tp.y : inf), loz = warp_min(valid ? tp.z : inf);
+        const double hix = warp_max(valid ? tp.x : -inf), hiy = warp_max(valid ? tp.y : -inf), hiz = warp_max(valid ? tp.z : -inf);
+        const double cgx = 0.5 * (lox + hix), cgy = 0.5 * (loy + hiy), cgz = 0.5 * (loz + hiz);
+        float2 nth_x = make_float2(0.f, 0.f), nth_y = nth_x, nth_z = nth_x;
+        float hh4pf = 0.f;                                                       // prefilter threshold; 0 for everything but gas targets with h > 0
+        if (tgas) {
+            const double rx = (tp.x - cgx) * invR, ry = (tp.y - cgy) * invR, rz = (tp.z - cgz) * invR;
+            const float thx = (float)rx, thy = (float)ry, thz = (float)rz;
+            nth_x = make_float2(-thx, -thx); nth_y = make_float2(-thy, -thy); nth_z = make_float2(-thz, -thz);
+            float* tf = reinterpret_cast<float*>(&sm.tsph[3 * lane + 2]);
+            tf[0] = -thx; tf[1] = -thy; tf[2] = -thz;
+            tf[3] = -(float)(rx - (double)thx); tf[4] = -(float)(ry - (double)thy); tf[5] = -(float)(rz - (double)thz);
+            tf[6] = (float)(4.0 * h_t * h_t * invR2); tf[7] = __int_as_float((int)t);
+            // single-float positions are off by <= 2^-24 (|s| + |t|), |s|, |t| <~ half-diagonal + 2h: pad 2h accordingly
+            const float hd = (float)(0.5 * sqrt((hix - lox) * (hix - lox) + (hiy - loy) * (hiy - loy) + (hiz - loz) * (hiz - loz)) * invR);
+            const float hp = sqrtf(tf[6]) * (1.0f + 1e-5f) + 1e-6f * (hd + sqrtf(tf[6]));
+            hh4pf = hp * hp;
+        }
+        double ax = 0, ay = 0, az = 0, dU = 0;
+        int c_sp = 0;
+        for (int rec = head; rec >= 0; rec = P.rec_next[rec]) {
+            {
+                __syncwarp();
+                const int2 ent = P.rec_ent[(size_t)rec * 32 + lane];
+                const int src = ent.x;
+                const int cnt = __popc(__ballot_sync(0xffffffffu, src >= 0));
+                if (lane < cnt) {
+                    const double4 q = P.src_pm[src], gv = P.src_gv[src];
+                    const double rx = (q.x - cgx) * invR, ry = (q.y - cgy) * invR, rz = (q.z - cgz) * invR;
+                    const float hx = (float)rx, hy = (float)ry, hz = (float)rz;
+                    float* sf = reinterpret_cast<float*>(&sm.stage[lane & ~1]) + (lane & 1);
+                    sf[0] = hx; sf[2] = hy; sf[4] = hz; sf[6] = (q.w != 0.0 && gv.w > 0.0) ? 1.f : 0.f;   // Node.cpp:250,:319,:371
+                    sf[8] = (float)(rx - (double)hx); sf[10] = (float)(ry - (double)hy); sf[12] = (float)(rz - (double)hz);
+                    sm.gst[lane] = gv; sm.list[lane] = src;
+                    sm.lmask[lane] = (q.w != 0.0 && gv.w > 0.0) ? (unsigned)ent.y : 0u;
+                } else {
+                    if (lane == cnt) {                                           // odd tile: finite numbers in the unused half of the last pair
+                        float* sf = reinterpret_cast<float*>(&sm.stage[lane & ~1]) + (lane & 1);
+                        sf[0] = 1.f; sf[2] = 1.f; sf[4] = 1.f; sf[6] = 0.f; sf[8] = 0.f; sf[10] = 0.f; sf[12] = 0.f;
+                    }
+                    sm.lmask[lane] = 0u;
+                }
+                __syncwarp();
+                // my target's view of the record: bit j = entry j holds gas, was accepted by me and lies within ~2h (single-float
+                // distance with a generous margin: the pass below decides); two entries per iteration, packed FP32x2
+                unsigned mine = 0u;
+                for (int j = 0; j < cnt; j += 2) {
+                    const float4* rec4 = reinterpret_cast<const float4*>(&sm.stage[j]);
+                    const float4 r0 = rec4[0], r1 = rec4[1];
+                    const uint2 mm = *reinterpret_cast<const uint2*>(&sm.lmask[j]);
+                    const float2 dx = __fadd2_rn(make_float2(r0.x, r0.y), nth_x), dy = __fadd2_rn(make_float2(r0.z, r0.w), nth_y), dz = __fadd2_rn(make_float2(r1.x, r1.y), nth_z);
+                    const float2 r2 = __ffma2_rn(dz, dz, __ffma2_rn(dy, dy, __fmul2_rn(dx, dx)));
+                    mine |= ((((mm.x >> lane) & 1u) && r2.x < hh4pf ? 1u : 0u) | (((mm.y >> lane) & 1u) && r2.y < hh4pf ? 2u : 0u)) << j;
+                }
+                {
+                // Pair-parallel: the warp's candidate (target, source) pairs of this tile are enumerated in (target, source)
+                // order and handed out one per lane, 32 at a time; results travel through shared memory back to the owning
+                // lane, which adds its own pairs in source order (deterministic, identical to a per-target loop).
+                const int npair = __popc(mine);
+                const int incl = warp_incl_scan(npair, lane);
+                const int total = __shfl_sync(0xffffffffu, incl, 31);
+                for (int c0 = 0; c0 < total; c0 += 32) {
+                    const int p = c0 + lane;
+                    int owner = 0;                                   // first lane whose inclusive count exceeds p
+#pragma unroll
+                    for (int step = 16; step > 0; step >>= 1) {
+                        const int probe = __shfl_sync(0xffffffffu, incl, owner + step - 1);
+                        if (probe <= p) owner += step;
+                    }
+                    owner = min(owner, 31);
+                    const int o_incl = __shfl_sync(0xffffffffu, incl, owner), o_cnt = __shfl_sync(0xffffffffu, npair, owner);
+                    const unsigned o_mine = __shfl_sync(0xffffffffu, mine, owner);
+                    double fx = 0, fy = 0, fz = 0, du = 0;
+                    if (p < total) {
+                        const int j = __fns(o_mine, 0, p - (o_incl - o_cnt) + 1);
+                        const int esrc = sm.list[j];
+                        const double4 gv = sm.gst[j];                // (mVel | particle velocity, gasMass)
+                        const double4 k4 = sm.tsph[3 * owner], tv = sm.tsph[3 * owner + 1];
+                        const float* tf = reinterpret_cast<const float*>(&sm.tsph[3 * owner + 2]);
+                        const float* rec = reinterpret_cast<const float*>(&sm.stage[j & ~1]) + (j & 1);
+                        // displacement from the tile's float-float record (units of R), like the gravity loop; d = x_i - COM (Node.cpp:116)
+                        const float sx = -((rec[0] + tf[0]) + (rec[8] + tf[3])), sy = -((rec[2] + tf[1]) + (rec[10] + tf[4])),
+                                    sz = -((rec[4] + tf[2]) + (rec[12] + tf[5]));
+                        const float r2s = fmaf(sz, sz, fmaf(sy, sy, sx * sx)), hh4o = tf[6];
+                        const bool live = rec[6] != 0.f && r2s != 0.f;
+                        bool pass = live && r2s < hh4o;
+                        if (live && fabsf(r2s - hh4o) <= 4e-6f * hh4o) {
+                            // too close to the gate for FP32: the reference's own separately rounded FP64 expression
+                            const double4 q = P.src_pm[esrc], ot = P.src_pm[__float_as_int(tf[7])];
+                            const double dx = q.x - ot.x, dy = q.y - ot.y, dz = q.z - ot.z;
+                            const double r2e = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+                            pass = __dsqrt_rn(r2e) < __dmul_rn(tv.w, 2.0);
+                            tot_exact++;
+                        }
+                        if (pass) {
+                            const float hs = (float)(tv.w * invR), inv_hs = 1.0f / hs, ipi4 = inv_hs * inv_hs * inv_hs * inv_hs * 0.318309886f;
+                            float rinv;
+                            asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rinv) : "f"(r2s));
+                            const float r = r2s * rinv, qq = r * inv_hs;
+                            float gs = 0.f;                          // kernel.cpp:28-34
+                            if (qq < 1.f) gs = -3.f * qq + 2.25f * qq * qq;
+                            else if (qq < 2.f) { const float u = 2.f - qq; gs = -0.75f * u * u; }
+                            const float gfac = gs * ipi4 * rinv;
+                            const float gx = sx * gfac, gy = sy * gfac, gz = sz * gfac;   // grad W * R^4
+                            const float vx = (float)(tv.x - gv.x), vy = (float)(tv.y - gv.y), vz = (float)(tv.z - gv.z);
+                            const float vds = vx * sx + vy * sy + vz * sz;                // v_ij . d / R
+                            const float mu = hs * vds / (r2s + 0.01f * hs * hs);
+                            const float MUf = vds < 0.f ? (-0.5f * (float)k4.w * mu + mu * mu) : 0.f;   // Node.cpp:142-152
+                            const double amu = k4.z + (double)MUf, coef = -gv.w * amu * invR4;          // Node.cpp:127 + :154
+                            fx = coef * (double)gx; fy = coef * (double)gy; fz = coef * (double)gz;
+                            du = 0.5 * gv.w * amu * invR4 * (double)(vx * gx + vy * gy + vz * gz);      // Node.cpp:167
+                            if (isnan(fx) || isnan(fy) || isnan(fz)) { fx = 0; fy = 0; fz = 0; }         // Node.cpp:169
+                            tot_sph++;
+                        }
+                        sm.res[lane] = make_double4(fx, fy, fz, pass ? du : __longlong_as_double(0x7ff8000000000001ll));
+                    }
+                    __syncwarp();
+                    // my pairs inside this chunk are the contiguous lanes [a, b)
+                    const int a = max(incl - npair, c0) - c0, b = min(incl, c0 + 32) - c0;
+                    for (int i = a; i < b; i++) {
+                        const double4 r = sm.res[i];
+                        if (__double_as_longlong(r.w) != 0x7ff8000000000001ll) { ax += r.x; ay += r.y; az += r.z; dU += r.w; if (COUNT) c_sp++; }
+                    }
+                    __syncwarp();
+                }
+                }
+            }
+        }
+        if (tgas) {
+            const uint32_t p = P.perm[t];
+            if (ax != 0.0) P.ax[p] += ax;
+            if (ay != 0.0) P.ay[p] += ay;
+            if (az != 0.0) P.az[p] += az;
+            if (dU != 0.0) P.dUdt[p] += dU;
+            if (COUNT) P.c_sph[t] = c_sp;
+        }
+    }
+    tot_sph = warp_sum_u64(tot_sph); tot_exact = warp_sum_u64(tot_exact);
+    if (lane == 0) {
+        if (tot_sph) atomicAdd(&P.s->c_sph, tot_sph);
+        if (tot_exact) atomicAdd(&P.s->c_exact, tot_exact);
+    }
+}
+
 __global__ void k_walk_reset(AgbScalars* s)
 {
-    s->walk_next_group = 0; s->walk_overflow = 0;
+    s->walk_next_group = 0; s->walk_overflow = 0; s->cand_cursor = 0ull;
     s->st_rounds = 0; s->st_popped = 0; s->st_mixed = 0; s->st_open = 0; s->st_drain = 0;
     for (int c = 0; c < 10; c++) s->st_cls[c] = 0;
     s->c_interactions = 0; s->c_node = 0; s->c_leaf = 0; s->c_sph = 0; s->c_visits = 0; s->c_exact = 0; s->c_spill = 0;
@@ -865,7 +1030,7 @@ template <bool COUNT, bool SPH, bool MIXED>
 void launch_walk(const WalkParams& P, int64_t max_groups, int sm_count, int spill_warps, cudaStream_t st)
 {
     constexpr int WARPS = WalkCfg<SPH>::WARPS;
-    const int smem = (int)sizeof(WarpSmem<SPH>) * WARPS;
+    const int smem = (int)sizeof(WarpSmem<SPH, MIXED>) * WARPS;
     cudaFuncSetAttribute(k_walk<COUNT, SPH, MIXED>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);   // per device; cheap, so not cached
     int blocks = (int)std::min<int64_t>((int64_t)sm_count * WALK_CTAS, (max_groups + WARPS - 1) / WARPS);
     if (blocks * WARPS > spill_warps) blocks = spill_warps / WARPS;
@@ -911,6 +1076,7 @@ int agb_launch_walk(AgbDev& d, AgbScalars* s, double globalTime, double e0, doub
     P.c_visits = d.c_visits; P.c_accn = d.c_accn; P.c_accl = d.c_accl; P.c_sph = d.c_sph;
     P.spill = d.spill; P.spill_per_warp = d.spill_per_warp;
     P.far_list = d.far_list; P.far_front = d.far_front; P.far_cnt = d.far_cnt;
+    P.rec_ent = d.rec_ent; P.rec_next = d.rec_next; P.rec_head = d.rec_head; P.rec_cap = d.rec_cap;
     P.s = s; P.N = d.n; P.act_list = d.act_list; P.part = part; P.nparts = nparts;
     P.theta = theta; P.e0 = e0; P.globalTime = globalTime;
     // tuning knob (not part of the ABI): AGB200_WALK_FAR_K2=1e30 sends every pair through the float-float loop
@@ -936,8 +1102,16 @@ int agb_launch_walk(AgbDev& d, AgbScalars* s, double globalTime, double e0, doub
         k_far<<<(int)std::min<int64_t>((max_groups / SG_GROUPS + 4) / 4, (int64_t)sm_count * 8), 128, 0, st>>>(P); launches++;
         if (counters) { if (any_gas) launch_walk2<true, true>(P, max_groups, sm_count, d.spill_warps, mixed, st); else launch_walk2<true, false>(P, max_groups, sm_count, d.spill_warps, mixed, st); }
         else { if (any_gas) launch_walk2<false, true>(P, max_groups, sm_count, d.spill_warps, mixed, st); else launch_walk2<false, false>(P, max_groups, sm_count, d.spill_warps, mixed, st); }
-        if (ev1) cudaEventRecord(ev1, st);
         launches++;
+        if (any_gas && mixed) {
+            // the SPH pairs of the candidates the walk recorded (after it: acc += SPH part, dU/dt += ...)
+            const int smem = (int)sizeof(SphWarp) * 8;
+            const int blocks = (int)std::min<int64_t>((max_groups + 7) / 8, (int64_t)sm_count * 16);
+            if (counters) { cudaFuncSetAttribute(k_sph<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); k_sph<true><<<blocks, 256, smem, st>>>(P); }
+            else { cudaFuncSetAttribute(k_sph<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); k_sph<false><<<blocks, 256, smem, st>>>(P); }
+            launches++;
+        }
+        if (ev1) cudaEventRecord(ev1, st);
     }
     return launches;
 }
