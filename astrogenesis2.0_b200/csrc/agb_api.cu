@@ -17,7 +17,8 @@ struct agb_ctx {
     cudaStream_t st = nullptr, st_copy = nullptr;   // compute stream; upload stream for everything but x, y, z
     cudaEvent_t ev_in = nullptr;                      // uploads on st_copy complete
     bool in_pending = false;
-    cudaEvent_t ev[8] = {};
+    cudaEvent_t ev[10] = {};
+    bool gas_hint_valid = false, gas_hint = false;   // agb_force_path: "the particle set holds gas" as of the last completed step
     AgbDev d;
     AgbScalars* s = nullptr;            // device
     AgbScalars hs;                      // host mirror (tail only is valid)
@@ -421,6 +422,52 @@ int agb_forces_slice(agb_ctx* c, double global_time, double e0, double theta, in
 }
 
 int agb_forces(agb_ctx* c, double global_time, double e0, double theta) { return agb_forces_slice(c, global_time, e0, theta, 0, 1); }
+
+// The four calls in one, with a single host synchronisation at the end.  Two things the separate calls learn from the
+// device in between are taken from the previous step instead: the visual-density radius is the caller's (the reference
+// fixes it at init, Simulation.cpp:126) and "the particle set holds gas" (which decides whether the density kernels and the
+// SPH variant of the walk run) is verified after the fact; if it changed, the step is simply redone call by call.
+int agb_force_path(agb_ctx* c, double visual_density_radius, double mass_in_h, double global_time, double e0, double theta, int part, int nparts, double* root_radius)
+{
+    if (!c || !c->have_particles || nparts < 1 || part < 0 || part >= nparts) return AGB_ERR_INVALID;
+    auto stepwise = [&]() -> int {
+        double R = 0.0;
+        int rc = agb_build_tree(c, &R);
+        if (rc) return rc;
+        if (root_radius) *root_radius = R;
+        if ((rc = agb_visual_density(c, visual_density_radius))) return rc;
+        if ((rc = agb_gas_density(c, mass_in_h))) return rc;
+        if ((rc = agb_forces_slice(c, global_time, e0, theta, part, nparts))) return rc;
+        c->gas_hint_valid = true; c->gas_hint = c->hs.any_gas != 0;
+        return AGB_OK;
+    };
+    if (c->d.n == 0 || !c->gas_hint_valid) return stepwise();
+    if (!(e0 > 2.147483648e13)) return agb_forces_slice(c, global_time, e0, theta, part, nparts);   // reports AGB_ERR_UNSUPPORTED
+    CK(cudaSetDevice(c->device));
+    AgbDev& d = c->d;
+    c->built = false; c->dens_done = false; c->forces_done = false; c->counters_valid = false;
+    CK(cudaEventRecord(c->ev[8], c->st));
+    c->launches += agb_launch_extent(d, c->s, c->st);
+    c->launches += agb_launch_keygen(d, c->s, c->st);
+    c->launches += agb_launch_sort(d, c->s, c->st);
+    if (c->in_pending) { CK(cudaStreamWaitEvent(c->st, c->ev_in, 0)); c->in_pending = false; }
+    c->launches += agb_launch_links(d, c->s, c->st);
+    CK(cudaEventRecord(c->ev[9], c->st));
+    CK(cudaGetLastError());
+    c->built = true;
+    c->hs.any_gas = c->gas_hint ? 1 : 0;
+    int rc;
+    if ((rc = agb_visual_density(c, visual_density_radius))) return rc;
+    if ((rc = agb_gas_density(c, mass_in_h))) return rc;
+    rc = agb_forces_slice(c, global_time, e0, theta, part, nparts);          // ends with the step's only synchronisation
+    float ms = 0; if (cudaEventElapsedTime(&ms, c->ev[8], c->ev[9]) == cudaSuccess) c->phase_ms[0] = ms;
+    (void)cudaGetLastError();
+    c->hs.R = 0; memcpy(&c->hs.R, &c->hs.Rbits, 8);
+    if (root_radius) *root_radius = c->hs.R;
+    if (c->hs.dup_keys > 0) { c->built = false; c->forces_done = false; c->err = "coincident particles (shared 42-level path)"; return AGB_ERR_DEPTH; }
+    if ((c->hs.any_gas != 0) != c->gas_hint) { c->gas_hint_valid = false; return stepwise(); }   // gas appeared / vanished: redo with the right kernels
+    return rc;
+}
 
 int agb_get_counters(agb_ctx* c, agb_counters* o)
 {

@@ -841,10 +841,20 @@ __global__ void __launch_bounds__(256, 3) k_sph(const WalkParams P)
         }
         double ax = 0, ay = 0, az = 0, dU = 0;
         int c_sp = 0;
-        for (int rec = head; rec >= 0; rec = P.rec_next[rec]) {
+        int2 ent_next = P.rec_ent[(size_t)head * 32 + lane];
+        for (int rec = head; rec >= 0;) {
             {
                 __syncwarp();
-                const int2 ent = P.rec_ent[(size_t)rec * 32 + lane];
+                // the next record's entries (and its sources) are requested before this one is worked on
+                const int2 ent = ent_next;
+                rec = P.rec_next[rec];
+                if (rec >= 0) {
+                    ent_next = P.rec_ent[(size_t)rec * 32 + lane];
+                    if (ent_next.x >= 0) {
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(P.src_pm + ent_next.x));
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(P.src_gv + ent_next.x));
+                    }
+                }
                 const int src = ent.x;
                 const int cnt = __popc(__ballot_sync(0xffffffffu, src >= 0));
                 if (lane < cnt) {

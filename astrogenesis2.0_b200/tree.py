@@ -99,6 +99,13 @@ class Context:
     def forces(self, globalTime, e0, theta, part=0, nparts=1):
         capi.check(self.h, self.lib.agb_forces_slice(self.h, float(globalTime), float(e0), float(theta), int(part), int(nparts)))
 
+    def force_path(self, visual_radius, massInH, globalTime, e0, theta, part=0, nparts=1):
+        """build_tree + visual_density + gas_density + forces with one host synchronisation; returns this step's root radius."""
+        r = C.c_double()
+        capi.check(self.h, self.lib.agb_force_path(self.h, float(visual_radius), float(massInH), float(globalTime), float(e0), float(theta),
+                                                   int(part), int(nparts), C.byref(r)))
+        return r.value
+
     # ---- results
     def results(self, names=_OUT):
         out = {k: np.empty(self.n) for k in names}

@@ -211,16 +211,20 @@ def run_gpu_arm(args, pkg):
             stream.wait_stream(torch.cuda.current_stream())
         ptrs = {k: full[k].data_ptr() for k in full}
         ctx.set_particles_device(ptrs, n)
-        R = ctx.build_tree()
-        ctx.visual_density(R / 100000)
-        ctx.gas_density(mh)
-        ctx.forces(0.0, e0, THETA, rank, world)
+        # build_tree + visual_density + gas_density + forces, one host synchronisation (agb_force_path); the visual-density
+        # radius is fixed at init like in the reference (Simulation.cpp:126)
+        ctx.force_path(vis_radius, mh, 0.0, e0, THETA, rank, world)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    gather()
+    if world > 1:
+        stream.wait_stream(torch.cuda.current_stream())
+    ctx.set_particles_device({k: full[k].data_ptr() for k in full}, n)
+    vis_radius = ctx.build_tree() / 100000                                     # Simulation.cpp:123-126
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -276,10 +280,7 @@ def run_gpu_arm(args, pkg):
 
         def e2e_step():
             ctx.set_particles(host)
-            R = ctx.build_tree()
-            ctx.visual_density(R / 100000)
-            ctx.gas_density(mh)
-            ctx.forces(0.0, e0, THETA)
+            ctx.force_path(vis_radius, mh, 0.0, e0, THETA)
             ctx.results_into(out_np)
         for _ in range(max(1, args.warmup)):
             e2e_step()
@@ -337,7 +338,7 @@ def run_gpu_arm(args, pkg):
         ctx.integrator_assign_all()
         def res_step():
             t = ctx.step_begin()
-            ctx.build_tree(); ctx.visual_density(R / 100000); ctx.gas_density(mh); ctx.forces(t, e0, THETA)
+            ctx.force_path(R / 100000, mh, t, e0, THETA)
             ctx.step_end()
         for _ in range(2):
             res_step()
@@ -413,7 +414,7 @@ def run_gpu_arm(args, pkg):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="agb200", choices=["agb200", "reference"])
     ap.add_argument("--workload", default=None, choices=sorted(WORKLOADS))

@@ -117,6 +117,11 @@ int agb_forces(agb_ctx* ctx, double global_time, double e0, double theta);   /* 
 /* Multi-GPU variant: walk only the `part`-th of `nparts` contiguous slices of the tree-ordered
  * targets (every GPU holds the same gathered particles and builds the same tree). */
 int agb_forces_slice(agb_ctx* ctx, double global_time, double e0, double theta, int part, int nparts);
+/* The four calls above in one, with a single host synchronisation at the end (a driver that does not need root->radius
+ * between the calls: the reference reads it only at init, Simulation.cpp:123-126).  Same results as the separate calls;
+ * *root_radius (optional) is the radius of this step's tree. */
+int agb_force_path(agb_ctx* ctx, double visual_density_radius, double mass_in_h, double global_time, double e0, double theta,
+                   int part, int nparts, double* root_radius);
 /* The targets of slice (part, nparts) after agb_forces[_slice]: their number, and their results in compact form —
  * index[k] = position of the k-th target (tree order) in the caller's particle arrays, ax/ay/az/dUdt[k] its results.
  * What each GPU of a target-sharded run sends back instead of N-sized arrays: the slices of all parts are disjoint and

@@ -173,6 +173,25 @@ def test_counter_mode_is_the_production_arithmetic(pkg, ctxs, mixed):
             assert np.allclose(a[k], b[k], rtol=1e-11, atol=0), k
 
 
+def test_force_path_equals_the_four_calls(pkg, ctxs):
+    """agb_force_path (one host synchronisation per step) against build_tree / visual_density / gas_density / forces, bit
+    for bit; including a particle set whose gas vanishes between two steps (the remembered 'holds gas' is then wrong and the
+    step is redone) and one where it appears."""
+    ctx = ctxs(8)
+    gasy = pkg.ics.disk_galaxy(60000, seed=9)
+    dry = pkg.ics.plummer(40000, seed=10)
+    for p in (gasy, gasy, dry, dry, gasy):
+        mh = pkg.ics.gas_mass_in_h(p, 64) if (p["type"] == 2).any() else 1e40
+        want = run_gpu(pkg, ctx, p, 0.5, 1e18, mh)
+        ctx.set_particles(dict(p))
+        R = ctx.force_path(want["R"] / 100000, mh, 0.0, 1e18, 0.5)
+        got = ctx.results()
+        assert R == want["R"]
+        for k in ("ax", "ay", "az", "dUdt", "h", "rho", "P", "T"):
+            assert np.array_equal(got[k], want[k]), k
+        assert np.array_equal(got["visualDensity"], want["vis"])
+
+
 def test_slices_equal_whole(pkg, ctxs):
     """Multi-GPU sharding: walking the tree-ordered targets in 1 or 4 slices gives bit-identical results."""
     ctx = ctxs(8)
