@@ -82,7 +82,8 @@ def load(build_if_needed=True):
     lib.agb_gas_density.argtypes = [vp, C.c_double]
     lib.agb_forces.argtypes = [vp, C.c_double, C.c_double, C.c_double]
     lib.agb_forces_slice.argtypes = [vp, C.c_double, C.c_double, C.c_double, C.c_int, C.c_int]
-    lib.agb_force_path.argtypes = [vp, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int, C.c_int, _pd]
+    if hasattr(lib, "agb_force_path"):                        # absent only in older builds loaded through AGB200_LIB
+        lib.agb_force_path.argtypes = [vp, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int, C.c_int, _pd]
     lib.agb_get_slice_count.argtypes = [vp, C.c_int, C.c_int, C.POINTER(C.c_int64)]
     lib.agb_get_slice_results.argtypes = [vp, C.c_int, C.c_int, C.POINTER(C.c_uint32)] + [_pd] * 4 + [C.c_int]
     lib.agb_get_results.argtypes = [vp, C.POINTER(Results), C.c_int]

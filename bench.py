@@ -221,8 +221,7 @@ def run_gpu_arm(args, pkg):
         torch.cuda.synchronize()
 
     gather()
-    if world > 1:
-        stream.wait_stream(torch.cuda.current_stream())
+    torch.cuda.synchronize()                                                   # the uploads above ran on torch's stream, the path runs on its own
     ctx.set_particles_device({k: full[k].data_ptr() for k in full}, n)
     vis_radius = ctx.build_tree() / 100000                                     # Simulation.cpp:123-126
     sampler = ClockSampler(local)
@@ -340,17 +339,22 @@ def run_gpu_arm(args, pkg):
             t = ctx.step_begin()
             ctx.force_path(R / 100000, mh, t, e0, THETA)
             ctx.step_end()
-        for _ in range(2):
-            res_step()
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        nres = max(3, args.steps // 2)
-        for _ in range(nres):
-            res_step()
-        torch.cuda.synchronize()
-        tr = (time.perf_counter() - t0) / nres
-        resident = {"value": n / tr, "unit": "particles/s", "ms_per_step": tr * 1e3,
-                    "what": "full KDK simulation step (re-binning, kick, drift, tree, densities, forces, Ueuler, Hubble, kick) with state resident in HBM"}
+        try:
+            for _ in range(2):
+                res_step()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            nres = min(20, max(3, args.steps // 2))
+            for _ in range(nres):
+                res_step()
+            torch.cuda.synchronize()
+            tr = (time.perf_counter() - t0) / nres
+            resident = {"value": n / tr, "unit": "particles/s", "ms_per_step": tr * 1e3, "steps": nres,
+                        "what": "full KDK simulation step (re-binning, kick, drift, tree, densities, forces, Ueuler, Hubble, kick) with state resident in HBM"}
+        except Exception as e:  # noqa: BLE001
+            # the shipped fixed dt = 1e13 s is far too long for the densest synthetic sets (64M merger): close encounters fling
+            # particles out after a few steps and the rest of the system then sits deeper than 42 octree levels (AGB_ERR_DEPTH)
+            resident = {"error": str(e), "what": "device-resident KDK loop with the shipped fixed time step"}
 
     if rank != 0:
         if world > 1:
