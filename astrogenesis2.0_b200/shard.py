@@ -94,3 +94,33 @@ class PackedGather:
                     self.out[k][off: off + cnt].copy_(src[row, r * self.mx: r * self.mx + cnt])
                     off += cnt
         return self.out
+
+
+class InPlaceGather:
+    """The cheapest form of the step's exchange: every rank's shard IS its slot of the full-length arrays (a distributed
+    driver integrates it in place), and the arrays are completed by in-place all-gathers issued as ONE coalesced NCCL group —
+    no packing, no transposes, one launch.  Needs n % world == 0 (equal slots); PackedGather covers the ragged case."""
+
+    def __init__(self, dtypes, n, world, rank, device):
+        if n % world:
+            raise ValueError("InPlaceGather needs n divisible by the world size")
+        self.n, self.world, self.rank, self.device = n, world, rank, device
+        lo, hi = shard_bounds(n, rank, world)
+        self.out = {k: torch.empty(n, dtype=dt, device=device) for k, dt in dtypes.items()}
+        self.shard = {k: v[lo:hi] for k, v in self.out.items()}
+
+    def gather(self, shard=None):
+        if shard is not None and shard is not self.shard:
+            for k, v in shard.items():
+                if v.data_ptr() != self.shard[k].data_ptr():
+                    self.shard[k].copy_(v)
+        if self.world > 1:
+            coalesce = getattr(dist, "_coalescing_manager", None)
+            if coalesce is not None and dist.get_backend() == "nccl":
+                with coalesce(device=self.device):
+                    for k in self.out:
+                        dist.all_gather_into_tensor(self.out[k], self.shard[k])
+            else:
+                for k in self.out:
+                    dist.all_gather_into_tensor(self.out[k], self.shard[k].clone())
+        return self.out

@@ -27,6 +27,11 @@ def _worker(rank, world, port, n, q):
         pg = pkg.shard.PackedGather(shard, n, world)
         out = pg.gather(shard)
         ok = ok and all(np.array_equal(out[k].numpy(), p[k]) for k in shard)
+        if n % world == 0:
+            ig = pkg.shard.InPlaceGather({k: v.dtype for k, v in shard.items()}, n, world, rank, torch.device("cpu"))
+            out2 = ig.gather(shard)                    # copies the shard into its slot, then completes the arrays in place
+            ok = ok and all(np.array_equal(out2[k].numpy(), p[k]) for k in shard)
+            ok = ok and all(ig.shard[k].data_ptr() == out2[k][lo:hi].data_ptr() for k in shard)
         q.put((rank, ok, pkg.shard.slice_bounds(n, rank, world)))
     finally:
         dist.destroy_process_group()
