@@ -12,4 +12,6 @@ for mixed in (1, 0):
     mh = pkg.ics.gas_mass_in_h(p, 32)
     out, _ = pkg.run_step(dict(p), 0.5, 1e18, mh, 0.0, context=ctx)
     ctx.tree_particles(); ctx.nodes(); ctx.target_counters()
+    ctx.set_particles(dict(p))                                  # the fused call (one synchronisation) on the same particles
+    ctx.force_path(out["R"] / 1e5, mh, 0.0, 1e18, 0.5)
 print("done", ctx.counters()["interactions"])
