@@ -442,7 +442,7 @@ int agb_force_path(agb_ctx* c, double visual_density_radius, double mass_in_h, d
         return AGB_OK;
     };
     if (c->d.n == 0 || !c->gas_hint_valid) return stepwise();
-    if (!(e0 > 2.147483648e13)) return agb_forces_slice(c, global_time, e0, theta, part, nparts);   // reports AGB_ERR_UNSUPPORTED
+    if (!(e0 > 2.147483648e13)) { c->err = "e0 <= 2^31 * 1e4: the reference's int-abs softening branch is not covered"; return AGB_ERR_UNSUPPORTED; }
     CK(cudaSetDevice(c->device));
     AgbDev& d = c->d;
     c->built = false; c->dens_done = false; c->forces_done = false; c->counters_valid = false;

@@ -489,8 +489,26 @@ struct Driver {
         in.ax = p.ax.data(); in.ay = p.ay.data(); in.az = p.az.data();
         check(ctx, agb_set_particles(ctx, &in, AGB_MEM_HOST), "set_particles");
     }
+    void log_ms(const std::string& name, double ms)
+    {
+        if (log.path.empty()) return;
+        std::ostringstream os; os << ms * 1e-3;
+        std::string num = os.str();
+        std::replace(num.begin(), num.end(), '.', ',');
+        std::ofstream f(log.path, std::ios::app);
+        f << name << ";" << num << "\n";
+    }
     void device_force_path(bool first)
     {
+        if (!first) {
+            // steady state: the four calls in one (a single host synchronisation); the reference's phase rows come from the device timers
+            log.end();
+            check(ctx, agb_force_path(ctx, visualDensityRadius, cfg.massInH, globalTime, cfg.e0, cfg.theta, 0, 1, nullptr), "force_path");
+            double ms[5] = {0, 0, 0, 0, 0};
+            agb_get_phase_ms(ctx, ms);
+            log_ms("build tree", ms[0]); log_ms("Visual Density", ms[1]); log_ms("SPH density and update", ms[2]); log_ms("Force Calculation", ms[4]);
+            return;
+        }
         log.start("build tree");
         double R = 0;
         check(ctx, agb_build_tree(ctx, &R), "build_tree");
