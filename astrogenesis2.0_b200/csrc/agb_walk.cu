@@ -1,4 +1,4 @@
-// agb_walk.cu — warp-cooperative Barnes–Hut walk with in-walk SPH (sm_100a).
+// agb_walk.cu — warp-cooperative Barnes–Hut walk and the SPH pair kernel (sm_100a).
 //
 // Replaces Tree::calculateForces (Physics/Tree/Tree.cpp:57-83), Node::calculateGravityForce
 // (Physics/Tree/Node.cpp:247-399) and Node::calcSPHForce (Node.cpp:88-172, Math/kernel.cpp:18-39).
@@ -10,19 +10,25 @@
 // e0 > 2.15e13); SPH pressure + Monaghan–Gingold viscosity + dU/dt against every
 // accepted node/leaf that holds gas and lies within r < 2 h_i, with the target's own h, rho, P.
 //
-// B200 mapping: one warp owns 32 tree-adjacent targets.  The warp walks the UNION of their trees
-// with a shared-memory stack of (node, lane-mask) pairs.  Each lane pops a different node and
-// classifies it against the bounding box of the warp's targets:
+// B200 mapping: one warp owns 32 tree-adjacent targets.  k_far walks the upper tree once per 256
+// targets; k_walk continues per warp on the UNION of its targets' trees with a shared-memory stack
+// of (node, lane-mask) pairs.  Each lane pops a different node and classifies it against the
+// bounding box of the warp's targets:
 //     box entirely beyond radius/theta   -> accepted by every lane in the mask
 //     box entirely inside radius/theta   -> opened by every lane in the mask (children inherit mask)
-//     straddling                         -> per-lane exact test (__ballot_sync splits the mask)
+//     straddling                         -> per-lane test (__ballot_sync splits the mask)
 // so the per-target accepted set is exact while most of the tree is pruned at 1/32 of the cost.
 // Accepted sources go to a shared-memory interaction list; the list is drained in tiles of 32:
-// lanes gather the 32 sources (coalesced double4 loads) into a staging buffer, then every lane runs
-// all of them against its own target out of shared memory (broadcast reads).  Arithmetic is FP64 on
-// the CUDA-core FP64 pipe (no tensor cores: this is not a dense contraction).  Decisions that must
-// match the reference bit for bit (MAC, r < 2h) use a cheap guarded test and fall back to the
-// reference's exact separately-rounded expression when within 1e-13 of the threshold.
+// lanes gather the 32 sources (double4 loads) into a staging buffer, then every lane runs all of
+// them against its own target out of shared memory (broadcast reads).  No tensor cores: this is
+// not a dense contraction.  Pair arithmetic is FP32 with float-float displacements where pairs are
+// close (default "mixed" mode; three evaluation classes, packed FFMA2/FADD2, one MUFU per pair) or
+// FP64 throughout.  Decisions that must match the reference bit for bit (MAC, r < 2h) are taken in
+// FP32 only where that provably gives the FP64 answer, otherwise in FP64, and within 1e-13 of the
+// threshold by the reference's own separately rounded expression.
+// SPH pairs: inside the walk in FP64 mode; in mixed mode the walk records (source, accepting gas
+// targets) entries and k_sph evaluates them afterwards (keeps the walk's hot code inside the 32 KB
+// instruction cache).
 #include "agb_internal.cuh"
 #include <algorithm>
 #include <cstdlib>
@@ -37,8 +43,6 @@ constexpr int LGROW = 288;                 // worst-case growth per pop round: 3
 #endif
 constexpr int WALK_CTAS = AGB_WALK_CTAS_PER_SM;
 constexpr int SCAP = 384;   // shared part of the traversal stack (the rest spills to global memory)
-constexpr int GASBIT = 1 << 30;
-constexpr int IDXMASK = GASBIT - 1;
 constexpr double kG = 6.67430e-11;         // Math/Constants.h:7
 constexpr double kPI = 3.14159265358979323846;
 constexpr double kGAMMA = 5.0 / 3.0;
@@ -284,7 +288,6 @@ __global__ void __launch_bounds__(WalkCfg<SPH>::TPB, WALK_CTAS) k_walk(const Wal
     const double m0 = n_nodes > 0 ? fmax(P.src_pm[N].w / (double)max(n_in_tree, 1), 1e-300) : (n_in_tree > 0 && P.src_pm[0].w > 0.0 ? P.src_pm[0].w : 1.0);
     const double inv_m0 = 1.0 / m0, acc_scale = kG * m0 * invR2;
     const float e02f = (float)e02s;
-    const double invR4 = invR2 * invR2;
 
     unsigned long long tot_node = 0, tot_leaf = 0, tot_sph = 0, tot_visit = 0, tot_exact = 0, tot_spill = 0;
     unsigned long long st_rounds = 0, st_popped = 0, st_mixed = 0, st_open = 0, st_drain = 0;
