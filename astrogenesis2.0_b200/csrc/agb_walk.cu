@@ -384,7 +384,7 @@ __global__ void __launch_bounds__(WalkCfg<SPH>::TPB, WALK_CTAS) k_walk(const Wal
                 nth_x = make_float2(-thx, -thx); nth_y = make_float2(-thy, -thy); nth_z = make_float2(-thz, -thz);
                 ntl_x = make_float2(-tlx, -tlx); ntl_y = make_float2(-tly, -tly); ntl_z = make_float2(-tlz, -tlz);
                 hh4sf = (float)(hh4 * invR2);
-                far2 = P.far_k2 * hd2;                                      // the squared "far" distance: 2 half-diagonals of the box
+                far2 = P.far_k2 * hd2;                                      // the squared "far" distance: half a half-diagonal of the box
                 hh4cf = hh4sf * (1.0f + 1e-5f);
             }
             // SPLIT: a source can only matter to SPH if it lies within 2 h_max of the warp's box (h = 2 radius of a cell, so 2h / L
@@ -549,8 +549,9 @@ __global__ void __launch_bounds__(WalkCfg<SPH>::TPB, WALK_CTAS) k_walk(const Wal
                     //   0  far + accepted by every target: single-float displacements, no mask
                     //   1  far: single-float displacements
                     //   2  near: float-float displacements (close pairs cancel)
-                    // "far" = at least 2 half-diagonals of the warp's box away from the box: dropping the low parts then costs
-                    // <= 2^-24 (|s| + |t|) / |d| <= 1.2e-7 relative per pair.
+                    // "far" = at least half a half-diagonal of the warp's box away from the box: dropping the low parts then costs
+                    // <= 2^-24 (|s| + |t|) / |d| <= 3e-7 relative per pair (measured: 2, 1, 1/2, 1/4.5 half-diagonals give 1.410, 1.406,
+                    // 1.392, 1.379 ms on C1; median / p99 error 4.35e-8 / 9.6e-7 at 2 and 4.45e-8 / 1.0e-6 at 1/2).
                     int pos = lane, cls = 3;
                     int2 e = make_int2(0, 0);
                     if (lane < cnt) e = sm.list[base + lane];
@@ -1093,7 +1094,7 @@ int agb_launch_walk(AgbDev& d, AgbScalars* s, double globalTime, double e0, doub
     P.s = s; P.N = d.n; P.act_list = d.act_list; P.part = part; P.nparts = nparts;
     P.theta = theta; P.e0 = e0; P.globalTime = globalTime;
     // tuning knob (not part of the ABI): AGB200_WALK_FAR_K2=1e30 sends every pair through the float-float loop
-    static const float far_k2 = getenv("AGB200_WALK_FAR_K2") ? (float)atof(getenv("AGB200_WALK_FAR_K2")) : 4.0f;
+    static const float far_k2 = getenv("AGB200_WALK_FAR_K2") ? (float)atof(getenv("AGB200_WALK_FAR_K2")) : 0.25f;
     P.far_k2 = far_k2;
     int launches = 0;
     const int nb = (int)((d.n + 255) / 256);

@@ -213,8 +213,16 @@ def run_gpu_arm(args, pkg):
         if world > 1:
             packed.gather(shard)
 
+    breakdown = os.environ.get("AGB_BENCH_BREAKDOWN") == "1"      # development: per-step device time of the exchange vs the path
+    bd_ev = []
+
     def step():
+        if breakdown:
+            e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+            e[0].record(torch.cuda.current_stream())
         gather()
+        if breakdown:
+            e[1].record(torch.cuda.current_stream())
         if world > 1:
             stream.wait_stream(torch.cuda.current_stream())
         ptrs = {k: full[k].data_ptr() for k in full}
@@ -222,6 +230,9 @@ def run_gpu_arm(args, pkg):
         # build_tree + visual_density + gas_density + forces, one host synchronisation (agb_force_path); the visual-density
         # radius is fixed at init like in the reference (Simulation.cpp:126)
         ctx.force_path(vis_radius, mh, 0.0, e0, THETA, rank, world)
+        if breakdown:
+            e[2].record(stream)
+            bd_ev.append((e, ctx.phase_ms()))
 
     def barrier():
         if world > 1:
@@ -368,6 +379,12 @@ def run_gpu_arm(args, pkg):
             # particles out after a few steps and the rest of the system then sits deeper than 42 octree levels (AGB_ERR_DEPTH)
             resident = {"error": str(e), "what": "device-resident KDK loop with the shipped fixed time step"}
 
+    if breakdown:
+        torch.cuda.synchronize()
+        ex = np.mean([e[0].elapsed_time(e[1]) for e, _ in bd_ev[args.warmup:args.warmup + args.steps]])
+        pa = np.mean([e[1].elapsed_time(e[2]) for e, _ in bd_ev[args.warmup:args.warmup + args.steps]])
+        ph = {k: float(np.mean([q[k] for _, q in bd_ev[args.warmup:args.warmup + args.steps]])) for k in bd_ev[0][1]}
+        print("rank %d breakdown: exchange %.3f ms, path call %.3f ms, phases %s" % (rank, ex, pa, json.dumps(ph)), file=sys.stderr, flush=True)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
