@@ -51,3 +51,25 @@ def test_ics_shapes(pkg):
     assert len(p["x"]) == 1000 and set(p["type"]) <= {1, 2, 3} and (p["type"] == 2).sum() > 0
     p = pkg.ics.plummer(100, seed=1)
     assert p["mass"].sum() == pytest.approx(1e11 * pkg.ics.MSUN)
+
+
+def test_ctypes_mirror_matches_the_header(pkg, tmp_path):
+    """The ctypes structures of capi.py must have the layout a C compiler gives the structs of include/agb200.h
+    (a field added on one side only would silently shift every later field)."""
+    import subprocess
+    fields = {"agb_particles": pkg.capi.Particles, "agb_results": pkg.capi.Results, "agb_aos_layout": pkg.capi.AosLayout, "agb_counters": pkg.capi.Counters}
+    prog = ['#include <stdio.h>', '#include <stddef.h>', '#include "agb200.h"', "int main(void) {"]
+    for cname, ct in fields.items():
+        prog.append('printf("%s %%zu\\n", sizeof(%s));' % (cname, cname))
+        for fname, _ in ct._fields_:
+            prog.append('printf("%s.%s %%zu\\n", offsetof(%s, %s));' % (cname, fname, cname, fname))
+    prog += ["return 0; }"]
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(prog))
+    exe = tmp_path / "layout"
+    subprocess.check_call(["gcc", "-std=c11", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    got = dict(line.split() for line in subprocess.check_output([str(exe)], text=True).splitlines())
+    for cname, ct in fields.items():
+        assert int(got[cname]) == C.sizeof(ct), cname
+        for fname, _ in ct._fields_:
+            assert int(got["%s.%s" % (cname, fname)]) == getattr(ct, fname).offset, (cname, fname)
