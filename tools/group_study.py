@@ -194,12 +194,20 @@ def main():
     rng = np.random.default_rng(1)
     sample = 400
     base = evaluate("fixed32", groups_fixed(n), pos, T, theta, sample, np.random.default_rng(1))
-    for lo in (28, 24, 16):
+    for lo in (28,):
         evaluate("cut%d..32" % lo, groups_cut(key, depth, lo, 32), pos, T, theta, sample, np.random.default_rng(1))
     evaluate("nodes<=32", groups_nodes(T, n), pos, T, theta, sample, np.random.default_rng(1))
     h = hilbert_order(pos, R)
     hg = [h[i:i + 32] for i in range(0, n, 32)]
     evaluate("hilbert32", hg, pos, T, theta, sample, np.random.default_rng(1))
+    rank = np.empty(n, np.int64); rank[h] = np.arange(n)                        # position along the Hilbert curve
+    for blk in (256, 2048):                                                     # Hilbert order only inside blocks of tree-ordered targets
+        lg = []
+        for b0 in range(0, n, blk):
+            idx = np.arange(b0, min(n, b0 + blk))
+            idx = idx[np.argsort(rank[idx], kind="stable")]
+            lg += [idx[i:i + 32] for i in range(0, len(idx), 32)]
+        evaluate("hilb/%d" % blk, lg, pos, T, theta, sample, np.random.default_rng(1))
     evaluate("fixed16", groups_fixed(n, 16), pos, T, theta, sample, np.random.default_rng(1))
     evaluate("fixed64", groups_fixed(n, 64), pos, T, theta, sample // 2, np.random.default_rng(1))       # two targets per lane
     evaluate("hilbert64", [h[i:i + 64] for i in range(0, n, 64)], pos, T, theta, sample // 2, np.random.default_rng(1))
