@@ -101,7 +101,7 @@ int ensure_pool(agb_ctx* c, int64_t n)
     for (auto& q : c->in_d) CK(dalloc(q, cap));
     CK(dalloc(c->timestep, cap));
     CK(dalloc(c->in_type, cap));
-    CK(dalloc(d.blockhist, 256 * ((cap + 2047) / 2048 + 1)));   // sort tiles are >= 2048 keys
+    CK(dalloc(d.blockhist, 256 * ((cap + 2047) / 2048 + 1) + 8 * 256 + 64));   // sort tiles are >= 2048 keys (+ digit totals and tickets of the one-sweep variant)
     CK(dalloc(d.scanblk, (cap + 2047) / 2048 + 1));
     d.cap = (int64_t)cap;
     return AGB_OK;
