@@ -8,6 +8,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libagb200.so")
 SOURCES = ["agb_api.cu", "agb_build.cu", "agb_density.cu", "agb_walk.cu", "agb_integrate.cu"]
+# tree geometry, moments and densities are compared with the reference's separately rounded sums: no FMA contraction there
+NO_FMAD = ("agb_build.cu", "agb_density.cu", "agb_integrate.cu")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-O2", "--use_fast_math=false"]
 
@@ -35,7 +37,7 @@ def build_lib(force=False, verbose=False):
     for src in SOURCES:
         obj = os.path.join(CSRC, src.replace(".cu", ".o"))
         cmd = [_nvcc()] + [f for f in NVCC_FLAGS if f != "--use_fast_math=false"] + (["-Xptxas", "-v"] if verbose else []) + \
-              ["-c", os.path.join(CSRC, src), "-o", obj]
+              (["-fmad=false"] if src in NO_FMAD else []) + ["-c", os.path.join(CSRC, src), "-o", obj]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
         objs.append(obj)
     for src, p in procs:

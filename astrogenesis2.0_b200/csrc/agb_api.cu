@@ -16,8 +16,11 @@ struct agb_ctx {
     int device = 0, sm_count = 148;
     cudaStream_t st = nullptr, st_copy = nullptr;   // compute stream; upload stream for everything but x, y, z
     cudaEvent_t ev_in = nullptr;                      // uploads on st_copy complete
+    cudaEvent_t ev_sync = nullptr;                    // compute stream reached the point of a new hand-over (orders st_copy after it)
     bool in_pending = false;
     cudaEvent_t ev[10] = {};
+    cudaEvent_t evk[10] = {};                         // kernel-level timing: walk [0..3] = before k_far, k_walk, k_sph, after; build [4..9] = start, keys, sort, gather, links, end
+    double kernel_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // k_far k_walk k_sph | extent+keys sort gather lcp+scan+links upward+finalize
     bool gas_hint_valid = false, gas_hint = false;   // agb_force_path: "the particle set holds gas" as of the last completed step
     AgbDev d;
     AgbScalars* s = nullptr;            // device
@@ -26,7 +29,7 @@ struct agb_ctx {
     uint8_t* in_type = nullptr;
     bool bound = false, have_particles = false, built = false, dens_done = false, forces_done = false;
     bool mixed = true;                  // AGB_OPT_PRECISION
-    bool target_counters = false, counters_valid = false, vis_timed = false, gas_timed = false;
+    bool target_counters = false, counters_valid = false, vis_timed = false, gas_timed = false, build_timed = false;
     double phase_ms[5] = {0, 0, 0, 0, 0};
     int64_t launches = 0;
     std::string err;
@@ -49,25 +52,39 @@ constexpr int64_t SPILL_PER_WARP = 8192;
         cudaError_t e_ = (call);                                                                   \
         if (e_ != cudaSuccess) {                                                                   \
             c->err = std::string(#call) + ": " + cudaGetErrorString(e_);                           \
+            if (e_ == cudaErrorMemoryAllocation) { (void)cudaGetLastError(); return AGB_ERR_NOMEM; } \
             return AGB_ERR_CUDA;                                                                   \
         }                                                                                          \
     } while (0)
 
 template <class T> cudaError_t dalloc(T*& p, size_t count) { return cudaMalloc((void**)&p, std::max<size_t>(count, 1) * sizeof(T)); }
 template <class T> void dfree(T*& p) { if (p) cudaFree((void*)p); p = nullptr; }
+template <class T> struct DevTmp { T* p = nullptr; ~DevTmp() { if (p) cudaFree((void*)p); } };   // scoped device temporary
+
+// Node-indexed arrays (and the scratch that doubles as per-node storage in the density pass).  Their capacity is separate
+// from the particle capacity: the tree has one node per (first particle, depth) pair, so M ~ 0.48 N for galaxies but up
+// to 41 N for sets of tight pairs (Sun / Earth / Moon: N = 3, M = 9).
+void free_nodes(agb_ctx* c)
+{
+    AgbDev& d = c->d;
+    dfree(d.src_pm); dfree(d.src_gv); dfree(d.src_flag);
+    dfree(d.child); dfree(d.nfirst); dfree(d.nlast); dfree(d.nparent); dfree(d.arrived); dfree(d.ndepth);
+    dfree(d.nmark); dfree(d.ndup); dfree(d.mom_pm); dfree(d.mom_gv); dfree(d.grouplist);
+    dfree(d.klo[0]); dfree(d.nodebase);
+    d.ncap = 0;
+}
 
 void free_pool(agb_ctx* c)
 {
     AgbDev& d = c->d;
+    free_nodes(c);
     for (auto& q : c->in_d) dfree(q);
     dfree(c->in_type); dfree(c->timestep);
     dfree(d.ax); dfree(d.ay); dfree(d.az); dfree(d.dUdt); dfree(d.h); dfree(d.rho); dfree(d.P); dfree(d.T); dfree(d.vis);
     for (int i = 0; i < 2; i++) { dfree(d.khi[i]); dfree(d.klo[i]); dfree(d.perm[i]); }
-    dfree(d.src_pm); dfree(d.src_gv); dfree(d.src_flag);
     dfree(d.s_h); dfree(d.s_rho); dfree(d.s_P); dfree(d.s_U); dfree(d.s_mu); dfree(d.s_next); dfree(d.s_T); dfree(d.s_type);
-    dfree(d.lcp); dfree(d.nodebase); dfree(d.nodecnt); dfree(d.leafparent); dfree(d.group); dfree(d.leafdepth);
-    dfree(d.child); dfree(d.nfirst); dfree(d.nlast); dfree(d.nparent); dfree(d.arrived); dfree(d.ndepth);
-    dfree(d.nmark); dfree(d.ndup); dfree(d.leafmark); dfree(d.mom_pm); dfree(d.mom_gv); dfree(d.grouplist); dfree(d.gasrank);
+    dfree(d.lcp); dfree(d.nodecnt); dfree(d.leafparent); dfree(d.group); dfree(d.leafdepth);
+    dfree(d.leafmark); dfree(d.gasrank);
     dfree(d.rec); dfree(d.blockhist); dfree(d.scanblk);
     dfree(d.far_list); dfree(d.far_front); dfree(d.far_cnt); dfree(d.act_list);
     dfree(d.c_visits); dfree(d.c_accn); dfree(d.c_accl); dfree(d.c_sph);
@@ -75,22 +92,37 @@ void free_pool(agb_ctx* c)
     d.cap = 0;
 }
 
+int ensure_nodes(agb_ctx* c, int64_t want)
+{
+    AgbDev& d = c->d;
+    want = std::max<int64_t>(want, d.cap);
+    if (want <= d.ncap) return AGB_OK;
+    if (want + d.cap >= (1ll << 31)) { c->err = "more than 2^31 particles + nodes"; return AGB_ERR_NOMEM; }
+    free_nodes(c);
+    const size_t nc = (size_t)want, cap = (size_t)d.cap;
+    CK(dalloc(d.src_pm, cap + nc)); CK(dalloc(d.src_gv, cap + nc)); CK(dalloc(d.src_flag, cap + nc));
+    CK(dalloc(d.child, 8 * nc)); CK(dalloc(d.nfirst, nc)); CK(dalloc(d.nlast, nc)); CK(dalloc(d.nparent, nc)); CK(dalloc(d.arrived, nc)); CK(dalloc(d.ndepth, nc));
+    CK(dalloc(d.nmark, nc)); CK(dalloc(d.ndup, nc)); CK(dalloc(d.mom_pm, nc)); CK(dalloc(d.mom_gv, nc)); CK(dalloc(d.grouplist, nc));
+    CK(dalloc(d.klo[0], nc)); CK(dalloc(d.nodebase, nc));     // per particle in the build, per node (exact sums, fold list) in the density pass
+    d.ncap = (int64_t)nc;
+    return AGB_OK;
+}
+
 int ensure_pool(agb_ctx* c, int64_t n)
 {
     AgbDev& d = c->d;
-    if (n <= d.cap) return AGB_OK;
+    if (n <= d.cap && d.ncap > 0) return AGB_OK;
     free_pool(c);
     const size_t cap = (size_t)n;
     d.x = d.y = d.z = d.vx = d.vy = d.vz = d.mass = d.U = d.next = d.mu = nullptr; d.type = nullptr;
     CK(dalloc(d.ax, cap)); CK(dalloc(d.ay, cap)); CK(dalloc(d.az, cap)); CK(dalloc(d.dUdt, cap)); CK(dalloc(d.h, cap));
     CK(dalloc(d.rho, cap)); CK(dalloc(d.P, cap)); CK(dalloc(d.T, cap)); CK(dalloc(d.vis, cap));
-    for (int i = 0; i < 2; i++) { CK(dalloc(d.khi[i], cap)); CK(dalloc(d.klo[i], cap)); CK(dalloc(d.perm[i], cap)); }
-    CK(dalloc(d.src_pm, 2 * cap)); CK(dalloc(d.src_gv, 2 * cap)); CK(dalloc(d.src_flag, 2 * cap));
+    for (int i = 0; i < 2; i++) { CK(dalloc(d.khi[i], cap)); CK(dalloc(d.perm[i], cap)); }
+    CK(dalloc(d.klo[1], cap));
     CK(dalloc(d.s_h, cap)); CK(dalloc(d.s_rho, cap)); CK(dalloc(d.s_P, cap)); CK(dalloc(d.s_U, cap)); CK(dalloc(d.s_mu, cap));
     CK(dalloc(d.s_next, cap)); CK(dalloc(d.s_T, cap)); CK(dalloc(d.s_type, cap));
-    CK(dalloc(d.lcp, cap)); CK(dalloc(d.nodebase, cap)); CK(dalloc(d.nodecnt, cap)); CK(dalloc(d.leafparent, cap)); CK(dalloc(d.group, cap)); CK(dalloc(d.leafdepth, cap));
-    CK(dalloc(d.child, 8 * cap)); CK(dalloc(d.nfirst, cap)); CK(dalloc(d.nlast, cap)); CK(dalloc(d.nparent, cap)); CK(dalloc(d.arrived, cap)); CK(dalloc(d.ndepth, cap));
-    CK(dalloc(d.nmark, cap)); CK(dalloc(d.ndup, cap)); CK(dalloc(d.leafmark, cap)); CK(dalloc(d.mom_pm, cap)); CK(dalloc(d.mom_gv, cap)); CK(dalloc(d.grouplist, cap)); CK(dalloc(d.gasrank, cap + 1));
+    CK(dalloc(d.lcp, cap)); CK(dalloc(d.nodecnt, cap)); CK(dalloc(d.leafparent, cap)); CK(dalloc(d.group, cap)); CK(dalloc(d.leafdepth, cap));
+    CK(dalloc(d.leafmark, cap)); CK(dalloc(d.gasrank, cap + 1));
     CK(dalloc(d.rec, cap));
     {
         int lcap, fcap, tg; agb_far_capacity(&lcap, &fcap, &tg);
@@ -104,7 +136,7 @@ int ensure_pool(agb_ctx* c, int64_t n)
     CK(dalloc(d.blockhist, 256 * ((cap + 2047) / 2048 + 1) + 8 * 256 + 64));   // sort tiles are >= 2048 keys (+ digit totals and tickets of the one-sweep variant)
     CK(dalloc(d.scanblk, (cap + 2047) / 2048 + 1));
     d.cap = (int64_t)cap;
-    return AGB_OK;
+    return ensure_nodes(c, (int64_t)cap + 1024);
 }
 
 int ensure_counters(agb_ctx* c)
@@ -203,6 +235,21 @@ const char* agb_strerror(int st)
 
 const char* agb_last_error(agb_ctx* c) { return c ? c->err.c_str() : ""; }
 
+static void destroy_handles(agb_ctx* c)
+{
+    if (c->ev_in) cudaEventDestroy(c->ev_in);
+    if (c->ev_out) cudaEventDestroy(c->ev_out);
+    if (c->ev_sync) cudaEventDestroy(c->ev_sync);
+    for (auto& e : c->ev) if (e) cudaEventDestroy(e);
+    for (auto& e : c->evk) if (e) cudaEventDestroy(e);
+    if (c->st_copy) cudaStreamDestroy(c->st_copy);
+    if (c->st) cudaStreamDestroy(c->st);
+    if (c->d.spill) cudaFree(c->d.spill);
+    if (c->s) cudaFree(c->s);
+    if (c->stage) cudaFreeHost(c->stage);
+    if (c->d_min) cudaFree(c->d_min);
+}
+
 int agb_create(agb_ctx** out, int device, int compat_cores)
 {
     if (!out) return AGB_ERR_INVALID;
@@ -217,17 +264,19 @@ int agb_create(agb_ctx** out, int device, int compat_cores)
     c->device = device;
     c->sm_count = prop.multiProcessorCount;
     c->d.cores = compat_cores > 0 ? compat_cores : 1;
-    if (cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking) != cudaSuccess) { delete c; return AGB_ERR_NO_DEVICE; }
-    if (cudaStreamCreateWithFlags(&c->st_copy, cudaStreamNonBlocking) != cudaSuccess) { delete c; return AGB_ERR_NO_DEVICE; }
-    cudaEventCreateWithFlags(&c->ev_in, cudaEventDisableTiming);
-    cudaEventCreateWithFlags(&c->ev_out, cudaEventDisableTiming);
-    for (auto& e : c->ev) cudaEventCreate(&e);
-    if (cudaMalloc((void**)&c->s, sizeof(AgbScalars)) != cudaSuccess) { delete c; return AGB_ERR_NOMEM; }
+    auto fail = [&](int rc) { destroy_handles(c); delete c; (void)cudaGetLastError(); return rc; };
+    if (cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking) != cudaSuccess) return fail(AGB_ERR_NO_DEVICE);
+    if (cudaStreamCreateWithFlags(&c->st_copy, cudaStreamNonBlocking) != cudaSuccess) return fail(AGB_ERR_NO_DEVICE);
+    if (cudaEventCreateWithFlags(&c->ev_in, cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&c->ev_out, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c->ev_sync, cudaEventDisableTiming) != cudaSuccess) return fail(AGB_ERR_NO_DEVICE);
+    for (auto& e : c->ev) if (cudaEventCreate(&e) != cudaSuccess) return fail(AGB_ERR_NO_DEVICE);
+    for (auto& e : c->evk) if (cudaEventCreate(&e) != cudaSuccess) return fail(AGB_ERR_NO_DEVICE);
+    if (cudaMalloc((void**)&c->s, sizeof(AgbScalars)) != cudaSuccess) return fail(AGB_ERR_NOMEM);
     cudaMemsetAsync(c->s, 0, sizeof(AgbScalars), c->st);
     memset(&c->hs, 0, sizeof(c->hs));
     c->d.spill_warps = agb_walk_blocks(c->sm_count) * agb_walk_warps_per_block();
     c->d.spill_per_warp = SPILL_PER_WARP;
-    if (cudaMalloc((void**)&c->d.spill, (size_t)c->d.spill_warps * SPILL_PER_WARP * sizeof(int2)) != cudaSuccess) { cudaFree(c->s); delete c; return AGB_ERR_NOMEM; }
+    if (cudaMalloc((void**)&c->d.spill, (size_t)c->d.spill_warps * SPILL_PER_WARP * sizeof(int2)) != cudaSuccess) return fail(AGB_ERR_NOMEM);
     *out = c;
     return AGB_OK;
 }
@@ -238,12 +287,7 @@ int agb_destroy(agb_ctx* c)
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->st); cudaStreamSynchronize(c->st_copy);
     free_pool(c);
-    cudaEventDestroy(c->ev_in); cudaEventDestroy(c->ev_out); cudaStreamDestroy(c->st_copy);
-    cudaFree(c->d.spill);
-    cudaFree(c->s);
-    if (c->stage) cudaFreeHost(c->stage);
-    for (auto& e : c->ev) cudaEventDestroy(e);
-    cudaStreamDestroy(c->st);
+    destroy_handles(c);
     delete c;
     return AGB_OK;
 }
@@ -265,6 +309,10 @@ int agb_set_particles(agb_ctx* c, const agb_particles* p, int memspace)
     if (rc) return rc;
     AgbDev& d = c->d;
     d.n = n;
+    // Everything already queued on the compute stream (densities, walk, integrator kernels of the previous step) reads or
+    // writes the buffers the copy stream is about to overwrite: order the copy stream after it.
+    CK(cudaEventRecord(c->ev_sync, c->st));
+    CK(cudaStreamWaitEvent(c->st_copy, c->ev_sync, 0));
     if (memspace == AGB_MEM_DEVICE) {
         // zero-copy: the caller's device arrays are read in place (they must stay valid until the next set_particles)
         d.x = p->x; d.y = p->y; d.z = p->z; d.vx = p->vx; d.vy = p->vy; d.vz = p->vz; d.mass = p->mass; d.U = p->U; d.next = p->next_time; d.mu = p->mu;
@@ -297,7 +345,10 @@ static inline double* aos_d(void* base, int64_t off) { return reinterpret_cast<d
 
 int agb_set_particles_aos(agb_ctx* c, void* const* parts, int64_t n, const agb_aos_layout* L)
 {
-    if (!c || !parts || !L || n < 0 || L->position < 0 || L->mass < 0 || L->type < 0) return AGB_ERR_INVALID;
+    if (!c || !parts || !L || n < 0 || n >= (1ll << 30) || L->position < 0 || L->mass < 0 || L->type < 0) return AGB_ERR_INVALID;
+    CK(cudaSetDevice(c->device));
+    // the pinned staging buffer may still be the source of an upload in flight (or the target of a download)
+    CK(cudaStreamSynchronize(c->st_copy)); CK(cudaStreamSynchronize(c->st));
     // gather the array-of-structs records (the reference's Particle, 264 B each) into 21 SoA columns
     const size_t cols = 21, need = cols * (size_t)std::max<int64_t>(n, 1) * sizeof(double) + (size_t)n;
     if (need > c->stage_bytes) {
@@ -330,6 +381,29 @@ int agb_set_particles_aos(agb_ctx* c, void* const* parts, int64_t n, const agb_a
     return agb_set_particles(c, &p, AGB_MEM_HOST);
 }
 
+// the kernels of Tree::buildTree on the context's stream (no synchronisation)
+static void launch_build(agb_ctx* c)
+{
+    AgbDev& d = c->d;
+    cudaEventRecord(c->evk[4], c->st);
+    c->launches += agb_launch_extent(d, c->s, c->st);
+    c->launches += agb_launch_keygen(d, c->s, c->st);
+    cudaEventRecord(c->evk[5], c->st);
+    c->launches += agb_launch_sort(d, c->s, c->st);
+    cudaEventRecord(c->evk[6], c->st);
+    if (c->in_pending) { cudaStreamWaitEvent(c->st, c->ev_in, 0); c->in_pending = false; }
+    c->launches += agb_launch_links(d, c->s, c->st, &c->evk[7]);
+    cudaEventRecord(c->evk[9], c->st);
+    c->build_timed = true;
+}
+
+// more (first particle, depth) pairs than node slots: the step wrote nothing past the capacity; make room for a rebuild
+static int grow_nodes(agb_ctx* c)
+{
+    const int64_t m = c->hs.n_nodes;
+    return ensure_nodes(c, m + m / 8 + 1024);
+}
+
 int agb_build_tree(agb_ctx* c, double* root_radius)
 {
     if (!c || !c->have_particles) return AGB_ERR_INVALID;
@@ -337,16 +411,17 @@ int agb_build_tree(agb_ctx* c, double* root_radius)
     AgbDev& d = c->d;
     c->built = false; c->dens_done = false; c->forces_done = false; c->counters_valid = false;
     if (d.n == 0) { if (root_radius) *root_radius = 0.0; memset((char*)&c->hs + offsetof(AgbScalars, mean), 0, sizeof(AgbScalars) - offsetof(AgbScalars, mean)); c->built = true; return AGB_OK; }
-    CK(cudaEventRecord(c->ev[0], c->st));
-    c->launches += agb_launch_extent(d, c->s, c->st);
-    c->launches += agb_launch_keygen(d, c->s, c->st);
-    c->launches += agb_launch_sort(d, c->s, c->st);
-    if (c->in_pending) { CK(cudaStreamWaitEvent(c->st, c->ev_in, 0)); c->in_pending = false; }
-    c->launches += agb_launch_links(d, c->s, c->st);
-    CK(cudaEventRecord(c->ev[1], c->st));
-    CK(cudaGetLastError());
-    int rc = fetch_scalars(c);
-    if (rc) return rc;
+    for (int attempt = 0;; attempt++) {
+        CK(cudaEventRecord(c->ev[0], c->st));
+        launch_build(c);
+        CK(cudaEventRecord(c->ev[1], c->st));
+        CK(cudaGetLastError());
+        int rc = fetch_scalars(c);
+        if (rc) return rc;
+        if (c->hs.n_nodes <= d.ncap) break;
+        if (attempt >= 1) { c->err = "node table overflow"; return AGB_ERR_NOMEM; }
+        if ((rc = grow_nodes(c))) return rc;
+    }
     float ms = 0; cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]); c->phase_ms[0] = ms;
     c->hs.R = 0; memcpy(&c->hs.R, &c->hs.Rbits, 8);
     if (root_radius) *root_radius = c->hs.R;
@@ -400,7 +475,7 @@ int agb_forces_slice(agb_ctx* c, double global_time, double e0, double theta, in
     // gas targets need h/rho/P: if the caller skipped gas_density they are orphans (h = 0) and get no SPH, like the reference
     const bool any_gas = c->hs.any_gas != 0;
     for (int attempt = 0;; attempt++) {
-        c->launches += agb_launch_walk(d, c->s, global_time, e0, theta, part, nparts, c->target_counters, any_gas, c->mixed, c->sm_count, c->st, c->ev[0], c->ev[1]);
+        c->launches += agb_launch_walk(d, c->s, global_time, e0, theta, part, nparts, c->target_counters, any_gas, c->mixed, c->sm_count, c->st, c->evk);
         CK(cudaEventRecord(c->ev[7], c->st));
         CK(cudaGetLastError());
         int rc = fetch_scalars(c);
@@ -411,8 +486,10 @@ int agb_forces_slice(agb_ctx* c, double global_time, double e0, double theta, in
         if (rc) return rc;
     }
     float ms = 0;
-    if (cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]) == cudaSuccess) c->phase_ms[3] = ms;
+    if (cudaEventElapsedTime(&ms, c->evk[0], c->evk[3]) == cudaSuccess) c->phase_ms[3] = ms;
     if (cudaEventElapsedTime(&ms, c->ev[6], c->ev[7]) == cudaSuccess) c->phase_ms[4] = ms;
+    for (int k = 0; k < 3; k++) if (cudaEventElapsedTime(&ms, c->evk[k], c->evk[k + 1]) == cudaSuccess) c->kernel_ms[k] = ms;
+    if (c->build_timed) for (int k = 0; k < 5; k++) if (cudaEventElapsedTime(&ms, c->evk[4 + k], c->evk[5 + k]) == cudaSuccess) c->kernel_ms[3 + k] = ms;
     if (c->vis_timed && cudaEventElapsedTime(&ms, c->ev[2], c->ev[3]) == cudaSuccess) c->phase_ms[1] = ms;
     if (c->gas_timed && cudaEventElapsedTime(&ms, c->ev[4], c->ev[5]) == cudaSuccess) c->phase_ms[2] = ms;
     (void)cudaGetLastError();
@@ -447,11 +524,7 @@ int agb_force_path(agb_ctx* c, double visual_density_radius, double mass_in_h, d
     AgbDev& d = c->d;
     c->built = false; c->dens_done = false; c->forces_done = false; c->counters_valid = false;
     CK(cudaEventRecord(c->ev[8], c->st));
-    c->launches += agb_launch_extent(d, c->s, c->st);
-    c->launches += agb_launch_keygen(d, c->s, c->st);
-    c->launches += agb_launch_sort(d, c->s, c->st);
-    if (c->in_pending) { CK(cudaStreamWaitEvent(c->st, c->ev_in, 0)); c->in_pending = false; }
-    c->launches += agb_launch_links(d, c->s, c->st);
+    launch_build(c);
     CK(cudaEventRecord(c->ev[9], c->st));
     CK(cudaGetLastError());
     c->built = true;
@@ -464,6 +537,11 @@ int agb_force_path(agb_ctx* c, double visual_density_radius, double mass_in_h, d
     (void)cudaGetLastError();
     c->hs.R = 0; memcpy(&c->hs.R, &c->hs.Rbits, 8);
     if (root_radius) *root_radius = c->hs.R;
+    if (c->hs.n_nodes > d.ncap) {                                   // node table overflow: every kernel after the node count returned at once
+        c->built = false; c->forces_done = false;
+        if ((rc = grow_nodes(c))) return rc;
+        return stepwise();
+    }
     if (c->hs.dup_keys > 0) { c->built = false; c->forces_done = false; c->err = "coincident particles (shared 42-level path)"; return AGB_ERR_DEPTH; }
     if ((c->hs.any_gas != 0) != c->gas_hint) { c->gas_hint_valid = false; return stepwise(); }   // gas appeared / vanished: redo with the right kernels
     return rc;
@@ -529,32 +607,44 @@ int agb_get_slice_count(agb_ctx* c, int part, int nparts, int64_t* count)
     return AGB_OK;
 }
 
-int agb_get_slice_results(agb_ctx* c, int part, int nparts, uint32_t* index, double* ax, double* ay, double* az, double* dUdt, int memspace)
+int agb_get_slice_results_all(agb_ctx* c, int part, int nparts, uint32_t* index, const agb_results* r, int memspace)
 {
     int64_t cnt = 0;
-    if (agb_get_slice_count(c, part, nparts, &cnt) != AGB_OK) return AGB_ERR_INVALID;
+    if (!r || agb_get_slice_count(c, part, nparts, &cnt) != AGB_OK) return AGB_ERR_INVALID;
     if (cnt == 0) return AGB_OK;
     CK(cudaSetDevice(c->device));
     AgbDev& d = c->d;
     int64_t a0 = 0, a1 = 0;
     agb_slice_bounds(c->hs.n_active, part, nparts, &a0, &a1);
     const bool ident = c->hs.n_active == d.n;
+    double* want[9] = {r->ax, r->ay, r->az, r->dUdt, r->h, r->rho, r->P, r->T, r->visualDensity};
     if (memspace == AGB_MEM_DEVICE) {
-        c->launches += agb_launch_slice_results(d, a0, a1, ident, index, ax, ay, az, dUdt, c->st);
+        c->launches += agb_launch_slice_results(d, a0, a1, ident, index, want, c->st);
         CK(cudaStreamSynchronize(c->st));
         return AGB_OK;
     }
-    // host destination: compact on the device first (scratch that is idle between the walk and the next build), then D2H
-    double* col = reinterpret_cast<double*>(d.rec);                    // 4 columns of cnt <= cap doubles
+    // host destination: compact on the device first, then D2H.  Scratch that is idle between the walk and the next build:
+    // rec (4 doubles per particle), the idle halves of the sort's ping-pong (key_hi, key_lo) and the per-node moments.
+    double* pool[9] = {reinterpret_cast<double*>(d.rec), reinterpret_cast<double*>(d.rec) + cnt, reinterpret_cast<double*>(d.rec) + 2 * cnt, reinterpret_cast<double*>(d.rec) + 3 * cnt,
+                       reinterpret_cast<double*>(d.khi[d.cur ^ 1]), reinterpret_cast<double*>(d.klo[0]), reinterpret_cast<double*>(d.mom_pm), reinterpret_cast<double*>(d.mom_pm) + cnt,
+                       reinterpret_cast<double*>(d.mom_gv)};
+    double* dev[9];
+    for (int k = 0; k < 9; k++) dev[k] = want[k] ? pool[k] : nullptr;
     uint32_t* idx = reinterpret_cast<uint32_t*>(d.nodecnt);
-    c->launches += agb_launch_slice_results(d, a0, a1, ident, index ? idx : nullptr, ax ? col : nullptr, ay ? col + cnt : nullptr, az ? col + 2 * cnt : nullptr,
-                                            dUdt ? col + 3 * cnt : nullptr, c->st);
+    c->launches += agb_launch_slice_results(d, a0, a1, ident, index ? idx : nullptr, dev, c->st);
     if (index) CK(cudaMemcpyAsync(index, idx, (size_t)cnt * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->st));
-    double* dst[4] = {ax, ay, az, dUdt};
-    for (int k = 0; k < 4; k++) if (dst[k]) CK(cudaMemcpyAsync(dst[k], col + (size_t)k * cnt, (size_t)cnt * sizeof(double), cudaMemcpyDeviceToHost, c->st));
+    for (int k = 0; k < 9; k++) if (want[k]) CK(cudaMemcpyAsync(want[k], dev[k], (size_t)cnt * sizeof(double), cudaMemcpyDeviceToHost, c->st));
     CK(cudaStreamSynchronize(c->st));
     CK(cudaGetLastError());
     return AGB_OK;
+}
+
+int agb_get_slice_results(agb_ctx* c, int part, int nparts, uint32_t* index, double* ax, double* ay, double* az, double* dUdt, int memspace)
+{
+    agb_results r;
+    memset(&r, 0, sizeof(r));
+    r.ax = ax; r.ay = ay; r.az = az; r.dUdt = dUdt;
+    return agb_get_slice_results_all(c, part, nparts, index, &r, memspace);
 }
 
 int agb_get_results_aos(agb_ctx* c, void* const* parts, int64_t n, const agb_aos_layout* L)
@@ -590,14 +680,13 @@ int agb_get_tree_particles(agb_ctx* c, int32_t* leafdepth, uint64_t* key_hi, uin
     CK(cudaSetDevice(c->device));
     const int64_t n = c->d.n;
     if (n == 0) return AGB_OK;
-    int32_t* dl = nullptr; uint64_t *dh = nullptr, *dlo = nullptr;
-    CK(dalloc(dl, (size_t)n)); CK(dalloc(dh, (size_t)n)); CK(dalloc(dlo, (size_t)n));
-    c->launches += agb_launch_dump_tree(c->d, c->s, dl, dh, dlo, c->st);
-    CK(cudaMemcpyAsync(leafdepth, dl, (size_t)n * 4, cudaMemcpyDeviceToHost, c->st));
-    CK(cudaMemcpyAsync(key_hi, dh, (size_t)n * 8, cudaMemcpyDeviceToHost, c->st));
-    CK(cudaMemcpyAsync(key_lo, dlo, (size_t)n * 8, cudaMemcpyDeviceToHost, c->st));
+    DevTmp<int32_t> dl; DevTmp<uint64_t> dh, dlo;                       // freed on every return path
+    CK(dalloc(dl.p, (size_t)n)); CK(dalloc(dh.p, (size_t)n)); CK(dalloc(dlo.p, (size_t)n));
+    c->launches += agb_launch_dump_tree(c->d, c->s, dl.p, dh.p, dlo.p, c->st);
+    CK(cudaMemcpyAsync(leafdepth, dl.p, (size_t)n * 4, cudaMemcpyDeviceToHost, c->st));
+    CK(cudaMemcpyAsync(key_hi, dh.p, (size_t)n * 8, cudaMemcpyDeviceToHost, c->st));
+    CK(cudaMemcpyAsync(key_lo, dlo.p, (size_t)n * 8, cudaMemcpyDeviceToHost, c->st));
     CK(cudaStreamSynchronize(c->st));
-    cudaFree(dl); cudaFree(dh); cudaFree(dlo);
     return AGB_OK;
 }
 
@@ -656,15 +745,15 @@ int agb_get_target_counters(agb_ctx* c, int32_t* visits, int32_t* acc_nodes, int
     CK(cudaSetDevice(c->device));
     const int64_t n = c->d.n;
     if (n == 0) return AGB_OK;
-    int32_t* tmp = nullptr;
-    CK(dalloc(tmp, 4 * (size_t)n));
+    DevTmp<int32_t> t;
+    CK(dalloc(t.p, 4 * (size_t)n));
+    int32_t* tmp = t.p;
     c->launches += agb_launch_unpermute_counters(c->d, tmp, tmp + n, tmp + 2 * n, tmp + 3 * n, c->st);
     CK(cudaMemcpyAsync(visits, tmp, (size_t)n * 4, cudaMemcpyDeviceToHost, c->st));
     CK(cudaMemcpyAsync(acc_nodes, tmp + n, (size_t)n * 4, cudaMemcpyDeviceToHost, c->st));
     CK(cudaMemcpyAsync(acc_leaves, tmp + 2 * n, (size_t)n * 4, cudaMemcpyDeviceToHost, c->st));
     CK(cudaMemcpyAsync(sph, tmp + 3 * n, (size_t)n * 4, cudaMemcpyDeviceToHost, c->st));
     CK(cudaStreamSynchronize(c->st));
-    cudaFree(tmp);
     return AGB_OK;
 }
 
@@ -672,6 +761,13 @@ int agb_get_phase_ms(agb_ctx* c, double ms[5])
 {
     if (!c || !ms) return AGB_ERR_INVALID;
     for (int i = 0; i < 5; i++) ms[i] = c->phase_ms[i];
+    return AGB_OK;
+}
+
+int agb_get_kernel_ms(agb_ctx* c, double ms[8])
+{
+    if (!c || !ms) return AGB_ERR_INVALID;
+    for (int i = 0; i < 8; i++) ms[i] = c->kernel_ms[i];
     return AGB_OK;
 }
 
@@ -689,7 +785,7 @@ int agb_integrator_init(agb_ctx* c, double eta, double min_time_step, double max
     if (!(min_time_step > 0.0) || !(max_time_step >= min_time_step)) return AGB_ERR_INVALID;
     CK(cudaSetDevice(c->device));
     AgbDev& d = c->d;
-    if (!d.vx || !d.vy || !d.vz || !d.U || !d.next) { c->err = "integrator needs vx, vy, vz, U and next_time arrays"; return AGB_ERR_INVALID; }
+    if (d.n > 0 && (!d.vx || !d.vy || !d.vz || !d.U || !d.next)) { c->err = "integrator needs vx, vy, vz, U and next_time arrays"; return AGB_ERR_INVALID; }
     if (c->in_pending) { CK(cudaStreamWaitEvent(c->st, c->ev_in, 0)); c->in_pending = false; }
     AgbInt& I = c->I;
     I.x = c->in_d[0]; I.y = c->in_d[1]; I.z = c->in_d[2]; I.vx = c->in_d[3]; I.vy = c->in_d[4]; I.vz = c->in_d[5]; I.U = c->in_d[7]; I.next = c->in_d[8];
@@ -703,7 +799,7 @@ int agb_integrator_init(agb_ctx* c, double eta, double min_time_step, double max
     for (int j = 0; j < AGB_INT_BINS; j++) I.scale_tab[j] = exp(H0SI * ldexp(1.0, I.k0 + j));
     I.scale_min = exp(H0SI * min_time_step);
     if (!c->d_min) CK(cudaMalloc((void**)&c->d_min, sizeof(unsigned long long)));
-    c->launches += agb_launch_int_init(d, I, c->st);
+    if (d.n > 0) c->launches += agb_launch_int_init(d, I, c->st);
     c->int_time = 0.0; c->int_ready = true;
     CK(cudaGetLastError());
     return AGB_OK;
@@ -713,7 +809,7 @@ int agb_integrator_assign_all(agb_ctx* c)
 {
     if (!c || !c->int_ready) return AGB_ERR_INVALID;
     CK(cudaSetDevice(c->device));
-    c->launches += agb_launch_int_assign(c->d, c->I, c->int_time, true, c->st);     // Simulation.cpp:189-208
+    if (c->d.n > 0) c->launches += agb_launch_int_assign(c->d, c->I, c->int_time, true, c->st);     // Simulation.cpp:189-208
     CK(cudaGetLastError());
     return AGB_OK;
 }
@@ -723,6 +819,7 @@ int agb_step_begin(agb_ctx* c, double* global_time)
     if (!c || !c->int_ready || !global_time) return AGB_ERR_INVALID;
     CK(cudaSetDevice(c->device));
     AgbDev& d = c->d;
+    if (d.n == 0) { *global_time = c->int_time; c->built = false; c->dens_done = false; c->forces_done = false; c->counters_valid = false; return AGB_OK; }
     c->launches += agb_launch_int_assign(d, c->I, c->int_time, false, c->st);         // Simulation.cpp:213-234
     c->launches += agb_launch_int_min(d, c->I, c->d_min, c->st);                      // :237-254
     unsigned long long bits = 0;
@@ -741,7 +838,7 @@ int agb_step_end(agb_ctx* c)
 {
     if (!c || !c->int_ready || !c->forces_done) return AGB_ERR_INVALID;
     CK(cudaSetDevice(c->device));
-    c->launches += agb_launch_int_second(c->d, c->I, c->int_time, c->st);             // :296-341
+    if (c->d.n > 0) c->launches += agb_launch_int_second(c->d, c->I, c->int_time, c->st);             // :296-341
     CK(cudaGetLastError());
     return AGB_OK;
 }

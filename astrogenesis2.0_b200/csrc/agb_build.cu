@@ -10,7 +10,8 @@
 //                              descent (strict '>' against cell centres produced by c +- r/2), packed
 //                              3 bit/level into a 126-bit key; particles outside the root cube are
 //                              flagged and sort to the end (they stay force targets, Node.cpp:606-612)
-//   k_sort_*                   LSD radix sort, 8-bit digits, 16 passes over (key_hi, key_lo, index)
+//   k_sort_*                   LSD radix sort, 8-bit digits, 8 passes over (key_hi, index); key_lo (levels 21..41) is
+//                              computed lazily and only orders runs of equal key_hi (k_fix_runs)
 //   k_gather                   permute particle data into tree order (unified source table)
 //   k_lcp + scan               shared-levels of neighbouring keys -> one internal node per (first
 //                              particle, depth) pair; ids by prefix sum (children get larger ids)
@@ -80,7 +81,7 @@ __global__ void k_extent_finish(AgbScalars* s, int nblocks, int64_t n)
     s->mean = mean; s->stdev = sd;
     s->limit = __dadd_rn(mean, __dmul_rn(10.0, sd));     // Tree.cpp:89,105
     s->Rbits = 0ull;
-    s->n_long_runs = 0; s->any_gas = 0; s->n_outliers = 0; s->dup_keys = 0; s->edge_dropped = 0; s->max_depth = 0; s->n_nodes = 0;
+    s->n_long_runs = 0; s->any_gas = 0; s->n_outliers = 0; s->dup_keys = 0; s->edge_dropped = 0; s->max_depth = 0; s->n_nodes = 0; s->node_overflow = 0;
 }
 
 __global__ void __launch_bounds__(TPB) k_extent_max(const double4* __restrict__ rec, int64_t n, AgbScalars* s)
@@ -620,6 +621,10 @@ __global__ void __launch_bounds__(TPB) k_scan_apply(const int32_t* __restrict__ 
 __global__ void __launch_bounds__(TPB) k_init_nodes(AgbDev d, const AgbScalars* __restrict__ s)
 {
     int64_t k = (int64_t)blockIdx.x * TPB + threadIdx.x;
+    if (s->n_nodes > d.ncap) {                          // more (first particle, depth) pairs than node slots: nothing is written,
+        if (k == 0) const_cast<AgbScalars*>(s)->node_overflow = 1;   // every later kernel of the step returns at once, the host grows the arrays
+        return;
+    }
     if (k >= s->n_nodes) return;
     int4 e = make_int4(-1, -1, -1, -1);
     reinterpret_cast<int4*>(d.child)[2 * k] = e;
@@ -667,7 +672,7 @@ __global__ void __launch_bounds__(TPB) k_links(AgbDev d, const uint64_t* __restr
 {
     int64_t i = (int64_t)blockIdx.x * TPB + threadIdx.x;
     const int64_t nt = s->n_in_tree;
-    if (i >= nt) return;
+    if (i >= nt || s->n_nodes > d.ncap) return;
     if (nt < 2) { d.leafdepth[i] = 0; return; }              // a single particle: the root itself is the leaf (Node.cpp:409-418)
     KeyView K{khi, klo};
     const uint64_t h = khi[i], l = klo[i];
@@ -759,7 +764,7 @@ __device__ __forceinline__ void node_moments(const AgbDev& d, int k, int N, bool
 __global__ void __launch_bounds__(TPB) k_upward(AgbDev d, const AgbScalars* __restrict__ s)
 {
     int k = blockIdx.x * TPB + threadIdx.x;
-    if (k >= s->n_nodes) return;
+    if (k >= s->n_nodes || s->n_nodes > d.ncap) return;
     const int N = (int)d.n;
     ChildLinks L = load_links(d.child, k);
     if (count_node_children(L, N) != 0) return;               // only nodes whose children are all leaves start a climb
@@ -783,7 +788,7 @@ __global__ void __launch_bounds__(TPB) k_upward(AgbDev d, const AgbScalars* __re
 // including those outside the cube that are never inserted (Node.cpp:477-499 precede the octant test).
 __global__ void __launch_bounds__(TPB) k_root_fix(AgbDev d, const AgbScalars* __restrict__ s)
 {
-    if (s->n_nodes < 1) return;
+    if (s->n_nodes < 1 || s->n_nodes > d.ncap) return;
     if (d.n < (int64_t)d.cores * 100) return;                  // one-by-one insertion rejects them at the root (Node.cpp:606-612)
     __shared__ double sh[8][TPB / 32];
     double v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -811,7 +816,7 @@ __global__ void __launch_bounds__(TPB) k_root_fix(AgbDev d, const AgbScalars* __
 __global__ void __launch_bounds__(TPB) k_finalize(AgbDev d, const AgbScalars* __restrict__ s)
 {
     int k = blockIdx.x * TPB + threadIdx.x;
-    if (k >= s->n_nodes) return;
+    if (k >= s->n_nodes || s->n_nodes > d.ncap) return;
     const int64_t N = d.n;
     double4 pm = d.mom_pm[k], gv = s->any_gas ? d.mom_gv[k] : make_double4(0, 0, 0, 0);
     double4 com = make_double4(0, 0, 0, pm.w), mv = make_double4(0, 0, 0, gv.w);
@@ -923,21 +928,24 @@ int agb_launch_sort(AgbDev& d, AgbScalars* s, cudaStream_t st)
     return launches + 2;
 }
 
-int agb_launch_links(AgbDev& d, AgbScalars* s, cudaStream_t st)
+int agb_launch_links(AgbDev& d, AgbScalars* s, cudaStream_t st, cudaEvent_t* ev)
 {
     const int nb = nblk(d.n, TPB);
     const uint64_t *khi = d.khi[d.cur], *klo = d.klo[1];
     k_gather<<<nb, TPB, 0, st>>>(d, d.perm[d.cur], s);
+    if (ev) cudaEventRecord(ev[0], st);
     k_lcp<<<nb, TPB, 0, st>>>(khi, klo, d.n, d.lcp, d.nodecnt, s);
     const int sb = nblk(d.n, SCAN_TILE);
     k_scan_reduce<<<sb, TPB, 0, st>>>(d.nodecnt, d.n, d.scanblk, nullptr);
     k_scan_blocks<<<1, TPB, 0, st>>>(d.scanblk, sb, &s->n_nodes, nullptr, d.n);
     k_scan_apply<<<sb, TPB, 0, st>>>(d.nodecnt, d.n, d.scanblk, d.nodebase, nullptr);
-    k_init_nodes<<<nb, TPB, 0, st>>>(d, s);
+    const int nnb = nblk(d.ncap, TPB);                        // node kernels: one thread per node slot
+    k_init_nodes<<<nnb, TPB, 0, st>>>(d, s);
     k_links<<<nb, TPB, 0, st>>>(d, khi, klo, s);
-    k_upward<<<nb, TPB, 0, st>>>(d, s);
+    if (ev) cudaEventRecord(ev[1], st);
+    k_upward<<<nnb, TPB, 0, st>>>(d, s);
     k_root_fix<<<1, TPB, 0, st>>>(d, s);
-    k_finalize<<<nb, TPB, 0, st>>>(d, s);
+    k_finalize<<<nnb, TPB, 0, st>>>(d, s);
     return 10;
 }
 

@@ -34,7 +34,7 @@ __device__ __forceinline__ double radius_at(double R, int depth) { return scalbn
 __global__ void __launch_bounds__(TPB) k_visual(AgbDev d, const uint32_t* __restrict__ perm, const AgbScalars* __restrict__ s, double rt)
 {
     int64_t i = (int64_t)blockIdx.x * TPB + threadIdx.x;
-    if (i >= d.n) return;
+    if (i >= d.n || s->node_overflow) return;
     const uint32_t p = perm[i];
     double out = 0.0;                                          // Tree.cpp:156-161 zeroes every particle first
     if (i < s->n_in_tree) {
@@ -122,7 +122,7 @@ template <int PASS>
 __global__ void __launch_bounds__(TPB) k_gas_mark(AgbDev d, AgbScalars* s, double M, GasFold F)
 {
     int64_t i = (int64_t)blockIdx.x * TPB + threadIdx.x;
-    if (i >= s->n_in_tree) return;
+    if (i >= s->n_in_tree || s->node_overflow) return;
     if (d.s_type[i] != 2) return;
     if (PASS == 1 && !F.pending[i]) return;
     const int N = (int)d.n;
@@ -169,6 +169,7 @@ __global__ void __launch_bounds__(TPB) k_gas_fold(AgbDev d, AgbScalars* s, GasFo
     extern __shared__ __align__(16) unsigned char fold_smem[];
     double* sm_m = reinterpret_cast<double*>(fold_smem);
     uint32_t* sm_i = reinterpret_cast<uint32_t*>(sm_m + FOLD_MAX);
+    if (s->node_overflow) return;
     for (int q = blockIdx.x; q < s->n_fold; q += gridDim.x) {
         const int k = F.foldlist[q];
         int g0, g1;
@@ -210,7 +211,7 @@ __global__ void __launch_bounds__(TPB) k_gas_group(AgbDev d, AgbScalars* s)
 {
     int64_t i = (int64_t)blockIdx.x * TPB + threadIdx.x;
     bool orphan = false;
-    if (i < s->n_in_tree && d.s_type[i] == 2) {
+    if (i < s->n_in_tree && !s->node_overflow && d.s_type[i] == 2) {
         int grp = d.leafmark[i] ? (int)i : -1;
         for (int k = d.leafparent[i]; k >= 0; k = d.nparent[k]) if (d.nmark[k]) grp = (int)d.n + k;
         d.group[i] = grp;
@@ -234,7 +235,7 @@ __global__ void __launch_bounds__(TPB) k_gas_group(AgbDev d, AgbScalars* s)
 __global__ void __launch_bounds__(TPB) k_gas_collect(AgbDev d, AgbScalars* s)
 {
     int k = blockIdx.x * TPB + threadIdx.x;
-    if (k >= s->n_nodes || !d.nmark[k]) return;
+    if (k >= s->n_nodes || s->node_overflow || !d.nmark[k]) return;
     for (int a = d.nparent[k]; a >= 0; a = d.nparent[a]) if (d.nmark[a]) return;
     d.grouplist[atomicAdd(&s->n_gas_groups, 1)] = k;
 }
@@ -253,6 +254,7 @@ __global__ void __launch_bounds__(TPB) k_gas_sum(AgbDev d, const AgbScalars* __r
 {
     const int lane = threadIdx.x & 31;
     const double R = __longlong_as_double((long long)s->Rbits);
+    if (s->node_overflow) return;
     for (int g = (blockIdx.x * TPB + threadIdx.x) >> 5; g < s->n_gas_groups; g += (gridDim.x * TPB) >> 5) {
     const int k = d.grouplist[g];
     const double h = __dmul_rn(radius_at(R, d.ndepth[k]), 2.0);          // Node.cpp:765
@@ -315,7 +317,7 @@ int agb_launch_gas_density(AgbDev& d, AgbScalars* s, double massInH, cudaStream_
     // nodebase (int32/particle), and the caller-order copy of key_lo (8 B/particle)
     GasFold F{d.gasrank, g_orig, g_pm, g_tree, reinterpret_cast<uint8_t*>(d.arrived), reinterpret_cast<double*>(d.klo[0]), d.nodebase,
               reinterpret_cast<uint8_t*>(d.lcp)};
-    cudaMemsetAsync(d.arrived, 0, (size_t)d.n * sizeof(int32_t), st);
+    cudaMemsetAsync(d.arrived, 0, (size_t)d.ncap * sizeof(int32_t), st);
     cudaMemsetAsync(d.lcp, 0, (size_t)d.n, st);
     k_gas_mark<0><<<nb, TPB, 0, st>>>(d, s, massInH, F);
     const int fold_smem = FOLD_MAX * 12;
@@ -323,7 +325,7 @@ int agb_launch_gas_density(AgbDev& d, AgbScalars* s, double massInH, cudaStream_
     k_gas_fold<<<296, TPB, fold_smem, st>>>(d, s, F);
     k_gas_mark<1><<<nb, TPB, 0, st>>>(d, s, massInH, F);
     k_gas_group<<<nb, TPB, 0, st>>>(d, s);
-    k_gas_collect<<<nb, TPB, 0, st>>>(d, s);
+    k_gas_collect<<<nblk(d.ncap, TPB), TPB, 0, st>>>(d, s);
     k_gas_sum<<<std::min(nblk(d.n, TPB / 32), 148 * 16), TPB, 0, st>>>(d, s, F);   // one warp per group, grid-stride
     k_gas_scatter<<<nb, TPB, 0, st>>>(d, s, F);
     return 10 + launches;

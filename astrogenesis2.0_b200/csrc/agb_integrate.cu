@@ -12,6 +12,25 @@ namespace {
 constexpr int TPB = 256;
 constexpr double kGAMMA = 5.0 / 3.0, kKB = 1.38064852e-23, kPRTN = 1.6726219e-27;
 
+// floor(log2(t)) exactly as the reference's `std::floor(std::log2(t))` (Simulation.cpp:199-202) evaluates it: libm's log2 is
+// correctly rounded here, so for t a few ulps below a power of two 2^k the value k - eps/ln2 rounds UP to k and the
+// reference picks 2^k, not 2^(k-1).  frexp gives the mathematical floor; the correction applies when the distance of
+// log2(t) to k is below half an ulp of k (ulp of the binade log2(t) lies in).
+__device__ __forceinline__ int floor_log2_like_libm(double t)
+{
+    int ex;
+    const double f = frexp(t, &ex);                                 // t = f 2^ex, f in [0.5, 1): floor(log2 t) = ex - 1
+    if (ex == 0) return -1;                                         // t just below 1: log2(t) is a tiny negative number, floor = -1
+    const double eps = __dadd_rn(1.0, -f);                          // exact (Sterbenz); relative gap to the next power of two
+    const int ak = ex < 0 ? -ex : ex;
+    int lg = 31 - __clz(ak);                                        // binade of |k|
+    if (ex > 0 && (ak & (ak - 1)) == 0) lg -= 1;                    // k - delta lies in the binade below a positive power of two
+    const double half_ulp = ldexp(1.0, lg - 53);
+    // log2(1 - eps) = -(eps + eps^2/2 + ..) / ln 2
+    const double dist = eps * (1.0 + 0.5 * eps) * 1.4426950408889634;
+    return dist < half_ulp ? ex : ex - 1;
+}
+
 __device__ __forceinline__ void assign_timestep(const AgbDev& d, const AgbInt& I, int64_t i, double gt)
 {
     const double ax = d.ax[i], ay = d.ay[i], az = d.az[i];
@@ -20,9 +39,7 @@ __device__ __forceinline__ void assign_timestep(const AgbDev& d, const AgbInt& I
     if (a > 0.0) {
         double t = __dmul_rn(I.eta, __dsqrt_rn(__ddiv_rn(I.e0, a)));
         t = fmin(fmax(t, I.min_ts), I.max_ts);                      // std::clamp
-        int ex;
-        frexp(t, &ex);                                              // floor(log2(t)) == ex - 1
-        ts = fmax(ldexp(1.0, ex - 1), I.min_ts);
+        ts = fmax(ldexp(1.0, floor_log2_like_libm(t)), I.min_ts);
     }
     I.timestep[i] = ts;
     I.next[i] = __dadd_rn(gt, ts);

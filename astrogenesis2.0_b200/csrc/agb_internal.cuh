@@ -22,6 +22,8 @@
 
 struct AgbDev {
     int64_t n = 0, cap = 0;
+    int64_t ncap = 0;                  // capacity of the node arrays: one node per (first particle, depth) pair, so a tight pair
+                                       // alone costs up to 41 nodes; grown on demand when a build reports more (agb_api.cu)
     int cores = 1;
     // caller-order inputs (owned copies unless `bound`)
     const double *x = nullptr, *y = nullptr, *z = nullptr, *vx = nullptr, *vy = nullptr, *vz = nullptr;
@@ -77,6 +79,7 @@ struct AgbScalars {
     int32_t bintotal[256];
     int32_t vis_level;
     int32_t walk_overflow, any_gas;
+    int32_t node_overflow;             // the build needed more than ncap nodes: nothing past the capacity was written, the host grows and rebuilds
     int32_t n_gas_total, tie_exact, tie_unresolved, n_fold, n_long_runs, n_scan_tmp;
     unsigned long long st_rounds, st_popped, st_mixed, st_open, st_drain;   // walk statistics (tuning)
     unsigned long long st_cls[10];     // counter mode: list entries / acceptor bits by lane span (any, one half, one quarter), far-list entries, entries per evaluation class
@@ -100,14 +103,14 @@ int agb_launch_int_second(AgbDev& d, const AgbInt& I, double gt, cudaStream_t st
 int agb_launch_extent(const AgbDev& d, AgbScalars* s, cudaStream_t st);
 int agb_launch_keygen(AgbDev& d, AgbScalars* s, cudaStream_t st);
 int agb_launch_sort(AgbDev& d, AgbScalars* s, cudaStream_t st);
-int agb_launch_links(AgbDev& d, AgbScalars* s, cudaStream_t st);
+int agb_launch_links(AgbDev& d, AgbScalars* s, cudaStream_t st, cudaEvent_t* ev = nullptr);   // ev[0] after the gather, ev[1] after the links, before the upward pass
 int agb_launch_visual(AgbDev& d, AgbScalars* s, double radius, cudaStream_t st);
 int agb_launch_gas_density(AgbDev& d, AgbScalars* s, double massInH, cudaStream_t st);
 // compact (index, acc, dUdt) of the active targets [a0, a1) in tree order (agb_get_slice_results)
 void agb_slice_bounds(int64_t n_active, int part, int nparts, int64_t* a0, int64_t* a1);
-int agb_launch_slice_results(const AgbDev& d, int64_t a0, int64_t a1, bool ident, uint32_t* index, double* ax, double* ay, double* az, double* dUdt, cudaStream_t st);
+int agb_launch_slice_results(const AgbDev& d, int64_t a0, int64_t a1, bool ident, uint32_t* index, double* const dst[9], cudaStream_t st);   // dst: ax ay az dUdt h rho P T vis
 int agb_launch_walk(AgbDev& d, AgbScalars* s, double globalTime, double e0, double theta, int part, int nparts,
-                    bool counters, bool any_gas, bool mixed, int sm_count, cudaStream_t st, cudaEvent_t ev0, cudaEvent_t ev1);
+                    bool counters, bool any_gas, bool mixed, int sm_count, cudaStream_t st, cudaEvent_t* ev);   // ev[0..3]: before k_far, k_walk, k_sph, after
 int agb_launch_dump_tree(AgbDev& d, AgbScalars* s, int32_t* leafdepth, uint64_t* khi, uint64_t* klo, cudaStream_t st);
 int agb_launch_scan_i32(const int32_t* in, int32_t* out, int64_t n, int32_t* blk, int32_t* total_out, cudaStream_t st, const int32_t* skip_if_n = nullptr);
 int agb_launch_microbench(int kind, int sm_count, cudaStream_t st, double* result);

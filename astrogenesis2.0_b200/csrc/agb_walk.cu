@@ -174,6 +174,7 @@ __global__ void __launch_bounds__(128) k_far(const WalkParams P)
     const double inf = __longlong_as_double(0x7ff0000000000000ll);
     const Slice sl = target_slice(P);
     const int nsg = (int)((sl.a1 - sl.a0 + 32 * SG_GROUPS - 1) / (32 * SG_GROUPS));
+    if (P.s->node_overflow) return;                                 // no usable tree this step (the host grows the node arrays and rebuilds)
     for (int sgi = blockIdx.x * 4 + warp; sgi < nsg; sgi += gridDim.x * 4) {
         const int64_t tb = sl.a0 + (int64_t)sgi * (32 * SG_GROUPS);
         int32_t* const fl = P.far_list + (size_t)sgi * FAR_LCAP;
@@ -304,6 +305,7 @@ __global__ void __launch_bounds__(WalkCfg<SPH>::TPB, WALK_CTAS) k_walk(const Wal
         return make_int2(-1, 0);
     };
 
+    if (P.s->node_overflow) return;
     for (;;) {
         unsigned g = 0;
         if (lane == 0) g = atomicAdd(&P.s->walk_next_group, 1u);
@@ -800,7 +802,7 @@ __global__ void __launch_bounds__(256, 3) k_sph(const WalkParams P)
     const Slice sl = target_slice(P);
     const unsigned ngroups = (unsigned)((sl.a1 - sl.a0 + 31) / 32);
     unsigned long long tot_sph = 0, tot_exact = 0;
-    if (P.s->walk_overflow) return;                                             // incomplete records: agb_forces grows the pool and walks again
+    if (P.s->walk_overflow || P.s->node_overflow) return;                       // incomplete records: agb_forces grows the pool and walks again
     for (unsigned g = blockIdx.x * 8 + warp; g < ngroups; g += gridDim.x * 8) {
         const int head = P.rec_head[g];
         if (head < 0) continue;
@@ -1024,9 +1026,9 @@ __global__ void k_unpermute_i32(const uint32_t* __restrict__ perm, int64_t n, co
     oa[p] = a[i]; ob[p] = b[i]; oc[p] = c[i]; od[p] = d_[i];
 }
 
+struct SliceCols { const double* src[9]; double* dst[9]; };     // ax ay az dUdt h rho P T visualDensity (caller order -> compact)
 __global__ void k_slice_results(const uint32_t* __restrict__ perm, const int32_t* __restrict__ act_list, int64_t a0, int64_t a1, bool ident,
-                                const double* __restrict__ sax, const double* __restrict__ say, const double* __restrict__ saz, const double* __restrict__ sdu,
-                                uint32_t* __restrict__ index, double* __restrict__ ax, double* __restrict__ ay, double* __restrict__ az, double* __restrict__ dUdt)
+                                const SliceCols C, uint32_t* __restrict__ index)
 {
     const int64_t i = a0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= a1) return;
@@ -1034,10 +1036,8 @@ __global__ void k_slice_results(const uint32_t* __restrict__ perm, const int32_t
     const uint32_t p = perm[t];
     const int64_t k = i - a0;
     if (index) index[k] = p;
-    if (ax) ax[k] = sax[p];
-    if (ay) ay[k] = say[p];
-    if (az) az[k] = saz[p];
-    if (dUdt) dUdt[k] = sdu[p];
+#pragma unroll
+    for (int c = 0; c < 9; c++) if (C.dst[c]) C.dst[c][k] = C.src[c][p];
 }
 
 template <bool COUNT, bool SPH, bool MIXED>
@@ -1081,7 +1081,7 @@ int agb_walk_warps_per_block() { return 8; }
 void agb_far_capacity(int* lcap, int* fcap, int* targets) { *lcap = FAR_LCAP; *fcap = FAR_FCAP; *targets = 32 * SG_GROUPS; }
 
 int agb_launch_walk(AgbDev& d, AgbScalars* s, double globalTime, double e0, double theta, int part, int nparts,
-                    bool counters, bool any_gas, bool mixed, int sm_count, cudaStream_t st, cudaEvent_t ev0, cudaEvent_t ev1)
+                    bool counters, bool any_gas, bool mixed, int sm_count, cudaStream_t st, cudaEvent_t* ev)
 {
     WalkParams P;
     P.src_pm = d.src_pm; P.src_gv = d.src_gv; P.src_flag = d.src_flag; P.child = d.child; P.ndepth = d.ndepth;
@@ -1111,12 +1111,14 @@ int agb_launch_walk(AgbDev& d, AgbScalars* s, double globalTime, double e0, doub
             cudaMemsetAsync(d.c_accl, 0, (size_t)d.n * 4, st); cudaMemsetAsync(d.c_sph, 0, (size_t)d.n * 4, st);
         }
         const int64_t max_groups = (d.n / nparts + 32 * SG_GROUPS + 31) / 32;
-        if (ev0) cudaEventRecord(ev0, st);
+        if (ev) cudaEventRecord(ev[0], st);
         // far-field prepass, one warp per super-group of 256 targets
         k_far<<<(int)std::min<int64_t>((max_groups / SG_GROUPS + 4) / 4, (int64_t)sm_count * 8), 128, 0, st>>>(P); launches++;
+        if (ev) cudaEventRecord(ev[1], st);
         if (counters) { if (any_gas) launch_walk2<true, true>(P, max_groups, sm_count, d.spill_warps, mixed, st); else launch_walk2<true, false>(P, max_groups, sm_count, d.spill_warps, mixed, st); }
         else { if (any_gas) launch_walk2<false, true>(P, max_groups, sm_count, d.spill_warps, mixed, st); else launch_walk2<false, false>(P, max_groups, sm_count, d.spill_warps, mixed, st); }
         launches++;
+        if (ev) cudaEventRecord(ev[2], st);
         if (any_gas && mixed) {
             // the SPH pairs of the candidates the walk recorded (after it: acc += SPH part, dU/dt += ...)
             const int smem = (int)sizeof(SphWarp) * 8;
@@ -1125,7 +1127,7 @@ int agb_launch_walk(AgbDev& d, AgbScalars* s, double globalTime, double e0, doub
             else { cudaFuncSetAttribute(k_sph<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); k_sph<false><<<blocks, 256, smem, st>>>(P); }
             launches++;
         }
-        if (ev1) cudaEventRecord(ev1, st);
+        if (ev) cudaEventRecord(ev[3], st);
     }
     return launches;
 }
@@ -1138,10 +1140,13 @@ void agb_slice_bounds(int64_t n_active, int part, int nparts, int64_t* a0, int64
     *a1 = std::min(n_active, nsg * (part + 1) / nparts * g);
 }
 
-int agb_launch_slice_results(const AgbDev& d, int64_t a0, int64_t a1, bool ident, uint32_t* index, double* ax, double* ay, double* az, double* dUdt, cudaStream_t st)
+int agb_launch_slice_results(const AgbDev& d, int64_t a0, int64_t a1, bool ident, uint32_t* index, double* const dst[9], cudaStream_t st)
 {
     if (a1 <= a0) return 0;
-    k_slice_results<<<(int)((a1 - a0 + 255) / 256), 256, 0, st>>>(d.perm[d.cur], d.act_list, a0, a1, ident, d.ax, d.ay, d.az, d.dUdt, index, ax, ay, az, dUdt);
+    SliceCols C;
+    const double* src[9] = {d.ax, d.ay, d.az, d.dUdt, d.h, d.rho, d.P, d.T, d.vis};
+    for (int c = 0; c < 9; c++) { C.src[c] = src[c]; C.dst[c] = dst[c]; }
+    k_slice_results<<<(int)((a1 - a0 + 255) / 256), 256, 0, st>>>(d.perm[d.cur], d.act_list, a0, a1, ident, C, index);
     return 1;
 }
 

@@ -127,8 +127,10 @@ class Context:
         res = {"index": (out["index"][:cnt] if out else np.empty(cnt, np.uint32))}
         for k in names:
             res[k] = out[k][:cnt] if out else np.empty(cnt)
-        cols = [capi.dptr(res.get(k)) for k in ("ax", "ay", "az", "dUdt")]
-        capi.check(self.h, self.lib.agb_get_slice_results(self.h, int(part), int(nparts), capi.dptr(res["index"], C.c_uint32), *cols, capi.AGB_MEM_HOST))
+        r = capi.Results()
+        for k in _OUT:                                     # any of the nine result columns (agb_get_slice_results_all)
+            setattr(r, k, capi.dptr(res.get(k)))
+        capi.check(self.h, self.lib.agb_get_slice_results_all(self.h, int(part), int(nparts), capi.dptr(res["index"], C.c_uint32), C.byref(r), capi.AGB_MEM_HOST))
         return res
 
     def bind_results(self, out):
@@ -190,6 +192,11 @@ class Context:
         a = (C.c_double * 5)()
         capi.check(self.h, self.lib.agb_get_phase_ms(self.h, a))
         return dict(zip(("build", "visual", "gas_density", "walk_kernel", "forces"), list(a)))
+
+    def kernel_ms(self):
+        a = (C.c_double * 8)()
+        capi.check(self.h, self.lib.agb_get_kernel_ms(self.h, a))
+        return dict(zip(("k_far", "k_walk", "k_sph", "build_keys", "build_sort", "build_gather", "build_links", "build_upward"), list(a)))
 
     def stream(self):
         s = C.c_void_p()

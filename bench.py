@@ -5,7 +5,8 @@
 
 A step = one pass of the path over one synthetic particle set: build_tree -> visual_density ->
 gas_density -> forces (the reference's Simulation::run step, Simulation.cpp:276-285), all particles
-active.  `value` = particle-updates/s with the particles already resident in HBM; `e2e` = the same
+active.  Default workload at every N: BASELINE.json's north-star configuration C3, the gas-rich disk
+galaxy with 16M particles (gravity + SPH); `--workload plummer1m` is C1 (gravity only).  `value` = particle-updates/s with the particles already resident in HBM; `e2e` = the same
 through the reference-facing Tree API with pinned HOST arrays (H2D of the particles and D2H of the
 results inside the timed region).  N > 1 (torchrun): every rank owns 1/N of the particles, the
 positions are all-gathered over NCCL each step, every GPU builds the same tree and walks its own
@@ -41,6 +42,18 @@ WORKLOADS = {
     "disk400k": ("disk", 400_000, 1e18, 64, "small disk (debug)"),
 }
 THETA = 0.5
+
+
+DEFAULT_WORKLOAD = "gas16m"
+
+
+def workload_config(pkg, name):
+    """The `config` object of the JSON line: identical (keys and values) in the GPU arm and in --impl reference."""
+    gen, n, e0, nb, desc = WORKLOADS[name]
+    # massInH = nb gas-particle masses of the FULL-size set (equal-mass generators: M_tot / n per particle)
+    mtot = {"plummer": 1e11, "disk": 1e12, "gasdisk": 1e12, "merger": 2e12}[gen] * pkg.ics.MSUN
+    mh = float(nb * (mtot / n)) if nb else 1e40
+    return {"workload": name, "description": desc, "n_particles": n, "theta": THETA, "e0": e0, "massInH": mh, "all_active": True}
 
 
 def make_particles(pkg, name, n_override=None):
@@ -144,25 +157,34 @@ def sample_size_for_cpu(n_full, steps, budget_s=25.0):
 
 
 def run_reference_arm(args, pkg):
+    """The reference's own CPU implementation of the path (unmodified sources compiled in place: oracle/_ref/ag_ref_omp, all host
+    threads) on the GPU arm's config.  Each step is a bounded sample of the workload: the same generator at a particle count
+    sized so that the whole --steps/--warmup run ends within a few minutes.  The reference's throughput FALLS with the
+    particle count (deeper tree, more interactions per target), so the smaller sample favours the CPU arm."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    name = args.workload or "plummer1m"
-    n_full = WORKLOADS[name][1]
+    name = args.workload or DEFAULT_WORKLOAD
+    cfg = workload_config(pkg, name)
+    n_full = cfg["n_particles"]
     total = args.steps + args.warmup
     n = sample_size_for_cpu(n_full, total, budget_s=150.0)
-    p, e0, mh, desc = make_particles(pkg, name, n)
+    p, e0, _, desc = make_particles(pkg, name, n)
+    nb = WORKLOADS[name][3]
+    mh = cfg["massInH"] * (n_full / n) if nb else cfg["massInH"]           # the same number of gas-particle masses in the sample
     with tempfile.TemporaryDirectory() as d:
         secs, kind, cores, rows = cpu_reference_run(p, e0, mh, total, d)
     timed = secs[args.warmup:]
     t = float(np.mean(timed))
     value = n / t
+    sample = ("%d of %d particles (same generator and seed at the smaller count; the reference's per-particle cost grows with N, so this favours the CPU), "
+              "%d timed steps, phases build+visual+gas_density+forces" % (n, n_full, len(timed))) if n < n_full else \
+             ("all %d particles, %d timed steps, phases build+visual+gas_density+forces" % (n_full, len(timed)))
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "particles/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": name, "description": desc, "n_particles": n_full, "theta": THETA, "e0": e0},
-        "cpu_baseline": {"value": value, "unit": "particles/s", "cores": cores, "kind": kind,
-                         "sample": "%d of %d particles of %s, %d timed steps, phases build+visual+gas_density+forces" % (n, n_full, name, len(timed))},
+        "config": cfg,
+        "cpu_baseline": {"value": value, "unit": "particles/s", "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": "particles/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "phases_s": rows[-1],
     }
@@ -170,6 +192,10 @@ def run_reference_arm(args, pkg):
 
 
 # ------------------------------------------------------------------ GPU arm
+RESULT_COLS_GRAVITY = ("ax", "ay", "az", "visualDensity")
+RESULT_COLS_GAS = ("dUdt", "h", "rho", "P", "T")
+
+
 def run_gpu_arm(args, pkg):
     import torch
     import torch.distributed as dist
@@ -182,12 +208,15 @@ def run_gpu_arm(args, pkg):
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    name = args.workload or "plummer1m"
-    p, e0, mh, desc = make_particles(pkg, name)
+    name = args.workload or DEFAULT_WORKLOAD
+    cfg = workload_config(pkg, name)
+    p, e0, _, desc = make_particles(pkg, name)
+    mh = cfg["massInH"]
     n = len(p["x"])
     any_gas = bool((p["type"] == 2).any())
     ctx = pkg.Context(local, 8)
     stream = torch.cuda.ExternalStream(ctx.stream(), device=dev)
+    out_cols = RESULT_COLS_GRAVITY + (RESULT_COLS_GAS if any_gas else ())      # what a step hands back, for any number of GPUs
 
     f8 = ["x", "y", "z", "vx", "vy", "vz", "mass", "U", "next_time", "mu"] if any_gas else ["x", "y", "z", "mass"]
     # rank-local shard of the particle arrays (what a distributed driver would own and integrate)
@@ -241,12 +270,31 @@ def run_gpu_arm(args, pkg):
 
     gather()
     torch.cuda.synchronize()                                                   # the uploads above ran on torch's stream, the path runs on its own
+    multi_gpu_check = None
     if world > 1:                                                              # the exchange really delivered every rank's shard (checked once, untimed)
         for k in full:
             if not torch.equal(full[k], torch.from_numpy(np.ascontiguousarray(p[k])).to(dev)):
                 raise SystemExit("all-gather of %s does not reproduce the particle set" % k)
     ctx.set_particles_device({k: full[k].data_ptr() for k in full}, n)
     vis_radius = ctx.build_tree() / 100000                                     # Simulation.cpp:123-126
+    if world > 1:
+        # Untimed, once: the compact results of this rank's slice of an N-way sharded walk equal, bit for bit, the same
+        # particles' results of a whole (1-GPU style) walk of the same tree.
+        ctx.visual_density(vis_radius); ctx.gas_density(mh)
+        ctx.forces(0.0, e0, THETA, rank, world)
+        mine = ctx.slice_results(rank, world, names=out_cols)
+        mine = {k: v.copy() for k, v in mine.items()}
+        ctx.set_particles_device({k: full[k].data_ptr() for k in full}, n)     # fresh carried state (dU/dt accumulates across calls)
+        ctx.build_tree(); ctx.visual_density(vis_radius); ctx.gas_density(mh)
+        ctx.forces(0.0, e0, THETA, 0, 1)
+        whole = ctx.results(names=out_cols)
+        same = all(np.array_equal(whole[k][mine["index"]], mine[k]) for k in out_cols)
+        flag = torch.tensor([1.0 if same else 0.0, float(len(mine["index"]))], dtype=torch.float64, device=dev)
+        mn = flag.clone(); dist.all_reduce(mn, op=dist.ReduceOp.MIN)
+        sm_ = flag.clone(); dist.all_reduce(sm_, op=dist.ReduceOp.SUM)
+        if float(mn[0]) != 1.0 or int(sm_[1]) != n:
+            raise SystemExit("sharded walk differs from the whole walk (or the slices do not cover every particle once)")
+        multi_gpu_check = "slices of the %d-way sharded walk cover all %d particles once and equal the whole walk bit for bit (%s)" % (world, n, ", ".join(out_cols))
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -257,7 +305,8 @@ def run_gpu_arm(args, pkg):
     barrier()
     launches0 = ctx.launch_count()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    walk_ms, build_ms, inter = [], [], 0
+    kms = {}
+    inter = sph_pairs = 0
     barrier()
     t_wall0 = time.perf_counter()
     for i in range(args.steps):
@@ -267,23 +316,52 @@ def run_gpu_arm(args, pkg):
         step()
         ev[i][1].record(stream)
         ev[i][1].synchronize()
-        ph = ctx.phase_ms()
-        walk_ms.append(ph["walk_kernel"]); build_ms.append(ph["build"])
-        inter = ctx.counters()["interactions"]
+        for k, v in list(ctx.phase_ms().items()) + list(ctx.kernel_ms().items()):
+            kms.setdefault(k, []).append(v)
+        cnt = ctx.counters()
+        inter, sph_pairs = cnt["interactions"], cnt["sph_interactions"]
     barrier()
     t_wall = time.perf_counter() - t_wall0
     step_ms = [a.elapsed_time(b) for a, b in ev]
     launches = ctx.launch_count() - launches0
     clocks = sampler.stop(t_wall0, t_wall0 + t_wall) if rank == 0 else None
-    tot = torch.tensor([sum(step_ms), float(inter), sum(walk_ms)], dtype=torch.float64, device=dev)
+    kavg = {k: float(np.mean(v)) for k, v in kms.items()}
+    tot = torch.tensor([sum(step_ms), float(inter), kavg["k_walk"], float(sph_pairs), kavg["k_sph"]], dtype=torch.float64, device=dev)
     if world > 1:
         mx = tot.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
         sm = tot.clone(); dist.all_reduce(sm, op=dist.ReduceOp.SUM)
-        total_ms, walk_total_ms, inter_all = float(mx[0]), float(mx[2]), float(sm[1])
+        total_ms, walk_ms_avg, sph_ms_avg, inter_all, sph_all = float(mx[0]), float(mx[2]), float(mx[4]), float(sm[1]), float(sm[3])
     else:
-        total_ms, walk_total_ms, inter_all = float(tot[0]), float(tot[2]), float(inter)
+        total_ms, walk_ms_avg, sph_ms_avg, inter_all, sph_all = float(tot[0]), float(tot[2]), float(tot[4]), float(inter), float(sph_pairs)
     ms_per_step = total_ms / args.steps
     value = n / (ms_per_step * 1e-3)
+    divergence = {k: cnt[k] for k in ("edge_dropped", "gas_ties_unresolved", "mac_exact_fallbacks", "walk_stack_spills", "n_outliers", "max_depth", "gas_orphans")}
+
+    # ---- the same steps with FP64 pair arithmetic throughout (AGB_OPT_PRECISION = 0): the reference's own arithmetic type
+    fp64 = None
+    if not args.no_fp64:
+        ctx.set_option(pkg.capi.AGB_OPT_PRECISION, 0)
+        nf = max(3, args.steps // 4)
+        for _ in range(2):
+            step()
+        barrier()
+        evf = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(nf)]
+        wf = []
+        for i in range(nf):
+            flush.fill_(i & 0xff)
+            barrier()
+            evf[i][0].record(stream if world == 1 else torch.cuda.current_stream())
+            step()
+            evf[i][1].record(stream)
+            evf[i][1].synchronize()
+            wf.append(ctx.kernel_ms()["k_walk"])
+        barrier()
+        tf = torch.tensor([sum(a.elapsed_time(b) for a, b in evf) / nf, float(np.mean(wf))], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tf, op=dist.ReduceOp.MAX)
+        fp64 = {"ms_per_step": float(tf[0]), "value": n / (float(tf[0]) * 1e-3), "unit": "particles/s", "steps": nf, "k_walk_ms": float(tf[1]),
+                "what": "same workload with FP64 pair forces and in-walk FP64 SPH (agrees with the reference to ~1e-14)"}
+        ctx.set_option(pkg.capi.AGB_OPT_PRECISION, 1)
 
     # ---- end-to-end through the Tree API with pinned host arrays (N GPUs: every rank uploads its shard, results of its slice come back)
     e2e = None
@@ -292,10 +370,7 @@ def run_gpu_arm(args, pkg):
         for k in f8 + ["type"]:
             t = torch.from_numpy(np.ascontiguousarray(p[k])).pin_memory()
             host[k] = t.numpy()
-        sim = pkg.Simulation(host, THETA, e0, mh, 0.0)
-        tree = pkg.Tree(sim, ctx)
-        outn = ("ax", "ay", "az", "visualDensity") + (("dUdt", "h", "rho", "P", "T") if any_gas else ())
-        pinned_out = {k: torch.empty(n, dtype=torch.float64).pin_memory() for k in outn}
+        pinned_out = {k: torch.empty(n, dtype=torch.float64).pin_memory() for k in out_cols}
 
         out_np = {k: v.numpy() for k, v in pinned_out.items()}
         ctx.bind_results(out_np)          # density outputs leave while the walk runs; acc / dUdt follow in results_into
@@ -314,15 +389,15 @@ def run_gpu_arm(args, pkg):
         te = (time.perf_counter() - t0) / args.steps
         h2d = sum(host[k].nbytes for k in host) + 0
         d2h = sum(v.numel() * 8 for v in pinned_out.values())
-        e2e = {"value": n / te, "unit": "particles/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "ms_per_step": te * 1e3}
+        e2e = {"value": n / te, "unit": "particles/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "ms_per_step": te * 1e3,
+               "what": "agb_set_particles (pinned host arrays) -> agb_force_path -> agb_get_results (%s) per step" % ", ".join(out_cols)}
         ctx.bind_results(None)
     else:
         # multi-GPU e2e: host shard -> device shard (H2D), gather, step, then every rank brings back the compact results of
-        # ITS slice of the targets (caller-order index + acc [+ dUdt]; agb_get_slice_results) into pinned host memory
+        # ITS slice of the targets — the same columns as the 1-GPU run plus the caller-order index (agb_get_slice_results_all)
         host = {k: torch.from_numpy(np.ascontiguousarray(p[k][lo:hi])).pin_memory() for k in f8 + ["type"]}
-        cols = ("ax", "ay", "az") + (("dUdt",) if any_gas else ())
         cap = n // world + 1024
-        out_t = {k: torch.empty(cap, dtype=torch.float64).pin_memory() for k in cols}
+        out_t = {k: torch.empty(cap, dtype=torch.float64).pin_memory() for k in out_cols}
         out_t["index"] = torch.empty(cap, dtype=torch.int32).pin_memory()
         out_np = {k: v.numpy() for k, v in out_t.items()}
         out_np["index"] = out_np["index"].view(np.uint32)
@@ -331,9 +406,9 @@ def run_gpu_arm(args, pkg):
             for k in host:
                 shard[k].copy_(host[k], non_blocking=True)
             step()
-            return ctx.slice_results(rank, world, names=cols, out=out_np)
+            return ctx.slice_results(rank, world, names=out_cols, out=out_np)
         r = e2e_step()
-        mine = len(r["index"]) * (4 + 8 * len(cols))
+        mine = len(r["index"]) * (4 + 8 * len(out_cols))
         barrier()
         t0 = time.perf_counter()
         for _ in range(args.steps):
@@ -346,7 +421,7 @@ def run_gpu_arm(args, pkg):
         te = float(te[0])
         e2e = {"value": n / te, "unit": "particles/s", "h2d_bytes_per_step": int(sum(v.numel() * v.element_size() for v in host.values()) * world),
                "d2h_bytes_per_step": int(by[1]), "ms_per_step": te * 1e3,
-               "what": "per rank: H2D of its particle shard, NCCL all-gather, build, densities, walk of its target slice, D2H of that slice's (index, acc[, dUdt])"}
+               "what": "per rank: H2D of its particle shard, NCCL all-gather, build, densities, walk of its target slice, D2H of that slice's (index, %s)" % ", ".join(out_cols)}
 
     # ---- device-resident simulation steps (integrator kernels + force path, nothing but the time crosses PCIe)
     resident = None
@@ -375,8 +450,6 @@ def run_gpu_arm(args, pkg):
             resident = {"value": n / tr, "unit": "particles/s", "ms_per_step": tr * 1e3, "steps": nres,
                         "what": "full KDK simulation step (re-binning, kick, drift, tree, densities, forces, Ueuler, Hubble, kick) with state resident in HBM"}
         except Exception as e:  # noqa: BLE001
-            # the shipped fixed dt = 1e13 s is far too long for the densest synthetic sets (64M merger): close encounters fling
-            # particles out after a few steps and the rest of the system then sits deeper than 42 octree levels (AGB_ERR_DEPTH)
             resident = {"error": str(e), "what": "device-resident KDK loop with the shipped fixed time step"}
 
     if breakdown:
@@ -384,7 +457,7 @@ def run_gpu_arm(args, pkg):
         ex = np.mean([e[0].elapsed_time(e[1]) for e, _ in bd_ev[args.warmup:args.warmup + args.steps]])
         pa = np.mean([e[1].elapsed_time(e[2]) for e, _ in bd_ev[args.warmup:args.warmup + args.steps]])
         ph = {k: float(np.mean([q[k] for _, q in bd_ev[args.warmup:args.warmup + args.steps]])) for k in bd_ev[0][1]}
-        print("rank %d breakdown: exchange %.3f ms, path call %.3f ms, phases %s" % (rank, ex, pa, json.dumps(ph)), file=sys.stderr, flush=True)
+        print("rank %d breakdown: exchange %.3f ms, path call %.3f ms, phases %s kernels %s" % (rank, ex, pa, json.dumps(ph), json.dumps(kavg)), file=sys.stderr, flush=True)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -394,21 +467,33 @@ def run_gpu_arm(args, pkg):
     # Pair forces run in FP32 (packed FFMA2/FADD2) in the default mixed mode, traversal decisions in FP64; the denominator is
     # the FP32 FMA throughput measured on this GPU by agb_microbench (MEASURED_PEAKS.json has no CUDA-core figure).
     flop_per_interaction = 21.5                      # 10 flop per node visit x 1.15 + 10 flop per accepted pair
-    walk_ms_avg = walk_total_ms / args.steps
+    flop_per_sph_pair = 55.0
     fp32_peak, fp64_peak = ctx.microbench(1), ctx.microbench(0)
     inter_rank = inter_all / world
     achieved = flop_per_interaction * inter_rank / (walk_ms_avg * 1e-3) / 1e12
-    traffic = None
+    traffic = traffic_src = None
+    kname = "k_walk<COUNT=0,SPH=%d,MIXED=1>" % (1 if any_gas else 0)
     try:
         tr = json.load(open(os.path.join(ROOT, "profiles", "walk_dram_traffic.json")))
-        traffic = tr.get(name, {}).get("bytes_per_launch")
+        ent = tr.get(name, {})
+        traffic = ent.get("bytes_per_launch")
+        traffic_src = ent.get("source")
     except Exception:  # noqa: BLE001
         pass
-    roofline = {"bound": "fp32", "kernel": "k_walk<mixed>", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved / fp32_peak if fp32_peak else None,
-                "traffic": traffic, "peak_source": "measured on this GPU: FP32 FMA chain microbenchmark (agb_microbench kind 1); FP64 chain = %.1f TFLOP/s" % fp64_peak,
+    roofline = {"bound": "fp32", "kernel": kname, "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved / fp32_peak if fp32_peak else None,
+                "traffic": traffic, "traffic_source": traffic_src,
+                "peak_source": "measured on this GPU: FP32 FMA chain microbenchmark (agb_microbench kind 1); FP64 chain = %.1f TFLOP/s" % fp64_peak,
                 "algorithmic_flop_per_interaction": flop_per_interaction, "interactions_per_launch": inter_rank,
-                "interactions_per_s": inter_all / (walk_ms_avg * 1e-3), "walk_ms": walk_ms_avg, "build_ms": float(np.mean(build_ms)),
-                "note": "DRAM traffic of the walk is ~0.1 GB per launch (tree is L2 resident): not HBM bound"}
+                "interactions_per_s": inter_all / (walk_ms_avg * 1e-3), "k_walk_ms": walk_ms_avg, "kernel_ms": kavg,
+                "note": "the walk's DRAM traffic is a few %% of HBM peak (tree L2 resident): bounded by the CUDA-core issue rate, not by HBM"}
+    if any_gas and sph_ms_avg > 0:
+        a = flop_per_sph_pair * (sph_all / world) / (sph_ms_avg * 1e-3) / 1e12
+        roofline["k_sph"] = {"bound": "fp32", "achieved": a, "peak": fp32_peak, "unit": "TFLOP/s", "frac": a / fp32_peak if fp32_peak else None,
+                             "algorithmic_flop_per_pair": flop_per_sph_pair, "pairs_per_launch": sph_all / world, "k_sph_ms": sph_ms_avg}
+    if fp64 is not None:
+        a = flop_per_interaction * inter_rank / (fp64["k_walk_ms"] * 1e-3) / 1e12
+        fp64["roofline"] = {"bound": "fp64", "kernel": "k_walk<COUNT=0,SPH=%d,MIXED=0>" % (1 if any_gas else 0), "achieved": a, "peak": fp64_peak, "unit": "TFLOP/s",
+                            "frac": a / fp64_peak if fp64_peak else None, "peak_source": "FP64 FMA chain microbenchmark on this GPU"}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
         hbm_peak, hbm_src = float(peaks["hbm_gbs"]), "MEASURED_PEAKS.json"
@@ -416,28 +501,31 @@ def run_gpu_arm(args, pkg):
         hbm_peak, hbm_src = 6650.0, "fallback (B200_PROFILING.md)"
     # build: key-gen 24+12 B, 8-pass sort of 12-byte items 2*8*12 B + 8*8 B histogram reads, permute ~100 B, links + upward ~190 B
     build_bytes = (36.0 + 256.0 + 100.0 + 190.0) * n
-    bms = float(np.mean(build_ms)) * 1e-3
+    bms = kavg["build"] * 1e-3
     roofline["hbm_build"] = {"bound": "hbm", "kernels": "k_keygen k_sort_* k_gather k_links k_upward ...", "achieved": build_bytes / bms / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                             "frac": build_bytes / bms / 1e9 / hbm_peak, "peak_source": hbm_src, "algorithmic_bytes_per_particle": build_bytes / n}
+                             "frac": build_bytes / bms / 1e9 / hbm_peak, "peak_source": hbm_src, "algorithmic_bytes_per_particle": build_bytes / n, "build_ms": kavg["build"]}
 
     # ---- CPU baseline on this box's host cores (bounded sample of the same workload)
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         ns = sample_size_for_cpu(n, 2, budget_s=20.0)
         ps, _, _, _ = make_particles(pkg, name, ns)
+        mhs = mh * (n / ns) if WORKLOADS[name][3] else mh
         with tempfile.TemporaryDirectory() as d:
-            secs, kind, cores, rows = cpu_reference_run(ps, e0, mh, 2, d)
+            secs, kind, cores, rows = cpu_reference_run(ps, e0, mhs, 2, d)
         cpu = {"value": ns / secs[-1], "unit": "particles/s", "cores": cores, "kind": kind,
-               "sample": "%d of %d particles of %s, 2nd of 2 steps, phases build+visual+gas_density+forces = %.3f s" % (ns, n, name, secs[-1])}
+               "sample": "%d of %d particles of %s (same generator at the smaller count: favours the CPU), 2nd of 2 steps, phases build+visual+gas_density+forces = %.3f s" % (ns, n, name, secs[-1])}
 
     line = {
         "metric": METRIC, "value": value, "unit": "particles/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64 decisions and accumulation, f32 pair forces (mixed mode)", "data": "synthetic",
-        "config": {"workload": name, "description": desc, "n_particles": n, "theta": THETA, "e0": e0, "massInH": mh, "all_active": True, "precision": "mixed",
-                   "l2": "256 MiB buffer written between timed steps (L2 flush); working set %.0f MB" % (n * 330 / 1e6),
-                   "parallelism": "replicated tree, tree-ordered target slices, 1 coalesced NCCL all-gather group/step (in place)" if world > 1 else "single GPU"},
-        "e2e": e2e, "resident_sim_step": resident, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
-        "interactions_per_s": inter_all / (walk_ms_avg * 1e-3), "wall_s_timed_region": t_wall,
+        "config": cfg,
+        "run": {"precision": "mixed", "l2": "256 MiB buffer written between timed steps (L2 flush); working set %.0f MB" % (n * 330 / 1e6),
+                "parallelism": "replicated tree, tree-ordered target slices, 1 coalesced NCCL all-gather group/step (in place)" if world > 1 else "single GPU",
+                "result_columns": list(out_cols)},
+        "e2e": e2e, "fp64": fp64, "resident_sim_step": resident, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+        "interactions_per_s": inter_all / (walk_ms_avg * 1e-3), "sph_pairs_per_step": sph_all, "divergence_counters": divergence, "multi_gpu_check": multi_gpu_check,
+        "wall_s_timed_region": t_wall,
     }
     print(json.dumps(line))
     if world > 1:
@@ -447,11 +535,12 @@ def run_gpu_arm(args, pkg):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="agb200", choices=["agb200", "reference"])
     ap.add_argument("--workload", default=None, choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-fp64", action="store_true", help="skip the FP64-arithmetic leg")
     args = ap.parse_args()
     import __graft_entry__ as ge
     pkg = ge.load_package()

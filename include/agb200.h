@@ -85,7 +85,7 @@ typedef struct {
     int64_t mac_exact_fallbacks;    /* MAC / SPH-gate decisions taken on the exact FP64 slow path  */
     int64_t groups, gas_groups, gas_orphans;
     int64_t gas_ties_exact;         /* density-group decisions re-taken with the reference's own left-fold gasMass sums */
-    int64_t gas_ties_unresolved;    /* ... that involved more than 1024 gas particles and kept the tree-order sums       */
+    int64_t gas_ties_unresolved;    /* ... that involved more than 8192 gas particles and kept the tree-order sums       */
     /* walk statistics: pop rounds, nodes popped, nodes straddling the opening radius of their warp, nodes opened by the
      * whole mask, 32-source tiles drained, rounds that touched the global-memory part of the stack */
     int64_t walk_rounds, walk_popped, walk_straddling, walk_opened, walk_tiles, walk_stack_spills;
@@ -129,6 +129,9 @@ int agb_force_path(agb_ctx* ctx, double visual_density_radius, double mass_in_h,
  * Output arrays need room for *count entries (query with index = NULL first, or size them for N); NULL = not wanted. */
 int agb_get_slice_count(agb_ctx* ctx, int part, int nparts, int64_t* count);
 int agb_get_slice_results(agb_ctx* ctx, int part, int nparts, uint32_t* index, double* ax, double* ay, double* az, double* dUdt, int memspace);
+/* ... the same for every field the path writes into Particle: r names the wanted columns (NULL = skip), each with room for the
+ * slice's *count entries; h / rho / P / T / visualDensity are those of the slice's targets (every GPU computes all densities). */
+int agb_get_slice_results_all(agb_ctx* ctx, int part, int nparts, uint32_t* index, const agb_results* r, int memspace);
 
 /* -------- device-resident driver loop (optional).  With particles handed over from HOST memory the
  * context owns device copies; these calls advance them in place exactly like the reference's loop, so nothing but the
@@ -161,7 +164,8 @@ typedef enum {
     AGB_OPT_TARGET_COUNTERS = 1,    /* 1: also record per-target visit / accept / SPH counts (parity tests) */
     AGB_OPT_PRECISION = 2           /* arithmetic of the pair forces: 0 = FP64 throughout (agrees with the reference to ~1e-14),
                                        1 = mixed (default): float-float displacements, FP32 law, FP64 accumulation; ~1e-7.
-                                       The accepted (target, source) sets, densities and SPH terms are identical in both. */
+                                       The accepted (target, source) sets, SPH pair sets and densities are identical in both;
+                                       the SPH pair algebra (kernel gradient, viscosity) runs in FP32 in mixed mode (~1e-7). */
 } agb_option;
 int agb_set_option(agb_ctx* ctx, int option, int64_t value);
 
@@ -177,6 +181,9 @@ int agb_get_target_counters(agb_ctx* ctx, int32_t* visits, int32_t* acc_nodes, i
 /* Device time (ms, CUDA events on the context's stream) of the last call of each phase:
  * [0] build_tree [1] visual_density [2] gas_density [3] forces (walk kernel only) [4] forces (whole call). */
 int agb_get_phase_ms(agb_ctx* ctx, double ms[5]);
+/* Finer device times of the last step (ms): [0] k_far [1] k_walk [2] k_sph; build_tree split into [3] root extent + keys
+ * [4] radix sort [5] gather into tree order [6] lcp + scan + links [7] upward pass + finalize. */
+int agb_get_kernel_ms(agb_ctx* ctx, double ms[8]);
 /* The CUDA stream (cudaStream_t) all work of this context is issued on. */
 int agb_get_stream(agb_ctx* ctx, void** stream);
 /* Number of kernels this context launched since creation. */

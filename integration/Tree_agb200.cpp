@@ -39,9 +39,13 @@ agb_ctx* context()
     return g_ctx;
 }
 
+// The reference's Tree methods return void and its driver has no error path (it prints and continues, Tree.cpp:70-74).
+// Continuing after a failed GPU call would integrate stale accelerations, so a non-OK status ends the run here.
 void check(int rc, const char* what)
 {
-    if (rc != AGB_OK) std::fprintf(stderr, "agb200: %s failed: %s (%s)\n", what, agb_strerror(rc), agb_last_error(g_ctx));
+    if (rc == AGB_OK) return;
+    std::fprintf(stderr, "agb200: %s failed: %s (%s)\n", what, agb_strerror(rc), agb_last_error(g_ctx));
+    std::abort();
 }
 
 const agb_aos_layout& layout()

@@ -40,4 +40,4 @@ def load_golden(name):
     return p, out, par
 
 
-GOLDEN_CASES = ["gassphere", "galaxy_gas", "plummer_gas3k", "galic22k"]
+GOLDEN_CASES = ["gassphere", "galaxy_gas", "plummer_gas3k", "galic22k", "galaxy60k"]

@@ -55,3 +55,5 @@ if __name__ == "__main__":
     save("plummer_gas3k", p, 0.5, 1e18, ics.gas_mass_in_h(p, 16), 2, True)
     p = convert("gadget", "Example/galiC_M1_22k.dat")       # the shipped example of Config.ini:42 (C0)
     save("galic22k", p, 0.5, 1e19, 1e40, 8, False)
+    p = convert("gadget", "Example/galaxy_littleendian.dat")  # 60 000 particles (halo + disk), masses from the header
+    save("galaxy60k", p, 0.5, 1e19, 1e40, 8, False)
