@@ -11,6 +11,7 @@
 int agb_walk_blocks(int sm_count);
 int agb_walk_warps_per_block();
 void agb_far_capacity(int* lcap, int* fcap, int* targets);
+size_t agb_sort_scratch_words(int64_t cap);
 
 struct agb_ctx {
     int device = 0, sm_count = 148;
@@ -85,7 +86,7 @@ void free_pool(agb_ctx* c)
     dfree(d.s_h); dfree(d.s_rho); dfree(d.s_P); dfree(d.s_U); dfree(d.s_mu); dfree(d.s_next); dfree(d.s_T); dfree(d.s_type);
     dfree(d.lcp); dfree(d.nodecnt); dfree(d.leafparent); dfree(d.group); dfree(d.leafdepth);
     dfree(d.leafmark); dfree(d.gasrank);
-    dfree(d.rec); dfree(d.blockhist); dfree(d.scanblk);
+    dfree(d.rec); dfree(d.grec); dfree(d.blockhist); dfree(d.scanblk);
     dfree(d.far_list); dfree(d.far_front); dfree(d.far_cnt); dfree(d.act_list);
     dfree(d.c_visits); dfree(d.c_accn); dfree(d.c_accl); dfree(d.c_sph);
     dfree(d.rec_ent); dfree(d.rec_next); dfree(d.rec_head); d.rec_cap = 0;
@@ -123,7 +124,7 @@ int ensure_pool(agb_ctx* c, int64_t n)
     CK(dalloc(d.s_next, cap)); CK(dalloc(d.s_T, cap)); CK(dalloc(d.s_type, cap));
     CK(dalloc(d.lcp, cap)); CK(dalloc(d.nodecnt, cap)); CK(dalloc(d.leafparent, cap)); CK(dalloc(d.group, cap)); CK(dalloc(d.leafdepth, cap));
     CK(dalloc(d.leafmark, cap)); CK(dalloc(d.gasrank, cap + 1));
-    CK(dalloc(d.rec, cap));
+    CK(dalloc(d.rec, cap)); CK(dalloc(d.grec, 2 * cap));
     {
         int lcap, fcap, tg; agb_far_capacity(&lcap, &fcap, &tg);
         const size_t nsg = cap / (size_t)tg + 2;
@@ -133,7 +134,7 @@ int ensure_pool(agb_ctx* c, int64_t n)
     for (auto& q : c->in_d) CK(dalloc(q, cap));
     CK(dalloc(c->timestep, cap));
     CK(dalloc(c->in_type, cap));
-    CK(dalloc(d.blockhist, 256 * ((cap + 2047) / 2048 + 1) + 8 * 256 + 64));   // sort tiles are >= 2048 keys (+ digit totals and tickets of the one-sweep variant)
+    CK(dalloc(d.blockhist, agb_sort_scratch_words((int64_t)cap)));               // digit totals, tickets and look-back status words of the 8 sort passes
     CK(dalloc(d.scanblk, (cap + 2047) / 2048 + 1));
     d.cap = (int64_t)cap;
     return ensure_nodes(c, (int64_t)cap + 1024);
@@ -178,12 +179,13 @@ int put_array(agb_ctx* c, double* dst, const double* src, int64_t n, int memspac
     return AGB_OK;
 }
 
-// positions go on the compute stream (the build starts with them); everything else is uploaded on a second stream
-// that the build only joins before it permutes the particle data (k_gather), so it overlaps extent + keys + sort
+// positions and masses go on the compute stream (the build starts with them: the extent pass packs (x, y, z, m) records);
+// everything else is uploaded on a second stream that the build only joins before it permutes the particle data
+// (k_gather), so it overlaps extent + keys + sort
 int own_input(agb_ctx* c, const double*& slot, int which, const double* src, int64_t n)
 {
     if (!src) { slot = nullptr; return AGB_OK; }
-    CK(cudaMemcpyAsync(c->in_d[which], src, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, which < 3 ? c->st : c->st_copy));
+    CK(cudaMemcpyAsync(c->in_d[which], src, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, (which < 3 || which == 6) ? c->st : c->st_copy));
     slot = c->in_d[which];
     return AGB_OK;
 }
@@ -260,6 +262,7 @@ int agb_create(agb_ctx** out, int device, int compat_cores)
     if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return AGB_ERR_NO_DEVICE;
     if (prop.major != 10) return AGB_ERR_NO_DEVICE;         // the kernels are built for sm_100a only
     if (cudaSetDevice(device) != cudaSuccess) return AGB_ERR_NO_DEVICE;
+    if (getenv("AGB200_L2_FETCH")) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(getenv("AGB200_L2_FETCH")));   // tuning probe: 32 / 64 / 128 bytes
     agb_ctx* c = new agb_ctx();
     c->device = device;
     c->sm_count = prop.multiProcessorCount;
@@ -319,11 +322,12 @@ int agb_set_particles(agb_ctx* c, const agb_particles* p, int memspace)
         d.type = p->type;
         c->bound = true;
     } else {
-        CK(cudaMemcpyAsync(c->in_type, p->type, (size_t)n, cudaMemcpyHostToDevice, c->st));   // needed by the key pass
         if ((rc = own_input(c, d.x, 0, p->x, n)) || (rc = own_input(c, d.y, 1, p->y, n)) || (rc = own_input(c, d.z, 2, p->z, n)) ||
+            (rc = own_input(c, d.mass, 6, p->mass, n))) return rc;
+        CK(cudaMemcpyAsync(c->in_type, p->type, (size_t)n, cudaMemcpyHostToDevice, c->st));   // needed by the key pass
+        if ((rc = own_input(c, d.next, 8, p->next_time, n)) ||
             (rc = own_input(c, d.vx, 3, p->vx, n)) || (rc = own_input(c, d.vy, 4, p->vy, n)) || (rc = own_input(c, d.vz, 5, p->vz, n)) ||
-            (rc = own_input(c, d.mass, 6, p->mass, n)) || (rc = own_input(c, d.U, 7, p->U, n)) || (rc = own_input(c, d.next, 8, p->next_time, n)) ||
-            (rc = own_input(c, d.mu, 9, p->mu, n))) return rc;
+            (rc = own_input(c, d.U, 7, p->U, n)) || (rc = own_input(c, d.mu, 9, p->mu, n))) return rc;
         d.type = c->in_type;
         c->bound = false;
     }

@@ -44,16 +44,21 @@ __device__ __forceinline__ double warp_max(double v)
 }
 
 // ------------------------------------------------------------------ root extent
+// vec3::length (Math/vec3.cpp:76-78): sqrt(x*x + y*y + z*z), separately rounded
+__device__ __forceinline__ double length3(double px, double py, double pz)
+{
+    return __dsqrt_rn(__dadd_rn(__dadd_rn(__dmul_rn(px, px), __dmul_rn(py, py)), __dmul_rn(pz, pz)));
+}
+
 __global__ void __launch_bounds__(TPB) k_dist_partial(const double* __restrict__ x, const double* __restrict__ y, const double* __restrict__ z,
-                                                        int64_t n, double4* __restrict__ rec, AgbScalars* s)
+                                                        const double* __restrict__ mass, int64_t n, double4* __restrict__ rec, AgbScalars* s)
 {
     __shared__ double sh[2][TPB / 32];
     double a = 0.0, b = 0.0;
     for (int64_t i = (int64_t)blockIdx.x * TPB + threadIdx.x; i < n; i += (int64_t)gridDim.x * TPB) {
         double px = x[i], py = y[i], pz = z[i];
-        // vec3::length (Math/vec3.cpp:76-78): sqrt(x*x + y*y + z*z), separately rounded
-        double d = __dsqrt_rn(__dadd_rn(__dadd_rn(__dmul_rn(px, px), __dmul_rn(py, py)), __dmul_rn(pz, pz)));
-        rec[i] = make_double4(px, py, pz, d);          // packed once, coalesced: later random accesses touch one 32-byte sector
+        double d = length3(px, py, pz);
+        rec[i] = make_double4(px, py, pz, mass[i]);    // (position, mass) packed once, coalesced: the gather reads one 32-byte sector per particle
         a += d;
         b += __dmul_rn(d, d);
     }
@@ -82,6 +87,8 @@ __global__ void k_extent_finish(AgbScalars* s, int nblocks, int64_t n)
     s->limit = __dadd_rn(mean, __dmul_rn(10.0, sd));     // Tree.cpp:89,105
     s->Rbits = 0ull;
     s->n_long_runs = 0; s->any_gas = 0; s->n_outliers = 0; s->dup_keys = 0; s->edge_dropped = 0; s->max_depth = 0; s->n_nodes = 0; s->node_overflow = 0;
+    s->next_uniform = 1; s->grid_bar = 0u;
+    for (int k = 0; k < 48; k++) { s->lvl_cnt[k] = 0; s->lvl_cur[k] = 0; }
 }
 
 __global__ void __launch_bounds__(TPB) k_extent_max(const double4* __restrict__ rec, int64_t n, AgbScalars* s)
@@ -90,7 +97,8 @@ __global__ void __launch_bounds__(TPB) k_extent_max(const double4* __restrict__ 
     const double lim = s->limit;
     double m = 0.0;
     for (int64_t i = (int64_t)blockIdx.x * TPB + threadIdx.x; i < n; i += (int64_t)gridDim.x * TPB) {
-        double d = rec[i].w;
+        const double4 r4 = rec[i];
+        const double d = length3(r4.x, r4.y, r4.z);
         if (d <= lim && d > m) m = d;
     }
     m = warp_max(m);
@@ -113,11 +121,14 @@ __device__ __forceinline__ uint64_t descend21(double px, double py, double pz, C
     uint64_t key = 0;
 #pragma unroll 1
     for (int l = 0; l < 21; l++) {
-        if (l > 0 || check_bounds_first) {
-            edge |= px < __dadd_rn(c.cx, -c.r) || px > __dadd_rn(c.cx, c.r) || py < __dadd_rn(c.cy, -c.r) || py > __dadd_rn(c.cy, c.r) ||
-                    pz < __dadd_rn(c.cz, -c.r) || pz > __dadd_rn(c.cz, c.r);
-        }
         const bool ox = px > c.cx, oy = py > c.cy, oz = pz > c.cz;       // Node.cpp:713-716, strict '>'
+        if (l > 0 || check_bounds_first) {
+            // the cell's inclusive bounds (Node.cpp:606-612): a coordinate above the centre can only violate the upper bound,
+            // one at or below it only the lower bound, so one rounded sum and one comparison per axis decide
+            const double tx = ox ? c.r : -c.r, ty = oy ? c.r : -c.r, tz = oz ? c.r : -c.r;
+            const double bx = __dadd_rn(c.cx, tx), by = __dadd_rn(c.cy, ty), bz = __dadd_rn(c.cz, tz);
+            edge |= (ox ? px > bx : px < bx) || (oy ? py > by : py < by) || (oz ? pz > bz : pz < bz);
+        }
         key |= ((uint64_t)ox | ((uint64_t)oy << 1) | ((uint64_t)oz << 2)) << (60 - 3 * l);
         const double hr = __dmul_rn(c.r, 0.5);                             // Node.cpp:436-440
         c.cx = __dadd_rn(c.cx, ox ? hr : -hr);
@@ -128,10 +139,17 @@ __device__ __forceinline__ uint64_t descend21(double px, double py, double pz, C
     return key;
 }
 
-// key_hi (outlier flag + levels 0..20) for every particle; key_lo is produced on demand by key_lo_of()
+__device__ __forceinline__ uint32_t digit_of(uint64_t w, int shift) { return (uint32_t)(w >> shift) & 255u; }
+
+// key_hi (outlier flag + levels 0..20) for every particle; key_lo is produced on demand by key_lo_of().
+// The digit histograms of all 8 radix passes are counted here as well (block-private counters in shared memory, one
+// global add per non-empty bin), so the sort needs no histogram pass of its own.
 __global__ void __launch_bounds__(TPB) k_keygen(const double4* __restrict__ rec, const uint8_t* __restrict__ type, int64_t n,
-                                                  uint64_t* __restrict__ khi, uint32_t* __restrict__ perm, AgbScalars* s)
+                                                  uint64_t* __restrict__ khi, uint32_t* __restrict__ perm, AgbScalars* s, uint32_t* __restrict__ ghist)
 {
+    __shared__ uint32_t h[8][256];
+    for (int k = threadIdx.x; k < 8 * 256; k += TPB) (&h[0][0])[k] = 0;
+    __syncthreads();
     int64_t i = (int64_t)blockIdx.x * TPB + threadIdx.x;
     bool outl = false, edge = false;
     if (i < n) {
@@ -144,12 +162,16 @@ __global__ void __launch_bounds__(TPB) k_keygen(const double4* __restrict__ rec,
         if (outl) hi = AGB_OUTLIER_BIT;           // the stable sort keeps caller order among the outliers
         else { Cell c{0.0, 0.0, 0.0, R}; hi = descend21(px, py, pz, c, false, edge); }
         khi[i] = hi; perm[i] = (uint32_t)i | (type[i] == 2 ? AGB_GAS_BIT : 0u);   // the sort payload also carries "is gas"
+#pragma unroll
+        for (int p = 0; p < 8; p++) atomicAdd(&h[p][digit_of(hi, 8 * p)], 1u);
     }
     unsigned mo = __ballot_sync(0xffffffffu, outl), me = __ballot_sync(0xffffffffu, edge);
     if ((threadIdx.x & 31) == 0) {
         if (mo) atomicAdd(&s->n_outliers, __popc(mo));
         if (me) atomicAdd(&s->edge_dropped, __popc(me));
     }
+    __syncthreads();
+    for (int k = threadIdx.x; k < 8 * 256; k += TPB) { const uint32_t v = (&h[0][0])[k]; if (v) atomicAdd(&ghist[k], v); }
 }
 
 // levels 21..41 of one particle (only needed where two particles share all of key_hi)
@@ -164,165 +186,23 @@ __device__ uint64_t key_lo_of(double px, double py, double pz, double R, AgbScal
     return lo;
 }
 
-// ------------------------------------------------------------------ LSD radix sort (8-bit digits)
-// Only key_hi (outlier flag + the first 21 levels) is radix sorted, together with the caller index: 8 stable
-// passes over 12-byte items.  key_lo (levels 21..41) matters only between particles that share all 21 upper
-// levels; it is gathered afterwards and those (short, rare) runs are ordered by k_fix_runs / k_fix_long_runs.
+// ------------------------------------------------------------------ LSD radix sort (8-bit digits), one sweep per pass
+// Only key_hi (outlier flag + the first 21 levels) is radix sorted, together with the caller index: 8 stable passes over
+// 12-byte items.  key_lo (levels 21..41) matters only between particles that share all 21 upper levels; it is computed
+// afterwards and those (short, rare) runs are ordered by k_fix_runs / k_fix_long_runs.
+//
+// One kernel per pass (Adinets & Merrill's Onesweep): the digit totals of all passes come from k_keygen, tiles are taken
+// in ticket order, every tile publishes its per-digit counts and finds its global offsets by decoupled look-back over the
+// tiles before it (Merrill & Garland's single-pass scan) — no histogram / scan kernels between the passes.  Inside a tile:
+// per-warp digit counts by shared-memory adds ("early counts": the tile totals are published before any ranking), ranks by
+// eight ballots per key (no MATCH.ANY, no shared-memory round trip per key), then the tile is reordered in shared memory
+// so that every digit's keys leave as one contiguous run.
+// Status word per (pass, tile, digit): [31:30] 0 = not ready, 1 = tile count, 2 = inclusive prefix; [29:0] value (n < 2^30).
 template <int ITEMS> struct SortCfg { static constexpr int TILE = TPB * ITEMS; };
-
-__device__ __forceinline__ uint32_t digit_of(uint64_t w, int shift) { return (uint32_t)(w >> shift) & 255u; }
-
-// per-block digit histogram, written bin-major: hist[bin * nblocks + block]
-template <int ITEMS>
-__global__ void __launch_bounds__(TPB) k_sort_hist(const uint64_t* __restrict__ word, int64_t n, int shift, uint32_t* __restrict__ hist, int nblocks)
-{
-    __shared__ uint32_t h[256];
-    h[threadIdx.x] = 0;
-    __syncthreads();
-    const int64_t base = (int64_t)blockIdx.x * SortCfg<ITEMS>::TILE;
-    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
-#pragma unroll
-    for (int j = 0; j < ITEMS; j++) {
-        int64_t i = base + (int64_t)w * (32 * ITEMS) + j * 32 + l;
-        if (i < n) atomicAdd(&h[digit_of(word[i], shift)], 1u);
-    }
-    __syncthreads();
-    hist[(size_t)threadIdx.x * nblocks + blockIdx.x] = h[threadIdx.x];
-}
-
-// one block per bin: exclusive scan along the blocks of that bin, total per bin
-__global__ void __launch_bounds__(1024) k_sort_scan(uint32_t* __restrict__ hist, int nblocks, AgbScalars* s)
-{
-    __shared__ uint32_t wsum[32];
-    __shared__ uint32_t carry;
-    uint32_t* row = hist + (size_t)blockIdx.x * nblocks;
-    if (threadIdx.x == 0) carry = 0;
-    __syncthreads();
-    const int l = threadIdx.x & 31, w = threadIdx.x >> 5;
-    for (int b0 = 0; b0 < nblocks; b0 += 1024) {
-        int i = b0 + threadIdx.x;
-        uint32_t v = i < nblocks ? row[i] : 0u, inc = v;
-        for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, inc, o); if (l >= o) inc += t; }
-        if (l == 31) wsum[w] = inc;
-        __syncthreads();
-        if (w == 0) {
-            uint32_t t = wsum[l], ti = t;
-            for (int o = 1; o < 32; o <<= 1) { uint32_t u = __shfl_up_sync(0xffffffffu, ti, o); if (l >= o) ti += u; }
-            wsum[l] = ti - t;
-        }
-        __syncthreads();
-        uint32_t excl = carry + wsum[w] + inc - v;
-        if (i < nblocks) row[i] = excl;
-        __syncthreads();
-        if (threadIdx.x == 1023) carry = excl + v;
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) s->bintotal[blockIdx.x] = (int32_t)carry;
-}
-
-// stable scatter: rank inside the block by warp match + per-warp digit counters, reorder the tile in shared
-// memory so that every digit's items leave as one contiguous, coalesced run
-template <int ITEMS>
-__global__ void __launch_bounds__(TPB) k_sort_scatter(const uint64_t* __restrict__ ihi, const uint32_t* __restrict__ iv,
-                                                        uint64_t* __restrict__ ohi, uint32_t* __restrict__ ov,
-                                                        int64_t n, int shift, const uint32_t* __restrict__ hist, int nblocks, const AgbScalars* __restrict__ s)
-{
-    constexpr int TILE = SortCfg<ITEMS>::TILE;
-    extern __shared__ __align__(16) unsigned char sort_smem[];
-    uint64_t* t_hi = reinterpret_cast<uint64_t*>(sort_smem);                 // [TILE]
-    uint32_t* t_v = reinterpret_cast<uint32_t*>(t_hi + TILE);                // [TILE]
-    uint32_t (*wcnt)[256] = reinterpret_cast<uint32_t (*)[256]>(t_v + TILE); // [TPB/32][256]
-    uint32_t* gbase = &wcnt[TPB / 32][0];                                    // [256] global base of (digit, block)
-    uint32_t* lbase = gbase + 256;                                           // [256] tile-local base of digit
-    __shared__ uint32_t ws[TPB / 32];
-    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
-    for (int k = threadIdx.x; k < (TPB / 32) * 256; k += TPB) (&wcnt[0][0])[k] = 0;
-    {   // exclusive scan of the 256 bin totals (every block repeats this tiny scan)
-        uint32_t v = (uint32_t)s->bintotal[threadIdx.x], inc = v;
-        for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, inc, o); if (l >= o) inc += t; }
-        if (l == 31) ws[w] = inc;
-        __syncthreads();
-        uint32_t off = 0;
-        for (int k = 0; k < w; k++) off += ws[k];
-        gbase[threadIdx.x] = off + inc - v + hist[(size_t)threadIdx.x * nblocks + blockIdx.x];
-    }
-    __syncthreads();
-    const int64_t tile0 = (int64_t)blockIdx.x * TILE;
-    const int64_t base = tile0 + (int64_t)w * (32 * ITEMS) + l;
-    uint64_t kh[ITEMS]; uint32_t kv[ITEMS]; uint32_t rk[ITEMS];
-#pragma unroll
-    for (int j = 0; j < ITEMS; j++) {
-        int64_t i = base + j * 32;
-        if (i < n) { kh[j] = ihi[i]; kv[j] = iv[i]; } else { kh[j] = ~0ull; kv[j] = 0; }
-    }
-    const unsigned lt = (1u << l) - 1u;
-#pragma unroll
-    for (int j = 0; j < ITEMS; j++) {
-        const bool valid = base + j * 32 < n;
-        const uint32_t d = digit_of(kh[j], shift);
-        const unsigned vm = __ballot_sync(0xffffffffu, valid);
-        const unsigned peers = __match_any_sync(0xffffffffu, valid ? d : 256u + (uint32_t)l) & vm;
-        const uint32_t prev = valid ? wcnt[w][d] : 0u;
-        __syncwarp();
-        if (valid && (peers & lt) == 0) wcnt[w][d] = prev + __popc(peers);
-        __syncwarp();
-        rk[j] = prev + __popc(peers & lt);
-    }
-    __syncthreads();
-    {   // per digit: exclusive offsets across the warps of this block, then across digits
-        uint32_t off = 0;
-#pragma unroll
-        for (int k = 0; k < TPB / 32; k++) { uint32_t t = wcnt[k][threadIdx.x]; wcnt[k][threadIdx.x] = off; off += t; }
-        uint32_t inc = off;
-        for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, inc, o); if (l >= o) inc += t; }
-        if (l == 31) ws[w] = inc;
-        __syncthreads();
-        uint32_t woff = 0;
-        for (int k = 0; k < w; k++) woff += ws[k];
-        lbase[threadIdx.x] = woff + inc - off;
-    }
-    __syncthreads();
-#pragma unroll
-    for (int j = 0; j < ITEMS; j++) {
-        if (base + j * 32 < n) {
-            const uint32_t d = digit_of(kh[j], shift);
-            const uint32_t pos = lbase[d] + wcnt[w][d] + rk[j];
-            t_hi[pos] = kh[j]; t_v[pos] = kv[j];
-        }
-    }
-    __syncthreads();
-    const int cnt = (int)min((int64_t)TILE, n - tile0);
-    for (int k = threadIdx.x; k < cnt; k += TPB) {
-        const uint64_t h = t_hi[k];
-        const uint32_t d = digit_of(h, shift);
-        const uint32_t pos = gbase[d] + ((uint32_t)k - lbase[d]);
-        ohi[pos] = h; ov[pos] = t_v[k];
-    }
-}
-
-// ------------------------------------------------------------------ one-sweep variant of the passes (EXPERIMENTAL, off by default)
-// One histogram kernel for all 8 digits up front, then ONE kernel per pass: tiles are taken in ticket order, every tile
-// publishes its per-digit counts and finds its offsets by decoupled look-back over the tiles before it (Merrill & Garland's
-// single-pass scan, as in Adinets & Merrill's Onesweep), instead of a histogram kernel + a scan kernel per pass.
-// Status word per (tile, digit): [31:30] 1 = tile count, 2 = inclusive prefix; [29:27] pass; [26:0] value (n < 2^27).
-// Enabled with AGB200_SORT_ONESWEEP=1.  Passes the golden / oracle parity tests (keys, topology exact) up to 100k particles and
-// takes the C1 build from 0.591 to 0.569 ms; the 16-items variant (n >= 4M) is untested, so the three-kernel passes stay the default.
-__global__ void __launch_bounds__(TPB) k_sort_hist_all(const uint64_t* __restrict__ word, int64_t n, uint32_t* __restrict__ ghist)
-{
-    __shared__ uint32_t h[8][256];
-    for (int k = threadIdx.x; k < 8 * 256; k += TPB) (&h[0][0])[k] = 0;
-    __syncthreads();
-    for (int64_t i = (int64_t)blockIdx.x * TPB + threadIdx.x; i < n; i += (int64_t)gridDim.x * TPB) {
-        const uint64_t w = word[i];
-#pragma unroll
-        for (int p = 0; p < 8; p++) atomicAdd(&h[p][digit_of(w, 8 * p)], 1u);
-    }
-    __syncthreads();
-    for (int k = threadIdx.x; k < 8 * 256; k += TPB) { const uint32_t v = (&h[0][0])[k]; if (v) atomicAdd(&ghist[k], v); }
-}
+enum : uint32_t { ST_AGG = 1u << 30, ST_INC = 2u << 30, ST_VAL = (1u << 30) - 1u };
 
 template <int ITEMS>
-__global__ void __launch_bounds__(TPB) k_sort_onesweep(const uint64_t* __restrict__ ihi, const uint32_t* __restrict__ iv,
+__global__ void __launch_bounds__(TPB, 3) k_sort_onesweep(const uint64_t* __restrict__ ihi, const uint32_t* __restrict__ iv,
                                                          uint64_t* __restrict__ ohi, uint32_t* __restrict__ ov, int64_t n, int pass,
                                                          const uint32_t* __restrict__ ghist, uint32_t* status, uint32_t* ticket)
 {
@@ -330,96 +210,105 @@ __global__ void __launch_bounds__(TPB) k_sort_onesweep(const uint64_t* __restric
     extern __shared__ __align__(16) unsigned char sort_smem[];
     uint64_t* t_hi = reinterpret_cast<uint64_t*>(sort_smem);                 // [TILE]
     uint32_t* t_v = reinterpret_cast<uint32_t*>(t_hi + TILE);                // [TILE]
-    uint32_t (*wcnt)[256] = reinterpret_cast<uint32_t (*)[256]>(t_v + TILE); // [TPB/32][256]
-    uint32_t* gbase = &wcnt[TPB / 32][0];                                    // [256] global base of (digit, tile)
-    uint32_t* lbase = gbase + 256;                                           // [256] tile-local base of digit
+    uint32_t (*wcnt)[256] = reinterpret_cast<uint32_t (*)[256]>(t_v + TILE); // [TPB/32][256] per-warp digit counts, then running offsets
+    uint32_t* gbase = &wcnt[TPB / 32][0];                                    // [256] global position of the tile's first key of each digit
+    uint32_t* lbase = gbase + 256;                                           // [256] tile-local position of the first key of each digit
     __shared__ uint32_t ws[TPB / 32];
     __shared__ uint32_t s_tile;
     const int shift = 8 * pass;
     const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
     if (threadIdx.x == 0) s_tile = atomicAdd(&ticket[pass], 1u);             // tiles in ticket order: a tile only ever waits for running ones
     for (int k = threadIdx.x; k < (TPB / 32) * 256; k += TPB) (&wcnt[0][0])[k] = 0;
-    uint32_t dbase;                                                           // first output position of my digit (exclusive scan of the 256 totals)
-    {
-        uint32_t v = ghist[pass * 256 + threadIdx.x], inc = v;
-        for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, inc, o); if (l >= o) inc += t; }
-        if (l == 31) ws[w] = inc;
-        __syncthreads();
-        uint32_t off = 0;
-        for (int k = 0; k < w; k++) off += ws[k];
-        dbase = off + inc - v;
-    }
     __syncthreads();
     const uint32_t tile = s_tile;
     const int64_t tile0 = (int64_t)tile * TILE;
     const int64_t base = tile0 + (int64_t)w * (32 * ITEMS) + l;
-    uint64_t kh[ITEMS]; uint32_t kv[ITEMS]; uint32_t rk[ITEMS];
+    uint64_t kh[ITEMS];
 #pragma unroll
     for (int j = 0; j < ITEMS; j++) {
-        int64_t i = base + j * 32;
-        if (i < n) { kh[j] = ihi[i]; kv[j] = iv[i]; } else { kh[j] = ~0ull; kv[j] = 0; }
+        const int64_t i = base + j * 32;
+        kh[j] = i < n ? ihi[i] : ~0ull;
     }
+    // per-warp digit counts (the counters of warp w are only ever touched by warp w)
+#pragma unroll
+    for (int j = 0; j < ITEMS; j++) if (base + j * 32 < n) atomicAdd(&wcnt[w][digit_of(kh[j], shift)], 1u);
+    __syncthreads();
+    uint32_t dbase, cnt_d;                                                    // thread d owns digit d
+    {
+        uint32_t off = 0;
+#pragma unroll
+        for (int k = 0; k < TPB / 32; k++) { const uint32_t t = wcnt[k][threadIdx.x]; wcnt[k][threadIdx.x] = off; off += t; }   // -> exclusive offsets of the warps
+        cnt_d = off;
+        volatile uint32_t* st = status + ((size_t)pass * gridDim.x + tile) * 256;
+        st[threadIdx.x] = (tile == 0 ? ST_INC : ST_AGG) | cnt_d;            // published before the ranking: the tiles behind need not wait for it
+        // first output position of digit d (exclusive scan of the 256 totals) and first tile-local position (scan of the tile's counts)
+        uint32_t v = ghist[pass * 256 + threadIdx.x], inc = v, linc = cnt_d;
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o), u = __shfl_up_sync(0xffffffffu, linc, o);
+            if (l >= o) { inc += t; linc += u; }
+        }
+        if (l == 31) { ws[w] = inc; gbase[w] = linc; }                        // gbase[0..7] doubles as scratch for the second scan
+        __syncthreads();
+        uint32_t o1 = 0, o2 = 0;
+        for (int k = 0; k < w; k++) { o1 += ws[k]; o2 += gbase[k]; }
+        dbase = o1 + inc - v;
+        __syncthreads();
+        lbase[threadIdx.x] = o2 + linc - cnt_d;
+    }
+    __syncthreads();
+    // stable ranks: keys of one warp with the same digit are numbered in lane order, item by item
+    uint32_t rk[ITEMS];
     const unsigned lt = (1u << l) - 1u;
 #pragma unroll
     for (int j = 0; j < ITEMS; j++) {
         const bool valid = base + j * 32 < n;
         const uint32_t d = digit_of(kh[j], shift);
-        const unsigned vm = __ballot_sync(0xffffffffu, valid);
-        const unsigned peers = __match_any_sync(0xffffffffu, valid ? d : 256u + (uint32_t)l) & vm;
-        const uint32_t prev = valid ? wcnt[w][d] : 0u;
+        unsigned peers = __ballot_sync(0xffffffffu, valid);
+#pragma unroll
+        for (int b = 0; b < 8; b++) {
+            const bool bit = (d >> b) & 1u;
+            const unsigned m = __ballot_sync(0xffffffffu, bit);
+            peers &= bit ? m : ~m;
+        }
+        const uint32_t prev = wcnt[w][d];
         __syncwarp();
         if (valid && (peers & lt) == 0) wcnt[w][d] = prev + __popc(peers);
         __syncwarp();
-        rk[j] = prev + __popc(peers & lt);
+        rk[j] = lbase[d] + prev + __popc(peers & lt);
     }
-    __syncthreads();
-    {   // per digit: exclusive offsets across the warps of this tile, the tile's count, then across digits
-        uint32_t off = 0;
-#pragma unroll
-        for (int k = 0; k < TPB / 32; k++) { uint32_t t = wcnt[k][threadIdx.x]; wcnt[k][threadIdx.x] = off; off += t; }
-        // publish my digit's count, look back for the tiles before this one
-        volatile uint32_t* st = status;
-        const uint32_t tag = (uint32_t)pass << 27, d = threadIdx.x;
+    // look back for the keys of digit d in the tiles before this one
+    {
+        volatile uint32_t* st = status + (size_t)pass * gridDim.x * 256;
         uint32_t excl = 0;
-        if (tile == 0) st[d] = (2u << 30) | tag | off;
-        else {
-            st[(size_t)tile * 256 + d] = (1u << 30) | tag | off;
-            // look back 8 tiles at a time (independent loads), consume them in order up to the first prefix / first tile not ready
+        if (tile > 0) {
             int64_t t = (int64_t)tile - 1;
             for (bool done = false; !done;) {
                 uint32_t v[8];
 #pragma unroll
-                for (int k = 0; k < 8; k++) v[k] = t - k >= 0 ? st[(size_t)(t - k) * 256 + d] : ((2u << 30) | tag);   // before tile 0: prefix 0
+                for (int k = 0; k < 8; k++) v[k] = t - k >= 0 ? st[(size_t)(t - k) * 256 + threadIdx.x] : ST_INC;   // before tile 0: prefix 0
                 int used = 0;
 #pragma unroll
                 for (int k = 0; k < 8; k++) {
-                    if (done || used != k) continue;
-                    if ((v[k] >> 30) == 0u || ((v[k] >> 27) & 7u) != (uint32_t)pass) continue;   // not written yet in this pass: read again from here
-                    excl += v[k] & 0x7ffffffu;
+                    if (done || used != k || (v[k] >> 30) == 0u) continue;  // not published yet: read again from here
+                    excl += v[k] & ST_VAL;
                     used = k + 1;
                     done = (v[k] >> 30) == 2u;
                 }
                 t -= used;
             }
-            st[(size_t)tile * 256 + d] = (2u << 30) | tag | (excl + off);
+            st[(size_t)tile * 256 + threadIdx.x] = ST_INC | (excl + cnt_d);
         }
         gbase[threadIdx.x] = dbase + excl;
-        uint32_t inc = off;
-        for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, inc, o); if (l >= o) inc += t; }
-        if (l == 31) ws[w] = inc;
-        __syncthreads();
-        uint32_t woff = 0;
-        for (int k = 0; k < w; k++) woff += ws[k];
-        lbase[threadIdx.x] = woff + inc - off;
     }
-    __syncthreads();
+    // keys first (their registers are free afterwards), then the payload: it is only read now, so the kernel fits 3 blocks per SM
 #pragma unroll
-    for (int j = 0; j < ITEMS; j++) {
-        if (base + j * 32 < n) {
-            const uint32_t d = digit_of(kh[j], shift);
-            const uint32_t pos = lbase[d] + wcnt[w][d] + rk[j];
-            t_hi[pos] = kh[j]; t_v[pos] = kv[j];
-        }
+    for (int j = 0; j < ITEMS; j++) if (base + j * 32 < n) t_hi[rk[j]] = kh[j];
+    {
+        uint32_t kv[ITEMS];
+#pragma unroll
+        for (int j = 0; j < ITEMS; j++) kv[j] = base + j * 32 < n ? iv[base + j * 32] : 0u;
+#pragma unroll
+        for (int j = 0; j < ITEMS; j++) if (base + j * 32 < n) t_v[rk[j]] = kv[j];
     }
     __syncthreads();
     const int cnt = (int)min((int64_t)TILE, n - tile0);
@@ -499,6 +388,28 @@ __global__ void __launch_bounds__(TPB) k_fix_long_runs(const uint64_t* __restric
 }
 
 // ------------------------------------------------------------------ gather into tree order
+// "every particle is due at the same time" (the shipped fixed-step configuration): then the tree-order copy of
+// nextIntegrationTime is a constant and the gather need not fetch it with one random 32-byte sector per particle
+__global__ void __launch_bounds__(TPB) k_next_uniform(const double* __restrict__ next, int64_t n, AgbScalars* s)
+{
+    const double v0 = next[0];
+    bool differ = false;
+    for (int64_t i = (int64_t)blockIdx.x * TPB + threadIdx.x; i < n; i += (int64_t)gridDim.x * TPB) differ |= next[i] != v0;
+    if (__any_sync(0xffffffffu, differ) && (threadIdx.x & 31) == 0) s->next_uniform = 0;
+}
+
+// Caller order, streaming: the eight fields only gas particles carry, packed into one 64-byte record per gas particle
+// (indexed by caller position, written for gas only).  A random 8-byte read costs a whole DRAM burst (measured: 534 B of DRAM
+// reads per particle in the old gather, 16 times the bytes it used), so the gather below touches ONE record per particle
+// (+ one per gas particle) instead of one sector per field.
+__global__ void __launch_bounds__(TPB) k_pack_gas(AgbDev d)
+{
+    int64_t i = (int64_t)blockIdx.x * TPB + threadIdx.x;
+    if (i >= d.n || d.type[i] != 2) return;
+    d.grec[2 * i] = make_double4(d.vx ? d.vx[i] : 0.0, d.vy ? d.vy[i] : 0.0, d.vz ? d.vz[i] : 0.0, d.U ? d.U[i] : 0.0);
+    d.grec[2 * i + 1] = make_double4(d.mu ? d.mu[i] : 0.58, d.rho[i], d.P[i], d.T[i]);
+}
+
 __global__ void __launch_bounds__(TPB) k_gather(AgbDev d, uint32_t* __restrict__ perm, AgbScalars* s)
 {
     int64_t i = (int64_t)blockIdx.x * TPB + threadIdx.x;
@@ -506,19 +417,20 @@ __global__ void __launch_bounds__(TPB) k_gather(AgbDev d, uint32_t* __restrict__
     const uint32_t val = perm[i], p = val & AGB_IDX_MASK;
     const bool gas = (val & AGB_GAS_BIT) != 0u;
     perm[i] = p;                                      // from here on the permutation is a plain caller index
-    const double m = d.mass[p];
-    const double4 r4 = d.rec[p];
-    d.src_pm[i] = make_double4(r4.x, r4.y, r4.z, m);
+    const double4 r4 = d.rec[p];                      // (x, y, z, mass), one sector
+    const double m = r4.w;
+    d.src_pm[i] = r4;
     d.s_type[i] = gas ? 2 : 1;                        // only "gas or not" matters on the path (Node.cpp:319,371,478,679,763)
-    d.s_next[i] = d.next ? d.next[p] : 0.0;
+    d.s_next[i] = !d.next ? 0.0 : s->next_uniform ? d.next[0] : d.next[p];
     if (gas) {
         // velocity, U, mu and the carried h/rho/P/T are only ever read for gas (Node.cpp:88-172, :722-796)
-        d.src_gv[i] = make_double4(d.vx ? d.vx[p] : 0.0, d.vy ? d.vy[p] : 0.0, d.vz ? d.vz[p] : 0.0, m);
+        const double4 g0 = d.grec[2 * (size_t)p], g1 = d.grec[2 * (size_t)p + 1];   // (vx, vy, vz, U), (mu, rho, P, T)
+        d.src_gv[i] = make_double4(g0.x, g0.y, g0.z, m);
         d.src_flag[i] = m > 0.0 ? 1 : 0;
         s->any_gas = 1;
-        d.s_U[i] = d.U ? d.U[p] : 0.0;
-        d.s_mu[i] = d.mu ? d.mu[p] : 0.58;
-        d.s_rho[i] = d.rho[p]; d.s_P[i] = d.P[p]; d.s_T[i] = d.T[p];
+        d.s_U[i] = g0.w;
+        d.s_mu[i] = g1.x;
+        d.s_rho[i] = g1.y; d.s_P[i] = g1.z; d.s_T[i] = g1.w;
         d.s_h[i] = 0.0;                               // Tree.cpp:123-133 zeroes h of every gas particle
     } else {
         d.src_gv[i] = make_double4(0.0, 0.0, 0.0, 0.0);
@@ -629,22 +541,38 @@ __global__ void __launch_bounds__(TPB) k_init_nodes(AgbDev d, const AgbScalars* 
     int4 e = make_int4(-1, -1, -1, -1);
     reinterpret_cast<int4*>(d.child)[2 * k] = e;
     reinterpret_cast<int4*>(d.child)[2 * k + 1] = e;
-    d.arrived[k] = 0;
     d.nmark[k] = 0;
 }
 
 struct KeyView { const uint64_t* hi; const uint64_t* lo; };
 
+// "key j shares >= d levels with (h, l)" for a fixed d: one shift of the xor; key_lo is only read for d > 21
+struct SharesLevels {
+    KeyView K; uint64_t h, l; int sh_hi, sh_lo; bool deep;
+    __device__ __forceinline__ SharesLevels(KeyView K_, uint64_t h_, uint64_t l_, int d) : K(K_), h(h_), l(l_)
+    {
+        deep = d > 21;
+        sh_hi = deep ? 0 : 63 - 3 * d;                // d <= 21: the top 1 + 3 d bits of key_hi (outlier flag + d levels) agree
+        sh_lo = deep ? 63 - 3 * (d - 21) : 0;
+    }
+    __device__ __forceinline__ bool operator()(int64_t j) const
+    {
+        if (!deep) return ((K.hi[j] ^ h) >> sh_hi) == 0ull;
+        return K.hi[j] == h && ((K.lo[j] ^ l) >> sh_lo) == 0ull;
+    }
+};
+
 // smallest s <= i whose key shares >= d levels with key i
 __device__ __forceinline__ int64_t find_first(KeyView K, int64_t i, int d, uint64_t h, uint64_t l)
 {
     if (d <= 0) return 0;
+    const SharesLevels same(K, h, l, d);
     int64_t step = 1;
-    while (i - step >= 0 && agb_common_levels(K.hi[i - step], K.lo[i - step], h, l) >= d) step <<= 1;
+    while (i - step >= 0 && same(i - step)) step <<= 1;
     int64_t lo = max((int64_t)-1, i - step), hi = i - (step >> 1);      // key[lo] fails (or lo == -1), key[hi] passes
     while (hi - lo > 1) {
         int64_t mid = (lo + hi) >> 1;
-        if (agb_common_levels(K.hi[mid], K.lo[mid], h, l) >= d) hi = mid; else lo = mid;
+        if (same(mid)) hi = mid; else lo = mid;
     }
     return hi;
 }
@@ -668,12 +596,16 @@ __device__ __forceinline__ int node_id_at(const AgbDev& d, int64_t s, int depth)
     return d.nodebase[s] + (depth - Lprev - 1);
 }
 
-__global__ void __launch_bounds__(TPB) k_links(AgbDev d, const uint64_t* __restrict__ khi, const uint64_t* __restrict__ klo, const AgbScalars* __restrict__ s)
+__global__ void __launch_bounds__(TPB) k_links(AgbDev d, const uint64_t* __restrict__ khi, const uint64_t* __restrict__ klo, AgbScalars* s)
 {
+    __shared__ int lvl[AGB_MAX_LEVELS + 1];                  // nodes of this block per depth (for the level lists of the upward pass)
+    if (threadIdx.x <= AGB_MAX_LEVELS) lvl[threadIdx.x] = 0;
+    __syncthreads();
     int64_t i = (int64_t)blockIdx.x * TPB + threadIdx.x;
     const int64_t nt = s->n_in_tree;
-    if (i >= nt || s->n_nodes > d.ncap) return;
-    if (nt < 2) { d.leafdepth[i] = 0; return; }              // a single particle: the root itself is the leaf (Node.cpp:409-418)
+    if (s->n_nodes > d.ncap) return;                         // whole grid: no usable node table this step
+    if (i < nt && nt < 2) d.leafdepth[i] = 0;                // a single particle: the root itself is the leaf (Node.cpp:409-418)
+    if (i < nt && nt >= 2) {
     KeyView K{khi, klo};
     const uint64_t h = khi[i], l = klo[i];
     const int Li = d.lcp[i], Lm = i > 0 ? (int)d.lcp[i - 1] : -1;
@@ -681,6 +613,7 @@ __global__ void __launch_bounds__(TPB) k_links(AgbDev d, const uint64_t* __restr
     const int N = (int)d.n;
     for (int dep = Lm + 1; dep <= Li; dep++) {
         int k = base + (dep - Lm - 1);
+        atomicAdd(&lvl[dep], 1);
         d.ndepth[k] = (int8_t)dep;
         d.nfirst[k] = (int32_t)i;
         int par;
@@ -699,6 +632,9 @@ __global__ void __launch_bounds__(TPB) k_links(AgbDev d, const uint64_t* __restr
     d.child[(size_t)par * 8 + agb_octant_at(h, l, dp)] = (int32_t)i;
     d.leafparent[i] = par;
     d.leafdepth[i] = (int8_t)(dp + 1);
+    }
+    __syncthreads();
+    if (threadIdx.x <= AGB_MAX_LEVELS && lvl[threadIdx.x]) atomicAdd(&s->lvl_cnt[threadIdx.x], lvl[threadIdx.x]);
 }
 
 // ------------------------------------------------------------------ upward pass (monopole + gas moments)
@@ -759,36 +695,78 @@ __device__ __forceinline__ void node_moments(const AgbDev& d, int k, int N, bool
     d.nlast[k] = last;
 }
 
-// Last-arriver climb.  The dependent chain per level is kept to: child moments -> store + fence -> atomic; the parent's
-// links (needed for the arrival count now and for its moments next) and the grandparent id are fetched ahead of it.
-__global__ void __launch_bounds__(TPB) k_upward(AgbDev d, const AgbScalars* __restrict__ s)
+// Level lists: the nodes of each depth, compacted (order inside a depth is irrelevant: every node sums its own children in
+// fixed octant order).  Counts per depth come from k_links.
+__global__ void __launch_bounds__(TPB) k_level_lists(AgbDev d, AgbScalars* s, int32_t* __restrict__ list)
 {
-    int k = blockIdx.x * TPB + threadIdx.x;
-    if (k >= s->n_nodes || s->n_nodes > d.ncap) return;
-    const int N = (int)d.n;
-    ChildLinks L = load_links(d.child, k);
-    if (count_node_children(L, N) != 0) return;               // only nodes whose children are all leaves start a climb
-    int cur = k, par = d.nparent[cur];
-    const bool any_gas = s->any_gas != 0;
-    while (true) {
-        ChildLinks Lp = L; int ppar = -1;
-        if (par >= 0) { Lp = load_links(d.child, par); ppar = d.nparent[par]; }
-        node_moments(d, cur, N, any_gas, L);
-        if (par < 0) break;
-        __threadfence();
-        const int need = count_node_children(Lp, N);
-        const int old = atomicAdd(&d.arrived[par], 1);
-        if (old + 1 < need) break;                             // a sibling subtree is still being summed
-        __threadfence();
-        cur = par; par = ppar; L = Lp;
+    __shared__ int cnt[AGB_MAX_LEVELS + 1], basep[AGB_MAX_LEVELS + 1];
+    if (threadIdx.x <= AGB_MAX_LEVELS) cnt[threadIdx.x] = 0;
+    __syncthreads();
+    const int nn = s->n_nodes;
+    if (nn > d.ncap) return;
+    const int k = blockIdx.x * TPB + threadIdx.x;
+    int dep = -1, r = 0;
+    if (k < nn) { dep = d.ndepth[k]; r = atomicAdd(&cnt[dep], 1); }
+    __syncthreads();
+    if (threadIdx.x <= AGB_MAX_LEVELS && cnt[threadIdx.x]) {
+        int off = 0;
+        for (int q = 0; q < (int)threadIdx.x; q++) off += s->lvl_cnt[q];       // first slot of this depth
+        basep[threadIdx.x] = off + atomicAdd(&s->lvl_cur[threadIdx.x], cnt[threadIdx.x]);
     }
+    __syncthreads();
+    if (k < nn) list[basep[dep] + r] = k;
+}
+
+// all blocks of a co-resident grid wait for each other (bar starts at 0; epoch counts arrivals expected so far)
+__device__ __forceinline__ void grid_sync(unsigned int* bar, unsigned int nblocks, unsigned int& epoch)
+{
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        epoch += nblocks;
+        __threadfence();
+        atomicAdd(bar, 1u);
+        while (*(volatile unsigned int*)bar < epoch) { }
+        __threadfence();
+    }
+    __syncthreads();
+}
+
+// Upward pass, level by level from the deepest internal nodes to the root: one thread per node of the level, children of
+// deeper levels are complete (grid-wide barrier between levels; the grid is sized to be co-resident).  No atomics, no
+// fences per node, full warps.  Then the reference's root quirk and the normalisation (COM, mVel, duplication flags).
+__device__ __forceinline__ void root_fix_block(const AgbDev& d, const AgbScalars* s);
+__device__ __forceinline__ void finalize_node(const AgbDev& d, const AgbScalars* s, int k);
+
+__global__ void __launch_bounds__(TPB) k_upward_levels(AgbDev d, AgbScalars* s, const int32_t* __restrict__ list)
+{
+    const int nn = s->n_nodes;
+    if (nn > d.ncap || nn < 1) return;
+    const int N = (int)d.n;
+    const bool any_gas = s->any_gas != 0;
+    unsigned int epoch = 0;
+    int off_end = nn;                                         // list segment of depth `dep` is [off_end - cnt, off_end)
+    int maxd = AGB_MAX_LEVELS;
+    while (maxd > 0 && s->lvl_cnt[maxd] == 0) maxd--;
+    for (int q = maxd + 1; q <= AGB_MAX_LEVELS; q++) off_end -= s->lvl_cnt[q];
+    for (int dep = maxd; dep >= 0; dep--) {
+        const int cnt = s->lvl_cnt[dep];
+        const int beg = off_end - cnt;
+        for (int idx = beg + blockIdx.x * TPB + threadIdx.x; idx < off_end; idx += gridDim.x * TPB) {
+            const int k = list[idx];
+            node_moments(d, k, N, any_gas, load_links(d.child, k));
+        }
+        off_end = beg;
+        if (cnt > 0 || dep == 0) grid_sync(&s->grid_bar, gridDim.x, epoch);
+    }
+    if (blockIdx.x == 0) root_fix_block(d, s);
+    grid_sync(&s->grid_bar, gridDim.x, epoch);
+    for (int k = blockIdx.x * TPB + threadIdx.x; k < nn; k += gridDim.x * TPB) finalize_node(d, s, k);
 }
 
 // Reference quirk: bulk insertion accumulates the ROOT's mass / COM / gasMass / mVel over ALL particles,
 // including those outside the cube that are never inserted (Node.cpp:477-499 precede the octant test).
-__global__ void __launch_bounds__(TPB) k_root_fix(AgbDev d, const AgbScalars* __restrict__ s)
+__device__ __forceinline__ void root_fix_block(const AgbDev& d, const AgbScalars* s)
 {
-    if (s->n_nodes < 1 || s->n_nodes > d.ncap) return;
     if (d.n < (int64_t)d.cores * 100) return;                  // one-by-one insertion rejects them at the root (Node.cpp:606-612)
     __shared__ double sh[8][TPB / 32];
     double v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -806,19 +784,17 @@ __global__ void __launch_bounds__(TPB) k_root_fix(AgbDev d, const AgbScalars* __
     if (threadIdx.x == 0) {
         double t[8];
         for (int k = 0; k < 8; k++) { t[k] = 0; for (int w = 0; w < TPB / 32; w++) t[k] += sh[k][w]; }
-        double4 pm = d.mom_pm[0], gv = s->any_gas ? d.mom_gv[0] : make_double4(0, 0, 0, 0);
+        double4 pm = ldcg4(&d.mom_pm[0]), gv = s->any_gas ? ldcg4(&d.mom_gv[0]) : make_double4(0, 0, 0, 0);
         pm.x += t[0]; pm.y += t[1]; pm.z += t[2]; pm.w += t[3];
         gv.x += t[4]; gv.y += t[5]; gv.z += t[6]; gv.w += t[7];
         d.mom_pm[0] = pm; d.mom_gv[0] = gv;
     }
 }
 
-__global__ void __launch_bounds__(TPB) k_finalize(AgbDev d, const AgbScalars* __restrict__ s)
+__device__ __forceinline__ void finalize_node(const AgbDev& d, const AgbScalars* s, int k)
 {
-    int k = blockIdx.x * TPB + threadIdx.x;
-    if (k >= s->n_nodes || s->n_nodes > d.ncap) return;
     const int64_t N = d.n;
-    double4 pm = d.mom_pm[k], gv = s->any_gas ? d.mom_gv[k] : make_double4(0, 0, 0, 0);
+    double4 pm = ldcg4(&d.mom_pm[k]), gv = s->any_gas ? ldcg4(&d.mom_gv[k]) : make_double4(0, 0, 0, 0);
     double4 com = make_double4(0, 0, 0, pm.w), mv = make_double4(0, 0, 0, gv.w);
     if (pm.w > 0.0) { com.x = pm.x / pm.w; com.y = pm.y / pm.w; com.z = pm.z / pm.w; }
     if (gv.w > 0.0) { mv.x = gv.x / gv.w; mv.y = gv.y / gv.w; mv.z = gv.z / gv.w; }
@@ -830,8 +806,8 @@ __global__ void __launch_bounds__(TPB) k_finalize(AgbDev d, const AgbScalars* __
     int par = d.nparent[k];
     uint8_t dup = 0;
     if (par >= 0) {
-        int64_t cnt = (int64_t)d.nlast[k] - d.nfirst[k] + 1;
-        int64_t pcnt = par == 0 ? N : (int64_t)d.nlast[par] - d.nfirst[par] + 1;   // the root is handed all N particles
+        int64_t cnt = (int64_t)__ldcg(&d.nlast[k]) - d.nfirst[k] + 1;
+        int64_t pcnt = par == 0 ? N : (int64_t)__ldcg(&d.nlast[par]) - d.nfirst[par] + 1;   // the root is handed all N particles
         dup = cnt < thr && pcnt >= thr;
     }
     d.ndup[k] = dup;
@@ -863,64 +839,49 @@ static inline int nblk(int64_t n, int per) { return (int)((n + per - 1) / per); 
 int agb_launch_extent(const AgbDev& d, AgbScalars* s, cudaStream_t st)
 {
     int nb = (int)std::min<int64_t>(1024, std::max<int64_t>(1, nblk(d.n, TPB)));
-    k_dist_partial<<<nb, TPB, 0, st>>>(d.x, d.y, d.z, d.n, d.rec, s);
+    k_dist_partial<<<nb, TPB, 0, st>>>(d.x, d.y, d.z, d.mass, d.n, d.rec, s);
     k_extent_finish<<<1, 32, 0, st>>>(s, nb, d.n);
     k_extent_max<<<nb, TPB, 0, st>>>(d.rec, d.n, s);
     return 3;
 }
 
-int agb_launch_keygen(AgbDev& d, AgbScalars* s, cudaStream_t st)
-{
-    k_keygen<<<nblk(d.n, TPB), TPB, 0, st>>>(d.rec, d.type, d.n, d.khi[0], d.perm[0], s);
-    d.cur = 0;
-    return 1;
-}
-
 template <int ITEMS>
-static int sort_passes(AgbDev& d, AgbScalars* s, cudaStream_t st)
+static int sort_passes(AgbDev& d, cudaStream_t st)
 {
     constexpr int TILE = SortCfg<ITEMS>::TILE;
     const int nb = nblk(d.n, TILE);
     const int smem = TILE * 12 + (TPB / 32) * 256 * 4 + 2 * 256 * 4;
-    cudaFuncSetAttribute(k_sort_scatter<ITEMS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);   // per device; cheap, so not cached
-    for (int pass = 0; pass < 8; pass++) {
-        const int in = d.cur, out = d.cur ^ 1;
-        k_sort_hist<ITEMS><<<nb, TPB, 0, st>>>(d.khi[in], d.n, pass * 8, d.blockhist, nb);
-        k_sort_scan<<<256, 1024, 0, st>>>(d.blockhist, nb, s);
-        k_sort_scatter<ITEMS><<<nb, TPB, smem, st>>>(d.khi[in], d.perm[in], d.khi[out], d.perm[out], d.n, pass * 8, d.blockhist, nb, s);
-        d.cur = out;
-    }
-    return 24;
-}
-
-template <int ITEMS>
-static int sort_passes_onesweep(AgbDev& d, cudaStream_t st)
-{
-    constexpr int TILE = SortCfg<ITEMS>::TILE;
-    const int nb = nblk(d.n, TILE);
-    const int smem = TILE * 12 + (TPB / 32) * 256 * 4 + 2 * 256 * 4;
-    cudaFuncSetAttribute(k_sort_onesweep<ITEMS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    uint32_t* status = d.blockhist;                          // [nb][256], then the 8 x 256 digit totals, then the 8 tickets
-    uint32_t* ghist = status + (size_t)nb * 256;
+    cudaFuncSetAttribute(k_sort_onesweep<ITEMS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);   // per device; cheap, so not cached
+    uint32_t* ghist = d.blockhist;                           // [8][256] digit totals (k_keygen), [8] tickets, then status [8][nb][256]
     uint32_t* ticket = ghist + 8 * 256;
-    cudaMemsetAsync(status, 0, ((size_t)nb * 256 + 8 * 256 + 8) * sizeof(uint32_t), st);
-    k_sort_hist_all<<<(int)std::min<int64_t>(nblk(d.n, TPB * 8), 4 * 148), TPB, 0, st>>>(d.khi[d.cur], d.n, ghist);
+    uint32_t* status = ticket + 64;
     for (int pass = 0; pass < 8; pass++) {
         const int in = d.cur, out = d.cur ^ 1;
         k_sort_onesweep<ITEMS><<<nb, TPB, smem, st>>>(d.khi[in], d.perm[in], d.khi[out], d.perm[out], d.n, pass, ghist, status, ticket);
         d.cur = out;
     }
-    return 9;
+    return 8;
+}
+
+// items per thread of the sort tiles for n keys (the status area is sized for the smaller tile)
+static inline int sort_items(int64_t n) { return n >= (4 << 20) ? 16 : 8; }
+size_t agb_sort_scratch_words(int64_t cap) { return 8 * 256 + 64 + 8 * (size_t)((cap + 2047) / 2048 + 1) * 256; }
+
+int agb_launch_keygen(AgbDev& d, AgbScalars* s, cudaStream_t st)
+{
+    // digit totals + tickets + status words of the 8 sort passes start at zero
+    const size_t nb = (size_t)nblk(d.n, TPB * sort_items(d.n));
+    cudaMemsetAsync(d.blockhist, 0, (8 * 256 + 64 + 8 * nb * 256) * sizeof(uint32_t), st);
+    k_keygen<<<nblk(d.n, TPB), TPB, 0, st>>>(d.rec, d.type, d.n, d.khi[0], d.perm[0], s, d.blockhist);
+    d.cur = 0;
+    return 1;
 }
 
 int agb_launch_sort(AgbDev& d, AgbScalars* s, cudaStream_t st)
 {
     // key_hi + caller index: 8 passes; the result lands in half 0 again.  key_lo (tree order, klo[1]) is zero except
     // inside runs of equal key_hi, where it is computed on demand and decides the order.
-    static const bool onesweep = getenv("AGB200_SORT_ONESWEEP") && atoi(getenv("AGB200_SORT_ONESWEEP")) != 0;   // experimental, see k_sort_onesweep
-    int launches;
-    if (onesweep && d.n < (1 << 27)) launches = d.n >= (4 << 20) ? sort_passes_onesweep<16>(d, st) : sort_passes_onesweep<8>(d, st);
-    else launches = d.n >= (4 << 20) ? sort_passes<16>(d, s, st) : sort_passes<8>(d, s, st);
+    int launches = sort_items(d.n) == 16 ? sort_passes<16>(d, st) : sort_passes<8>(d, st);
     const int nb = nblk(d.n, TPB);
     cudaMemsetAsync(d.klo[1], 0, (size_t)d.n * sizeof(uint64_t), st);
     k_fix_runs<<<nb, TPB, 0, st>>>(d.khi[d.cur], d.klo[1], d.perm[d.cur], d.n, d.rec, s, d.nodecnt);
@@ -932,6 +893,8 @@ int agb_launch_links(AgbDev& d, AgbScalars* s, cudaStream_t st, cudaEvent_t* ev)
 {
     const int nb = nblk(d.n, TPB);
     const uint64_t *khi = d.khi[d.cur], *klo = d.klo[1];
+    if (d.next) k_next_uniform<<<std::min(nb, 2048), TPB, 0, st>>>(d.next, d.n, s);
+    k_pack_gas<<<nb, TPB, 0, st>>>(d);
     k_gather<<<nb, TPB, 0, st>>>(d, d.perm[d.cur], s);
     if (ev) cudaEventRecord(ev[0], st);
     k_lcp<<<nb, TPB, 0, st>>>(khi, klo, d.n, d.lcp, d.nodecnt, s);
@@ -943,10 +906,14 @@ int agb_launch_links(AgbDev& d, AgbScalars* s, cudaStream_t st, cudaEvent_t* ev)
     k_init_nodes<<<nnb, TPB, 0, st>>>(d, s);
     k_links<<<nb, TPB, 0, st>>>(d, khi, klo, s);
     if (ev) cudaEventRecord(ev[1], st);
-    k_upward<<<nnb, TPB, 0, st>>>(d, s);
-    k_root_fix<<<1, TPB, 0, st>>>(d, s);
-    k_finalize<<<nnb, TPB, 0, st>>>(d, s);
-    return 10;
+    // level lists (scratch: grouplist, unused until the density pass), then the persistent level-by-level upward pass
+    k_level_lists<<<nnb, TPB, 0, st>>>(d, s, d.grouplist);
+    static int occ = 0;                                       // co-resident blocks per SM of the level kernel (same on every B200)
+    if (!occ) { cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_upward_levels, TPB, 0); occ = std::max(1, std::min(occ, 4)); }
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    k_upward_levels<<<std::min(sms * occ, std::max(1, nnb)), TPB, 0, st>>>(d, s, d.grouplist);
+    return 11 + (d.next ? 1 : 0);
 }
 
 // skip_if_n (device, optional): the three kernels return at once when *skip_if_n == n (nothing to compact)

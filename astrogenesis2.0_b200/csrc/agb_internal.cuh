@@ -52,7 +52,8 @@ struct AgbDev {
     int32_t* grouplist = nullptr;
     int32_t* gasrank = nullptr;        // exclusive count of gas particles before tree position i
     // scratch
-    double4* rec = nullptr;            // caller order: (x, y, z, |x|) packed by the extent pass
+    double4* rec = nullptr;            // caller order: (x, y, z, mass) packed by the extent pass
+    double4* grec = nullptr;           // caller order, gas only: (vx, vy, vz, U), (mu, rho, P, T) packed before the gather
     uint32_t* blockhist = nullptr;     // radix sort: [256][nblocks]
     int32_t* scanblk = nullptr;
     // per-target counters (optional)
@@ -79,6 +80,9 @@ struct AgbScalars {
     int32_t bintotal[256];
     int32_t vis_level;
     int32_t walk_overflow, any_gas;
+    int32_t next_uniform;              // every particle has the same nextIntegrationTime (fixed-step runs): the gather skips that column
+    unsigned int grid_bar;             // arrival counter of the level-synchronous upward pass
+    int32_t lvl_cnt[48], lvl_cur[48];  // internal nodes per depth, fill cursors of the level lists
     int32_t node_overflow;             // the build needed more than ncap nodes: nothing past the capacity was written, the host grows and rebuilds
     int32_t n_gas_total, tie_exact, tie_unresolved, n_fold, n_long_runs, n_scan_tmp;
     unsigned long long st_rounds, st_popped, st_mixed, st_open, st_drain;   // walk statistics (tuning)

@@ -36,8 +36,12 @@
 
 namespace {
 
-constexpr int LCAP = 512;                  // interaction-list entries per warp
+#ifndef AGB_WALK_LCAP
+#define AGB_WALK_LCAP 512
+#endif
+constexpr int LCAP = AGB_WALK_LCAP;        // interaction-list entries per warp
 constexpr int LGROW = 288;                 // worst-case growth per pop round: 32 lanes x (8 leaves + 1 node)
+constexpr int PCAP = 64;                   // straddling nodes waiting for their per-target tests (< 32 left over + 32 new)
 #ifndef AGB_WALK_CTAS_PER_SM
 #define AGB_WALK_CTAS_PER_SM 2
 #endif
@@ -59,7 +63,9 @@ template <bool SPH, bool MIXED> struct WarpSmem : SphSmem<SPH && !MIXED> {
     int2 rsrc[SPH && MIXED ? 64 : 2];      // SPLIT: (source, gas targets that accepted it) waiting for the next k_sph record
     int2 list[LCAP];
     int2 stack[SCAP];
-    double4 stage[32];                     // drain: the 32 sources of a tile; traversal: FP32 records of straddling nodes
+    int2 pend[PCAP];                       // (node, lane mask) of straddling nodes, resolved 32 at a time (one node per lane, loop over targets)
+    float4 tpos[32];                       // minus the targets' positions about the box centre (units of L) + their tree positions
+    double4 stage[32];                     // drain: the 32 sources of a tile
 };
 // k_sph: per gas target (1/h, 1/(pi h^4), 2 P/rho^2, sound speed), (vx, vy, vz, h), 8 floats: -(float-float position), (2h/L)^2, tree position
 struct SphWarp {
@@ -404,7 +410,8 @@ __global__ void __launch_bounds__(WalkCfg<SPH>::TPB, WALK_CTAS) k_walk(const Wal
             const int n_fl = P.far_cnt[3 * sgi], n_ff = P.far_cnt[3 * sgi + 1];
             if (COUNT && valid) c_vis += P.far_cnt[3 * sgi + 2];
             if (COUNT) st_cls[6] += n_fl;
-            int sp = n_ff, lc = 0, cpos = 0;
+            int sp = n_ff, lc = 0, cpos = 0, npend = 0;
+            sm.tpos[lane] = make_float4(ntx, nty, ntz, __int_as_float((int)t));
             for (int i = lane; i < n_ff; i += 32) stack_put(i, make_int2(ff[i], (int)vmask));
             __syncwarp();
 
@@ -417,55 +424,70 @@ __global__ void __launch_bounds__(WalkCfg<SPH>::TPB, WALK_CTAS) k_walk(const Wal
                     __syncwarp();
                 } else
                 // ------------------------------------------------ traversal: fill the interaction list
-                while (sp > 0 && lc <= LCAP - LGROW) {
-                    const int cnt = min(sp, 32);
-                    sp -= cnt;
+                // Two kinds of rounds feed one common "append / push" phase.  POP: every lane pops one (node, mask) entry and
+                // classifies it against the warp's box; nodes the whole mask accepts or opens are finished, straddling nodes are
+                // parked in sm.pend.  RESOLVE (32 nodes parked, or nothing left to pop): one parked node per LANE, loop over the
+                // 32 TARGETS (their positions are broadcast from shared memory): the accept / open bits of a node accumulate in
+                // its own lane's registers — no ballots, no shuffles, 32 (node, target) tests per ~16 instructions.
+                while ((sp > 0 || npend > 0) && lc <= LCAP - LGROW) {
                     int2 e = make_int2(-1, 0);
-                    if (lane < cnt) e = stack_get(sp + lane);
-                    __syncwarp();                                            // the slots just read are overwritten by this round's pushes
-                    if (sp + cnt > SCAP) tot_spill += 1;
-                    int outcome = OUT_NONE;
-                    double rad2 = 0, pmx = 0, pmy = 0, pmz = 0;
-                    // the child slots are requested together with the node record (two independent L2 round trips instead
-                    // of two dependent ones); they are simply not used when the node turns out to be accepted
+                    unsigned amask = 0u, omask = 0u;                         // lanes of the entry's mask that accept the node / open it
                     int4 c0 = make_int4(-1, -1, -1, -1), c1 = c0;
-                    if (lane < cnt && e.x >= 0) {
-                        c0 = __ldg(reinterpret_cast<const int4*>(P.child) + 2 * (size_t)(e.x - N));
-                        c1 = __ldg(reinterpret_cast<const int4*>(P.child) + 2 * (size_t)(e.x - N) + 1);
-                        const double4 pm = P.src_pm[e.x];
-                        pmx = pm.x; pmy = pm.y; pmz = pm.z;
-                        if (pm.w != 0.0) {                                       // Node.cpp:250 / :390
-                            const double rad = scalbn(R, -(int)P.ndepth[e.x - N]);
-                            rad2 = rad * rad;
-                            outcome = classify_box(pm, rad2, wb, theta2, fast_mac);
+                    if (npend < 32 && sp > 0) {
+                        const int cnt = min(sp, 32);
+                        sp -= cnt;
+                        if (lane < cnt) e = stack_get(sp + lane);
+                        __syncwarp();                                        // the slots just read are overwritten by this round's pushes
+                        if (sp + cnt > SCAP) tot_spill += 1;
+                        int outcome = OUT_NONE;
+                        // the child slots are requested together with the node record (two independent L2 round trips instead
+                        // of two dependent ones); they are simply not used when the node turns out to be accepted
+                        if (lane < cnt && e.x >= 0) {
+                            c0 = __ldg(reinterpret_cast<const int4*>(P.child) + 2 * (size_t)(e.x - N));
+                            c1 = __ldg(reinterpret_cast<const int4*>(P.child) + 2 * (size_t)(e.x - N) + 1);
+                            const double4 pm = P.src_pm[e.x];
+                            if (pm.w != 0.0) {                                   // Node.cpp:250 / :390
+                                const double rad = scalbn(R, -(int)P.ndepth[e.x - N]);
+                                outcome = classify_box(pm, rad * rad, wb, theta2, fast_mac);
+                            }
                         }
-                    }
-                    if (COUNT) {
-                        const unsigned vm = (outcome != OUT_NONE && e.x != N) ? (unsigned)e.y : 0u;
-                        for (int j = 0; j < cnt; j++) c_vis += (__shfl_sync(0xffffffffu, vm, j) >> lane) & 1u;
-                    }
-                    // lanes of the entry's mask that accept the node / open it
-                    unsigned amask = outcome == OUT_ACCEPT ? (unsigned)e.y : 0u, omask = outcome == OUT_OPEN ? (unsigned)e.y : 0u;
-                    // straddling nodes: per-lane test, one node at a time; (COM, radius^2) parked in shared memory by the owners
-                    unsigned mm = __ballot_sync(0xffffffffu, outcome == OUT_MIXED);
-                    if (lane == 0) { st_rounds++; st_popped += cnt; st_mixed += __popc(mm); }
-                    if (mm) {
-                        // Per-lane tests in FP32 first: the node's position about the box centre (units of L) and two thresholds on r^2
-                        // that bracket radius^2 / theta^2 by +-4e-5.  With |d| > half-diagonal / 16 (the guard) the FP32 r^2 is within
-                        // 7e-6 of the true one, so an FP32 verdict outside the bracket is the FP64 verdict; everything else (inside
-                        // the bracket, too close to the node, theta <= 0) is re-decided in FP64 exactly as before.
-                        if (outcome == OUT_MIXED) {
-                            const double thr = rad2 * invR2 * inv_theta2;
-                            float4* st = reinterpret_cast<float4*>(&sm.stage[lane]);
-                            st[0] = make_float4((float)((pmx - cgx) * invR), (float)((pmy - cgy) * invR), (float)((pmz - cgz) * invR), fmaxf((float)(thr * (1.0 + 4e-5)), guard2));
-                            st[1] = make_float4((float)(thr * (1.0 - 4e-5)), __int_as_float(e.x), 0.f, 0.f);
+                        if (COUNT) {
+                            const unsigned vm = (outcome != OUT_NONE && e.x != N) ? (unsigned)e.y : 0u;
+                            for (int j = 0; j < cnt; j++) c_vis += (__shfl_sync(0xffffffffu, vm, j) >> lane) & 1u;
+                        }
+                        if (outcome == OUT_ACCEPT) amask = (unsigned)e.y;
+                        if (outcome == OUT_OPEN) omask = (unsigned)e.y;
+                        const unsigned mm = __ballot_sync(0xffffffffu, outcome == OUT_MIXED);
+                        if (outcome == OUT_MIXED) sm.pend[npend + __popc(mm & lt)] = e;
+                        npend += __popc(mm);
+                        if (lane == 0) { st_rounds++; st_popped += cnt; st_mixed += __popc(mm); }
+                    } else {
+                        // ---- resolve up to 32 parked nodes (the most recent ones)
+                        const int nb = min(npend, 32);
+                        npend -= nb;
+                        float nx = 0.f, ny = 0.f, nz = 0.f, thi = 0.f, tlo = 0.f;
+                        unsigned my = 0u;
+                        if (lane < nb) {
+                            e = sm.pend[npend + lane];
+                            my = (unsigned)e.y;
+                            c0 = __ldg(reinterpret_cast<const int4*>(P.child) + 2 * (size_t)(e.x - N));
+                            c1 = __ldg(reinterpret_cast<const int4*>(P.child) + 2 * (size_t)(e.x - N) + 1);
+                            // Per-target tests in FP32 first: the node's position about the box centre (units of L) and two thresholds on
+                            // r^2 that bracket radius^2 / theta^2 by +-4e-5.  With |d| > half-diagonal / 16 (the guard) the FP32 r^2 is
+                            // within 7e-6 of the true one, so an FP32 verdict outside the bracket is the FP64 verdict; everything else
+                            // (inside the bracket, too close to the node, theta <= 0) is re-decided in FP64.
+                            const double4 pm = P.src_pm[e.x];
+                            const double rad = scalbn(R, -(int)P.ndepth[e.x - N]);
+                            const double thr = rad * rad * invR2 * inv_theta2;
+                            nx = (float)((pm.x - cgx) * invR); ny = (float)((pm.y - cgy) * invR); nz = (float)((pm.z - cgz) * invR);
+                            thi = fmaxf((float)(thr * (1.0 + 4e-5)), guard2);
+                            tlo = (float)(thr * (1.0 - 4e-5));
                         }
                         __syncwarp();
-                        const unsigned my = (unsigned)e.y;
-                        auto exact_mac = [&](const int node, bool& acc, bool& open) {
-                            const double4 q = P.src_pm[node];
+                        auto exact_mac = [&](const int node, const int tidx, bool& acc, bool& open) {
+                            const double4 q = P.src_pm[node], tq = P.src_pm[tidx];
                             const double rad = scalbn(R, -(int)P.ndepth[node - N]), qw = rad * rad;
-                            const double dx = q.x - tp.x, dy = q.y - tp.y, dz = q.z - tp.z;
+                            const double dx = q.x - tq.x, dy = q.y - tq.y, dz = q.z - tq.z;
                             const double r2 = fma(dz, dz, fma(dy, dy, dx * dx)), lhs = r2 * theta2;
                             acc = false; open = false;
                             if (r2 != 0.0) {                                         // Node.cpp:274 (r == 0 -> return)
@@ -479,32 +501,26 @@ __global__ void __launch_bounds__(WalkCfg<SPH>::TPB, WALK_CTAS) k_walk(const Wal
                                 }
                             }
                         };
-                        // two nodes per iteration: their dependency chains interleave
-                        do {
-                            const int src0 = __ffs(mm) - 1;
-                            mm &= mm - 1;
-                            const int src1 = mm ? __ffs(mm) - 1 : src0;
-                            const bool two = mm != 0u;
-                            mm &= mm - 1;
-                            const unsigned nmask0 = __shfl_sync(0xffffffffu, my, src0), nmask1 = __shfl_sync(0xffffffffu, my, src1);
-                            const float4* s0 = reinterpret_cast<const float4*>(&sm.stage[src0]);
-                            const float4* s1 = reinterpret_cast<const float4*>(&sm.stage[src1]);
-                            const float4 a0_ = s0[0], b0_ = s0[1], a1_ = s1[0], b1_ = s1[1];
-                            const float dx0 = a0_.x + ntx, dy0 = a0_.y + nty, dz0 = a0_.z + ntz, dx1 = a1_.x + ntx, dy1 = a1_.y + nty, dz1 = a1_.z + ntz;
-                            const float r20 = fmaf(dz0, dz0, fmaf(dy0, dy0, dx0 * dx0)), r21 = fmaf(dz1, dz1, fmaf(dy1, dy1, dx1 * dx1));
-                            const bool in0 = (nmask0 >> lane) & 1u, in1 = two && ((nmask1 >> lane) & 1u);
-                            bool acc0 = in0 && fast_mac && r20 > a0_.w, open0 = in0 && fast_mac && r20 < b0_.x && r20 > guard2;
-                            bool acc1 = in1 && fast_mac && r21 > a1_.w, open1 = in1 && fast_mac && r21 < b1_.x && r21 > guard2;
-                            const bool ex0 = in0 && !acc0 && !open0, ex1 = in1 && !acc1 && !open1;
-                            if (ex0 || ex1) {
-                                if (ex0) exact_mac(__float_as_int(b0_.y), acc0, open0);
-                                if (ex1) exact_mac(__float_as_int(b1_.y), acc1, open1);
-                            }
-                            const unsigned a0 = __ballot_sync(0xffffffffu, acc0), o0 = __ballot_sync(0xffffffffu, open0);
-                            const unsigned a1 = __ballot_sync(0xffffffffu, acc1), o1 = __ballot_sync(0xffffffffu, open1);
-                            if (lane == src0) { amask = a0; omask = o0; }
-                            if (two && lane == src1) { amask = a1; omask = o1; }
-                        } while (mm);
+                        unsigned amb = 0u;
+#pragma unroll 4
+                        for (int t = 0; t < 32; t++) {
+                            const float4 tq = sm.tpos[t];                            // broadcast
+                            const float dx = nx + tq.x, dy = ny + tq.y, dz = nz + tq.z;
+                            const float r2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+                            const bool in = (my >> t) & 1u;
+                            const bool acc = in && fast_mac && r2 > thi, open = in && fast_mac && r2 < tlo && r2 > guard2;
+                            amask |= acc ? 1u << t : 0u;
+                            omask |= open ? 1u << t : 0u;
+                            amb |= (in && !acc && !open) ? 1u << t : 0u;
+                        }
+                        while (amb) {                                                // rare: decided in FP64 (one copy of the code, lanes diverge)
+                            const int t = __ffs(amb) - 1;
+                            amb &= amb - 1;
+                            bool acc, open;
+                            exact_mac(e.x, __float_as_int(sm.tpos[t].w), acc, open);
+                            amask |= acc ? 1u << t : 0u;
+                            omask |= open ? 1u << t : 0u;
+                        }
                     }
                     // one list entry per node with acceptors
                     const unsigned am = __ballot_sync(0xffffffffu, amask != 0u);
@@ -535,8 +551,8 @@ __global__ void __launch_bounds__(WalkCfg<SPH>::TPB, WALK_CTAS) k_walk(const Wal
                     __syncwarp();
                     // warm L1 with the node records the next round will pop
                     if (lane < sp && lane < 32) {
-                        const int2 nx = stack_get(sp - 1 - lane);
-                        if (nx.x >= 0) asm volatile("prefetch.global.L1 [%0];" ::"l"(P.src_pm + nx.x));
+                        const int2 nx_ = stack_get(sp - 1 - lane);
+                        if (nx_.x >= 0) asm volatile("prefetch.global.L1 [%0];" ::"l"(P.src_pm + nx_.x));
                     }
                 }
 
@@ -755,7 +771,7 @@ __global__ void __launch_bounds__(WalkCfg<SPH>::TPB, WALK_CTAS) k_walk(const Wal
                 }
                 lc = 0;
                 __syncwarp();                                                // the list is rewritten by the next import / round
-                if (sp == 0 && cpos >= n_fl) break;
+                if (sp == 0 && npend == 0 && cpos >= n_fl) break;
             }
         }
         if (SPLIT) { rec_flush(false); if (lane == 0) P.rec_head[g] = rec_last; }
