@@ -17,8 +17,11 @@ struct agb_ctx {
     int device = 0, sm_count = 148;
     cudaStream_t st = nullptr, st_copy = nullptr;   // compute stream; upload stream for everything but x, y, z
     cudaEvent_t ev_in = nullptr;                      // uploads on st_copy complete
+    cudaEvent_t ev_next = nullptr;                    // ... their first group (next_time and the carried acc / dUdt / h / rho): all the build, the densities and the gravity walk read
     cudaEvent_t ev_sync = nullptr;                    // compute stream reached the point of a new hand-over (orders st_copy after it)
-    bool in_pending = false;
+    cudaEvent_t ev_pos = nullptr;                     // x, y, z, mass, type are on the device (st): the other uploads start after them (they would share the link)
+    bool in_pending = false, next_pending = false;
+    cudaEvent_t evw[5] = {};                          // walk timing: before k_far, before k_walk, after k_walk, after k_sph, before k_sph
     cudaEvent_t ev[10] = {};
     cudaEvent_t evk[10] = {};                         // kernel-level timing: walk [0..3] = before k_far, k_walk, k_sph, after; build [4..9] = start, keys, sort, gather, links, end
     double kernel_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // k_far k_walk k_sph | extent+keys sort gather lcp+scan+links upward+finalize
@@ -70,7 +73,7 @@ void free_nodes(agb_ctx* c)
     AgbDev& d = c->d;
     dfree(d.src_pm); dfree(d.src_gv); dfree(d.src_flag);
     dfree(d.child); dfree(d.nfirst); dfree(d.nlast); dfree(d.nparent); dfree(d.arrived); dfree(d.ndepth);
-    dfree(d.nmark); dfree(d.ndup); dfree(d.mom_pm); dfree(d.mom_gv); dfree(d.grouplist);
+    dfree(d.nmark); dfree(d.ndup); dfree(d.mom_pm); dfree(d.mom_gv); dfree(d.grouplist); dfree(d.lvl_list);
     dfree(d.klo[0]); dfree(d.nodebase);
     d.ncap = 0;
 }
@@ -103,7 +106,7 @@ int ensure_nodes(agb_ctx* c, int64_t want)
     const size_t nc = (size_t)want, cap = (size_t)d.cap;
     CK(dalloc(d.src_pm, cap + nc)); CK(dalloc(d.src_gv, cap + nc)); CK(dalloc(d.src_flag, cap + nc));
     CK(dalloc(d.child, 8 * nc)); CK(dalloc(d.nfirst, nc)); CK(dalloc(d.nlast, nc)); CK(dalloc(d.nparent, nc)); CK(dalloc(d.arrived, nc)); CK(dalloc(d.ndepth, nc));
-    CK(dalloc(d.nmark, nc)); CK(dalloc(d.ndup, nc)); CK(dalloc(d.mom_pm, nc)); CK(dalloc(d.mom_gv, nc)); CK(dalloc(d.grouplist, nc));
+    CK(dalloc(d.nmark, nc)); CK(dalloc(d.ndup, nc)); CK(dalloc(d.mom_pm, nc)); CK(dalloc(d.mom_gv, nc)); CK(dalloc(d.grouplist, nc)); CK(dalloc(d.lvl_list, nc));
     CK(dalloc(d.klo[0], nc)); CK(dalloc(d.nodebase, nc));     // per particle in the build, per node (exact sums, fold list) in the density pass
     d.ncap = (int64_t)nc;
     return AGB_OK;
@@ -242,6 +245,9 @@ static void destroy_handles(agb_ctx* c)
     if (c->ev_in) cudaEventDestroy(c->ev_in);
     if (c->ev_out) cudaEventDestroy(c->ev_out);
     if (c->ev_sync) cudaEventDestroy(c->ev_sync);
+    if (c->ev_next) cudaEventDestroy(c->ev_next);
+    if (c->ev_pos) cudaEventDestroy(c->ev_pos);
+    for (auto& e : c->evw) if (e) cudaEventDestroy(e);
     for (auto& e : c->ev) if (e) cudaEventDestroy(e);
     for (auto& e : c->evk) if (e) cudaEventDestroy(e);
     if (c->st_copy) cudaStreamDestroy(c->st_copy);
@@ -271,7 +277,9 @@ int agb_create(agb_ctx** out, int device, int compat_cores)
     if (cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking) != cudaSuccess) return fail(AGB_ERR_NO_DEVICE);
     if (cudaStreamCreateWithFlags(&c->st_copy, cudaStreamNonBlocking) != cudaSuccess) return fail(AGB_ERR_NO_DEVICE);
     if (cudaEventCreateWithFlags(&c->ev_in, cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&c->ev_out, cudaEventDisableTiming) != cudaSuccess ||
-        cudaEventCreateWithFlags(&c->ev_sync, cudaEventDisableTiming) != cudaSuccess) return fail(AGB_ERR_NO_DEVICE);
+        cudaEventCreateWithFlags(&c->ev_sync, cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&c->ev_next, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c->ev_pos, cudaEventDisableTiming) != cudaSuccess) return fail(AGB_ERR_NO_DEVICE);
+    for (auto& e : c->evw) if (cudaEventCreate(&e) != cudaSuccess) return fail(AGB_ERR_NO_DEVICE);
     for (auto& e : c->ev) if (cudaEventCreate(&e) != cudaSuccess) return fail(AGB_ERR_NO_DEVICE);
     for (auto& e : c->evk) if (cudaEventCreate(&e) != cudaSuccess) return fail(AGB_ERR_NO_DEVICE);
     if (cudaMalloc((void**)&c->s, sizeof(AgbScalars)) != cudaSuccess) return fail(AGB_ERR_NOMEM);
@@ -325,18 +333,27 @@ int agb_set_particles(agb_ctx* c, const agb_particles* p, int memspace)
         if ((rc = own_input(c, d.x, 0, p->x, n)) || (rc = own_input(c, d.y, 1, p->y, n)) || (rc = own_input(c, d.z, 2, p->z, n)) ||
             (rc = own_input(c, d.mass, 6, p->mass, n))) return rc;
         CK(cudaMemcpyAsync(c->in_type, p->type, (size_t)n, cudaMemcpyHostToDevice, c->st));   // needed by the key pass
-        if ((rc = own_input(c, d.next, 8, p->next_time, n)) ||
-            (rc = own_input(c, d.vx, 3, p->vx, n)) || (rc = own_input(c, d.vy, 4, p->vy, n)) || (rc = own_input(c, d.vz, 5, p->vz, n)) ||
-            (rc = own_input(c, d.U, 7, p->U, n)) || (rc = own_input(c, d.mu, 9, p->mu, n))) return rc;
+        // the build starts as soon as these have landed; everything else follows on the copy stream, in the order the path
+        // needs it, and only AFTER them (two concurrent host-to-device streams would share the link and delay the positions)
+        CK(cudaEventRecord(c->ev_pos, c->st));
+        CK(cudaStreamWaitEvent(c->st_copy, c->ev_pos, 0));
+        if ((rc = own_input(c, d.next, 8, p->next_time, n))) return rc;
         d.type = c->in_type;
         c->bound = false;
     }
+    // first group: what the gather, the densities and the gravity walk read or write (active flags, carried acc / dUdt / h / rho)
     if ((rc = put_array(c, d.ax, p->ax, n, memspace)) || (rc = put_array(c, d.ay, p->ay, n, memspace)) || (rc = put_array(c, d.az, p->az, n, memspace)) ||
-        (rc = put_array(c, d.dUdt, p->dUdt, n, memspace)) || (rc = put_array(c, d.h, p->h, n, memspace)) || (rc = put_array(c, d.rho, p->rho, n, memspace)) ||
-        (rc = put_array(c, d.P, p->P, n, memspace)) || (rc = put_array(c, d.T, p->T, n, memspace))) return rc;
+        (rc = put_array(c, d.dUdt, p->dUdt, n, memspace)) || (rc = put_array(c, d.h, p->h, n, memspace)) || (rc = put_array(c, d.rho, p->rho, n, memspace))) return rc;
     CK(cudaMemsetAsync(d.vis, 0, (size_t)std::max<int64_t>(n, 1) * sizeof(double), c->st_copy));
+    CK(cudaEventRecord(c->ev_next, c->st_copy));
+    // second group: only the SPH pair pass (and P, T of the density groups) needs these
+    if (memspace != AGB_MEM_DEVICE) {
+        if ((rc = own_input(c, d.vx, 3, p->vx, n)) || (rc = own_input(c, d.vy, 4, p->vy, n)) || (rc = own_input(c, d.vz, 5, p->vz, n)) ||
+            (rc = own_input(c, d.U, 7, p->U, n)) || (rc = own_input(c, d.mu, 9, p->mu, n))) return rc;
+    }
+    if ((rc = put_array(c, d.P, p->P, n, memspace)) || (rc = put_array(c, d.T, p->T, n, memspace))) return rc;
     CK(cudaEventRecord(c->ev_in, c->st_copy));
-    c->in_pending = true;
+    c->in_pending = true; c->next_pending = true;
     // Host arrays are read asynchronously (pinned memory makes that a true overlap): like the reference, which reads
     // Simulation::particles during buildTree, they must stay untouched until agb_build_tree has returned.
     c->have_particles = true; c->built = false; c->dens_done = false; c->forces_done = false; c->counters_valid = false;
@@ -386,7 +403,9 @@ int agb_set_particles_aos(agb_ctx* c, void* const* parts, int64_t n, const agb_a
 }
 
 // the kernels of Tree::buildTree on the context's stream (no synchronisation)
-static void launch_build(agb_ctx* c)
+// late_gas (agb_force_path, host hand-over, mixed precision, gas): the build only waits for the first upload group; the
+// tree's gas velocities are completed by launch_late_gas once the second group is there
+static void launch_build(agb_ctx* c, bool late_gas = false)
 {
     AgbDev& d = c->d;
     cudaEventRecord(c->evk[4], c->st);
@@ -395,8 +414,9 @@ static void launch_build(agb_ctx* c)
     cudaEventRecord(c->evk[5], c->st);
     c->launches += agb_launch_sort(d, c->s, c->st);
     cudaEventRecord(c->evk[6], c->st);
-    if (c->in_pending) { cudaStreamWaitEvent(c->st, c->ev_in, 0); c->in_pending = false; }
-    c->launches += agb_launch_links(d, c->s, c->st, &c->evk[7]);
+    if (late_gas) { if (c->next_pending) { cudaStreamWaitEvent(c->st, c->ev_next, 0); c->next_pending = false; } }
+    else if (c->in_pending) { cudaStreamWaitEvent(c->st, c->ev_in, 0); c->in_pending = false; c->next_pending = false; }
+    c->launches += agb_launch_links(d, c->s, c->st, &c->evk[7], late_gas);
     cudaEventRecord(c->evk[9], c->st);
     c->build_timed = true;
 }
@@ -447,21 +467,29 @@ int agb_visual_density(agb_ctx* c, double radius)
     return stream_out(c, 8, 8);
 }
 
-int agb_gas_density(agb_ctx* c, double mass_in_h)
+static int gas_density_impl(agb_ctx* c, double mass_in_h, bool late_pt);
+int agb_gas_density(agb_ctx* c, double mass_in_h) { return gas_density_impl(c, mass_in_h, false); }
+
+static int gas_density_impl(agb_ctx* c, double mass_in_h, bool late_pt)
 {
     if (!c || !c->built) return AGB_ERR_INVALID;
     CK(cudaSetDevice(c->device));
     c->dens_done = true;
     if (c->d.n == 0) return AGB_OK;
     CK(cudaEventRecord(c->ev[4], c->st));
-    if (c->hs.any_gas) c->launches += agb_launch_gas_density(c->d, c->s, mass_in_h, c->st);
+    if (c->hs.any_gas) c->launches += agb_launch_gas_density(c->d, c->s, mass_in_h, c->st, late_pt);
     CK(cudaEventRecord(c->ev[5], c->st));
     c->gas_timed = true;
     CK(cudaGetLastError());
-    return stream_out(c, 4, 7);
+    return stream_out(c, 4, late_pt ? 5 : 7);                // P and T follow after the late part of the build
 }
 
-int agb_forces_slice(agb_ctx* c, double global_time, double e0, double theta, int part, int nparts)
+static int forces_impl(agb_ctx* c, double global_time, double e0, double theta, int part, int nparts, bool late_gas);
+int agb_forces_slice(agb_ctx* c, double global_time, double e0, double theta, int part, int nparts) { return forces_impl(c, global_time, e0, theta, part, nparts, false); }
+
+// late_gas: the tree was built without the gas velocities / U / mu (launch_build(c, true)); they are folded in between the
+// gravity walk and the SPH pair pass, by which time their upload has long finished
+static int forces_impl(agb_ctx* c, double global_time, double e0, double theta, int part, int nparts, bool late_gas)
 {
     if (!c || !c->built || nparts < 1 || part < 0 || part >= nparts) return AGB_ERR_INVALID;
     // For e0 <= 2.1474836e13 the reference's `abs(e)` (int abs(int), Node.cpp:302,354) can switch to the spline
@@ -479,7 +507,17 @@ int agb_forces_slice(agb_ctx* c, double global_time, double e0, double theta, in
     // gas targets need h/rho/P: if the caller skipped gas_density they are orphans (h = 0) and get no SPH, like the reference
     const bool any_gas = c->hs.any_gas != 0;
     for (int attempt = 0;; attempt++) {
-        c->launches += agb_launch_walk(d, c->s, global_time, e0, theta, part, nparts, c->target_counters, any_gas, c->mixed, c->sm_count, c->st, c->evk);
+        if (late_gas) {
+            c->launches += agb_launch_walk(d, c->s, global_time, e0, theta, part, nparts, c->target_counters, any_gas, c->mixed, c->sm_count, c->st, c->evw, 1);
+            if (attempt == 0) {
+                if (c->in_pending) { CK(cudaStreamWaitEvent(c->st, c->ev_in, 0)); c->in_pending = false; }
+                c->launches += agb_launch_late_gas(d, c->s, c->st);
+                int rc = stream_out(c, 6, 7);
+                if (rc) return rc;
+            }
+            c->launches += agb_launch_walk(d, c->s, global_time, e0, theta, part, nparts, c->target_counters, any_gas, c->mixed, c->sm_count, c->st, c->evw, 2);
+        } else
+            c->launches += agb_launch_walk(d, c->s, global_time, e0, theta, part, nparts, c->target_counters, any_gas, c->mixed, c->sm_count, c->st, c->evw, 0);
         CK(cudaEventRecord(c->ev[7], c->st));
         CK(cudaGetLastError());
         int rc = fetch_scalars(c);
@@ -490,9 +528,10 @@ int agb_forces_slice(agb_ctx* c, double global_time, double e0, double theta, in
         if (rc) return rc;
     }
     float ms = 0;
-    if (cudaEventElapsedTime(&ms, c->evk[0], c->evk[3]) == cudaSuccess) c->phase_ms[3] = ms;
+    if (cudaEventElapsedTime(&ms, c->evw[0], c->evw[3]) == cudaSuccess) c->phase_ms[3] = ms;
     if (cudaEventElapsedTime(&ms, c->ev[6], c->ev[7]) == cudaSuccess) c->phase_ms[4] = ms;
-    for (int k = 0; k < 3; k++) if (cudaEventElapsedTime(&ms, c->evk[k], c->evk[k + 1]) == cudaSuccess) c->kernel_ms[k] = ms;
+    for (int k = 0; k < 2; k++) if (cudaEventElapsedTime(&ms, c->evw[k], c->evw[k + 1]) == cudaSuccess) c->kernel_ms[k] = ms;
+    if (cudaEventElapsedTime(&ms, c->evw[4], c->evw[3]) == cudaSuccess) c->kernel_ms[2] = ms;
     if (c->build_timed) for (int k = 0; k < 5; k++) if (cudaEventElapsedTime(&ms, c->evk[4 + k], c->evk[5 + k]) == cudaSuccess) c->kernel_ms[3 + k] = ms;
     if (c->vis_timed && cudaEventElapsedTime(&ms, c->ev[2], c->ev[3]) == cudaSuccess) c->phase_ms[1] = ms;
     if (c->gas_timed && cudaEventElapsedTime(&ms, c->ev[4], c->ev[5]) == cudaSuccess) c->phase_ms[2] = ms;
@@ -527,16 +566,20 @@ int agb_force_path(agb_ctx* c, double visual_density_radius, double mass_in_h, d
     CK(cudaSetDevice(c->device));
     AgbDev& d = c->d;
     c->built = false; c->dens_done = false; c->forces_done = false; c->counters_valid = false;
+    // Host hand-over still uploading (set_particles is asynchronous): in mixed precision only the SPH pair pass needs the gas
+    // velocities / U / mu, so the build, the densities and the gravity walk start on the first upload group and the rest of
+    // the transfer hides behind them.
+    const bool late_gas = c->in_pending && !c->bound && c->mixed && c->gas_hint;
     CK(cudaEventRecord(c->ev[8], c->st));
-    launch_build(c);
+    launch_build(c, late_gas);
     CK(cudaEventRecord(c->ev[9], c->st));
     CK(cudaGetLastError());
     c->built = true;
     c->hs.any_gas = c->gas_hint ? 1 : 0;
     int rc;
     if ((rc = agb_visual_density(c, visual_density_radius))) return rc;
-    if ((rc = agb_gas_density(c, mass_in_h))) return rc;
-    rc = agb_forces_slice(c, global_time, e0, theta, part, nparts);          // ends with the step's only synchronisation
+    if ((rc = gas_density_impl(c, mass_in_h, late_gas))) return rc;
+    rc = forces_impl(c, global_time, e0, theta, part, nparts, late_gas);     // ends with the step's only synchronisation
     float ms = 0; if (cudaEventElapsedTime(&ms, c->ev[8], c->ev[9]) == cudaSuccess) c->phase_ms[0] = ms;
     (void)cudaGetLastError();
     c->hs.R = 0; memcpy(&c->hs.R, &c->hs.Rbits, 8);

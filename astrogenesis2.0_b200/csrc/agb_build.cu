@@ -87,7 +87,7 @@ __global__ void k_extent_finish(AgbScalars* s, int nblocks, int64_t n)
     s->limit = __dadd_rn(mean, __dmul_rn(10.0, sd));     // Tree.cpp:89,105
     s->Rbits = 0ull;
     s->n_long_runs = 0; s->any_gas = 0; s->n_outliers = 0; s->dup_keys = 0; s->edge_dropped = 0; s->max_depth = 0; s->n_nodes = 0; s->node_overflow = 0;
-    s->next_uniform = 1; s->grid_bar = 0u;
+    s->next_uniform = 1; s->grid_bar = 0u; s->grid_bar2 = 0u;
     for (int k = 0; k < 48; k++) { s->lvl_cnt[k] = 0; s->lvl_cur[k] = 0; }
 }
 
@@ -410,6 +410,9 @@ __global__ void __launch_bounds__(TPB) k_pack_gas(AgbDev d)
     d.grec[2 * i + 1] = make_double4(d.mu ? d.mu[i] : 0.58, d.rho[i], d.P[i], d.T[i]);
 }
 
+// LATE: the hand-over is still uploading velocities / U / mu (agb_force_path with host arrays): only what the build, the
+// densities and the gravity walk read is gathered here; k_gather_late fills in the rest once it has arrived.
+template <bool LATE>
 __global__ void __launch_bounds__(TPB) k_gather(AgbDev d, uint32_t* __restrict__ perm, AgbScalars* s)
 {
     int64_t i = (int64_t)blockIdx.x * TPB + threadIdx.x;
@@ -423,15 +426,18 @@ __global__ void __launch_bounds__(TPB) k_gather(AgbDev d, uint32_t* __restrict__
     d.s_type[i] = gas ? 2 : 1;                        // only "gas or not" matters on the path (Node.cpp:319,371,478,679,763)
     d.s_next[i] = !d.next ? 0.0 : s->next_uniform ? d.next[0] : d.next[p];
     if (gas) {
-        // velocity, U, mu and the carried h/rho/P/T are only ever read for gas (Node.cpp:88-172, :722-796)
-        const double4 g0 = d.grec[2 * (size_t)p], g1 = d.grec[2 * (size_t)p + 1];   // (vx, vy, vz, U), (mu, rho, P, T)
-        d.src_gv[i] = make_double4(g0.x, g0.y, g0.z, m);
         d.src_flag[i] = m > 0.0 ? 1 : 0;
         s->any_gas = 1;
-        d.s_U[i] = g0.w;
-        d.s_mu[i] = g1.x;
-        d.s_rho[i] = g1.y; d.s_P[i] = g1.z; d.s_T[i] = g1.w;
         d.s_h[i] = 0.0;                               // Tree.cpp:123-133 zeroes h of every gas particle
+        if (LATE) d.src_gv[i] = make_double4(0.0, 0.0, 0.0, m);
+        else {
+            // velocity, U, mu and the carried h/rho/P/T are only ever read for gas (Node.cpp:88-172, :722-796)
+            const double4 g0 = d.grec[2 * (size_t)p], g1 = d.grec[2 * (size_t)p + 1];   // (vx, vy, vz, U), (mu, rho, P, T)
+            d.src_gv[i] = make_double4(g0.x, g0.y, g0.z, m);
+            d.s_U[i] = g0.w;
+            d.s_mu[i] = g1.x;
+            d.s_rho[i] = g1.y; d.s_P[i] = g1.z; d.s_T[i] = g1.w;
+        }
     } else {
         d.src_gv[i] = make_double4(0.0, 0.0, 0.0, 0.0);
         d.src_flag[i] = 0;
@@ -440,6 +446,26 @@ __global__ void __launch_bounds__(TPB) k_gather(AgbDev d, uint32_t* __restrict__
     d.leafparent[i] = -1;
     d.leafdepth[i] = -1;
     d.leafmark[i] = 0;
+}
+
+// The rest of a LATE gather, after the gas densities: velocity, U, mu of the gas particles; P and T of the particles that
+// belong to a density group (Node.cpp:789-791, with the rho the group pass has just written), in tree and in caller order;
+// orphans keep the state they were handed over with.
+__global__ void __launch_bounds__(TPB) k_gather_late(AgbDev d, const uint32_t* __restrict__ perm, const AgbScalars* __restrict__ s)
+{
+    constexpr double kGAMMA = 5.0 / 3.0, kKB = 1.38064852e-23, kPRTN = 1.6726219e-27;   // Math/Constants.h:15-18
+    int64_t i = (int64_t)blockIdx.x * TPB + threadIdx.x;
+    if (i >= d.n || s->node_overflow || d.s_type[i] != 2) return;
+    const uint32_t p = perm[i];
+    const double4 g0 = d.grec[2 * (size_t)p], g1 = d.grec[2 * (size_t)p + 1];
+    d.src_gv[i] = make_double4(g0.x, g0.y, g0.z, d.src_pm[i].w);
+    d.s_U[i] = g0.w;
+    d.s_mu[i] = g1.x;
+    if (i < s->n_in_tree && d.group[i] >= 0) {
+        const double P = (kGAMMA - 1.0) * g0.w * d.s_rho[i], T = (kGAMMA - 1.0) * g0.w * kPRTN * g1.x / kKB;
+        d.s_P[i] = P; d.s_T[i] = T;
+        d.P[p] = P; d.T[p] = T;
+    } else { d.s_rho[i] = g1.y; d.s_P[i] = g1.z; d.s_T[i] = g1.w; }
 }
 
 // ------------------------------------------------------------------ shared levels of neighbours, node counts
@@ -656,12 +682,28 @@ __device__ __forceinline__ int count_node_children(const ChildLinks& L, int N)
     return (L.a.x >= N) + (L.a.y >= N) + (L.a.z >= N) + (L.a.w >= N) + (L.b.x >= N) + (L.b.y >= N) + (L.b.z >= N) + (L.b.w >= N);
 }
 
+// MODE 0: everything; MODE 1: mass moments and gasMass (velocities not there yet: mVel sums stay 0); MODE 2: the mVel sums alone,
+// with the same operations in the same order as MODE 0 (bit-identical).
+template <int MODE>
 __device__ __forceinline__ void node_moments(const AgbDev& d, int k, int N, bool any_gas, const ChildLinks& L)
 {
     double sx = 0, sy = 0, sz = 0, m = 0, gx = 0, gy = 0, gz = 0, g = 0;
     // the node's particle range ends where its last child's range ends (children are in key order)
     int last = -1;
     const int ch[8] = {L.a.x, L.a.y, L.a.z, L.a.w, L.b.x, L.b.y, L.b.z, L.b.w};
+    if (MODE == 2) {
+        const double4 own = ldcg4(&d.mom_gv[k]);
+        if (!(own.w > 0.0)) return;                     // no gas below this node: mVel stays 0
+#pragma unroll
+        for (int o = 0; o < 8; o++) {
+            const int c = ch[o];
+            if (c < 0) continue;
+            if (c < N) { const double4 gv = d.src_gv[c]; gx += gv.x * gv.w; gy += gv.y * gv.w; gz += gv.z * gv.w; }
+            else { const double4 gv = ldcg4(&d.mom_gv[c - N]); gx += gv.x; gy += gv.y; gz += gv.z; }
+        }
+        d.mom_gv[k] = make_double4(gx, gy, gz, own.w);
+        return;
+    }
     if (!any_gas) {
 #pragma unroll
         for (int o = 0; o < 8; o++) {
@@ -681,12 +723,14 @@ __device__ __forceinline__ void node_moments(const AgbDev& d, int k, int N, bool
         if (c < N) {
             double4 pm = d.src_pm[c], gv = d.src_gv[c];
             m += pm.w; sx += pm.x * pm.w; sy += pm.y * pm.w; sz += pm.z * pm.w;
-            g += gv.w; gx += gv.x * gv.w; gy += gv.y * gv.w; gz += gv.z * gv.w;
+            g += gv.w;
+            if (MODE == 0) { gx += gv.x * gv.w; gy += gv.y * gv.w; gz += gv.z * gv.w; }
             last = max(last, c);
         } else {
             double4 pm = ldcg4(&d.mom_pm[c - N]), gv = ldcg4(&d.mom_gv[c - N]);
             m += pm.w; sx += pm.x; sy += pm.y; sz += pm.z;
-            g += gv.w; gx += gv.x; gy += gv.y; gz += gv.z;
+            g += gv.w;
+            if (MODE == 0) { gx += gv.x; gy += gv.y; gz += gv.z; }
             last = max(last, __ldcg(&d.nlast[c - N]));
         }
     }
@@ -734,15 +778,18 @@ __device__ __forceinline__ void grid_sync(unsigned int* bar, unsigned int nblock
 // Upward pass, level by level from the deepest internal nodes to the root: one thread per node of the level, children of
 // deeper levels are complete (grid-wide barrier between levels; the grid is sized to be co-resident).  No atomics, no
 // fences per node, full warps.  Then the reference's root quirk and the normalisation (COM, mVel, duplication flags).
-__device__ __forceinline__ void root_fix_block(const AgbDev& d, const AgbScalars* s);
-__device__ __forceinline__ void finalize_node(const AgbDev& d, const AgbScalars* s, int k);
+template <int MODE> __device__ __forceinline__ void root_fix_block(const AgbDev& d, const AgbScalars* s);
+template <int MODE> __device__ __forceinline__ void finalize_node(const AgbDev& d, const AgbScalars* s, int k);
 
+template <int MODE>
 __global__ void __launch_bounds__(TPB) k_upward_levels(AgbDev d, AgbScalars* s, const int32_t* __restrict__ list)
 {
     const int nn = s->n_nodes;
     if (nn > d.ncap || nn < 1) return;
+    if (MODE == 2 && !s->any_gas) return;
     const int N = (int)d.n;
     const bool any_gas = s->any_gas != 0;
+    unsigned int* const bar = MODE == 2 ? &s->grid_bar2 : &s->grid_bar;
     unsigned int epoch = 0;
     int off_end = nn;                                         // list segment of depth `dep` is [off_end - cnt, off_end)
     int maxd = AGB_MAX_LEVELS;
@@ -753,18 +800,19 @@ __global__ void __launch_bounds__(TPB) k_upward_levels(AgbDev d, AgbScalars* s, 
         const int beg = off_end - cnt;
         for (int idx = beg + blockIdx.x * TPB + threadIdx.x; idx < off_end; idx += gridDim.x * TPB) {
             const int k = list[idx];
-            node_moments(d, k, N, any_gas, load_links(d.child, k));
+            node_moments<MODE>(d, k, N, any_gas, load_links(d.child, k));
         }
         off_end = beg;
-        if (cnt > 0 || dep == 0) grid_sync(&s->grid_bar, gridDim.x, epoch);
+        if (cnt > 0 || dep == 0) grid_sync(bar, gridDim.x, epoch);
     }
-    if (blockIdx.x == 0) root_fix_block(d, s);
-    grid_sync(&s->grid_bar, gridDim.x, epoch);
-    for (int k = blockIdx.x * TPB + threadIdx.x; k < nn; k += gridDim.x * TPB) finalize_node(d, s, k);
+    if (blockIdx.x == 0) root_fix_block<MODE>(d, s);
+    grid_sync(bar, gridDim.x, epoch);
+    for (int k = blockIdx.x * TPB + threadIdx.x; k < nn; k += gridDim.x * TPB) finalize_node<MODE>(d, s, k);
 }
 
 // Reference quirk: bulk insertion accumulates the ROOT's mass / COM / gasMass / mVel over ALL particles,
 // including those outside the cube that are never inserted (Node.cpp:477-499 precede the octant test).
+template <int MODE>
 __device__ __forceinline__ void root_fix_block(const AgbDev& d, const AgbScalars* s)
 {
     if (d.n < (int64_t)d.cores * 100) return;                  // one-by-one insertion rejects them at the root (Node.cpp:606-612)
@@ -785,19 +833,24 @@ __device__ __forceinline__ void root_fix_block(const AgbDev& d, const AgbScalars
         double t[8];
         for (int k = 0; k < 8; k++) { t[k] = 0; for (int w = 0; w < TPB / 32; w++) t[k] += sh[k][w]; }
         double4 pm = ldcg4(&d.mom_pm[0]), gv = s->any_gas ? ldcg4(&d.mom_gv[0]) : make_double4(0, 0, 0, 0);
-        pm.x += t[0]; pm.y += t[1]; pm.z += t[2]; pm.w += t[3];
-        gv.x += t[4]; gv.y += t[5]; gv.z += t[6]; gv.w += t[7];
-        d.mom_pm[0] = pm; d.mom_gv[0] = gv;
+        if (MODE != 2) { pm.x += t[0]; pm.y += t[1]; pm.z += t[2]; pm.w += t[3]; gv.w += t[7]; }
+        if (MODE != 1) { gv.x += t[4]; gv.y += t[5]; gv.z += t[6]; }
+        if (MODE != 2) d.mom_pm[0] = pm;
+        d.mom_gv[0] = gv;
     }
 }
 
+template <int MODE>
 __device__ __forceinline__ void finalize_node(const AgbDev& d, const AgbScalars* s, int k)
 {
     const int64_t N = d.n;
-    double4 pm = ldcg4(&d.mom_pm[k]), gv = s->any_gas ? ldcg4(&d.mom_gv[k]) : make_double4(0, 0, 0, 0);
-    double4 com = make_double4(0, 0, 0, pm.w), mv = make_double4(0, 0, 0, gv.w);
-    if (pm.w > 0.0) { com.x = pm.x / pm.w; com.y = pm.y / pm.w; com.z = pm.z / pm.w; }
+    double4 gv = s->any_gas ? ldcg4(&d.mom_gv[k]) : make_double4(0, 0, 0, 0);
+    double4 mv = make_double4(0, 0, 0, gv.w);
     if (gv.w > 0.0) { mv.x = gv.x / gv.w; mv.y = gv.y / gv.w; mv.z = gv.z / gv.w; }
+    if (MODE == 2) { if (gv.w > 0.0) d.src_gv[N + k] = mv; return; }
+    double4 pm = ldcg4(&d.mom_pm[k]);
+    double4 com = make_double4(0, 0, 0, pm.w);
+    if (pm.w > 0.0) { com.x = pm.x / pm.w; com.y = pm.y / pm.w; com.z = pm.z / pm.w; }
     d.src_pm[N + k] = com;
     d.src_gv[N + k] = mv;
     d.src_flag[N + k] = gv.w > 0.0 ? 1 : 0;
@@ -889,13 +942,32 @@ int agb_launch_sort(AgbDev& d, AgbScalars* s, cudaStream_t st)
     return launches + 2;
 }
 
-int agb_launch_links(AgbDev& d, AgbScalars* s, cudaStream_t st, cudaEvent_t* ev)
+static int upward_blocks(int nnb)
+{
+    static int occ = 0;                                       // co-resident blocks per SM of the level kernels (same on every B200)
+    if (!occ) {
+        int o0 = 0, o1 = 0, o2 = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o0, k_upward_levels<0>, TPB, 0);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o1, k_upward_levels<1>, TPB, 0);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o2, k_upward_levels<2>, TPB, 0);
+        occ = std::max(1, std::min(std::min(o0, o1), std::min(o2, 4)));
+    }
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    return std::min(sms * occ, std::max(1, nnb));
+}
+
+// late_gas: velocities / U / mu of the hand-over are still on their way (agb_launch_late_gas completes the tree afterwards)
+int agb_launch_links(AgbDev& d, AgbScalars* s, cudaStream_t st, cudaEvent_t* ev, bool late_gas)
 {
     const int nb = nblk(d.n, TPB);
     const uint64_t *khi = d.khi[d.cur], *klo = d.klo[1];
     if (d.next) k_next_uniform<<<std::min(nb, 2048), TPB, 0, st>>>(d.next, d.n, s);
-    k_pack_gas<<<nb, TPB, 0, st>>>(d);
-    k_gather<<<nb, TPB, 0, st>>>(d, d.perm[d.cur], s);
+    if (late_gas) k_gather<true><<<nb, TPB, 0, st>>>(d, d.perm[d.cur], s);
+    else {
+        k_pack_gas<<<nb, TPB, 0, st>>>(d);
+        k_gather<false><<<nb, TPB, 0, st>>>(d, d.perm[d.cur], s);
+    }
     if (ev) cudaEventRecord(ev[0], st);
     k_lcp<<<nb, TPB, 0, st>>>(khi, klo, d.n, d.lcp, d.nodecnt, s);
     const int sb = nblk(d.n, SCAN_TILE);
@@ -906,14 +978,22 @@ int agb_launch_links(AgbDev& d, AgbScalars* s, cudaStream_t st, cudaEvent_t* ev)
     k_init_nodes<<<nnb, TPB, 0, st>>>(d, s);
     k_links<<<nb, TPB, 0, st>>>(d, khi, klo, s);
     if (ev) cudaEventRecord(ev[1], st);
-    // level lists (scratch: grouplist, unused until the density pass), then the persistent level-by-level upward pass
-    k_level_lists<<<nnb, TPB, 0, st>>>(d, s, d.grouplist);
-    static int occ = 0;                                       // co-resident blocks per SM of the level kernel (same on every B200)
-    if (!occ) { cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_upward_levels, TPB, 0); occ = std::max(1, std::min(occ, 4)); }
-    int dev = 0, sms = 148;
-    cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    k_upward_levels<<<std::min(sms * occ, std::max(1, nnb)), TPB, 0, st>>>(d, s, d.grouplist);
-    return 11 + (d.next ? 1 : 0);
+    // level lists, then the persistent level-by-level upward pass
+    k_level_lists<<<nnb, TPB, 0, st>>>(d, s, d.lvl_list);
+    if (late_gas) k_upward_levels<1><<<upward_blocks(nnb), TPB, 0, st>>>(d, s, d.lvl_list);
+    else k_upward_levels<0><<<upward_blocks(nnb), TPB, 0, st>>>(d, s, d.lvl_list);
+    return (late_gas ? 10 : 11) + (d.next ? 1 : 0);
+}
+
+// second half of a late_gas build, after the gas densities: gas velocities / U / mu into tree order, P and T of the density
+// groups, mVel of the nodes
+int agb_launch_late_gas(AgbDev& d, AgbScalars* s, cudaStream_t st)
+{
+    const int nb = nblk(d.n, TPB), nnb = nblk(d.ncap, TPB);
+    k_pack_gas<<<nb, TPB, 0, st>>>(d);
+    k_gather_late<<<nb, TPB, 0, st>>>(d, d.perm[d.cur], s);
+    k_upward_levels<2><<<upward_blocks(nnb), TPB, 0, st>>>(d, s, d.lvl_list);
+    return 3;
 }
 
 // skip_if_n (device, optional): the three kernels return at once when *skip_if_n == n (nothing to compact)

@@ -207,6 +207,8 @@ __global__ void __launch_bounds__(TPB) k_gas_fold(AgbDev d, AgbScalars* s, GasFo
 }
 
 // topmost marked node on the root path -> group id: N+k (node), i (own leaf) or -1 (orphan)
+// LATE: U and mu have not arrived yet; P and T are written by k_gather_late (agb_build.cu)
+template <bool LATE>
 __global__ void __launch_bounds__(TPB) k_gas_group(AgbDev d, AgbScalars* s)
 {
     int64_t i = (int64_t)blockIdx.x * TPB + threadIdx.x;
@@ -223,8 +225,10 @@ __global__ void __launch_bounds__(TPB) k_gas_group(AgbDev d, AgbScalars* s)
             const double a = 1.0 / (kPI * h * h * h);
             const double rho = d.src_pm[i].w * a;
             d.s_h[i] = h; d.s_rho[i] = rho;
-            d.s_P[i] = (kGAMMA - 1.0) * d.s_U[i] * rho;
-            d.s_T[i] = (kGAMMA - 1.0) * d.s_U[i] * kPRTN * d.s_mu[i] / kKB;
+            if (!LATE) {
+                d.s_P[i] = (kGAMMA - 1.0) * d.s_U[i] * rho;
+                d.s_T[i] = (kGAMMA - 1.0) * d.s_U[i] * kPRTN * d.s_mu[i] / kKB;
+            }
         }
     }
     unsigned m = __ballot_sync(0xffffffffu, orphan);
@@ -250,6 +254,7 @@ __device__ __forceinline__ double spline_w(double r, double h)
 }
 
 // one warp per surviving group: fixed-shape (lane-strided, then butterfly) sum => deterministic
+template <bool LATE>
 __global__ void __launch_bounds__(TPB) k_gas_sum(AgbDev d, const AgbScalars* __restrict__ s, GasFold F)
 {
     const int lane = threadIdx.x & 31;
@@ -272,20 +277,24 @@ __global__ void __launch_bounds__(TPB) k_gas_sum(AgbDev d, const AgbScalars* __r
     for (int r = g0 + lane; r < g1; r += 32) {
         const int j = F.g_tree[r];
         d.s_h[j] = h; d.s_rho[j] = acc;
-        d.s_P[j] = (kGAMMA - 1.0) * d.s_U[j] * acc;                       // Node.cpp:789
-        d.s_T[j] = (kGAMMA - 1.0) * d.s_U[j] * kPRTN * d.s_mu[j] / kKB;   // Node.cpp:791
+        if (!LATE) {
+            d.s_P[j] = (kGAMMA - 1.0) * d.s_U[j] * acc;                       // Node.cpp:789
+            d.s_T[j] = (kGAMMA - 1.0) * d.s_U[j] * kPRTN * d.s_mu[j] / kKB;   // Node.cpp:791
+        }
     }
     }
 }
 
-// back to caller order (gas only, through the compact list)
+// back to caller order (gas only, through the compact list).  LATE: h and the new rho only; orphans keep the rho they came with
+template <bool LATE>
 __global__ void __launch_bounds__(TPB) k_gas_scatter(AgbDev d, const AgbScalars* __restrict__ s, GasFold F)
 {
     const int r = blockIdx.x * TPB + threadIdx.x;
     if (r >= s->n_gas_total) return;
     const int i = F.g_tree[r];
     const uint32_t p = F.g_orig[r];
-    d.h[p] = d.s_h[i]; d.rho[p] = d.s_rho[i]; d.P[p] = d.s_P[i]; d.T[p] = d.s_T[i];
+    if (LATE) { d.h[p] = d.s_h[i]; if (i < s->n_in_tree && d.group[i] >= 0) d.rho[p] = d.s_rho[i]; }
+    else { d.h[p] = d.s_h[i]; d.rho[p] = d.s_rho[i]; d.P[p] = d.s_P[i]; d.T[p] = d.s_T[i]; }
 }
 
 __global__ void k_gas_reset(AgbScalars* s) { s->n_gas_groups = 0; s->n_gas_orphans = 0; s->tie_exact = 0; s->tie_unresolved = 0; s->n_fold = 0; }
@@ -300,7 +309,7 @@ int agb_launch_visual(AgbDev& d, AgbScalars* s, double radius, cudaStream_t st)
     return 1;
 }
 
-int agb_launch_gas_density(AgbDev& d, AgbScalars* s, double massInH, cudaStream_t st)
+int agb_launch_gas_density(AgbDev& d, AgbScalars* s, double massInH, cudaStream_t st, bool late_pt)
 {
     const int nb = nblk(d.n, TPB);
     k_gas_reset<<<1, 1, 0, st>>>(s);
@@ -324,9 +333,10 @@ int agb_launch_gas_density(AgbDev& d, AgbScalars* s, double massInH, cudaStream_
     cudaFuncSetAttribute(k_gas_fold, cudaFuncAttributeMaxDynamicSharedMemorySize, fold_smem);
     k_gas_fold<<<296, TPB, fold_smem, st>>>(d, s, F);
     k_gas_mark<1><<<nb, TPB, 0, st>>>(d, s, massInH, F);
-    k_gas_group<<<nb, TPB, 0, st>>>(d, s);
+    if (late_pt) k_gas_group<true><<<nb, TPB, 0, st>>>(d, s); else k_gas_group<false><<<nb, TPB, 0, st>>>(d, s);
     k_gas_collect<<<nblk(d.ncap, TPB), TPB, 0, st>>>(d, s);
-    k_gas_sum<<<std::min(nblk(d.n, TPB / 32), 148 * 16), TPB, 0, st>>>(d, s, F);   // one warp per group, grid-stride
-    k_gas_scatter<<<nb, TPB, 0, st>>>(d, s, F);
+    const int sumb = std::min(nblk(d.n, TPB / 32), 148 * 16);                      // one warp per group, grid-stride
+    if (late_pt) { k_gas_sum<true><<<sumb, TPB, 0, st>>>(d, s, F); k_gas_scatter<true><<<nb, TPB, 0, st>>>(d, s, F); }
+    else { k_gas_sum<false><<<sumb, TPB, 0, st>>>(d, s, F); k_gas_scatter<false><<<nb, TPB, 0, st>>>(d, s, F); }
     return 10 + launches;
 }

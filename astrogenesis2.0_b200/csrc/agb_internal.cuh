@@ -50,6 +50,7 @@ struct AgbDev {
     uint8_t *nmark = nullptr, *ndup = nullptr, *leafmark = nullptr;
     double4 *mom_pm = nullptr, *mom_gv = nullptr;
     int32_t* grouplist = nullptr;
+    int32_t* lvl_list = nullptr;       // node ids by depth (level lists of the upward passes)
     int32_t* gasrank = nullptr;        // exclusive count of gas particles before tree position i
     // scratch
     double4* rec = nullptr;            // caller order: (x, y, z, mass) packed by the extent pass
@@ -81,7 +82,7 @@ struct AgbScalars {
     int32_t vis_level;
     int32_t walk_overflow, any_gas;
     int32_t next_uniform;              // every particle has the same nextIntegrationTime (fixed-step runs): the gather skips that column
-    unsigned int grid_bar;             // arrival counter of the level-synchronous upward pass
+    unsigned int grid_bar, grid_bar2;  // arrival counters of the level-synchronous upward passes (all / mVel only)
     int32_t lvl_cnt[48], lvl_cur[48];  // internal nodes per depth, fill cursors of the level lists
     int32_t node_overflow;             // the build needed more than ncap nodes: nothing past the capacity was written, the host grows and rebuilds
     int32_t n_gas_total, tie_exact, tie_unresolved, n_fold, n_long_runs, n_scan_tmp;
@@ -107,14 +108,15 @@ int agb_launch_int_second(AgbDev& d, const AgbInt& I, double gt, cudaStream_t st
 int agb_launch_extent(const AgbDev& d, AgbScalars* s, cudaStream_t st);
 int agb_launch_keygen(AgbDev& d, AgbScalars* s, cudaStream_t st);
 int agb_launch_sort(AgbDev& d, AgbScalars* s, cudaStream_t st);
-int agb_launch_links(AgbDev& d, AgbScalars* s, cudaStream_t st, cudaEvent_t* ev = nullptr);   // ev[0] after the gather, ev[1] after the links, before the upward pass
+int agb_launch_links(AgbDev& d, AgbScalars* s, cudaStream_t st, cudaEvent_t* ev = nullptr, bool late_gas = false);   // ev[0] after the gather, ev[1] after the links, before the upward pass
+int agb_launch_late_gas(AgbDev& d, AgbScalars* s, cudaStream_t st);            // completes a late_gas build once velocities / U / mu have arrived (after the gas densities)
 int agb_launch_visual(AgbDev& d, AgbScalars* s, double radius, cudaStream_t st);
-int agb_launch_gas_density(AgbDev& d, AgbScalars* s, double massInH, cudaStream_t st);
+int agb_launch_gas_density(AgbDev& d, AgbScalars* s, double massInH, cudaStream_t st, bool late_pt = false);   // late_pt: h and rho only (P, T follow in agb_launch_late_gas)
 // compact (index, acc, dUdt) of the active targets [a0, a1) in tree order (agb_get_slice_results)
 void agb_slice_bounds(int64_t n_active, int part, int nparts, int64_t* a0, int64_t* a1);
 int agb_launch_slice_results(const AgbDev& d, int64_t a0, int64_t a1, bool ident, uint32_t* index, double* const dst[9], cudaStream_t st);   // dst: ax ay az dUdt h rho P T vis
 int agb_launch_walk(AgbDev& d, AgbScalars* s, double globalTime, double e0, double theta, int part, int nparts,
-                    bool counters, bool any_gas, bool mixed, int sm_count, cudaStream_t st, cudaEvent_t* ev);   // ev[0..3]: before k_far, k_walk, k_sph, after
+                    bool counters, bool any_gas, bool mixed, int sm_count, cudaStream_t st, cudaEvent_t* ev, int phase = 0);   // ev[0..4]: before k_far, before k_walk, after k_walk, after k_sph, before k_sph
 int agb_launch_dump_tree(AgbDev& d, AgbScalars* s, int32_t* leafdepth, uint64_t* khi, uint64_t* klo, cudaStream_t st);
 int agb_launch_scan_i32(const int32_t* in, int32_t* out, int64_t n, int32_t* blk, int32_t* total_out, cudaStream_t st, const int32_t* skip_if_n = nullptr);
 int agb_launch_microbench(int kind, int sm_count, cudaStream_t st, double* result);

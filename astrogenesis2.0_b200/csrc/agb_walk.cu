@@ -1096,8 +1096,10 @@ int agb_walk_blocks(int sm_count) { return sm_count * WALK_CTAS; }
 int agb_walk_warps_per_block() { return 8; }
 void agb_far_capacity(int* lcap, int* fcap, int* targets) { *lcap = FAR_LCAP; *fcap = FAR_FCAP; *targets = 32 * SG_GROUPS; }
 
+// phase 0: everything; 1: up to and including k_walk; 2: k_sph only (mixed mode with gas: the caller completes a late_gas
+// build between 1 and 2).  ev[0..4]: before k_far, before k_walk, after k_walk, after k_sph, before k_sph.
 int agb_launch_walk(AgbDev& d, AgbScalars* s, double globalTime, double e0, double theta, int part, int nparts,
-                    bool counters, bool any_gas, bool mixed, int sm_count, cudaStream_t st, cudaEvent_t* ev)
+                    bool counters, bool any_gas, bool mixed, int sm_count, cudaStream_t st, cudaEvent_t* ev, int phase)
 {
     WalkParams P;
     P.src_pm = d.src_pm; P.src_gv = d.src_gv; P.src_flag = d.src_flag; P.child = d.child; P.ndepth = d.ndepth;
@@ -1114,8 +1116,9 @@ int agb_launch_walk(AgbDev& d, AgbScalars* s, double globalTime, double e0, doub
     P.far_k2 = far_k2;
     int launches = 0;
     const int nb = (int)((d.n + 255) / 256);
-    k_walk_reset<<<1, 1, 0, st>>>(s); launches++;
-    if (d.n > 0) {
+    const int64_t max_groups = (d.n / nparts + 32 * SG_GROUPS + 31) / 32;
+    if (phase != 2) { k_walk_reset<<<1, 1, 0, st>>>(s); launches++; }
+    if (d.n > 0 && phase != 2) {
         cudaMemsetAsync(&s->n_active, 0, sizeof(int32_t), st);
         k_count_active<<<std::min(nb, 4 * sm_count), 256, 0, st>>>(d.s_next, d.n, globalTime, s); launches++;
         // compact list of the active targets (scratch: flags -> nodecnt, ranks -> nodebase; both are idle after the densities)
@@ -1126,7 +1129,6 @@ int agb_launch_walk(AgbDev& d, AgbScalars* s, double globalTime, double e0, doub
             cudaMemsetAsync(d.c_visits, 0, (size_t)d.n * 4, st); cudaMemsetAsync(d.c_accn, 0, (size_t)d.n * 4, st);
             cudaMemsetAsync(d.c_accl, 0, (size_t)d.n * 4, st); cudaMemsetAsync(d.c_sph, 0, (size_t)d.n * 4, st);
         }
-        const int64_t max_groups = (d.n / nparts + 32 * SG_GROUPS + 31) / 32;
         if (ev) cudaEventRecord(ev[0], st);
         // far-field prepass, one warp per super-group of 256 targets
         k_far<<<(int)std::min<int64_t>((max_groups / SG_GROUPS + 4) / 4, (int64_t)sm_count * 8), 128, 0, st>>>(P); launches++;
@@ -1135,6 +1137,9 @@ int agb_launch_walk(AgbDev& d, AgbScalars* s, double globalTime, double e0, doub
         else { if (any_gas) launch_walk2<false, true>(P, max_groups, sm_count, d.spill_warps, mixed, st); else launch_walk2<false, false>(P, max_groups, sm_count, d.spill_warps, mixed, st); }
         launches++;
         if (ev) cudaEventRecord(ev[2], st);
+    }
+    if (d.n > 0 && phase != 1) {
+        if (ev) cudaEventRecord(ev[4], st);
         if (any_gas && mixed) {
             // the SPH pairs of the candidates the walk recorded (after it: acc += SPH part, dU/dt += ...)
             const int smem = (int)sizeof(SphWarp) * 8;

@@ -192,6 +192,41 @@ def test_force_path_equals_the_four_calls(pkg, ctxs):
         assert np.array_equal(got["visualDensity"], want["vis"])
 
 
+def test_force_path_late_upload_path(pkg, ctxs):
+    """agb_force_path on a host hand-over in mixed precision starts the build on (x, y, z, mass, type), the walk on the first
+    upload group and folds the gas velocities / U / mu in before the SPH pair pass.  Same bits as the four calls, with carried
+    state (orphans keep rho / P / T, dU/dt accumulates), with bound result arrays, and again after a step that ran the other way."""
+    ctx = ctxs(8)
+    rng = np.random.default_rng(77)
+    p = pkg.ics.disk_galaxy(80000, seed=19)
+    n = len(p["x"])
+    for k in ("rho", "P", "T", "h", "dUdt", "ax", "ay", "az"):
+        p[k] = rng.random(n) + 0.5
+    mh = pkg.ics.gas_mass_in_h(p, 64)
+    want = run_gpu(pkg, ctx, dict(p), 0.5, 1e18, mh)
+    want["visualDensity"] = want["vis"]
+    assert ctx.counters()["gas_orphans"] > 0
+    names = ("ax", "ay", "az", "dUdt", "h", "rho", "P", "T", "visualDensity")
+    out = {k: np.full(n, np.nan) for k in names}
+    for bound in (False, True, False):
+        ctx.bind_results(out if bound else None)
+        try:
+            for rep in range(2):                            # the first force_path of a context runs call by call, later ones the late path
+                ctx.set_particles(dict(p))
+                ctx.force_path(want["R"] / 100000, mh, 0.0, 1e18, 0.5)
+                got = ctx.results_into(out) if bound else ctx.results()
+                for k in names:
+                    assert np.array_equal(got[k], want[k]), (k, bound, rep)
+        finally:
+            ctx.bind_results(None)
+    # the tree the late path leaves behind is the complete one (node velocities included)
+    nd_late = ctx.nodes()
+    ctx.set_particles(dict(p)); ctx.build_tree()
+    nd = ctx.nodes()
+    for k in nd:
+        assert np.array_equal(nd[k], nd_late[k]), k
+
+
 def test_slices_equal_whole(pkg, ctxs):
     """Multi-GPU sharding: walking the tree-ordered targets in 1 or 4 slices gives bit-identical results."""
     ctx = ctxs(8)
