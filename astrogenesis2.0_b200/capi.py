@@ -20,6 +20,10 @@ EXPORTS = [
     "agb_set_option", "agb_get_tree_particles", "agb_get_node_count", "agb_get_nodes", "agb_get_target_counters",
     "agb_get_phase_ms", "agb_get_stream", "agb_get_launch_count", "agb_microbench",
     "agb_integrator_init", "agb_integrator_assign_all", "agb_step_begin", "agb_step_end", "agb_get_state", "agb_strerror", "agb_last_error", "agb_version",
+    "agb_multi_create", "agb_multi_destroy", "agb_multi_device_count", "agb_multi_context", "agb_multi_set_option", "agb_multi_set_particles",
+    "agb_multi_set_particles_aos", "agb_multi_build_tree", "agb_multi_visual_density", "agb_multi_gas_density", "agb_multi_forces", "agb_multi_force_path",
+    "agb_multi_get_results", "agb_multi_get_results_aos", "agb_multi_integrator_init", "agb_multi_integrator_assign_all", "agb_multi_step_begin",
+    "agb_multi_step_end", "agb_multi_get_state", "agb_multi_last_error",
 ]
 
 
@@ -111,6 +115,28 @@ def load(build_if_needed=True):
     lib.agb_last_error.restype = C.c_char_p
     lib.agb_last_error.argtypes = [vp]
     lib.agb_version.restype = C.c_char_p
+    if hasattr(lib, "agb_multi_create"):
+        lib.agb_multi_create.argtypes = [C.POINTER(vp), C.POINTER(C.c_int), C.c_int, C.c_int]
+        lib.agb_multi_destroy.argtypes = [vp]
+        lib.agb_multi_device_count.argtypes = [vp]
+        lib.agb_multi_context.argtypes = [vp, C.c_int, C.POINTER(vp)]
+        lib.agb_multi_set_option.argtypes = [vp, C.c_int, C.c_int64]
+        lib.agb_multi_set_particles.argtypes = [vp, C.POINTER(Particles)]
+        lib.agb_multi_set_particles_aos.argtypes = [vp, C.POINTER(vp), C.c_int64, C.POINTER(AosLayout)]
+        lib.agb_multi_build_tree.argtypes = [vp, _pd]
+        lib.agb_multi_visual_density.argtypes = [vp, C.c_double]
+        lib.agb_multi_gas_density.argtypes = [vp, C.c_double]
+        lib.agb_multi_forces.argtypes = [vp, C.c_double, C.c_double, C.c_double]
+        lib.agb_multi_force_path.argtypes = [vp, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, _pd]
+        lib.agb_multi_get_results.argtypes = [vp, C.POINTER(Results)]
+        lib.agb_multi_get_results_aos.argtypes = [vp, C.POINTER(vp), C.c_int64, C.POINTER(AosLayout)]
+        lib.agb_multi_integrator_init.argtypes = [vp] + [C.c_double] * 5
+        lib.agb_multi_integrator_assign_all.argtypes = [vp]
+        lib.agb_multi_step_begin.argtypes = [vp, _pd]
+        lib.agb_multi_step_end.argtypes = [vp]
+        lib.agb_multi_get_state.argtypes = [vp] + [_pd] * 9
+        lib.agb_multi_last_error.restype = C.c_char_p
+        lib.agb_multi_last_error.argtypes = [vp]
     _lib = lib
     return lib
 

@@ -5,7 +5,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <string>
+#include <thread>
 #include <vector>
 
 int agb_walk_blocks(int sm_count);
@@ -364,6 +366,16 @@ int agb_set_particles(agb_ctx* c, const agb_particles* p, int memspace)
 
 static inline double* aos_d(void* base, int64_t off) { return reinterpret_cast<double*>(static_cast<char*>(base) + off); }
 
+// host loops over the caller's records (264 bytes apart in the reference: latency bound), split over a few threads
+static void host_parallel(int64_t n, const std::function<void(int64_t, int64_t)>& f)
+{
+    const int nt = (int)std::max<int64_t>(1, std::min<int64_t>({(int64_t)std::thread::hardware_concurrency(), (int64_t)16, n / 65536}));
+    if (nt <= 1) { f(0, n); return; }
+    std::vector<std::thread> th;
+    for (int t = 0; t < nt; t++) th.emplace_back([&, t] { f(n * t / nt, n * (t + 1) / nt); });
+    for (auto& t : th) t.join();
+}
+
 int agb_set_particles_aos(agb_ctx* c, void* const* parts, int64_t n, const agb_aos_layout* L)
 {
     if (!c || !parts || !L || n < 0 || n >= (1ll << 30) || L->position < 0 || L->mass < 0 || L->type < 0) return AGB_ERR_INVALID;
@@ -386,13 +398,15 @@ int agb_set_particles_aos(agb_ctx* c, void* const* parts, int64_t n, const agb_a
         const double* v = aos_d(parts[i], off); col[k0][i] = v[0]; col[k0 + 1][i] = v[1]; col[k0 + 2][i] = v[2];
     };
     auto sca = [&](int64_t off, int64_t i, int k, double dflt) { col[k][i] = off < 0 ? dflt : *aos_d(parts[i], off); };
-    for (int64_t i = 0; i < n; i++) {
-        if (!parts[i]) return AGB_ERR_INVALID;
-        vec(L->position, i, 0); vec(L->velocity, i, 3); vec(L->acc, i, 6);
-        sca(L->mass, i, 9, 0); sca(L->U, i, 10, 0); sca(L->next_time, i, 11, 0); sca(L->mu, i, 12, 0.58);
-        sca(L->rho, i, 13, 0); sca(L->P, i, 14, 0); sca(L->T, i, 15, 0); sca(L->h, i, 16, 0); sca(L->dUdt, i, 17, 0);
-        typ[i] = *reinterpret_cast<const uint8_t*>(static_cast<const char*>(parts[i]) + L->type);
-    }
+    for (int64_t i = 0; i < n; i++) if (!parts[i]) return AGB_ERR_INVALID;
+    host_parallel(n, [&](int64_t a, int64_t b) {
+        for (int64_t i = a; i < b; i++) {
+            vec(L->position, i, 0); vec(L->velocity, i, 3); vec(L->acc, i, 6);
+            sca(L->mass, i, 9, 0); sca(L->U, i, 10, 0); sca(L->next_time, i, 11, 0); sca(L->mu, i, 12, 0.58);
+            sca(L->rho, i, 13, 0); sca(L->P, i, 14, 0); sca(L->T, i, 15, 0); sca(L->h, i, 16, 0); sca(L->dUdt, i, 17, 0);
+            typ[i] = *reinterpret_cast<const uint8_t*>(static_cast<const char*>(parts[i]) + L->type);
+        }
+    });
     agb_particles p;
     memset(&p, 0, sizeof(p));
     p.n = n;
@@ -709,15 +723,17 @@ int agb_get_results_aos(agb_ctx* c, void* const* parts, int64_t n, const agb_aos
     agb_results r = {col[0], col[1], col[2], col[3], col[4], col[5], col[6], col[7], col[8]};
     int rc = agb_get_results(c, &r, AGB_MEM_HOST);
     if (rc) return rc;
-    for (int64_t i = 0; i < n; i++) {
-        if (L->acc >= 0) { double* a = aos_d(parts[i], L->acc); a[0] = col[0][i]; a[1] = col[1][i]; a[2] = col[2][i]; }
-        if (L->dUdt >= 0) *aos_d(parts[i], L->dUdt) = col[3][i];
-        if (L->h >= 0) *aos_d(parts[i], L->h) = col[4][i];
-        if (L->rho >= 0) *aos_d(parts[i], L->rho) = col[5][i];
-        if (L->P >= 0) *aos_d(parts[i], L->P) = col[6][i];
-        if (L->T >= 0) *aos_d(parts[i], L->T) = col[7][i];
-        if (L->visualDensity >= 0) *aos_d(parts[i], L->visualDensity) = col[8][i];
-    }
+    host_parallel(n, [&](int64_t a0, int64_t b0) {
+        for (int64_t i = a0; i < b0; i++) {
+            if (L->acc >= 0) { double* a = aos_d(parts[i], L->acc); a[0] = col[0][i]; a[1] = col[1][i]; a[2] = col[2][i]; }
+            if (L->dUdt >= 0) *aos_d(parts[i], L->dUdt) = col[3][i];
+            if (L->h >= 0) *aos_d(parts[i], L->h) = col[4][i];
+            if (L->rho >= 0) *aos_d(parts[i], L->rho) = col[5][i];
+            if (L->P >= 0) *aos_d(parts[i], L->P) = col[6][i];
+            if (L->T >= 0) *aos_d(parts[i], L->T) = col[7][i];
+            if (L->visualDensity >= 0) *aos_d(parts[i], L->visualDensity) = col[8][i];
+        }
+    });
     return AGB_OK;
 }
 
@@ -921,3 +937,15 @@ int agb_get_launch_count(agb_ctx* c, int64_t* launches)
 }
 
 } // extern "C"
+
+void agb_ctx_internals(agb_ctx* c, AgbDev** d, cudaStream_t* st, int* device)
+{
+    if (d) *d = &c->d;
+    if (st) *st = c->st;
+    if (device) *device = c->device;
+}
+
+void agb_ctx_join_uploads(agb_ctx* c)
+{
+    if (c->in_pending) { cudaStreamWaitEvent(c->st, c->ev_in, 0); c->in_pending = false; c->next_pending = false; }
+}

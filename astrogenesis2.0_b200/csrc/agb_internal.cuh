@@ -120,6 +120,9 @@ int agb_launch_walk(AgbDev& d, AgbScalars* s, double globalTime, double e0, doub
 int agb_launch_dump_tree(AgbDev& d, AgbScalars* s, int32_t* leafdepth, uint64_t* khi, uint64_t* klo, cudaStream_t st);
 int agb_launch_scan_i32(const int32_t* in, int32_t* out, int64_t n, int32_t* blk, int32_t* total_out, cudaStream_t st, const int32_t* skip_if_n = nullptr);
 int agb_launch_microbench(int kind, int sm_count, cudaStream_t st, double* result);
+// agb_multi.cu reaches into a context it drives (agb_api.cu)
+void agb_ctx_internals(agb_ctx* c, AgbDev** d, cudaStream_t* st, int* device);
+void agb_ctx_join_uploads(agb_ctx* c);            // the compute stream waits for every upload of the last hand-over
 int agb_launch_unpermute_counters(AgbDev& d, int32_t* v, int32_t* an, int32_t* al, int32_t* sp, cudaStream_t st);
 
 // ---- small device helpers ----

@@ -619,7 +619,8 @@ __global__ void __launch_bounds__(WalkCfg<SPH>::TPB, WALK_CTAS) k_walk(const Wal
                     if (SPLIT && wgas) {
                         // sources within 2 h_max of the warp's box that a gas target accepted: (source, those targets) for k_sph
                         const unsigned gm = pc_mask & gasl;
-                        const bool cand = gm != 0u && dmin2 < cand2;
+                        bool cand = gm != 0u && dmin2 < cand2;
+                        if (cand) cand = P.src_flag[e.x] != 0;                       // sources without gas never pass Node.cpp:319 / :371
                         const unsigned cm = __ballot_sync(0xffffffffu, cand);
                         if (cm) {
                             if (cand) sm.rsrc[rfill + __popc(cm & lt)] = make_int2(e.x, (int)gm);
@@ -807,8 +808,11 @@ __global__ void __launch_bounds__(WalkCfg<SPH>::TPB, WALK_CTAS) k_walk(const Wal
 // r < 2 h_i (FP32, FP64 when within 4e-6 of the threshold), the kernel gradient / viscosity algebra in FP32, the final
 // products in FP64; results travel through shared memory back to the owning lane, which adds its own pairs in source
 // order (deterministic: bit-identical from run to run and for any number of GPUs).
+#ifndef AGB_SPH_CTAS_PER_SM
+#define AGB_SPH_CTAS_PER_SM 3
+#endif
 template <bool COUNT>
-__global__ void __launch_bounds__(256, 3) k_sph(const WalkParams P)
+__global__ void __launch_bounds__(256, AGB_SPH_CTAS_PER_SM) k_sph(const WalkParams P)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;

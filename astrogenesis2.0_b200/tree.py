@@ -236,6 +236,102 @@ class Context:
         return v.value
 
 
+class MultiContext:
+    """Several GPUs of one box behind one handle (agb_multi_*): every device builds the same tree, walks a slice of the targets,
+    the slices are exchanged device to device.  Results are bit-identical to a one-GPU Context."""
+
+    def __init__(self, devices, compat_cores=8):
+        self.lib = capi.load()
+        self.h = C.c_void_p()
+        devs = (C.c_int * len(devices))(*devices)
+        capi.check(None, self.lib.agb_multi_create(C.byref(self.h), devs, len(devices), int(compat_cores)))
+        self._keep = None
+        self.n = 0
+
+    def _ck(self, st):
+        if st != 0:
+            raise capi.AgbError(st, self.lib.agb_strerror(st).decode() + " (" + self.lib.agb_multi_last_error(self.h).decode() + ")")
+
+    def close(self):
+        if self.h:
+            self.lib.agb_multi_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_option(self, opt, value):
+        self._ck(self.lib.agb_multi_set_option(self.h, int(opt), int(value)))
+
+    def set_particles(self, p):
+        n = len(p["x"])
+        st = capi.Particles()
+        st.n = n
+        keep = {}
+        for k in _F8:
+            a = p.get(k)
+            if a is not None:
+                a = np.ascontiguousarray(a, dtype=np.float64)
+                keep[k] = a
+            setattr(st, k, capi.dptr(a))
+        t = np.ascontiguousarray(p["type"], dtype=np.uint8)
+        keep["type"] = t
+        st.type = capi.dptr(t, C.c_uint8)
+        self._ck(self.lib.agb_multi_set_particles(self.h, C.byref(st)))
+        self._keep = keep
+        self.n = n
+
+    def build_tree(self):
+        r = C.c_double()
+        self._ck(self.lib.agb_multi_build_tree(self.h, C.byref(r)))
+        return r.value
+
+    def visual_density(self, radius):
+        self._ck(self.lib.agb_multi_visual_density(self.h, float(radius)))
+
+    def gas_density(self, massInH):
+        self._ck(self.lib.agb_multi_gas_density(self.h, float(massInH)))
+
+    def forces(self, globalTime, e0, theta):
+        self._ck(self.lib.agb_multi_forces(self.h, float(globalTime), float(e0), float(theta)))
+
+    def force_path(self, visual_radius, massInH, globalTime, e0, theta):
+        r = C.c_double()
+        self._ck(self.lib.agb_multi_force_path(self.h, float(visual_radius), float(massInH), float(globalTime), float(e0), float(theta), C.byref(r)))
+        return r.value
+
+    def results(self, names=_OUT):
+        out = {k: np.empty(self.n) for k in names}
+        r = capi.Results()
+        for k in _OUT:
+            setattr(r, k, capi.dptr(out.get(k)))
+        self._ck(self.lib.agb_multi_get_results(self.h, C.byref(r)))
+        return out
+
+    def integrator_init(self, eta, min_ts, max_ts, H0, e0):
+        self._ck(self.lib.agb_multi_integrator_init(self.h, float(eta), float(min_ts), float(max_ts), float(H0), float(e0)))
+
+    def integrator_assign_all(self):
+        self._ck(self.lib.agb_multi_integrator_assign_all(self.h))
+
+    def step_begin(self):
+        t = C.c_double()
+        self._ck(self.lib.agb_multi_step_begin(self.h, C.byref(t)))
+        return t.value
+
+    def step_end(self):
+        self._ck(self.lib.agb_multi_step_end(self.h))
+
+    def state(self):
+        names = ("x", "y", "z", "vx", "vy", "vz", "U", "next_time", "timeStep")
+        out = {k: np.empty(self.n) for k in names}
+        self._ck(self.lib.agb_multi_get_state(self.h, *[capi.dptr(out[k]) for k in names]))
+        return out
+
+
 class Tree:
     """Drop-in for the reference's Tree (Tree.h:13-27): same construction, same four calls, `root.radius`."""
 

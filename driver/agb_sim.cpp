@@ -16,7 +16,7 @@
 // Cooling / star formation are no-ops in the reference (calls commented out, Simulation.cpp:312-320) and here.
 // The force path itself is only reached through the C ABI (include/agb200.h); there is no CPU fallback.
 //
-//   agb_sim --config Config.ini [--input-root DIR] [--output-root DIR] [--steps K] [--device D] [--cores C]
+//   agb_sim --config Config.ini [--input-root DIR] [--output-root DIR] [--steps K] [--device D] [--gpus N] [--cores C]
 //           [--precision fp64|mixed] [--dump final.agp] [--overwrite] [--device-resident] [--convert-only out.agp] [--snapshot-only DIR [--snapshot-index N] [--snapshot-time T]]
 // --device-resident keeps positions, velocities and results in HBM between steps (agb_integrator_* / agb_step_*):
 // only the scalar time crosses PCIe per step; state is copied back for snapshots and at the end.
@@ -447,13 +447,13 @@ struct PhaseLog {                                            // File/Log.cpp:175
     }
 };
 
-void check(agb_ctx* c, int rc, const char* what)
+void check(agb_multi* m, int rc, const char* what)
 {
-    if (rc != AGB_OK) { fprintf(stderr, "agb200: %s failed: %s (%s)\n", what, agb_strerror(rc), agb_last_error(c)); exit(3); }
+    if (rc != AGB_OK) { fprintf(stderr, "agb200: %s failed: %s (%s)\n", what, agb_strerror(rc), agb_multi_last_error(m)); exit(3); }
 }
 
 struct Driver {
-    Config cfg; Particles p; agb_ctx* ctx = nullptr; PhaseLog log;
+    Config cfg; Particles p; agb_multi* ctx = nullptr; PhaseLog log;     // one handle for --gpus N devices (N = 1: a plain context behind it)
     double globalTime = 0, visualDensityRadius = 0;
     bool device_resident = false;
 
@@ -465,18 +465,18 @@ struct Driver {
         in.rho = p.rho.data(); in.P = p.P.data(); in.T = p.T.data(); in.h = p.h.data(); in.dUdt = p.dUdt.data();
         in.ax = p.ax.data(); in.ay = p.ay.data(); in.az = p.az.data();
         log.start("build tree");
-        check(ctx, agb_set_particles(ctx, &in, AGB_MEM_HOST), "set_particles");
+        check(ctx, agb_multi_set_particles(ctx, &in), "set_particles");
         double R = 0;
-        check(ctx, agb_build_tree(ctx, &R), "build_tree");
+        check(ctx, agb_multi_build_tree(ctx, &R), "build_tree");
         if (first) visualDensityRadius = R / 100000;                    // Simulation.cpp:126
         log.start("Visual Density");
-        check(ctx, agb_visual_density(ctx, visualDensityRadius), "visual_density");
+        check(ctx, agb_multi_visual_density(ctx, visualDensityRadius), "visual_density");
         log.start("SPH density and update");
-        check(ctx, agb_gas_density(ctx, cfg.massInH), "gas_density");
+        check(ctx, agb_multi_gas_density(ctx, cfg.massInH), "gas_density");
         log.start("Force Calculation");
-        check(ctx, agb_forces(ctx, globalTime, cfg.e0, cfg.theta), "forces");
+        check(ctx, agb_multi_forces(ctx, globalTime, cfg.e0, cfg.theta), "forces");
         agb_results out{p.ax.data(), p.ay.data(), p.az.data(), p.dUdt.data(), p.h.data(), p.rho.data(), p.P.data(), p.T.data(), p.vis.data()};
-        check(ctx, agb_get_results(ctx, &out, AGB_MEM_HOST), "get_results");
+        check(ctx, agb_multi_get_results(ctx, &out), "get_results");
         log.end();
     }
 
@@ -487,7 +487,7 @@ struct Driver {
         in.mass = p.mass.data(); in.U = p.U.data(); in.next_time = p.next.data(); in.mu = p.mu.data(); in.type = p.type.data();
         in.rho = p.rho.data(); in.P = p.P.data(); in.T = p.T.data(); in.h = p.h.data(); in.dUdt = p.dUdt.data();
         in.ax = p.ax.data(); in.ay = p.ay.data(); in.az = p.az.data();
-        check(ctx, agb_set_particles(ctx, &in, AGB_MEM_HOST), "set_particles");
+        check(ctx, agb_multi_set_particles(ctx, &in), "set_particles");
     }
     void log_ms(const std::string& name, double ms)
     {
@@ -503,29 +503,31 @@ struct Driver {
         if (!first) {
             // steady state: the four calls in one (a single host synchronisation); the reference's phase rows come from the device timers
             log.end();
-            check(ctx, agb_force_path(ctx, visualDensityRadius, cfg.massInH, globalTime, cfg.e0, cfg.theta, 0, 1, nullptr), "force_path");
+            check(ctx, agb_multi_force_path(ctx, visualDensityRadius, cfg.massInH, globalTime, cfg.e0, cfg.theta, nullptr), "force_path");
             double ms[5] = {0, 0, 0, 0, 0};
-            agb_get_phase_ms(ctx, ms);
+            agb_ctx* c0 = nullptr;
+            agb_multi_context(ctx, 0, &c0);
+            agb_get_phase_ms(c0, ms);
             log_ms("build tree", ms[0]); log_ms("Visual Density", ms[1]); log_ms("SPH density and update", ms[2]); log_ms("Force Calculation", ms[4]);
             return;
         }
         log.start("build tree");
         double R = 0;
-        check(ctx, agb_build_tree(ctx, &R), "build_tree");
+        check(ctx, agb_multi_build_tree(ctx, &R), "build_tree");
         if (first) visualDensityRadius = R / 100000;
         log.start("Visual Density");
-        check(ctx, agb_visual_density(ctx, visualDensityRadius), "visual_density");
+        check(ctx, agb_multi_visual_density(ctx, visualDensityRadius), "visual_density");
         log.start("SPH density and update");
-        check(ctx, agb_gas_density(ctx, cfg.massInH), "gas_density");
+        check(ctx, agb_multi_gas_density(ctx, cfg.massInH), "gas_density");
         log.start("Force Calculation");
-        check(ctx, agb_forces(ctx, globalTime, cfg.e0, cfg.theta), "forces");
+        check(ctx, agb_multi_forces(ctx, globalTime, cfg.e0, cfg.theta), "forces");
         log.end();
     }
     void download()
     {
         agb_results out{p.ax.data(), p.ay.data(), p.az.data(), p.dUdt.data(), p.h.data(), p.rho.data(), p.P.data(), p.T.data(), p.vis.data()};
-        check(ctx, agb_get_results(ctx, &out, AGB_MEM_HOST), "get_results");
-        check(ctx, agb_get_state(ctx, p.x.data(), p.y.data(), p.z.data(), p.vx.data(), p.vy.data(), p.vz.data(), p.U.data(), p.next.data(), p.timeStep.data()), "get_state");
+        check(ctx, agb_multi_get_results(ctx, &out), "get_results");
+        check(ctx, agb_multi_get_state(ctx, p.x.data(), p.y.data(), p.z.data(), p.vx.data(), p.vy.data(), p.vz.data(), p.U.data(), p.next.data(), p.timeStep.data()), "get_state");
     }
     int run_device(int64_t max_steps, const std::string& outdir)
     {
@@ -533,18 +535,18 @@ struct Driver {
         globalTime = 0.0;
         for (int64_t i = 0; i < p.n; i++) p.next[i] = 0.0;
         upload();
-        check(ctx, agb_integrator_init(ctx, cfg.eta, cfg.minTimeStep, cfg.maxTimeStep, cfg.H0, cfg.e0), "integrator_init");
+        check(ctx, agb_multi_integrator_init(ctx, cfg.eta, cfg.minTimeStep, cfg.maxTimeStep, cfg.H0, cfg.e0), "integrator_init");
         device_force_path(true);
         if (!outdir.empty()) { download(); save_snapshot(outdir, cfg.outputDataFormat, 0, p, (int64_t)cfg.numParticlesOutput, fixedStep, cfg.endTime, 0.0); }
-        check(ctx, agb_integrator_assign_all(ctx), "assign_all");
+        check(ctx, agb_multi_integrator_assign_all(ctx), "assign_all");
         double nextSaveTime = fixedStep;
         int64_t step = 0;
         while (globalTime < cfg.endTime && (max_steps < 0 || step < max_steps)) {
             log.start("first kick");
-            check(ctx, agb_step_begin(ctx, &globalTime), "step_begin");
+            check(ctx, agb_multi_step_begin(ctx, &globalTime), "step_begin");
             device_force_path(false);
             log.start("second kick");
-            check(ctx, agb_step_end(ctx), "step_end");
+            check(ctx, agb_multi_step_end(ctx), "step_end");
             log.end();
             step++;
             if (!outdir.empty() && globalTime >= nextSaveTime) {
@@ -646,7 +648,7 @@ int main(int argc, char** argv)
         if (a == "--overwrite") { overwrite = true; continue; }
         if (a == "--device-resident") { device_resident = true; continue; }
         if (a.rfind("--", 0) == 0 && i + 1 < argc) { opt[a.substr(2)] = argv[++i]; continue; }
-        fprintf(stderr, "usage: agb_sim --config Config.ini [--input-root DIR] [--output-root DIR] [--steps K] [--device D] [--cores C] [--precision fp64|mixed] [--dump final.agp] [--overwrite]\n");
+        fprintf(stderr, "usage: agb_sim --config Config.ini [--input-root DIR] [--output-root DIR] [--steps K] [--device D] [--gpus N] [--cores C] [--precision fp64|mixed] [--dump final.agp] [--overwrite]\n");
         return 2;
     }
     Driver d;
@@ -679,12 +681,22 @@ int main(int argc, char** argv)
         std::ofstream(d.log.path, std::ios::trunc);
     }
     const int cores = opt.count("cores") ? atoi(opt["cores"].c_str()) : 8;
-    int rc = agb_create(&d.ctx, opt.count("device") ? atoi(opt["device"].c_str()) : 0, cores);
+    // --gpus N: devices first .. first+N-1 (first = --device, default 0); every device builds the tree, each walks 1/N of the targets
+    const int ngpus = opt.count("gpus") ? std::max(1, atoi(opt["gpus"].c_str())) : 1, first = opt.count("device") ? atoi(opt["device"].c_str()) : 0;
+    std::vector<int> devs;
+    for (int i = 0; i < ngpus; i++) devs.push_back(first + i);
+    if (opt.count("devices")) {                                          // explicit list, e.g. --devices 0,2,4,6
+        devs.clear();
+        const std::string s = opt["devices"];
+        for (size_t a = 0; a < s.size();) { size_t b = s.find(',', a); if (b == std::string::npos) b = s.size(); if (b > a) devs.push_back(atoi(s.substr(a, b - a).c_str())); a = b + 1; }
+        if (devs.empty()) devs.push_back(0);
+    }
+    int rc = agb_multi_create(&d.ctx, devs.data(), (int)devs.size(), cores);
     if (rc != AGB_OK) { fprintf(stderr, "agb200: %s\n", agb_strerror(rc)); return 3; }
-    if (opt.count("precision")) agb_set_option(d.ctx, AGB_OPT_PRECISION, opt["precision"] == "fp64" ? 0 : 1);
+    if (opt.count("precision")) agb_multi_set_option(d.ctx, AGB_OPT_PRECISION, opt["precision"] == "fp64" ? 0 : 1);
     const int64_t max_steps = opt.count("steps") ? atoll(opt["steps"].c_str()) : -1;
     rc = device_resident ? d.run_device(max_steps, outdir) : d.run(max_steps, outdir);
     if (opt.count("dump")) save_agp(opt["dump"], d.p);
-    agb_destroy(d.ctx);
+    agb_multi_destroy(d.ctx);
     return rc;
 }

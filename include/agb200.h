@@ -189,6 +189,36 @@ int agb_get_stream(agb_ctx* ctx, void** stream);
 /* Number of kernels this context launched since creation. */
 int agb_get_launch_count(agb_ctx* ctx, int64_t* launches);
 
+/* -------- several GPUs of one box behind one handle.  The reference's data-parallel axis is the loop
+ * over force targets against one shared tree (Tree::calculateForces, Tree.cpp:65).  Every device receives the whole particle
+ * set, builds the same tree and computes the same densities, walks its own slice of the tree-ordered targets, and the slices'
+ * (index, acc, dU/dt) are exchanged over peer-to-peer copies, so every device ends with the complete result arrays — bit-identical
+ * to a single-GPU run, for any number of devices.  One process, one host thread per device inside the calls, no NCCL.
+ * devices = NULL selects 0 .. ndev-1.  Same call order and meaning as the single-context functions above; particle arrays are
+ * HOST arrays; agb_multi_get_results fills caller-order host arrays (each device sends 1/ndev of the rows over its own link). */
+typedef struct agb_multi agb_multi;
+int agb_multi_create(agb_multi** out, const int* devices, int ndev, int compat_cores);
+int agb_multi_destroy(agb_multi* m);
+int agb_multi_device_count(agb_multi* m);
+int agb_multi_context(agb_multi* m, int i, agb_ctx** ctx);              /* the i-th device's context (counters, timings) */
+int agb_multi_set_option(agb_multi* m, int option, int64_t value);
+int agb_multi_set_particles(agb_multi* m, const agb_particles* p);
+int agb_multi_set_particles_aos(agb_multi* m, void* const* particles, int64_t n, const agb_aos_layout* layout);
+int agb_multi_build_tree(agb_multi* m, double* root_radius);
+int agb_multi_visual_density(agb_multi* m, double visual_density_radius);
+int agb_multi_gas_density(agb_multi* m, double mass_in_h);
+int agb_multi_forces(agb_multi* m, double global_time, double e0, double theta);
+int agb_multi_force_path(agb_multi* m, double visual_density_radius, double mass_in_h, double global_time, double e0, double theta, double* root_radius);
+int agb_multi_get_results(agb_multi* m, const agb_results* r);
+int agb_multi_get_results_aos(agb_multi* m, void* const* particles, int64_t n, const agb_aos_layout* layout);
+/* device-resident loop: the integrator kernels run replicated on every device, only the slices' results cross NVLink */
+int agb_multi_integrator_init(agb_multi* m, double eta, double min_time_step, double max_time_step, double H0, double e0);
+int agb_multi_integrator_assign_all(agb_multi* m);
+int agb_multi_step_begin(agb_multi* m, double* global_time);
+int agb_multi_step_end(agb_multi* m);
+int agb_multi_get_state(agb_multi* m, double* x, double* y, double* z, double* vx, double* vy, double* vz, double* U, double* next_time, double* time_step);
+const char* agb_multi_last_error(agb_multi* m);
+
 /* Roofline denominators measured on this device with tiny kernels (not part of the force path):
  * kind 0 = FP64 FMA throughput [TFLOP/s], 1 = FP32 FMA throughput [TFLOP/s], 2 = HBM copy bandwidth [GB/s]. */
 int agb_microbench(agb_ctx* ctx, int kind, double* result);

@@ -12,25 +12,34 @@
 // does exactly that with the test harness as the driver; tests/test_gpu_integration.py compares its output with
 // the CPU reference.  No reference source is copied: only its public headers are included at compile time.
 //
-// State kept across steps: one agb_ctx per process (pooled device memory), created on first use with
+// State kept across steps: one handle per process (pooled device memory), created on first use with
 // compat_cores = omp_get_max_threads() — the value the reference passes to Node::insert (Tree.cpp:44-48).
+// Devices: AGB_DEVICES="0,1,2,3" (several GPUs of the box: every one builds the tree, each walks a share of the
+// targets — the reference's `#pragma omp parallel for` over targets, Tree.cpp:65) or AGB_DEVICE=<n> (default 0).
 #include <cstddef>
 #include <cstdio>
 #include <cstdlib>
 #include <omp.h>
+#include <string>
+#include <vector>
 
 #include "Tree.h"
 #include "agb200.h"
 
 namespace {
 
-agb_ctx* g_ctx = nullptr;
+agb_multi* g_ctx = nullptr;
 
-agb_ctx* context()
+agb_multi* context()
 {
     if (!g_ctx) {
-        const char* dev = getenv("AGB_DEVICE");
-        int rc = agb_create(&g_ctx, dev ? atoi(dev) : 0, omp_get_max_threads());
+        std::vector<int> devs;
+        if (const char* list = getenv("AGB_DEVICES")) {
+            std::string s(list);
+            for (size_t a = 0; a < s.size();) { size_t b = s.find(',', a); if (b == std::string::npos) b = s.size(); if (b > a) devs.push_back(atoi(s.substr(a, b - a).c_str())); a = b + 1; }
+        }
+        if (devs.empty()) { const char* dev = getenv("AGB_DEVICE"); devs.push_back(dev ? atoi(dev) : 0); }
+        int rc = agb_multi_create(&g_ctx, devs.data(), (int)devs.size(), omp_get_max_threads());
         if (rc != AGB_OK) {
             std::fprintf(stderr, "agb200: %s\n", agb_strerror(rc));   // no CPU fallback: the run cannot continue
             std::abort();
@@ -44,7 +53,7 @@ agb_ctx* context()
 void check(int rc, const char* what)
 {
     if (rc == AGB_OK) return;
-    std::fprintf(stderr, "agb200: %s failed: %s (%s)\n", what, agb_strerror(rc), agb_last_error(g_ctx));
+    std::fprintf(stderr, "agb200: %s failed: %s (%s)\n", what, agb_strerror(rc), agb_multi_last_error(g_ctx));
     std::abort();
 }
 
@@ -75,26 +84,26 @@ Tree::~Tree()
 
 void Tree::buildTree()
 {
-    agb_ctx* c = context();
+    agb_multi* c = context();
     root = new Node();
     root->position = vec3(0.0, 0.0, 0.0);
     root->depth = 0;
-    check(agb_set_particles_aos(c, reinterpret_cast<void* const*>(simulation->particles.data()), simulation->numberOfParticles, &layout()), "set_particles");
+    check(agb_multi_set_particles_aos(c, reinterpret_cast<void* const*>(simulation->particles.data()), simulation->numberOfParticles, &layout()), "set_particles");
     double R = 0.0;
-    check(agb_build_tree(c, &R), "build_tree");
+    check(agb_multi_build_tree(c, &R), "build_tree");
     root->radius = R;
 }
 
 double Tree::calcTreeWidth() { return root ? root->radius : 0.0; }
 
-void Tree::calcVisualDensity() { check(agb_visual_density(context(), simulation->visualDensityRadius), "visual_density"); }
+void Tree::calcVisualDensity() { check(agb_multi_visual_density(context(), simulation->visualDensityRadius), "visual_density"); }
 
-void Tree::calcGasDensity() { check(agb_gas_density(context(), simulation->massInH), "gas_density"); }
+void Tree::calcGasDensity() { check(agb_multi_gas_density(context(), simulation->massInH), "gas_density"); }
 
 void Tree::calculateForces()
 {
-    agb_ctx* c = context();
-    check(agb_forces(c, simulation->globalTime, simulation->e0, simulation->theta), "forces");
+    agb_multi* c = context();
+    check(agb_multi_forces(c, simulation->globalTime, simulation->e0, simulation->theta), "forces");
     // the reference writes acc, dUdt, h, rho, P, T, visualDensity straight into Particle; copy them back
-    check(agb_get_results_aos(c, reinterpret_cast<void* const*>(simulation->particles.data()), simulation->numberOfParticles, &layout()), "get_results");
+    check(agb_multi_get_results_aos(c, reinterpret_cast<void* const*>(simulation->particles.data()), simulation->numberOfParticles, &layout()), "get_results");
 }

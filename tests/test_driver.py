@@ -183,3 +183,27 @@ def test_unknown_output_format_is_rejected():
         open(cfg, "w").write("numberOfParticles = 240\ninputPath = in.age\ninputDataFormat = age\noutputDataFormat = hdf5\n")
         r = subprocess.run([b, "--config", cfg, "--input-root", SNAP, "--snapshot-only", d], capture_output=True, text=True)
         assert r.returncode == 2 and "Unknown output data format" in r.stderr         # DataManager.cpp:106-110 (hdf5 is a stub, :259)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("resident", [False, True], ids=["host-loop", "device-resident"])
+def test_driver_several_devices_reproduce_one_device(pkg, resident):
+    """agb_sim on several devices (agb_multi_*; the same device twice on a one-GPU box) writes the same final state, bit for bit."""
+    import torch
+    b = ensure_bin()
+    from oracle import agio
+    p = pkg.ics.plummer(6000, seed=43, gas_fraction=0.3)
+    mh = pkg.ics.gas_mass_in_h(p, 16)
+    par = dict(n=6000, eta=0.02, max_ts=1e13, min_ts=1e10, e0=1e18, mh=repr(mh))
+    devs = "0,1" if torch.cuda.device_count() >= 2 else "0,0"
+    outs = []
+    with tempfile.TemporaryDirectory() as d:
+        agio.write_agp(os.path.join(d, "ic.agp"), p)
+        open(os.path.join(d, "Config.ini"), "w").write(CONFIG.format(**par))
+        for tag, extra in (("one", []), ("many", ["--devices", devs])):
+            out = os.path.join(d, tag + ".agp")
+            r = subprocess.run([b, "--config", os.path.join(d, "Config.ini"), "--input-root", d, "--steps", "5", "--cores", "8", "--dump", out] + extra +
+                               (["--device-resident"] if resident else []), capture_output=True, text=True)
+            assert r.returncode == 0, r.stderr
+            outs.append((open(out, "rb").read(), open(out + ".acc", "rb").read()))
+    assert outs[0] == outs[1]
