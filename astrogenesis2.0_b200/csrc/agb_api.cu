@@ -92,6 +92,8 @@ void free_pool(agb_ctx* c)
     dfree(d.lcp); dfree(d.nodecnt); dfree(d.leafparent); dfree(d.group); dfree(d.leafdepth);
     dfree(d.leafmark); dfree(d.gasrank);
     dfree(d.rec); dfree(d.grec); dfree(d.blockhist); dfree(d.scanblk);
+    for (auto& q : d.dk) dfree(q);
+    dfree(d.kex);
     dfree(d.far_list); dfree(d.far_front); dfree(d.far_cnt); dfree(d.act_list);
     dfree(d.c_visits); dfree(d.c_accn); dfree(d.c_accl); dfree(d.c_sph);
     dfree(d.rec_ent); dfree(d.rec_next); dfree(d.rec_head); d.rec_cap = 0;
@@ -113,6 +115,8 @@ int ensure_nodes(agb_ctx* c, int64_t want)
     d.ncap = (int64_t)nc;
     return AGB_OK;
 }
+
+int ensure_deep(agb_ctx* c);
 
 int ensure_pool(agb_ctx* c, int64_t n)
 {
@@ -142,7 +146,21 @@ int ensure_pool(agb_ctx* c, int64_t n)
     CK(dalloc(d.blockhist, agb_sort_scratch_words((int64_t)cap)));               // digit totals, tickets and look-back status words of the 8 sort passes
     CK(dalloc(d.scanblk, (cap + 2047) / 2048 + 1));
     d.cap = (int64_t)cap;
+    if (d.deep) { int rc = ensure_deep(c); if (rc) return rc; }
     return ensure_nodes(c, (int64_t)cap + 1024);
+}
+
+// Three-word keys (63 levels): switched on for good when a two-word build reports particles it cannot tell apart, or more than
+// 4096 of them inside one 21-level cell (a root cube blown up by a few runaway particles: Tree.cpp:85-117 has no outlier guard)
+int ensure_deep(agb_ctx* c)
+{
+    AgbDev& d = c->d;
+    d.deep = true;
+    if (d.kex) return AGB_OK;
+    const size_t cap = (size_t)d.cap;
+    for (auto& q : d.dk) CK(dalloc(q, cap));
+    CK(dalloc(d.kex, cap));
+    return AGB_OK;
 }
 
 int ensure_counters(agb_ctx* c)
@@ -233,7 +251,7 @@ const char* agb_strerror(int st)
     case AGB_ERR_NO_DEVICE: return "no usable CUDA device (sm_100 required; there is no CPU fallback)";
     case AGB_ERR_CUDA: return "CUDA error";
     case AGB_ERR_INVALID: return "invalid argument or call order";
-    case AGB_ERR_DEPTH: return "coincident particles: octree deeper than 42 levels";
+    case AGB_ERR_DEPTH: return "coincident particles: octree deeper than 63 levels";
     case AGB_ERR_UNSUPPORTED: return "parameter range not covered by the parity path";
     case AGB_ERR_NOMEM: return "out of memory / traversal stack overflow";
     }
@@ -456,6 +474,7 @@ int agb_build_tree(agb_ctx* c, double* root_radius)
         CK(cudaGetLastError());
         int rc = fetch_scalars(c);
         if (rc) return rc;
+        if (c->hs.need_deep && !d.deep) { if ((rc = ensure_deep(c))) return rc; attempt = -1; continue; }   // rebuild with three-word keys
         if (c->hs.n_nodes <= d.ncap) break;
         if (attempt >= 1) { c->err = "node table overflow"; return AGB_ERR_NOMEM; }
         if ((rc = grow_nodes(c))) return rc;
@@ -463,7 +482,7 @@ int agb_build_tree(agb_ctx* c, double* root_radius)
     float ms = 0; cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]); c->phase_ms[0] = ms;
     c->hs.R = 0; memcpy(&c->hs.R, &c->hs.Rbits, 8);
     if (root_radius) *root_radius = c->hs.R;
-    if (c->hs.dup_keys > 0) { c->err = "coincident particles (shared 42-level path)"; return AGB_ERR_DEPTH; }
+    if (c->hs.dup_keys > 0) { c->err = "two particles share all 63 octree levels (coincident points)"; return AGB_ERR_DEPTH; }
     c->built = true;
     return AGB_OK;
 }
@@ -598,12 +617,13 @@ int agb_force_path(agb_ctx* c, double visual_density_radius, double mass_in_h, d
     (void)cudaGetLastError();
     c->hs.R = 0; memcpy(&c->hs.R, &c->hs.Rbits, 8);
     if (root_radius) *root_radius = c->hs.R;
+    if (c->hs.need_deep && !d.deep) { c->built = false; c->forces_done = false; return stepwise(); }   // agb_build_tree switches to three-word keys
     if (c->hs.n_nodes > d.ncap) {                                   // node table overflow: every kernel after the node count returned at once
         c->built = false; c->forces_done = false;
         if ((rc = grow_nodes(c))) return rc;
         return stepwise();
     }
-    if (c->hs.dup_keys > 0) { c->built = false; c->forces_done = false; c->err = "coincident particles (shared 42-level path)"; return AGB_ERR_DEPTH; }
+    if (c->hs.dup_keys > 0) { c->built = false; c->forces_done = false; c->err = "two particles share all 63 octree levels (coincident points)"; return AGB_ERR_DEPTH; }
     if ((c->hs.any_gas != 0) != c->gas_hint) { c->gas_hint_valid = false; return stepwise(); }   // gas appeared / vanished: redo with the right kernels
     return rc;
 }
@@ -784,7 +804,7 @@ int agb_get_nodes(agb_ctx* c, int32_t* depth, int64_t* count, int32_t* duplicate
         uint64_t h = khi[(size_t)first[(size_t)k]], l = klo[(size_t)first[(size_t)k]];
         if (dp <= 0) { h = 0; l = 0; }
         else if (dp <= 21) { h &= ~0ull << (63 - 3 * dp); l = 0; }
-        else if (dp < AGB_MAX_LEVELS) { l &= ~0ull << (63 - 3 * (dp - 21)); }
+        else if (dp < 42) { l &= ~0ull << (63 - 3 * (dp - 21)); }   // deeper nodes: all of key_lo belongs to the path
         if (depth) depth[k] = dp;
         if (count) count[k] = (int64_t)last[(size_t)k] - first[(size_t)k] + 1;
         if (duplicated) duplicated[k] = dup[(size_t)k];

@@ -86,9 +86,9 @@ __global__ void k_extent_finish(AgbScalars* s, int nblocks, int64_t n)
     s->mean = mean; s->stdev = sd;
     s->limit = __dadd_rn(mean, __dmul_rn(10.0, sd));     // Tree.cpp:89,105
     s->Rbits = 0ull;
-    s->n_long_runs = 0; s->any_gas = 0; s->n_outliers = 0; s->dup_keys = 0; s->edge_dropped = 0; s->max_depth = 0; s->n_nodes = 0; s->node_overflow = 0;
+    s->n_long_runs = 0; s->any_gas = 0; s->n_outliers = 0; s->dup_keys = 0; s->edge_dropped = 0; s->max_depth = 0; s->n_nodes = 0; s->node_overflow = 0; s->need_deep = 0;
     s->next_uniform = 1; s->grid_bar = 0u; s->grid_bar2 = 0u;
-    for (int k = 0; k < 48; k++) { s->lvl_cnt[k] = 0; s->lvl_cur[k] = 0; }
+    for (int k = 0; k < 64; k++) { s->lvl_cnt[k] = 0; s->lvl_cur[k] = 0; }
 }
 
 __global__ void __launch_bounds__(TPB) k_extent_max(const double4* __restrict__ rec, int64_t n, AgbScalars* s)
@@ -184,6 +184,56 @@ __device__ uint64_t key_lo_of(double px, double py, double pz, double R, AgbScal
     const uint64_t lo = descend21(px, py, pz, c, true, edge2);
     if (edge2 && !edge) atomicAdd(&s->edge_dropped, 1);
     return lo;
+}
+
+// ---- deep builds: all 63 levels of every particle (caller order), digit totals per word by k_hist64, keys of the next
+// word brought into the current order by k_gather_keys
+__global__ void __launch_bounds__(TPB) k_keygen_deep(const double4* __restrict__ rec, const uint8_t* __restrict__ type, int64_t n,
+                                                       uint64_t* __restrict__ khi, uint64_t* __restrict__ klo, uint64_t* __restrict__ kex, uint32_t* __restrict__ perm, AgbScalars* s)
+{
+    int64_t i = (int64_t)blockIdx.x * TPB + threadIdx.x;
+    bool outl = false, edge = false;
+    if (i < n) {
+        const double R = __longlong_as_double((long long)s->Rbits);
+        const double4 r4 = rec[i];
+        const double px = r4.x, py = r4.y, pz = r4.z;
+        uint64_t hi = AGB_OUTLIER_BIT, lo = 0, ex = 0;
+        outl = px < -R || px > R || py < -R || py > R || pz < -R || pz > R;
+        if (!outl) {
+            Cell c{0.0, 0.0, 0.0, R};
+            bool below = false;                                       // bound violations below level 21 only matter for particles that descend that far
+            hi = descend21(px, py, pz, c, false, edge);
+            lo = descend21(px, py, pz, c, true, below);
+            ex = descend21(px, py, pz, c, true, below);
+        }
+        khi[i] = hi; klo[i] = lo; kex[i] = ex;
+        perm[i] = (uint32_t)i | (type[i] == 2 ? AGB_GAS_BIT : 0u);
+    }
+    unsigned mo = __ballot_sync(0xffffffffu, outl), me = __ballot_sync(0xffffffffu, edge);
+    if ((threadIdx.x & 31) == 0) {
+        if (mo) atomicAdd(&s->n_outliers, __popc(mo));
+        if (me) atomicAdd(&s->edge_dropped, __popc(me));
+    }
+}
+
+__global__ void __launch_bounds__(TPB) k_hist64(const uint64_t* __restrict__ key, int64_t n, uint32_t* __restrict__ ghist)
+{
+    __shared__ uint32_t h[8][256];
+    for (int k = threadIdx.x; k < 8 * 256; k += TPB) (&h[0][0])[k] = 0;
+    __syncthreads();
+    for (int64_t i = (int64_t)blockIdx.x * TPB + threadIdx.x; i < n; i += (int64_t)gridDim.x * TPB) {
+        const uint64_t w = key[i];
+#pragma unroll
+        for (int p = 0; p < 8; p++) atomicAdd(&h[p][digit_of(w, 8 * p)], 1u);
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < 8 * 256; k += TPB) { const uint32_t v = (&h[0][0])[k]; if (v) atomicAdd(&ghist[k], v); }
+}
+
+__global__ void __launch_bounds__(TPB) k_gather_keys(const uint64_t* __restrict__ src, const uint32_t* __restrict__ perm, int64_t n, uint64_t* __restrict__ dst)
+{
+    const int64_t i = (int64_t)blockIdx.x * TPB + threadIdx.x;
+    if (i < n) dst[i] = src[perm[i] & AGB_IDX_MASK];
 }
 
 // ------------------------------------------------------------------ LSD radix sort (8-bit digits), one sweep per pass
@@ -335,7 +385,7 @@ __global__ void __launch_bounds__(TPB) k_fix_runs(const uint64_t* __restrict__ h
     while (e + 1 < nt && hi[e + 1] == h) e++;
     const int len = (int)(e - i + 1);
     if (len > FIX_SHORT) {
-        if (len > FIX_LONG_MAX) { atomicAdd(&s->dup_keys, 1); return; }
+        if (len > FIX_LONG_MAX) { s->need_deep = 1; return; }        // the host rebuilds with three-word keys and three sorts
         longlist[atomicAdd(&s->n_long_runs, 1)] = (int32_t)i;
         return;
     }
@@ -469,20 +519,26 @@ __global__ void __launch_bounds__(TPB) k_gather_late(AgbDev d, const uint32_t* _
 }
 
 // ------------------------------------------------------------------ shared levels of neighbours, node counts
-__global__ void __launch_bounds__(TPB) k_lcp(const uint64_t* __restrict__ khi, const uint64_t* __restrict__ klo, int64_t n,
+__global__ void __launch_bounds__(TPB) k_lcp(const uint64_t* __restrict__ khi, const uint64_t* __restrict__ klo, const uint64_t* __restrict__ kex, int64_t n,
                                                int8_t* __restrict__ lcp, int32_t* __restrict__ cnt, AgbScalars* s)
 {
     int64_t i = (int64_t)blockIdx.x * TPB + threadIdx.x;
     if (i >= n) return;
     const int64_t nt = n - s->n_outliers;
+    const bool deep = kex != nullptr;
+    const int cap = deep ? AGB_MAX_LEVELS : AGB_SHALLOW_LEVELS;     // levels this build can tell apart
     int Li = -1, Lm = -1;
     if (i < nt) {
-        uint64_t h = khi[i], l = klo[i];
+        const uint64_t h = khi[i], l = klo[i], x = deep ? kex[i] : 0ull;
         if (i + 1 < nt) {
-            Li = agb_common_levels(h, l, khi[i + 1], klo[i + 1]);
-            if (Li >= AGB_MAX_LEVELS) { atomicAdd(&s->dup_keys, 1); Li = AGB_MAX_LEVELS - 1; }
+            Li = agb_common_levels(h, l, x, khi[i + 1], klo[i + 1], deep ? kex[i + 1] : 0ull, deep);
+            if (Li >= cap) {
+                // shallow build: the third key word is needed (the host rebuilds); deep build: coincident points (Node.cpp:618-666 never returns)
+                if (deep) atomicAdd(&s->dup_keys, 1); else s->need_deep = 1;
+                Li = cap - 1;
+            }
         }
-        if (i > 0) { Lm = agb_common_levels(khi[i - 1], klo[i - 1], h, l); if (Lm >= AGB_MAX_LEVELS) Lm = AGB_MAX_LEVELS - 1; }
+        if (i > 0) { Lm = agb_common_levels(khi[i - 1], klo[i - 1], deep ? kex[i - 1] : 0ull, h, l, x, deep); if (Lm >= cap) Lm = cap - 1; }
         int md = max(Li, Lm) + 1;
         if (md > s->max_depth) atomicMax(&s->max_depth, md);
     }
@@ -559,7 +615,7 @@ __global__ void __launch_bounds__(TPB) k_scan_apply(const int32_t* __restrict__ 
 __global__ void __launch_bounds__(TPB) k_init_nodes(AgbDev d, const AgbScalars* __restrict__ s)
 {
     int64_t k = (int64_t)blockIdx.x * TPB + threadIdx.x;
-    if (s->n_nodes > d.ncap) {                          // more (first particle, depth) pairs than node slots: nothing is written,
+    if (s->n_nodes > d.ncap || s->need_deep) {          // more (first particle, depth) pairs than node slots (or keys too short): nothing is written,
         if (k == 0) const_cast<AgbScalars*>(s)->node_overflow = 1;   // every later kernel of the step returns at once, the host grows the arrays
         return;
     }
@@ -570,29 +626,29 @@ __global__ void __launch_bounds__(TPB) k_init_nodes(AgbDev d, const AgbScalars* 
     d.nmark[k] = 0;
 }
 
-struct KeyView { const uint64_t* hi; const uint64_t* lo; };
+struct KeyView { const uint64_t* hi; const uint64_t* lo; const uint64_t* ex; };     // ex == nullptr: two-word build
 
-// "key j shares >= d levels with (h, l)" for a fixed d: one shift of the xor; key_lo is only read for d > 21
+// "key j shares >= d levels with (h, l, x)" for a fixed d: one shift of the xor; the lower words are only read for d > 21 / d > 42
 struct SharesLevels {
-    KeyView K; uint64_t h, l; int sh_hi, sh_lo; bool deep;
-    __device__ __forceinline__ SharesLevels(KeyView K_, uint64_t h_, uint64_t l_, int d) : K(K_), h(h_), l(l_)
+    KeyView K; uint64_t h, l, x; int word, sh;
+    __device__ __forceinline__ SharesLevels(KeyView K_, uint64_t h_, uint64_t l_, uint64_t x_, int d) : K(K_), h(h_), l(l_), x(x_)
     {
-        deep = d > 21;
-        sh_hi = deep ? 0 : 63 - 3 * d;                // d <= 21: the top 1 + 3 d bits of key_hi (outlier flag + d levels) agree
-        sh_lo = deep ? 63 - 3 * (d - 21) : 0;
+        word = d > 42 ? 2 : d > 21 ? 1 : 0;
+        sh = 63 - 3 * (d - 21 * word);                // the top 1 + 3 d' bits of the deciding word (the flag bit of hi, an always-zero bit otherwise)
     }
     __device__ __forceinline__ bool operator()(int64_t j) const
     {
-        if (!deep) return ((K.hi[j] ^ h) >> sh_hi) == 0ull;
-        return K.hi[j] == h && ((K.lo[j] ^ l) >> sh_lo) == 0ull;
+        if (word == 0) return ((K.hi[j] ^ h) >> sh) == 0ull;
+        if (word == 1) return K.hi[j] == h && ((K.lo[j] ^ l) >> sh) == 0ull;
+        return K.hi[j] == h && K.lo[j] == l && ((K.ex[j] ^ x) >> sh) == 0ull;
     }
 };
 
 // smallest s <= i whose key shares >= d levels with key i
-__device__ __forceinline__ int64_t find_first(KeyView K, int64_t i, int d, uint64_t h, uint64_t l)
+__device__ __forceinline__ int64_t find_first(KeyView K, int64_t i, int d, uint64_t h, uint64_t l, uint64_t x)
 {
     if (d <= 0) return 0;
-    const SharesLevels same(K, h, l, d);
+    const SharesLevels same(K, h, l, x, d);
     int64_t step = 1;
     while (i - step >= 0 && same(i - step)) step <<= 1;
     int64_t lo = max((int64_t)-1, i - step), hi = i - (step >> 1);      // key[lo] fails (or lo == -1), key[hi] passes
@@ -602,19 +658,6 @@ __device__ __forceinline__ int64_t find_first(KeyView K, int64_t i, int d, uint6
     }
     return hi;
 }
-// largest e >= i (e < nt) whose key shares >= d levels with key i
-__device__ __forceinline__ int64_t find_last(KeyView K, int64_t i, int d, uint64_t h, uint64_t l, int64_t nt)
-{
-    if (d <= 0) return nt - 1;
-    int64_t step = 1;
-    while (i + step < nt && agb_common_levels(K.hi[i + step], K.lo[i + step], h, l) >= d) step <<= 1;
-    int64_t hi = min(nt, i + step), lo = i + (step >> 1);                // key[lo] passes, key[hi] fails (or hi == nt)
-    while (hi - lo > 1) {
-        int64_t mid = (lo + hi) >> 1;
-        if (agb_common_levels(K.hi[mid], K.lo[mid], h, l) >= d) lo = mid; else hi = mid;
-    }
-    return lo;
-}
 
 __device__ __forceinline__ int node_id_at(const AgbDev& d, int64_t s, int depth)
 {   // id of the node of depth `depth` whose first particle is s
@@ -622,18 +665,18 @@ __device__ __forceinline__ int node_id_at(const AgbDev& d, int64_t s, int depth)
     return d.nodebase[s] + (depth - Lprev - 1);
 }
 
-__global__ void __launch_bounds__(TPB) k_links(AgbDev d, const uint64_t* __restrict__ khi, const uint64_t* __restrict__ klo, AgbScalars* s)
+__global__ void __launch_bounds__(TPB) k_links(AgbDev d, const uint64_t* __restrict__ khi, const uint64_t* __restrict__ klo, const uint64_t* __restrict__ kex, AgbScalars* s)
 {
     __shared__ int lvl[AGB_MAX_LEVELS + 1];                  // nodes of this block per depth (for the level lists of the upward pass)
     if (threadIdx.x <= AGB_MAX_LEVELS) lvl[threadIdx.x] = 0;
     __syncthreads();
     int64_t i = (int64_t)blockIdx.x * TPB + threadIdx.x;
     const int64_t nt = s->n_in_tree;
-    if (s->n_nodes > d.ncap) return;                         // whole grid: no usable node table this step
+    if (s->node_overflow) return;                            // whole grid: no usable node table this step (k_init_nodes)
     if (i < nt && nt < 2) d.leafdepth[i] = 0;                // a single particle: the root itself is the leaf (Node.cpp:409-418)
     if (i < nt && nt >= 2) {
-    KeyView K{khi, klo};
-    const uint64_t h = khi[i], l = klo[i];
+    KeyView K{khi, klo, kex};
+    const uint64_t h = khi[i], l = klo[i], x = kex ? kex[i] : 0ull;
     const int Li = d.lcp[i], Lm = i > 0 ? (int)d.lcp[i - 1] : -1;
     const int base = d.nodebase[i];
     const int N = (int)d.n;
@@ -645,17 +688,17 @@ __global__ void __launch_bounds__(TPB) k_links(AgbDev d, const uint64_t* __restr
         int par;
         if (dep == Lm + 1) {
             if (dep == 0) par = -1;
-            else { int64_t sfirst = find_first(K, i, dep - 1, h, l); par = node_id_at(d, sfirst, dep - 1); }
+            else { int64_t sfirst = find_first(K, i, dep - 1, h, l, x); par = node_id_at(d, sfirst, dep - 1); }
         } else par = k - 1;
         d.nparent[k] = par;
-        if (par >= 0) d.child[(size_t)par * 8 + agb_octant_at(h, l, dep - 1)] = N + k;
+        if (par >= 0) d.child[(size_t)par * 8 + agb_octant_at(h, l, x, dep - 1)] = N + k;
     }
     // the particle's own leaf hangs below the deepest internal node that contains it
     const int dp = max(Li, Lm);
     int par;
     if (Li > Lm) par = base + (Li - Lm - 1);
-    else { int64_t sfirst = find_first(K, i, dp, h, l); par = node_id_at(d, sfirst, dp); }
-    d.child[(size_t)par * 8 + agb_octant_at(h, l, dp)] = (int32_t)i;
+    else { int64_t sfirst = find_first(K, i, dp, h, l, x); par = node_id_at(d, sfirst, dp); }
+    d.child[(size_t)par * 8 + agb_octant_at(h, l, x, dp)] = (int32_t)i;
     d.leafparent[i] = par;
     d.leafdepth[i] = (int8_t)(dp + 1);
     }
@@ -747,7 +790,7 @@ __global__ void __launch_bounds__(TPB) k_level_lists(AgbDev d, AgbScalars* s, in
     if (threadIdx.x <= AGB_MAX_LEVELS) cnt[threadIdx.x] = 0;
     __syncthreads();
     const int nn = s->n_nodes;
-    if (nn > d.ncap) return;
+    if (s->node_overflow) return;
     const int k = blockIdx.x * TPB + threadIdx.x;
     int dep = -1, r = 0;
     if (k < nn) { dep = d.ndepth[k]; r = atomicAdd(&cnt[dep], 1); }
@@ -785,7 +828,7 @@ template <int MODE>
 __global__ void __launch_bounds__(TPB) k_upward_levels(AgbDev d, AgbScalars* s, const int32_t* __restrict__ list)
 {
     const int nn = s->n_nodes;
-    if (nn > d.ncap || nn < 1) return;
+    if (s->node_overflow || nn < 1) return;
     if (MODE == 2 && !s->any_gas) return;
     const int N = (int)d.n;
     const bool any_gas = s->any_gas != 0;
@@ -880,7 +923,7 @@ __global__ void __launch_bounds__(TPB) k_dump_tree(AgbDev d, const uint64_t* __r
     // keep only the first `ld` levels of the path
     if (ld <= 0) { h = 0; l = 0; }
     else if (ld <= 21) { h &= ~0ull << (63 - 3 * ld); l = 0; }
-    else if (ld < AGB_MAX_LEVELS) { l &= ~0ull << (63 - 3 * (ld - 21)); }
+    else if (ld < 42) { l &= ~0ull << (63 - 3 * (ld - 21)); }      // deeper leaves: all 21 levels of key_lo belong to the path
     ohi[p] = h & ~AGB_OUTLIER_BIT; olo[p] = l;
 }
 
@@ -925,17 +968,33 @@ int agb_launch_keygen(AgbDev& d, AgbScalars* s, cudaStream_t st)
     // digit totals + tickets + status words of the 8 sort passes start at zero
     const size_t nb = (size_t)nblk(d.n, TPB * sort_items(d.n));
     cudaMemsetAsync(d.blockhist, 0, (8 * 256 + 64 + 8 * nb * 256) * sizeof(uint32_t), st);
-    k_keygen<<<nblk(d.n, TPB), TPB, 0, st>>>(d.rec, d.type, d.n, d.khi[0], d.perm[0], s, d.blockhist);
     d.cur = 0;
+    if (d.deep) { k_keygen_deep<<<nblk(d.n, TPB), TPB, 0, st>>>(d.rec, d.type, d.n, d.dk[0], d.dk[1], d.dk[2], d.perm[0], s); return 1; }
+    k_keygen<<<nblk(d.n, TPB), TPB, 0, st>>>(d.rec, d.type, d.n, d.khi[0], d.perm[0], s, d.blockhist);
     return 1;
 }
 
 int agb_launch_sort(AgbDev& d, AgbScalars* s, cudaStream_t st)
 {
+    const int nb = nblk(d.n, TPB);
+    if (d.deep) {
+        // three stable 8-pass sorts, least significant word first: levels 42..62, then 21..41, then the flag + levels 0..20
+        int launches = 0;
+        const size_t snb = (size_t)nblk(d.n, TPB * sort_items(d.n));
+        for (int w = 2; w >= 0; w--) {
+            if (w == 2) cudaMemcpyAsync(d.khi[d.cur], d.dk[2], (size_t)d.n * 8, cudaMemcpyDeviceToDevice, st);   // caller order = the identity permutation
+            else { k_gather_keys<<<nb, TPB, 0, st>>>(d.dk[w], d.perm[d.cur], d.n, d.khi[d.cur]); launches++; }
+            cudaMemsetAsync(d.blockhist, 0, (8 * 256 + 64 + 8 * snb * 256) * sizeof(uint32_t), st);
+            k_hist64<<<std::min(nb, 8 * 148), TPB, 0, st>>>(d.khi[d.cur], d.n, d.blockhist); launches++;
+            launches += sort_items(d.n) == 16 ? sort_passes<16>(d, st) : sort_passes<8>(d, st);
+        }
+        k_gather_keys<<<nb, TPB, 0, st>>>(d.dk[1], d.perm[d.cur], d.n, d.klo[1]);
+        k_gather_keys<<<nb, TPB, 0, st>>>(d.dk[2], d.perm[d.cur], d.n, d.kex);
+        return launches + 2;
+    }
     // key_hi + caller index: 8 passes; the result lands in half 0 again.  key_lo (tree order, klo[1]) is zero except
     // inside runs of equal key_hi, where it is computed on demand and decides the order.
     int launches = sort_items(d.n) == 16 ? sort_passes<16>(d, st) : sort_passes<8>(d, st);
-    const int nb = nblk(d.n, TPB);
     cudaMemsetAsync(d.klo[1], 0, (size_t)d.n * sizeof(uint64_t), st);
     k_fix_runs<<<nb, TPB, 0, st>>>(d.khi[d.cur], d.klo[1], d.perm[d.cur], d.n, d.rec, s, d.nodecnt);
     k_fix_long_runs<<<64, TPB, 0, st>>>(d.khi[d.cur], d.klo[1], d.perm[d.cur], d.n, d.rec, s, d.nodecnt);
@@ -961,7 +1020,7 @@ static int upward_blocks(int nnb)
 int agb_launch_links(AgbDev& d, AgbScalars* s, cudaStream_t st, cudaEvent_t* ev, bool late_gas)
 {
     const int nb = nblk(d.n, TPB);
-    const uint64_t *khi = d.khi[d.cur], *klo = d.klo[1];
+    const uint64_t *khi = d.khi[d.cur], *klo = d.klo[1], *kex = d.deep ? d.kex : nullptr;
     if (d.next) k_next_uniform<<<std::min(nb, 2048), TPB, 0, st>>>(d.next, d.n, s);
     if (late_gas) k_gather<true><<<nb, TPB, 0, st>>>(d, d.perm[d.cur], s);
     else {
@@ -969,14 +1028,14 @@ int agb_launch_links(AgbDev& d, AgbScalars* s, cudaStream_t st, cudaEvent_t* ev,
         k_gather<false><<<nb, TPB, 0, st>>>(d, d.perm[d.cur], s);
     }
     if (ev) cudaEventRecord(ev[0], st);
-    k_lcp<<<nb, TPB, 0, st>>>(khi, klo, d.n, d.lcp, d.nodecnt, s);
+    k_lcp<<<nb, TPB, 0, st>>>(khi, klo, kex, d.n, d.lcp, d.nodecnt, s);
     const int sb = nblk(d.n, SCAN_TILE);
     k_scan_reduce<<<sb, TPB, 0, st>>>(d.nodecnt, d.n, d.scanblk, nullptr);
     k_scan_blocks<<<1, TPB, 0, st>>>(d.scanblk, sb, &s->n_nodes, nullptr, d.n);
     k_scan_apply<<<sb, TPB, 0, st>>>(d.nodecnt, d.n, d.scanblk, d.nodebase, nullptr);
     const int nnb = nblk(d.ncap, TPB);                        // node kernels: one thread per node slot
     k_init_nodes<<<nnb, TPB, 0, st>>>(d, s);
-    k_links<<<nb, TPB, 0, st>>>(d, khi, klo, s);
+    k_links<<<nb, TPB, 0, st>>>(d, khi, klo, kex, s);
     if (ev) cudaEventRecord(ev[1], st);
     // level lists, then the persistent level-by-level upward pass
     k_level_lists<<<nnb, TPB, 0, st>>>(d, s, d.lvl_list);

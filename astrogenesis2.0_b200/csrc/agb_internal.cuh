@@ -15,7 +15,8 @@
 #include <stdint.h>
 #include "../../include/agb200.h"
 
-#define AGB_MAX_LEVELS 42
+#define AGB_MAX_LEVELS 63          /* three key words of 21 levels; the third exists only in 'deep' builds */
+#define AGB_SHALLOW_LEVELS 42      /* key_hi + key_lo: what the default build can tell apart */
 #define AGB_OUTLIER_BIT 0x8000000000000000ull
 #define AGB_GAS_BIT 0x80000000u          /* sort payload: caller index (< 2^30) | "type == 2" */
 #define AGB_IDX_MASK 0x7fffffffu
@@ -54,6 +55,11 @@ struct AgbDev {
     int32_t* gasrank = nullptr;        // exclusive count of gas particles before tree position i
     // scratch
     double4* rec = nullptr;            // caller order: (x, y, z, mass) packed by the extent pass
+    // 'deep' builds (agb_api.cu switches them on when a default build reports need_deep): all three key words of every particle,
+    // three 8-pass sorts.  dk = caller-order key words (hi, lo, ex); kex = levels 42..62 in tree order
+    bool deep = false;
+    uint64_t* dk[3] = {nullptr, nullptr, nullptr};
+    uint64_t* kex = nullptr;
     double4* grec = nullptr;           // caller order, gas only: (vx, vy, vz, U), (mu, rho, P, T) packed before the gather
     uint32_t* blockhist = nullptr;     // radix sort: [256][nblocks]
     int32_t* scanblk = nullptr;
@@ -74,6 +80,7 @@ struct AgbScalars {
     double mean, stdev, limit, R;
     unsigned long long Rbits;
     int32_t n_in_tree, n_outliers, n_nodes, dup_keys, edge_dropped, max_depth;
+    int32_t need_deep;                 // the two-word build met particles that share 42 levels, or > 4096 that share 21: rebuild with full keys
     int32_t n_groups, n_gas_groups, n_gas_orphans, n_active;
     unsigned int walk_next_group;
     unsigned long long cand_cursor;    // bump allocator of the SPH tile records
@@ -83,7 +90,7 @@ struct AgbScalars {
     int32_t walk_overflow, any_gas;
     int32_t next_uniform;              // every particle has the same nextIntegrationTime (fixed-step runs): the gather skips that column
     unsigned int grid_bar, grid_bar2;  // arrival counters of the level-synchronous upward passes (all / mVel only)
-    int32_t lvl_cnt[48], lvl_cur[48];  // internal nodes per depth, fill cursors of the level lists
+    int32_t lvl_cnt[64], lvl_cur[64];  // internal nodes per depth, fill cursors of the level lists
     int32_t node_overflow;             // the build needed more than ncap nodes: nothing past the capacity was written, the host grows and rebuilds
     int32_t n_gas_total, tie_exact, tie_unresolved, n_fold, n_long_runs, n_scan_tmp;
     unsigned long long st_rounds, st_popped, st_mixed, st_open, st_drain;   // walk statistics (tuning)
@@ -126,17 +133,20 @@ void agb_ctx_join_uploads(agb_ctx* c);            // the compute stream waits fo
 int agb_launch_unpermute_counters(AgbDev& d, int32_t* v, int32_t* an, int32_t* al, int32_t* sp, cudaStream_t st);
 
 // ---- small device helpers ----
-__device__ __forceinline__ int agb_octant_at(uint64_t hi, uint64_t lo, int level)
+__device__ __forceinline__ int agb_octant_at(uint64_t hi, uint64_t lo, uint64_t ex, int level)
 {
-    return level < 21 ? (int)((hi >> (60 - 3 * level)) & 7) : (int)((lo >> (60 - 3 * (level - 21))) & 7);
+    return level < 21 ? (int)((hi >> (60 - 3 * level)) & 7) : level < 42 ? (int)((lo >> (60 - 3 * (level - 21))) & 7) : (int)((ex >> (60 - 3 * (level - 42))) & 7);
 }
 
-// number of leading octree levels two keys share (0..42)
-__device__ __forceinline__ int agb_common_levels(uint64_t ahi, uint64_t alo, uint64_t bhi, uint64_t blo)
+// number of leading octree levels two keys share (0..63; 42 is the most a build without the third word can report)
+__device__ __forceinline__ int agb_common_levels(uint64_t ahi, uint64_t alo, uint64_t aex, uint64_t bhi, uint64_t blo, uint64_t bex, bool deep)
 {
     uint64_t xh = ahi ^ bhi;
     if (xh) return (__clzll((long long)xh) - 1) / 3;
     uint64_t xl = alo ^ blo;
     if (xl) return 21 + (__clzll((long long)xl) - 1) / 3;
+    if (!deep) return AGB_SHALLOW_LEVELS;
+    uint64_t xe = aex ^ bex;
+    if (xe) return 42 + (__clzll((long long)xe) - 1) / 3;
     return AGB_MAX_LEVELS;
 }

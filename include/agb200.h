@@ -32,7 +32,7 @@ typedef enum {
     AGB_ERR_NO_DEVICE = 1,      /* no usable sm_100 device / CUDA runtime failure at create      */
     AGB_ERR_CUDA = 2,           /* a CUDA call or kernel failed; agb_last_error() has the text   */
     AGB_ERR_INVALID = 3,        /* bad argument or call order (e.g. forces before build_tree)    */
-    AGB_ERR_DEPTH = 4,          /* two in-tree particles share all 42 octree levels (coincident  */
+    AGB_ERR_DEPTH = 4,          /* two in-tree particles share all 63 octree levels (coincident  */
                                 /* points: the reference recurses without bound, Node.cpp:618-666) */
     AGB_ERR_UNSUPPORTED = 5,    /* parameter range the parity path does not cover (see forces)   */
     AGB_ERR_NOMEM = 6

@@ -375,17 +375,79 @@ def test_small_opening_angle_far_list_overflow(pkg, oracle, ctxs):
     assert_parity(rep)
 
 
-def test_coincident_particles_are_an_error(pkg, ctxs):
-    """Two particles at the same position: the reference recurses until the stack overflows (Node.cpp:618-666); here AGB_ERR_DEPTH."""
-    ctx = ctxs(8)
-    p = pkg.ics.plummer(1000, seed=17)
-    p["x"][10], p["y"][10], p["z"][10] = p["x"][500], p["y"][500], p["z"][500]
-    ctx.set_particles(p)
-    with pytest.raises(pkg.capi.AgbError) as ei:
-        ctx.build_tree()
-    assert ei.value.status == 4
-    with pytest.raises(pkg.capi.AgbError):
-        ctx.forces(0.0, 1e18, 0.5)                                    # no usable tree
+def test_coincident_particles_are_an_error(pkg):
+    """Two particles at the same position: the reference recurses until the stack overflows (Node.cpp:618-666); here AGB_ERR_DEPTH
+    (after the build has switched to three-word keys and found that 63 levels do not separate them either)."""
+    ctx = pkg.Context(0, 8)
+    try:
+        p = pkg.ics.plummer(1000, seed=17)
+        p["x"][10], p["y"][10], p["z"][10] = p["x"][500], p["y"][500], p["z"][500]
+        ctx.set_particles(p)
+        with pytest.raises(pkg.capi.AgbError) as ei:
+            ctx.build_tree()
+        assert ei.value.status == 4 and "63" in str(ei.value)
+        with pytest.raises(pkg.capi.AgbError):
+            ctx.forces(0.0, 1e18, 0.5)                                # no usable tree
+    finally:
+        ctx.close()
+
+
+@pytest.mark.parametrize("mixed", PRECISIONS)
+def test_pairs_closer_than_42_levels(pkg, oracle, mixed):
+    """The reference recurses as deep as two particles need (Node.cpp:618-666).  Pairs 2^-46 .. 2^-55 of the root apart share
+    more levels than key_hi + key_lo hold: the build switches to three-word keys (63 levels) and the tree, the densities and
+    the forces still match the reference's."""
+    p = pkg.ics.plummer(3000, seed=21, gas_fraction=0.3)
+    R = float(np.abs(np.stack([p["x"], p["y"], p["z"]])).max())
+    for j, k in enumerate((46, 50, 55)):
+        a, b = 100 + j, 2000 + j
+        p["x"][b] = p["x"][a] + R * 2.0 ** -k
+        p["y"][b] = p["y"][a]; p["z"][b] = p["z"][a]
+        assert p["x"][b] != p["x"][a]
+    mh = pkg.ics.gas_mass_in_h(p, 16)
+    want = oracle.run(p, 0.5, 1e16, mh, 0.0, 8)
+    assert want["leafdepth"].max() > 43
+    ctx = pkg.Context(0, 8)
+    try:
+        ctx.set_option(pkg.capi.AGB_OPT_TARGET_COUNTERS, 1)
+        ctx.set_option(pkg.capi.AGB_OPT_PRECISION, 1 if mixed else 0)
+        got = run_gpu(pkg, ctx, p, 0.5, 1e16, mh)
+        rep = compare(got, want, p, ctx)
+        assert ctx.counters()["max_depth"] == int(want["leafdepth"].max())
+        assert_parity(rep)
+        # and through the fused call, twice (the context stays on three-word keys)
+        for _ in range(2):
+            ctx.set_particles(dict(p))
+            ctx.force_path(want["R"] / 100000, mh, 0.0, 1e16, 0.5)
+            out = ctx.results()
+            for k in ("ax", "ay", "az", "h", "rho"):
+                assert np.array_equal(out[k], got[k]), k
+    finally:
+        ctx.close()
+
+
+def test_root_cube_blown_up_by_runaway_particles(pkg, oracle):
+    """A few particles far outside (the shipped fixed time step ejects some after a few steps of C3 / C4) inflate the root cube
+    (Tree.cpp:85-117: R = mean + 10 sigma of |x|) until the whole system sits inside one 21-level cell: more than 4096
+    particles share key_hi.  The build falls back to three-word keys and three sorts and still reproduces the reference."""
+    p = pkg.ics.plummer(12000, seed=23, gas_fraction=0.2)
+    a = float(np.abs(np.stack([p["x"], p["y"], p["z"]])).max())
+    rng = np.random.default_rng(4)
+    far = rng.choice(12000, 150, replace=False)                  # > 1 % of the particles: they stay inside mean + 10 sigma and set R
+    u = rng.standard_normal((3, 150)); u /= np.linalg.norm(u, axis=0)
+    for k, c in enumerate(("x", "y", "z")):
+        p[c][far] = u[k] * 3e8 * a * (1.0 + 0.3 * rng.random(150))
+    mh = pkg.ics.gas_mass_in_h(p, 16)
+    want = oracle.run(p, 0.5, 1e16, mh, 0.0, 8)
+    assert want["R"] > 1e8 * a and want["leafdepth"].max() > 30
+    ctx = pkg.Context(0, 8)
+    try:
+        ctx.set_option(pkg.capi.AGB_OPT_TARGET_COUNTERS, 1)
+        got = run_gpu(pkg, ctx, p, 0.5, 1e16, mh)
+        rep = compare(got, want, p, ctx)
+        assert_parity(rep)
+    finally:
+        ctx.close()
 
 
 @pytest.mark.parametrize("theta", [0.0, 1.5])
