@@ -46,7 +46,7 @@ def build_lib(force=False, verbose=False):
             print(out)
         if p.returncode:
             raise RuntimeError("nvcc failed on %s" % src)
-    subprocess.check_call([_nvcc(), "-shared", "-o", LIB] + objs + ["-lcudart", "-lpthread"])
+    subprocess.check_call([_nvcc(), "-shared", "-o", LIB] + objs + ["-lcudart", "-lpthread", "-ldl"])
     return LIB
 
 

@@ -13,17 +13,19 @@ _pu8 = C.POINTER(C.c_uint8)
 AGB_MEM_HOST, AGB_MEM_DEVICE = 0, 1
 AGB_OPT_TARGET_COUNTERS = 1
 AGB_OPT_PRECISION = 2
+AGB_OPT_COOLING = 3
+AGB_OPT_STAR_FORMATION = 4
 
 EXPORTS = [
     "agb_create", "agb_destroy", "agb_set_particles", "agb_set_particles_aos", "agb_build_tree", "agb_visual_density",
     "agb_gas_density", "agb_forces", "agb_forces_slice", "agb_force_path", "agb_get_slice_count", "agb_get_slice_results", "agb_get_slice_results_all", "agb_get_kernel_ms", "agb_get_results", "agb_bind_results", "agb_get_results_aos", "agb_get_counters",
     "agb_set_option", "agb_get_tree_particles", "agb_get_node_count", "agb_get_nodes", "agb_get_target_counters",
     "agb_get_phase_ms", "agb_get_stream", "agb_get_launch_count", "agb_microbench",
-    "agb_integrator_init", "agb_integrator_assign_all", "agb_step_begin", "agb_step_end", "agb_get_state", "agb_strerror", "agb_last_error", "agb_version",
+    "agb_integrator_init", "agb_integrator_assign_all", "agb_step_begin", "agb_step_end", "agb_get_state", "agb_get_subgrid_state", "agb_strerror", "agb_last_error", "agb_version",
     "agb_multi_create", "agb_multi_destroy", "agb_multi_device_count", "agb_multi_context", "agb_multi_set_option", "agb_multi_set_particles",
     "agb_multi_set_particles_aos", "agb_multi_build_tree", "agb_multi_visual_density", "agb_multi_gas_density", "agb_multi_forces", "agb_multi_force_path",
     "agb_multi_get_results", "agb_multi_get_results_aos", "agb_multi_integrator_init", "agb_multi_integrator_assign_all", "agb_multi_step_begin",
-    "agb_multi_step_end", "agb_multi_get_state", "agb_multi_last_error",
+    "agb_multi_step_end", "agb_multi_get_state", "agb_multi_get_subgrid_state", "agb_multi_last_error",
 ]
 
 
@@ -110,6 +112,8 @@ def load(build_if_needed=True):
     lib.agb_step_begin.argtypes = [vp, _pd]
     lib.agb_step_end.argtypes = [vp]
     lib.agb_get_state.argtypes = [vp] + [_pd] * 9
+    if hasattr(lib, "agb_get_subgrid_state"):
+        lib.agb_get_subgrid_state.argtypes = [vp, _pu8, _pd]
     lib.agb_strerror.restype = C.c_char_p
     lib.agb_strerror.argtypes = [C.c_int]
     lib.agb_last_error.restype = C.c_char_p
@@ -135,6 +139,7 @@ def load(build_if_needed=True):
         lib.agb_multi_step_begin.argtypes = [vp, _pd]
         lib.agb_multi_step_end.argtypes = [vp]
         lib.agb_multi_get_state.argtypes = [vp] + [_pd] * 9
+        lib.agb_multi_get_subgrid_state.argtypes = [vp, _pu8, _pd]
         lib.agb_multi_last_error.restype = C.c_char_p
         lib.agb_multi_last_error.argtypes = [vp]
     _lib = lib

@@ -1,6 +1,7 @@
 // agb_api.cu — the C ABI (include/agb200.h) over the device kernels: context, memory pool,
 // particle hand-over, the four Tree calls and result read-back.  Host-side only.
 #include "agb_internal.cuh"
+#include <nvtx3/nvToolsExt.h>
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
@@ -35,6 +36,9 @@ struct agb_ctx {
     uint8_t* in_type = nullptr;
     bool bound = false, have_particles = false, built = false, dens_done = false, forces_done = false;
     bool mixed = true;                  // AGB_OPT_PRECISION
+    bool walked_mixed = false;          // the last walk used the FP32 pair law (mixed_in_range)
+    bool opt_cooling = false; unsigned long long opt_sf_seed = 0;   // AGB_OPT_COOLING, AGB_OPT_STAR_FORMATION
+    double* sfr = nullptr;              // Particle::sfr (device-resident loop)
     bool target_counters = false, counters_valid = false, vis_timed = false, gas_timed = false, build_timed = false;
     double phase_ms[5] = {0, 0, 0, 0, 0};
     int64_t launches = 0;
@@ -50,6 +54,13 @@ struct agb_ctx {
 };
 
 namespace {
+
+// NVTX ranges named like the reference's own phase log (Log::startProcess, Simulation.cpp:120-139 / :256-295), so a timeline
+// of a run reads like its logs/processLog.csv.  Header-only NVTX: a no-op unless a profiler is attached.
+struct Phase {
+    explicit Phase(const char* name) { nvtxRangePushA(name); }
+    ~Phase() { nvtxRangePop(); }
+};
 
 constexpr int64_t SPILL_PER_WARP = 8192;
 
@@ -276,6 +287,7 @@ static void destroy_handles(agb_ctx* c)
     if (c->s) cudaFree(c->s);
     if (c->stage) cudaFreeHost(c->stage);
     if (c->d_min) cudaFree(c->d_min);
+    if (c->sfr) cudaFree(c->sfr);
 }
 
 int agb_create(agb_ctx** out, int device, int compat_cores)
@@ -328,6 +340,8 @@ int agb_set_option(agb_ctx* c, int option, int64_t value)
     if (!c) return AGB_ERR_INVALID;
     if (option == AGB_OPT_TARGET_COUNTERS) { c->target_counters = value != 0; return AGB_OK; }
     if (option == AGB_OPT_PRECISION) { if (value != 0 && value != 1) return AGB_ERR_INVALID; c->mixed = value == 1; return AGB_OK; }
+    if (option == AGB_OPT_COOLING) { c->opt_cooling = value != 0; return AGB_OK; }
+    if (option == AGB_OPT_STAR_FORMATION) { c->opt_sf_seed = (unsigned long long)value; return AGB_OK; }
     return AGB_ERR_INVALID;
 }
 
@@ -463,6 +477,7 @@ static int grow_nodes(agb_ctx* c)
 int agb_build_tree(agb_ctx* c, double* root_radius)
 {
     if (!c || !c->have_particles) return AGB_ERR_INVALID;
+    Phase ph("build tree");
     CK(cudaSetDevice(c->device));
     AgbDev& d = c->d;
     c->built = false; c->dens_done = false; c->forces_done = false; c->counters_valid = false;
@@ -490,6 +505,7 @@ int agb_build_tree(agb_ctx* c, double* root_radius)
 int agb_visual_density(agb_ctx* c, double radius)
 {
     if (!c || !c->built) return AGB_ERR_INVALID;
+    Phase ph("Visual Density");
     CK(cudaSetDevice(c->device));
     if (c->d.n == 0) return AGB_OK;
     CK(cudaEventRecord(c->ev[2], c->st));
@@ -506,6 +522,7 @@ int agb_gas_density(agb_ctx* c, double mass_in_h) { return gas_density_impl(c, m
 static int gas_density_impl(agb_ctx* c, double mass_in_h, bool late_pt)
 {
     if (!c || !c->built) return AGB_ERR_INVALID;
+    Phase ph("SPH density and update");
     CK(cudaSetDevice(c->device));
     c->dens_done = true;
     if (c->d.n == 0) return AGB_OK;
@@ -518,6 +535,17 @@ static int gas_density_impl(agb_ctx* c, double mass_in_h, bool late_pt)
 }
 
 static int forces_impl(agb_ctx* c, double global_time, double e0, double theta, int part, int nparts, bool late_gas);
+
+// The FP32 pair law of the mixed mode works in units of R / 2^16 and keeps r^2 (r^2 + e0^2)^2 inside the FP32 range for
+// separations down to ~1e-12 R and softening lengths between ~1e-10 R and ~50 R (agb_walk.cu).  A root cube blown up by runaway
+// particles (or an exotic unit system) leaves that range: such steps are walked with FP64 pair arithmetic instead.
+static bool mixed_in_range(const agb_ctx* c, double e0)
+{
+    if (!c->mixed) return false;
+    double R = 0; memcpy(&R, &c->hs.Rbits, 8);
+    if (!(R > 0.0)) return true;
+    return e0 >= 1e-10 * R && e0 <= 50.0 * R && c->hs.max_depth <= 40;
+}
 int agb_forces_slice(agb_ctx* c, double global_time, double e0, double theta, int part, int nparts) { return forces_impl(c, global_time, e0, theta, part, nparts, false); }
 
 // late_gas: the tree was built without the gas velocities / U / mu (launch_build(c, true)); they are folded in between the
@@ -528,11 +556,14 @@ static int forces_impl(agb_ctx* c, double global_time, double e0, double theta, 
     // For e0 <= 2.1474836e13 the reference's `abs(e)` (int abs(int), Node.cpp:302,354) can switch to the spline
     // softening length; that branch is not reproduced (dead for every SI configuration).
     if (!(e0 > 2.147483648e13)) { c->err = "e0 <= 2^31 * 1e4: the reference's int-abs softening branch is not covered"; return AGB_ERR_UNSUPPORTED; }
+    Phase ph("Force Calculation");
     CK(cudaSetDevice(c->device));
     AgbDev& d = c->d;
     if (d.n == 0) { c->forces_done = true; return AGB_OK; }
     if (c->target_counters) { int rc = ensure_counters(c); if (rc) return rc; }
-    if (c->hs.any_gas && c->mixed) { int rc = ensure_sph_records(c, 0); if (rc) return rc; }
+    const bool mixed = mixed_in_range(c, e0);                  // with the scalars of the tree the walk will run on (call by call), or of the last step's (agb_force_path)
+    c->walked_mixed = mixed;
+    if (c->hs.any_gas && mixed) { int rc = ensure_sph_records(c, 0); if (rc) return rc; }
     // The targets are the ACTIVE particles in tree order; slice boundaries fall on multiples of 256 of them (the far-field
     // super-groups), so every warp owns the same 32 targets whatever the number of parts: results are bit-identical for
     // 1, 2, 4, 8 GPUs (same groups => same summation order).  The slicing itself happens on the device (agb_walk.cu).
@@ -541,16 +572,16 @@ static int forces_impl(agb_ctx* c, double global_time, double e0, double theta, 
     const bool any_gas = c->hs.any_gas != 0;
     for (int attempt = 0;; attempt++) {
         if (late_gas) {
-            c->launches += agb_launch_walk(d, c->s, global_time, e0, theta, part, nparts, c->target_counters, any_gas, c->mixed, c->sm_count, c->st, c->evw, 1);
+            c->launches += agb_launch_walk(d, c->s, global_time, e0, theta, part, nparts, c->target_counters, any_gas, mixed, c->sm_count, c->st, c->evw, 1);
             if (attempt == 0) {
                 if (c->in_pending) { CK(cudaStreamWaitEvent(c->st, c->ev_in, 0)); c->in_pending = false; }
                 c->launches += agb_launch_late_gas(d, c->s, c->st);
                 int rc = stream_out(c, 6, 7);
                 if (rc) return rc;
             }
-            c->launches += agb_launch_walk(d, c->s, global_time, e0, theta, part, nparts, c->target_counters, any_gas, c->mixed, c->sm_count, c->st, c->evw, 2);
+            c->launches += agb_launch_walk(d, c->s, global_time, e0, theta, part, nparts, c->target_counters, any_gas, mixed, c->sm_count, c->st, c->evw, 2);
         } else
-            c->launches += agb_launch_walk(d, c->s, global_time, e0, theta, part, nparts, c->target_counters, any_gas, c->mixed, c->sm_count, c->st, c->evw, 0);
+            c->launches += agb_launch_walk(d, c->s, global_time, e0, theta, part, nparts, c->target_counters, any_gas, mixed, c->sm_count, c->st, c->evw, 0);
         CK(cudaEventRecord(c->ev[7], c->st));
         CK(cudaGetLastError());
         int rc = fetch_scalars(c);
@@ -602,9 +633,9 @@ int agb_force_path(agb_ctx* c, double visual_density_radius, double mass_in_h, d
     // Host hand-over still uploading (set_particles is asynchronous): in mixed precision only the SPH pair pass needs the gas
     // velocities / U / mu, so the build, the densities and the gravity walk start on the first upload group and the rest of
     // the transfer hides behind them.
-    const bool late_gas = c->in_pending && !c->bound && c->mixed && c->gas_hint;
+    const bool late_gas = c->in_pending && !c->bound && mixed_in_range(c, e0) && c->gas_hint;
     CK(cudaEventRecord(c->ev[8], c->st));
-    launch_build(c, late_gas);
+    { Phase ph("build tree"); launch_build(c, late_gas); }
     CK(cudaEventRecord(c->ev[9], c->st));
     CK(cudaGetLastError());
     c->built = true;
@@ -618,6 +649,7 @@ int agb_force_path(agb_ctx* c, double visual_density_radius, double mass_in_h, d
     c->hs.R = 0; memcpy(&c->hs.R, &c->hs.Rbits, 8);
     if (root_radius) *root_radius = c->hs.R;
     if (c->hs.need_deep && !d.deep) { c->built = false; c->forces_done = false; return stepwise(); }   // agb_build_tree switches to three-word keys
+    if (c->walked_mixed && !mixed_in_range(c, e0)) { c->built = false; c->forces_done = false; return stepwise(); }   // this step's tree left the FP32 range: redo in FP64
     if (c->hs.n_nodes > d.ncap) {                                   // node table overflow: every kernel after the node count returned at once
         c->built = false; c->forces_done = false;
         if ((rc = grow_nodes(c))) return rc;
@@ -881,6 +913,14 @@ int agb_integrator_init(agb_ctx* c, double eta, double min_time_step, double max
     if (kmax - I.k0 >= AGB_INT_BINS) { c->err = "time-step range spans more than 2^126"; return AGB_ERR_UNSUPPORTED; }
     for (int j = 0; j < AGB_INT_BINS; j++) I.scale_tab[j] = exp(H0SI * ldexp(1.0, I.k0 + j));
     I.scale_min = exp(H0SI * min_time_step);
+    // SFR.cpp:21-22: p = 1 - exp(-epsilon * timeStep / t_star), epsilon = 0.1, t_star = 1e15 s
+    for (int j = 0; j < AGB_INT_BINS; j++) I.sf_tab[j] = 1 - exp(-0.1 * ldexp(1.0, I.k0 + j) / 1e15);
+    I.sf_min = 1 - exp(-0.1 * min_time_step / 1e15);
+    I.type = c->in_type;
+    dfree(c->sfr);
+    CK(dalloc(c->sfr, (size_t)d.n));
+    CK(cudaMemsetAsync(c->sfr, 0, (size_t)std::max<int64_t>(d.n, 1) * sizeof(double), c->st));
+    I.sfr = c->sfr;
     if (!c->d_min) CK(cudaMalloc((void**)&c->d_min, sizeof(unsigned long long)));
     if (d.n > 0) c->launches += agb_launch_int_init(d, I, c->st);
     c->int_time = 0.0; c->int_ready = true;
@@ -900,6 +940,7 @@ int agb_integrator_assign_all(agb_ctx* c)
 int agb_step_begin(agb_ctx* c, double* global_time)
 {
     if (!c || !c->int_ready || !global_time) return AGB_ERR_INVALID;
+    Phase ph("first kick");
     CK(cudaSetDevice(c->device));
     AgbDev& d = c->d;
     if (d.n == 0) { *global_time = c->int_time; c->built = false; c->dens_done = false; c->forces_done = false; c->counters_valid = false; return AGB_OK; }
@@ -920,7 +961,9 @@ int agb_step_begin(agb_ctx* c, double* global_time)
 int agb_step_end(agb_ctx* c)
 {
     if (!c || !c->int_ready || !c->forces_done) return AGB_ERR_INVALID;
+    Phase ph("second kick");
     CK(cudaSetDevice(c->device));
+    c->I.cooling = c->opt_cooling ? 1 : 0; c->I.star_formation = c->opt_sf_seed != 0 ? 1 : 0; c->I.seed = c->opt_sf_seed;
     if (c->d.n > 0) c->launches += agb_launch_int_second(c->d, c->I, c->int_time, c->st);             // :296-341
     CK(cudaGetLastError());
     return AGB_OK;
@@ -934,6 +977,16 @@ int agb_get_state(agb_ctx* c, double* x, double* y, double* z, double* vx, doubl
     struct { double* dst; const double* src; } cp[] = {{x, c->in_d[0]}, {y, c->in_d[1]}, {z, c->in_d[2]}, {vx, c->in_d[3]}, {vy, c->in_d[4]}, {vz, c->in_d[5]},
                                                        {U, c->in_d[7]}, {next_time, c->in_d[8]}, {time_step, c->timestep}};
     for (auto& e : cp) if (e.dst && b) CK(cudaMemcpyAsync(e.dst, e.src, b, cudaMemcpyDeviceToHost, c->st));
+    CK(cudaStreamSynchronize(c->st));
+    return AGB_OK;
+}
+
+int agb_get_subgrid_state(agb_ctx* c, uint8_t* type, double* sfr)
+{
+    if (!c || !c->int_ready) return AGB_ERR_INVALID;
+    CK(cudaSetDevice(c->device));
+    if (type && c->d.n) CK(cudaMemcpyAsync(type, c->in_type, (size_t)c->d.n, cudaMemcpyDeviceToHost, c->st));
+    if (sfr && c->d.n) CK(cudaMemcpyAsync(sfr, c->sfr, (size_t)c->d.n * sizeof(double), cudaMemcpyDeviceToHost, c->st));
     CK(cudaStreamSynchronize(c->st));
     return AGB_OK;
 }

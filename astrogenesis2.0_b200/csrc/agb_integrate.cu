@@ -99,15 +99,29 @@ __global__ void __launch_bounds__(TPB) k_int_second(AgbDev d, AgbInt I, double g
     int64_t i = (int64_t)blockIdx.x * TPB + threadIdx.x;
     if (i >= d.n || I.next[i] != gt) return;
     const double dt = I.timestep[i];
-    if (d.type[i] == 2) {                                                // Ueuler
+    int ex;
+    frexp(dt, &ex);
+    const int bin = min(max(ex - 1 - I.k0, 0), AGB_INT_BINS - 1);
+    if (I.type[i] == 2) {
+        const double T = d.T[i], rho = d.rho[i];
+        if (I.cooling) {                                                 // Cooling::coolingRoutine, Cooling.cpp:6-25 (free-free emission)
+            const double rate_cgs = __dmul_rn(__dmul_rn(__dmul_rn(__dmul_rn(1.42e-27, 1.1), __dsqrt_rn(T)), 1e6), 1e6);
+            const double rate = __dmul_rn(rate_cgs, 1e-7);
+            if (rate > 0.0 && rho > 0.0) d.dUdt[i] = __dadd_rn(d.dUdt[i], -__ddiv_rn(rate, rho));
+        }
+        if (I.star_formation && rho > 1e-22 && T < 1e4) {                // SFR::sfrRoutine, SFR.cpp:12-34
+            const double p = dt == I.min_ts ? I.sf_min : I.sf_tab[bin];
+            I.sfr[i] = p;
+            if (agb_u01(I.seed, (unsigned long long)i, gt) < p) { I.type[i] = 1; I.U[i] = 0.0; }   // gas -> star
+        }
+    }
+    if (I.type[i] == 2) {                                                // Ueuler (Simulation.cpp:322-326)
         const double du = d.dUdt[i];
         if (!isnan(du)) I.U[i] = __dadd_rn(I.U[i], __dmul_rn(du, dt));
         d.dUdt[i] = 0.0;
     }
     // exp(H0 dt) comes from a host (libm) table over the power-of-two bins, so the factor is the reference's bit for bit
-    int ex;
-    frexp(dt, &ex);
-    const double scale = dt == I.min_ts ? I.scale_min : I.scale_tab[min(max(ex - 1 - I.k0, 0), AGB_INT_BINS - 1)];
+    const double scale = dt == I.min_ts ? I.scale_min : I.scale_tab[bin];
     I.x[i] = __dmul_rn(I.x[i], scale); I.y[i] = __dmul_rn(I.y[i], scale); I.z[i] = __dmul_rn(I.z[i], scale);
     kick(d, I, i, dt);
     I.next[i] = __dadd_rn(I.next[i], dt);

@@ -13,6 +13,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <string.h>
 #include "../../include/agb200.h"
 
 #define AGB_MAX_LEVELS 63          /* three key words of 21 levels; the third exists only in 'deep' builds */
@@ -104,7 +105,24 @@ struct AgbInt {
     double* timestep;
     double eta, e0, min_ts, max_ts;
     double scale_min; int k0; double scale_tab[AGB_INT_BINS];   // exp(H0 dt) per power-of-two bin 2^(k0 + j), from the host's libm
+    // sub-grid hooks of the second kick (Simulation.cpp:311-320 calls them from there; commented out in the reference)
+    int cooling, star_formation; unsigned long long seed;
+    uint8_t* type; double* sfr;                                  // particle types (gas -> star) and Particle::sfr
+    double sf_min, sf_tab[AGB_INT_BINS];                         // 1 - exp(-epsilon dt / t_star) per time-step bin, from the host's libm
 };
+
+// uniform deviate in [0, 1) of (seed, particle, time): the reference draws rand() / RAND_MAX inside an OpenMP loop (SFR.cpp:25),
+// which is neither reproducible nor thread safe; a counter-based generator gives every (particle, step) its own number
+__host__ __device__ __forceinline__ double agb_u01(unsigned long long seed, unsigned long long particle, double time)
+{
+    unsigned long long tb;
+    memcpy(&tb, &time, 8);
+    unsigned long long z = seed + particle * 0x9E3779B97F4A7C15ull + tb * 0xD1B54A32D192ED03ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    z ^= z >> 31;
+    return (double)(z >> 11) * (1.0 / 9007199254740992.0);
+}
 int agb_launch_int_init(AgbDev& d, const AgbInt& I, cudaStream_t st);
 int agb_launch_int_assign(AgbDev& d, const AgbInt& I, double gt, bool all, cudaStream_t st);
 int agb_launch_int_min(AgbDev& d, const AgbInt& I, unsigned long long* out, cudaStream_t st);

@@ -349,5 +349,6 @@ int agb_multi_step_begin(agb_multi* m, double* global_time)
 int agb_multi_step_end(agb_multi* m) { return m ? fan_out(m, [&](int i) { return agb_step_end(m->ctx[(size_t)i]); }) : AGB_ERR_INVALID; }
 int agb_multi_get_state(agb_multi* m, double* x, double* y, double* z, double* vx, double* vy, double* vz, double* U, double* next_time, double* time_step)
 { return m ? agb_get_state(m->ctx[0], x, y, z, vx, vy, vz, U, next_time, time_step) : AGB_ERR_INVALID; }
+int agb_multi_get_subgrid_state(agb_multi* m, uint8_t* type, double* sfr) { return m ? agb_get_subgrid_state(m->ctx[0], type, sfr) : AGB_ERR_INVALID; }
 
 } // extern "C"

@@ -224,6 +224,12 @@ class Context:
         capi.check(self.h, self.lib.agb_get_state(self.h, *[capi.dptr(out[k]) for k in names]))
         return out
 
+    def subgrid_state(self):
+        """(type, sfr) after device-resident steps with AGB_OPT_COOLING / AGB_OPT_STAR_FORMATION."""
+        t = np.empty(self.n, np.uint8); s = np.empty(self.n)
+        capi.check(self.h, self.lib.agb_get_subgrid_state(self.h, capi.dptr(t, C.c_uint8), capi.dptr(s)))
+        return t, s
+
     def microbench(self, kind):
         """0: FP64 FMA TFLOP/s, 1: FP32 FMA TFLOP/s, 2: HBM copy GB/s (measured, not part of the path)."""
         v = C.c_double()

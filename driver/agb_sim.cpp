@@ -96,13 +96,13 @@ bool load_config(const std::string& path, Config& c)
 
 struct Particles {
     int64_t n = 0;
-    std::vector<double> x, y, z, vx, vy, vz, mass, U, next, mu, rho, P, T, h, dUdt, ax, ay, az, vis, timeStep;
+    std::vector<double> x, y, z, vx, vy, vz, mass, U, next, mu, rho, P, T, h, dUdt, ax, ay, az, vis, timeStep, sfr;
     std::vector<uint8_t> type, galaxyPart;
     std::vector<uint32_t> id;
     void resize(int64_t m)
     {
         n = m;
-        for (auto* v : {&x, &y, &z, &vx, &vy, &vz, &mass, &U, &next, &rho, &P, &T, &h, &dUdt, &ax, &ay, &az, &vis, &timeStep}) v->assign((size_t)m, 0.0);
+        for (auto* v : {&x, &y, &z, &vx, &vy, &vz, &mass, &U, &next, &rho, &P, &T, &h, &dUdt, &ax, &ay, &az, &vis, &timeStep, &sfr}) v->assign((size_t)m, 0.0);
         mu.assign((size_t)m, 0.58);
         type.assign((size_t)m, 1); galaxyPart.assign((size_t)m, 1); id.assign((size_t)m, 0);
     }
@@ -210,7 +210,7 @@ template <class Rec, class Fill> bool save_records(const std::string& path, cons
 bool save_ag(const std::string& path, const Particles& p, int64_t count, double deltaTime, double endTime, double currentTime)
 {
     return save_records<AgRecord>(path, p, count, deltaTime, endTime, currentTime, [&](AgRecord& r, int64_t i) {
-        r.pos[0] = p.x[i]; r.pos[1] = p.y[i]; r.pos[2] = p.z[i]; r.mass = p.mass[i]; r.T = p.T[i]; r.visualDensity = p.vis[i]; r.sfr = 0.0;
+        r.pos[0] = p.x[i]; r.pos[1] = p.y[i]; r.pos[2] = p.z[i]; r.mass = p.mass[i]; r.T = p.T[i]; r.visualDensity = p.vis[i]; r.sfr = p.sfr[i];
         r.type = p.type[i]; r.galaxyPart = p.galaxyPart[i]; r.id = p.id[i];
     });
 }
@@ -218,7 +218,7 @@ bool save_ag(const std::string& path, const Particles& p, int64_t count, double 
 bool save_agc(const std::string& path, const Particles& p, int64_t count, double deltaTime, double endTime, double currentTime)
 {
     return save_records<AgcRecord>(path, p, count, deltaTime, endTime, currentTime, [&](AgcRecord& r, int64_t i) {
-        r.pos[0] = (float)p.x[i]; r.pos[1] = (float)p.y[i]; r.pos[2] = (float)p.z[i]; r.visualDensity = (float)p.vis[i]; r.sfr = 0.f; r.T = (float)p.T[i];
+        r.pos[0] = (float)p.x[i]; r.pos[1] = (float)p.y[i]; r.pos[2] = (float)p.z[i]; r.visualDensity = (float)p.vis[i]; r.sfr = (float)p.sfr[i]; r.T = (float)p.T[i];
         r.type = p.type[i]; r.galaxyPart = p.galaxyPart[i];
     });
 }
@@ -456,6 +456,14 @@ struct Driver {
     Config cfg; Particles p; agb_multi* ctx = nullptr; PhaseLog log;     // one handle for --gpus N devices (N = 1: a plain context behind it)
     double globalTime = 0, visualDensityRadius = 0;
     bool device_resident = false;
+    unsigned long long sf_seed = 1;                                      // --sf-seed (star formation draws; the same numbers in both loops)
+    static double u01(unsigned long long seed, unsigned long long particle, double time)     // agb_u01 of the library (splitmix64 of seed, particle, time bits)
+    {
+        unsigned long long tb; memcpy(&tb, &time, 8);
+        unsigned long long z = seed + particle * 0x9E3779B97F4A7C15ull + tb * 0xD1B54A32D192ED03ull;
+        z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull; z = (z ^ (z >> 27)) * 0x94D049BB133111EBull; z ^= z >> 31;
+        return (double)(z >> 11) * (1.0 / 9007199254740992.0);
+    }
 
     void force_path(bool first)
     {
@@ -528,6 +536,7 @@ struct Driver {
         agb_results out{p.ax.data(), p.ay.data(), p.az.data(), p.dUdt.data(), p.h.data(), p.rho.data(), p.P.data(), p.T.data(), p.vis.data()};
         check(ctx, agb_multi_get_results(ctx, &out), "get_results");
         check(ctx, agb_multi_get_state(ctx, p.x.data(), p.y.data(), p.z.data(), p.vx.data(), p.vy.data(), p.vz.data(), p.U.data(), p.next.data(), p.timeStep.data()), "get_state");
+        if (cfg.cooling || cfg.starFormation) check(ctx, agb_multi_get_subgrid_state(ctx, p.type.data(), p.sfr.data()), "get_subgrid_state");
     }
     int run_device(int64_t max_steps, const std::string& outdir)
     {
@@ -614,6 +623,18 @@ struct Driver {
             for (int64_t i = 0; i < n; i++)
                 if (globalTime == p.next[i]) {
                     const double dt = p.timeStep[i];
+                    if (p.type[i] == 2) {
+                        // the sub-grid hooks the reference calls from here (commented out in its source, Simulation.cpp:311-320)
+                        if (cfg.cooling) {                                // Cooling.cpp:6-25
+                            const double rate = 1.42e-27 * 1.1 * std::sqrt(p.T[i]) * 1e6 * 1e6 * 1e-7;
+                            if (rate > 0 && p.rho[i] > 0) p.dUdt[i] -= rate / p.rho[i];
+                        }
+                        if (cfg.starFormation && p.rho[i] > 1e-22 && p.T[i] < 1e4) {   // SFR.cpp:12-34, counter-based deviate instead of rand()
+                            const double pr = 1 - std::exp(-0.1 * dt / 1e15);
+                            p.sfr[i] = pr;
+                            if (u01(sf_seed, (unsigned long long)i, globalTime) < pr) { p.type[i] = 1; p.U[i] = 0.0; }
+                        }
+                    }
                     if (p.type[i] == 2) {                                // Ueuler, TimeIntegration.cpp:28-41
                         if (!std::isnan(p.dUdt[i])) p.U[i] += p.dUdt[i] * dt;
                         p.dUdt[i] = 0;
@@ -694,6 +715,9 @@ int main(int argc, char** argv)
     int rc = agb_multi_create(&d.ctx, devs.data(), (int)devs.size(), cores);
     if (rc != AGB_OK) { fprintf(stderr, "agb200: %s\n", agb_strerror(rc)); return 3; }
     if (opt.count("precision")) agb_multi_set_option(d.ctx, AGB_OPT_PRECISION, opt["precision"] == "fp64" ? 0 : 1);
+    if (opt.count("sf-seed")) d.sf_seed = std::max(1ull, strtoull(opt["sf-seed"].c_str(), nullptr, 10));
+    agb_multi_set_option(d.ctx, AGB_OPT_COOLING, d.cfg.cooling ? 1 : 0);
+    agb_multi_set_option(d.ctx, AGB_OPT_STAR_FORMATION, d.cfg.starFormation ? (int64_t)d.sf_seed : 0);
     const int64_t max_steps = opt.count("steps") ? atoll(opt["steps"].c_str()) : -1;
     rc = device_resident ? d.run_device(max_steps, outdir) : d.run(max_steps, outdir);
     if (opt.count("dump")) save_agp(opt["dump"], d.p);

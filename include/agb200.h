@@ -148,6 +148,8 @@ int agb_integrator_assign_all(agb_ctx* ctx);
 int agb_step_begin(agb_ctx* ctx, double* global_time);
 int agb_step_end(agb_ctx* ctx);
 int agb_get_state(agb_ctx* ctx, double* x, double* y, double* z, double* vx, double* vy, double* vz, double* U, double* next_time, double* time_step);
+/* what the sub-grid hooks changed: particle types (gas that became stars) and Particle::sfr (the last conversion probability) */
+int agb_get_subgrid_state(agb_ctx* ctx, uint8_t* type, double* sfr);
 
 /* -------- results (replaces the path's direct writes into Particle) */
 int agb_get_results(agb_ctx* ctx, const agb_results* r, int memspace);
@@ -162,6 +164,11 @@ int agb_get_counters(agb_ctx* ctx, agb_counters* c);
 /* -------- options */
 typedef enum {
     AGB_OPT_TARGET_COUNTERS = 1,    /* 1: also record per-target visit / accept / SPH counts (parity tests) */
+    AGB_OPT_COOLING = 3,            /* device-resident loop: 1 = free-free cooling of active gas in the second kick (Cooling.cpp:6-25;
+                                       the reference ships the call commented out, Simulation.cpp:312-315).  Default 0. */
+    AGB_OPT_STAR_FORMATION = 4,     /* device-resident loop: != 0 = stochastic gas -> star conversion (SFR.cpp:12-34; commented out in the
+                                       reference, Simulation.cpp:316-320); the value seeds a counter-based generator keyed by
+                                       (particle, time) in place of the reference's rand().  Default 0. */
     AGB_OPT_PRECISION = 2           /* arithmetic of the pair forces: 0 = FP64 throughout (agrees with the reference to ~1e-14),
                                        1 = mixed (default): float-float displacements, FP32 law, FP64 accumulation; ~1e-7.
                                        The accepted (target, source) sets, SPH pair sets and densities are identical in both;
@@ -217,6 +224,7 @@ int agb_multi_integrator_assign_all(agb_multi* m);
 int agb_multi_step_begin(agb_multi* m, double* global_time);
 int agb_multi_step_end(agb_multi* m);
 int agb_multi_get_state(agb_multi* m, double* x, double* y, double* z, double* vx, double* vy, double* vz, double* U, double* next_time, double* time_step);
+int agb_multi_get_subgrid_state(agb_multi* m, uint8_t* type, double* sfr);
 const char* agb_multi_last_error(agb_multi* m);
 
 /* Roofline denominators measured on this device with tiny kernels (not part of the force path):

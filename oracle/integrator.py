@@ -26,12 +26,29 @@ def _assign(st, sel, gt, eta, e0, min_ts, max_ts):
     st["next_time"][sel] = gt + ts
 
 
-def run_steps(p, forces, e0, eta, min_ts, max_ts, H0, nsteps):
+def u01(seed, idx, gt):
+    """The library's agb_u01 (agb_internal.cuh): splitmix64 of (seed, particle, time bits) -> [0, 1)."""
+    M = (1 << 64) - 1
+    tb = int(np.float64(gt).view(np.uint64))
+    out = np.empty(len(idx))
+    for k, i in enumerate(idx):
+        z = (seed + int(i) * 0x9E3779B97F4A7C15 + tb * 0xD1B54A32D192ED03) & M
+        z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & M
+        z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & M
+        z ^= z >> 31
+        out[k] = (z >> 11) * (1.0 / 9007199254740992.0)
+    return out
+
+
+def run_steps(p, forces, e0, eta, min_ts, max_ts, H0, nsteps, cooling=False, sf_seed=0):
+    """cooling / sf_seed != 0: the sub-grid hooks the reference's loop calls for active gas before Ueuler (Simulation.cpp:311-320,
+    commented out there; Cooling.cpp:6-25, SFR.cpp:12-34 with a counter-based deviate in place of rand())."""
     st = {k: np.array(v, copy=True) for k, v in p.items()}
     n = len(st["x"])
     for k in ("ax", "ay", "az", "dUdt", "h", "vis"):
         st.setdefault(k, np.zeros(n))
     st["timeStep"] = np.zeros(n)
+    st["sfr"] = np.zeros(n)
     gas = st["type"] == 2
     st["T"][gas] = (GAMMA - 1.0) * st["U"][gas] * PRTN * st["mu"][gas] / KB          # Simulation.cpp:108-112
     gt = 0.0
@@ -52,7 +69,23 @@ def run_steps(p, forces, e0, eta, min_ts, max_ts, H0, nsteps):
         for x, v in (("x", "vx"), ("y", "vy"), ("z", "vz")):                           # Drift
             st[x][act] = st[x][act] + st[v][act] * dt[act]
         st.update(forces(st, gt))
+        gas = st["type"] == 2
         ga = act & gas
+        if cooling:                                                                    # Cooling.cpp:6-25
+            rate = 1.42e-27 * 1.1 * np.sqrt(st["T"][ga]) * 1e6 * 1e6 * 1e-7
+            okc = (rate > 0) & (st["rho"][ga] > 0)
+            idx = np.flatnonzero(ga)[okc]
+            st["dUdt"][idx] = st["dUdt"][idx] - rate[okc] / st["rho"][idx]
+        if sf_seed:                                                                    # SFR.cpp:12-34
+            cand = np.flatnonzero(ga & (st["rho"] > 1e-22) & (st["T"] < 1e4))
+            if len(cand):
+                pr = np.array([1 - math.exp(-0.1 * d / 1e15) for d in dt[cand]])
+                st["sfr"][cand] = pr
+                born = cand[u01(sf_seed, cand, gt) < pr]
+                st["type"][born] = 1
+                st["U"][born] = 0.0
+            gas = st["type"] == 2
+            ga = act & gas
         good = ga & ~np.isnan(st["dUdt"])
         st["U"][good] = st["U"][good] + st["dUdt"][good] * dt[good]                    # Ueuler
         st["dUdt"][ga] = 0

@@ -207,3 +207,41 @@ def test_driver_several_devices_reproduce_one_device(pkg, resident):
             assert r.returncode == 0, r.stderr
             outs.append((open(out, "rb").read(), open(out + ".acc", "rb").read()))
     assert outs[0] == outs[1]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("resident", [False, True], ids=["host-loop", "device-resident"])
+def test_subgrid_hooks_cooling_and_star_formation(oracle, pkg, resident):
+    """SURVEY.md §8(f)-4: Cooling::coolingRoutine (Cooling.cpp:6-25) and SFR::sfrRoutine (SFR.cpp:12-34) at the place the
+    reference's loop calls them (Simulation.cpp:311-320; commented out there, so parity is pinned by the numpy restatement
+    only), with a counter-based deviate keyed by (seed, particle, time) in place of rand().  The same particles become
+    stars in the host loop, in the device-resident loop and in the restatement."""
+    b = ensure_bin()
+    from oracle import agio, integrator
+    p = pkg.ics.plummer(3000, seed=42, gas_fraction=0.3)
+    for k in ("x", "y", "z"):
+        p[k] = p[k] * 0.2                                             # dense enough for rho > 1e-22 kg/m^3 (SFR.cpp:8)
+    gas = p["type"] == 2
+    p["U"][gas] = np.where(np.arange(gas.sum()) % 2 == 0, 1e8, p["U"][gas])   # half of the gas below T_th = 1e4 K
+    mh = pkg.ics.gas_mass_in_h(p, 16)
+    nsteps = 4           # with this crude cooling and steps this long the gas blows up soon after (velocities of 1e23 m/s by step 5)
+    want = integrator.run_steps(p, integrator.oracle_forces(0.5, 1e18, mh, 8), e0=1e18, eta=2.0, min_ts=1e13, max_ts=2e14, H0=70.0, nsteps=nsteps,
+                                cooling=True, sf_seed=7)
+    born = want["type"] != p["type"]
+    assert born.sum() >= 3
+    par = dict(n=3000, eta=2.0, max_ts=2e14, min_ts=1e13, e0=1e18, mh=repr(mh))
+    with tempfile.TemporaryDirectory() as d:
+        agio.write_agp(os.path.join(d, "ic.agp"), p)
+        open(os.path.join(d, "Config.ini"), "w").write(CONFIG.format(**par).replace("starformation = false", "starformation = true").replace("cooling = false", "cooling = true"))
+        out = os.path.join(d, "final.agp")
+        r = subprocess.run([b, "--config", os.path.join(d, "Config.ini"), "--input-root", d, "--steps", str(nsteps), "--cores", "8", "--precision", "fp64",
+                            "--sf-seed", "7", "--dump", out] + (["--device-resident"] if resident else []), capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        got = agio.read_agp(out)
+    assert ("globalTime %.17g" % want["globalTime"]) in r.stdout
+    assert np.array_equal(got["type"], want["type"])                                  # the same gas particles became stars
+    assert np.all(got["U"][born] == 0.0)
+    still = want["type"] == 2
+    assert np.allclose(got["U"][still], want["U"][still], rtol=1e-8, atol=0)          # cooling included
+    uncooled = integrator.run_steps(p, integrator.oracle_forces(0.5, 1e18, mh, 8), e0=1e18, eta=2.0, min_ts=1e13, max_ts=2e14, H0=70.0, nsteps=1)
+    assert not np.allclose(want["U"][still], uncooled["U"][still])
