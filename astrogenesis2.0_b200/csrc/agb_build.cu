@@ -141,6 +141,37 @@ __device__ __forceinline__ uint64_t descend21(double px, double py, double pz, C
 
 __device__ __forceinline__ uint32_t digit_of(uint64_t w, int shift) { return (uint32_t)(w >> shift) & 255u; }
 
+// 21 bits -> every third bit of a 63-bit word (bit b -> bit 3 b)
+__device__ __forceinline__ uint64_t spread3(uint64_t v)
+{
+    v &= 0x1fffffull;
+    v = (v | (v << 32)) & 0x001f00000000ffffull;
+    v = (v | (v << 16)) & 0x001f0000ff0000ffull;
+    v = (v | (v << 8)) & 0x100f00f00f00f00full;
+    v = (v | (v << 4)) & 0x10c30c30c30c30c3ull;
+    v = (v | (v << 2)) & 0x1249249249249249ull;
+    return v;
+}
+
+// The first 21 levels without the descent, for all but ~1e-5 of the particles.  The reference's cell centres are the rounded
+// chain c_{l+1} = rn(c_l +- R 2^-(l+1)) (Node.cpp:436-440): each step is off by <= ulp(R)/2, so every centre of levels 0..20
+// lies within 11 ulp(R) < 2^-48 R of the exact value R (m / 2^l).  In the coordinate s = (x / R + 1) 2^20 in [0, 2^21] those
+// centres are integers; s itself is computed to ~2^-29.  A particle whose s is further than 2^-20 from every integer on all
+// three axes (2^-40 R in space) therefore takes all 21 strict comparisons, and the inclusive cell-bound tests (Node.cpp:606-612),
+// exactly as the descent does, and its octants are the bits of floor(s).  Everything else takes the descent.
+__device__ __forceinline__ bool key_hi_fast(double px, double py, double pz, double invR, uint64_t* key)
+{
+    const double sx = fma(px, invR, 1.0) * 1048576.0, sy = fma(py, invR, 1.0) * 1048576.0, sz = fma(pz, invR, 1.0) * 1048576.0;
+    const double fx = floor(sx), fy = floor(sy), fz = floor(sz);
+    const double dx = sx - fx, dy = sy - fy, dz = sz - fz;
+    const double lo = 9.5367431640625e-07, hi = 1.0 - 9.5367431640625e-07;         // 2^-20
+    if (!(dx > lo && dx < hi && dy > lo && dy < hi && dz > lo && dz < hi)) return false;
+    if (!(fx >= 0.0 && fx < 2097152.0 && fy >= 0.0 && fy < 2097152.0 && fz >= 0.0 && fz < 2097152.0)) return false;
+    const uint64_t kx = (uint64_t)fx, ky = (uint64_t)fy, kz = (uint64_t)fz;     // bit (20 - l) = "above the centre" at level l
+    *key = spread3(kx) | (spread3(ky) << 1) | (spread3(kz) << 2);                 // level l at bit 60 - 3 l = 3 (20 - l)
+    return true;
+}
+
 // key_hi (outlier flag + levels 0..20) for every particle; key_lo is produced on demand by key_lo_of().
 // The digit histograms of all 8 radix passes are counted here as well (block-private counters in shared memory, one
 // global add per non-empty bin), so the sort needs no histogram pass of its own.
@@ -160,7 +191,7 @@ __global__ void __launch_bounds__(TPB) k_keygen(const double4* __restrict__ rec,
         // root cube is centred on the origin (Tree.cpp:31); inclusive bounds (Node.cpp:706-711)
         outl = px < -R || px > R || py < -R || py > R || pz < -R || pz > R;
         if (outl) hi = AGB_OUTLIER_BIT;           // the stable sort keeps caller order among the outliers
-        else { Cell c{0.0, 0.0, 0.0, R}; hi = descend21(px, py, pz, c, false, edge); }
+        else if (!key_hi_fast(px, py, pz, 1.0 / R, &hi)) { Cell c{0.0, 0.0, 0.0, R}; hi = descend21(px, py, pz, c, false, edge); }
         khi[i] = hi; perm[i] = (uint32_t)i | (type[i] == 2 ? AGB_GAS_BIT : 0u);   // the sort payload also carries "is gas"
 #pragma unroll
         for (int p = 0; p < 8; p++) atomicAdd(&h[p][digit_of(hi, 8 * p)], 1u);
@@ -741,7 +772,7 @@ __device__ __forceinline__ void node_moments(const AgbDev& d, int k, int N, bool
         for (int o = 0; o < 8; o++) {
             const int c = ch[o];
             if (c < 0) continue;
-            if (c < N) { const double4 gv = d.src_gv[c]; gx += gv.x * gv.w; gy += gv.y * gv.w; gz += gv.z * gv.w; }
+            if (c < N) { if (d.src_flag[c]) { const double4 gv = d.src_gv[c]; gx += gv.x * gv.w; gy += gv.y * gv.w; gz += gv.z * gv.w; } }
             else { const double4 gv = ldcg4(&d.mom_gv[c - N]); gx += gv.x; gy += gv.y; gz += gv.z; }
         }
         d.mom_gv[k] = make_double4(gx, gy, gz, own.w);
@@ -764,7 +795,8 @@ __device__ __forceinline__ void node_moments(const AgbDev& d, int k, int N, bool
         const int c = ch[o];
         if (c < 0) continue;
         if (c < N) {
-            double4 pm = d.src_pm[c], gv = d.src_gv[c];
+            // particles without gas carry an all-zero (velocity, gasMass) record: the 1-byte flag (L2 resident) saves its 32-byte read
+            const double4 pm = d.src_pm[c], gv = d.src_flag[c] ? d.src_gv[c] : make_double4(0.0, 0.0, 0.0, 0.0);
             m += pm.w; sx += pm.x * pm.w; sy += pm.y * pm.w; sz += pm.z * pm.w;
             g += gv.w;
             if (MODE == 0) { gx += gv.x * gv.w; gy += gv.y * gv.w; gz += gv.z * gv.w; }
