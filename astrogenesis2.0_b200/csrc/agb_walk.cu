@@ -243,8 +243,9 @@ __global__ void __launch_bounds__(128) k_far(const WalkParams P)
 #pragma unroll
                         for (int c = 0; c < 8; c++) { cl += (ch[c] >= 0 && ch[c] < N); cn += (ch[c] >= N); }
                     }
-                    const int il = warp_incl_scan(cl, lane), in_ = warp_incl_scan(cn, lane);
-                    const int tl = __shfl_sync(0xffffffffu, il, 31), tn = __shfl_sync(0xffffffffu, in_, 31);
+                    // both counts are <= 8 per lane: one scan of the packed pair (leaves in the low half, nodes in the high half)
+                    const int sc = warp_incl_scan(cl | (cn << 16), lane), st_ = __shfl_sync(0xffffffffu, sc, 31);
+                    const int il = sc & 0xffff, in_ = sc >> 16, tl = st_ & 0xffff, tn = st_ >> 16;
                     if (outcome == OUT_OPEN) {
                         int pl = nl + il - cl, pn = sp + in_ - cn;
 #pragma unroll
@@ -535,8 +536,9 @@ __global__ void __launch_bounds__(WalkCfg<SPH>::TPB, WALK_CTAS) k_walk(const Wal
 #pragma unroll
                             for (int c = 0; c < 8; c++) { nl += (ch[c] >= 0 && ch[c] < N); nn += (ch[c] >= N); }
                         }
-                        const int il = warp_incl_scan(nl, lane), in_ = warp_incl_scan(nn, lane);
-                        const int tl = __shfl_sync(0xffffffffu, il, 31), tn = __shfl_sync(0xffffffffu, in_, 31);
+                        // both counts are <= 8 per lane: one scan of the packed pair (leaves in the low half, nodes in the high half)
+                        const int sc = warp_incl_scan(nl | (nn << 16), lane), st_ = __shfl_sync(0xffffffffu, sc, 31);
+                        const int il = sc & 0xffff, in_ = sc >> 16, tl = st_ & 0xffff, tn = st_ >> 16;
                         if (omask != 0u) {
                             int pl = lc + il - nl, pn = sp + in_ - nn;
 #pragma unroll
@@ -578,6 +580,7 @@ __global__ void __launch_bounds__(WalkCfg<SPH>::TPB, WALK_CTAS) k_walk(const Wal
                     float hx = 0, hy = 0, hz = 0, lx = 0, ly = 0, lz = 0, dmin2 = 0;
                     if (lane < cnt) {
                         q = P.src_pm[e.x];
+                        if (SPLIT && wgas) src_gas = P.src_flag[e.x] != 0;          // requested together with the record (the candidate test below needs it)
                         if (INWALK && wgas) { gvv = P.src_gv[e.x]; src_gas = gvv.w > 0.0; }   // independent of the load above
                         if (MIXED) {
                             const double rx = (q.x - cgx) * invR, ry = (q.y - cgy) * invR, rz = (q.z - cgz) * invR;
@@ -619,8 +622,7 @@ __global__ void __launch_bounds__(WalkCfg<SPH>::TPB, WALK_CTAS) k_walk(const Wal
                     if (SPLIT && wgas) {
                         // sources within 2 h_max of the warp's box that a gas target accepted: (source, those targets) for k_sph
                         const unsigned gm = pc_mask & gasl;
-                        bool cand = gm != 0u && dmin2 < cand2;
-                        if (cand) cand = P.src_flag[e.x] != 0;                       // sources without gas never pass Node.cpp:319 / :371
+                        const bool cand = gm != 0u && dmin2 < cand2 && src_gas;     // sources without gas never pass Node.cpp:319 / :371
                         const unsigned cm = __ballot_sync(0xffffffffu, cand);
                         if (cm) {
                             if (cand) sm.rsrc[rfill + __popc(cm & lt)] = make_int2(e.x, (int)gm);
