@@ -46,7 +46,10 @@ constexpr int PCAP = 64;                   // straddling nodes waiting for their
 #define AGB_WALK_CTAS_PER_SM 2
 #endif
 constexpr int WALK_CTAS = AGB_WALK_CTAS_PER_SM;
-constexpr int SCAP = 384;   // shared part of the traversal stack (the rest spills to global memory)
+#ifndef AGB_WALK_SCAP
+#define AGB_WALK_SCAP 384
+#endif
+constexpr int SCAP = AGB_WALK_SCAP;   // shared part of the traversal stack (the rest spills to global memory)
 constexpr double kG = 6.67430e-11;         // Math/Constants.h:7
 constexpr double kPI = 3.14159265358979323846;
 constexpr double kGAMMA = 5.0 / 3.0;
@@ -66,7 +69,9 @@ template <bool SPH, bool MIXED> struct WarpSmem : SphSmem<SPH && !MIXED> {
     int2 pend[PCAP];                       // (node, lane mask) of straddling nodes, resolved 32 at a time (one node per lane, loop over targets)
     float4 tpos[32];                       // minus the targets' positions about the box centre (units of L) + their tree positions
     double4 stage[32];                     // drain: the 32 sources of a tile
+    unsigned long long stat[12];           // per-warp statistics (kept out of the register file): node / leaf / SPH pairs, visits, exact tests, spills, rounds, popped, straddling, opened, tiles
 };
+enum { ST_NODE = 0, ST_LEAF, ST_SPH, ST_VISIT, ST_EXACT, ST_SPILL, ST_ROUNDS, ST_POPPED, ST_MIXED, ST_OPEN, ST_DRAIN };
 // k_sph: per gas target (1/h, 1/(pi h^4), 2 P/rho^2, sound speed), (vx, vy, vz, h), 8 floats: -(float-float position), (2h/L)^2, tree position
 struct SphWarp {
     double4 tsph[96];
@@ -76,7 +81,10 @@ struct SphWarp {
     int list[32];                          // the record's sources
     unsigned lmask[32];                    // ... and the gas targets that accepted each (0 for sources without gas)
 };
-template <bool SPH> struct WalkCfg { static constexpr int WARPS = 8, TPB = WARPS * 32; };
+#ifndef AGB_WALK_WARPS
+#define AGB_WALK_WARPS 8
+#endif
+template <bool SPH> struct WalkCfg { static constexpr int WARPS = AGB_WALK_WARPS, TPB = WARPS * 32; };
 
 // 1/sqrt(x) for positive normal x: MUFU.RSQ64H seed (~2^-22) + one cubically convergent step (~2^-60).
 // None of the special-case handling of the library rsqrt() is needed here (x = 0 is masked by the caller).
@@ -297,8 +305,8 @@ __global__ void __launch_bounds__(WalkCfg<SPH>::TPB, WALK_CTAS) k_walk(const Wal
     const double inv_m0 = 1.0 / m0, acc_scale = kG * m0 * invR2;
     const float e02f = (float)e02s;
 
-    unsigned long long tot_node = 0, tot_leaf = 0, tot_sph = 0, tot_visit = 0, tot_exact = 0, tot_spill = 0;
-    unsigned long long st_rounds = 0, st_popped = 0, st_mixed = 0, st_open = 0, st_drain = 0;
+    if (lane < 12) sm.stat[lane] = 0ull;
+    __syncwarp();
     unsigned long long st_cls[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};   // COUNT only: list entries / set bits by lane span (any, one half, one quarter), far-list entries
 
     auto stack_put = [&](int idx, int2 v) {
@@ -342,6 +350,7 @@ __global__ void __launch_bounds__(WalkCfg<SPH>::TPB, WALK_CTAS) k_walk(const Wal
             }
         }
         double ax = 0, ay = 0, az = 0, dU = 0;
+        int n_sph_lane = 0;                                                      // in-walk SPH pairs of this lane's target
         int c_vis = (active && (n_nodes > 0 || !valid)) ? 1 : 0, c_an = 0, c_al = 0, c_sp = 0;              // the root call itself
         const unsigned vmask = __ballot_sync(0xffffffffu, valid);
         const int tmin = __shfl_sync(0xffffffffu, (int)t, 0), tmax = __reduce_max_sync(0xffffffffu, (int)t);   // targets are sorted by tree position
@@ -439,7 +448,7 @@ __global__ void __launch_bounds__(WalkCfg<SPH>::TPB, WALK_CTAS) k_walk(const Wal
                         sp -= cnt;
                         if (lane < cnt) e = stack_get(sp + lane);
                         __syncwarp();                                        // the slots just read are overwritten by this round's pushes
-                        if (sp + cnt > SCAP) tot_spill += 1;
+                        if (sp + cnt > SCAP && lane == 0) sm.stat[ST_SPILL] += 1;
                         int outcome = OUT_NONE;
                         // the child slots are requested together with the node record (two independent L2 round trips instead
                         // of two dependent ones); they are simply not used when the node turns out to be accepted
@@ -461,7 +470,7 @@ __global__ void __launch_bounds__(WalkCfg<SPH>::TPB, WALK_CTAS) k_walk(const Wal
                         const unsigned mm = __ballot_sync(0xffffffffu, outcome == OUT_MIXED);
                         if (outcome == OUT_MIXED) sm.pend[npend + __popc(mm & lt)] = e;
                         npend += __popc(mm);
-                        if (lane == 0) { st_rounds++; st_popped += cnt; st_mixed += __popc(mm); }
+                        if (lane == 0) { sm.stat[ST_ROUNDS] += 1; sm.stat[ST_POPPED] += cnt; sm.stat[ST_MIXED] += __popc(mm); }
                     } else {
                         // ---- resolve up to 32 parked nodes (the most recent ones)
                         const int nb = min(npend, 32);
@@ -498,7 +507,7 @@ __global__ void __launch_bounds__(WalkCfg<SPH>::TPB, WALK_CTAS) k_walk(const Wal
                                     const double r2e = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
                                     acc = __ddiv_rn(__dsqrt_rn(qw), __dsqrt_rn(r2e)) < theta;      // sqrt(radius^2) is exact: radius = R 2^-k
                                     open = !acc;
-                                    tot_exact++;
+                                    atomicAdd(&sm.stat[ST_EXACT], 1ull);
                                 }
                             }
                         };
@@ -548,7 +557,7 @@ __global__ void __launch_bounds__(WalkCfg<SPH>::TPB, WALK_CTAS) k_walk(const Wal
                             }
                         }
                         lc += tl; sp += tn;
-                        if (lane == 0) st_open += __popc(om);
+                        if (lane == 0) sm.stat[ST_OPEN] += __popc(om);
                     }
                     __syncwarp();
                     // warm L1 with the node records the next round will pop
@@ -559,7 +568,7 @@ __global__ void __launch_bounds__(WalkCfg<SPH>::TPB, WALK_CTAS) k_walk(const Wal
                 }
 
                 // ------------------------------------------------ drain the interaction list
-                if (lane == 0) st_drain += (lc + 31) / 32;
+                if (lane == 0) sm.stat[ST_DRAIN] += (lc + 31) / 32;
                 for (int base = 0; base < lc; base += 32) {
                     const int cnt = min(32, lc - base);
                     __syncwarp();
@@ -617,7 +626,8 @@ __global__ void __launch_bounds__(WalkCfg<SPH>::TPB, WALK_CTAS) k_walk(const Wal
                         if (sl.ident) { if (maybe) pc_mask &= ~(1u << (ex_part - tmin)); }        // every particle active: lane = offset in the group
                         else if (__any_sync(0xffffffffu, maybe))
                             for (int l2 = 0; l2 < 32; l2++) { const int tl = __shfl_sync(0xffffffffu, (int)t, l2); if (ex_part >= 0 && ex_part == tl) pc_mask &= ~(1u << l2); }
-                        if (ex_part >= 0) tot_leaf += __popc(pc_mask); else tot_node += __popc(pc_mask);
+                        const unsigned nlf = __reduce_add_sync(0xffffffffu, ex_part >= 0 ? __popc(pc_mask) : 0), nnd = __reduce_add_sync(0xffffffffu, ex_part >= 0 ? 0 : __popc(pc_mask));
+                        if (lane == 0) { sm.stat[ST_LEAF] += nlf; sm.stat[ST_NODE] += nnd; }
                     }
                     if (SPLIT && wgas) {
                         // sources within 2 h_max of the warp's box that a gas target accepted: (source, those targets) for k_sph
@@ -746,7 +756,7 @@ __global__ void __launch_bounds__(WalkCfg<SPH>::TPB, WALK_CTAS) k_walk(const Wal
                                     // within 1e-13 of the gate: the reference's own separately rounded expression
                                     const double r2e = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
                                     pass = __dsqrt_rn(r2e) < __dmul_rn(h_t, 2.0);
-                                    tot_exact++;
+                                    atomicAdd(&sm.stat[ST_EXACT], 1ull);
                                 }
                                 if (pass) {
                                     const double inv_h = k4.x, inv_pi_h4 = k4.y, cs = k4.w;
@@ -765,7 +775,7 @@ __global__ void __launch_bounds__(WalkCfg<SPH>::TPB, WALK_CTAS) k_walk(const Wal
                                     const double fx = coef * gx, fy = coef * gy, fz = coef * gz;
                                     dU += 0.5 * gv.w * (A2 + MU) * (vx * gx + vy * gy + vz * gz);      // Node.cpp:167
                                     if (!(isnan(fx) || isnan(fy) || isnan(fz))) { ax += fx; ay += fy; az += fz; }   // Node.cpp:169
-                                    tot_sph++;
+                                    n_sph_lane++;
                                     if (COUNT) c_sp++;
                                 }
                             }
@@ -784,21 +794,23 @@ __global__ void __launch_bounds__(WalkCfg<SPH>::TPB, WALK_CTAS) k_walk(const Wal
             P.ax[p] = ax; P.ay[p] = ay; P.az[p] = az;                           // Tree.cpp:77 (acc = 0) + accumulated force
             if (INWALK && tgas && dU != 0.0) P.dUdt[p] += dU;
             if (COUNT) { P.c_visits[t] = c_vis; P.c_accn[t] = c_an; P.c_accl[t] = c_al; P.c_sph[t] = c_sp; }
-            tot_visit += (unsigned long long)c_vis;
+        }
+        {
+            const unsigned nv = __reduce_add_sync(0xffffffffu, active ? (unsigned)c_vis : 0u), ns = __reduce_add_sync(0xffffffffu, (unsigned)n_sph_lane);
+            if (lane == 0) { sm.stat[ST_VISIT] += nv; sm.stat[ST_SPH] += ns; }
         }
     }
 
-    tot_node = warp_sum_u64(tot_node); tot_leaf = warp_sum_u64(tot_leaf); tot_sph = warp_sum_u64(tot_sph);
-    tot_visit = warp_sum_u64(tot_visit); tot_exact = warp_sum_u64(tot_exact); tot_spill = warp_sum_u64(tot_spill);
+    __syncwarp();
     if (lane == 0) {
-        if (tot_node) atomicAdd(&P.s->c_node, tot_node);
-        if (tot_leaf) atomicAdd(&P.s->c_leaf, tot_leaf);
-        if (tot_sph) atomicAdd(&P.s->c_sph, tot_sph);
-        if (tot_visit) atomicAdd(&P.s->c_visits, tot_visit);
-        if (tot_exact) atomicAdd(&P.s->c_exact, tot_exact);
-        if (tot_spill) atomicAdd(&P.s->c_spill, tot_spill);
-        atomicAdd(&P.s->st_rounds, st_rounds); atomicAdd(&P.s->st_popped, st_popped); atomicAdd(&P.s->st_mixed, st_mixed);
-        atomicAdd(&P.s->st_open, st_open); atomicAdd(&P.s->st_drain, st_drain);
+        if (sm.stat[ST_NODE]) atomicAdd(&P.s->c_node, sm.stat[ST_NODE]);
+        if (sm.stat[ST_LEAF]) atomicAdd(&P.s->c_leaf, sm.stat[ST_LEAF]);
+        if (sm.stat[ST_SPH]) atomicAdd(&P.s->c_sph, sm.stat[ST_SPH]);
+        if (sm.stat[ST_VISIT]) atomicAdd(&P.s->c_visits, sm.stat[ST_VISIT]);
+        if (sm.stat[ST_EXACT]) atomicAdd(&P.s->c_exact, sm.stat[ST_EXACT]);
+        if (sm.stat[ST_SPILL]) atomicAdd(&P.s->c_spill, sm.stat[ST_SPILL]);
+        atomicAdd(&P.s->st_rounds, sm.stat[ST_ROUNDS]); atomicAdd(&P.s->st_popped, sm.stat[ST_POPPED]); atomicAdd(&P.s->st_mixed, sm.stat[ST_MIXED]);
+        atomicAdd(&P.s->st_open, sm.stat[ST_OPEN]); atomicAdd(&P.s->st_drain, sm.stat[ST_DRAIN]);
         if (COUNT) for (int c = 0; c < 10; c++) atomicAdd(&P.s->st_cls[c], st_cls[c]);
     }
 }
@@ -1099,7 +1111,7 @@ __global__ void __launch_bounds__(256) k_copy_peak(const double2* __restrict__ i
 }
 
 int agb_walk_blocks(int sm_count) { return sm_count * WALK_CTAS; }
-int agb_walk_warps_per_block() { return 8; }
+int agb_walk_warps_per_block() { return WalkCfg<false>::WARPS; }
 void agb_far_capacity(int* lcap, int* fcap, int* targets) { *lcap = FAR_LCAP; *fcap = FAR_FCAP; *targets = 32 * SG_GROUPS; }
 
 // phase 0: everything; 1: up to and including k_walk; 2: k_sph only (mixed mode with gas: the caller completes a late_gas
