@@ -1018,6 +1018,56 @@ void agb_ctx_internals(agb_ctx* c, AgbDev** d, cudaStream_t* st, int* device)
     if (device) *device = c->device;
 }
 
+// The hand-over `src` (another device) has just received from the host, repeated on `c` by peer-to-peer copies in the same
+// three groups and on the same two streams as agb_set_particles, each group as soon as the source has it: several GPUs behind
+// one handle read the host arrays once instead of once per device (agb_multi.cu).
+int agb_ctx_copy_particles_from(agb_ctx* c, agb_ctx* src)
+{
+    if (!c || !src || !src->have_particles || src->bound) return AGB_ERR_INVALID;
+    CK(cudaSetDevice(c->device));
+    const int64_t n = src->d.n;
+    int rc = ensure_pool(c, n);
+    if (rc) return rc;
+    AgbDev& d = c->d;
+    const AgbDev& sd = src->d;
+    d.n = n;
+    CK(cudaEventRecord(c->ev_sync, c->st));
+    CK(cudaStreamWaitEvent(c->st_copy, c->ev_sync, 0));
+    auto peer = [&](void* dst, const void* from, size_t bytes, cudaStream_t st) -> cudaError_t {
+        return bytes ? cudaMemcpyPeerAsync(dst, c->device, from, src->device, bytes, st) : cudaSuccess;
+    };
+    const size_t b = (size_t)n * sizeof(double);
+    auto input = [&](const double*& slot, int which, const double* from, cudaStream_t st) -> cudaError_t {
+        if (!from) { slot = nullptr; return cudaSuccess; }
+        slot = c->in_d[which];
+        return peer(c->in_d[which], from, b, st);
+    };
+    // group 0: positions, masses, types (the build starts on them)
+    CK(cudaStreamWaitEvent(c->st, src->ev_pos, 0));
+    CK(input(d.x, 0, sd.x, c->st)); CK(input(d.y, 1, sd.y, c->st)); CK(input(d.z, 2, sd.z, c->st)); CK(input(d.mass, 6, sd.mass, c->st));
+    CK(peer(c->in_type, src->in_type, (size_t)n, c->st));
+    d.type = c->in_type; c->bound = false;
+    CK(cudaEventRecord(c->ev_pos, c->st));
+    // group 1: next_time and the carried acc / dUdt / h / rho
+    CK(cudaStreamWaitEvent(c->st_copy, src->ev_next, 0));
+    CK(input(d.next, 8, sd.next, c->st_copy));
+    CK(peer(d.ax, sd.ax, b, c->st_copy)); CK(peer(d.ay, sd.ay, b, c->st_copy)); CK(peer(d.az, sd.az, b, c->st_copy));
+    CK(peer(d.dUdt, sd.dUdt, b, c->st_copy)); CK(peer(d.h, sd.h, b, c->st_copy)); CK(peer(d.rho, sd.rho, b, c->st_copy));
+    CK(cudaMemsetAsync(d.vis, 0, (size_t)std::max<int64_t>(n, 1) * sizeof(double), c->st_copy));
+    CK(cudaEventRecord(c->ev_next, c->st_copy));
+    // group 2: what only the SPH pair pass needs
+    CK(cudaStreamWaitEvent(c->st_copy, src->ev_in, 0));
+    CK(input(d.vx, 3, sd.vx, c->st_copy)); CK(input(d.vy, 4, sd.vy, c->st_copy)); CK(input(d.vz, 5, sd.vz, c->st_copy));
+    CK(input(d.U, 7, sd.U, c->st_copy)); CK(input(d.mu, 9, sd.mu, c->st_copy));
+    CK(peer(d.P, sd.P, b, c->st_copy)); CK(peer(d.T, sd.T, b, c->st_copy));
+    CK(cudaEventRecord(c->ev_in, c->st_copy));
+    c->in_pending = true; c->next_pending = true;
+    c->have_particles = true; c->built = false; c->dens_done = false; c->forces_done = false; c->counters_valid = false;
+    c->int_ready = false;
+    for (bool& f : c->bres_sent) f = false;
+    return AGB_OK;
+}
+
 void agb_ctx_join_uploads(agb_ctx* c)
 {
     if (c->in_pending) { cudaStreamWaitEvent(c->st, c->ev_in, 0); c->in_pending = false; c->next_pending = false; }

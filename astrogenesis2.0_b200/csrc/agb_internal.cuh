@@ -147,6 +147,7 @@ int agb_launch_scan_i32(const int32_t* in, int32_t* out, int64_t n, int32_t* blk
 int agb_launch_microbench(int kind, int sm_count, cudaStream_t st, double* result);
 // agb_multi.cu reaches into a context it drives (agb_api.cu)
 void agb_ctx_internals(agb_ctx* c, AgbDev** d, cudaStream_t* st, int* device);
+int agb_ctx_copy_particles_from(agb_ctx* c, agb_ctx* src);   // the host hand-over `src` received, repeated on c by peer-to-peer copies
 void agb_ctx_join_uploads(agb_ctx* c);            // the compute stream waits for every upload of the last hand-over
 int agb_launch_unpermute_counters(AgbDev& d, int32_t* v, int32_t* an, int32_t* al, int32_t* sp, cudaStream_t st);
 

@@ -199,8 +199,15 @@ int agb_multi_set_particles(agb_multi* m, const agb_particles* p)
     int rc = ensure_buffers(m, p->n);
     if (rc) return rc;
     m->n = p->n; m->forces_done = false;
-    // every device uploads the whole set over its own PCIe link
-    return fan_out(m, [&](int i) { return agb_set_particles(m->ctx[(size_t)i], p, AGB_MEM_HOST); });
+    // The host arrays are read once: device 0 uploads them, the others repeat its hand-over with peer-to-peer copies over
+    // NVLink, group by group as the data arrives (caller memory is usually pageable: N uploads of it would share the host's
+    // staging bandwidth).  Without peer access, or on a one-GPU test box, every context uploads for itself.
+    bool p2p = !m->serial;
+    for (size_t i = 1; i < m->ctx.size() && p2p; i++) { int can = 0; cudaDeviceCanAccessPeer(&can, m->dev[i], m->dev[0]); p2p = can != 0; }
+    if (!p2p || m->ctx.size() == 1) return fan_out(m, [&](int i) { return agb_set_particles(m->ctx[(size_t)i], p, AGB_MEM_HOST); });
+    rc = agb_set_particles(m->ctx[0], p, AGB_MEM_HOST);
+    if (rc) { m->err = agb_last_error(m->ctx[0]); return rc; }
+    return fan_out(m, [&](int i) { return i == 0 ? (int)AGB_OK : agb_ctx_copy_particles_from(m->ctx[(size_t)i], m->ctx[0]); });
 }
 
 int agb_multi_set_particles_aos(agb_multi* m, void* const* parts, int64_t n, const agb_aos_layout* L)
