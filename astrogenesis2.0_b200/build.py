@@ -7,7 +7,7 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libagb200.so")
-SOURCES = ["agb_api.cu", "agb_build.cu", "agb_density.cu", "agb_walk.cu", "agb_integrate.cu", "agb_multi.cu"]
+SOURCES = ["agb_api.cu", "agb_build.cu", "agb_density.cu", "agb_walk.cu", "agb_integrate.cu", "agb_multi.cu", "agb_extended.cu"]
 # tree geometry, moments and densities are compared with the reference's separately rounded sums: no FMA contraction there
 NO_FMAD = ("agb_build.cu", "agb_density.cu", "agb_integrate.cu")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

@@ -15,6 +15,7 @@ AGB_OPT_TARGET_COUNTERS = 1
 AGB_OPT_PRECISION = 2
 AGB_OPT_COOLING = 3
 AGB_OPT_STAR_FORMATION = 4
+AGB_OPT_EXTENDED = 5
 
 EXPORTS = [
     "agb_create", "agb_destroy", "agb_set_particles", "agb_set_particles_aos", "agb_build_tree", "agb_visual_density",

@@ -37,6 +37,8 @@ struct agb_ctx {
     bool bound = false, have_particles = false, built = false, dens_done = false, forces_done = false;
     bool mixed = true;                  // AGB_OPT_PRECISION
     bool walked_mixed = false;          // the last walk used the FP32 pair law (mixed_in_range)
+    bool ext_quad = true;               // ... with the quadrupole term (AGB_OPT_EXTENDED = 2: monopole only, for validation)
+    bool extended = false;              // AGB_OPT_EXTENDED: quadrupoles + spline softening + per-particle-h SPH (agb_extended.cu)
     bool opt_cooling = false; unsigned long long opt_sf_seed = 0;   // AGB_OPT_COOLING, AGB_OPT_STAR_FORMATION
     double* sfr = nullptr;              // Particle::sfr (device-resident loop)
     bool target_counters = false, counters_valid = false, vis_timed = false, gas_timed = false, build_timed = false;
@@ -87,7 +89,7 @@ void free_nodes(agb_ctx* c)
     dfree(d.src_pm); dfree(d.src_gv); dfree(d.src_flag);
     dfree(d.child); dfree(d.nfirst); dfree(d.nlast); dfree(d.nparent); dfree(d.arrived); dfree(d.ndepth);
     dfree(d.nmark); dfree(d.ndup); dfree(d.mom_pm); dfree(d.mom_gv); dfree(d.grouplist); dfree(d.lvl_list);
-    dfree(d.klo[0]); dfree(d.nodebase);
+    dfree(d.klo[0]); dfree(d.nodebase); dfree(d.quad); dfree(d.ext_bar);
     d.ncap = 0;
 }
 
@@ -123,6 +125,7 @@ int ensure_nodes(agb_ctx* c, int64_t want)
     CK(dalloc(d.child, 8 * nc)); CK(dalloc(d.nfirst, nc)); CK(dalloc(d.nlast, nc)); CK(dalloc(d.nparent, nc)); CK(dalloc(d.arrived, nc)); CK(dalloc(d.ndepth, nc));
     CK(dalloc(d.nmark, nc)); CK(dalloc(d.ndup, nc)); CK(dalloc(d.mom_pm, nc)); CK(dalloc(d.mom_gv, nc)); CK(dalloc(d.grouplist, nc)); CK(dalloc(d.lvl_list, nc));
     CK(dalloc(d.klo[0], nc)); CK(dalloc(d.nodebase, nc));     // per particle in the build, per node (exact sums, fold list) in the density pass
+    if (c->extended) { CK(dalloc(d.quad, 6 * nc)); CK(dalloc(d.ext_bar, 1)); }
     d.ncap = (int64_t)nc;
     return AGB_OK;
 }
@@ -341,6 +344,11 @@ int agb_set_option(agb_ctx* c, int option, int64_t value)
     if (option == AGB_OPT_TARGET_COUNTERS) { c->target_counters = value != 0; return AGB_OK; }
     if (option == AGB_OPT_PRECISION) { if (value != 0 && value != 1) return AGB_ERR_INVALID; c->mixed = value == 1; return AGB_OK; }
     if (option == AGB_OPT_COOLING) { c->opt_cooling = value != 0; return AGB_OK; }
+    if (option == AGB_OPT_EXTENDED) {
+        c->extended = value != 0; c->ext_quad = value != 2;
+        if (c->extended && c->d.ncap > 0 && !c->d.quad) { CK(cudaSetDevice(c->device)); CK(dalloc(c->d.quad, 6 * (size_t)c->d.ncap)); CK(dalloc(c->d.ext_bar, 1)); }
+        return AGB_OK;
+    }
     if (option == AGB_OPT_STAR_FORMATION) { c->opt_sf_seed = (unsigned long long)value; return AGB_OK; }
     return AGB_ERR_INVALID;
 }
@@ -527,7 +535,8 @@ static int gas_density_impl(agb_ctx* c, double mass_in_h, bool late_pt)
     c->dens_done = true;
     if (c->d.n == 0) return AGB_OK;
     CK(cudaEventRecord(c->ev[4], c->st));
-    if (c->hs.any_gas) c->launches += agb_launch_gas_density(c->d, c->s, mass_in_h, c->st, late_pt);
+    if (c->hs.any_gas && c->extended) c->launches += agb_launch_extended_density(c->d, c->s, mass_in_h, c->st);
+    else if (c->hs.any_gas) c->launches += agb_launch_gas_density(c->d, c->s, mass_in_h, c->st, late_pt);
     CK(cudaEventRecord(c->ev[5], c->st));
     c->gas_timed = true;
     CK(cudaGetLastError());
@@ -561,7 +570,7 @@ static int forces_impl(agb_ctx* c, double global_time, double e0, double theta, 
     AgbDev& d = c->d;
     if (d.n == 0) { c->forces_done = true; return AGB_OK; }
     if (c->target_counters) { int rc = ensure_counters(c); if (rc) return rc; }
-    const bool mixed = mixed_in_range(c, e0);                  // with the scalars of the tree the walk will run on (call by call), or of the last step's (agb_force_path)
+    const bool mixed = !c->extended && mixed_in_range(c, e0);  // with the scalars of the tree the walk will run on (call by call), or of the last step's (agb_force_path)
     c->walked_mixed = mixed;
     if (c->hs.any_gas && mixed) { int rc = ensure_sph_records(c, 0); if (rc) return rc; }
     // The targets are the ACTIVE particles in tree order; slice boundaries fall on multiples of 256 of them (the far-field
@@ -571,7 +580,9 @@ static int forces_impl(agb_ctx* c, double global_time, double e0, double theta, 
     // gas targets need h/rho/P: if the caller skipped gas_density they are orphans (h = 0) and get no SPH, like the reference
     const bool any_gas = c->hs.any_gas != 0;
     for (int attempt = 0;; attempt++) {
-        if (late_gas) {
+        if (c->extended)
+            c->launches += agb_launch_extended_forces(d, c->s, global_time, e0, theta, part, nparts, any_gas, c->ext_quad, c->sm_count, c->st, c->evw);
+        else if (late_gas) {
             c->launches += agb_launch_walk(d, c->s, global_time, e0, theta, part, nparts, c->target_counters, any_gas, mixed, c->sm_count, c->st, c->evw, 1);
             if (attempt == 0) {
                 if (c->in_pending) { CK(cudaStreamWaitEvent(c->st, c->ev_in, 0)); c->in_pending = false; }
@@ -633,7 +644,7 @@ int agb_force_path(agb_ctx* c, double visual_density_radius, double mass_in_h, d
     // Host hand-over still uploading (set_particles is asynchronous): in mixed precision only the SPH pair pass needs the gas
     // velocities / U / mu, so the build, the densities and the gravity walk start on the first upload group and the rest of
     // the transfer hides behind them.
-    const bool late_gas = c->in_pending && !c->bound && mixed_in_range(c, e0) && c->gas_hint;
+    const bool late_gas = c->in_pending && !c->bound && !c->extended && mixed_in_range(c, e0) && c->gas_hint;
     CK(cudaEventRecord(c->ev[8], c->st));
     { Phase ph("build tree"); launch_build(c, late_gas); }
     CK(cudaEventRecord(c->ev[9], c->st));

@@ -61,6 +61,8 @@ struct AgbDev {
     bool deep = false;
     uint64_t* dk[3] = {nullptr, nullptr, nullptr};
     uint64_t* kex = nullptr;
+    double* quad = nullptr;            // extended mode: traceless quadrupole of every node about its COM, (xx xy xz yy yz zz)
+    unsigned int* ext_bar = nullptr;   // ... arrival counter of its level-synchronous pass
     double4* grec = nullptr;           // caller order, gas only: (vx, vy, vz, U), (mu, rho, P, T) packed before the gather
     uint32_t* blockhist = nullptr;     // radix sort: [256][nblocks]
     int32_t* scanblk = nullptr;
@@ -142,6 +144,11 @@ void agb_slice_bounds(int64_t n_active, int part, int nparts, int64_t* a0, int64
 int agb_launch_slice_results(const AgbDev& d, int64_t a0, int64_t a1, bool ident, uint32_t* index, double* const dst[9], cudaStream_t st);   // dst: ax ay az dUdt h rho P T vis
 int agb_launch_walk(AgbDev& d, AgbScalars* s, double globalTime, double e0, double theta, int part, int nparts,
                     bool counters, bool any_gas, bool mixed, int sm_count, cudaStream_t st, cudaEvent_t* ev, int phase = 0);   // ev[0..4]: before k_far, before k_walk, after k_walk, after k_sph, before k_sph
+// the step's force targets (globalTime == nextIntegrationTime) in tree order, compacted; resets the walk's counters
+int agb_launch_active_list(AgbDev& d, AgbScalars* s, double globalTime, int sm_count, cudaStream_t st);
+// extended-accuracy mode (agb_extended.cu): per-particle smoothing lengths and densities; quadrupole walk + neighbour-loop SPH forces
+int agb_launch_extended_density(AgbDev& d, AgbScalars* s, double massInH, cudaStream_t st);
+int agb_launch_extended_forces(AgbDev& d, AgbScalars* s, double globalTime, double e0, double theta, int part, int nparts, bool any_gas, bool use_quad, int sm_count, cudaStream_t st, cudaEvent_t* ev);
 int agb_launch_dump_tree(AgbDev& d, AgbScalars* s, int32_t* leafdepth, uint64_t* khi, uint64_t* klo, cudaStream_t st);
 int agb_launch_scan_i32(const int32_t* in, int32_t* out, int64_t n, int32_t* blk, int32_t* total_out, cudaStream_t st, const int32_t* skip_if_n = nullptr);
 int agb_launch_microbench(int kind, int sm_count, cudaStream_t st, double* result);

@@ -1133,16 +1133,9 @@ int agb_launch_walk(AgbDev& d, AgbScalars* s, double globalTime, double e0, doub
     static const float far_k2 = getenv("AGB200_WALK_FAR_K2") ? (float)atof(getenv("AGB200_WALK_FAR_K2")) : 0.25f;
     P.far_k2 = far_k2;
     int launches = 0;
-    const int nb = (int)((d.n + 255) / 256);
     const int64_t max_groups = (d.n / nparts + 32 * SG_GROUPS + 31) / 32;
-    if (phase != 2) { k_walk_reset<<<1, 1, 0, st>>>(s); launches++; }
+    if (phase != 2) launches += agb_launch_active_list(d, s, globalTime, sm_count, st);
     if (d.n > 0 && phase != 2) {
-        cudaMemsetAsync(&s->n_active, 0, sizeof(int32_t), st);
-        k_count_active<<<std::min(nb, 4 * sm_count), 256, 0, st>>>(d.s_next, d.n, globalTime, s); launches++;
-        // compact list of the active targets (scratch: flags -> nodecnt, ranks -> nodebase; both are idle after the densities)
-        k_active_flags<<<nb, 256, 0, st>>>(d.s_next, d.n, globalTime, s, d.nodecnt); launches++;
-        launches += agb_launch_scan_i32(d.nodecnt, d.nodebase, d.n, d.scanblk, &s->n_scan_tmp, st, &s->n_active);
-        k_active_compact<<<nb, 256, 0, st>>>(d.s_next, d.n, globalTime, s, d.nodebase, d.act_list); launches++;
         if (counters) {
             cudaMemsetAsync(d.c_visits, 0, (size_t)d.n * 4, st); cudaMemsetAsync(d.c_accn, 0, (size_t)d.n * 4, st);
             cudaMemsetAsync(d.c_accl, 0, (size_t)d.n * 4, st); cudaMemsetAsync(d.c_sph, 0, (size_t)d.n * 4, st);
@@ -1167,6 +1160,22 @@ int agb_launch_walk(AgbDev& d, AgbScalars* s, double globalTime, double e0, doub
             launches++;
         }
         if (ev) cudaEventRecord(ev[3], st);
+    }
+    return launches;
+}
+
+int agb_launch_active_list(AgbDev& d, AgbScalars* s, double globalTime, int sm_count, cudaStream_t st)
+{
+    int launches = 1;
+    const int nb = (int)((d.n + 255) / 256);
+    k_walk_reset<<<1, 1, 0, st>>>(s);
+    if (d.n > 0) {
+        cudaMemsetAsync(&s->n_active, 0, sizeof(int32_t), st);
+        k_count_active<<<std::min(nb, 4 * sm_count), 256, 0, st>>>(d.s_next, d.n, globalTime, s);
+        // compact list of the active targets (scratch: flags -> nodecnt, ranks -> nodebase; both are idle after the densities)
+        k_active_flags<<<nb, 256, 0, st>>>(d.s_next, d.n, globalTime, s, d.nodecnt);
+        launches += 3 + agb_launch_scan_i32(d.nodecnt, d.nodebase, d.n, d.scanblk, &s->n_scan_tmp, st, &s->n_active);
+        k_active_compact<<<nb, 256, 0, st>>>(d.s_next, d.n, globalTime, s, d.nodebase, d.act_list);
     }
     return launches;
 }

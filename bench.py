@@ -215,6 +215,11 @@ def run_gpu_arm(args, pkg):
     n = len(p["x"])
     any_gas = bool((p["type"] == 2).any())
     ctx = pkg.Context(local, 8)
+    if args.extended:
+        # SURVEY.md §8(f)-3, reported on its own lines: quadrupole walk with spline softening + per-particle-h neighbour SPH (FP64; not the
+        # reference's algorithm, so there is no reference arm and no parity claim for this line)
+        ctx.set_option(pkg.capi.AGB_OPT_EXTENDED, 1)
+        args.no_fp64 = True
     stream = torch.cuda.ExternalStream(ctx.stream(), device=dev)
     out_cols = RESULT_COLS_GRAVITY + (RESULT_COLS_GAS if any_gas else ())      # what a step hands back, for any number of GPUs
 
@@ -473,14 +478,20 @@ def run_gpu_arm(args, pkg):
     achieved = flop_per_interaction * inter_rank / (walk_ms_avg * 1e-3) / 1e12
     traffic = traffic_src = None
     kname = "k_walk<COUNT=0,SPH=%d,MIXED=1>" % (1 if any_gas else 0)
+    if args.extended:
+        # monopole with spline softening ~23 flop per pair, + ~37 for the quadrupole term of a node source
+        kname = "k_walk_ext (kernel_ms: k_far = quadrupole upward pass, k_walk = k_walk_ext, k_sph = k_ext_sph_force)"
+        flop_per_interaction = (23.0 * cnt["leaf_interactions"] + 60.0 * cnt["node_interactions"]) / max(1, cnt["interactions"])
+        fp32_peak = fp64_peak
+        achieved = flop_per_interaction * inter_rank / (walk_ms_avg * 1e-3) / 1e12
     try:
         tr = json.load(open(os.path.join(ROOT, "profiles", "walk_dram_traffic.json")))
-        ent = tr.get(name, {})
+        ent = tr.get(name + ("_extended" if args.extended else ""), {})
         traffic = ent.get("bytes_per_launch")
         traffic_src = ent.get("source")
     except Exception:  # noqa: BLE001
         pass
-    roofline = {"bound": "fp32", "kernel": kname, "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved / fp32_peak if fp32_peak else None,
+    roofline = {"bound": "fp64" if args.extended else "fp32", "kernel": kname, "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved / fp32_peak if fp32_peak else None,
                 "traffic": traffic, "traffic_source": traffic_src,
                 "peak_source": "measured on this GPU: FP32 FMA chain microbenchmark (agb_microbench kind 1); FP64 chain = %.1f TFLOP/s" % fp64_peak,
                 "algorithmic_flop_per_interaction": flop_per_interaction, "interactions_per_launch": inter_rank,
@@ -518,9 +529,10 @@ def run_gpu_arm(args, pkg):
 
     line = {
         "metric": METRIC, "value": value, "unit": "particles/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
-        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64 decisions and accumulation, f32 pair forces (mixed mode)", "data": "synthetic",
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f64" if args.extended else "f64 decisions and accumulation, f32 pair forces (mixed mode)", "data": "synthetic",
         "config": cfg,
-        "run": {"precision": "mixed", "l2": "256 MiB buffer written between timed steps (L2 flush); working set %.0f MB" % (n * 330 / 1e6),
+        "run": {"precision": "extended-accuracy mode (AGB_OPT_EXTENDED): quadrupoles, spline softening, width/d < theta per 32-target group, per-particle-h SPH; FP64; parity unpinned by the reference" if args.extended else "mixed", "l2": "256 MiB buffer written between timed steps (L2 flush); working set %.0f MB" % (n * 330 / 1e6),
                 "parallelism": "replicated tree, tree-ordered target slices, 1 coalesced NCCL all-gather group/step (in place)" if world > 1 else "single GPU",
                 "result_columns": list(out_cols)},
         "e2e": e2e, "fp64": fp64, "resident_sim_step": resident, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
@@ -541,6 +553,7 @@ def main():
     ap.add_argument("--workload", default=None, choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-fp64", action="store_true", help="skip the FP64-arithmetic leg")
+    ap.add_argument("--extended", action="store_true", help="extended-accuracy mode (quadrupoles, spline softening, neighbour-loop SPH): its own line, no reference arm")
     args = ap.parse_args()
     import __graft_entry__ as ge
     pkg = ge.load_package()

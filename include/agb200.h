@@ -169,6 +169,11 @@ typedef enum {
     AGB_OPT_STAR_FORMATION = 4,     /* device-resident loop: != 0 = stochastic gas -> star conversion (SFR.cpp:12-34; commented out in the
                                        reference, Simulation.cpp:316-320); the value seeds a counter-based generator keyed by
                                        (particle, time) in place of the reference's rand().  Default 0. */
+    AGB_OPT_EXTENDED = 5,           /* 1 = extended-accuracy mode (NOT the reference's algorithm, parity unpinned): gravity with
+                                       monopole + quadrupole moments, Newtonian with cubic-spline softening (length 2.8 e0), one interaction
+                                       list per 32 targets, opening test (cell WIDTH) / distance < theta; SPH with a smoothing length per particle from (4 pi/3)(2h)^3 rho = massInH and
+                                       neighbour loops for density, pressure, viscosity and dU/dt.  Same calls, FP64 throughout.  Default 0.
+                                       (2 = the same without the quadrupole term: a validation aid.) */
     AGB_OPT_PRECISION = 2           /* arithmetic of the pair forces: 0 = FP64 throughout (agrees with the reference to ~1e-14),
                                        1 = mixed (default): float-float displacements, FP32 law, FP64 accumulation; ~1e-7.
                                        The accepted (target, source) sets, SPH pair sets and densities are identical in both;

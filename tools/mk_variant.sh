@@ -7,6 +7,6 @@ name=$1; shift
 C=astrogenesis2.0_b200/csrc
 mkdir -p dev_libs
 nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC "$@" -c $C/agb_walk.cu -o dev_libs/agb_walk_$name.o
-nvcc -shared -o dev_libs/libagb200_$name.so $C/agb_api.o $C/agb_build.o $C/agb_density.o $C/agb_integrate.o $C/agb_multi.o dev_libs/agb_walk_$name.o -lcudart -lpthread -ldl
+nvcc -shared -o dev_libs/libagb200_$name.so $C/agb_api.o $C/agb_build.o $C/agb_density.o $C/agb_integrate.o $C/agb_multi.o $C/agb_extended.o dev_libs/agb_walk_$name.o -lcudart -lpthread -ldl
 rm -f dev_libs/agb_walk_$name.o
 ls -la dev_libs/libagb200_$name.so
