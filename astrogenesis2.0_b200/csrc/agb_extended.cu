@@ -87,7 +87,7 @@ __global__ void __launch_bounds__(TPB) k_quad_levels(AgbDev d, const AgbScalars*
 }
 
 // ------------------------------------------------------------------ gravity: one interaction list per group of 32 targets
-constexpr int XWARPS = 8, XL = 1024, XS = 1024;
+constexpr int XWARPS = 4, XL = 1024, XS = 2048;      // 14.5 KB of shared memory per warp, 3 CTAs per SM
 struct ExtWarp {
     int list[XL];
     int stack[XS];
@@ -114,16 +114,25 @@ __device__ __forceinline__ Slice target_slice(const AgbScalars* s, int64_t N, in
     return sl;
 }
 
-// spline-softened Newtonian attraction per unit mass and unit G: returns f with a = -f d  (Springel et al. 2001, eq. A1; Gadget-2)
-__device__ __forceinline__ double soft_fac(double r2, double hs, double hs_inv3)
+// 1/sqrt(x) for positive normal x: MUFU.RSQ64H seed (~2^-22) + one cubically convergent step (~2^-60), as in agb_walk.cu
+__device__ __forceinline__ double rsqrt_pos(double x)
 {
-    if (r2 >= hs * hs) { const double ri = rsqrt(r2); return ri * ri * ri; }
-    const double u = sqrt(r2) / hs;
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    const double e = fma(-x * y, y, 1.0);
+    return fma(y, e * fma(0.375, e, 0.5), y);
+}
+
+// spline-softened Newtonian attraction per unit mass and unit G: returns f with a = -f d  (Springel et al. 2001, eq. A1; Gadget-2)
+__device__ __forceinline__ double soft_fac(double r2, double ri, double hs, double hs_inv3)
+{
+    if (r2 >= hs * hs) return ri * ri * ri;
+    const double u = r2 * ri / hs;
     if (u < 0.5) return hs_inv3 * (10.666666666666666 + u * u * (32.0 * u - 38.4));
     return hs_inv3 * (21.333333333333332 - 48.0 * u + 38.4 * u * u - 10.666666666666666 * u * u * u - 0.06666666666666667 / (u * u * u));
 }
 
-__global__ void __launch_bounds__(XWARPS * 32, 2) k_walk_ext(AgbDev d, AgbScalars* s, const double* __restrict__ quad, double theta, double eps, int part, int nparts, int use_quad)
+__global__ void __launch_bounds__(XWARPS * 32, 3) k_walk_ext(AgbDev d, AgbScalars* s, const double* __restrict__ quad, double theta, double eps, int part, int nparts, int use_quad)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -158,9 +167,10 @@ __global__ void __launch_bounds__(XWARPS * 32, 2) k_walk_ext(AgbDev d, AgbScalar
         while (sp > 0 || lc > 0) {
             // ---- traversal: one node per lane against the group's box
             while (sp > 0 && lc <= XL - 32 * 9) {
-                // a round pops up to 32 nodes and pushes up to 8 children each; near the end of the stack the rounds narrow down
-                // to a plain depth-first descent, which never needs more than 7 entries per level
-                const int cnt = min(sp, min(32, max(1, (XS - sp) / 7)));
+                // A round pops up to 32 nodes and pushes up to 8 children each.  The rounds narrow as the stack fills so that a round
+                // never leaves more than XS - 441 entries: from there even a plain depth-first descent (at most 7 entries per level,
+                // 63 levels) fits.
+                const int cnt = min(sp, max(1, min(32, (XS - 441 - sp) / 7)));
                 sp -= cnt;
                 const int node = lane < cnt ? sm.stack[sp + lane] : -1;
                 __syncwarp();
@@ -206,33 +216,47 @@ __global__ void __launch_bounds__(XWARPS * 32, 2) k_walk_ext(AgbDev d, AgbScalar
             while (lc - done >= 32 || (sp == 0 && lc - done > 0)) {
                 const int cnt = min(32, lc - done);
                 int e = -1;
+                if (lane < cnt) e = sm.list[done + lane];
+                // nodes to the front of the tile, particles behind them: two branch-free loops
+                const unsigned nodem = __ballot_sync(0xffffffffu, e >= N), leafm = __ballot_sync(0xffffffffu, e >= 0 && e < N);
+                const int nnodes = use_quad ? __popc(nodem) : 0;
                 if (lane < cnt) {
-                    e = sm.list[done + lane];
-                    sm.spm[lane] = d.src_pm[e];
-                    double q[6] = {0, 0, 0, 0, 0, 0};
-                    if (e >= N && use_quad) ldcg6(quad + 6 * (size_t)(e - N), q);
+                    const bool nd = e >= N && use_quad;
+                    const int pos = nd ? __popc(nodem & lt) : nnodes + __popc((use_quad ? leafm : (nodem | leafm)) & lt);
+                    sm.spm[pos] = d.src_pm[e];
+                    if (nd) {
+                        double q[6];
+                        ldcg6(quad + 6 * (size_t)(e - N), q);
 #pragma unroll
-                    for (int k = 0; k < 6; k++) sm.sq[lane][k] = q[k];
+                        for (int k = 0; k < 6; k++) sm.sq[pos][k] = q[k];
+                    }
                 }
-                const unsigned nodem = __ballot_sync(0xffffffffu, e >= N);
                 __syncwarp();
                 if (active) {
-                    for (int j = 0; j < cnt; j++) {
+#pragma unroll 2
+                    for (int j = 0; j < nnodes; j++) {
                         const double4 q = sm.spm[j];
                         const double dx = tp.x - q.x, dy = tp.y - q.y, dz = tp.z - q.z;
                         const double r2 = dx * dx + dy * dy + dz * dz;
-                        if (r2 == 0.0 || q.w == 0.0) continue;                       // the target itself / coincident / massless
-                        const double f = q.w * soft_fac(r2, hs, hs_inv3);
-                        ax -= f * dx; ay -= f * dy; az -= f * dz;
-                        if ((nodem >> j) & 1u) {
-                            const double* Q = sm.sq[j];
-                            const double qx = Q[0] * dx + Q[1] * dy + Q[2] * dz, qy = Q[1] * dx + Q[3] * dy + Q[4] * dz, qz = Q[2] * dx + Q[4] * dy + Q[5] * dz;
-                            const double ri2 = 1.0 / r2, ri = sqrt(ri2), ri5 = ri2 * ri2 * ri, dqd = dx * qx + dy * qy + dz * qz, c7 = 2.5 * dqd * ri5 * ri2;
-                            ax += qx * ri5 - c7 * dx; ay += qy * ri5 - c7 * dy; az += qz * ri5 - c7 * dz;
-                        }
+                        const double ri = r2 > 0.0 ? rsqrt_pos(r2) : 0.0;
+                        const double f = q.w * soft_fac(r2, ri, hs, hs_inv3);
+                        const double* Q = sm.sq[j];
+                        const double qx = Q[0] * dx + Q[1] * dy + Q[2] * dz, qy = Q[1] * dx + Q[3] * dy + Q[4] * dz, qz = Q[2] * dx + Q[4] * dy + Q[5] * dz;
+                        const double ri2 = ri * ri, ri5 = ri2 * ri2 * ri, dqd = dx * qx + dy * qy + dz * qz, c7 = 2.5 * dqd * ri5 * ri2;
+                        ax += qx * ri5 - (c7 + f) * dx; ay += qy * ri5 - (c7 + f) * dy; az += qz * ri5 - (c7 + f) * dz;
                     }
-                    const int nnodes = __popc(nodem);
-                    tot_node += nnodes; tot_leaf += cnt - nnodes;
+#pragma unroll 4
+                    for (int j = nnodes; j < cnt; j++) {
+                        const double4 q = sm.spm[j];
+                        const double dx = tp.x - q.x, dy = tp.y - q.y, dz = tp.z - q.z;
+                        const double r2 = dx * dx + dy * dy + dz * dz;
+                        // the target itself / a coincident source: d = 0 makes the term vanish as long as the factor stays finite
+                        const double ri = r2 > 0.0 ? rsqrt_pos(r2) : 0.0;
+                        const double f = q.w * soft_fac(r2, ri, hs, hs_inv3);
+                        ax -= f * dx; ay -= f * dy; az -= f * dz;
+                    }
+                    const int nn_ = __popc(nodem);
+                    tot_node += nn_; tot_leaf += cnt - nn_;
                 }
                 done += cnt;
                 __syncwarp();
@@ -273,31 +297,45 @@ __device__ __forceinline__ double spline_dw(double r, double h)
 }
 
 // squared distance from a point to the cell of node k (the depth-`dep` cell that holds the node's first particle)
-__device__ __forceinline__ double cell_dist2(const AgbDev& d, double R, int k, double px, double py, double pz)
+__device__ __forceinline__ double cell_dist2(const AgbDev& d, double R, double invR, int k, double px, double py, double pz)
 {
     const int dep = d.ndepth[k];
-    const double w = scalbn(R, 1 - dep);                                   // cell width 2 R / 2^dep
+    const double w = scalbn(R, 1 - dep), iw = scalbn(invR, dep - 1);      // cell width 2 R / 2^dep and its inverse
     const double4 f = d.src_pm[d.nfirst[k]];
-    const double cx = floor((f.x + R) / w) * w - R, cy = floor((f.y + R) / w) * w - R, cz = floor((f.z + R) / w) * w - R;
-    const double m = 1e-9 * w;                                             // rounding of the cell planes
+    const double cx = floor((f.x + R) * iw) * w - R, cy = floor((f.y + R) * iw) * w - R, cz = floor((f.z + R) * iw) * w - R;
+    const double m = 1e-9 * w;                                             // rounding of the cell planes (and of 1 / R)
     const double dx = fmax(0.0, fmax(cx - m - px, px - (cx + w + m))), dy = fmax(0.0, fmax(cy - m - py, py - (cy + w + m))), dz = fmax(0.0, fmax(cz - m - pz, pz - (cz + w + m)));
     return dx * dx + dy * dy + dz * dz;
 }
 
 // sum_j m_j W(r_ij, h) over the gas particles within 2 h of (px, py, pz): depth-first over the cells that touch the sphere
-__device__ double density_at(const AgbDev& d, const AgbScalars* s, double R, double px, double py, double pz, double h)
+// the smallest cell on the root path of tree position i that holds the whole ball of radius rad about (px, py, pz): searches start there
+__device__ __forceinline__ int enclosing_node(const AgbDev& d, double R, double invR, int64_t i, double px, double py, double pz, double rad)
+{
+    int k = d.leafparent[i];
+    while (k > 0) {
+        const int dep = d.ndepth[k];
+        const double w = scalbn(R, 1 - dep), iw = scalbn(invR, dep - 1);
+        const double cx = floor((px + R) * iw) * w - R, cy = floor((py + R) * iw) * w - R, cz = floor((pz + R) * iw) * w - R, m = 1e-9 * w;
+        if (px - rad > cx + m && px + rad < cx + w - m && py - rad > cy + m && py + rad < cy + w - m && pz - rad > cz + m && pz + rad < cz + w - m) break;
+        k = d.nparent[k];
+    }
+    return max(k, 0);
+}
+
+__device__ double density_at(const AgbDev& d, const AgbScalars* s, double R, double invR, int64_t self, double px, double py, double pz, double h)
 {
     const int N = (int)d.n;
     const double r2max = 4.0 * h * h;
     double rho = 0.0;
     int stack[96];
     int sp = 0;
-    if (s->n_nodes > 0) stack[sp++] = 0;
+    if (s->n_nodes > 0) stack[sp++] = enclosing_node(d, R, invR, self, px, py, pz, 2.0 * h);
     else if (s->n_in_tree == 1 && d.s_type[0] == 2) { const double4 q = d.src_pm[0]; const double r2 = (q.x - px) * (q.x - px) + (q.y - py) * (q.y - py) + (q.z - pz) * (q.z - pz); if (r2 < r2max) rho += q.w * spline_w(sqrt(r2), h); }
     while (sp > 0) {
         const int k = stack[--sp];
         if (!(d.src_gv[N + k].w > 0.0)) continue;                         // no gas below
-        if (cell_dist2(d, R, k, px, py, pz) >= r2max) continue;
+        if (cell_dist2(d, R, invR, k, px, py, pz) >= r2max) continue;
         const Links L = load_links(d.child, k);
         const int ch[8] = {L.a.x, L.a.y, L.a.z, L.a.w, L.b.x, L.b.y, L.b.z, L.b.w};
 #pragma unroll
@@ -322,16 +360,18 @@ __global__ void __launch_bounds__(128) k_ext_density(AgbDev d, const AgbScalars*
     if (i >= d.n || s->node_overflow || d.s_type[i] != 2) return;
     const uint32_t p = d.perm[d.cur][i];
     if (i >= s->n_in_tree) { d.s_h[i] = 0.0; d.h[p] = 0.0; return; }       // outside the root cube: no neighbours, no SPH (like the reference's outliers)
-    const double R = __longlong_as_double((long long)s->Rbits);
+    const double R = __longlong_as_double((long long)s->Rbits), invR = 1.0 / R;
     const double4 x = d.src_pm[i];
-    auto F = [&](double h, double& rho) { rho = density_at(d, s, R, x.x, x.y, x.z, h); return (4.0 * kPI / 3.0) * 8.0 * h * h * h * rho - massInH; };
+    auto F = [&](double h, double& rho) { rho = density_at(d, s, R, invR, i, x.x, x.y, x.z, h); return (4.0 * kPI / 3.0) * 8.0 * h * h * h * rho - massInH; };
     double rho = 0.0;
-    double lo = scalbn(R, -(int)d.leafdepth[i]), hi = lo;                   // start at the particle's leaf cell
-    if (d.h[p] > 0.0 && d.h[p] < 4.0 * R) lo = hi = d.h[p];                 // ... or at the smoothing length handed over with the particle
+    // start at the particle's leaf cell (cheap evaluations first: the cost of one grows with h^3), or at the smoothing length
+    // handed over with the particle
+    double lo = scalbn(R, -(int)d.leafdepth[i]), hi = lo;
+    if (d.h[p] > 0.0 && d.h[p] < 4.0 * R) lo = hi = d.h[p];
     double flo = F(lo, rho), fhi = flo;
     int guard = 0;
-    if (flo > 0.0) { while (flo > 0.0 && guard++ < 200) { hi = lo; fhi = flo; lo *= 0.5; flo = F(lo, rho); } }
-    else { while (fhi <= 0.0 && guard++ < 200) { lo = hi; flo = fhi; hi *= 2.0; fhi = F(hi, rho); if (hi > 4.0 * R) break; } }
+    if (flo > 0.0) { while (flo > 0.0 && guard++ < 400) { hi = lo; fhi = flo; lo *= 0.5; flo = F(lo, rho); } }
+    else { while (fhi <= 0.0 && guard++ < 400) { lo = hi; flo = fhi; hi *= 2.0; fhi = F(hi, rho); if (hi > 4.0 * R) break; } }
     // Illinois variant of regula falsi inside the bracket (F is smooth and increasing), to 1e-9 relative
     int side = 0;
     for (int it = 0; it < 60 && hi - lo > 1e-9 * hi && fhi > 0.0 && flo <= 0.0; it++) {
@@ -342,7 +382,7 @@ __global__ void __launch_bounds__(128) k_ext_density(AgbDev d, const AgbScalars*
         else { lo = mid; flo = fm; if (side == -1) fhi *= 0.5; side = -1; }
     }
     const double h = fhi > 0.0 && flo <= 0.0 ? (lo * fhi - hi * flo) / (fhi - flo) : hi;
-    rho = density_at(d, s, R, x.x, x.y, x.z, h);
+    rho = density_at(d, s, R, invR, i, x.x, x.y, x.z, h);
     const double U = d.s_U[i], mu = d.s_mu[i];
     const double P = (kGAMMA - 1.0) * U * rho, T = (kGAMMA - 1.0) * U * kPRTN * mu / kKB;
     d.s_h[i] = h; d.s_rho[i] = rho; d.s_P[i] = P; d.s_T[i] = T;
@@ -362,17 +402,17 @@ __global__ void __launch_bounds__(128) k_ext_sph_force(AgbDev d, const AgbScalar
     const double hi_ = d.s_h[i], rhoi = d.s_rho[i];
     if (!(hi_ > 0.0) || !(rhoi > 0.0)) return;
     const int N = (int)d.n;
-    const double R = __longlong_as_double((long long)s->Rbits);
+    const double R = __longlong_as_double((long long)s->Rbits), invR = 1.0 / R;
     const double4 xi = d.src_pm[i], vi = d.src_gv[i];
     const double Pi = d.s_P[i], ci = sqrt(kGAMMA * Pi / rhoi), pri = Pi / (rhoi * rhoi), r2max = 4.0 * hi_ * hi_;
     double ax = 0, ay = 0, az = 0, dU = 0;
     int stack[96];
     int sp = 0;
-    if (s->n_nodes > 0) stack[sp++] = 0;
+    if (s->n_nodes > 0) stack[sp++] = enclosing_node(d, R, invR, i, xi.x, xi.y, xi.z, 2.0 * hi_);
     while (sp > 0) {
         const int k = stack[--sp];
         if (!(d.src_gv[N + k].w > 0.0)) continue;
-        if (cell_dist2(d, R, k, xi.x, xi.y, xi.z) >= r2max) continue;
+        if (cell_dist2(d, R, invR, k, xi.x, xi.y, xi.z) >= r2max) continue;
         const Links L = load_links(d.child, k);
         const int ch[8] = {L.a.x, L.a.y, L.a.z, L.a.w, L.b.x, L.b.y, L.b.z, L.b.w};
 #pragma unroll
@@ -429,7 +469,7 @@ int agb_launch_extended_forces(AgbDev& d, AgbScalars* s, double globalTime, doub
     const int smem = (int)sizeof(ExtWarp) * XWARPS;
     cudaFuncSetAttribute(k_walk_ext, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     const int64_t max_groups = (d.n / nparts + 256 + 31) / 32;
-    k_walk_ext<<<(int)std::min<int64_t>((int64_t)sm_count * 2, (max_groups + XWARPS - 1) / XWARPS), XWARPS * 32, smem, st>>>(d, s, d.quad, theta, e0, part, nparts, use_quad ? 1 : 0); launches++;
+    k_walk_ext<<<(int)std::min<int64_t>((int64_t)sm_count * 3, (max_groups + XWARPS - 1) / XWARPS), XWARPS * 32, smem, st>>>(d, s, d.quad, theta, e0, part, nparts, use_quad ? 1 : 0); launches++;
     if (ev) { cudaEventRecord(ev[2], st); cudaEventRecord(ev[4], st); }
     if (any_gas) { k_ext_sph_force<<<nblk(d.n / nparts + 512, 128), 128, 0, st>>>(d, s, part, nparts); launches++; }
     if (ev) cudaEventRecord(ev[3], st);
