@@ -193,8 +193,18 @@ __global__ void __launch_bounds__(TPB) k_keygen(const double4* __restrict__ rec,
         if (outl) hi = AGB_OUTLIER_BIT;           // the stable sort keeps caller order among the outliers
         else if (!key_hi_fast(px, py, pz, 1.0 / R, &hi)) { Cell c{0.0, 0.0, 0.0, R}; hi = descend21(px, py, pz, c, false, edge); }
         khi[i] = hi; perm[i] = (uint32_t)i | (type[i] == 2 ? AGB_GAS_BIT : 0u);   // the sort payload also carries "is gas"
+        // the upper digits (first ~8 levels) take few values inside a block: one add per distinct value of a warp instead of 32
+        // serialised ones on the same counter; the lower digits are spread out
+        const unsigned am = __activemask();
+        const int lane = threadIdx.x & 31;
 #pragma unroll
-        for (int p = 0; p < 8; p++) atomicAdd(&h[p][digit_of(hi, 8 * p)], 1u);
+        for (int p = 0; p < 8; p++) {
+            const uint32_t dg = digit_of(hi, 8 * p);
+            if (p >= 5) {
+                const unsigned peers = __match_any_sync(am, dg);
+                if (lane == __ffs(peers) - 1) atomicAdd(&h[p][dg], (uint32_t)__popc(peers));
+            } else atomicAdd(&h[p][dg], 1u);
+        }
     }
     unsigned mo = __ballot_sync(0xffffffffu, outl), me = __ballot_sync(0xffffffffu, edge);
     if ((threadIdx.x & 31) == 0) {
@@ -790,22 +800,34 @@ __device__ __forceinline__ void node_moments(const AgbDev& d, int k, int N, bool
         d.nlast[k] = last;
         return;
     }
+    // Four children at a time: their records are requested together (independent loads in flight: the pass is latency bound),
+    // then summed in fixed octant order => run-to-run identical sums.  (Gating the gas record of a particle by src_flag saves
+    // 0.7 GB of DRAM reads on C3 but adds a dependent load: 0.1 ms slower.)
 #pragma unroll
-    for (int o = 0; o < 8; o++) {                      // fixed octant order => run-to-run identical sums
-        const int c = ch[o];
-        if (c < 0) continue;
-        if (c < N) {
-            const double4 pm = d.src_pm[c], gv = d.src_gv[c];       // (gating the second read by src_flag saves 0.7 GB of DRAM reads but costs 0.1 ms: latency bound)
-            m += pm.w; sx += pm.x * pm.w; sy += pm.y * pm.w; sz += pm.z * pm.w;
-            g += gv.w;
-            if (MODE == 0) { gx += gv.x * gv.w; gy += gv.y * gv.w; gz += gv.z * gv.w; }
-            last = max(last, c);
-        } else {
-            double4 pm = ldcg4(&d.mom_pm[c - N]), gv = ldcg4(&d.mom_gv[c - N]);
-            m += pm.w; sx += pm.x; sy += pm.y; sz += pm.z;
-            g += gv.w;
-            if (MODE == 0) { gx += gv.x; gy += gv.y; gz += gv.z; }
-            last = max(last, __ldcg(&d.nlast[c - N]));
+    for (int half = 0; half < 2; half++) {
+        double4 pm[4], gv[4];
+        int lst[4];
+#pragma unroll
+        for (int o = 0; o < 4; o++) {
+            const int c = ch[4 * half + o];
+            pm[o] = make_double4(0, 0, 0, 0); gv[o] = pm[o]; lst[o] = -1;
+            if (c >= N) { pm[o] = ldcg4(&d.mom_pm[c - N]); gv[o] = ldcg4(&d.mom_gv[c - N]); lst[o] = __ldcg(&d.nlast[c - N]); }
+            else if (c >= 0) { pm[o] = d.src_pm[c]; gv[o] = d.src_gv[c]; lst[o] = c; }
+        }
+#pragma unroll
+        for (int o = 0; o < 4; o++) {
+            const int c = ch[4 * half + o];
+            if (c < 0) continue;
+            if (c < N) {
+                m += pm[o].w; sx += pm[o].x * pm[o].w; sy += pm[o].y * pm[o].w; sz += pm[o].z * pm[o].w;
+                g += gv[o].w;
+                if (MODE == 0) { gx += gv[o].x * gv[o].w; gy += gv[o].y * gv[o].w; gz += gv[o].z * gv[o].w; }
+            } else {
+                m += pm[o].w; sx += pm[o].x; sy += pm[o].y; sz += pm[o].z;
+                g += gv[o].w;
+                if (MODE == 0) { gx += gv[o].x; gy += gv[o].y; gz += gv[o].z; }
+            }
+            last = max(last, lst[o]);
         }
     }
     d.mom_pm[k] = make_double4(sx, sy, sz, m);

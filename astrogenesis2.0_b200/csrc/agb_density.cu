@@ -81,14 +81,23 @@ __global__ void __launch_bounds__(TPB) k_gas_flags(AgbDev d, int32_t* __restrict
 }
 
 __global__ void __launch_bounds__(TPB) k_gas_compact(AgbDev d, const uint32_t* __restrict__ perm, uint32_t* __restrict__ g_orig, double4* __restrict__ g_pm,
-                                                       int32_t* __restrict__ g_tree)
+                                                       int32_t* __restrict__ g_tree, AgbScalars* s)
 {
     int64_t i = (int64_t)blockIdx.x * TPB + threadIdx.x;
-    if (i >= d.n || d.s_type[i] != 2) return;
-    const int r = d.gasrank[i];
-    g_orig[r] = perm[i];
-    g_pm[r] = d.src_pm[i];
-    g_tree[r] = (int32_t)i;
+    const bool gas = i < d.n && d.s_type[i] == 2;
+    unsigned long long mb = 0ull;
+    if (gas) {
+        const int r = d.gasrank[i];
+        const double4 pm = d.src_pm[i];
+        g_orig[r] = perm[i];
+        g_pm[r] = pm;
+        g_tree[r] = (int32_t)i;
+        mb = (unsigned long long)__double_as_longlong(pm.w);       // masses are >= 0: bit order == value order
+    }
+    // smallest / largest gas mass of the step (one atomic pair per warp)
+    unsigned long long lo = gas ? mb : ~0ull, hi = mb;
+    for (int o = 16; o > 0; o >>= 1) { lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o)); hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o)); }
+    if ((threadIdx.x & 31) == 0 && lo != ~0ull) { atomicMin(&s->gas_mmin, lo); atomicMax(&s->gas_mmax, hi); }
 }
 
 struct GasFold {
@@ -170,6 +179,27 @@ __global__ void __launch_bounds__(TPB) k_gas_fold(AgbDev d, AgbScalars* s, GasFo
     double* sm_m = reinterpret_cast<double*>(fold_smem);
     uint32_t* sm_i = reinterpret_cast<uint32_t*>(sm_m + FOLD_MAX);
     if (s->node_overflow) return;
+    if (s->gas_mmin == s->gas_mmax) {
+        // Every gas particle has the same mass m (the usual SPH initial conditions): the reference's left fold over a node's c gas
+        // particles is m added c times, whatever their order.  One table of those sums per block, no sorting.
+        if (threadIdx.x == 0) {
+            const double m = __longlong_as_double((long long)s->gas_mmin);
+            double sum = 0.0;
+            sm_m[0] = 0.0;
+            for (int j = 1; j <= FOLD_MAX; j++) { sum = __dadd_rn(sum, m); sm_m[j] = sum; }
+        }
+        __syncthreads();
+        for (int q = blockIdx.x * TPB + threadIdx.x; q < s->n_fold; q += gridDim.x * TPB) {
+            const int k = F.foldlist[q];
+            int g0, g1;
+            node_gas_range(d, F, s, k, &g0, &g1);
+            const int cnt = g1 - g0;
+            if (cnt > FOLD_MAX) { F.nflag[k] = 3; continue; }
+            F.nexact[k] = sm_m[cnt];
+            F.nflag[k] = 2;
+        }
+        return;
+    }
     for (int q = blockIdx.x; q < s->n_fold; q += gridDim.x) {
         const int k = F.foldlist[q];
         int g0, g1;
@@ -297,7 +327,11 @@ __global__ void __launch_bounds__(TPB) k_gas_scatter(AgbDev d, const AgbScalars*
     else { d.h[p] = d.s_h[i]; d.rho[p] = d.s_rho[i]; d.P[p] = d.s_P[i]; d.T[p] = d.s_T[i]; }
 }
 
-__global__ void k_gas_reset(AgbScalars* s) { s->n_gas_groups = 0; s->n_gas_orphans = 0; s->tie_exact = 0; s->tie_unresolved = 0; s->n_fold = 0; }
+__global__ void k_gas_reset(AgbScalars* s)
+{
+    s->n_gas_groups = 0; s->n_gas_orphans = 0; s->tie_exact = 0; s->tie_unresolved = 0; s->n_fold = 0;
+    s->gas_mmin = ~0ull; s->gas_mmax = 0ull;
+}
 
 } // namespace
 
@@ -321,7 +355,7 @@ int agb_launch_gas_density(AgbDev& d, AgbScalars* s, double massInH, cudaStream_
     k_gas_flags<<<nb, TPB, 0, st>>>(d, d.nodecnt);
     int launches = agb_launch_scan_i32(d.nodecnt, d.gasrank, d.n, d.scanblk, &s->n_gas_total, st);
     cudaMemcpyAsync(d.gasrank + d.n, &s->n_gas_total, sizeof(int32_t), cudaMemcpyDeviceToDevice, st);
-    k_gas_compact<<<nb, TPB, 0, st>>>(d, d.perm[d.cur], g_orig, g_pm, g_tree);
+    k_gas_compact<<<nb, TPB, 0, st>>>(d, d.perm[d.cur], g_orig, g_pm, g_tree, s);
     // nflag/pending/foldlist/nexact borrow scratch that is idle here: arrived (int32/node), lcp (int8/particle),
     // nodebase (int32/particle), and the caller-order copy of key_lo (8 B/particle)
     GasFold F{d.gasrank, g_orig, g_pm, g_tree, reinterpret_cast<uint8_t*>(d.arrived), reinterpret_cast<double*>(d.klo[0]), d.nodebase,
@@ -329,7 +363,7 @@ int agb_launch_gas_density(AgbDev& d, AgbScalars* s, double massInH, cudaStream_
     cudaMemsetAsync(d.arrived, 0, (size_t)d.ncap * sizeof(int32_t), st);
     cudaMemsetAsync(d.lcp, 0, (size_t)d.n, st);
     k_gas_mark<0><<<nb, TPB, 0, st>>>(d, s, massInH, F);
-    const int fold_smem = FOLD_MAX * 12;
+    const int fold_smem = (FOLD_MAX + 1) * 12;
     cudaFuncSetAttribute(k_gas_fold, cudaFuncAttributeMaxDynamicSharedMemorySize, fold_smem);
     k_gas_fold<<<296, TPB, fold_smem, st>>>(d, s, F);
     k_gas_mark<1><<<nb, TPB, 0, st>>>(d, s, massInH, F);

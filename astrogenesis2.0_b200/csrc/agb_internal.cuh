@@ -96,6 +96,7 @@ struct AgbScalars {
     int32_t lvl_cnt[64], lvl_cur[64];  // internal nodes per depth, fill cursors of the level lists
     int32_t node_overflow;             // the build needed more than ncap nodes: nothing past the capacity was written, the host grows and rebuilds
     int32_t n_gas_total, tie_exact, tie_unresolved, n_fold, n_long_runs, n_scan_tmp;
+    unsigned long long gas_mmin, gas_mmax;   // bit patterns of the smallest / largest gas particle mass (equal: the exact tie sums need no sort)
     unsigned long long st_rounds, st_popped, st_mixed, st_open, st_drain;   // walk statistics (tuning)
     unsigned long long st_cls[10];     // counter mode: list entries / acceptor bits by lane span (any, one half, one quarter), far-list entries, entries per evaluation class
 };
