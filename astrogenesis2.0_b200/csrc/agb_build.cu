@@ -181,22 +181,23 @@ __global__ void __launch_bounds__(TPB) k_keygen(const double4* __restrict__ rec,
     __shared__ uint32_t h[8][256];
     for (int k = threadIdx.x; k < 8 * 256; k += TPB) (&h[0][0])[k] = 0;
     __syncthreads();
-    int64_t i = (int64_t)blockIdx.x * TPB + threadIdx.x;
-    bool outl = false, edge = false;
-    if (i < n) {
-        const double R = __longlong_as_double((long long)s->Rbits);
+    // grid-stride: a block keeps its 8 x 256 counters for many keys (clearing and flushing them per 256 keys cost more than the keys)
+    int n_outl = 0, n_edge = 0;
+    const double R = __longlong_as_double((long long)s->Rbits), invR = 1.0 / R;
+    const int lane = threadIdx.x & 31;
+    for (int64_t i = (int64_t)blockIdx.x * TPB + threadIdx.x; i < n; i += (int64_t)gridDim.x * TPB) {
+        bool outl = false, edge = false;
         const double4 r4 = rec[i];
         const double px = r4.x, py = r4.y, pz = r4.z;
         uint64_t hi;
         // root cube is centred on the origin (Tree.cpp:31); inclusive bounds (Node.cpp:706-711)
         outl = px < -R || px > R || py < -R || py > R || pz < -R || pz > R;
         if (outl) hi = AGB_OUTLIER_BIT;           // the stable sort keeps caller order among the outliers
-        else if (!key_hi_fast(px, py, pz, 1.0 / R, &hi)) { Cell c{0.0, 0.0, 0.0, R}; hi = descend21(px, py, pz, c, false, edge); }
+        else if (!key_hi_fast(px, py, pz, invR, &hi)) { Cell c{0.0, 0.0, 0.0, R}; hi = descend21(px, py, pz, c, false, edge); }
         khi[i] = hi; perm[i] = (uint32_t)i | (type[i] == 2 ? AGB_GAS_BIT : 0u);   // the sort payload also carries "is gas"
         // the upper digits (first ~8 levels) take few values inside a block: one add per distinct value of a warp instead of 32
         // serialised ones on the same counter; the lower digits are spread out
         const unsigned am = __activemask();
-        const int lane = threadIdx.x & 31;
 #pragma unroll
         for (int p = 0; p < 8; p++) {
             const uint32_t dg = digit_of(hi, 8 * p);
@@ -205,11 +206,12 @@ __global__ void __launch_bounds__(TPB) k_keygen(const double4* __restrict__ rec,
                 if (lane == __ffs(peers) - 1) atomicAdd(&h[p][dg], (uint32_t)__popc(peers));
             } else atomicAdd(&h[p][dg], 1u);
         }
+        n_outl += outl; n_edge += edge;
     }
-    unsigned mo = __ballot_sync(0xffffffffu, outl), me = __ballot_sync(0xffffffffu, edge);
-    if ((threadIdx.x & 31) == 0) {
-        if (mo) atomicAdd(&s->n_outliers, __popc(mo));
-        if (me) atomicAdd(&s->edge_dropped, __popc(me));
+    n_outl = __reduce_add_sync(0xffffffffu, n_outl); n_edge = __reduce_add_sync(0xffffffffu, n_edge);
+    if (lane == 0) {
+        if (n_outl) atomicAdd(&s->n_outliers, n_outl);
+        if (n_edge) atomicAdd(&s->edge_dropped, n_edge);
     }
     __syncthreads();
     for (int k = threadIdx.x; k < 8 * 256; k += TPB) { const uint32_t v = (&h[0][0])[k]; if (v) atomicAdd(&ghist[k], v); }
@@ -1023,7 +1025,7 @@ int agb_launch_keygen(AgbDev& d, AgbScalars* s, cudaStream_t st)
     cudaMemsetAsync(d.blockhist, 0, (8 * 256 + 64 + 8 * nb * 256) * sizeof(uint32_t), st);
     d.cur = 0;
     if (d.deep) { k_keygen_deep<<<nblk(d.n, TPB), TPB, 0, st>>>(d.rec, d.type, d.n, d.dk[0], d.dk[1], d.dk[2], d.perm[0], s); return 1; }
-    k_keygen<<<nblk(d.n, TPB), TPB, 0, st>>>(d.rec, d.type, d.n, d.khi[0], d.perm[0], s, d.blockhist);
+    k_keygen<<<std::min(nblk(d.n, TPB), 148 * 16), TPB, 0, st>>>(d.rec, d.type, d.n, d.khi[0], d.perm[0], s, d.blockhist);
     return 1;
 }
 

@@ -97,7 +97,10 @@ __global__ void __launch_bounds__(TPB) k_gas_compact(AgbDev d, const uint32_t* _
     // smallest / largest gas mass of the step (one atomic pair per warp)
     unsigned long long lo = gas ? mb : ~0ull, hi = mb;
     for (int o = 16; o > 0; o >>= 1) { lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o)); hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o)); }
-    if ((threadIdx.x & 31) == 0 && lo != ~0ull) { atomicMin(&s->gas_mmin, lo); atomicMax(&s->gas_mmax, hi); }
+    if ((threadIdx.x & 31) == 0 && lo != ~0ull) {                   // equal masses: only the first few warps find anything to update
+        if (lo < *(volatile unsigned long long*)&s->gas_mmin) atomicMin(&s->gas_mmin, lo);
+        if (hi > *(volatile unsigned long long*)&s->gas_mmax) atomicMax(&s->gas_mmax, hi);
+    }
 }
 
 struct GasFold {
