@@ -69,9 +69,7 @@ template <bool SPH, bool MIXED> struct WarpSmem : SphSmem<SPH && !MIXED> {
     int2 pend[PCAP];                       // (node, lane mask) of straddling nodes, resolved 32 at a time (one node per lane, loop over targets)
     float4 tpos[32];                       // minus the targets' positions about the box centre (units of L) + their tree positions
     double4 stage[32];                     // drain: the 32 sources of a tile
-    unsigned long long stat[12];           // per-warp statistics (kept out of the register file): node / leaf / SPH pairs, visits, exact tests, spills, rounds, popped, straddling, opened, tiles
 };
-enum { ST_NODE = 0, ST_LEAF, ST_SPH, ST_VISIT, ST_EXACT, ST_SPILL, ST_ROUNDS, ST_POPPED, ST_MIXED, ST_OPEN, ST_DRAIN };
 // k_sph: per gas target (1/h, 1/(pi h^4), 2 P/rho^2, sound speed), (vx, vy, vz, h), 8 floats: -(float-float position), (2h/L)^2, tree position
 struct SphWarp {
     double4 tsph[96];
@@ -305,8 +303,9 @@ __global__ void __launch_bounds__(WalkCfg<SPH>::TPB, WALK_CTAS) k_walk(const Wal
     const double inv_m0 = 1.0 / m0, acc_scale = kG * m0 * invR2;
     const float e02f = (float)e02s;
 
-    if (lane < 12) sm.stat[lane] = 0ull;
-    __syncwarp();
+    // statistics live in registers: keeping them in shared memory instead frees 22 registers (no spills) but costs 4 % on C1
+    unsigned long long tot_node = 0, tot_leaf = 0, tot_sph = 0, tot_visit = 0, tot_exact = 0, tot_spill = 0;
+    unsigned long long st_rounds = 0, st_popped = 0, st_mixed = 0, st_open = 0, st_drain = 0;
     unsigned long long st_cls[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};   // COUNT only: list entries / set bits by lane span (any, one half, one quarter), far-list entries
 
     auto stack_put = [&](int idx, int2 v) {
@@ -350,7 +349,6 @@ __global__ void __launch_bounds__(WalkCfg<SPH>::TPB, WALK_CTAS) k_walk(const Wal
             }
         }
         double ax = 0, ay = 0, az = 0, dU = 0;
-        int n_sph_lane = 0;                                                      // in-walk SPH pairs of this lane's target
         int c_vis = (active && (n_nodes > 0 || !valid)) ? 1 : 0, c_an = 0, c_al = 0, c_sp = 0;              // the root call itself
         const unsigned vmask = __ballot_sync(0xffffffffu, valid);
         const int tmin = __shfl_sync(0xffffffffu, (int)t, 0), tmax = __reduce_max_sync(0xffffffffu, (int)t);   // targets are sorted by tree position
@@ -448,7 +446,7 @@ __global__ void __launch_bounds__(WalkCfg<SPH>::TPB, WALK_CTAS) k_walk(const Wal
                         sp -= cnt;
                         if (lane < cnt) e = stack_get(sp + lane);
                         __syncwarp();                                        // the slots just read are overwritten by this round's pushes
-                        if (sp + cnt > SCAP && lane == 0) sm.stat[ST_SPILL] += 1;
+                        if (sp + cnt > SCAP) tot_spill += 1;
                         int outcome = OUT_NONE;
                         // the child slots are requested together with the node record (two independent L2 round trips instead
                         // of two dependent ones); they are simply not used when the node turns out to be accepted
@@ -470,7 +468,7 @@ __global__ void __launch_bounds__(WalkCfg<SPH>::TPB, WALK_CTAS) k_walk(const Wal
                         const unsigned mm = __ballot_sync(0xffffffffu, outcome == OUT_MIXED);
                         if (outcome == OUT_MIXED) sm.pend[npend + __popc(mm & lt)] = e;
                         npend += __popc(mm);
-                        if (lane == 0) { sm.stat[ST_ROUNDS] += 1; sm.stat[ST_POPPED] += cnt; sm.stat[ST_MIXED] += __popc(mm); }
+                        if (lane == 0) { st_rounds++; st_popped += cnt; st_mixed += __popc(mm); }
                     } else {
                         // ---- resolve up to 32 parked nodes (the most recent ones)
                         const int nb = min(npend, 32);
@@ -507,7 +505,7 @@ __global__ void __launch_bounds__(WalkCfg<SPH>::TPB, WALK_CTAS) k_walk(const Wal
                                     const double r2e = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
                                     acc = __ddiv_rn(__dsqrt_rn(qw), __dsqrt_rn(r2e)) < theta;      // sqrt(radius^2) is exact: radius = R 2^-k
                                     open = !acc;
-                                    atomicAdd(&sm.stat[ST_EXACT], 1ull);
+                                    tot_exact++;
                                 }
                             }
                         };
@@ -557,7 +555,7 @@ __global__ void __launch_bounds__(WalkCfg<SPH>::TPB, WALK_CTAS) k_walk(const Wal
                             }
                         }
                         lc += tl; sp += tn;
-                        if (lane == 0) sm.stat[ST_OPEN] += __popc(om);
+                        if (lane == 0) st_open += __popc(om);
                     }
                     __syncwarp();
                     // warm L1 with the node records the next round will pop
@@ -568,7 +566,7 @@ __global__ void __launch_bounds__(WalkCfg<SPH>::TPB, WALK_CTAS) k_walk(const Wal
                 }
 
                 // ------------------------------------------------ drain the interaction list
-                if (lane == 0) sm.stat[ST_DRAIN] += (lc + 31) / 32;
+                if (lane == 0) st_drain += (lc + 31) / 32;
                 for (int base = 0; base < lc; base += 32) {
                     const int cnt = min(32, lc - base);
                     __syncwarp();
@@ -626,8 +624,7 @@ __global__ void __launch_bounds__(WalkCfg<SPH>::TPB, WALK_CTAS) k_walk(const Wal
                         if (sl.ident) { if (maybe) pc_mask &= ~(1u << (ex_part - tmin)); }        // every particle active: lane = offset in the group
                         else if (__any_sync(0xffffffffu, maybe))
                             for (int l2 = 0; l2 < 32; l2++) { const int tl = __shfl_sync(0xffffffffu, (int)t, l2); if (ex_part >= 0 && ex_part == tl) pc_mask &= ~(1u << l2); }
-                        const unsigned nlf = __reduce_add_sync(0xffffffffu, ex_part >= 0 ? __popc(pc_mask) : 0), nnd = __reduce_add_sync(0xffffffffu, ex_part >= 0 ? 0 : __popc(pc_mask));
-                        if (lane == 0) { sm.stat[ST_LEAF] += nlf; sm.stat[ST_NODE] += nnd; }
+                        if (ex_part >= 0) tot_leaf += __popc(pc_mask); else tot_node += __popc(pc_mask);
                     }
                     if (SPLIT && wgas) {
                         // sources within 2 h_max of the warp's box that a gas target accepted: (source, those targets) for k_sph
@@ -756,7 +753,7 @@ __global__ void __launch_bounds__(WalkCfg<SPH>::TPB, WALK_CTAS) k_walk(const Wal
                                     // within 1e-13 of the gate: the reference's own separately rounded expression
                                     const double r2e = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
                                     pass = __dsqrt_rn(r2e) < __dmul_rn(h_t, 2.0);
-                                    atomicAdd(&sm.stat[ST_EXACT], 1ull);
+                                    tot_exact++;
                                 }
                                 if (pass) {
                                     const double inv_h = k4.x, inv_pi_h4 = k4.y, cs = k4.w;
@@ -775,7 +772,7 @@ __global__ void __launch_bounds__(WalkCfg<SPH>::TPB, WALK_CTAS) k_walk(const Wal
                                     const double fx = coef * gx, fy = coef * gy, fz = coef * gz;
                                     dU += 0.5 * gv.w * (A2 + MU) * (vx * gx + vy * gy + vz * gz);      // Node.cpp:167
                                     if (!(isnan(fx) || isnan(fy) || isnan(fz))) { ax += fx; ay += fy; az += fz; }   // Node.cpp:169
-                                    n_sph_lane++;
+                                    tot_sph++;
                                     if (COUNT) c_sp++;
                                 }
                             }
@@ -794,23 +791,21 @@ __global__ void __launch_bounds__(WalkCfg<SPH>::TPB, WALK_CTAS) k_walk(const Wal
             P.ax[p] = ax; P.ay[p] = ay; P.az[p] = az;                           // Tree.cpp:77 (acc = 0) + accumulated force
             if (INWALK && tgas && dU != 0.0) P.dUdt[p] += dU;
             if (COUNT) { P.c_visits[t] = c_vis; P.c_accn[t] = c_an; P.c_accl[t] = c_al; P.c_sph[t] = c_sp; }
-        }
-        {
-            const unsigned nv = __reduce_add_sync(0xffffffffu, active ? (unsigned)c_vis : 0u), ns = __reduce_add_sync(0xffffffffu, (unsigned)n_sph_lane);
-            if (lane == 0) { sm.stat[ST_VISIT] += nv; sm.stat[ST_SPH] += ns; }
+            tot_visit += (unsigned long long)c_vis;
         }
     }
 
-    __syncwarp();
+    tot_node = warp_sum_u64(tot_node); tot_leaf = warp_sum_u64(tot_leaf); tot_sph = warp_sum_u64(tot_sph);
+    tot_visit = warp_sum_u64(tot_visit); tot_exact = warp_sum_u64(tot_exact); tot_spill = warp_sum_u64(tot_spill);
     if (lane == 0) {
-        if (sm.stat[ST_NODE]) atomicAdd(&P.s->c_node, sm.stat[ST_NODE]);
-        if (sm.stat[ST_LEAF]) atomicAdd(&P.s->c_leaf, sm.stat[ST_LEAF]);
-        if (sm.stat[ST_SPH]) atomicAdd(&P.s->c_sph, sm.stat[ST_SPH]);
-        if (sm.stat[ST_VISIT]) atomicAdd(&P.s->c_visits, sm.stat[ST_VISIT]);
-        if (sm.stat[ST_EXACT]) atomicAdd(&P.s->c_exact, sm.stat[ST_EXACT]);
-        if (sm.stat[ST_SPILL]) atomicAdd(&P.s->c_spill, sm.stat[ST_SPILL]);
-        atomicAdd(&P.s->st_rounds, sm.stat[ST_ROUNDS]); atomicAdd(&P.s->st_popped, sm.stat[ST_POPPED]); atomicAdd(&P.s->st_mixed, sm.stat[ST_MIXED]);
-        atomicAdd(&P.s->st_open, sm.stat[ST_OPEN]); atomicAdd(&P.s->st_drain, sm.stat[ST_DRAIN]);
+        if (tot_node) atomicAdd(&P.s->c_node, tot_node);
+        if (tot_leaf) atomicAdd(&P.s->c_leaf, tot_leaf);
+        if (tot_sph) atomicAdd(&P.s->c_sph, tot_sph);
+        if (tot_visit) atomicAdd(&P.s->c_visits, tot_visit);
+        if (tot_exact) atomicAdd(&P.s->c_exact, tot_exact);
+        if (tot_spill) atomicAdd(&P.s->c_spill, tot_spill);
+        atomicAdd(&P.s->st_rounds, st_rounds); atomicAdd(&P.s->st_popped, st_popped); atomicAdd(&P.s->st_mixed, st_mixed);
+        atomicAdd(&P.s->st_open, st_open); atomicAdd(&P.s->st_drain, st_drain);
         if (COUNT) for (int c = 0; c < 10; c++) atomicAdd(&P.s->st_cls[c], st_cls[c]);
     }
 }
