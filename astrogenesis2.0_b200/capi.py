@@ -48,7 +48,7 @@ COUNTER_FIELDS = ("n_particles", "n_in_tree", "n_outliers", "n_nodes", "n_active
                   "groups", "gas_groups", "gas_orphans", "gas_ties_exact", "gas_ties_unresolved",
                   "walk_rounds", "walk_popped", "walk_straddling", "walk_opened", "walk_tiles", "walk_stack_spills",
                   "walk_ent_wide", "walk_ent_half", "walk_ent_quarter", "walk_bits_wide", "walk_bits_half", "walk_bits_quarter", "walk_ent_far",
-                  "walk_ent_class0", "walk_ent_class1", "walk_ent_class2")
+                  "walk_ent_class0", "walk_ent_class1", "walk_ent_class2", "sph_records")
 
 
 class Counters(C.Structure):

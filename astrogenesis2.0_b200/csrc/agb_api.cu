@@ -169,11 +169,12 @@ int ensure_pool(agb_ctx* c, int64_t n)
 int ensure_deep(agb_ctx* c)
 {
     AgbDev& d = c->d;
-    d.deep = true;
-    if (d.kex) return AGB_OK;
-    const size_t cap = (size_t)d.cap;
-    for (auto& q : d.dk) CK(dalloc(q, cap));
-    CK(dalloc(d.kex, cap));
+    if (!d.kex) {
+        const size_t cap = (size_t)d.cap;
+        for (auto& q : d.dk) CK(dalloc(q, cap));
+        CK(dalloc(d.kex, cap));
+    }
+    d.deep = true;                                              // only once the buffers exist
     return AGB_OK;
 }
 
@@ -191,7 +192,7 @@ int ensure_counters(agb_ctx* c)
 int ensure_sph_records(agb_ctx* c, int64_t want)
 {
     AgbDev& d = c->d;
-    want = std::min<int64_t>(std::max<int64_t>(want, std::max<int64_t>(65536, d.cap / 8)), 0x7fffff00);
+    want = std::min<int64_t>(std::max<int64_t>(want, std::max<int64_t>(65536, d.cap / 4)), 0x7fffff00);   // C3 needs ~0.2 records per particle: no second walk on the first gas step
     if (!d.rec_head) CK(dalloc(d.rec_head, (size_t)d.cap / 32 + 16));
     if (d.rec_ent && d.rec_cap >= want) return AGB_OK;
     dfree(d.rec_ent); dfree(d.rec_next); d.rec_cap = 0;
@@ -345,8 +346,8 @@ int agb_set_option(agb_ctx* c, int option, int64_t value)
     if (option == AGB_OPT_PRECISION) { if (value != 0 && value != 1) return AGB_ERR_INVALID; c->mixed = value == 1; return AGB_OK; }
     if (option == AGB_OPT_COOLING) { c->opt_cooling = value != 0; return AGB_OK; }
     if (option == AGB_OPT_EXTENDED) {
+        if (value != 0 && c->d.ncap > 0 && !c->d.quad) { CK(cudaSetDevice(c->device)); CK(dalloc(c->d.quad, 6 * (size_t)c->d.ncap)); CK(dalloc(c->d.ext_bar, 1)); }
         c->extended = value != 0; c->ext_quad = value != 2;
-        if (c->extended && c->d.ncap > 0 && !c->d.quad) { CK(cudaSetDevice(c->device)); CK(dalloc(c->d.quad, 6 * (size_t)c->d.ncap)); CK(dalloc(c->d.ext_bar, 1)); }
         return AGB_OK;
     }
     if (option == AGB_OPT_STAR_FORMATION) { c->opt_sf_seed = (unsigned long long)value; return AGB_OK; }
@@ -687,6 +688,7 @@ int agb_get_counters(agb_ctx* c, agb_counters* o)
     o->walk_bits_wide = (int64_t)h.st_cls[3]; o->walk_bits_half = (int64_t)h.st_cls[4]; o->walk_bits_quarter = (int64_t)h.st_cls[5];
     o->walk_ent_far = (int64_t)h.st_cls[6];
     o->walk_ent_class0 = (int64_t)h.st_cls[7]; o->walk_ent_class1 = (int64_t)h.st_cls[8]; o->walk_ent_class2 = (int64_t)h.st_cls[9];
+    o->sph_records = (int64_t)h.cand_cursor;
     return AGB_OK;
 }
 

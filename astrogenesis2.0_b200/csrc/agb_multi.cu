@@ -11,6 +11,7 @@
 // fan out, join, and return the first error.  No NCCL: one process owns all devices, cudaMemcpyPeerAsync is the collective.
 #include "agb_internal.cuh"
 #include <algorithm>
+#include <atomic>
 #include <cstring>
 #include <functional>
 #include <string>
@@ -115,8 +116,11 @@ int exchange_results(agb_multi* m)
             const int i = (j + k) % nd;                              // staggered: no two devices pull from the same peer at once
             const int64_t cnt = m->s_cnt[(size_t)i];
             if (cnt == 0) continue;
-            cudaMemcpyPeerAsync(m->r_idx[(size_t)j], dev, m->s_idx[(size_t)i], m->dev[(size_t)i], (size_t)cnt * 4, st);
-            cudaMemcpyPeerAsync(m->r_val[(size_t)j], dev, m->s_val[(size_t)i], m->dev[(size_t)i], (size_t)(3 * m->buf_cap + cnt) * 8, st);
+            if (cudaMemcpyPeerAsync(m->r_idx[(size_t)j], dev, m->s_idx[(size_t)i], m->dev[(size_t)i], (size_t)cnt * 4, st) != cudaSuccess ||
+                cudaMemcpyPeerAsync(m->r_val[(size_t)j], dev, m->s_val[(size_t)i], m->dev[(size_t)i], (size_t)(3 * m->buf_cap + cnt) * 8, st) != cudaSuccess) {
+                (void)cudaGetLastError();
+                return AGB_ERR_CUDA;
+            }
             k_apply_slice<<<(int)((cnt + 255) / 256), 256, 0, st>>>(m->r_idx[(size_t)j], m->r_val[(size_t)j], cnt, m->buf_cap, d->ax, d->ay, d->az, d->dUdt);
         }
         if (cudaStreamSynchronize(st) != cudaSuccess || cudaGetLastError() != cudaSuccess) return AGB_ERR_CUDA;
@@ -228,7 +232,7 @@ int agb_multi_set_particles_aos(agb_multi* m, void* const* parts, int64_t n, con
     double* col[18];
     for (size_t k = 0; k < cols; k++) col[k] = m->stage + k * nn;
     uint8_t* typ = reinterpret_cast<uint8_t*>(m->stage + cols * nn);
-    bool bad = false;
+    std::atomic<bool> bad{false};
     host_parallel(n, [&](int64_t a, int64_t b) {
         auto vec = [&](int64_t off, int64_t i, int k0) {
             if (off < 0) { col[k0][i] = col[k0 + 1][i] = col[k0 + 2][i] = 0.0; return; }

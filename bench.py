@@ -536,7 +536,7 @@ def run_gpu_arm(args, pkg):
                 "parallelism": "replicated tree, tree-ordered target slices, 1 coalesced NCCL all-gather group/step (in place)" if world > 1 else "single GPU",
                 "result_columns": list(out_cols)},
         "e2e": e2e, "fp64": fp64, "resident_sim_step": resident, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
-        "interactions_per_s": inter_all / (walk_ms_avg * 1e-3), "sph_pairs_per_step": sph_all, "divergence_counters": divergence, "multi_gpu_check": multi_gpu_check,
+        "interactions_per_s": inter_all / (walk_ms_avg * 1e-3), "sph_pairs_per_step": sph_all, "sph_records_per_step_rank0": cnt.get("sph_records"), "divergence_counters": divergence, "multi_gpu_check": multi_gpu_check,
         "wall_s_timed_region": t_wall,
     }
     print(json.dumps(line))

@@ -94,6 +94,7 @@ typedef struct {
     int64_t walk_ent_wide, walk_ent_half, walk_ent_quarter, walk_bits_wide, walk_bits_half, walk_bits_quarter, walk_ent_far;
     /* ... and the entries evaluated by each of the three pair loops of the mixed-precision walk (far + every target, far, near) */
     int64_t walk_ent_class0, walk_ent_class1, walk_ent_class2;
+    int64_t sph_records;            /* mixed mode: 32-entry candidate records the walk wrote for the SPH pair kernel */
 } agb_counters;
 
 /* -------- lifetime: `new Tree(sim)` / `delete tree`, but persistent across steps (pooled memory) */
