@@ -677,3 +677,63 @@ def test_device_timestep_bins_round_like_libm(pkg, ctxs):
     ctx.integrator_assign_all()
     ts = ctx.state()["timeStep"]
     assert np.array_equal(ts, np.array(want)), np.flatnonzero(ts != np.array(want))
+
+
+def test_call_sequences_keep_their_state_straight(pkg):
+    """One long-lived context driven through a random mix of hand-overs and call styles (four calls, the fused call with and
+    without bound result arrays, slices, precision switches, particle sets with and without gas, with inactive particles): every
+    step must give the bits a fresh context gives for the same particles and options.  Guards the bookkeeping of the asynchronous
+    hand-over (three upload groups, late-upload path, remembered 'holds gas' / FP32-range decisions, pool growth)."""
+    rng = np.random.default_rng(123)
+    sets = []
+    for k, p in enumerate((pkg.ics.disk_galaxy(30000, seed=71), pkg.ics.plummer(20000, seed=72), pkg.ics.plummer(12000, seed=73, gas_fraction=0.3),
+                           pkg.ics.disk_galaxy(45000, seed=74))):
+        n = len(p["x"])
+        if k >= 2:
+            p["next_time"] = np.where(rng.random(n) < 0.6, 0.0, 1e13)
+            for c in ("dUdt", "rho", "P", "T", "ax", "ay", "az", "h"):
+                p[c] = rng.random(n) + 0.5
+        mh = pkg.ics.gas_mass_in_h(p, 32) if (p["type"] == 2).any() else 1e40
+        sets.append((p, mh))
+    names = ("ax", "ay", "az", "dUdt", "h", "rho", "P", "T", "visualDensity")
+    fresh = {}
+
+    def expected(k, mixed):
+        if (k, mixed) not in fresh:
+            c = pkg.Context(0, 8)
+            c.set_option(pkg.capi.AGB_OPT_PRECISION, 1 if mixed else 0)
+            p, mh = sets[k]
+            out, _ = pkg.run_step(dict(p), 0.5, 1e18, mh, 0.0, context=c)
+            out["visualDensity"] = out["vis"]
+            fresh[(k, mixed)] = out
+            c.close()
+        return fresh[(k, mixed)]
+    ctx = pkg.Context(0, 8)
+    try:
+        for step in range(28):
+            k = int(rng.integers(len(sets))); mixed = bool(rng.integers(2)); style = int(rng.integers(4))
+            p, mh = sets[k]
+            n = len(p["x"])
+            want = expected(k, mixed)
+            ctx.set_option(pkg.capi.AGB_OPT_PRECISION, 1 if mixed else 0)
+            bound = None
+            if style == 2:
+                bound = {c: np.full(n, np.nan) for c in names}
+                ctx.bind_results(bound)
+            ctx.set_particles(dict(p))
+            if style == 0:
+                R = ctx.build_tree(); ctx.visual_density(R / 100000); ctx.gas_density(mh); ctx.forces(0.0, 1e18, 0.5)
+            elif style == 3:
+                R = ctx.build_tree(); ctx.visual_density(R / 100000); ctx.gas_density(mh)
+                for part in rng.permutation(3):
+                    ctx.forces(0.0, 1e18, 0.5, int(part), 3)
+            else:
+                R = ctx.force_path(want["R"] / 100000, mh, 0.0, 1e18, 0.5)
+            assert R == want["R"], (step, k, mixed, style)
+            got = ctx.results_into(bound) if bound is not None else ctx.results()
+            if bound is not None:
+                ctx.bind_results(None)
+            for c in names:
+                assert np.array_equal(got[c], want[c]), (step, k, mixed, style, c)
+    finally:
+        ctx.close()
