@@ -18,7 +18,7 @@ AGB_OPT_STAR_FORMATION = 4
 AGB_OPT_EXTENDED = 5
 
 EXPORTS = [
-    "agb_create", "agb_destroy", "agb_set_particles", "agb_set_particles_aos", "agb_build_tree", "agb_visual_density",
+    "agb_create", "agb_destroy", "agb_set_particles", "agb_set_particles_staged", "agb_set_particles_aos", "agb_build_tree", "agb_visual_density",
     "agb_gas_density", "agb_forces", "agb_forces_slice", "agb_force_path", "agb_get_slice_count", "agb_get_slice_results", "agb_get_slice_results_all", "agb_get_kernel_ms", "agb_get_results", "agb_bind_results", "agb_get_results_aos", "agb_get_counters",
     "agb_set_option", "agb_get_tree_particles", "agb_get_node_count", "agb_get_nodes", "agb_get_target_counters",
     "agb_get_phase_ms", "agb_get_stream", "agb_get_launch_count", "agb_microbench",
@@ -84,6 +84,8 @@ def load(build_if_needed=True):
     lib.agb_destroy.argtypes = [vp]
     lib.agb_set_particles.argtypes = [vp, C.POINTER(Particles), C.c_int]
     lib.agb_set_particles_aos.argtypes = [vp, C.POINTER(vp), C.c_int64, C.POINTER(AosLayout)]
+    if hasattr(lib, "agb_set_particles_staged"):
+        lib.agb_set_particles_staged.argtypes = [vp, C.POINTER(Particles), C.c_int, vp, vp, vp]
     lib.agb_build_tree.argtypes = [vp, _pd]
     lib.agb_visual_density.argtypes = [vp, C.c_double]
     lib.agb_gas_density.argtypes = [vp, C.c_double]

@@ -24,6 +24,7 @@ struct agb_ctx {
     cudaEvent_t ev_sync = nullptr;                    // compute stream reached the point of a new hand-over (orders st_copy after it)
     cudaEvent_t ev_pos = nullptr;                     // x, y, z, mass, type are on the device (st): the other uploads start after them (they would share the link)
     bool in_pending = false, next_pending = false;
+    cudaEvent_t xev[3] = {};                          // agb_set_particles_staged: the caller's "group is complete" events (positions+mass+type, next_time, the rest)
     cudaEvent_t evw[5] = {};                          // walk timing: before k_far, before k_walk, after k_walk, after k_sph, before k_sph
     cudaEvent_t ev[10] = {};
     cudaEvent_t evk[10] = {};                         // kernel-level timing: walk [0..3] = before k_far, k_walk, k_sph, after; build [4..9] = start, keys, sort, gather, links, end
@@ -363,6 +364,7 @@ int agb_set_particles(agb_ctx* c, const agb_particles* p, int memspace)
     if (rc) return rc;
     AgbDev& d = c->d;
     d.n = n;
+    for (auto& e : c->xev) e = nullptr;
     // Everything already queued on the compute stream (densities, walk, integrator kernels of the previous step) reads or
     // writes the buffers the copy stream is about to overwrite: order the copy stream after it.
     CK(cudaEventRecord(c->ev_sync, c->st));
@@ -402,6 +404,17 @@ int agb_set_particles(agb_ctx* c, const agb_particles* p, int memspace)
     c->have_particles = true; c->built = false; c->dens_done = false; c->forces_done = false; c->counters_valid = false;
     c->int_ready = false;
     for (bool& f : c->bres_sent) f = false;
+    return AGB_OK;
+}
+
+int agb_set_particles_staged(agb_ctx* c, const agb_particles* p, int memspace, void* ready_positions, void* ready_next_time, void* ready_all)
+{
+    int rc = agb_set_particles(c, p, memspace);
+    if (rc) return rc;
+    // The caller's arrays are still being produced (an all-gather, a copy, its own kernels) on streams of its own: each group
+    // is read only after the event the caller recorded behind its producer.  The compute stream needs the first group at once.
+    c->xev[0] = (cudaEvent_t)ready_positions; c->xev[1] = (cudaEvent_t)ready_next_time; c->xev[2] = (cudaEvent_t)ready_all;
+    if (c->xev[0]) CK(cudaStreamWaitEvent(c->st, c->xev[0], 0));
     return AGB_OK;
 }
 
@@ -458,6 +471,15 @@ int agb_set_particles_aos(agb_ctx* c, void* const* parts, int64_t n, const agb_a
 }
 
 // the kernels of Tree::buildTree on the context's stream (no synchronisation)
+// the compute stream waits for every group of the last hand-over (the library's own uploads and the caller's staged events)
+static void join_uploads(agb_ctx* c)
+{
+    if (!c->in_pending) return;
+    cudaStreamWaitEvent(c->st, c->ev_in, 0);
+    for (int k = 1; k < 3; k++) if (c->xev[k]) cudaStreamWaitEvent(c->st, c->xev[k], 0);
+    c->in_pending = false; c->next_pending = false;
+}
+
 // late_gas (agb_force_path, host hand-over, mixed precision, gas): the build only waits for the first upload group; the
 // tree's gas velocities are completed by launch_late_gas once the second group is there
 static void launch_build(agb_ctx* c, bool late_gas = false)
@@ -469,8 +491,8 @@ static void launch_build(agb_ctx* c, bool late_gas = false)
     cudaEventRecord(c->evk[5], c->st);
     c->launches += agb_launch_sort(d, c->s, c->st);
     cudaEventRecord(c->evk[6], c->st);
-    if (late_gas) { if (c->next_pending) { cudaStreamWaitEvent(c->st, c->ev_next, 0); c->next_pending = false; } }
-    else if (c->in_pending) { cudaStreamWaitEvent(c->st, c->ev_in, 0); c->in_pending = false; c->next_pending = false; }
+    if (late_gas) { if (c->next_pending) { cudaStreamWaitEvent(c->st, c->ev_next, 0); if (c->xev[1]) cudaStreamWaitEvent(c->st, c->xev[1], 0); c->next_pending = false; } }
+    else if (c->in_pending) { join_uploads(c); }
     c->launches += agb_launch_links(d, c->s, c->st, &c->evk[7], late_gas);
     cudaEventRecord(c->evk[9], c->st);
     c->build_timed = true;
@@ -586,7 +608,7 @@ static int forces_impl(agb_ctx* c, double global_time, double e0, double theta, 
         else if (late_gas) {
             c->launches += agb_launch_walk(d, c->s, global_time, e0, theta, part, nparts, c->target_counters, any_gas, mixed, c->sm_count, c->st, c->evw, 1);
             if (attempt == 0) {
-                if (c->in_pending) { CK(cudaStreamWaitEvent(c->st, c->ev_in, 0)); c->in_pending = false; }
+                join_uploads(c);
                 c->launches += agb_launch_late_gas(d, c->s, c->st);
                 int rc = stream_out(c, 6, 7);
                 if (rc) return rc;
@@ -645,7 +667,7 @@ int agb_force_path(agb_ctx* c, double visual_density_radius, double mass_in_h, d
     // Host hand-over still uploading (set_particles is asynchronous): in mixed precision only the SPH pair pass needs the gas
     // velocities / U / mu, so the build, the densities and the gravity walk start on the first upload group and the rest of
     // the transfer hides behind them.
-    const bool late_gas = c->in_pending && !c->bound && !c->extended && mixed_in_range(c, e0) && c->gas_hint;
+    const bool late_gas = c->in_pending && (!c->bound || c->xev[2]) && !c->extended && mixed_in_range(c, e0) && c->gas_hint;
     CK(cudaEventRecord(c->ev[8], c->st));
     { Phase ph("build tree"); launch_build(c, late_gas); }
     CK(cudaEventRecord(c->ev[9], c->st));
@@ -698,7 +720,7 @@ int agb_get_results(agb_ctx* c, const agb_results* r, int memspace)
     CK(cudaSetDevice(c->device));
     const size_t b = (size_t)c->d.n * sizeof(double);
     const cudaMemcpyKind k = memspace == AGB_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
-    if (c->in_pending) { CK(cudaStreamWaitEvent(c->st, c->ev_in, 0)); c->in_pending = false; }
+    join_uploads(c);
     ResCol cp[9], bp[9];
     result_table(*r, c->d, cp);
     result_table(c->bres, c->d, bp);
@@ -914,7 +936,7 @@ int agb_integrator_init(agb_ctx* c, double eta, double min_time_step, double max
     CK(cudaSetDevice(c->device));
     AgbDev& d = c->d;
     if (d.n > 0 && (!d.vx || !d.vy || !d.vz || !d.U || !d.next)) { c->err = "integrator needs vx, vy, vz, U and next_time arrays"; return AGB_ERR_INVALID; }
-    if (c->in_pending) { CK(cudaStreamWaitEvent(c->st, c->ev_in, 0)); c->in_pending = false; }
+    join_uploads(c);
     AgbInt& I = c->I;
     I.x = c->in_d[0]; I.y = c->in_d[1]; I.z = c->in_d[2]; I.vx = c->in_d[3]; I.vy = c->in_d[4]; I.vz = c->in_d[5]; I.U = c->in_d[7]; I.next = c->in_d[8];
     I.mu = d.mu; I.timestep = c->timestep;
@@ -1083,5 +1105,5 @@ int agb_ctx_copy_particles_from(agb_ctx* c, agb_ctx* src)
 
 void agb_ctx_join_uploads(agb_ctx* c)
 {
-    if (c->in_pending) { cudaStreamWaitEvent(c->st, c->ev_in, 0); c->in_pending = false; c->next_pending = false; }
+    join_uploads(c);
 }

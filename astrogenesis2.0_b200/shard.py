@@ -109,6 +109,20 @@ class InPlaceGather:
         self.out = {k: torch.empty(n, dtype=dt, device=device) for k, dt in dtypes.items()}
         self.shard = {k: v[lo:hi] for k, v in self.out.items()}
 
+    def gather_fields(self, fields):
+        """One coalesced group of in-place all-gathers for some of the arrays (a driver that hands the arrays over in stages:
+        positions / masses / types first, so that the tree build overlaps the exchange of the rest)."""
+        if self.world > 1:
+            coalesce = getattr(dist, "_coalescing_manager", None)
+            if coalesce is not None and dist.get_backend() == "nccl":
+                with coalesce(device=self.device):
+                    for k in fields:
+                        dist.all_gather_into_tensor(self.out[k], self.shard[k])
+            else:
+                for k in fields:
+                    dist.all_gather_into_tensor(self.out[k], self.shard[k].clone())
+        return self.out
+
     def gather(self, shard=None):
         if shard is not None and shard is not self.shard:
             for k, v in shard.items():

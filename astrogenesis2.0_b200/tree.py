@@ -74,14 +74,19 @@ class Context:
         self._keep = keep          # uploads are asynchronous: the arrays must outlive agb_build_tree
         self.n = n
 
-    def set_particles_device(self, ptrs, n):
-        """ptrs: dict name -> device address (int) of float64 arrays (uint8 for 'type'); read in place."""
+    def set_particles_device(self, ptrs, n, events=None):
+        """ptrs: dict name -> device address (int) of float64 arrays (uint8 for 'type'); read in place.
+        events: optional (ready_positions, ready_next_time, ready_all) cudaEvent_t handles (ints, 0 = ready now) recorded behind
+        whatever still produces the arrays on the caller's streams (agb_set_particles_staged)."""
         st = capi.Particles()
         st.n = n
         for k in _F8:
             setattr(st, k, C.cast(C.c_void_p(ptrs.get(k, 0) or None), C.POINTER(C.c_double)))
         st.type = C.cast(C.c_void_p(ptrs["type"]), C.POINTER(C.c_uint8))
-        capi.check(self.h, self.lib.agb_set_particles(self.h, C.byref(st), capi.AGB_MEM_DEVICE))
+        if events is None:
+            capi.check(self.h, self.lib.agb_set_particles(self.h, C.byref(st), capi.AGB_MEM_DEVICE))
+        else:
+            capi.check(self.h, self.lib.agb_set_particles_staged(self.h, C.byref(st), capi.AGB_MEM_DEVICE, *[C.c_void_p(int(e) or None) for e in events]))
         self.n = n
 
     # ---- the four calls

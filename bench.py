@@ -247,20 +247,49 @@ def run_gpu_arm(args, pkg):
         if world > 1:
             packed.gather(shard)
 
+    # Staged exchange (equal shards): positions / masses / types first, then next_time, then velocities / U / mu, each group as one
+    # coalesced in-place all-gather with an event behind it.  agb_set_particles_staged reads a group only after its event, so the
+    # tree build, the densities and the gravity walk overlap the exchange (and, end to end, the upload) of the later groups.
+    staged = world > 1 and isinstance(packed, pkg.shard.InPlaceGather)
+    groups = [[k for k in g if k in shard] for g in (("x", "y", "z", "mass", "type"), ("next_time",), ("vx", "vy", "vz", "U", "mu"))]
+    keep_events = []
+
     breakdown = os.environ.get("AGB_BENCH_BREAKDOWN") == "1"      # development: per-step device time of the exchange vs the path
     bd_ev = []
 
-    def step():
+    def step(upload=None):
         if breakdown:
             e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
             e[0].record(torch.cuda.current_stream())
-        gather()
-        if breakdown:
-            e[1].record(torch.cuda.current_stream())
-        if world > 1:
-            stream.wait_stream(torch.cuda.current_stream())
         ptrs = {k: full[k].data_ptr() for k in full}
-        ctx.set_particles_device(ptrs, n)
+        if staged:
+            evs = []
+            del keep_events[:]
+            for grp in groups:
+                if not grp:
+                    evs.append(0)
+                    continue
+                if upload is not None:
+                    for k in grp:
+                        shard[k].copy_(upload[k], non_blocking=True)
+                packed.gather_fields(grp)
+                ev_ = torch.cuda.Event()
+                ev_.record(torch.cuda.current_stream())
+                keep_events.append(ev_)
+                evs.append(ev_.cuda_event)
+            if breakdown:
+                e[1].record(torch.cuda.current_stream())
+            ctx.set_particles_device(ptrs, n, events=evs)
+        else:
+            if upload is not None:
+                for k in upload:
+                    shard[k].copy_(upload[k], non_blocking=True)
+            gather()
+            if breakdown:
+                e[1].record(torch.cuda.current_stream())
+            if world > 1:
+                stream.wait_stream(torch.cuda.current_stream())
+            ctx.set_particles_device(ptrs, n)
         # build_tree + visual_density + gas_density + forces, one host synchronisation (agb_force_path); the visual-density
         # radius is fixed at init like in the reference (Simulation.cpp:126)
         ctx.force_path(vis_radius, mh, 0.0, e0, THETA, rank, world)
@@ -289,6 +318,7 @@ def run_gpu_arm(args, pkg):
         ctx.forces(0.0, e0, THETA, rank, world)
         mine = ctx.slice_results(rank, world, names=out_cols)
         mine = {k: v.copy() for k, v in mine.items()}
+        mine_check = mine
         ctx.set_particles_device({k: full[k].data_ptr() for k in full}, n)     # fresh carried state (dU/dt accumulates across calls)
         ctx.build_tree(); ctx.visual_density(vis_radius); ctx.gas_density(mh)
         ctx.forces(0.0, e0, THETA, 0, 1)
@@ -408,11 +438,12 @@ def run_gpu_arm(args, pkg):
         out_np["index"] = out_np["index"].view(np.uint32)
 
         def e2e_step():
-            for k in host:
-                shard[k].copy_(host[k], non_blocking=True)
-            step()
+            step(upload=host)
             return ctx.slice_results(rank, world, names=out_cols, out=out_np)
         r = e2e_step()
+        # the staged, overlapped step returns the bits of the untimed call-by-call walk of this slice
+        if not (np.array_equal(r["index"], mine_check["index"]) and all(np.array_equal(r[k], mine_check[k]) for k in out_cols)):
+            raise SystemExit("end-to-end step differs from the checked slice results")
         mine = len(r["index"]) * (4 + 8 * len(out_cols))
         barrier()
         t0 = time.perf_counter()
@@ -426,7 +457,7 @@ def run_gpu_arm(args, pkg):
         te = float(te[0])
         e2e = {"value": n / te, "unit": "particles/s", "h2d_bytes_per_step": int(sum(v.numel() * v.element_size() for v in host.values()) * world),
                "d2h_bytes_per_step": int(by[1]), "ms_per_step": te * 1e3,
-               "what": "per rank: H2D of its particle shard, NCCL all-gather, build, densities, walk of its target slice, D2H of that slice's (index, %s)" % ", ".join(out_cols)}
+               "what": "per rank: H2D of its particle shard and NCCL all-gather in three groups (positions+mass+type | next_time | velocities, U, mu) overlapped with build, densities and walk of its target slice, D2H of that slice's (index, %s)" % ", ".join(out_cols)}
 
     # ---- device-resident simulation steps (integrator kernels + force path, nothing but the time crosses PCIe)
     resident = None
@@ -533,7 +564,8 @@ def run_gpu_arm(args, pkg):
         "dtype": "f64" if args.extended else "f64 decisions and accumulation, f32 pair forces (mixed mode)", "data": "synthetic",
         "config": cfg,
         "run": {"precision": "extended-accuracy mode (AGB_OPT_EXTENDED): quadrupoles, spline softening, width/d < theta per 32-target group, per-particle-h SPH; FP64; parity unpinned by the reference" if args.extended else "mixed", "l2": "256 MiB buffer written between timed steps (L2 flush); working set %.0f MB" % (n * 330 / 1e6),
-                "parallelism": "replicated tree, tree-ordered target slices, 1 coalesced NCCL all-gather group/step (in place)" if world > 1 else "single GPU",
+                "parallelism": ("replicated tree, tree-ordered target slices, in-place NCCL all-gathers in 3 coalesced groups per step, overlapped with the build (agb_set_particles_staged)" if staged else
+                                "replicated tree, tree-ordered target slices, packed NCCL all-gather per step") if world > 1 else "single GPU",
                 "result_columns": list(out_cols)},
         "e2e": e2e, "fp64": fp64, "resident_sim_step": resident, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
         "interactions_per_s": inter_all / (walk_ms_avg * 1e-3), "sph_pairs_per_step": sph_all, "sph_records_per_step_rank0": cnt.get("sph_records"), "divergence_counters": divergence, "multi_gpu_check": multi_gpu_check,

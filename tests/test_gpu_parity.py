@@ -737,3 +737,47 @@ def test_call_sequences_keep_their_state_straight(pkg):
                 assert np.array_equal(got[c], want[c]), (step, k, mixed, style, c)
     finally:
         ctx.close()
+
+
+def test_staged_device_hand_over_waits_for_its_events(pkg):
+    """agb_set_particles_staged: device arrays that are still being filled on another stream when they are handed over (what the
+    multi-GPU bench does with its all-gathers).  The arrays hold NaN until a delayed copy lands; every group is read only after
+    its event, in the call-by-call step and in the fused step that overlaps the last group with the build and the walk."""
+    import torch
+    p = pkg.ics.disk_galaxy(60000, seed=81)
+    n = len(p["x"])
+    mh = pkg.ics.gas_mass_in_h(p, 48)
+    one = pkg.Context(0, 8)
+    want, _ = pkg.run_step(dict(p), 0.5, 1e18, mh, 0.0, context=one)
+    want["visualDensity"] = want["vis"]
+    one.close()
+    dev = torch.device("cuda", 0)
+    f8 = ("x", "y", "z", "vx", "vy", "vz", "mass", "U", "next_time", "mu")
+    src = {k: torch.from_numpy(np.ascontiguousarray(p[k])).to(dev) for k in f8}
+    src["type"] = torch.from_numpy(np.ascontiguousarray(p["type"])).to(dev)
+    stage = {k: torch.empty_like(v) for k, v in src.items()}
+    groups = (("x", "y", "z", "mass", "type"), ("next_time",), ("vx", "vy", "vz", "U", "mu"))
+    side = torch.cuda.Stream(device=dev)
+    ctx = pkg.Context(0, 8)
+    try:
+        for rep in range(3):                                   # the first fused step of a context runs call by call, the others take the late path
+            for k, t in stage.items():
+                t.fill_(0 if k == "type" else float("nan"))
+            torch.cuda.synchronize()
+            evs = []
+            with torch.cuda.stream(side):
+                for grp in groups:
+                    torch.cuda._sleep(30_000_000)              # ~15 ms: the path would run far ahead of the data without the events
+                    for k in grp:
+                        stage[k].copy_(src[k])
+                    e = torch.cuda.Event()
+                    e.record(side)
+                    evs.append(e)
+            ctx.set_particles_device({k: t.data_ptr() for k, t in stage.items()}, n, events=[e.cuda_event for e in evs])
+            R = ctx.force_path(want["R"] / 100000, mh, 0.0, 1e18, 0.5)
+            got = ctx.results()
+            assert R == want["R"]
+            for k in ("ax", "ay", "az", "dUdt", "h", "rho", "P", "T", "visualDensity"):
+                assert np.array_equal(got[k], want[k]), (k, rep)
+    finally:
+        ctx.close()
