@@ -19,7 +19,7 @@ AGB_OPT_EXTENDED = 5
 
 EXPORTS = [
     "agb_create", "agb_destroy", "agb_set_particles", "agb_set_particles_staged", "agb_set_particles_aos", "agb_build_tree", "agb_visual_density",
-    "agb_gas_density", "agb_forces", "agb_forces_slice", "agb_force_path", "agb_get_slice_count", "agb_get_slice_results", "agb_get_slice_results_all", "agb_get_kernel_ms", "agb_get_results", "agb_bind_results", "agb_get_results_aos", "agb_get_counters",
+    "agb_gas_density", "agb_forces", "agb_forces_slice", "agb_force_path", "agb_get_slice_count", "agb_get_slice_results", "agb_get_slice_results_all", "agb_bind_slice_results", "agb_get_kernel_ms", "agb_get_results", "agb_bind_results", "agb_get_results_aos", "agb_get_counters",
     "agb_set_option", "agb_get_tree_particles", "agb_get_node_count", "agb_get_nodes", "agb_get_target_counters",
     "agb_get_phase_ms", "agb_get_stream", "agb_get_launch_count", "agb_microbench",
     "agb_integrator_init", "agb_integrator_assign_all", "agb_step_begin", "agb_step_end", "agb_get_state", "agb_get_subgrid_state", "agb_strerror", "agb_last_error", "agb_version",
@@ -96,6 +96,8 @@ def load(build_if_needed=True):
     lib.agb_get_slice_count.argtypes = [vp, C.c_int, C.c_int, C.POINTER(C.c_int64)]
     lib.agb_get_slice_results.argtypes = [vp, C.c_int, C.c_int, C.POINTER(C.c_uint32)] + [_pd] * 4 + [C.c_int]
     lib.agb_get_slice_results_all.argtypes = [vp, C.c_int, C.c_int, C.POINTER(C.c_uint32), C.POINTER(Results), C.c_int]
+    if hasattr(lib, "agb_bind_slice_results"):
+        lib.agb_bind_slice_results.argtypes = [vp, C.c_int, C.c_int, C.POINTER(C.c_uint32), C.POINTER(Results)]
     lib.agb_get_kernel_ms.argtypes = [vp, _pd]
     lib.agb_get_results.argtypes = [vp, C.POINTER(Results), C.c_int]
     lib.agb_bind_results.argtypes = [vp, C.POINTER(Results), C.c_int]

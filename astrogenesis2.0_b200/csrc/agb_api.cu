@@ -54,6 +54,9 @@ struct agb_ctx {
     // agb_bind_results: destinations registered in advance, streamed out as soon as their phase is done
     agb_results bres = {}; bool bres_on = false; int bres_space = AGB_MEM_HOST; bool bres_sent[9] = {};
     cudaEvent_t ev_out = nullptr;
+    // agb_bind_slice_results: host destinations of one target slice's compact results, delivered by agb_force_path itself
+    bool bs_on = false, bs_early = false, bs_late = false; int bs_part = 0, bs_nparts = 1; uint32_t* bs_index = nullptr; agb_results bs_res = {};
+    double* bs_buf = nullptr; uint32_t* bs_idx = nullptr; int64_t bs_cap = 0;
 };
 
 namespace {
@@ -293,6 +296,8 @@ static void destroy_handles(agb_ctx* c)
     if (c->stage) cudaFreeHost(c->stage);
     if (c->d_min) cudaFree(c->d_min);
     if (c->sfr) cudaFree(c->sfr);
+    if (c->bs_buf) cudaFree(c->bs_buf);
+    if (c->bs_idx) cudaFree(c->bs_idx);
 }
 
 int agb_create(agb_ctx** out, int device, int compat_cores)
@@ -645,11 +650,61 @@ int agb_forces(agb_ctx* c, double global_time, double e0, double theta) { return
 // device in between are taken from the previous step instead: the visual-density radius is the caller's (the reference
 // fixes it at init, Simulation.cpp:126) and "the particle set holds gas" (which decides whether the density kernels and the
 // SPH variant of the walk run) is verified after the fact; if it changed, the step is simply redone call by call.
+// columns [first, last] (results table order: ax ay az dUdt h rho P T vis) of the bound slice: compact on `st`, copy out on `out`
+static int send_slice_columns(agb_ctx* c, int64_t a0, int64_t a1, int first, int last, bool with_index, cudaStream_t out)
+{
+    const int64_t cnt = a1 - a0;
+    if (cnt <= 0) return AGB_OK;
+    double* host[9] = {c->bs_res.ax, c->bs_res.ay, c->bs_res.az, c->bs_res.dUdt, c->bs_res.h, c->bs_res.rho, c->bs_res.P, c->bs_res.T, c->bs_res.visualDensity};
+    double* dev[9];
+    bool any = with_index && c->bs_index;
+    for (int k = 0; k < 9; k++) { dev[k] = (k >= first && k <= last && host[k]) ? c->bs_buf + (size_t)k * c->bs_cap : nullptr; any = any || dev[k]; }
+    if (!any) return AGB_OK;
+    c->launches += agb_launch_slice_results(c->d, a0, a1, true, (with_index && c->bs_index) ? c->bs_idx : nullptr, dev, c->st);
+    if (out != c->st) { CK(cudaEventRecord(c->ev_out, c->st)); CK(cudaStreamWaitEvent(out, c->ev_out, 0)); }
+    if (with_index && c->bs_index) CK(cudaMemcpyAsync(c->bs_index, c->bs_idx, (size_t)cnt * sizeof(uint32_t), cudaMemcpyDeviceToHost, out));
+    for (int k = 0; k < 9; k++) if (dev[k]) CK(cudaMemcpyAsync(host[k], dev[k], (size_t)cnt * sizeof(double), cudaMemcpyDeviceToHost, out));
+    return AGB_OK;
+}
+
+int agb_bind_slice_results(agb_ctx* c, int part, int nparts, uint32_t* index, const agb_results* r)
+{
+    if (!c || (r && (nparts < 1 || part < 0 || part >= nparts))) return AGB_ERR_INVALID;
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->st_copy));                 // nothing may still be flowing to the old destinations
+    c->bs_on = r != nullptr;
+    if (r) { c->bs_res = *r; c->bs_index = index; c->bs_part = part; c->bs_nparts = nparts; }
+    return AGB_OK;
+}
+
+static int force_path_impl(agb_ctx* c, double visual_density_radius, double mass_in_h, double global_time, double e0, double theta, int part, int nparts, double* root_radius);
+
 int agb_force_path(agb_ctx* c, double visual_density_radius, double mass_in_h, double global_time, double e0, double theta, int part, int nparts, double* root_radius)
 {
     if (!c || !c->have_particles || nparts < 1 || part < 0 || part >= nparts) return AGB_ERR_INVALID;
+    c->bs_early = false;
+    int rc = force_path_impl(c, visual_density_radius, mass_in_h, global_time, e0, theta, part, nparts, root_radius);
+    if (rc || !c->bs_on || part != c->bs_part || nparts != c->bs_nparts) return rc;
+    // bound slice results: the density columns left during the walk when the step ran fused with every particle active (as the
+    // last step had it); whatever is still missing goes now
+    CK(cudaSetDevice(c->device));
+    if (c->bs_early && c->hs.n_active == c->d.n) {
+        int64_t a0 = 0, a1 = 0;
+        agb_slice_bounds(c->d.n, part, nparts, &a0, &a1);
+        if ((rc = send_slice_columns(c, a0, a1, 0, 3, false, c->st))) return rc;
+        if (c->bs_late && (rc = send_slice_columns(c, a0, a1, 6, 7, false, c->st))) return rc;      // P, T exist only after the late part of the build
+        CK(cudaStreamSynchronize(c->st)); CK(cudaStreamSynchronize(c->st_copy));
+        return AGB_OK;
+    }
+    CK(cudaStreamSynchronize(c->st_copy));
+    return agb_get_slice_results_all(c, part, nparts, c->bs_index, &c->bs_res, AGB_MEM_HOST);
+}
+
+static int force_path_impl(agb_ctx* c, double visual_density_radius, double mass_in_h, double global_time, double e0, double theta, int part, int nparts, double* root_radius)
+{
     auto stepwise = [&]() -> int {
         double R = 0.0;
+        c->bs_early = false;                                    // whatever left early came from an abandoned attempt
         int rc = agb_build_tree(c, &R);
         if (rc) return rc;
         if (root_radius) *root_radius = R;
@@ -677,6 +732,22 @@ int agb_force_path(agb_ctx* c, double visual_density_radius, double mass_in_h, d
     int rc;
     if ((rc = agb_visual_density(c, visual_density_radius))) return rc;
     if ((rc = gas_density_impl(c, mass_in_h, late_gas))) return rc;
+    if (c->bs_on && part == c->bs_part && nparts == c->bs_nparts && c->hs.n_active == d.n && d.n > 0) {
+        // bound slice results, every particle a target in the last step (verified for this one afterwards): index and density
+        // columns of the slice leave on the copy stream while the walk runs
+        int64_t a0 = 0, a1 = 0;
+        agb_slice_bounds(d.n, part, nparts, &a0, &a1);
+        if (a1 - a0 + 1 > c->bs_cap) {
+            dfree(c->bs_buf); dfree(c->bs_idx); c->bs_cap = 0;
+            const int64_t cap = a1 - a0 + 1024;
+            CK(dalloc(c->bs_buf, 9 * (size_t)cap)); CK(dalloc(c->bs_idx, (size_t)cap));
+            c->bs_cap = cap;
+        }
+        c->bs_late = late_gas;
+        if ((rc = send_slice_columns(c, a0, a1, 4, late_gas ? 5 : 7, true, c->st_copy))) return rc;
+        if ((rc = send_slice_columns(c, a0, a1, 8, 8, false, c->st_copy))) return rc;
+        c->bs_early = true;
+    }
     rc = forces_impl(c, global_time, e0, theta, part, nparts, late_gas);     // ends with the step's only synchronisation
     float ms = 0; if (cudaEventElapsedTime(&ms, c->ev[8], c->ev[9]) == cudaSuccess) c->phase_ms[0] = ms;
     (void)cudaGetLastError();

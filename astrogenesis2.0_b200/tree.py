@@ -138,6 +138,19 @@ class Context:
         capi.check(self.h, self.lib.agb_get_slice_results_all(self.h, int(part), int(nparts), capi.dptr(res["index"], C.c_uint32), C.byref(r), capi.AGB_MEM_HOST))
         return res
 
+    def bind_slice_results(self, part, nparts, out):
+        """Register (pinned) host arrays — `index` (uint32) and any of the nine result columns, each with room for the slice — as the
+        destination of slice (part, nparts): force_path(.., part, nparts) then delivers them itself (agb_bind_slice_results).
+        out = None unbinds."""
+        if out is None:
+            capi.check(self.h, self.lib.agb_bind_slice_results(self.h, 0, 1, None, None))
+            return
+        r = capi.Results()
+        for k in _OUT:
+            setattr(r, k, capi.dptr(out.get(k)))
+        capi.check(self.h, self.lib.agb_bind_slice_results(self.h, int(part), int(nparts), capi.dptr(out["index"], C.c_uint32), C.byref(r)))
+        self._bound_slice = out
+
     def bind_results(self, out):
         """Register host arrays (dict name -> float64 numpy array of length n, ideally pinned) as the destination of the
         results: density outputs are sent while the walk runs (agb_bind_results).  `results_into(out)` completes them."""

@@ -138,6 +138,10 @@ int agb_get_slice_results(agb_ctx* ctx, int part, int nparts, uint32_t* index, d
 /* ... the same for every field the path writes into Particle: r names the wanted columns (NULL = skip), each with room for the
  * slice's *count entries; h / rho / P / T / visualDensity are those of the slice's targets (every GPU computes all densities). */
 int agb_get_slice_results_all(agb_ctx* ctx, int part, int nparts, uint32_t* index, const agb_results* r, int memspace);
+/* Registers HOST destinations (ideally pinned) for the compact results of slice (part, nparts): agb_force_path(.., part, nparts, ..)
+ * then delivers them itself and returns when they have arrived — index and the density columns while the walk still runs (when
+ * every particle is a force target, as in fixed-step runs), acc / dU/dt after it.  r = NULL unbinds. */
+int agb_bind_slice_results(agb_ctx* ctx, int part, int nparts, uint32_t* index, const agb_results* r);
 
 /* -------- device-resident driver loop (optional).  With particles handed over from HOST memory the
  * context owns device copies; these calls advance them in place exactly like the reference's loop, so nothing but the

@@ -781,3 +781,39 @@ def test_staged_device_hand_over_waits_for_its_events(pkg):
                 assert np.array_equal(got[k], want[k]), (k, rep)
     finally:
         ctx.close()
+
+
+@pytest.mark.parametrize("active_frac", [1.0, 0.4])
+def test_bound_slice_results_are_delivered_by_the_fused_call(pkg, active_frac):
+    """agb_bind_slice_results: agb_force_path sends the bound slice's compact results itself (index and density columns during the
+    walk when every particle is a target, the rest after it; everything afterwards when some particles are inactive).  Same bits
+    as agb_get_slice_results_all after a plain step, for host hand-overs (late-upload path) and after the remembered state changes."""
+    rng = np.random.default_rng(9)
+    p = pkg.ics.disk_galaxy(70000, seed=91)
+    n = len(p["x"])
+    if active_frac < 1.0:
+        p["next_time"] = np.where(rng.random(n) < active_frac, 0.0, 1e13)
+    mh = pkg.ics.gas_mass_in_h(p, 48)
+    names = ("ax", "ay", "az", "dUdt", "h", "rho", "P", "T", "visualDensity")
+    ref = pkg.Context(0, 8)
+    want, _ = pkg.run_step(dict(p), 0.5, 1e18, mh, 0.0, context=ref)
+    ctx = pkg.Context(0, 8)
+    try:
+        for part, nparts in ((0, 1), (1, 3), (2, 3), (1, 3)):
+            ref.set_particles(dict(p)); R = ref.build_tree(); ref.visual_density(R / 100000); ref.gas_density(mh); ref.forces(0.0, 1e18, 0.5, part, nparts)
+            exp = ref.slice_results(part, nparts, names=names)
+            cnt = len(exp["index"])
+            out = {k: np.full(n, np.nan) for k in names}
+            out["index"] = np.full(n, 0xffffffff, np.uint32)
+            ctx.bind_slice_results(part, nparts, out)
+            for rep in range(3):                                # call by call, then fused (late-upload path), then fused again
+                for k in names:
+                    out[k].fill(np.nan)
+                ctx.set_particles(dict(p))
+                ctx.force_path(want["R"] / 100000, mh, 0.0, 1e18, 0.5, part, nparts)
+                assert np.array_equal(out["index"][:cnt], exp["index"]), (part, nparts, rep)
+                for k in names:
+                    assert np.array_equal(out[k][:cnt], exp[k]), (k, part, nparts, rep)
+            ctx.bind_slice_results(0, 1, None)
+    finally:
+        ctx.close(); ref.close()
