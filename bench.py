@@ -486,7 +486,10 @@ def run_gpu_arm(args, pkg):
                 res_step()
             torch.cuda.synchronize()
             t0 = time.perf_counter()
-            nres = min(20, max(3, args.steps // 2))
+            # 2 + 3 steps only: with the shipped fixed step (1e13 s) the gas of C3 / C4 starts to blow up after ~5 steps (a few particles
+            # are ejected at >> c, the root cube grows by 2^20 within a few steps); the path follows that (three-word keys, FP64
+            # pair arithmetic outside the FP32 law's range) but those steps are not the workload this line describes
+            nres = 3
             for _ in range(nres):
                 res_step()
             torch.cuda.synchronize()
