@@ -346,6 +346,18 @@ int agb_launch_visual(AgbDev& d, AgbScalars* s, double radius, cudaStream_t st)
     return 1;
 }
 
+// tree positions of the gas particles, compact and in tree order, in d.nodecnt; their number in s->n_gas_total (device)
+int agb_launch_gas_list(AgbDev& d, AgbScalars* s, cudaStream_t st)
+{
+    const int nb = nblk(d.n, TPB);
+    k_gas_reset<<<1, 1, 0, st>>>(s);
+    k_gas_flags<<<nb, TPB, 0, st>>>(d, d.nodecnt);
+    int launches = agb_launch_scan_i32(d.nodecnt, d.gasrank, d.n, d.scanblk, &s->n_gas_total, st);
+    cudaMemcpyAsync(d.gasrank + d.n, &s->n_gas_total, sizeof(int32_t), cudaMemcpyDeviceToDevice, st);
+    k_gas_compact<<<nb, TPB, 0, st>>>(d, d.perm[d.cur], d.perm[d.cur ^ 1], d.rec, d.nodecnt, s);
+    return launches + 3;
+}
+
 int agb_launch_gas_density(AgbDev& d, AgbScalars* s, double massInH, cudaStream_t st, bool late_pt)
 {
     const int nb = nblk(d.n, TPB);

@@ -354,10 +354,13 @@ __device__ double density_at(const AgbDev& d, const AgbScalars* s, double R, dou
 }
 
 // h_i from (4 pi / 3) (2 h)^3 rho(h) = massInH (monotone in h): bracket by doubling / halving, then bisection to 1e-10 relative
-__global__ void __launch_bounds__(128) k_ext_density(AgbDev d, const AgbScalars* __restrict__ s, double massInH)
+// one thread per GAS particle, taken from the compact tree-ordered list: the lanes of a warp search neighbouring regions
+// (one thread per particle of any type left 2 of 32 lanes busy on a disk galaxy)
+__global__ void __launch_bounds__(128) k_ext_density(AgbDev d, const AgbScalars* __restrict__ s, const int32_t* __restrict__ gas_list, double massInH)
 {
-    const int64_t i = (int64_t)blockIdx.x * 128 + threadIdx.x;
-    if (i >= d.n || s->node_overflow || d.s_type[i] != 2) return;
+    const int64_t r = (int64_t)blockIdx.x * 128 + threadIdx.x;
+    if (r >= s->n_gas_total || s->node_overflow) return;
+    const int64_t i = gas_list[r];
     const uint32_t p = d.perm[d.cur][i];
     if (i >= s->n_in_tree) { d.s_h[i] = 0.0; d.h[p] = 0.0; return; }       // outside the root cube: no neighbours, no SPH (like the reference's outliers)
     const double R = __longlong_as_double((long long)s->Rbits), invR = 1.0 / R;
@@ -451,8 +454,9 @@ static inline int nblk(int64_t n, int per) { return (int)((n + per - 1) / per); 
 
 int agb_launch_extended_density(AgbDev& d, AgbScalars* s, double massInH, cudaStream_t st)
 {
-    k_ext_density<<<nblk(d.n, 128), 128, 0, st>>>(d, s, massInH);
-    return 1;
+    int launches = agb_launch_gas_list(d, s, st);
+    k_ext_density<<<nblk(d.n, 128), 128, 0, st>>>(d, s, d.nodecnt, massInH);     // (grid sized for "every particle is gas"; surplus blocks return at once)
+    return launches + 1;
 }
 
 int agb_launch_extended_forces(AgbDev& d, AgbScalars* s, double globalTime, double e0, double theta, int part, int nparts, bool any_gas, bool use_quad, int sm_count, cudaStream_t st, cudaEvent_t* ev)

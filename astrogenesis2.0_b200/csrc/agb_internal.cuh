@@ -148,6 +148,7 @@ int agb_launch_walk(AgbDev& d, AgbScalars* s, double globalTime, double e0, doub
 // the step's force targets (globalTime == nextIntegrationTime) in tree order, compacted; resets the walk's counters
 int agb_launch_active_list(AgbDev& d, AgbScalars* s, double globalTime, int sm_count, cudaStream_t st);
 // extended-accuracy mode (agb_extended.cu): per-particle smoothing lengths and densities; quadrupole walk + neighbour-loop SPH forces
+int agb_launch_gas_list(AgbDev& d, AgbScalars* s, cudaStream_t st);   // tree positions of the gas particles, compact, in d.nodecnt; count in s->n_gas_total
 int agb_launch_extended_density(AgbDev& d, AgbScalars* s, double massInH, cudaStream_t st);
 int agb_launch_extended_forces(AgbDev& d, AgbScalars* s, double globalTime, double e0, double theta, int part, int nparts, bool any_gas, bool use_quad, int sm_count, cudaStream_t st, cudaEvent_t* ev);
 int agb_launch_dump_tree(AgbDev& d, AgbScalars* s, int32_t* leafdepth, uint64_t* khi, uint64_t* klo, cudaStream_t st);

@@ -3,8 +3,8 @@
 cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
 timeout 600 python -m pytest tests/test_gpu_extended.py -m gpu -q > gpurun_out/r2s_pytest.log 2>&1; echo "pytest rc $?" >> gpurun_out/r2s_pytest.log
-timeout 600 python bench.py --extended --workload plummer1m --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/r2s_bench_c1_ext.json 2> gpurun_out/r2s_bench_c1_ext.err
-timeout 900 python bench.py --extended --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/r2s_bench_c3_ext.json 2> gpurun_out/r2s_bench_c3_ext.err
+
+timeout 900 python bench.py --extended --steps 3 --warmup 2 --no-cpu-baseline > gpurun_out/r2s_bench_c3_ext.json 2> gpurun_out/r2s_bench_c3_ext.err
 
 tail -8 gpurun_out/r2s_pytest.log
 python - <<'P'
