@@ -763,10 +763,6 @@ __device__ __forceinline__ ChildLinks load_links(const int32_t* child, int k)
     L.a = reinterpret_cast<const int4*>(child)[2 * (size_t)k]; L.b = reinterpret_cast<const int4*>(child)[2 * (size_t)k + 1];
     return L;
 }
-__device__ __forceinline__ int count_node_children(const ChildLinks& L, int N)
-{
-    return (L.a.x >= N) + (L.a.y >= N) + (L.a.z >= N) + (L.a.w >= N) + (L.b.x >= N) + (L.b.y >= N) + (L.b.z >= N) + (L.b.w >= N);
-}
 
 // MODE 0: everything; MODE 1: mass moments and gasMass (velocities not there yet: mVel sums stay 0); MODE 2: the mVel sums alone,
 // with the same operations in the same order as MODE 0 (bit-identical).

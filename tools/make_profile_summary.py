@@ -40,7 +40,7 @@ for rep in reps:
             for k, v in sorted(st.items(), key=lambda x: -x[1])[:10]:
                 f.write("%-40s %5.1f%%\n" % (k.replace("smsp__pcsamp_warps_issue_stalled_", ""), 100 * v / tot))
             f.write("\n# hottest CUDA source lines\n")
-            fn = kname.split("(")[0].replace("void ", "").split("<")[0].split("::")[-1]
+            fn = kname.split("(")[0].replace("void ", "").replace("<unnamed>::", "").split("<")[0].split("::")[-1]
             f.write(subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_lines.py"), rep, "30", fn], stdout=subprocess.PIPE, text=True).stdout)
         def num(k):
             u, v = d[k]; v = float(v.replace(",", ""))
