@@ -22,7 +22,8 @@ struct agb_ctx {
     cudaEvent_t ev_in = nullptr;                      // uploads on st_copy complete
     cudaEvent_t ev_next = nullptr;                    // ... their first group (next_time and the carried acc / dUdt / h / rho): all the build, the densities and the gravity walk read
     cudaEvent_t ev_sync = nullptr;                    // compute stream reached the point of a new hand-over (orders st_copy after it)
-    cudaEvent_t ev_pos = nullptr;                     // x, y, z, mass, type are on the device (st): the other uploads start after them (they would share the link)
+    cudaEvent_t ev_pos = nullptr;                     // type, x, y, z are on the device (st): the other uploads start after them (they would share the link)
+    cudaEvent_t ev_mass = nullptr; bool mass_late = false;   // host hand-over: the masses follow on the copy stream (needed from the gather on)
     bool in_pending = false, next_pending = false;
     cudaEvent_t xev[3] = {};                          // agb_set_particles_staged: the caller's "group is complete" events (positions+mass+type, next_time, the rest)
     cudaEvent_t evw[5] = {};                          // walk timing: before k_far, before k_walk, after k_walk, after k_sph, before k_sph
@@ -227,7 +228,7 @@ int put_array(agb_ctx* c, double* dst, const double* src, int64_t n, int memspac
 int own_input(agb_ctx* c, const double*& slot, int which, const double* src, int64_t n)
 {
     if (!src) { slot = nullptr; return AGB_OK; }
-    CK(cudaMemcpyAsync(c->in_d[which], src, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, (which < 3 || which == 6) ? c->st : c->st_copy));
+    CK(cudaMemcpyAsync(c->in_d[which], src, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, which < 3 ? c->st : c->st_copy));
     slot = c->in_d[which];
     return AGB_OK;
 }
@@ -286,6 +287,7 @@ static void destroy_handles(agb_ctx* c)
     if (c->ev_sync) cudaEventDestroy(c->ev_sync);
     if (c->ev_next) cudaEventDestroy(c->ev_next);
     if (c->ev_pos) cudaEventDestroy(c->ev_pos);
+    if (c->ev_mass) cudaEventDestroy(c->ev_mass);
     for (auto& e : c->evw) if (e) cudaEventDestroy(e);
     for (auto& e : c->ev) if (e) cudaEventDestroy(e);
     for (auto& e : c->evk) if (e) cudaEventDestroy(e);
@@ -320,7 +322,7 @@ int agb_create(agb_ctx** out, int device, int compat_cores)
     if (cudaStreamCreateWithFlags(&c->st_copy, cudaStreamNonBlocking) != cudaSuccess) return fail(AGB_ERR_NO_DEVICE);
     if (cudaEventCreateWithFlags(&c->ev_in, cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&c->ev_out, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&c->ev_sync, cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&c->ev_next, cudaEventDisableTiming) != cudaSuccess ||
-        cudaEventCreateWithFlags(&c->ev_pos, cudaEventDisableTiming) != cudaSuccess) return fail(AGB_ERR_NO_DEVICE);
+        cudaEventCreateWithFlags(&c->ev_pos, cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&c->ev_mass, cudaEventDisableTiming) != cudaSuccess) return fail(AGB_ERR_NO_DEVICE);
     for (auto& e : c->evw) if (cudaEventCreate(&e) != cudaSuccess) return fail(AGB_ERR_NO_DEVICE);
     for (auto& e : c->ev) if (cudaEventCreate(&e) != cudaSuccess) return fail(AGB_ERR_NO_DEVICE);
     for (auto& e : c->evk) if (cudaEventCreate(&e) != cudaSuccess) return fail(AGB_ERR_NO_DEVICE);
@@ -370,6 +372,7 @@ int agb_set_particles(agb_ctx* c, const agb_particles* p, int memspace)
     AgbDev& d = c->d;
     d.n = n;
     for (auto& e : c->xev) e = nullptr;
+    c->mass_late = false;
     // Everything already queued on the compute stream (densities, walk, integrator kernels of the previous step) reads or
     // writes the buffers the copy stream is about to overwrite: order the copy stream after it.
     CK(cudaEventRecord(c->ev_sync, c->st));
@@ -380,13 +383,15 @@ int agb_set_particles(agb_ctx* c, const agb_particles* p, int memspace)
         d.type = p->type;
         c->bound = true;
     } else {
-        if ((rc = own_input(c, d.x, 0, p->x, n)) || (rc = own_input(c, d.y, 1, p->y, n)) || (rc = own_input(c, d.z, 2, p->z, n)) ||
-            (rc = own_input(c, d.mass, 6, p->mass, n))) return rc;
         CK(cudaMemcpyAsync(c->in_type, p->type, (size_t)n, cudaMemcpyHostToDevice, c->st));   // needed by the key pass
+        if ((rc = own_input(c, d.x, 0, p->x, n)) || (rc = own_input(c, d.y, 1, p->y, n)) || (rc = own_input(c, d.z, 2, p->z, n))) return rc;
         // the build starts as soon as these have landed; everything else follows on the copy stream, in the order the path
         // needs it, and only AFTER them (two concurrent host-to-device streams would share the link and delay the positions)
         CK(cudaEventRecord(c->ev_pos, c->st));
         CK(cudaStreamWaitEvent(c->st_copy, c->ev_pos, 0));
+        if ((rc = own_input(c, d.mass, 6, p->mass, n))) return rc;             // the extent, key and sort passes run without the masses
+        CK(cudaEventRecord(c->ev_mass, c->st_copy));
+        c->mass_late = true;
         if ((rc = own_input(c, d.next, 8, p->next_time, n))) return rc;
         d.type = c->in_type;
         c->bound = false;
@@ -491,11 +496,12 @@ static void launch_build(agb_ctx* c, bool late_gas = false)
 {
     AgbDev& d = c->d;
     cudaEventRecord(c->evk[4], c->st);
-    c->launches += agb_launch_extent(d, c->s, c->st);
+    c->launches += agb_launch_extent(d, c->s, c->st, c->mass_late);
     c->launches += agb_launch_keygen(d, c->s, c->st);
     cudaEventRecord(c->evk[5], c->st);
     c->launches += agb_launch_sort(d, c->s, c->st);
     cudaEventRecord(c->evk[6], c->st);
+    if (c->mass_late) { cudaStreamWaitEvent(c->st, c->ev_mass, 0); c->launches += agb_launch_fill_mass(d, c->st); c->mass_late = false; }
     if (late_gas) { if (c->next_pending) { cudaStreamWaitEvent(c->st, c->ev_next, 0); if (c->xev[1]) cudaStreamWaitEvent(c->st, c->xev[1], 0); c->next_pending = false; } }
     else if (c->in_pending) { join_uploads(c); }
     c->launches += agb_launch_links(d, c->s, c->st, &c->evk[7], late_gas);
@@ -1150,8 +1156,10 @@ int agb_ctx_copy_particles_from(agb_ctx* c, agb_ctx* src)
     };
     // group 0: positions, masses, types (the build starts on them)
     CK(cudaStreamWaitEvent(c->st, src->ev_pos, 0));
-    CK(input(d.x, 0, sd.x, c->st)); CK(input(d.y, 1, sd.y, c->st)); CK(input(d.z, 2, sd.z, c->st)); CK(input(d.mass, 6, sd.mass, c->st));
+    CK(input(d.x, 0, sd.x, c->st)); CK(input(d.y, 1, sd.y, c->st)); CK(input(d.z, 2, sd.z, c->st));
     CK(peer(c->in_type, src->in_type, (size_t)n, c->st));
+    CK(cudaStreamWaitEvent(c->st, src->ev_mass, 0));           // the source receives its masses right behind the positions
+    CK(input(d.mass, 6, sd.mass, c->st));
     d.type = c->in_type; c->bound = false;
     CK(cudaEventRecord(c->ev_pos, c->st));
     // group 1: next_time and the carried acc / dUdt / h / rho

@@ -58,7 +58,7 @@ __global__ void __launch_bounds__(TPB) k_dist_partial(const double* __restrict__
     for (int64_t i = (int64_t)blockIdx.x * TPB + threadIdx.x; i < n; i += (int64_t)gridDim.x * TPB) {
         double px = x[i], py = y[i], pz = z[i];
         double d = length3(px, py, pz);
-        rec[i] = make_double4(px, py, pz, mass[i]);    // (position, mass) packed once, coalesced: the gather reads one 32-byte sector per particle
+        rec[i] = make_double4(px, py, pz, mass ? mass[i] : 0.0);    // (position, mass) packed once, coalesced: the gather reads one 32-byte sector per particle (mass == nullptr: k_fill_mass follows)
         a += d;
         b += __dmul_rn(d, d);
     }
@@ -108,6 +108,13 @@ __global__ void __launch_bounds__(TPB) k_extent_max(const double4* __restrict__ 
         for (int i = 1; i < TPB / 32; i++) m = fmax(m, sh[i]);
         atomicMax(&s->Rbits, (unsigned long long)__double_as_longlong(m));   // d >= 0: bit order == value order
     }
+}
+
+// masses that arrived after the positions (host hand-over: the extent, key and sort passes do not need them)
+__global__ void __launch_bounds__(TPB) k_fill_mass(const double* __restrict__ mass, int64_t n, double4* __restrict__ rec)
+{
+    const int64_t i = (int64_t)blockIdx.x * TPB + threadIdx.x;
+    if (i < n) reinterpret_cast<double*>(rec + i)[3] = mass[i];
 }
 
 // ------------------------------------------------------------------ keys
@@ -983,10 +990,16 @@ __global__ void __launch_bounds__(TPB) k_dump_tree(AgbDev d, const uint64_t* __r
 // ====================================================================== launchers
 static inline int nblk(int64_t n, int per) { return (int)((n + per - 1) / per); }
 
-int agb_launch_extent(const AgbDev& d, AgbScalars* s, cudaStream_t st)
+int agb_launch_fill_mass(const AgbDev& d, cudaStream_t st)
+{
+    k_fill_mass<<<nblk(d.n, TPB), TPB, 0, st>>>(d.mass, d.n, d.rec);
+    return 1;
+}
+
+int agb_launch_extent(const AgbDev& d, AgbScalars* s, cudaStream_t st, bool mass_late)
 {
     int nb = (int)std::min<int64_t>(1024, std::max<int64_t>(1, nblk(d.n, TPB)));
-    k_dist_partial<<<nb, TPB, 0, st>>>(d.x, d.y, d.z, d.mass, d.n, d.rec, s);
+    k_dist_partial<<<nb, TPB, 0, st>>>(d.x, d.y, d.z, mass_late ? nullptr : d.mass, d.n, d.rec, s);
     k_extent_finish<<<1, 32, 0, st>>>(s, nb, d.n);
     k_extent_max<<<nb, TPB, 0, st>>>(d.rec, d.n, s);
     return 3;

@@ -133,7 +133,8 @@ int agb_launch_int_first(AgbDev& d, const AgbInt& I, double gt, cudaStream_t st)
 int agb_launch_int_second(AgbDev& d, const AgbInt& I, double gt, cudaStream_t st);
 
 // ---- host-callable launchers (each returns the number of kernels it launched) ----
-int agb_launch_extent(const AgbDev& d, AgbScalars* s, cudaStream_t st);
+int agb_launch_extent(const AgbDev& d, AgbScalars* s, cudaStream_t st, bool mass_late = false);   // mass_late: the masses are still on their way (agb_launch_fill_mass before the gather)
+int agb_launch_fill_mass(const AgbDev& d, cudaStream_t st);
 int agb_launch_keygen(AgbDev& d, AgbScalars* s, cudaStream_t st);
 int agb_launch_sort(AgbDev& d, AgbScalars* s, cudaStream_t st);
 int agb_launch_links(AgbDev& d, AgbScalars* s, cudaStream_t st, cudaEvent_t* ev = nullptr, bool late_gas = false);   // ev[0] after the gather, ev[1] after the links, before the upward pass
