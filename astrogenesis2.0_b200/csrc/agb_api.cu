@@ -40,6 +40,7 @@ struct agb_ctx {
     bool mixed = true;                  // AGB_OPT_PRECISION
     bool walked_mixed = false;          // the last walk used the FP32 pair law (mixed_in_range)
     bool ext_quad = true;               // ... with the quadrupole term (AGB_OPT_EXTENDED = 2: monopole only, for validation)
+    int64_t piece_targets = 2000000;    // AGB_OPT_SLICE_PIECE: bound slice results are pipelined in up to 4 pieces of at least this many targets
     bool extended = false;              // AGB_OPT_EXTENDED: quadrupoles + spline softening + per-particle-h SPH (agb_extended.cu)
     bool opt_cooling = false; unsigned long long opt_sf_seed = 0;   // AGB_OPT_COOLING, AGB_OPT_STAR_FORMATION
     double* sfr = nullptr;              // Particle::sfr (device-resident loop)
@@ -56,7 +57,7 @@ struct agb_ctx {
     agb_results bres = {}; bool bres_on = false; int bres_space = AGB_MEM_HOST; bool bres_sent[9] = {};
     cudaEvent_t ev_out = nullptr;
     // agb_bind_slice_results: host destinations of one target slice's compact results, delivered by agb_force_path itself
-    bool bs_on = false, bs_early = false, bs_late = false; int bs_part = 0, bs_nparts = 1; uint32_t* bs_index = nullptr; agb_results bs_res = {};
+    bool bs_on = false, bs_early = false, bs_late = false, bs_piped = false; int bs_part = 0, bs_nparts = 1; uint32_t* bs_index = nullptr; agb_results bs_res = {};
     double* bs_buf = nullptr; uint32_t* bs_idx = nullptr; int64_t bs_cap = 0;
 };
 
@@ -353,6 +354,7 @@ int agb_set_option(agb_ctx* c, int option, int64_t value)
     if (option == AGB_OPT_TARGET_COUNTERS) { c->target_counters = value != 0; return AGB_OK; }
     if (option == AGB_OPT_PRECISION) { if (value != 0 && value != 1) return AGB_ERR_INVALID; c->mixed = value == 1; return AGB_OK; }
     if (option == AGB_OPT_COOLING) { c->opt_cooling = value != 0; return AGB_OK; }
+    if (option == AGB_OPT_SLICE_PIECE) { if (value < 256) return AGB_ERR_INVALID; c->piece_targets = value; return AGB_OK; }
     if (option == AGB_OPT_EXTENDED) {
         if (value != 0 && c->d.ncap > 0 && !c->d.quad) { CK(cudaSetDevice(c->device)); CK(dalloc(c->d.quad, 6 * (size_t)c->d.ncap)); CK(dalloc(c->d.ext_bar, 1)); }
         c->extended = value != 0; c->ext_quad = value != 2;
@@ -657,19 +659,20 @@ int agb_forces(agb_ctx* c, double global_time, double e0, double theta) { return
 // fixes it at init, Simulation.cpp:126) and "the particle set holds gas" (which decides whether the density kernels and the
 // SPH variant of the walk run) is verified after the fact; if it changed, the step is simply redone call by call.
 // columns [first, last] (results table order: ax ay az dUdt h rho P T vis) of the bound slice: compact on `st`, copy out on `out`
-static int send_slice_columns(agb_ctx* c, int64_t a0, int64_t a1, int first, int last, bool with_index, cudaStream_t out)
+// `off` = position of target a0 inside the bound slice (pieces of a slice are sent as they finish)
+static int send_slice_columns(agb_ctx* c, int64_t a0, int64_t a1, int first, int last, bool with_index, cudaStream_t out, int64_t off = 0)
 {
     const int64_t cnt = a1 - a0;
     if (cnt <= 0) return AGB_OK;
     double* host[9] = {c->bs_res.ax, c->bs_res.ay, c->bs_res.az, c->bs_res.dUdt, c->bs_res.h, c->bs_res.rho, c->bs_res.P, c->bs_res.T, c->bs_res.visualDensity};
     double* dev[9];
     bool any = with_index && c->bs_index;
-    for (int k = 0; k < 9; k++) { dev[k] = (k >= first && k <= last && host[k]) ? c->bs_buf + (size_t)k * c->bs_cap : nullptr; any = any || dev[k]; }
+    for (int k = 0; k < 9; k++) { dev[k] = (k >= first && k <= last && host[k]) ? c->bs_buf + (size_t)k * c->bs_cap + off : nullptr; any = any || dev[k]; }
     if (!any) return AGB_OK;
-    c->launches += agb_launch_slice_results(c->d, a0, a1, true, (with_index && c->bs_index) ? c->bs_idx : nullptr, dev, c->st);
+    c->launches += agb_launch_slice_results(c->d, a0, a1, true, (with_index && c->bs_index) ? c->bs_idx + off : nullptr, dev, c->st);
     if (out != c->st) { CK(cudaEventRecord(c->ev_out, c->st)); CK(cudaStreamWaitEvent(out, c->ev_out, 0)); }
-    if (with_index && c->bs_index) CK(cudaMemcpyAsync(c->bs_index, c->bs_idx, (size_t)cnt * sizeof(uint32_t), cudaMemcpyDeviceToHost, out));
-    for (int k = 0; k < 9; k++) if (dev[k]) CK(cudaMemcpyAsync(host[k], dev[k], (size_t)cnt * sizeof(double), cudaMemcpyDeviceToHost, out));
+    if (with_index && c->bs_index) CK(cudaMemcpyAsync(c->bs_index + off, c->bs_idx + off, (size_t)cnt * sizeof(uint32_t), cudaMemcpyDeviceToHost, out));
+    for (int k = 0; k < 9; k++) if (dev[k]) CK(cudaMemcpyAsync(host[k] + off, dev[k], (size_t)cnt * sizeof(double), cudaMemcpyDeviceToHost, out));
     return AGB_OK;
 }
 
@@ -688,7 +691,7 @@ static int force_path_impl(agb_ctx* c, double visual_density_radius, double mass
 int agb_force_path(agb_ctx* c, double visual_density_radius, double mass_in_h, double global_time, double e0, double theta, int part, int nparts, double* root_radius)
 {
     if (!c || !c->have_particles || nparts < 1 || part < 0 || part >= nparts) return AGB_ERR_INVALID;
-    c->bs_early = false;
+    c->bs_early = false; c->bs_piped = false;
     int rc = force_path_impl(c, visual_density_radius, mass_in_h, global_time, e0, theta, part, nparts, root_radius);
     if (rc || !c->bs_on || part != c->bs_part || nparts != c->bs_nparts) return rc;
     // bound slice results: the density columns left during the walk when the step ran fused with every particle active (as the
@@ -697,8 +700,10 @@ int agb_force_path(agb_ctx* c, double visual_density_radius, double mass_in_h, d
     if (c->bs_early && c->hs.n_active == c->d.n) {
         int64_t a0 = 0, a1 = 0;
         agb_slice_bounds(c->d.n, part, nparts, &a0, &a1);
-        if ((rc = send_slice_columns(c, a0, a1, 0, 3, false, c->st))) return rc;
-        if (c->bs_late && (rc = send_slice_columns(c, a0, a1, 6, 7, false, c->st))) return rc;      // P, T exist only after the late part of the build
+        if (!c->bs_piped) {
+            if ((rc = send_slice_columns(c, a0, a1, 0, 3, false, c->st))) return rc;
+            if (c->bs_late && (rc = send_slice_columns(c, a0, a1, 6, 7, false, c->st))) return rc;      // P, T exist only after the late part of the build
+        }
         CK(cudaStreamSynchronize(c->st)); CK(cudaStreamSynchronize(c->st_copy));
         return AGB_OK;
     }
@@ -710,7 +715,7 @@ static int force_path_impl(agb_ctx* c, double visual_density_radius, double mass
 {
     auto stepwise = [&]() -> int {
         double R = 0.0;
-        c->bs_early = false;                                    // whatever left early came from an abandoned attempt
+        c->bs_early = false; c->bs_piped = false;               // whatever left early came from an abandoned attempt
         int rc = agb_build_tree(c, &R);
         if (rc) return rc;
         if (root_radius) *root_radius = R;
@@ -754,6 +759,30 @@ static int force_path_impl(agb_ctx* c, double visual_density_radius, double mass
         if ((rc = send_slice_columns(c, a0, a1, 8, 8, false, c->st_copy))) return rc;
         c->bs_early = true;
     }
+    const int64_t my_targets = d.n / nparts;
+    const int pieces = c->bs_early ? (int)std::min<int64_t>(4, std::max<int64_t>(1, my_targets / c->piece_targets)) : 1;
+    if (pieces > 1) {
+        // Bound slice results of a large slice: the slice is walked in `pieces` sub-slices (exact sub-ranges of it: same groups, same
+        // bits) and the acc / dU/dt of each piece leave on the copy stream while the next piece walks.
+        int64_t a0 = 0, a1 = 0;
+        agb_slice_bounds(d.n, part, nparts, &a0, &a1);
+        unsigned long long sums[7] = {0, 0, 0, 0, 0, 0, 0};
+        bool sent_all = true;
+        for (int k = 0; k < pieces; k++) {
+            rc = forces_impl(c, global_time, e0, theta, part * pieces + k, nparts * pieces, late_gas && k == 0);
+            if (rc) break;
+            unsigned long long* f[7] = {&c->hs.c_node, &c->hs.c_leaf, &c->hs.c_sph, &c->hs.c_visits, &c->hs.c_exact, &c->hs.c_spill, &c->hs.c_interactions};
+            for (int q = 0; q < 7; q++) sums[q] += *f[q];
+            if (c->hs.n_active != d.n || c->hs.node_overflow || c->hs.need_deep) { sent_all = false; continue; }
+            int64_t b0 = 0, b1 = 0;
+            agb_slice_bounds(d.n, part * pieces + k, nparts * pieces, &b0, &b1);
+            if ((rc = send_slice_columns(c, b0, b1, 0, 3, false, c->st_copy, b0 - a0))) return rc;
+            if (c->bs_late && (rc = send_slice_columns(c, b0, b1, 6, 7, false, c->st_copy, b0 - a0))) return rc;
+        }
+        unsigned long long* f[7] = {&c->hs.c_node, &c->hs.c_leaf, &c->hs.c_sph, &c->hs.c_visits, &c->hs.c_exact, &c->hs.c_spill, &c->hs.c_interactions};
+        for (int q = 0; q < 7; q++) *f[q] = sums[q];
+        c->bs_piped = sent_all && rc == AGB_OK;
+    } else
     rc = forces_impl(c, global_time, e0, theta, part, nparts, late_gas);     // ends with the step's only synchronisation
     float ms = 0; if (cudaEventElapsedTime(&ms, c->ev[8], c->ev[9]) == cudaSuccess) c->phase_ms[0] = ms;
     (void)cudaGetLastError();

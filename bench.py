@@ -410,7 +410,10 @@ def run_gpu_arm(args, pkg):
         pinned_out = {k: torch.empty(n, dtype=torch.float64).pin_memory() for k in out_cols}
 
         out_np = {k: v.numpy() for k, v in pinned_out.items()}
-        ctx.bind_results(out_np)          # density outputs leave while the walk runs; acc / dUdt follow in results_into
+        # caller-order delivery: density outputs leave while the walk runs; acc / dUdt follow in results_into. (Measured alternative on C3:
+        # the N>1 form — agb_bind_slice_results(0, 1), tree-order pieces behind the walk plus the index — 62.0 ms against 61.5 ms for this
+        # one, and it leaves the caller a permutation to do; profiles/README.md.)
+        ctx.bind_results(out_np)
 
         def e2e_step():
             ctx.set_particles(host)

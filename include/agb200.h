@@ -140,7 +140,8 @@ int agb_get_slice_results(agb_ctx* ctx, int part, int nparts, uint32_t* index, d
 int agb_get_slice_results_all(agb_ctx* ctx, int part, int nparts, uint32_t* index, const agb_results* r, int memspace);
 /* Registers HOST destinations (ideally pinned) for the compact results of slice (part, nparts): agb_force_path(.., part, nparts, ..)
  * then delivers them itself and returns when they have arrived — index and the density columns while the walk still runs (when
- * every particle is a force target, as in fixed-step runs), acc / dU/dt after it.  r = NULL unbinds. */
+ * every particle is a force target, as in fixed-step runs), acc / dU/dt after it, piece by piece for a large slice (the walk of
+ * piece k+1 hides the transfer of piece k; the counters then hold the sums over the pieces).  r = NULL unbinds. */
 int agb_bind_slice_results(agb_ctx* ctx, int part, int nparts, uint32_t* index, const agb_results* r);
 
 /* -------- device-resident driver loop (optional).  With particles handed over from HOST memory the
@@ -184,6 +185,9 @@ typedef enum {
                                        list per 32 targets, opening test (cell WIDTH) / distance < theta; SPH with a smoothing length per particle from (4 pi/3)(2h)^3 rho = massInH and
                                        neighbour loops for density, pressure, viscosity and dU/dt.  Same calls, FP64 throughout.  Default 0.
                                        (2 = the same without the quadrupole term: a validation aid.) */
+    AGB_OPT_SLICE_PIECE = 6,        /* tuning: with agb_bind_slice_results, a slice of at least 2 x this many targets is walked in up to 4 pieces
+                                       (exact sub-ranges: same bits) so that the acc / dU/dt of a piece leave while the next one walks.
+                                       Default 2 000 000. */
     AGB_OPT_PRECISION = 2           /* arithmetic of the pair forces: 0 = FP64 throughout (agrees with the reference to ~1e-14),
                                        1 = mixed (default): float-float displacements, FP32 law, FP64 accumulation; ~1e-7.
                                        The accepted (target, source) sets, SPH pair sets and densities are identical in both;

@@ -798,6 +798,7 @@ def test_bound_slice_results_are_delivered_by_the_fused_call(pkg, active_frac):
     ref = pkg.Context(0, 8)
     want, _ = pkg.run_step(dict(p), 0.5, 1e18, mh, 0.0, context=ref)
     ctx = pkg.Context(0, 8)
+    ctx.set_option(pkg.capi.AGB_OPT_SLICE_PIECE, 4096)         # small pieces: the pipelined delivery (up to 4 pieces per slice) is exercised
     try:
         for part, nparts in ((0, 1), (1, 3), (2, 3), (1, 3)):
             ref.set_particles(dict(p)); R = ref.build_tree(); ref.visual_density(R / 100000); ref.gas_density(mh); ref.forces(0.0, 1e18, 0.5, part, nparts)
