@@ -19,6 +19,7 @@ size_t agb_sort_scratch_words(int64_t cap);
 struct agb_ctx {
     int device = 0, sm_count = 148;
     cudaStream_t st = nullptr, st_copy = nullptr;   // compute stream; upload stream for everything but x, y, z
+    cudaStream_t st_zero = nullptr; cudaEvent_t ev_zero = nullptr;   // zero fills of the columns a hand-over leaves out (see agb_set_particles)
     cudaEvent_t ev_in = nullptr;                      // uploads on st_copy complete
     cudaEvent_t ev_next = nullptr;                    // ... their first group (next_time and the carried acc / dUdt / h / rho): all the build, the densities and the gravity walk read
     cudaEvent_t ev_sync = nullptr;                    // compute stream reached the point of a new hand-over (orders st_copy after it)
@@ -28,6 +29,7 @@ struct agb_ctx {
     cudaEvent_t xev[3] = {};                          // agb_set_particles_staged: the caller's "group is complete" events (positions+mass+type, next_time, the rest)
     cudaEvent_t evw[5] = {};                          // walk timing: before k_far, before k_walk, after k_walk, after k_sph, before k_sph
     cudaEvent_t ev[10] = {};
+    cudaEvent_t tl[7] = {}; bool timeline = false;     // AGB_TIMELINE=1 (diagnostic): one step's hand-over / compute / delivery times on stderr
     cudaEvent_t evk[10] = {};                         // kernel-level timing: walk [0..3] = before k_far, k_walk, k_sph, after; build [4..9] = start, keys, sort, gather, links, end
     double kernel_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // k_far k_walk k_sph | extent+keys sort gather lcp+scan+links upward+finalize
     bool gas_hint_valid = false, gas_hint = false;   // agb_force_path: "the particle set holds gas" as of the last completed step
@@ -218,7 +220,7 @@ int fetch_scalars(agb_ctx* c)
 // copy (or zero / constant fill) one caller array into an owned device array
 int put_array(agb_ctx* c, double* dst, const double* src, int64_t n, int memspace)
 {
-    if (!src) { CK(cudaMemsetAsync(dst, 0, (size_t)n * sizeof(double), c->st_copy)); return AGB_OK; }
+    if (!src) return AGB_OK;                            // zero-filled at the start of the hand-over (st_zero)
     CK(cudaMemcpyAsync(dst, src, (size_t)n * sizeof(double), memspace == AGB_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, c->st_copy));
     return AGB_OK;
 }
@@ -289,6 +291,8 @@ static void destroy_handles(agb_ctx* c)
     if (c->ev_next) cudaEventDestroy(c->ev_next);
     if (c->ev_pos) cudaEventDestroy(c->ev_pos);
     if (c->ev_mass) cudaEventDestroy(c->ev_mass);
+    if (c->ev_zero) cudaEventDestroy(c->ev_zero);
+    if (c->st_zero) cudaStreamDestroy(c->st_zero);
     for (auto& e : c->evw) if (e) cudaEventDestroy(e);
     for (auto& e : c->ev) if (e) cudaEventDestroy(e);
     for (auto& e : c->evk) if (e) cudaEventDestroy(e);
@@ -321,12 +325,15 @@ int agb_create(agb_ctx** out, int device, int compat_cores)
     auto fail = [&](int rc) { destroy_handles(c); delete c; (void)cudaGetLastError(); return rc; };
     if (cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking) != cudaSuccess) return fail(AGB_ERR_NO_DEVICE);
     if (cudaStreamCreateWithFlags(&c->st_copy, cudaStreamNonBlocking) != cudaSuccess) return fail(AGB_ERR_NO_DEVICE);
+    if (cudaStreamCreateWithFlags(&c->st_zero, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreateWithFlags(&c->ev_zero, cudaEventDisableTiming) != cudaSuccess) return fail(AGB_ERR_NO_DEVICE);
     if (cudaEventCreateWithFlags(&c->ev_in, cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&c->ev_out, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&c->ev_sync, cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&c->ev_next, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&c->ev_pos, cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&c->ev_mass, cudaEventDisableTiming) != cudaSuccess) return fail(AGB_ERR_NO_DEVICE);
     for (auto& e : c->evw) if (cudaEventCreate(&e) != cudaSuccess) return fail(AGB_ERR_NO_DEVICE);
     for (auto& e : c->ev) if (cudaEventCreate(&e) != cudaSuccess) return fail(AGB_ERR_NO_DEVICE);
     for (auto& e : c->evk) if (cudaEventCreate(&e) != cudaSuccess) return fail(AGB_ERR_NO_DEVICE);
+    c->timeline = getenv("AGB_TIMELINE") != nullptr;
+    if (c->timeline) for (auto& e : c->tl) if (cudaEventCreate(&e) != cudaSuccess) return fail(AGB_ERR_NO_DEVICE);
     if (cudaMalloc((void**)&c->s, sizeof(AgbScalars)) != cudaSuccess) return fail(AGB_ERR_NOMEM);
     cudaMemsetAsync(c->s, 0, sizeof(AgbScalars), c->st);
     memset(&c->hs, 0, sizeof(c->hs));
@@ -341,7 +348,7 @@ int agb_destroy(agb_ctx* c)
 {
     if (!c) return AGB_ERR_INVALID;
     cudaSetDevice(c->device);
-    cudaStreamSynchronize(c->st); cudaStreamSynchronize(c->st_copy);
+    cudaStreamSynchronize(c->st); cudaStreamSynchronize(c->st_copy); cudaStreamSynchronize(c->st_zero);
     free_pool(c);
     destroy_handles(c);
     delete c;
@@ -379,20 +386,38 @@ int agb_set_particles(agb_ctx* c, const agb_particles* p, int memspace)
     // writes the buffers the copy stream is about to overwrite: order the copy stream after it.
     CK(cudaEventRecord(c->ev_sync, c->st));
     CK(cudaStreamWaitEvent(c->st_copy, c->ev_sync, 0));
+    // Columns the caller leaves out (carried acc / dUdt / h / rho / P / T) and the visual density start at zero.  The fills are
+    // kernels: queued behind the uploads they would have to wait until the persistent walk frees an SM, and the result copies
+    // queued behind THEM on the copy stream with it (measured: 20 ms).  They run at once on a stream of their own, while the
+    // positions are on the link, after everything of the last step on both streams.
+    CK(cudaEventRecord(c->ev_zero, c->st_copy));
+    CK(cudaStreamWaitEvent(c->st_zero, c->ev_zero, 0));
+    {
+        double* col[8] = {d.ax, d.ay, d.az, d.dUdt, d.h, d.rho, d.P, d.T};
+        const double* given[8] = {p->ax, p->ay, p->az, p->dUdt, p->h, p->rho, p->P, p->T};
+        for (int k = 0; k < 8; k++) if (!given[k] && n > 0) CK(cudaMemsetAsync(col[k], 0, (size_t)n * sizeof(double), c->st_zero));
+        CK(cudaMemsetAsync(d.vis, 0, (size_t)std::max<int64_t>(n, 1) * sizeof(double), c->st_zero));
+    }
+    CK(cudaEventRecord(c->ev_zero, c->st_zero));
     if (memspace == AGB_MEM_DEVICE) {
+        CK(cudaStreamWaitEvent(c->st, c->ev_zero, 0)); CK(cudaStreamWaitEvent(c->st_copy, c->ev_zero, 0));
         // zero-copy: the caller's device arrays are read in place (they must stay valid until the next set_particles)
         d.x = p->x; d.y = p->y; d.z = p->z; d.vx = p->vx; d.vy = p->vy; d.vz = p->vz; d.mass = p->mass; d.U = p->U; d.next = p->next_time; d.mu = p->mu;
         d.type = p->type;
         c->bound = true;
     } else {
+        if (c->timeline) cudaEventRecord(c->tl[0], c->st);
         CK(cudaMemcpyAsync(c->in_type, p->type, (size_t)n, cudaMemcpyHostToDevice, c->st));   // needed by the key pass
         if ((rc = own_input(c, d.x, 0, p->x, n)) || (rc = own_input(c, d.y, 1, p->y, n)) || (rc = own_input(c, d.z, 2, p->z, n))) return rc;
         // the build starts as soon as these have landed; everything else follows on the copy stream, in the order the path
         // needs it, and only AFTER them (two concurrent host-to-device streams would share the link and delay the positions)
+        CK(cudaStreamWaitEvent(c->st, c->ev_zero, 0));      // long done; the copy stream follows through ev_pos
         CK(cudaEventRecord(c->ev_pos, c->st));
+        if (c->timeline) cudaEventRecord(c->tl[1], c->st);
         CK(cudaStreamWaitEvent(c->st_copy, c->ev_pos, 0));
         if ((rc = own_input(c, d.mass, 6, p->mass, n))) return rc;             // the extent, key and sort passes run without the masses
         CK(cudaEventRecord(c->ev_mass, c->st_copy));
+        if (c->timeline) cudaEventRecord(c->tl[2], c->st_copy);
         c->mass_late = true;
         if ((rc = own_input(c, d.next, 8, p->next_time, n))) return rc;
         d.type = c->in_type;
@@ -401,8 +426,8 @@ int agb_set_particles(agb_ctx* c, const agb_particles* p, int memspace)
     // first group: what the gather, the densities and the gravity walk read or write (active flags, carried acc / dUdt / h / rho)
     if ((rc = put_array(c, d.ax, p->ax, n, memspace)) || (rc = put_array(c, d.ay, p->ay, n, memspace)) || (rc = put_array(c, d.az, p->az, n, memspace)) ||
         (rc = put_array(c, d.dUdt, p->dUdt, n, memspace)) || (rc = put_array(c, d.h, p->h, n, memspace)) || (rc = put_array(c, d.rho, p->rho, n, memspace))) return rc;
-    CK(cudaMemsetAsync(d.vis, 0, (size_t)std::max<int64_t>(n, 1) * sizeof(double), c->st_copy));
     CK(cudaEventRecord(c->ev_next, c->st_copy));
+    if (c->timeline) cudaEventRecord(c->tl[3], c->st_copy);
     // second group: only the SPH pair pass (and P, T of the density groups) needs these
     if (memspace != AGB_MEM_DEVICE) {
         if ((rc = own_input(c, d.vx, 3, p->vx, n)) || (rc = own_input(c, d.vy, 4, p->vy, n)) || (rc = own_input(c, d.vz, 5, p->vz, n)) ||
@@ -410,6 +435,7 @@ int agb_set_particles(agb_ctx* c, const agb_particles* p, int memspace)
     }
     if ((rc = put_array(c, d.P, p->P, n, memspace)) || (rc = put_array(c, d.T, p->T, n, memspace))) return rc;
     CK(cudaEventRecord(c->ev_in, c->st_copy));
+    if (c->timeline) cudaEventRecord(c->tl[4], c->st_copy);
     c->in_pending = true; c->next_pending = true;
     // Host arrays are read asynchronously (pinned memory makes that a true overlap): like the reference, which reads
     // Simulation::particles during buildTree, they must stay untouched until agb_build_tree has returned.
@@ -504,9 +530,14 @@ static void launch_build(agb_ctx* c, bool late_gas = false)
     c->launches += agb_launch_sort(d, c->s, c->st);
     cudaEventRecord(c->evk[6], c->st);
     if (c->mass_late) { cudaStreamWaitEvent(c->st, c->ev_mass, 0); c->launches += agb_launch_fill_mass(d, c->st); c->mass_late = false; }
-    if (late_gas) { if (c->next_pending) { cudaStreamWaitEvent(c->st, c->ev_next, 0); if (c->xev[1]) cudaStreamWaitEvent(c->st, c->xev[1], 0); c->next_pending = false; } }
-    else if (c->in_pending) { join_uploads(c); }
+    if (!late_gas && c->in_pending) join_uploads(c);
     c->launches += agb_launch_links(d, c->s, c->st, &c->evk[7], late_gas);
+    if (late_gas) {
+        // next_time (and the carried columns the densities and the walk write into) arrive behind the masses: nothing of the
+        // build reads them, so the tree-order copy of next_time is made here, after the build, instead of stalling the gather
+        if (c->next_pending) { cudaStreamWaitEvent(c->st, c->ev_next, 0); if (c->xev[1]) cudaStreamWaitEvent(c->st, c->xev[1], 0); c->next_pending = false; }
+        c->launches += agb_launch_gather_next(d, c->s, c->st);
+    }
     cudaEventRecord(c->evk[9], c->st);
     c->build_timed = true;
 }
@@ -836,8 +867,17 @@ int agb_get_results(agb_ctx* c, const agb_results* r, int memspace)
         if (c->bres_on && c->bres_sent[i] && cp[i].dst == bp[i].dst && memspace == c->bres_space) { streamed = streamed || cp[i].dst; continue; }
         if (cp[i].dst && b) CK(cudaMemcpyAsync(cp[i].dst, cp[i].src, b, k, c->st));
     }
+    if (c->timeline) { cudaEventRecord(c->tl[5], c->st); cudaEventRecord(c->tl[6], c->st_copy); }
     CK(cudaStreamSynchronize(c->st));
     if (streamed) CK(cudaStreamSynchronize(c->st_copy));
+    if (c->timeline && !c->bound) {
+        CK(cudaStreamSynchronize(c->st_copy));
+        auto at = [&](cudaEvent_t e) { float ms = -1.f; if (cudaEventElapsedTime(&ms, c->tl[0], e) != cudaSuccess) { (void)cudaGetLastError(); ms = -1.f; } return ms; };
+        fprintf(stderr, "agb timeline [ms after the hand-over began]: positions %.2f  masses %.2f  first group %.2f  all uploads %.2f | build %.2f..%.2f  visual density ..%.2f  gas density %.2f..%.2f"
+                        "  walk %.2f (k_walk %.2f, k_sph %.2f) ..%.2f | results on the compute stream %.2f, on the copy stream %.2f\n",
+                at(c->tl[1]), at(c->tl[2]), at(c->tl[3]), at(c->tl[4]), at(c->ev[8]), at(c->ev[9]), at(c->ev[3]), at(c->ev[4]), at(c->ev[5]),
+                at(c->evw[0]), at(c->evw[1]), at(c->evw[4]), at(c->evw[3]), at(c->tl[5]), at(c->tl[6]));
+    }
     return AGB_OK;
 }
 

@@ -524,7 +524,7 @@ __global__ void __launch_bounds__(TPB) k_gather(AgbDev d, uint32_t* __restrict__
     const double m = r4.w;
     d.src_pm[i] = r4;
     d.s_type[i] = gas ? 2 : 1;                        // only "gas or not" matters on the path (Node.cpp:319,371,478,679,763)
-    d.s_next[i] = !d.next ? 0.0 : s->next_uniform ? d.next[0] : d.next[p];
+    if (!LATE) d.s_next[i] = !d.next ? 0.0 : s->next_uniform ? d.next[0] : d.next[p];
     if (gas) {
         d.src_flag[i] = m > 0.0 ? 1 : 0;
         s->any_gas = 1;
@@ -546,6 +546,13 @@ __global__ void __launch_bounds__(TPB) k_gather(AgbDev d, uint32_t* __restrict__
     d.leafparent[i] = -1;
     d.leafdepth[i] = -1;
     d.leafmark[i] = 0;
+}
+
+// next_time of a LATE gather (it arrives behind the masses; nothing of the build reads it)
+__global__ void __launch_bounds__(TPB) k_gather_next(AgbDev d, const uint32_t* __restrict__ perm, const AgbScalars* __restrict__ s)
+{
+    int64_t i = (int64_t)blockIdx.x * TPB + threadIdx.x;
+    if (i < d.n) d.s_next[i] = !d.next ? 0.0 : s->next_uniform ? d.next[0] : d.next[perm[i]];
 }
 
 // The rest of a LATE gather, after the gas densities: velocity, U, mu of the gas particles; P and T of the particles that
@@ -1085,7 +1092,7 @@ int agb_launch_links(AgbDev& d, AgbScalars* s, cudaStream_t st, cudaEvent_t* ev,
 {
     const int nb = nblk(d.n, TPB);
     const uint64_t *khi = d.khi[d.cur], *klo = d.klo[1], *kex = d.deep ? d.kex : nullptr;
-    if (d.next) k_next_uniform<<<std::min(nb, 2048), TPB, 0, st>>>(d.next, d.n, s);
+    if (d.next && !late_gas) k_next_uniform<<<std::min(nb, 2048), TPB, 0, st>>>(d.next, d.n, s);
     if (late_gas) k_gather<true><<<nb, TPB, 0, st>>>(d, d.perm[d.cur], s);
     else {
         k_pack_gas<<<nb, TPB, 0, st>>>(d);
@@ -1105,7 +1112,15 @@ int agb_launch_links(AgbDev& d, AgbScalars* s, cudaStream_t st, cudaEvent_t* ev,
     k_level_lists<<<nnb, TPB, 0, st>>>(d, s, d.lvl_list);
     if (late_gas) k_upward_levels<1><<<upward_blocks(nnb), TPB, 0, st>>>(d, s, d.lvl_list);
     else k_upward_levels<0><<<upward_blocks(nnb), TPB, 0, st>>>(d, s, d.lvl_list);
-    return (late_gas ? 10 : 11) + (d.next ? 1 : 0);
+    return (late_gas ? 10 : 11) + (d.next && !late_gas ? 1 : 0);
+}
+
+int agb_launch_gather_next(AgbDev& d, AgbScalars* s, cudaStream_t st)
+{
+    const int nb = nblk(d.n, TPB);
+    if (d.next) k_next_uniform<<<std::min(nb, 2048), TPB, 0, st>>>(d.next, d.n, s);
+    k_gather_next<<<nb, TPB, 0, st>>>(d, d.perm[d.cur], s);
+    return d.next ? 2 : 1;
 }
 
 // second half of a late_gas build, after the gas densities: gas velocities / U / mu into tree order, P and T of the density

@@ -139,6 +139,7 @@ int agb_launch_keygen(AgbDev& d, AgbScalars* s, cudaStream_t st);
 int agb_launch_sort(AgbDev& d, AgbScalars* s, cudaStream_t st);
 int agb_launch_links(AgbDev& d, AgbScalars* s, cudaStream_t st, cudaEvent_t* ev = nullptr, bool late_gas = false);   // ev[0] after the gather, ev[1] after the links, before the upward pass
 int agb_launch_late_gas(AgbDev& d, AgbScalars* s, cudaStream_t st);            // completes a late_gas build once velocities / U / mu have arrived (after the gas densities)
+int agb_launch_gather_next(AgbDev& d, AgbScalars* s, cudaStream_t st);          // tree-order next_time of a late_gas build (arrives behind the masses)
 int agb_launch_visual(AgbDev& d, AgbScalars* s, double radius, cudaStream_t st);
 int agb_launch_gas_density(AgbDev& d, AgbScalars* s, double massInH, cudaStream_t st, bool late_pt = false);   // late_pt: h and rho only (P, T follow in agb_launch_late_gas)
 // compact (index, acc, dUdt) of the active targets [a0, a1) in tree order (agb_get_slice_results)
