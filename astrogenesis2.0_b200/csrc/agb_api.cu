@@ -20,6 +20,7 @@ struct agb_ctx {
     int device = 0, sm_count = 148;
     cudaStream_t st = nullptr, st_copy = nullptr;   // compute stream; upload stream for everything but x, y, z
     cudaStream_t st_zero = nullptr; cudaEvent_t ev_zero = nullptr;   // zero fills of the columns a hand-over leaves out (see agb_set_particles)
+    bool zero_pending = false;                        // ... the compute stream has not been ordered behind them yet (device hand-over: they overlap extent, keys and sort)
     cudaEvent_t ev_in = nullptr;                      // uploads on st_copy complete
     cudaEvent_t ev_next = nullptr;                    // ... their first group (next_time and the carried acc / dUdt / h / rho): all the build, the densities and the gravity walk read
     cudaEvent_t ev_sync = nullptr;                    // compute stream reached the point of a new hand-over (orders st_copy after it)
@@ -399,8 +400,8 @@ int agb_set_particles(agb_ctx* c, const agb_particles* p, int memspace)
         CK(cudaMemsetAsync(d.vis, 0, (size_t)std::max<int64_t>(n, 1) * sizeof(double), c->st_zero));
     }
     CK(cudaEventRecord(c->ev_zero, c->st_zero));
+    c->zero_pending = true;                                   // device hand-over: joined before the first kernel that touches those columns
     if (memspace == AGB_MEM_DEVICE) {
-        CK(cudaStreamWaitEvent(c->st, c->ev_zero, 0)); CK(cudaStreamWaitEvent(c->st_copy, c->ev_zero, 0));
         // zero-copy: the caller's device arrays are read in place (they must stay valid until the next set_particles)
         d.x = p->x; d.y = p->y; d.z = p->z; d.vx = p->vx; d.vy = p->vy; d.vz = p->vz; d.mass = p->mass; d.U = p->U; d.next = p->next_time; d.mu = p->mu;
         d.type = p->type;
@@ -412,6 +413,7 @@ int agb_set_particles(agb_ctx* c, const agb_particles* p, int memspace)
         // the build starts as soon as these have landed; everything else follows on the copy stream, in the order the path
         // needs it, and only AFTER them (two concurrent host-to-device streams would share the link and delay the positions)
         CK(cudaStreamWaitEvent(c->st, c->ev_zero, 0));      // long done; the copy stream follows through ev_pos
+        c->zero_pending = false;
         CK(cudaEventRecord(c->ev_pos, c->st));
         if (c->timeline) cudaEventRecord(c->tl[1], c->st);
         CK(cudaStreamWaitEvent(c->st_copy, c->ev_pos, 0));
@@ -510,8 +512,14 @@ int agb_set_particles_aos(agb_ctx* c, void* const* parts, int64_t n, const agb_a
 
 // the kernels of Tree::buildTree on the context's stream (no synchronisation)
 // the compute stream waits for every group of the last hand-over (the library's own uploads and the caller's staged events)
+static void join_zero(agb_ctx* c)
+{
+    if (c->zero_pending) { cudaStreamWaitEvent(c->st, c->ev_zero, 0); c->zero_pending = false; }
+}
+
 static void join_uploads(agb_ctx* c)
 {
+    join_zero(c);
     if (!c->in_pending) return;
     cudaStreamWaitEvent(c->st, c->ev_in, 0);
     for (int k = 1; k < 3; k++) if (c->xev[k]) cudaStreamWaitEvent(c->st, c->xev[k], 0);
@@ -530,6 +538,7 @@ static void launch_build(agb_ctx* c, bool late_gas = false)
     c->launches += agb_launch_sort(d, c->s, c->st);
     cudaEventRecord(c->evk[6], c->st);
     if (c->mass_late) { cudaStreamWaitEvent(c->st, c->ev_mass, 0); c->launches += agb_launch_fill_mass(d, c->st); c->mass_late = false; }
+    join_zero(c);
     if (!late_gas && c->in_pending) join_uploads(c);
     c->launches += agb_launch_links(d, c->s, c->st, &c->evk[7], late_gas);
     if (late_gas) {

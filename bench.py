@@ -196,6 +196,29 @@ RESULT_COLS_GRAVITY = ("ax", "ay", "az", "visualDensity")
 RESULT_COLS_GAS = ("dUdt", "h", "rho", "P", "T")
 
 
+def bind_near_gpu(torch, local):
+    """Several ranks on one node: keep this process (and the pinned host buffers it is about to allocate, first touch) on the NUMA
+    node its GPU hangs off, so that N ranks do not push their host<->device traffic across the socket interconnect.  Best effort:
+    returns the node, or None when the topology is not visible (containers) or the node's CPUs are not allowed."""
+    try:
+        pr = torch.cuda.get_device_properties(local)
+        bdf = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bdf).read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        use = os.sched_getaffinity(0) & cpus
+        if not use:
+            return None
+        os.sched_setaffinity(0, use)
+        return node
+    except Exception:  # noqa: BLE001
+        return None
+
+
 def run_gpu_arm(args, pkg):
     import torch
     import torch.distributed as dist
@@ -206,6 +229,7 @@ def run_gpu_arm(args, pkg):
         raise SystemExit("bench.py needs a B200: there is no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa_node = bind_near_gpu(torch, local) if world > 1 and os.environ.get("AGB_BENCH_NO_AFFINITY") != "1" else None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     name = args.workload or DEFAULT_WORKLOAD
@@ -467,7 +491,7 @@ def run_gpu_arm(args, pkg):
         te = float(te[0])
         ctx.bind_slice_results(rank, world, None)
         e2e = {"value": n / te, "unit": "particles/s", "h2d_bytes_per_step": int(sum(v.numel() * v.element_size() for v in host.values()) * world),
-               "d2h_bytes_per_step": int(by[1]), "ms_per_step": te * 1e3,
+               "d2h_bytes_per_step": int(by[1]), "ms_per_step": te * 1e3, "host_numa_node_rank0": numa_node,
                "what": "per rank: H2D of its particle shard and NCCL all-gather in three groups (positions+mass+type | next_time | velocities, U, mu) overlapped with build, densities and walk of its target slice, D2H of that slice's (index, %s)" % ", ".join(out_cols)}
 
     # ---- device-resident simulation steps (integrator kernels + force path, nothing but the time crosses PCIe)
