@@ -773,7 +773,9 @@ static int force_path_impl(agb_ctx* c, double visual_density_radius, double mass
     // Host hand-over still uploading (set_particles is asynchronous): in mixed precision only the SPH pair pass needs the gas
     // velocities / U / mu, so the build, the densities and the gravity walk start on the first upload group and the rest of
     // the transfer hides behind them.
-    const bool late_gas = c->in_pending && (!c->bound || c->xev[2]) && !c->extended && mixed_in_range(c, e0) && c->gas_hint;
+    // (A staged hand-over whose next_time and last group share one event has no late group: the build then joins it before the
+    // gather, which hides its production behind extent, keys and sort without the extra kernels of the late path.)
+    const bool late_gas = c->in_pending && (!c->bound || (c->xev[2] && c->xev[2] != c->xev[1])) && !c->extended && mixed_in_range(c, e0) && c->gas_hint;
     CK(cudaEventRecord(c->ev[8], c->st));
     { Phase ph("build tree"); launch_build(c, late_gas); }
     CK(cudaEventRecord(c->ev[9], c->st));

@@ -286,18 +286,30 @@ def run_gpu_arm(args, pkg):
             e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
             e[0].record(torch.cuda.current_stream())
         ptrs = {k: full[k].data_ptr() for k in full}
-        # staged only end to end: with the shards already on the device the late part of the build (1.4 ms of extra kernels on C3) costs
-        # more than the ~1 ms of exchange it hides (measured at 2 GPUs: 25.1 vs 24.6 ms); with the upload in the loop it hides 10+ ms
-        if staged and upload is not None:
+        if staged and upload is None:
+            # shards already on the device — two groups: what extent, keys and sort read, then everything else behind one event (no
+            # late group: the build joins it before the gather), so the exchange of the second group hides behind the first 2 ms of
+            # the build.  (Three groups with the late part of the build cost 1.4 ms of extra kernels on C3, more than the exchange
+            # they hide: 25.1 vs 24.6 ms at 2 GPUs; with the upload in the loop, below, they hide 10+ ms.)
+            del keep_events[:]
+            for grp in (groups[0], groups[1] + groups[2]):
+                if grp:
+                    packed.gather_fields(grp)
+                ev_ = torch.cuda.Event()
+                ev_.record(torch.cuda.current_stream())
+                keep_events.append(ev_)
+            if breakdown:
+                e[1].record(torch.cuda.current_stream())
+            ctx.set_particles_device(ptrs, n, events=[keep_events[0].cuda_event, keep_events[1].cuda_event, keep_events[1].cuda_event])
+        elif staged:
             evs = []
             del keep_events[:]
             for grp in groups:
                 if not grp:
                     evs.append(0)
                     continue
-                if upload is not None:
-                    for k in grp:
-                        shard[k].copy_(upload[k], non_blocking=True)
+                for k in grp:
+                    shard[k].copy_(upload[k], non_blocking=True)
                 packed.gather_fields(grp)
                 ev_ = torch.cuda.Event()
                 ev_.record(torch.cuda.current_stream())
@@ -602,7 +614,7 @@ def run_gpu_arm(args, pkg):
         "dtype": "f64" if args.extended else "f64 decisions and accumulation, f32 pair forces (mixed mode)", "data": "synthetic",
         "config": cfg,
         "run": {"precision": "extended-accuracy mode (AGB_OPT_EXTENDED): quadrupoles, spline softening, width/d < theta per 32-target group, per-particle-h SPH; FP64; parity unpinned by the reference" if args.extended else "mixed", "l2": "256 MiB buffer written between timed steps (L2 flush); working set %.0f MB" % (n * 330 / 1e6),
-                "parallelism": ("replicated tree, tree-ordered target slices, 1 coalesced group of in-place NCCL all-gathers per step (e2e: 3 groups, overlapped with the build through agb_set_particles_staged)" if staged else
+                "parallelism": ("replicated tree, tree-ordered target slices, in-place NCCL all-gathers in 2 coalesced groups per step, the second behind extent / keys / sort (e2e: 3 groups, overlapped with build, densities and gravity walk) through agb_set_particles_staged" if staged else
                                 "replicated tree, tree-ordered target slices, packed NCCL all-gather per step") if world > 1 else "single GPU",
                 "result_columns": list(out_cols)},
         "e2e": e2e, "fp64": fp64, "resident_sim_step": resident, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,

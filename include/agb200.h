@@ -112,7 +112,8 @@ int agb_set_particles_aos(agb_ctx* ctx, void* const* particles, int64_t n, const
 /* Hand-over of arrays that are still being produced on the caller's own streams (the all-gather of a multi-GPU driver, a copy,
  * its integrator kernels): each event (cudaEvent_t, NULL = ready now) must have been recorded behind the producer of its group —
  * x y z mass type | next_time | vx vy vz U mu and the carried state — and the path reads a group only after its event.  With
- * agb_force_path the build, the densities and the gravity walk overlap the production of the last group. */
+ * agb_force_path the build, the densities and the gravity walk overlap the production of the last group; when ready_next_time and
+ * ready_all are the same event there is no late group and only extent, keys and sort run ahead of it (no extra kernels). */
 int agb_set_particles_staged(agb_ctx* ctx, const agb_particles* p, int memspace, void* ready_positions, void* ready_next_time, void* ready_all);
 
 /* -------- the four calls of the reference's Tree (same order, same meaning) */
