@@ -739,10 +739,12 @@ def test_call_sequences_keep_their_state_straight(pkg):
         ctx.close()
 
 
-def test_staged_device_hand_over_waits_for_its_events(pkg):
+@pytest.mark.parametrize("two_groups", [False, True])
+def test_staged_device_hand_over_waits_for_its_events(pkg, two_groups):
     """agb_set_particles_staged: device arrays that are still being filled on another stream when they are handed over (what the
     multi-GPU bench does with its all-gathers).  The arrays hold NaN until a delayed copy lands; every group is read only after
-    its event, in the call-by-call step and in the fused step that overlaps the last group with the build and the walk."""
+    its event, in the call-by-call step and in the fused step that overlaps the last group with the build and the walk.
+    two_groups: next_time and the last group share one event (no late group: only extent, keys and sort run ahead of it)."""
     import torch
     p = pkg.ics.disk_galaxy(60000, seed=81)
     n = len(p["x"])
@@ -757,6 +759,8 @@ def test_staged_device_hand_over_waits_for_its_events(pkg):
     src["type"] = torch.from_numpy(np.ascontiguousarray(p["type"])).to(dev)
     stage = {k: torch.empty_like(v) for k, v in src.items()}
     groups = (("x", "y", "z", "mass", "type"), ("next_time",), ("vx", "vy", "vz", "U", "mu"))
+    if two_groups:
+        groups = (groups[0], groups[1] + groups[2])
     side = torch.cuda.Stream(device=dev)
     ctx = pkg.Context(0, 8)
     try:
@@ -773,6 +777,8 @@ def test_staged_device_hand_over_waits_for_its_events(pkg):
                     e = torch.cuda.Event()
                     e.record(side)
                     evs.append(e)
+            if two_groups:
+                evs.append(evs[1])
             ctx.set_particles_device({k: t.data_ptr() for k, t in stage.items()}, n, events=[e.cuda_event for e in evs])
             R = ctx.force_path(want["R"] / 100000, mh, 0.0, 1e18, 0.5)
             got = ctx.results()
