@@ -744,7 +744,14 @@ int agb_force_path(agb_ctx* c, double visual_density_radius, double mass_in_h, d
             if ((rc = send_slice_columns(c, a0, a1, 0, 3, false, c->st))) return rc;
             if (c->bs_late && (rc = send_slice_columns(c, a0, a1, 6, 7, false, c->st))) return rc;      // P, T exist only after the late part of the build
         }
+        if (c->timeline) { cudaEventRecord(c->tl[5], c->st); cudaEventRecord(c->tl[6], c->st_copy); }
         CK(cudaStreamSynchronize(c->st)); CK(cudaStreamSynchronize(c->st_copy));
+        if (c->timeline) {
+            auto at = [&](cudaEvent_t e) { float ms = -1.f; if (cudaEventElapsedTime(&ms, c->ev[8], e) != cudaSuccess) { (void)cudaGetLastError(); ms = -1.f; } return ms; };
+            fprintf(stderr, "agb timeline, bound slice %d/%d [ms after the build began]: build ..%.2f  visual density ..%.2f  gas density ..%.2f  last piece: walk %.2f (k_sph %.2f) ..%.2f |"
+                            " delivered on the compute stream %.2f, on the copy stream %.2f\n",
+                    part, nparts, at(c->ev[9]), at(c->ev[3]), at(c->ev[5]), at(c->evw[0]), at(c->evw[4]), at(c->evw[3]), at(c->tl[5]), at(c->tl[6]));
+        }
         return AGB_OK;
     }
     CK(cudaStreamSynchronize(c->st_copy));

@@ -483,6 +483,10 @@ def run_gpu_arm(args, pkg):
 
         def e2e_step():
             step(upload=host)
+            if breakdown and rank == 0:
+                e_, _ = bd_ev[-1]
+                torch.cuda.synchronize()
+                print("rank 0 e2e step: uploads + exchanges done %.2f ms after the step began, path done %.2f ms" % (e_[0].elapsed_time(e_[1]), e_[0].elapsed_time(e_[2])), file=sys.stderr, flush=True)
             return {k: v[:cnt_mine] for k, v in out_np.items()}
         for v in out_np.values():
             v.fill(0)
