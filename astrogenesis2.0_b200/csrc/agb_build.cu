@@ -512,8 +512,9 @@ __global__ void __launch_bounds__(TPB) k_pack_gas(AgbDev d)
 
 // LATE: the hand-over is still uploading velocities / U / mu (agb_force_path with host arrays): only what the build, the
 // densities and the gravity walk read is gathered here; k_gather_late fills in the rest once it has arrived.
+// split (with LATE): the gas columns follow at once in k_gather_gas, nothing is pending — everything else as in a late build
 template <bool LATE>
-__global__ void __launch_bounds__(TPB) k_gather(AgbDev d, uint32_t* __restrict__ perm, AgbScalars* s)
+__global__ void __launch_bounds__(TPB) k_gather(AgbDev d, uint32_t* __restrict__ perm, AgbScalars* s, bool split)
 {
     int64_t i = (int64_t)blockIdx.x * TPB + threadIdx.x;
     if (i >= d.n) return;
@@ -524,12 +525,12 @@ __global__ void __launch_bounds__(TPB) k_gather(AgbDev d, uint32_t* __restrict__
     const double m = r4.w;
     d.src_pm[i] = r4;
     d.s_type[i] = gas ? 2 : 1;                        // only "gas or not" matters on the path (Node.cpp:319,371,478,679,763)
-    if (!LATE) d.s_next[i] = !d.next ? 0.0 : s->next_uniform ? d.next[0] : d.next[p];
+    if (!LATE || split) d.s_next[i] = !d.next ? 0.0 : s->next_uniform ? d.next[0] : d.next[p];
     if (gas) {
         d.src_flag[i] = m > 0.0 ? 1 : 0;
         s->any_gas = 1;
         d.s_h[i] = 0.0;                               // Tree.cpp:123-133 zeroes h of every gas particle
-        if (LATE) d.src_gv[i] = make_double4(0.0, 0.0, 0.0, m);
+        if (LATE) { if (!split) d.src_gv[i] = make_double4(0.0, 0.0, 0.0, m); }
         else {
             // velocity, U, mu and the carried h/rho/P/T are only ever read for gas (Node.cpp:88-172, :722-796)
             const double4 g0 = d.grec[2 * (size_t)p], g1 = d.grec[2 * (size_t)p + 1];   // (vx, vy, vz, U), (mu, rho, P, T)
@@ -546,6 +547,19 @@ __global__ void __launch_bounds__(TPB) k_gather(AgbDev d, uint32_t* __restrict__
     d.leafparent[i] = -1;
     d.leafdepth[i] = -1;
     d.leafmark[i] = 0;
+}
+
+// The gas columns of a split gather: velocity, U, mu and the carried rho / P / T from the packed caller-order records.
+__global__ void __launch_bounds__(TPB) k_gather_gas(AgbDev d, const uint32_t* __restrict__ perm)
+{
+    int64_t i = (int64_t)blockIdx.x * TPB + threadIdx.x;
+    if (i >= d.n || d.s_type[i] != 2) return;
+    const uint32_t p = perm[i];
+    const double4 g0 = d.grec[2 * (size_t)p], g1 = d.grec[2 * (size_t)p + 1];
+    d.src_gv[i] = make_double4(g0.x, g0.y, g0.z, d.src_pm[i].w);
+    d.s_U[i] = g0.w;
+    d.s_mu[i] = g1.x;
+    d.s_rho[i] = g1.y; d.s_P[i] = g1.z; d.s_T[i] = g1.w;
 }
 
 // next_time of a LATE gather (it arrives behind the masses; nothing of the build reads it)
@@ -1093,10 +1107,15 @@ int agb_launch_links(AgbDev& d, AgbScalars* s, cudaStream_t st, cudaEvent_t* ev,
     const int nb = nblk(d.n, TPB);
     const uint64_t *khi = d.khi[d.cur], *klo = d.klo[1], *kex = d.deep ? d.kex : nullptr;
     if (d.next && !late_gas) k_next_uniform<<<std::min(nb, 2048), TPB, 0, st>>>(d.next, d.n, s);
-    if (late_gas) k_gather<true><<<nb, TPB, 0, st>>>(d, d.perm[d.cur], s);
-    else {
+    static const bool split = !getenv("AGB_GATHER_SPLIT") || atoi(getenv("AGB_GATHER_SPLIT")) != 0;
+    if (late_gas) k_gather<true><<<nb, TPB, 0, st>>>(d, d.perm[d.cur], s, false);
+    else if (split) {
         k_pack_gas<<<nb, TPB, 0, st>>>(d);
-        k_gather<false><<<nb, TPB, 0, st>>>(d, d.perm[d.cur], s);
+        k_gather<true><<<nb, TPB, 0, st>>>(d, d.perm[d.cur], s, true);
+        k_gather_gas<<<nb, TPB, 0, st>>>(d, d.perm[d.cur]);
+    } else {
+        k_pack_gas<<<nb, TPB, 0, st>>>(d);
+        k_gather<false><<<nb, TPB, 0, st>>>(d, d.perm[d.cur], s, false);
     }
     if (ev) cudaEventRecord(ev[0], st);
     k_lcp<<<nb, TPB, 0, st>>>(khi, klo, kex, d.n, d.lcp, d.nodecnt, s);
@@ -1112,7 +1131,7 @@ int agb_launch_links(AgbDev& d, AgbScalars* s, cudaStream_t st, cudaEvent_t* ev,
     k_level_lists<<<nnb, TPB, 0, st>>>(d, s, d.lvl_list);
     if (late_gas) k_upward_levels<1><<<upward_blocks(nnb), TPB, 0, st>>>(d, s, d.lvl_list);
     else k_upward_levels<0><<<upward_blocks(nnb), TPB, 0, st>>>(d, s, d.lvl_list);
-    return (late_gas ? 10 : 11) + (d.next && !late_gas ? 1 : 0);
+    return (late_gas ? 10 : split ? 12 : 11) + (d.next && !late_gas ? 1 : 0);
 }
 
 int agb_launch_gather_next(AgbDev& d, AgbScalars* s, cudaStream_t st)
