@@ -127,6 +127,17 @@ __device__ __forceinline__ int warp_incl_scan(int v, int lane)
     for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o) v += t; }
     return v;
 }
+// position of the n-th (0-based) set bit of m, n < popc(m): five popcount halvings (the library's __fns is a ~40-instruction loop)
+__device__ __forceinline__ int nth_set_bit(unsigned m, int n)
+{
+    int pos = 0, c;
+    c = __popc(m & 0xffffu); if (n >= c) { n -= c; pos = 16; m >>= 16; }
+    c = __popc(m & 0xffu);   if (n >= c) { n -= c; pos += 8; m >>= 8; }
+    c = __popc(m & 0xfu);    if (n >= c) { n -= c; pos += 4; m >>= 4; }
+    c = __popc(m & 0x3u);    if (n >= c) { n -= c; pos += 2; m >>= 2; }
+    if (n >= (int)(m & 1u)) pos += 1;
+    return pos;
+}
 __device__ __forceinline__ unsigned long long warp_sum_u64(unsigned long long v)
 {
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -940,7 +951,7 @@ __global__ void __launch_bounds__(256, AGB_SPH_CTAS_PER_SM) k_sph(const WalkPara
                     const unsigned o_mine = __shfl_sync(0xffffffffu, mine, owner);
                     double fx = 0, fy = 0, fz = 0, du = 0;
                     if (p < total) {
-                        const int j = __fns(o_mine, 0, p - (o_incl - o_cnt) + 1);
+                        const int j = nth_set_bit(o_mine, p - (o_incl - o_cnt));
                         const int esrc = sm.list[j];
                         const double4 gv = sm.gst[j];                // (mVel | particle velocity, gasMass)
                         const double4 k4 = sm.tsph[3 * owner], tv = sm.tsph[3 * owner + 1];
@@ -980,14 +991,17 @@ __global__ void __launch_bounds__(256, AGB_SPH_CTAS_PER_SM) k_sph(const WalkPara
                             if (isnan(fx) || isnan(fy) || isnan(fz)) { fx = 0; fy = 0; fz = 0; }         // Node.cpp:169
                             tot_sph++;
                         }
-                        sm.res[lane] = make_double4(fx, fy, fz, pass ? du : __longlong_as_double(0x7ff8000000000001ll));
+                        // a pair that fails the gate contributes exact zeros (x + 0.0 == x), so the owner adds every slot of its
+                        // range unconditionally; only the counting variant needs to tell the two apart
+                        sm.res[lane] = make_double4(fx, fy, fz, (COUNT && !pass) ? __longlong_as_double(0x7ff8000000000001ll) : du);
                     }
                     __syncwarp();
                     // my pairs inside this chunk are the contiguous lanes [a, b)
                     const int a = max(incl - npair, c0) - c0, b = min(incl, c0 + 32) - c0;
                     for (int i = a; i < b; i++) {
                         const double4 r = sm.res[i];
-                        if (__double_as_longlong(r.w) != 0x7ff8000000000001ll) { ax += r.x; ay += r.y; az += r.z; dU += r.w; if (COUNT) c_sp++; }
+                        if (!COUNT) { ax += r.x; ay += r.y; az += r.z; dU += r.w; }
+                        else if (__double_as_longlong(r.w) != 0x7ff8000000000001ll) { ax += r.x; ay += r.y; az += r.z; dU += r.w; c_sp++; }
                     }
                     __syncwarp();
                 }
