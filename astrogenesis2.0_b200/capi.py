@@ -17,6 +17,7 @@ AGB_OPT_COOLING = 3
 AGB_OPT_STAR_FORMATION = 4
 AGB_OPT_EXTENDED = 5
 AGB_OPT_SLICE_PIECE = 6
+AGB_OPT_SLICE_DENSITIES = 7
 
 EXPORTS = [
     "agb_create", "agb_destroy", "agb_set_particles", "agb_set_particles_staged", "agb_set_particles_aos", "agb_build_tree", "agb_visual_density",

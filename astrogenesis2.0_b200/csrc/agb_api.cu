@@ -43,6 +43,7 @@ struct agb_ctx {
     bool mixed = true;                  // AGB_OPT_PRECISION
     bool walked_mixed = false;          // the last walk used the FP32 pair law (mixed_in_range)
     bool ext_quad = true;               // ... with the quadrupole term (AGB_OPT_EXTENDED = 2: monopole only, for validation)
+    bool slice_dens = false;            // AGB_OPT_SLICE_DENSITIES
     int64_t piece_targets = 2000000;    // AGB_OPT_SLICE_PIECE: bound slice results are pipelined in up to 4 pieces of at least this many targets
     bool extended = false;              // AGB_OPT_EXTENDED: quadrupoles + spline softening + per-particle-h SPH (agb_extended.cu)
     bool opt_cooling = false; unsigned long long opt_sf_seed = 0;   // AGB_OPT_COOLING, AGB_OPT_STAR_FORMATION
@@ -363,6 +364,7 @@ int agb_set_option(agb_ctx* c, int option, int64_t value)
     if (option == AGB_OPT_PRECISION) { if (value != 0 && value != 1) return AGB_ERR_INVALID; c->mixed = value == 1; return AGB_OK; }
     if (option == AGB_OPT_COOLING) { c->opt_cooling = value != 0; return AGB_OK; }
     if (option == AGB_OPT_SLICE_PIECE) { if (value < 256) return AGB_ERR_INVALID; c->piece_targets = value; return AGB_OK; }
+    if (option == AGB_OPT_SLICE_DENSITIES) { c->slice_dens = value != 0; return AGB_OK; }
     if (option == AGB_OPT_EXTENDED) {
         if (value != 0 && c->d.ncap > 0 && !c->d.quad) { CK(cudaSetDevice(c->device)); CK(dalloc(c->d.quad, 6 * (size_t)c->d.ncap)); CK(dalloc(c->d.ext_bar, 1)); }
         c->extended = value != 0; c->ext_quad = value != 2;
@@ -381,6 +383,7 @@ int agb_set_particles(agb_ctx* c, const agb_particles* p, int memspace)
     if (rc) return rc;
     AgbDev& d = c->d;
     d.n = n;
+    d.dens_a0 = 0; d.dens_a1 = INT64_MAX;
     for (auto& e : c->xev) e = nullptr;
     c->mass_late = false;
     // Everything already queued on the compute stream (densities, walk, integrator kernels of the previous step) reads or
@@ -687,6 +690,7 @@ static int forces_impl(agb_ctx* c, double global_time, double e0, double theta, 
     if (c->vis_timed && cudaEventElapsedTime(&ms, c->ev[2], c->ev[3]) == cudaSuccess) c->phase_ms[1] = ms;
     if (c->gas_timed && cudaEventElapsedTime(&ms, c->ev[4], c->ev[5]) == cudaSuccess) c->phase_ms[2] = ms;
     (void)cudaGetLastError();
+    if (c->hs.walk_overflow == 3) { c->forces_done = false; return AGB_OK; }     // sliced densities, but some particles rest: nothing was walked, the caller redoes the step
     if (c->hs.walk_overflow) { c->err = c->hs.walk_overflow == 2 ? "SPH tile-record pool overflow" : "traversal stack overflow"; return AGB_ERR_NOMEM; }
     c->forces_done = true; c->counters_valid = c->target_counters;
     return AGB_OK;
@@ -763,6 +767,7 @@ static int force_path_impl(agb_ctx* c, double visual_density_radius, double mass
     auto stepwise = [&]() -> int {
         double R = 0.0;
         c->bs_early = false; c->bs_piped = false;               // whatever left early came from an abandoned attempt
+        c->d.dens_a0 = 0; c->d.dens_a1 = INT64_MAX;
         int rc = agb_build_tree(c, &R);
         if (rc) return rc;
         if (root_radius) *root_radius = R;
@@ -790,6 +795,11 @@ static int force_path_impl(agb_ctx* c, double visual_density_radius, double mass
     c->built = true;
     c->hs.any_gas = c->gas_hint ? 1 : 0;
     int rc;
+    // AGB_OPT_SLICE_DENSITIES: density outputs for this slice's targets only — as long as every particle is a target (as in the
+    // last step; verified for this one below), a slice of the targets is a range of tree positions
+    const bool dens_sliced = c->slice_dens && nparts > 1 && c->hs.n_active == d.n && d.n > 0 && !c->extended;
+    d.dens_a0 = 0; d.dens_a1 = INT64_MAX;
+    if (dens_sliced) agb_slice_bounds(d.n, part, nparts, &d.dens_a0, &d.dens_a1);
     if ((rc = agb_visual_density(c, visual_density_radius))) return rc;
     if ((rc = gas_density_impl(c, mass_in_h, late_gas))) return rc;
     if (c->bs_on && part == c->bs_part && nparts == c->bs_nparts && c->hs.n_active == d.n && d.n > 0) {
@@ -837,6 +847,8 @@ static int force_path_impl(agb_ctx* c, double visual_density_radius, double mass
     (void)cudaGetLastError();
     c->hs.R = 0; memcpy(&c->hs.R, &c->hs.Rbits, 8);
     if (root_radius) *root_radius = c->hs.R;
+    d.dens_a0 = 0; d.dens_a1 = INT64_MAX;
+    if (dens_sliced && c->hs.n_active != d.n) { c->built = false; c->forces_done = false; return stepwise(); }   // some particles rest: redo with all densities
     if (c->hs.need_deep && !d.deep) { c->built = false; c->forces_done = false; return stepwise(); }   // agb_build_tree switches to three-word keys
     if (c->walked_mixed && !mixed_in_range(c, e0)) { c->built = false; c->forces_done = false; return stepwise(); }   // this step's tree left the FP32 range: redo in FP64
     if (c->hs.n_nodes > d.ncap) {                                   // node table overflow: every kernel after the node count returned at once

@@ -33,8 +33,8 @@ __device__ __forceinline__ double radius_at(double R, int depth) { return scalbn
 // test only depends on the level.  The root never computes (parent == nullptr, Node.cpp:834).
 __global__ void __launch_bounds__(TPB) k_visual(AgbDev d, const uint32_t* __restrict__ perm, const AgbScalars* __restrict__ s, double rt)
 {
-    int64_t i = (int64_t)blockIdx.x * TPB + threadIdx.x;
-    if (i >= d.n || s->node_overflow) return;
+    int64_t i = (int64_t)blockIdx.x * TPB + threadIdx.x + d.dens_a0;
+    if (i >= d.n || i >= d.dens_a1 || s->node_overflow) return;
     const uint32_t p = perm[i];
     double out = 0.0;                                          // Tree.cpp:156-161 zeroes every particle first
     if (i < s->n_in_tree) {
@@ -246,7 +246,7 @@ __global__ void __launch_bounds__(TPB) k_gas_group(AgbDev d, AgbScalars* s)
 {
     int64_t i = (int64_t)blockIdx.x * TPB + threadIdx.x;
     bool orphan = false;
-    if (i < s->n_in_tree && !s->node_overflow && d.s_type[i] == 2) {
+    if (i < s->n_in_tree && i >= d.dens_a0 && i < d.dens_a1 && !s->node_overflow && d.s_type[i] == 2) {
         int grp = d.leafmark[i] ? (int)i : -1;
         for (int k = d.leafparent[i]; k >= 0; k = d.nparent[k]) if (d.nmark[k]) grp = (int)d.n + k;
         d.group[i] = grp;
@@ -295,6 +295,7 @@ __global__ void __launch_bounds__(TPB) k_gas_sum(AgbDev d, const AgbScalars* __r
     if (s->node_overflow) return;
     for (int g = (blockIdx.x * TPB + threadIdx.x) >> 5; g < s->n_gas_groups; g += (gridDim.x * TPB) >> 5) {
     const int k = d.grouplist[g];
+    if (d.nfirst[k] >= d.dens_a1 || d.nlast[k] < d.dens_a0) continue;     // none of its particles is asked for
     const double h = __dmul_rn(radius_at(R, d.ndepth[k]), 2.0);          // Node.cpp:765
     const double4 com = d.src_pm[d.n + k];
     // the node's gas particles are a contiguous range of the compact gas list (tree order)
@@ -325,6 +326,7 @@ __global__ void __launch_bounds__(TPB) k_gas_scatter(AgbDev d, const AgbScalars*
     const int r = blockIdx.x * TPB + threadIdx.x;
     if (r >= s->n_gas_total) return;
     const int i = F.g_tree[r];
+    if (i < d.dens_a0 || i >= d.dens_a1) return;
     const uint32_t p = F.g_orig[r];
     if (LATE) { d.h[p] = d.s_h[i]; if (i < s->n_in_tree && d.group[i] >= 0) d.rho[p] = d.s_rho[i]; }
     else { d.h[p] = d.s_h[i]; d.rho[p] = d.s_rho[i]; d.P[p] = d.s_P[i]; d.T[p] = d.s_T[i]; }
@@ -342,7 +344,8 @@ static inline int nblk(int64_t n, int per) { return (int)((n + per - 1) / per); 
 
 int agb_launch_visual(AgbDev& d, AgbScalars* s, double radius, cudaStream_t st)
 {
-    k_visual<<<nblk(d.n, TPB), TPB, 0, st>>>(d, d.perm[d.cur], s, radius);
+    const int64_t cnt = std::min<int64_t>(d.n, d.dens_a1) - d.dens_a0;
+    if (cnt > 0) k_visual<<<nblk(cnt, TPB), TPB, 0, st>>>(d, d.perm[d.cur], s, radius);
     return 1;
 }
 

@@ -24,6 +24,9 @@
 
 struct AgbDev {
     int64_t n = 0, cap = 0;
+    // AGB_OPT_SLICE_DENSITIES: the per-particle outputs of the density passes are only produced for tree positions [dens_a0, dens_a1)
+    // (a sliced step hands back nothing else; the SPH terms use the TARGET's h / rho / P only, Node.cpp:94,101,108)
+    int64_t dens_a0 = 0, dens_a1 = INT64_MAX;
     int64_t ncap = 0;                  // capacity of the node arrays: one node per (first particle, depth) pair, so a tight pair
                                        // alone costs up to 41 nodes; grown on demand when a build reports more (agb_api.cu)
     int cores = 1;

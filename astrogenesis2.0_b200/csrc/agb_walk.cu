@@ -197,7 +197,7 @@ __global__ void __launch_bounds__(128) k_far(const WalkParams P)
     const double inf = __longlong_as_double(0x7ff0000000000000ll);
     const Slice sl = target_slice(P);
     const int nsg = (int)((sl.a1 - sl.a0 + 32 * SG_GROUPS - 1) / (32 * SG_GROUPS));
-    if (P.s->node_overflow) return;                                 // no usable tree this step (the host grows the node arrays and rebuilds)
+    if (P.s->node_overflow || P.s->walk_overflow == 3) return;      // no usable tree this step (the host grows the node arrays and rebuilds) / densities not for these targets
     for (int sgi = blockIdx.x * 4 + warp; sgi < nsg; sgi += gridDim.x * 4) {
         const int64_t tb = sl.a0 + (int64_t)sgi * (32 * SG_GROUPS);
         int32_t* const fl = P.far_list + (size_t)sgi * FAR_LCAP;
@@ -330,7 +330,7 @@ __global__ void __launch_bounds__(WalkCfg<SPH>::TPB, WALK_CTAS) k_walk(const Wal
         return make_int2(-1, 0);
     };
 
-    if (P.s->node_overflow) return;
+    if (P.s->node_overflow || P.s->walk_overflow == 3) return;
     for (;;) {
         unsigned g = 0;
         if (lane == 0) g = atomicAdd(&P.s->walk_next_group, 1u);
@@ -1045,6 +1045,12 @@ __global__ void k_count_active(const double* __restrict__ s_next, int64_t n, dou
     __syncthreads();
     if (threadIdx.x == 0 && cnt) atomicAdd(&s->n_active, cnt);
 }
+// AGB_OPT_SLICE_DENSITIES assumed "every particle is a target" when it restricted the density passes to a range of tree positions:
+// if that does not hold, the walk kernels of this step return at once (walk_overflow = 3) and the host redoes it with all densities
+__global__ void k_dens_guard(AgbScalars* s, int64_t n)
+{
+    if (s->n_active != n) s->walk_overflow = 3;
+}
 // the three kernels below return at once when every particle is active (the list is then the identity and never read)
 __global__ void k_active_flags(const double* __restrict__ s_next, int64_t n, double gt, const AgbScalars* __restrict__ s, int32_t* __restrict__ flag)
 {
@@ -1181,6 +1187,7 @@ int agb_launch_active_list(AgbDev& d, AgbScalars* s, double globalTime, int sm_c
     if (d.n > 0) {
         cudaMemsetAsync(&s->n_active, 0, sizeof(int32_t), st);
         k_count_active<<<std::min(nb, 4 * sm_count), 256, 0, st>>>(d.s_next, d.n, globalTime, s);
+        if (d.dens_a1 != INT64_MAX) { k_dens_guard<<<1, 1, 0, st>>>(s, d.n); launches++; }
         // compact list of the active targets (scratch: flags -> nodecnt, ranks -> nodebase; both are idle after the densities)
         k_active_flags<<<nb, 256, 0, st>>>(d.s_next, d.n, globalTime, s, d.nodecnt);
         launches += 3 + agb_launch_scan_i32(d.nodecnt, d.nodebase, d.n, d.scanblk, &s->n_scan_tmp, st, &s->n_active);

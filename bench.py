@@ -368,6 +368,10 @@ def run_gpu_arm(args, pkg):
         if float(mn[0]) != 1.0 or int(sm_[1]) != n:
             raise SystemExit("sharded walk differs from the whole walk (or the slices do not cover every particle once)")
         multi_gpu_check = "slices of the %d-way sharded walk cover all %d particles once and equal the whole walk bit for bit (%s)" % (world, n, ", ".join(out_cols))
+        # every rank hands back its slice only: the density passes produce their per-particle outputs for that slice only (the SPH
+        # terms of a target use its own h, rho, P; the end-to-end leg below checks the delivered columns against the bits above)
+        if os.environ.get("AGB_BENCH_FULL_DENSITIES") != "1":
+            ctx.set_option(pkg.capi.AGB_OPT_SLICE_DENSITIES, 1)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -618,7 +622,7 @@ def run_gpu_arm(args, pkg):
         "dtype": "f64" if args.extended else "f64 decisions and accumulation, f32 pair forces (mixed mode)", "data": "synthetic",
         "config": cfg,
         "run": {"precision": "extended-accuracy mode (AGB_OPT_EXTENDED): quadrupoles, spline softening, width/d < theta per 32-target group, per-particle-h SPH; FP64; parity unpinned by the reference" if args.extended else "mixed", "l2": "256 MiB buffer written between timed steps (L2 flush); working set %.0f MB" % (n * 330 / 1e6),
-                "parallelism": ("replicated tree, tree-ordered target slices, in-place NCCL all-gathers in 2 coalesced groups per step, the second behind extent / keys / sort (e2e: 3 groups, overlapped with build, densities and gravity walk) through agb_set_particles_staged" if staged else
+                "parallelism": ("replicated tree, tree-ordered target slices, density outputs for the rank's slice only, in-place NCCL all-gathers in 2 coalesced groups per step, the second behind extent / keys / sort (e2e: 3 groups, overlapped with build, densities and gravity walk) through agb_set_particles_staged" if staged else
                                 "replicated tree, tree-ordered target slices, packed NCCL all-gather per step") if world > 1 else "single GPU",
                 "result_columns": list(out_cols)},
         "e2e": e2e, "fp64": fp64, "resident_sim_step": resident, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,

@@ -189,6 +189,11 @@ typedef enum {
     AGB_OPT_SLICE_PIECE = 6,        /* tuning: with agb_bind_slice_results, a slice of at least 2 x this many targets is walked in up to 4 pieces
                                        (exact sub-ranges: same bits) so that the acc / dU/dt of a piece leave while the next one walks.
                                        Default 2 000 000. */
+    AGB_OPT_SLICE_DENSITIES = 7,    /* 1: a sliced agb_force_path (nparts > 1) produces visualDensity / h / rho / P / T only for the targets of ITS slice —
+                                       what the slice getters hand back; the SPH terms of a target use its own h, rho, P only (Node.cpp:94,101,108), so
+                                       acc and dU/dt are unchanged.  For callers that collect results per slice (one process per GPU); the full-length
+                                       getters then hold zeros / the handed-over state outside the slice.  Needs every particle active (otherwise the step
+                                       is redone with all densities).  Default 0. */
     AGB_OPT_PRECISION = 2           /* arithmetic of the pair forces: 0 = FP64 throughout (agrees with the reference to ~1e-14),
                                        1 = mixed (default): float-float displacements, FP32 law, FP64 accumulation; ~1e-7.
                                        The accepted (target, source) sets, SPH pair sets and densities are identical in both;

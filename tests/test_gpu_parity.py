@@ -790,6 +790,60 @@ def test_staged_device_hand_over_waits_for_its_events(pkg, two_groups):
 
 
 @pytest.mark.parametrize("active_frac", [1.0, 0.4])
+@pytest.mark.parametrize("bound", [False, True])
+def test_slice_densities_option_returns_the_same_slice(pkg, active_frac, bound):
+    """AGB_OPT_SLICE_DENSITIES: a sliced agb_force_path produces the density outputs for its own targets only; what the slice
+    getters (and a bound slice delivery) hand back is bit for bit what the plain step returns for that slice, for host hand-overs
+    (late-upload path) and device hand-overs, and when some particles rest (the step is then redone with all densities)."""
+    rng = np.random.default_rng(19)
+    p = pkg.ics.disk_galaxy(70000, seed=93)
+    n = len(p["x"])
+    if active_frac < 1.0:
+        p["next_time"] = np.where(rng.random(n) < active_frac, 0.0, 1e13)
+    mh = pkg.ics.gas_mass_in_h(p, 48)
+    names = ("ax", "ay", "az", "dUdt", "h", "rho", "P", "T", "visualDensity")
+    ref = pkg.Context(0, 8)
+    ctx = pkg.Context(0, 8)
+    ctx.set_option(pkg.capi.AGB_OPT_SLICE_DENSITIES, 1)
+    ctx.set_option(pkg.capi.AGB_OPT_SLICE_PIECE, 4096)
+    try:
+        ref.set_particles(dict(p)); R = ref.build_tree()
+        for part, nparts in ((0, 3), (1, 3), (2, 3), (0, 1)):
+            ref.set_particles(dict(p)); ref.build_tree(); ref.visual_density(R / 100000); ref.gas_density(mh); ref.forces(0.0, 1e18, 0.5, part, nparts)
+            exp = ref.slice_results(part, nparts, names=names)
+            cnt = len(exp["index"])
+            out = {k: np.full(n, np.nan) for k in names}
+            out["index"] = np.full(n, 0xffffffff, np.uint32)
+            if bound:
+                ctx.bind_slice_results(part, nparts, out)
+            for rep in range(3):                                # call by call, then fused twice
+                ctx.set_particles(dict(p))
+                ctx.force_path(R / 100000, mh, 0.0, 1e18, 0.5, part, nparts)
+                got = {k: v[:cnt] for k, v in out.items()} if bound else ctx.slice_results(part, nparts, names=names)
+                assert np.array_equal(got["index"], exp["index"]), (part, nparts, rep)
+                for k in names:
+                    assert np.array_equal(got[k], exp[k]), (k, part, nparts, rep)
+            if active_frac == 1.0 and (part, nparts) == (1, 3):
+                # half of the particles go to rest between two steps: the sliced densities were started on "everyone is a target"
+                # and the step is redone with all of them
+                q = dict(p)
+                q["next_time"] = np.where(rng.random(n) < 0.5, 0.0, 1e13)
+                ref.set_particles(dict(q)); ref.build_tree(); ref.visual_density(R / 100000); ref.gas_density(mh); ref.forces(0.0, 1e18, 0.5, part, nparts)
+                exp2 = ref.slice_results(part, nparts, names=names)
+                ctx.set_particles(dict(q))
+                ctx.force_path(R / 100000, mh, 0.0, 1e18, 0.5, part, nparts)
+                c2 = len(exp2["index"])
+                got = {k: v[:c2] for k, v in out.items()} if bound else ctx.slice_results(part, nparts, names=names)
+                assert np.array_equal(got["index"], exp2["index"])
+                for k in names:
+                    assert np.array_equal(got[k], exp2[k]), (k, "resting")
+            if bound:
+                ctx.bind_slice_results(0, 1, None)
+    finally:
+        ctx.close(); ref.close()
+
+
+@pytest.mark.parametrize("active_frac", [1.0, 0.4])
 def test_bound_slice_results_are_delivered_by_the_fused_call(pkg, active_frac):
     """agb_bind_slice_results: agb_force_path sends the bound slice's compact results itself (index and density columns during the
     walk when every particle is a target, the rest after it; everything afterwards when some particles are inactive).  Same bits
