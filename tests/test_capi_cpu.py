@@ -73,3 +73,23 @@ def test_ctypes_mirror_matches_the_header(pkg, tmp_path):
         assert int(got[cname]) == C.sizeof(ct), cname
         for fname, _ in ct._fields_:
             assert int(got["%s.%s" % (cname, fname)]) == getattr(ct, fname).offset, (cname, fname)
+
+
+def test_constants_match_the_header(pkg, tmp_path):
+    """Every AGB_* integer constant of capi.py has the value the header's enums give it (a C compiler evaluates them), and every
+    AGB_OPT_* / AGB_MEM_* the header declares is mirrored."""
+    import subprocess
+    hdr = open(os.path.join(ROOT, "include", "agb200.h")).read()
+    declared = sorted(set(re.findall(r"\b(AGB_(?:OPT|MEM)_[A-Z_0-9]+)\b\s*=", hdr)))
+    mirrored = sorted(k for k in dir(pkg.capi) if re.fullmatch(r"AGB_(OPT|MEM)_[A-Z_0-9]+", k))
+    assert declared == mirrored
+    prog = ['#include <stdio.h>', '#include "agb200.h"', "int main(void) {"]
+    prog += ['printf("%s %%d\\n", (int)%s);' % (k, k) for k in declared]
+    prog += ["return 0; }"]
+    src = tmp_path / "consts.c"
+    src.write_text("\n".join(prog))
+    exe = tmp_path / "consts"
+    subprocess.check_call(["gcc", "-std=c11", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    got = dict(line.split() for line in subprocess.check_output([str(exe)], text=True).splitlines())
+    for k in declared:
+        assert int(got[k]) == getattr(pkg.capi, k), k
