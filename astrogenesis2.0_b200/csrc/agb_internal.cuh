@@ -151,7 +151,7 @@ int agb_launch_slice_results(const AgbDev& d, int64_t a0, int64_t a1, bool ident
 int agb_launch_walk(AgbDev& d, AgbScalars* s, double globalTime, double e0, double theta, int part, int nparts,
                     bool counters, bool any_gas, bool mixed, int sm_count, cudaStream_t st, cudaEvent_t* ev, int phase = 0);   // ev[0..4]: before k_far, before k_walk, after k_walk, after k_sph, before k_sph
 // the step's force targets (globalTime == nextIntegrationTime) in tree order, compacted; resets the walk's counters
-int agb_launch_active_list(AgbDev& d, AgbScalars* s, double globalTime, int sm_count, cudaStream_t st);
+int agb_launch_active_list(AgbDev& d, AgbScalars* s, double globalTime, int sm_count, cudaStream_t st, bool mixed = false, double e0 = 0.0);
 // extended-accuracy mode (agb_extended.cu): per-particle smoothing lengths and densities; quadrupole walk + neighbour-loop SPH forces
 int agb_launch_gas_list(AgbDev& d, AgbScalars* s, cudaStream_t st);   // tree positions of the gas particles, compact, in d.nodecnt; count in s->n_gas_total
 int agb_launch_extended_density(AgbDev& d, AgbScalars* s, double massInH, cudaStream_t st);

@@ -1045,11 +1045,18 @@ __global__ void k_count_active(const double* __restrict__ s_next, int64_t n, dou
     __syncthreads();
     if (threadIdx.x == 0 && cnt) atomicAdd(&s->n_active, cnt);
 }
-// AGB_OPT_SLICE_DENSITIES assumed "every particle is a target" when it restricted the density passes to a range of tree positions:
-// if that does not hold, the walk kernels of this step return at once (walk_overflow = 3) and the host redoes it with all densities
-__global__ void k_dens_guard(AgbScalars* s, int64_t n)
+// What a fused step (agb_force_path) took from the LAST step is checked here, on the device, before anything is walked — a walk
+// adds to dU/dt, so it cannot simply be repeated.  (1) AGB_OPT_SLICE_DENSITIES assumed "every particle is a target" when it
+// restricted the density passes to a range of tree positions.  (2) The FP32 pair law was chosen for the last step's root cube and
+// depth (mixed_in_range, agb_api.cu).  If either does not hold for THIS tree the walk kernels return at once (walk_overflow = 3)
+// and the host redoes the step call by call.
+__global__ void k_step_guard(AgbScalars* s, int64_t n, bool all_targets, bool mixed, double e0)
 {
-    if (s->n_active != n) s->walk_overflow = 3;
+    if (all_targets && s->n_active != n) s->walk_overflow = 3;
+    if (mixed) {
+        const double R = __longlong_as_double((long long)s->Rbits);
+        if (R > 0.0 && !(e0 >= 1e-10 * R && e0 <= 50.0 * R && s->max_depth <= 40)) s->walk_overflow = 3;
+    }
 }
 // the three kernels below return at once when every particle is active (the list is then the identity and never read)
 __global__ void k_active_flags(const double* __restrict__ s_next, int64_t n, double gt, const AgbScalars* __restrict__ s, int32_t* __restrict__ flag)
@@ -1149,7 +1156,7 @@ int agb_launch_walk(AgbDev& d, AgbScalars* s, double globalTime, double e0, doub
     P.far_k2 = far_k2;
     int launches = 0;
     const int64_t max_groups = (d.n / nparts + 32 * SG_GROUPS + 31) / 32;
-    if (phase != 2) launches += agb_launch_active_list(d, s, globalTime, sm_count, st);
+    if (phase != 2) launches += agb_launch_active_list(d, s, globalTime, sm_count, st, mixed, e0);
     if (d.n > 0 && phase != 2) {
         if (counters) {
             cudaMemsetAsync(d.c_visits, 0, (size_t)d.n * 4, st); cudaMemsetAsync(d.c_accn, 0, (size_t)d.n * 4, st);
@@ -1179,7 +1186,7 @@ int agb_launch_walk(AgbDev& d, AgbScalars* s, double globalTime, double e0, doub
     return launches;
 }
 
-int agb_launch_active_list(AgbDev& d, AgbScalars* s, double globalTime, int sm_count, cudaStream_t st)
+int agb_launch_active_list(AgbDev& d, AgbScalars* s, double globalTime, int sm_count, cudaStream_t st, bool mixed, double e0)
 {
     int launches = 1;
     const int nb = (int)((d.n + 255) / 256);
@@ -1187,7 +1194,7 @@ int agb_launch_active_list(AgbDev& d, AgbScalars* s, double globalTime, int sm_c
     if (d.n > 0) {
         cudaMemsetAsync(&s->n_active, 0, sizeof(int32_t), st);
         k_count_active<<<std::min(nb, 4 * sm_count), 256, 0, st>>>(d.s_next, d.n, globalTime, s);
-        if (d.dens_a1 != INT64_MAX) { k_dens_guard<<<1, 1, 0, st>>>(s, d.n); launches++; }
+        if (d.dens_a1 != INT64_MAX || mixed) { k_step_guard<<<1, 1, 0, st>>>(s, d.n, d.dens_a1 != INT64_MAX, mixed, e0); launches++; }
         // compact list of the active targets (scratch: flags -> nodecnt, ranks -> nodebase; both are idle after the densities)
         k_active_flags<<<nb, 256, 0, st>>>(d.s_next, d.n, globalTime, s, d.nodecnt);
         launches += 3 + agb_launch_scan_i32(d.nodecnt, d.nodebase, d.n, d.scanblk, &s->n_scan_tmp, st, &s->n_active);

@@ -450,6 +450,37 @@ def test_root_cube_blown_up_by_runaway_particles(pkg, oracle):
         ctx.close()
 
 
+def test_fused_step_that_leaves_the_fp32_range_is_walked_once(pkg):
+    """agb_force_path picks the FP32 pair law from the LAST step's root cube.  When this step's tree lies outside its range (here
+    the system has shrunk until e0 > 50 R) the choice is caught on the device before anything is walked and the step is redone
+    call by call in FP64: dU/dt accumulates, so a mixed walk followed by the FP64 one would have counted every SPH pair twice."""
+    p = pkg.ics.plummer(12000, seed=29, gas_fraction=0.2)
+    mh = pkg.ics.gas_mass_in_h(p, 16)
+    q = dict(p)
+    for c in ("x", "y", "z"):
+        q[c] = p[c] * 1e-6
+    names = ("ax", "ay", "az", "dUdt", "h", "rho", "P", "T", "visualDensity")
+    fresh = pkg.Context(0, 8)
+    ctx = pkg.Context(0, 8)
+    try:
+        want, _ = pkg.run_step(dict(q), 0.5, 1e18, mh, 0.0, context=fresh)
+        want["visualDensity"] = want["vis"]
+        assert 1e18 > 50.0 * want["R"]
+        ctx.set_particles(dict(p)); R0 = ctx.build_tree()
+        for rep in range(2):                                    # call by call, then fused (mixed precision)
+            ctx.set_particles(dict(p))
+            ctx.force_path(R0 / 100000, mh, 0.0, 1e18, 0.5)
+        assert 1e18 <= 50.0 * R0
+        ctx.set_particles(dict(q))
+        R = ctx.force_path(want["R"] / 100000, mh, 0.0, 1e18, 0.5)
+        got = ctx.results()
+        assert R == want["R"]
+        for k in names:
+            assert np.array_equal(got[k], want[k]), k
+    finally:
+        ctx.close(); fresh.close()
+
+
 @pytest.mark.parametrize("theta", [0.0, 1.5])
 def test_extreme_opening_angles(pkg, oracle, ctxs, theta):
     """theta = 0: nothing is ever accepted, the walk degenerates to a direct sum over leaves; theta = 1.5: beyond the reference's

@@ -1,4 +1,4 @@
 #!/bin/bash
 cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "slice_densities or bound_slice or sequence or golden" 2>&1 | tail -15
+timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "slice_densities or fp32_range or sequence or blown or late_upload" 2>&1 | tail -15
