@@ -32,6 +32,19 @@ def _worker(rank, world, port, n, q):
             out2 = ig.gather(shard)                    # copies the shard into its slot, then completes the arrays in place
             ok = ok and all(np.array_equal(out2[k].numpy(), p[k]) for k in shard)
             ok = ok and all(ig.shard[k].data_ptr() == out2[k][lo:hi].data_ptr() for k in shard)
+            # the staged exchange of the bench: one group of arrays at a time; a group completes exactly its own arrays
+            ig2 = pkg.shard.InPlaceGather({k: v.dtype for k, v in shard.items()}, n, world, rank, torch.device("cpu"))
+            for k, v in ig2.out.items():
+                v.fill_(0)
+            for k in shard:
+                ig2.shard[k].copy_(shard[k])
+            first, rest = ("x", "y", "z", "mass", "type"), ("vx",)
+            ig2.gather_fields(first)
+            ok = ok and all(np.array_equal(ig2.out[k].numpy(), p[k]) for k in first)
+            other = np.zeros(n, p["vx"].dtype); other[lo:hi] = p["vx"][lo:hi]
+            ok = ok and np.array_equal(ig2.out["vx"].numpy(), other)        # not exchanged yet: only this rank's slot is filled
+            ig2.gather_fields(rest)
+            ok = ok and np.array_equal(ig2.out["vx"].numpy(), p["vx"])
         q.put((rank, ok, pkg.shard.slice_bounds(n, rank, world)))
     finally:
         dist.destroy_process_group()
