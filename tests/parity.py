@@ -99,3 +99,54 @@ def assert_parity(rep):
     for k in ("node_mass_maxrel", "node_gas_maxrel"):
         if k in rep:
             assert rep[k] <= 1e-10, (k, rep)
+
+
+def beyond_fp32_law(p, want):
+    """True when a set lies outside what the mixed-precision pair law resolves and the library's own guard (root cube vs e0, depth
+    > 40: FP64 pair arithmetic) does not catch: targets further than ~40 R from the sources (r^6 in units of (R/2^16)^6 leaves the
+    FP32 range, the pair force underflows to zero: only particles far beyond mean + 10 sigma), or pairs 2^-38 R apart inside a
+    sparse set whose 32-target groups span the whole cube (float-float positions resolve 2^-47 R).  Measured on the adversarial
+    sets (tools/gpu_adversarial.py): every discrete decision stays exact, acc p99 reaches 1e-3 on such a set; DESIGN.md §2."""
+    R = float(want["R"])
+    far = max(float(np.abs(p[c]).max()) for c in ("x", "y", "z")) > 40.0 * R
+    return bool(far or int(want["leafdepth"].max()) >= 40)
+
+
+def adversarial_set(pkg, seed, lattice=True):
+    """Small random particle set built to hit the corners of the path: points on power-of-two planes (the split planes of a cube
+    whose half-width is a power of two; lattice=False leaves them out — exact opening-test ties on lattices are a documented
+    divergence of the GPU path), tight pairs that share ~30 octree levels, a few far outliers, mixed types, unequal
+    masses, resting particles, and every `cores` branch of the insertion.  Returns (particles, (theta, e0, massInH, globalTime, cores))."""
+    rng = np.random.default_rng(1000 + seed)
+    n = int(rng.integers(1, 420))
+    L = 1e20
+    kind = rng.integers(0, 4, n)
+    if not lattice:
+        kind = np.where(kind == 1, 0, kind)
+    pos = rng.normal(0.0, 1.0, (3, n)) * L
+    grid = np.ldexp(rng.integers(-8, 9, (3, n)).astype(np.float64), -3) * 2.0 ** 66           # multiples of 2^63 up to 2^66 ~ 0.7 L
+    pos = np.where(kind == 1, grid, pos)
+    if n > 4:
+        src = rng.integers(0, n, n)
+        tight = pos[:, src] * (1.0 + 1e-9 * rng.normal(size=(3, n)))                            # pairs that share ~30 levels
+        pos = np.where(kind == 2, tight, pos)
+        far = rng.random(n) < 0.01
+        pos[:, far] *= 1e3                                                                        # beyond mean + 10 sigma or just inside it
+    # truly coincident points send the reference (and its restatement) into an unbounded recursion: keep one of each
+    _, first = np.unique(pos.T, axis=0, return_index=True)
+    dup = np.ones(n, bool); dup[first] = False
+    pos[:, dup] = rng.normal(0.0, 1.0, (3, int(dup.sum()))) * L
+    p = pkg.ics._empty(n)
+    p["x"], p["y"], p["z"] = pos[0].copy(), pos[1].copy(), pos[2].copy()
+    p["type"] = rng.choice(np.array([1, 2, 2, 3], np.uint8), n)
+    p["mass"] = 1e35 * np.exp(rng.normal(0.0, 0.5, n)) if seed % 2 else np.full(n, 1e35)
+    for c in ("vx", "vy", "vz"):
+        p[c] = rng.normal(0.0, 1e5, n)
+    p["U"] = np.where(p["type"] == 2, 1e9 * (0.5 + rng.random(n)), 0.0)
+    if seed % 3 == 0:
+        p["next_time"] = np.where(rng.random(n) < 0.3, 7.0, 0.0)
+    gas = p["type"] == 2
+    mh = float(rng.integers(2, 12)) * (p["mass"][gas].mean() if gas.any() else 1e35)
+    cores = int(rng.choice([1, 2, 8]))
+    args = (float(rng.choice([0.3, 0.5, 0.8])), 1e18, mh, 0.0, cores)
+    return p, args

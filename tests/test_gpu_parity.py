@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 
 from conftest import GOLDEN_CASES, load_golden
-from parity import assert_parity, compare
+from parity import adversarial_set, assert_parity, beyond_fp32_law, compare
 
 pytestmark = pytest.mark.gpu
 
@@ -79,6 +79,26 @@ def test_against_oracle(pkg, oracle, ctxs, case, mixed):
     assert_parity(rep)
     if not mixed:
         assert rep["acc_median"] < 1e-12 and rep["acc_p99"] < 1e-10, rep        # the FP64 path only differs by summation order
+
+
+@pytest.mark.parametrize("mixed", PRECISIONS)
+@pytest.mark.parametrize("seed", range(16))
+def test_adversarial_random_sets(pkg, oracle, ctxs, seed, mixed):
+    """The sets the restatement is pinned on against the compiled reference (tests/test_oracle_pin.py), without the lattice points
+    (exact opening-test ties on lattices are a documented divergence): tight pairs down to 45 levels (three-word keys), far
+    outliers, unequal masses, resting particles, every `cores` branch.  Every tier holds in FP64; in mixed precision every
+    discrete tier holds and acc / dU/dt are inside the tolerance except on the sets beyond_fp32_law() describes."""
+    p, (theta, e0, mh, gt, cores) = adversarial_set(pkg, seed, lattice=False)
+    if len(p["x"]) < 20:
+        pytest.skip("tiny sets have their own test")
+    ctx = ctxs(cores, mixed)
+    want = oracle.run(p, theta, e0, mh, gt, cores)
+    got = run_gpu(pkg, ctx, p, theta, e0, mh, gt)
+    rep = compare(got, want, p, ctx)
+    print(seed, "mixed" if mixed else "fp64", rep)
+    if mixed and beyond_fp32_law(p, want):
+        rep = dict(rep, acc_median=0.0, acc_p99=0.0)
+    assert_parity(rep)
 
 
 @pytest.mark.parametrize("mixed", PRECISIONS)

@@ -5,6 +5,7 @@ import numpy as np
 import pytest
 
 from conftest import GOLDEN_CASES, load_golden
+from parity import adversarial_set
 
 BITWISE = ("ax", "ay", "az", "dUdt", "h", "rho", "P", "T", "vis", "leafdepth", "key_hi", "key_lo", "visits", "acc_nodes", "acc_leaves", "sph")
 
@@ -80,36 +81,8 @@ def test_oracle_matches_reference_binary_on_adversarial_random_sets(oracle, pkg,
     every `cores` branch (bulk insertion, hand-over to one-by-one insertion below cores*100, one-by-one from the root)."""
     if not oracle.have_ref():
         pytest.skip("oracle/_ref not built here (reference sources absent)")
-    rng = np.random.default_rng(1000 + seed)
-    n = int(rng.integers(1, 420))
-    L = 1e20
-    kind = rng.integers(0, 4, n)
-    pos = rng.normal(0.0, 1.0, (3, n)) * L
-    lattice = np.ldexp(rng.integers(-8, 9, (3, n)).astype(np.float64), -3) * 2.0 ** 66        # multiples of 2^63 up to 2^66 ~ 0.7 L
-    pos = np.where(kind == 1, lattice, pos)
-    if n > 4:
-        src = rng.integers(0, n, n)
-        tight = pos[:, src] * (1.0 + 1e-9 * rng.normal(size=(3, n)))                            # pairs that share ~30 levels
-        pos = np.where(kind == 2, tight, pos)
-        far = rng.random(n) < 0.01
-        pos[:, far] *= 1e3                                                                        # beyond mean + 10 sigma or just inside it
-    # truly coincident points send the reference (and its restatement) into an unbounded recursion: keep one of each
-    _, first = np.unique(pos.T, axis=0, return_index=True)
-    dup = np.ones(n, bool); dup[first] = False
-    pos[:, dup] = rng.normal(0.0, 1.0, (3, int(dup.sum()))) * L
-    p = pkg.ics._empty(n)
-    p["x"], p["y"], p["z"] = pos[0].copy(), pos[1].copy(), pos[2].copy()
-    p["type"] = rng.choice(np.array([1, 2, 2, 3], np.uint8), n)
-    p["mass"] = 1e35 * np.exp(rng.normal(0.0, 0.5, n)) if seed % 2 else np.full(n, 1e35)
-    for c in ("vx", "vy", "vz"):
-        p[c] = rng.normal(0.0, 1e5, n)
-    p["U"] = np.where(p["type"] == 2, 1e9 * (0.5 + rng.random(n)), 0.0)
-    if seed % 3 == 0:
-        p["next_time"] = np.where(rng.random(n) < 0.3, 7.0, 0.0)
-    gas = p["type"] == 2
-    mh = float(rng.integers(2, 12)) * (p["mass"][gas].mean() if gas.any() else 1e35)
-    cores = int(rng.choice([1, 2, 8]))
-    args = (float(rng.choice([0.3, 0.5, 0.8])), 1e18, mh, 0.0, cores)
+    p, args = adversarial_set(pkg, seed)
+    n, cores = len(p["x"]), args[4]
     got = oracle.run(p, *args)
     want = oracle.run_ref(p, *args)
     assert got["R"] == want["R"]
