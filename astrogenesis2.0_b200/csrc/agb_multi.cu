@@ -193,6 +193,7 @@ const char* agb_multi_last_error(agb_multi* m) { return m ? m->err.c_str() : "";
 int agb_multi_set_option(agb_multi* m, int option, int64_t value)
 {
     if (!m) return AGB_ERR_INVALID;
+    if (option == AGB_OPT_SLICE_DENSITIES && value != 0) return AGB_ERR_INVALID;   // this handle hands back whole arrays: every device needs all densities
     for (auto* c : m->ctx) { int rc = agb_set_option(c, option, value); if (rc) return rc; }
     return AGB_OK;
 }
